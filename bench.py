@@ -1,0 +1,270 @@
+#!/usr/bin/env python
+"""bench.py -- ECDSA-P256 verifies/sec of the B200 verifier (BASELINE.json metric) and of the reference's CPU path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one pass of the hot path over one batch of B synthetic signatures per GPU (default B = 65 536, the
+BASELINE.json configs[1] workload: K = 64 keys, SHA-256 digests of 1 KiB messages, low-S DER signatures).  With N > 1
+every rank verifies its own B signatures (weak scaling) and the validity bitmask is all-gathered (NCCL) inside the
+timed region.
+
+Printed JSON (one line, rank 0):
+  value        whole-job verifies/s, inputs resident in HBM, CUDA-event time summed over K steps (max over ranks);
+  e2e          same metric through the C-ABI call fabgpu_bccsp_verify_batch with HOST buffers (raw DER signatures,
+               digests, keys): host gates + pinned staging + H2D + kernel + D2H inside the timed region;
+  roofline     HBM view of the verify kernel (algorithmic 160.125 B/verify) -- the path is integer-issue bound,
+               so `roofline_int` carries the binding resource (217 600 32-bit MACs/verify vs the fma-pipe peak);
+  cpu_baseline the oracle's C port (OpenSSL curve arithmetic + restated bccsp/sw gates) on this box's host cores.
+--impl reference times that same CPU port as the reference arm (the reference itself is Go; no Go toolchain exists).
+"""
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "ECDSA-P256 verifies/sec"
+ALG_BYTES_PER_VERIFY = 160.125          # 5 x 32 B in, 1 bit out
+ALG_MACS_PER_VERIFY = 217600            # 3 400 modular multiplications x 64 MACs
+KEYS = 64
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured", float(d.get("sm_max_mhz", 1965.0))
+    return 6650.0, "fallback", 1965.0
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) >= 8:
+                self.rows.append(f)
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = sorted(float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit())
+        reasons = []
+        for i, name in ((4, "hw_slowdown"), (5, "hw_thermal_slowdown"), (6, "sw_thermal_slowdown"), (7, "sw_power_cap")):
+            if any(r[i].lower().startswith("active") for r in self.rows):
+                reasons.append(name)
+        mx = max([float(r[2]) for r in self.rows if r[2].replace(".", "").isdigit()] or [0.0])
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": reasons, "samples": len(sm)}
+
+
+def cpu_port_rate(w, threads, min_seconds=4.0):
+    """verifies/s of the oracle's C port on `threads` host threads over the workload `w` (bounded sample)."""
+    from oracle import fast
+    fast.verify_batch(w.keys_xy, w.key_idx[:2048], w.digest[:2048], w.dig_off()[:2049], w.sigs, w.sig_off[:2049], nthreads=threads)  # warm
+    done, t0 = 0, time.perf_counter()
+    while True:
+        st = fast.verify_batch(w.keys_xy, w.key_idx, w.digest, w.dig_off(), w.sigs, w.sig_off, nthreads=threads)
+        done += w.n
+        el = time.perf_counter() - t0
+        if el >= min_seconds:
+            break
+    assert (st == 0).all()
+    return done / el, done, el
+
+
+def run_reference(args):
+    """Reference arm: the reference's own CPU path is Go crypto/ecdsa behind bccsp/sw; Go is absent from this image, so
+    the arm times the oracle's C port of it (restated gates + OpenSSL nistz256 arithmetic) on all host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from tools import workload
+    cores = os.cpu_count() or 1
+    w = workload.Workload(args.batch, KEYS, seed=workload.DEFAULT_SEED + 2)
+    from oracle import fast
+    for _ in range(args.warmup):
+        fast.verify_batch(w.keys_xy, w.key_idx, w.digest, w.dig_off(), w.sigs, w.sig_off, nthreads=cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        st = fast.verify_batch(w.keys_xy, w.key_idx, w.digest, w.dig_off(), w.sigs, w.sig_off, nthreads=cores)
+    el = time.perf_counter() - t0
+    assert (st == 0).all()
+    v = args.steps * w.n / el
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "verifies/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 limbs (256-bit modular integer)",
+        "data": "synthetic",
+        "config": {"workload": "configs[1]: %d-signature batch, %d keys, SHA-256 digests, low-S DER signatures" % (w.n, KEYS), "batch_per_step": w.n},
+        "cpu_baseline": {"value": v, "unit": "verifies/s", "cores": cores, "kind": "port",
+                         "sample": "%d steps x %d signatures through oracle/c (bccsp/sw gates + OpenSSL ECDSA_do_verify), %d threads" % (args.steps, w.n, cores)},
+        "e2e": {"value": v, "unit": "verifies/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    pkg = importlib.import_module("fabric-mod_b200")
+    sharding = importlib.import_module("fabric-mod_b200.sharding")
+    from tools import workload
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node %d for --gpus %d" % (args.gpus, args.gpus))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    B = args.batch
+    n_total = B * world
+    # this rank's slice of the synthetic workload (rank-seeded so ranks do not verify identical bytes)
+    w = workload.Workload(B, KEYS, seed=workload.DEFAULT_SEED + 2 + 1000 * rank)
+    ctx = pkg.binding.Context(max_batch=B, device_ids=[local])
+
+    # ---- device-resident leg: ROT distinct input buffers, L2 flushed between steps ---------------------------
+    ROT = 3
+    host = [w.qx(), w.qy(), w.digest, w.r, w.s]
+    bufs = []
+    for k in range(ROT):
+        perm = np.roll(np.arange(B), 997 * k)                # same tuples, different order => different bytes per buffer
+        bufs.append([torch.from_numpy(np.ascontiguousarray(a[perm])).to(dev) for a in host])
+    words = sharding.shard_words(n_total, world)
+    assert words == B // 32
+    local_mask = torch.zeros(words, dtype=torch.int32, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream(dev)
+
+    def step(k):
+        t = bufs[k % ROT]
+        ctx.verify_p256_device(t[0].data_ptr(), t[1].data_ptr(), t[2].data_ptr(), t[3].data_ptr(), t[4].data_ptr(), B,
+                               local_mask.data_ptr(), 0, stream.cuda_stream)
+        return sharding.allgather_mask(local_mask, n_total, world)
+
+    def sync_all():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    for k in range(args.warmup):
+        full = step(k)
+    sync_all()
+    assert bool((full == -1).all()), "warm-up bitmask is not all-valid"
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = ctx.launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    sync_all()
+    wall0 = time.perf_counter()
+    for k in range(args.steps):
+        flush.fill_(k & 0xFF)                                 # L2 flush (256 MiB > 126 MB L2), outside the event pair
+        ev[k][0].record(stream)
+        full = step(k)
+        ev[k][1].record(stream)
+    sync_all()
+    wall = time.perf_counter() - wall0
+    launches = ctx.launch_count() - launches0
+    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    assert bool((full == -1).all())
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- end-to-end leg: raw DER + digests + keys in host memory through the bccsp-level C-ABI call ----------
+    e2e_steps = max(3, min(args.steps, 10))
+    dig_off = w.dig_off()
+    for _ in range(2):
+        st = ctx.bccsp_verify_batch(w.keys_xy, w.key_idx, w.digest, dig_off, w.sigs, w.sig_off)
+    assert (st == 0).all()
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        st = ctx.bccsp_verify_batch(w.keys_xy, w.key_idx, w.digest, dig_off, w.sigs, w.sig_off)
+    torch.cuda.synchronize(dev)
+    e2e_s = time.perf_counter() - t0
+    assert (st == 0).all()
+
+    # ---- max over ranks ---------------------------------------------------------------------------------------
+    times = torch.tensor([dev_ms, e2e_s * 1e3, wall * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms, wall_ms = [float(x) for x in times.tolist()]
+
+    if rank == 0:
+        hbm_peak, peak_src, sm_max = _peaks()
+        value = n_total * args.steps / (dev_ms * 1e-3)
+        per_launch_s = dev_ms * 1e-3 / args.steps
+        ach_gbs = B * ALG_BYTES_PER_VERIFY / per_launch_s / 1e9
+        mac_peak = 148 * 4 * 16 * sm_max * 1e6                  # 148 SMs x 4 SMSP x 16 lanes/clk (IMAD, rt 2)
+        ach_macs = B * ALG_MACS_PER_VERIFY / per_launch_s
+        cores = os.cpu_count() or 1
+        cpu_v, cpu_done, cpu_el = cpu_port_rate(w, cores)
+        out = {
+            "metric": METRIC, "value": value, "unit": "verifies/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u32 limbs (256-bit modular integer)", "data": "synthetic",
+            "config": {"workload": "configs[1]: %d-signature batch per GPU, %d keys, SHA-256 digests of 1 KiB messages, low-S DER signatures" % (B, KEYS),
+                       "batch_per_gpu": B, "global_batch": n_total, "parallelism": "batch split x%d + NCCL all-gather of the bitmask" % world,
+                       "timing": "per-step CUDA events on the launch stream, summed; L2 flushed (256 MiB fill) between steps; %d rotating input buffers" % ROT,
+                       "wall_ms_incl_flush": wall_ms},
+            "e2e": {"value": n_total * e2e_steps / (e2e_ms * 1e-3), "unit": "verifies/s", "h2d_bytes_per_step": 160 * B, "d2h_bytes_per_step": 8 * (B // 32),
+                    "api": "fabgpu_bccsp_verify_batch (raw DER signatures + digests + keys in host memory -> status bytes)", "steps": e2e_steps},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak, "traffic": None,
+                         "peak_source": peak_src, "kernel": "ecdsa_verify_kernel",
+                         "note": "integer-issue bound, not HBM bound: see roofline_int"},
+            "roofline_int": {"bound": "int32 mac (fma pipe)", "achieved": ach_macs / 1e12, "peak": mac_peak / 1e12, "unit": "TMAC/s",
+                             "frac": ach_macs / mac_peak, "peak_source": "model: 148 SM x 64 IMAD/clk x %d MHz" % int(sm_max)},
+            "cpu_baseline": {"value": cpu_v, "unit": "verifies/s", "cores": cores, "kind": "port",
+                             "sample": "%d signatures in %.1f s through oracle/c (bccsp/sw gates + OpenSSL ECDSA_do_verify), %d threads" % (cpu_done, cpu_el, cores)},
+            "clocks": clocks,
+        }
+        print(json.dumps(out))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=65536, help="signatures per GPU per step")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

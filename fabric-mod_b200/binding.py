@@ -1,0 +1,200 @@
+"""ctypes binding of include/fabgpu_ecdsa.h (libfabgpu_ecdsa.so).  Fails loudly when the library is absent."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libfabgpu_ecdsa.so")
+SLOTS = 2
+
+OK, E_NO_DEVICE, E_CUDA, E_ARG, E_INJECTED = 0, -1, -2, -3, -4
+(ST_VALID, ST_INVALID, ST_ERR_NIL_KEY, ST_ERR_EMPTY_SIG, ST_ERR_EMPTY_DIGEST, ST_ERR_UNMARSHAL, ST_ERR_R_NOT_POSITIVE,
+ ST_ERR_S_NOT_POSITIVE, ST_ERR_HIGH_S, ST_ERR_UNSUPPORTED_KEY, ST_ERR_OFF_CURVE) = range(11)
+
+# every symbol include/fabgpu_ecdsa.h declares (tests/test_abi.py checks the header against this and the .so)
+EXPORTS = [
+    "fabgpu_init", "fabgpu_destroy", "fabgpu_last_error", "fabgpu_device_count", "fabgpu_max_batch",
+    "fabgpu_host_buffers", "fabgpu_verify_p256", "fabgpu_verify_p256_async", "fabgpu_wait", "fabgpu_verify_p256_host",
+    "fabgpu_verify_p256_device", "fabgpu_bccsp_verify_batch", "fabgpu_bccsp_verify", "fabgpu_gate_signature",
+    "fabgpu_test_fieldop", "fabgpu_test_gtable", "fabgpu_launch_count",
+]
+
+
+class FabGpuError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("fabgpu error %d: %s" % (code, msg))
+        self.code = code
+
+
+def build(extra=""):
+    """Compile the CUDA library in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    env = dict(os.environ)
+    args = ["make", "-s", "-C", os.path.join(_HERE, "csrc")]
+    if extra:
+        args.append("EXTRA=" + extra)
+    subprocess.check_call(args, env=env)
+
+
+_LIB = None
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise FabGpuError(E_NO_DEVICE, "%s is missing: run __graft_entry__.build() (there is no CPU fallback)" % LIB_PATH)
+        L = ctypes.CDLL(LIB_PATH)
+        L.fabgpu_last_error.restype = ctypes.c_char_p
+        L.fabgpu_last_error.argtypes = [ctypes.c_void_p]
+        L.fabgpu_max_batch.restype = ctypes.c_size_t
+        L.fabgpu_max_batch.argtypes = [ctypes.c_void_p]
+        L.fabgpu_launch_count.restype = ctypes.c_ulonglong
+        L.fabgpu_launch_count.argtypes = [ctypes.c_void_p]
+        L.fabgpu_test_gtable.restype = ctypes.c_long
+        L.fabgpu_destroy.argtypes = [ctypes.c_void_p]
+        L.fabgpu_destroy.restype = None
+        L.fabgpu_device_count.argtypes = [ctypes.c_void_p]
+        _LIB = L
+    return _LIB
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p) if a is not None else None
+
+
+def gate_signature(sig: bytes):
+    """fabgpu_gate_signature: host gates only (no GPU).  Returns (status, r32, s32)."""
+    r = (ctypes.c_uint8 * 32)()
+    s = (ctypes.c_uint8 * 32)()
+    buf = (ctypes.c_uint8 * max(1, len(sig))).from_buffer_copy(sig if len(sig) else b"\x00")
+    st = lib().fabgpu_gate_signature(buf, ctypes.c_size_t(len(sig)), r, s)
+    return st, bytes(r), bytes(s)
+
+
+class Context:
+    """fabgpu_ctx owner.  device_ids=None -> CUDA device 0."""
+
+    def __init__(self, max_batch=65536, device_ids=None):
+        L = lib()
+        self._h = ctypes.c_void_p()
+        if device_ids:
+            arr = (ctypes.c_int * len(device_ids))(*device_ids)
+            rc = L.fabgpu_init(arr, ctypes.c_int(len(device_ids)), ctypes.c_size_t(max_batch), ctypes.byref(self._h))
+        else:
+            rc = L.fabgpu_init(None, ctypes.c_int(0), ctypes.c_size_t(max_batch), ctypes.byref(self._h))
+        if rc != OK:
+            raise FabGpuError(rc, (L.fabgpu_last_error(None) or b"").decode())
+        self.max_batch = max_batch
+
+    def close(self):
+        if self._h:
+            lib().fabgpu_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != OK:
+            raise FabGpuError(rc, (lib().fabgpu_last_error(self._h) or b"").decode())
+
+    def last_error(self):
+        return (lib().fabgpu_last_error(self._h) or b"").decode()
+
+    def launch_count(self):
+        return int(lib().fabgpu_launch_count(self._h))
+
+    def device_count(self):
+        return int(lib().fabgpu_device_count(self._h))
+
+    # ---- leaf -------------------------------------------------------------------------------------------
+    def host_buffers(self, slot=0):
+        """numpy views (no copy) of the slot's pinned SoA buffers: dict qx,qy,e,r,s -> uint8[max_batch,32]; mask, offcurve."""
+        ptrs = [ctypes.POINTER(ctypes.c_uint8)() for _ in range(5)]
+        mask = ctypes.POINTER(ctypes.c_uint32)()
+        off = ctypes.POINTER(ctypes.c_uint32)()
+        self._ck(lib().fabgpu_host_buffers(self._h, ctypes.c_int(slot), *[ctypes.byref(p) for p in ptrs], ctypes.byref(mask), ctypes.byref(off)))
+        out = {}
+        for name, p in zip(("qx", "qy", "e", "r", "s"), ptrs):
+            out[name] = np.ctypeslib.as_array(p, shape=(self.max_batch, 32))
+        words = (self.max_batch + 31) // 32
+        out["mask"] = np.ctypeslib.as_array(mask, shape=(words,))
+        out["offcurve"] = np.ctypeslib.as_array(off, shape=(words,))
+        return out
+
+    def verify_p256(self, slot, n):
+        self._ck(lib().fabgpu_verify_p256(self._h, ctypes.c_int(slot), ctypes.c_size_t(n)))
+
+    def verify_p256_async(self, slot, n):
+        self._ck(lib().fabgpu_verify_p256_async(self._h, ctypes.c_int(slot), ctypes.c_size_t(n)))
+
+    def wait(self, slot):
+        self._ck(lib().fabgpu_wait(self._h, ctypes.c_int(slot)))
+
+    def verify_p256_host(self, qx, qy, e, r, s):
+        """SoA uint8[n,32] arrays in ordinary host memory -> (mask uint32[ceil(n/32)], offcurve uint32[...])."""
+        arrs = [np.ascontiguousarray(a, dtype=np.uint8).reshape(-1, 32) for a in (qx, qy, e, r, s)]
+        n = arrs[0].shape[0]
+        assert all(a.shape[0] == n for a in arrs)
+        words = (n + 31) // 32
+        mask = np.zeros(max(words, 1), np.uint32)
+        off = np.zeros(max(words, 1), np.uint32)
+        self._ck(lib().fabgpu_verify_p256_host(self._h, *[_p(a) for a in arrs], ctypes.c_size_t(n), _p(mask), _p(off)))
+        return mask[:words], off[:words]
+
+    def verify_p256_device(self, d_qx, d_qy, d_e, d_r, d_s, n, d_mask, d_off=0, stream=0, dev_index=0):
+        """Raw device pointers (ints).  Enqueues on `stream` (a cudaStream_t as int) and returns immediately."""
+        self._ck(lib().fabgpu_verify_p256_device(self._h, ctypes.c_int(dev_index), ctypes.c_void_p(d_qx), ctypes.c_void_p(d_qy),
+                                                 ctypes.c_void_p(d_e), ctypes.c_void_p(d_r), ctypes.c_void_p(d_s), ctypes.c_size_t(n),
+                                                 ctypes.c_void_p(d_mask), ctypes.c_void_p(d_off), ctypes.c_void_p(stream)))
+
+    # ---- bccsp level ------------------------------------------------------------------------------------
+    def bccsp_verify_batch(self, keys_xy, key_idx, digests, dig_off, sigs, sig_off):
+        keys_xy = np.ascontiguousarray(keys_xy, dtype=np.uint8).reshape(-1, 64)
+        key_idx = np.ascontiguousarray(key_idx, dtype=np.int32)
+        digests = np.ascontiguousarray(digests, dtype=np.uint8).reshape(-1)
+        sigs = np.ascontiguousarray(sigs, dtype=np.uint8).reshape(-1)
+        dig_off = np.ascontiguousarray(dig_off, dtype=np.uint32)
+        sig_off = np.ascontiguousarray(sig_off, dtype=np.uint32)
+        n = key_idx.shape[0]
+        status = np.full(max(n, 1), 255, np.uint8)
+        if digests.size == 0:
+            digests = np.zeros(1, np.uint8)
+        if sigs.size == 0:
+            sigs = np.zeros(1, np.uint8)
+        self._ck(lib().fabgpu_bccsp_verify_batch(self._h, _p(keys_xy), ctypes.c_int(keys_xy.shape[0]), _p(key_idx), _p(digests), _p(dig_off),
+                                                 _p(sigs), _p(sig_off), ctypes.c_size_t(n), _p(status)))
+        return status[:n]
+
+    def bccsp_verify(self, key_xy, sig, digest):
+        """One sw.CSP.Verify call -> (valid: bool, err: str|None) with the reference's error strings."""
+        valid = ctypes.c_int(0)
+        err = ctypes.create_string_buffer(1024)
+        kb = (ctypes.c_uint8 * 64).from_buffer_copy(key_xy) if key_xy is not None else None
+        sb = (ctypes.c_uint8 * max(1, len(sig or b""))).from_buffer_copy(sig if sig else b"\x00")
+        db = (ctypes.c_uint8 * max(1, len(digest or b""))).from_buffer_copy(digest if digest else b"\x00")
+        self._ck(lib().fabgpu_bccsp_verify(self._h, kb, sb, ctypes.c_size_t(len(sig or b"")), db, ctypes.c_size_t(len(digest or b"")),
+                                           ctypes.byref(valid), err, ctypes.c_size_t(1024)))
+        e = err.value.decode()
+        return bool(valid.value), (e if e else None)
+
+    # ---- test hooks -------------------------------------------------------------------------------------
+    def test_fieldop(self, op, a, b):
+        a = np.ascontiguousarray(a, dtype=np.uint8).reshape(-1, 32)
+        b = np.ascontiguousarray(b, dtype=np.uint8).reshape(-1, 32)
+        out = np.zeros_like(a)
+        self._ck(lib().fabgpu_test_fieldop(self._h, ctypes.c_int(op), _p(a), _p(b), ctypes.c_size_t(a.shape[0]), _p(out)))
+        return out
+
+    def test_gtable(self):
+        size = lib().fabgpu_test_gtable(self._h, None, ctypes.c_size_t(0))
+        out = np.zeros(size, np.uint8)
+        got = lib().fabgpu_test_gtable(self._h, _p(out), ctypes.c_size_t(size))
+        if got != size:
+            raise FabGpuError(int(got), self.last_error())
+        return out

@@ -1,0 +1,75 @@
+// CUDA kernels for the batch verifier (sm_100a).  See ecdsa_verify.cuh for the per-signature algorithm.
+#pragma once
+#include <cuda_runtime.h>
+#include "ecdsa_verify.cuh"
+
+namespace fabgpu {
+
+#ifndef FAB_VERIFY_THREADS
+#define FAB_VERIFY_THREADS 128
+#endif
+
+// 32 big-endian bytes at a 16-byte aligned address -> limbs, as two 128-bit loads + byte permutes
+__device__ __forceinline__ u256 load_be32(const uint8_t* p)
+{
+    const uint4 hi = __ldg(reinterpret_cast<const uint4*>(p));        // bytes 0..15  (most significant)
+    const uint4 lo = __ldg(reinterpret_cast<const uint4*>(p) + 1);    // bytes 16..31
+    u256 r;
+    r.v[7] = __byte_perm(hi.x, 0, 0x0123); r.v[6] = __byte_perm(hi.y, 0, 0x0123);
+    r.v[5] = __byte_perm(hi.z, 0, 0x0123); r.v[4] = __byte_perm(hi.w, 0, 0x0123);
+    r.v[3] = __byte_perm(lo.x, 0, 0x0123); r.v[2] = __byte_perm(lo.y, 0, 0x0123);
+    r.v[1] = __byte_perm(lo.z, 0, 0x0123); r.v[0] = __byte_perm(lo.w, 0, 0x0123);
+    return r;
+}
+
+// Builds the fixed-base table: one thread per (window, digit).
+__global__ void build_g_table_kernel(aff* gtab)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int total = FAB_G_WINDOWS * FAB_G_ENTRIES;
+    if (idx >= total) return;
+    const int j = idx / FAB_G_ENTRIES;
+    const uint32_t d = (uint32_t)(idx % FAB_G_ENTRIES) + 1u;
+    gtab[idx] = g_table_entry(j, d);
+}
+
+// One signature per thread.  SoA inputs: n x 32 big-endian bytes each.  Output: bit i%32 of word i/32 is 1 iff
+// signature i is VALID; offcurve (optional) flags public keys that are not curve points.
+__global__ void __launch_bounds__(FAB_VERIFY_THREADS)
+ecdsa_verify_kernel(const uint8_t* __restrict__ qx, const uint8_t* __restrict__ qy, const uint8_t* __restrict__ e,
+                    const uint8_t* __restrict__ r, const uint8_t* __restrict__ s, uint32_t n,
+                    const aff* __restrict__ gtab, uint32_t* __restrict__ mask, uint32_t* __restrict__ offcurve)
+{
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t res = V_INVALID;
+    if (idx < n) {
+        const size_t o = (size_t)idx * 32;
+        res = ecdsa_verify_one(load_be32(qx + o), load_be32(qy + o), load_be32(e + o), load_be32(r + o), load_be32(s + o), gtab);
+    }
+    const uint32_t vmask = __ballot_sync(0xffffffffu, res == V_VALID);
+    const uint32_t omask = __ballot_sync(0xffffffffu, res == V_OFFCURVE);
+    if ((threadIdx.x & 31u) == 0 && idx < n) {
+        mask[idx >> 5] = vmask;
+        if (offcurve) offcurve[idx >> 5] = omask;
+    }
+}
+
+// Unit-test hook: out[i] = op(a[i], b[i]) on the device primitives (tests/test_gpu_field.py).
+__global__ void fieldop_kernel(int op, const uint8_t* a, const uint8_t* b, int n, uint8_t* out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const u256 x = load_be32(a + 32 * (size_t)i), y = load_be32(b + 32 * (size_t)i);
+    u256 z;
+    switch (op) {
+        case 0: z = fe_mul(x, y); break;
+        case 1: z = fe_add(x, y); break;
+        case 2: z = fe_sub(x, y); break;
+        case 3: z = sc_mul(x, y); break;
+        case 4: z = fe_inv(x); break;
+        default: z = sc_inv_to_mont(x); break;
+    }
+    u256_to_be(z, out + 32 * (size_t)i);
+}
+
+}  // namespace fabgpu

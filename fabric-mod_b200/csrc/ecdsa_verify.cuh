@@ -1,0 +1,139 @@
+// One ECDSA-P256 verification, written once for device (the product) and host (tests/host_sim).
+//
+// Restates, for the GPU, what the reference reaches at bccsp/sw/ecdsa.go:56 -- Go 1.14 crypto/ecdsa.Verify:
+//   r,s in [1,n-1]  ->  w = s^-1 mod n  ->  u1 = e*w, u2 = r*w  ->  R = u1*G + u2*Q  ->  R != inf and R.x mod n == r.
+// The DER parse, positivity and low-S gates (bccsp/utils/ecdsa.go:43-92, bccsp/sw/ecdsa.go:42-54) run on the host
+// before the batch is packed (see bccsp_host.cpp); the kernel still enforces the range checks itself.
+//
+// Scalar multiplication layout (B200-first, not Go's CombinedMult):
+//   u1*G : fixed-base, FAB_WG-bit unsigned windows over a precomputed affine table that lives in L2
+//          (256/FAB_WG mixed additions, no doublings);
+//   u2*Q : signed 5-bit Booth windows (52 of them), 16-entry Jacobian table of 1Q..16Q per signature.
+// The final comparison avoids the field inversion: R.x == r' * R.Z^2 for r' in {r, r+n (if < p)}.
+#pragma once
+#include "p256_point.cuh"
+
+#ifndef FAB_WG
+#define FAB_WG 8                      // window bits of the fixed-base table
+#endif
+#define FAB_G_WINDOWS ((256 + FAB_WG - 1) / FAB_WG)
+#define FAB_G_ENTRIES ((1 << FAB_WG) - 1)
+
+namespace fabgpu {
+
+enum : uint32_t { V_INVALID = 0u, V_VALID = 1u, V_OFFCURVE = 2u };
+
+// 6-bit Booth window -> (negative?, |digit| in 0..16)
+FAB_HD void booth5(uint32_t w6, uint32_t& neg, uint32_t& mag)
+{
+    neg = w6 >> 5;
+    const uint32_t d = neg ? (63u - w6) : w6;
+    mag = (d >> 1) + (d & 1u);
+}
+
+// out = (k+1)*Q for k = 0..15 (Jacobian)
+FAB_HD void build_q_table(jac* tab, const aff& q)
+{
+    tab[0] = jac_from_aff(q);
+    tab[1] = jac_double(tab[0]);
+    for (int k = 2; k < 16; k++) tab[k] = jac_add_aff(tab[k - 1], q);
+}
+
+// u2 * Q by signed 5-bit windows.  k9 holds u2 << 28 in 9 limbs so that the current 6-bit Booth window
+// (bits 5i+4 .. 5i-1 of u2) is always the top 6 bits; it is shifted left by 5 per window (no dynamic limb index).
+FAB_HD jac scalar_mul_var(const u256& k, const jac* tab)
+{
+    uint32_t k9[9];
+    k9[0] = k.v[0] << 28;
+#pragma unroll
+    for (int i = 1; i < 8; i++) k9[i] = (k.v[i] << 28) | (k.v[i - 1] >> 4);
+    k9[8] = k.v[7] >> 4;
+    jac r = jac_infinity();
+    for (int i = 51; i >= 0; i--) {
+        if (i != 51) {
+            for (int d = 0; d < 5; d++) r = jac_double(r);
+        }
+        uint32_t neg, mag;
+        booth5(k9[8] >> 26, neg, mag);
+#pragma unroll
+        for (int j = 8; j > 0; j--) k9[j] = (k9[j] << 5) | (k9[j - 1] >> 27);
+        k9[0] <<= 5;
+        if (mag) {
+            jac t = tab[mag - 1];
+            if (neg) t.Y = fe_neg(t.Y);
+            r = jac_add(r, t);
+        }
+    }
+    return r;
+}
+
+// r += u1 * G using the fixed-base table gtab[window][digit-1] (affine, Montgomery form)
+FAB_HD jac add_fixed_base(jac r, const u256& k, const aff* gtab)
+{
+    uint32_t kk[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) kk[i] = k.v[i];
+    for (int j = 0; j < FAB_G_WINDOWS; j++) {
+        const uint32_t d = kk[0] & (uint32_t)FAB_G_ENTRIES;
+#pragma unroll
+        for (int i = 0; i < 7; i++) kk[i] = (kk[i] >> FAB_WG) | (kk[i + 1] << (32 - FAB_WG));
+        kk[7] >>= FAB_WG;
+        if (d) r = jac_add_aff(r, gtab[(size_t)j * FAB_G_ENTRIES + (d - 1)]);
+    }
+    return r;
+}
+
+// All five inputs are plain 256-bit integers (e already formed by hashToInt: leftmost 32 digest bytes, left-padded).
+FAB_HD uint32_t ecdsa_verify_one(const u256& qx, const u256& qy, const u256& e, const u256& r, const u256& s, const aff* gtab)
+{
+    const u256 n = sc_n();
+    const u256 p = fe_p();
+    // Go: r.Sign() <= 0 || s.Sign() <= 0 -> false ; r >= N || s >= N -> false
+    if (u256_is_zero(r) || u256_is_zero(s) || !u256_lt(r, n) || !u256_lt(s, n)) return V_INVALID;
+    // Q must be a curve point: Go's Verify does not check, so off-curve keys are outside the restated domain
+    // and are reported separately (the host routes them to the CPU provider).
+    if (!u256_lt(qx, p) || !u256_lt(qy, p)) return V_OFFCURVE;
+    aff q; q.x = fe_to_mont(qx); q.y = fe_to_mont(qy);
+    if (!aff_on_curve(q)) return V_OFFCURVE;
+
+    const u256 w = sc_inv_to_mont(s);                 // s^-1 * 2^256 mod n
+    const u256 u1 = sc_mul(sc_reduce_once(e), w);     // e*w mod n, plain
+    const u256 u2 = sc_mul(r, w);                     // r*w mod n, plain
+
+    jac tab[16];
+    build_q_table(tab, q);
+    jac acc = scalar_mul_var(u2, tab);
+    acc = add_fixed_base(acc, u1, gtab);
+    if (jac_is_infinity(acc)) return V_INVALID;       // Go: x == 0 && y == 0 -> false
+
+    const u256 z2 = fe_sqr(acc.Z);
+    if (u256_eq(fe_mul(fe_to_mont(r), z2), acc.X)) return V_VALID;
+    if (u256_lt(r, p_minus_n())) {                    // x mod n == r also when x = r + n < p
+        u256 rn; uint32_t c = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const uint32_t a = r.v[i], b = n.v[i];
+            const uint32_t t = a + b; const uint32_t c1 = t < a;
+            const uint32_t t2 = t + c; const uint32_t c2 = t2 < t;
+            rn.v[i] = t2; c = c1 | c2;
+        }
+        if (u256_eq(fe_mul(fe_to_mont(rn), z2), acc.X)) return V_VALID;
+    }
+    return V_INVALID;
+}
+
+// Fixed-base table entry (window j, digit d in 1..FAB_G_ENTRIES) = d * 2^(FAB_WG*j) * G, affine Montgomery.
+FAB_HD aff g_table_entry(int j, uint32_t d)
+{
+    aff g; g.x = fe_gx_mont(); g.y = fe_gy_mont();
+    jac acc = jac_infinity();
+    // scalar = d << (FAB_WG*j): MSB-first double-and-add over d's bits, then FAB_WG*j doublings
+    for (int b = FAB_WG - 1; b >= 0; b--) {
+        acc = jac_double(acc);
+        if ((d >> b) & 1u) acc = jac_add_aff(acc, g);
+    }
+    for (int t = 0; t < FAB_WG * j; t++) acc = jac_double(acc);
+    return jac_to_aff(acc);
+}
+
+}  // namespace fabgpu

@@ -1,0 +1,406 @@
+// C-ABI shim of libfabgpu_ecdsa.so (declared in include/fabgpu_ecdsa.h): context, pinned SoA slots, multi-device
+// batch split, kernel launches.  No CPU verification fallback lives here by design: a failure is reported to the
+// caller, who falls back to the reference's software provider.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/fabgpu_ecdsa.h"
+#include "bccsp_host.hpp"
+#include "ecdsa_kernels.cuh"
+
+using namespace fabgpu;
+
+namespace {
+
+std::string g_init_error = "";
+
+struct DevSlot {
+    cudaStream_t stream = nullptr;
+    uint8_t* d_in[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // qx qy e r s
+    uint32_t* d_mask = nullptr;
+    uint32_t* d_off = nullptr;
+};
+
+struct Device {
+    int id = 0;
+    aff* gtab = nullptr;
+    DevSlot slot[FABGPU_SLOTS];
+};
+
+struct HostSlot {
+    uint8_t* h_in[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    uint32_t* h_mask = nullptr;
+    uint32_t* h_off = nullptr;
+};
+
+}  // namespace
+
+struct fabgpu_ctx {
+    std::vector<Device> devs;
+    HostSlot hslot[FABGPU_SLOTS];
+    size_t max_batch = 0;      // per slot, whole context
+    size_t dev_cap = 0;        // per device per slot (multiple of 32)
+    std::string last_error;
+    std::mutex mu;         // guards enqueue/wait
+    std::mutex slot0_mu;   // serialises the composite calls that stage through slot 0's pinned buffers
+    std::atomic<unsigned long long> launches{0};
+};
+
+namespace {
+
+#define CK(ctx, call)                                                                                       \
+    do {                                                                                                    \
+        cudaError_t e_ = (call);                                                                            \
+        if (e_ != cudaSuccess) {                                                                            \
+            char buf_[512];                                                                                 \
+            snprintf(buf_, sizeof buf_, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            if (ctx) (ctx)->last_error = buf_; else g_init_error = buf_;                                    \
+            return FABGPU_E_CUDA;                                                                           \
+        }                                                                                                   \
+    } while (0)
+
+bool fault_injected()
+{
+    const char* v = getenv("FABGPU_FAULT_INJECT");
+    return v && v[0] == '1';
+}
+
+size_t round_up32(size_t x) { return (x + 31) / 32 * 32; }
+
+int launch_verify(fabgpu_ctx* ctx, const uint8_t* qx, const uint8_t* qy, const uint8_t* e, const uint8_t* r,
+                  const uint8_t* s, size_t n, const aff* gtab, uint32_t* mask, uint32_t* off, cudaStream_t st)
+{
+    if (n == 0) return FABGPU_OK;
+    const unsigned blocks = (unsigned)((n + FAB_VERIFY_THREADS - 1) / FAB_VERIFY_THREADS);
+    ecdsa_verify_kernel<<<blocks, FAB_VERIFY_THREADS, 0, st>>>(qx, qy, e, r, s, (uint32_t)n, gtab, mask, off);
+    ctx->launches++;
+    CK(ctx, cudaGetLastError());
+    return FABGPU_OK;
+}
+
+int enqueue_slot(fabgpu_ctx* ctx, int slot, size_t n)
+{
+    // contiguous 32-aligned ranges per device
+    const size_t ndev = ctx->devs.size();
+    const size_t per = round_up32((n + ndev - 1) / ndev);
+    for (size_t d = 0; d < ndev; d++) {
+        const size_t begin = std::min(n, d * per), end = std::min(n, (d + 1) * per);
+        const size_t cnt = end - begin;
+        if (cnt == 0) continue;
+        Device& dv = ctx->devs[d];
+        DevSlot& ds = dv.slot[slot];
+        HostSlot& hs = ctx->hslot[slot];
+        CK(ctx, cudaSetDevice(dv.id));
+        for (int a = 0; a < 5; a++)
+            CK(ctx, cudaMemcpyAsync(ds.d_in[a], hs.h_in[a] + 32 * begin, 32 * cnt, cudaMemcpyHostToDevice, ds.stream));
+        int rc = launch_verify(ctx, ds.d_in[0], ds.d_in[1], ds.d_in[2], ds.d_in[3], ds.d_in[4], cnt, dv.gtab, ds.d_mask, ds.d_off, ds.stream);
+        if (rc) return rc;
+        const size_t words = (cnt + 31) / 32;
+        CK(ctx, cudaMemcpyAsync(hs.h_mask + begin / 32, ds.d_mask, 4 * words, cudaMemcpyDeviceToHost, ds.stream));
+        CK(ctx, cudaMemcpyAsync(hs.h_off + begin / 32, ds.d_off, 4 * words, cudaMemcpyDeviceToHost, ds.stream));
+    }
+    return FABGPU_OK;
+}
+
+int wait_slot(fabgpu_ctx* ctx, int slot)
+{
+    for (auto& dv : ctx->devs) {
+        CK(ctx, cudaSetDevice(dv.id));
+        CK(ctx, cudaStreamSynchronize(dv.slot[slot].stream));
+    }
+    return FABGPU_OK;
+}
+
+void free_all(fabgpu_ctx* ctx)
+{
+    for (auto& dv : ctx->devs) {
+        cudaSetDevice(dv.id);
+        if (dv.gtab) cudaFree(dv.gtab);
+        for (auto& ds : dv.slot) {
+            for (auto& p : ds.d_in) if (p) cudaFree(p);
+            if (ds.d_mask) cudaFree(ds.d_mask);
+            if (ds.d_off) cudaFree(ds.d_off);
+            if (ds.stream) cudaStreamDestroy(ds.stream);
+        }
+    }
+    for (auto& hs : ctx->hslot) {
+        for (auto& p : hs.h_in) if (p) cudaFreeHost(p);
+        if (hs.h_mask) cudaFreeHost(hs.h_mask);
+        if (hs.h_off) cudaFreeHost(hs.h_off);
+    }
+}
+
+int init_impl(fabgpu_ctx* ctx, const int* device_ids, int n_dev, size_t max_batch)
+{
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        ctx->last_error = std::string("no usable CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
+                          " (libfabgpu_ecdsa has no CPU fallback; use the software provider)";
+        return FABGPU_E_NO_DEVICE;
+    }
+    std::vector<int> ids;
+    if (device_ids == nullptr || n_dev <= 0) ids.push_back(0);
+    else ids.assign(device_ids, device_ids + n_dev);
+    for (int id : ids)
+        if (id < 0 || id >= count) { ctx->last_error = "device id out of range"; return FABGPU_E_NO_DEVICE; }
+    if (max_batch == 0) { ctx->last_error = "max_batch must be > 0"; return FABGPU_E_ARG; }
+    ctx->max_batch = max_batch;
+    ctx->dev_cap = round_up32((max_batch + ids.size() - 1) / ids.size());
+    ctx->devs.resize(ids.size());
+    const size_t words = ctx->dev_cap / 32;
+    const size_t tab_entries = (size_t)FAB_G_WINDOWS * FAB_G_ENTRIES;
+    for (size_t d = 0; d < ids.size(); d++) {
+        Device& dv = ctx->devs[d];
+        dv.id = ids[d];
+        CK(ctx, cudaSetDevice(dv.id));
+        CK(ctx, cudaMalloc(&dv.gtab, tab_entries * sizeof(aff)));
+        for (auto& ds : dv.slot) {
+            CK(ctx, cudaStreamCreateWithFlags(&ds.stream, cudaStreamNonBlocking));
+            for (auto& p : ds.d_in) CK(ctx, cudaMalloc(&p, 32 * ctx->dev_cap));
+            CK(ctx, cudaMalloc(&ds.d_mask, 4 * words));
+            CK(ctx, cudaMalloc(&ds.d_off, 4 * words));
+        }
+        build_g_table_kernel<<<(unsigned)((tab_entries + 63) / 64), 64, 0, dv.slot[0].stream>>>(dv.gtab);
+        ctx->launches++;
+        CK(ctx, cudaGetLastError());
+    }
+    const size_t hwords = (round_up32(max_batch) / 32) + ids.size();
+    for (auto& hs : ctx->hslot) {
+        for (auto& p : hs.h_in) CK(ctx, cudaHostAlloc(&p, 32 * round_up32(max_batch), cudaHostAllocPortable));
+        CK(ctx, cudaHostAlloc(&hs.h_mask, 4 * hwords, cudaHostAllocPortable));
+        CK(ctx, cudaHostAlloc(&hs.h_off, 4 * hwords, cudaHostAllocPortable));
+    }
+    for (auto& dv : ctx->devs) {
+        CK(ctx, cudaSetDevice(dv.id));
+        CK(ctx, cudaStreamSynchronize(dv.slot[0].stream));
+    }
+    return FABGPU_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int fabgpu_init(const int* device_ids, int n_dev, size_t max_batch, fabgpu_ctx** out)
+{
+    if (!out) return FABGPU_E_ARG;
+    *out = nullptr;
+    fabgpu_ctx* ctx = new fabgpu_ctx();
+    int rc = init_impl(ctx, device_ids, n_dev, max_batch);
+    if (rc != FABGPU_OK) {
+        g_init_error = ctx->last_error;
+        free_all(ctx);
+        delete ctx;
+        return rc;
+    }
+    *out = ctx;
+    return FABGPU_OK;
+}
+
+void fabgpu_destroy(fabgpu_ctx* ctx)
+{
+    if (!ctx) return;
+    for (int s = 0; s < FABGPU_SLOTS; s++) wait_slot(ctx, s);
+    free_all(ctx);
+    delete ctx;
+}
+
+const char* fabgpu_last_error(const fabgpu_ctx* ctx) { return ctx ? ctx->last_error.c_str() : g_init_error.c_str(); }
+int fabgpu_device_count(const fabgpu_ctx* ctx) { return ctx ? (int)ctx->devs.size() : 0; }
+size_t fabgpu_max_batch(const fabgpu_ctx* ctx) { return ctx ? ctx->max_batch : 0; }
+unsigned long long fabgpu_launch_count(const fabgpu_ctx* ctx) { return ctx ? ctx->launches.load() : 0ull; }
+
+int fabgpu_host_buffers(fabgpu_ctx* ctx, int slot, uint8_t** qx, uint8_t** qy, uint8_t** e, uint8_t** r, uint8_t** s,
+                        uint32_t** mask, uint32_t** offcurve)
+{
+    if (!ctx || slot < 0 || slot >= FABGPU_SLOTS) return FABGPU_E_ARG;
+    HostSlot& hs = ctx->hslot[slot];
+    if (qx) *qx = hs.h_in[0];
+    if (qy) *qy = hs.h_in[1];
+    if (e) *e = hs.h_in[2];
+    if (r) *r = hs.h_in[3];
+    if (s) *s = hs.h_in[4];
+    if (mask) *mask = hs.h_mask;
+    if (offcurve) *offcurve = hs.h_off;
+    return FABGPU_OK;
+}
+
+int fabgpu_verify_p256_async(fabgpu_ctx* ctx, int slot, size_t n)
+{
+    if (!ctx || slot < 0 || slot >= FABGPU_SLOTS) return FABGPU_E_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (n > ctx->max_batch) { ctx->last_error = "n exceeds max_batch"; return FABGPU_E_ARG; }
+    if (fault_injected()) { ctx->last_error = "fault injected (FABGPU_FAULT_INJECT=1)"; return FABGPU_E_INJECTED; }
+    return enqueue_slot(ctx, slot, n);
+}
+
+int fabgpu_wait(fabgpu_ctx* ctx, int slot)
+{
+    if (!ctx || slot < 0 || slot >= FABGPU_SLOTS) return FABGPU_E_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    return wait_slot(ctx, slot);
+}
+
+int fabgpu_verify_p256(fabgpu_ctx* ctx, int slot, size_t n)
+{
+    int rc = fabgpu_verify_p256_async(ctx, slot, n);
+    if (rc) return rc;
+    return fabgpu_wait(ctx, slot);
+}
+
+int fabgpu_verify_p256_host(fabgpu_ctx* ctx, const uint8_t* qx, const uint8_t* qy, const uint8_t* e, const uint8_t* r,
+                            const uint8_t* s, size_t n, uint32_t* mask, uint32_t* offcurve)
+{
+    if (!ctx || (n && (!qx || !qy || !e || !r || !s || !mask))) return FABGPU_E_ARG;
+    if (n > ctx->max_batch) { ctx->last_error = "n exceeds max_batch"; return FABGPU_E_ARG; }
+    std::lock_guard<std::mutex> lk0(ctx->slot0_mu);
+    HostSlot& hs = ctx->hslot[0];
+    const uint8_t* src[5] = {qx, qy, e, r, s};
+    for (int a = 0; a < 5; a++) memcpy(hs.h_in[a], src[a], 32 * n);
+    int rc = fabgpu_verify_p256(ctx, 0, n);
+    if (rc) return rc;
+    const size_t words = (n + 31) / 32;
+    memcpy(mask, hs.h_mask, 4 * words);
+    if (offcurve) memcpy(offcurve, hs.h_off, 4 * words);
+    return FABGPU_OK;
+}
+
+int fabgpu_verify_p256_device(fabgpu_ctx* ctx, int dev_index, const void* d_qx, const void* d_qy, const void* d_e,
+                              const void* d_r, const void* d_s, size_t n, void* d_mask, void* d_offcurve, void* cuda_stream)
+{
+    if (!ctx || dev_index < 0 || dev_index >= (int)ctx->devs.size()) return FABGPU_E_ARG;
+    if (n && (!d_qx || !d_qy || !d_e || !d_r || !d_s || !d_mask)) return FABGPU_E_ARG;
+    if (fault_injected()) { ctx->last_error = "fault injected (FABGPU_FAULT_INJECT=1)"; return FABGPU_E_INJECTED; }
+    Device& dv = ctx->devs[dev_index];
+    CK(ctx, cudaSetDevice(dv.id));
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : dv.slot[0].stream;
+    return launch_verify(ctx, (const uint8_t*)d_qx, (const uint8_t*)d_qy, (const uint8_t*)d_e, (const uint8_t*)d_r,
+                         (const uint8_t*)d_s, n, dv.gtab, (uint32_t*)d_mask, (uint32_t*)d_offcurve, st);
+}
+
+int fabgpu_gate_signature(const uint8_t* sig, size_t sig_len, uint8_t r_out[32], uint8_t s_out[32])
+{
+    host::Gate g;
+    host::gate_signature(sig, sig_len, g, false);
+    if (g.status == FABGPU_ST_VALID) { memcpy(r_out, g.r, 32); memcpy(s_out, g.s, 32); }
+    return g.status;
+}
+
+int fabgpu_bccsp_verify_batch(fabgpu_ctx* ctx, const uint8_t* keys_xy, int K, const int32_t* key_idx, const uint8_t* digests,
+                              const uint32_t* dig_off, const uint8_t* sigs, const uint32_t* sig_off, size_t n, uint8_t* status)
+{
+    if (!ctx || (n && (!key_idx || !dig_off || !sig_off || !status))) return FABGPU_E_ARG;
+    // Chunks of at most max_batch survivors go through slot 0; gates run on the calling thread.
+    std::lock_guard<std::mutex> lk0(ctx->slot0_mu);
+    HostSlot& hs = ctx->hslot[0];
+    std::vector<uint32_t> where;   // original index of each packed survivor
+    where.reserve(std::min(n, ctx->max_batch));
+    size_t i = 0;
+    while (i < n || !where.empty()) {
+        while (i < n && where.size() < ctx->max_batch) {
+            const int32_t ki = key_idx[i];
+            const size_t sl = sig_off[i + 1] - sig_off[i], dl = dig_off[i + 1] - dig_off[i];
+            uint8_t st;
+            if (ki < 0) st = FABGPU_ST_ERR_NIL_KEY;                    // bccsp/sw/impl.go:249-251
+            else if (sl == 0) st = FABGPU_ST_ERR_EMPTY_SIG;            // :252-254
+            else if (dl == 0) st = FABGPU_ST_ERR_EMPTY_DIGEST;         // :255-257
+            else if (ki >= K || !keys_xy) st = FABGPU_ST_ERR_UNSUPPORTED_KEY;
+            else {
+                host::Gate g;
+                host::gate_signature(sigs + sig_off[i], sl, g, false);
+                st = (uint8_t)g.status;
+                if (g.status == FABGPU_ST_VALID) {
+                    const size_t k = where.size();
+                    memcpy(hs.h_in[0] + 32 * k, keys_xy + 64 * (size_t)ki, 32);
+                    memcpy(hs.h_in[1] + 32 * k, keys_xy + 64 * (size_t)ki + 32, 32);
+                    host::hash_to_e(digests + dig_off[i], dl, hs.h_in[2] + 32 * k);
+                    memcpy(hs.h_in[3] + 32 * k, g.r, 32);
+                    memcpy(hs.h_in[4] + 32 * k, g.s, 32);
+                    where.push_back((uint32_t)i);
+                }
+            }
+            status[i] = st;
+            i++;
+        }
+        if (!where.empty()) {
+            int rc = fabgpu_verify_p256(ctx, 0, where.size());
+            if (rc) return rc;
+            for (size_t k = 0; k < where.size(); k++) {
+                const bool ok = (hs.h_mask[k >> 5] >> (k & 31)) & 1u;
+                const bool oc = (hs.h_off[k >> 5] >> (k & 31)) & 1u;
+                status[where[k]] = ok ? FABGPU_ST_VALID : (oc ? FABGPU_ST_ERR_OFF_CURVE : FABGPU_ST_INVALID);
+            }
+            where.clear();
+        }
+    }
+    return FABGPU_OK;
+}
+
+int fabgpu_bccsp_verify(fabgpu_ctx* ctx, const uint8_t* key_xy, const uint8_t* sig, size_t sig_len, const uint8_t* digest,
+                        size_t digest_len, int* valid, char* err, size_t errcap)
+{
+    if (!ctx || !valid) return FABGPU_E_ARG;
+    *valid = 0;
+    std::string msg;
+    auto finish = [&](const std::string& m) {
+        if (err && errcap) { size_t k = std::min(errcap - 1, m.size()); memcpy(err, m.data(), k); err[k] = 0; }
+        return FABGPU_OK;
+    };
+    // sw.CSP.Verify argument gates, reference bccsp/sw/impl.go:249-257
+    if (!key_xy) return finish("Invalid Key. It must not be nil.");
+    if (!sig || sig_len == 0) return finish("Invalid signature. Cannot be empty.");
+    if (!digest || digest_len == 0) return finish("Invalid digest. Cannot be empty.");
+    host::Gate g;
+    host::gate_signature(sig, sig_len, g, true);
+    if (g.status != FABGPU_ST_VALID && g.status != FABGPU_ST_INVALID)
+        return finish("Failed verifing with opts [<nil>]: " + g.err);          // errors.Wrapf at impl.go:266
+    if (g.status == FABGPU_ST_INVALID) return finish("");                       // r >= 2^256: (false, nil)
+    uint8_t e[32];
+    host::hash_to_e(digest, digest_len, e);
+    uint32_t mask = 0, off = 0;
+    int rc = fabgpu_verify_p256_host(ctx, key_xy, key_xy + 32, e, g.r, g.s, 1, &mask, &off);
+    if (rc) return rc;
+    if (off & 1u) { ctx->last_error = "public key is not on P-256"; return FABGPU_E_ARG; }
+    *valid = (int)(mask & 1u);
+    return finish("");
+}
+
+int fabgpu_test_fieldop(fabgpu_ctx* ctx, int op, const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out)
+{
+    if (!ctx || !a || !b || !out) return FABGPU_E_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    Device& dv = ctx->devs[0];
+    CK(ctx, cudaSetDevice(dv.id));
+    uint8_t *da = nullptr, *db = nullptr, *dout = nullptr;
+    CK(ctx, cudaMalloc(&da, 32 * n)); CK(ctx, cudaMalloc(&db, 32 * n)); CK(ctx, cudaMalloc(&dout, 32 * n));
+    CK(ctx, cudaMemcpy(da, a, 32 * n, cudaMemcpyHostToDevice));
+    CK(ctx, cudaMemcpy(db, b, 32 * n, cudaMemcpyHostToDevice));
+    fieldop_kernel<<<(unsigned)((n + 63) / 64), 64>>>(op, da, db, (int)n, dout);
+    ctx->launches++;
+    CK(ctx, cudaGetLastError());
+    CK(ctx, cudaMemcpy(out, dout, 32 * n, cudaMemcpyDeviceToHost));
+    cudaFree(da); cudaFree(db); cudaFree(dout);
+    return FABGPU_OK;
+}
+
+long fabgpu_test_gtable(fabgpu_ctx* ctx, uint8_t* out, size_t cap)
+{
+    const size_t bytes = (size_t)FAB_G_WINDOWS * FAB_G_ENTRIES * sizeof(aff);
+    if (!out) return (long)bytes;
+    if (!ctx || cap < bytes) return FABGPU_E_ARG;
+    CK(ctx, cudaSetDevice(ctx->devs[0].id));
+    CK(ctx, cudaMemcpy(out, ctx->devs[0].gtab, bytes, cudaMemcpyDeviceToHost));
+    return (long)bytes;
+}
+
+}  // extern "C"

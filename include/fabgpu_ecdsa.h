@@ -1,0 +1,125 @@
+/* fabgpu_ecdsa.h -- C ABI of the B200 batch ECDSA-P256 verifier (libfabgpu_ecdsa.so).
+ *
+ * Drop-in boundary for ONE path of trustbloc/fabric-mod: signature verification behind
+ *     bccsp.BCCSP.Verify(k, signature, digest, opts) (bool, error)         reference bccsp/bccsp.go:123-125
+ * as implemented by the software provider
+ *     sw.CSP.Verify -> verifyECDSA -> crypto/ecdsa.Verify                   reference bccsp/sw/impl.go:247-270,
+ *                                                                           bccsp/sw/ecdsa.go:41-57
+ * and reached from msp identity.Verify (reference msp/identities.go:169-196).  The reference has no native
+ * code on this path; these entry points are what a cgo provider (go/bccsp/gpu) binds, in the
+ * same way bccsp/pkcs11 binds an HSM library (reference bccsp/pkcs11/pkcs11.go:36-87,241-262).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no CUDA or torch types.  `cuda_stream` arguments are a cudaStream_t
+ *     passed as void* (NULL = the context's own stream).
+ *   - every function returns FABGPU_OK (0) or a negative FABGPU_E_* code.  A negative code means "could not
+ *     decide": the caller MUST fall back to the CPU provider for that batch.  A device fault is never
+ *     reported as "signature invalid" (that would fork the ledger).
+ *   - big integers cross the boundary as 32-byte big-endian strings, structure-of-arrays: element i of an
+ *     array lives at bytes [32*i, 32*i+32).
+ *   - validity bitmask: signature i -> bit (i % 32) of uint32 word (i / 32); 1 = VALID, i.e. (true, nil).
+ *   - there is NO CPU fallback inside this library: without a usable CUDA device fabgpu_init fails.
+ */
+#ifndef FABGPU_ECDSA_H
+#define FABGPU_ECDSA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct fabgpu_ctx fabgpu_ctx;
+
+enum {
+    FABGPU_OK = 0,
+    FABGPU_E_NO_DEVICE = -1,   /* no CUDA device / driver, or device id out of range */
+    FABGPU_E_CUDA = -2,        /* a CUDA call failed; see fabgpu_last_error */
+    FABGPU_E_ARG = -3,         /* bad argument (NULL, n > max_batch, bad slot ...) */
+    FABGPU_E_INJECTED = -4     /* FABGPU_FAULT_INJECT=1 is set: every verify call fails (fault-injection tests) */
+};
+
+/* Per-signature status of the bccsp-level entry points: the (bool, error) pair of sw.CSP.Verify as one byte.
+ * Error kinds follow reference bccsp/sw/impl.go:249-266, bccsp/sw/ecdsa.go:42-54, bccsp/utils/ecdsa.go:43-92. */
+enum {
+    FABGPU_ST_VALID = 0,              /* (true,  nil) */
+    FABGPU_ST_INVALID = 1,            /* (false, nil): well-formed but wrong, incl. r >= N, point at infinity */
+    FABGPU_ST_ERR_NIL_KEY = 2,        /* "Invalid Key. It must not be nil." */
+    FABGPU_ST_ERR_EMPTY_SIG = 3,      /* "Invalid signature. Cannot be empty." */
+    FABGPU_ST_ERR_EMPTY_DIGEST = 4,   /* "Invalid digest. Cannot be empty." */
+    FABGPU_ST_ERR_UNMARSHAL = 5,      /* "Failed unmashalling signature [...]" (asn1) */
+    FABGPU_ST_ERR_R_NOT_POSITIVE = 6, /* "invalid signature, R must be larger than zero" */
+    FABGPU_ST_ERR_S_NOT_POSITIVE = 7, /* "invalid signature, S must be larger than zero" */
+    FABGPU_ST_ERR_HIGH_S = 8,         /* "Invalid S. Must be smaller than half the order [..][..]." */
+    FABGPU_ST_ERR_UNSUPPORTED_KEY = 9,/* not a P-256 key: delegate to the embedded sw provider */
+    FABGPU_ST_ERR_OFF_CURVE = 10      /* public key is not a curve point: outside the reference's defined behaviour, delegate to CPU */
+};
+
+/* ---- lifetime ---------------------------------------------------------------------------------------- */
+
+/* Creates a context on the given CUDA devices (device_ids == NULL && n_dev == 0: device 0).  Allocates, per
+ * device, the fixed-base table, device SoA buffers and pinned host SoA buffers for `max_batch` signatures per
+ * slot (FABGPU_SLOTS slots), and builds the table on the device.  A batch given to the host-buffer entry points
+ * is split into contiguous, 32-aligned ranges across the context's devices. */
+int fabgpu_init(const int* device_ids, int n_dev, size_t max_batch, fabgpu_ctx** out);
+void fabgpu_destroy(fabgpu_ctx* ctx);
+/* Last error text of this context (or of the failed fabgpu_init when ctx == NULL). Never NULL. */
+const char* fabgpu_last_error(const fabgpu_ctx* ctx);
+int fabgpu_device_count(const fabgpu_ctx* ctx);
+size_t fabgpu_max_batch(const fabgpu_ctx* ctx);
+
+#define FABGPU_SLOTS 2
+
+/* ---- leaf: pre-gated SoA tuples -> bitmask (replaces the crypto/ecdsa.Verify call at bccsp/sw/ecdsa.go:56) */
+
+/* Pinned, library-owned host SoA buffers of one slot (cgo cannot hand Go memory to an async copy).  Each of
+ * qx,qy,e,r,s has max_batch*32 bytes; mask and offcurve have ceil(max_batch/32) words.  Caller pre-conditions,
+ * established by the host gates exactly as the reference does before calling ecdsa.Verify: 0 < r, 0 < s <= N/2,
+ * r < 2^256 (longer r is INVALID without asking the GPU), e = leftmost min(len,32) digest bytes left-padded. */
+int fabgpu_host_buffers(fabgpu_ctx* ctx, int slot, uint8_t** qx, uint8_t** qy, uint8_t** e, uint8_t** r,
+                        uint8_t** s, uint32_t** mask, uint32_t** offcurve);
+/* H2D + kernel + D2H for the first n tuples of the slot's pinned buffers; synchronous. */
+int fabgpu_verify_p256(fabgpu_ctx* ctx, int slot, size_t n);
+/* Same, asynchronous: returns after enqueueing; fabgpu_wait blocks until the slot's mask is complete. */
+int fabgpu_verify_p256_async(fabgpu_ctx* ctx, int slot, size_t n);
+int fabgpu_wait(fabgpu_ctx* ctx, int slot);
+/* Convenience for callers whose tuples sit in ordinary host memory: copies through slot 0. */
+int fabgpu_verify_p256_host(fabgpu_ctx* ctx, const uint8_t* qx, const uint8_t* qy, const uint8_t* e,
+                            const uint8_t* r, const uint8_t* s, size_t n, uint32_t* mask, uint32_t* offcurve);
+/* Inputs and outputs already resident in the memory of context device `dev_index`; enqueues on `cuda_stream`
+ * and returns without synchronising.  offcurve may be NULL. */
+int fabgpu_verify_p256_device(fabgpu_ctx* ctx, int dev_index, const void* d_qx, const void* d_qy, const void* d_e,
+                              const void* d_r, const void* d_s, size_t n, void* d_mask, void* d_offcurve,
+                              void* cuda_stream);
+
+/* ---- bccsp level: raw DER signatures + digests + keys -> three-valued status (sw.CSP.Verify semantics) -- */
+
+/* keys_xy: K x 64 bytes (X || Y, big-endian).  key_idx[i] in [0,K), or < 0 for a nil key.  digests / sigs are
+ * concatenations indexed by (n+1)-entry offset tables.  status[i] receives FABGPU_ST_*.  The host gates (DER per
+ * Go encoding/asn1, positivity, low-S, r < 2^256) run on the CPU; survivors are verified on the GPU. */
+int fabgpu_bccsp_verify_batch(fabgpu_ctx* ctx, const uint8_t* keys_xy, int K, const int32_t* key_idx,
+                              const uint8_t* digests, const uint32_t* dig_off, const uint8_t* sigs,
+                              const uint32_t* sig_off, size_t n, uint8_t* status);
+/* Single call with the reference's exact error strings (sw.CSP.Verify).  key_xy == NULL is the nil key.
+ * *valid and err (NUL-terminated, truncated to errcap) mirror the Go (bool, error) pair; err[0] == 0 is nil. */
+int fabgpu_bccsp_verify(fabgpu_ctx* ctx, const uint8_t* key_xy, const uint8_t* sig, size_t sig_len,
+                        const uint8_t* digest, size_t digest_len, int* valid, char* err, size_t errcap);
+/* The host gate alone (no GPU): parses one DER signature the way utils.UnmarshalECDSASignature + IsLowS do and,
+ * on success, writes r and s as 32-byte big-endian.  Returns a FABGPU_ST_* code: FABGPU_ST_VALID means "gates
+ * passed, ask the GPU"; FABGPU_ST_INVALID means r >= 2^256 (cannot be < N). */
+int fabgpu_gate_signature(const uint8_t* sig, size_t sig_len, uint8_t r_out[32], uint8_t s_out[32]);
+
+/* ---- test / bring-up hooks ------------------------------------------------------------------------------ */
+/* Device field primitives on arrays (op: 0 fe_mul, 1 fe_add, 2 fe_sub, 3 sc_mul, 4 fe_inv, 5 sc_inv_to_mont). */
+int fabgpu_test_fieldop(fabgpu_ctx* ctx, int op, const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out);
+/* Copies the device fixed-base table (entries x 64 bytes, Montgomery little-endian limbs) to `out`; returns the
+ * byte size needed when out == NULL. */
+long fabgpu_test_gtable(fabgpu_ctx* ctx, uint8_t* out, size_t cap);
+/* Kernel launches issued by this context so far (bench.py's gpu_launches). */
+unsigned long long fabgpu_launch_count(const fabgpu_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FABGPU_ECDSA_H */

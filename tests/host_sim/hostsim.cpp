@@ -1,0 +1,85 @@
+// TEST HELPER (not product code): compiles fabric-mod_b200/csrc/ecdsa_verify.cuh for the host so the exact
+// point / window / verify logic the CUDA kernel runs can be checked against the oracle on the GPU-less build
+// box.  Only the innermost limb primitives differ between the two builds (PTX on device, uint64_t here); those
+// are checked on the GPU by tests/test_gpu_field.py.
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#include "../../fabric-mod_b200/csrc/ecdsa_verify.cuh"
+
+using namespace fabgpu;
+
+static std::vector<aff> g_tab;
+
+extern "C" {
+
+void hostsim_build_gtable()
+{
+    if (!g_tab.empty()) return;
+    g_tab.resize((size_t)FAB_G_WINDOWS * FAB_G_ENTRIES);
+    // window j's entries from window j-1's by FAB_WG doublings would be faster; this mirrors the device kernel 1:1
+    for (int j = 0; j < FAB_G_WINDOWS; j++)
+        for (uint32_t d = 1; d <= (uint32_t)FAB_G_ENTRIES; d++)
+            g_tab[(size_t)j * FAB_G_ENTRIES + d - 1] = g_table_entry(j, d);
+}
+
+// raw table bytes (little-endian limbs, Montgomery form): entries x 64 bytes
+size_t hostsim_gtable(const uint8_t** out)
+{
+    hostsim_build_gtable();
+    *out = (const uint8_t*)g_tab.data();
+    return g_tab.size() * sizeof(aff);
+}
+
+// inputs: n x 32 big-endian bytes each; out[i] = V_INVALID / V_VALID / V_OFFCURVE
+void hostsim_verify_batch(const uint8_t* qx, const uint8_t* qy, const uint8_t* e, const uint8_t* r, const uint8_t* s, int n, uint8_t* out)
+{
+    hostsim_build_gtable();
+    for (int i = 0; i < n; i++) {
+        size_t o = 32 * (size_t)i;
+        out[i] = (uint8_t)ecdsa_verify_one(u256_from_be(qx + o), u256_from_be(qy + o), u256_from_be(e + o),
+                                           u256_from_be(r + o), u256_from_be(s + o), g_tab.data());
+    }
+}
+
+// field / scalar unit hooks: op 0 fe_mul, 1 fe_add, 2 fe_sub, 3 sc_mul, 4 fe_inv, 5 sc_inv_to_mont (b ignored for 4,5)
+void hostsim_fieldop(int op, const uint8_t* a, const uint8_t* b, int n, uint8_t* out)
+{
+    for (int i = 0; i < n; i++) {
+        u256 x = u256_from_be(a + 32 * (size_t)i), y = u256_from_be(b + 32 * (size_t)i), z;
+        switch (op) {
+            case 0: z = fe_mul(x, y); break;
+            case 1: z = fe_add(x, y); break;
+            case 2: z = fe_sub(x, y); break;
+            case 3: z = sc_mul(x, y); break;
+            case 4: z = fe_inv(x); break;
+            default: z = sc_inv_to_mont(x); break;
+        }
+        u256_to_be(z, out + 32 * (size_t)i);
+    }
+}
+
+// k*P for affine plain (x,y) and plain scalar k, via the same table + Booth routine the kernel uses; returns affine plain
+// coordinates, or all-zero for infinity.
+void hostsim_scalar_mul(const uint8_t* k, const uint8_t* px, const uint8_t* py, uint8_t* ox, uint8_t* oy)
+{
+    aff q; q.x = fe_to_mont(u256_from_be(px)); q.y = fe_to_mont(u256_from_be(py));
+    jac tab[16];
+    build_q_table(tab, q);
+    jac r = scalar_mul_var(u256_from_be(k), tab);
+    if (jac_is_infinity(r)) { memset(ox, 0, 32); memset(oy, 0, 32); return; }
+    aff a = jac_to_aff(r);
+    u256_to_be(fe_from_mont(a.x), ox); u256_to_be(fe_from_mont(a.y), oy);
+}
+
+// k*G via the fixed-base table
+void hostsim_base_mul(const uint8_t* k, uint8_t* ox, uint8_t* oy)
+{
+    hostsim_build_gtable();
+    jac r = add_fixed_base(jac_infinity(), u256_from_be(k), g_tab.data());
+    if (jac_is_infinity(r)) { memset(ox, 0, 32); memset(oy, 0, 32); return; }
+    aff a = jac_to_aff(r);
+    u256_to_be(fe_from_mont(a.x), ox); u256_to_be(fe_from_mont(a.y), oy);
+}
+
+}  // extern "C"

@@ -1,0 +1,248 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI, against the oracle.
+Integer work: the bar is bit-exact."""
+import ctypes
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+
+from oracle import bccsp_sw as o
+from oracle import fast, goasn1, p256
+from tools import workload
+from util import be32, from_be, hostsim, mask_bits, pkg
+import vectors
+
+pytestmark = pytest.mark.gpu
+
+R = 1 << 256
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = pkg().binding.Context(max_batch=1 << 17)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def csp():
+    c = pkg().bccsp.GPUCSP(max_batch=4096)
+    yield c
+    c.close()
+
+
+def _ints(arr):
+    return [from_be(row) for row in arr]
+
+
+# ---------------------------------------------------------------------------------------------------------
+# device limb primitives (PTX) vs Python integers
+# ---------------------------------------------------------------------------------------------------------
+def _operands(mod, rnd, n):
+    edge = [0, 1, 2, mod - 1, mod - 2, (1 << 255) % mod, (1 << 224) % mod, (1 << 32) - 1, ((1 << 256) - 1) % mod, (1 << 96) % mod]
+    a = [rnd.randrange(mod) for _ in range(n)] + [x for x in edge for _ in edge]
+    b = [rnd.randrange(mod) for _ in range(n)] + [y for _ in edge for y in edge]
+    return a, b
+
+
+def test_field_primitives(ctx):
+    rnd = random.Random(1)
+    P, N = p256.P, p256.N
+    a, b = _operands(P, rnd, 4000)
+    A = np.stack([be32(x) for x in a]); B = np.stack([be32(x) for x in b])
+    rinv = pow(R, -1, P)
+    assert _ints(ctx.test_fieldop(0, A, B)) == [x * y * rinv % P for x, y in zip(a, b)]
+    assert _ints(ctx.test_fieldop(1, A, B)) == [(x + y) % P for x, y in zip(a, b)]
+    assert _ints(ctx.test_fieldop(2, A, B)) == [(x - y) % P for x, y in zip(a, b)]
+    a, b = _operands(N, rnd, 4000)
+    A = np.stack([be32(x) for x in a]); B = np.stack([be32(x) for x in b])
+    rinvn = pow(R, -1, N)
+    assert _ints(ctx.test_fieldop(3, A, B)) == [x * y * rinvn % N for x, y in zip(a, b)]
+    a = [rnd.randrange(1, P) for _ in range(64)] + [1, P - 1]
+    A = np.stack([be32(x) for x in a])
+    assert _ints(ctx.test_fieldop(4, A, A)) == [pow(x * rinv % P, -1, P) * R % P for x in a]
+    a = [rnd.randrange(1, N) for _ in range(64)] + [1, N - 1, p256.HALF_N]
+    A = np.stack([be32(x) for x in a])
+    assert _ints(ctx.test_fieldop(5, A, A)) == [pow(x, -1, N) * R % N for x in a]
+
+
+def test_fixed_base_table(ctx):
+    """Device-built table == host build of the same code, and spot entries == oracle scalar multiplication."""
+    tab = ctx.test_gtable()
+    p = ctypes.POINTER(ctypes.c_uint8)()
+    size = hostsim().hostsim_gtable(ctypes.byref(p))
+    host = np.ctypeslib.as_array(p, shape=(size,))
+    assert tab.shape[0] == size and (tab == host).all()
+    ent = tab.view("<u4").reshape(-1, 16)
+    assert ent.shape[0] % 255 == 0
+    rinv = pow(R, -1, p256.P)
+    rnd = random.Random(3)
+    for _ in range(12):
+        j, d = rnd.randrange(ent.shape[0] // 255), rnd.randrange(1, 256)
+        row = ent[j * 255 + d - 1]
+        x = sum(int(row[i]) << (32 * i) for i in range(8)) * rinv % p256.P
+        y = sum(int(row[8 + i]) << (32 * i) for i in range(8)) * rinv % p256.P
+        assert (x, y) == p256.scalar_mult(d << (8 * j), (p256.GX, p256.GY))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# leaf: pre-gated SoA -> bitmask
+# ---------------------------------------------------------------------------------------------------------
+def test_config1_1024_tuples(ctx):
+    w = workload.Workload(1024, 16, seed=workload.DEFAULT_SEED)
+    exp = fast.verify_batch(w.keys_xy, w.key_idx, w.digest, w.dig_off(), w.sigs, w.sig_off, nthreads=8)
+    mask, off = ctx.verify_p256_host(w.qx(), w.qy(), w.digest, w.r, w.s)
+    assert (mask == fast.valid_mask(exp)).all() and (mask == 0xFFFFFFFF).all() and not off.any()
+
+
+def test_ragged_sizes_and_empty(ctx):
+    w = workload.Workload(300, 4, seed=11)
+    w.tamper_r(0.2)
+    exp = fast.verify_batch(w.keys_xy, w.key_idx, w.digest, w.dig_off(), w.sigs, w.sig_off, nthreads=4)
+    bits = (exp == o.VALID).astype(np.uint8)
+    for n in (0, 1, 31, 32, 33, 127, 128, 129, 300):
+        mask, off = ctx.verify_p256_host(w.qx()[:n], w.qy()[:n], w.digest[:n], w.r[:n], w.s[:n])
+        assert mask.shape[0] == (n + 31) // 32
+        assert (mask_bits(mask, n) == bits[:n]).all(), n
+        if n % 32:
+            assert int(mask[-1]) >> (n % 32) == 0       # padding bits are zero
+
+
+def test_config2_64k_all_valid(ctx):
+    # BASELINE.json configs[1]: 64k-signature batch, K = 64 keys, bitmask equals bccsp/sw (oracle: all ones)
+    w = workload.Workload(65536, 64, seed=workload.DEFAULT_SEED + 2)
+    exp = fast.verify_batch(w.keys_xy, w.key_idx, w.digest, w.dig_off(), w.sigs, w.sig_off, nthreads=os.cpu_count())
+    mask, off = ctx.verify_p256_host(w.qx(), w.qy(), w.digest, w.r, w.s)
+    assert (mask == fast.valid_mask(exp)).all()
+    assert (mask == 0xFFFFFFFF).all()
+
+
+def test_config5_tampered_mask_exact(ctx):
+    # BASELINE.json configs[4] on one GPU at reduced size: 5 % tampered r, exact-match bitmask, no false accept
+    w = workload.Workload(32768, 64, seed=workload.DEFAULT_SEED + 5)
+    picked = w.tamper_r(0.05)
+    exp = fast.verify_batch(w.keys_xy, w.key_idx, w.digest, w.dig_off(), w.sigs, w.sig_off, nthreads=os.cpu_count())
+    mask, off = ctx.verify_p256_host(w.qx(), w.qy(), w.digest, w.r, w.s)
+    assert (mask == fast.valid_mask(exp)).all()
+    bits = mask_bits(mask, w.n)
+    assert bits[picked].sum() == 0 and 1200 < len(picked) < 2100
+
+
+def test_async_slots_and_pinned_buffers(ctx):
+    w = workload.Workload(4096, 8, seed=21)
+    w.tamper_r(0.1)
+    exp = fast.valid_mask(fast.verify_batch(w.keys_xy, w.key_idx, w.digest, w.dig_off(), w.sigs, w.sig_off, nthreads=8))
+    half = 2048
+    for slot, sl in ((0, slice(0, half)), (1, slice(half, 4096))):
+        hb = ctx.host_buffers(slot)
+        for name, arr in (("qx", w.qx()), ("qy", w.qy()), ("e", w.digest), ("r", w.r), ("s", w.s)):
+            hb[name][:half] = arr[sl]
+        ctx.verify_p256_async(slot, half)
+    ctx.wait(0); ctx.wait(1)
+    got = np.concatenate([ctx.host_buffers(0)["mask"][:half // 32], ctx.host_buffers(1)["mask"][:half // 32]])
+    assert (got == exp).all()
+
+
+def test_x509_golden_fixtures(csp):
+    fix = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "x509_fixtures.json")))
+    keys, kidx, digs, sigs, exp = [], [], [], [], []
+    for i, x in enumerate(fix):
+        keys.append(csp.KeyImport((int(x["qx"], 16), int(x["qy"], 16))))
+        kidx.append(i); digs.append(bytes.fromhex(x["digest"])); sigs.append(bytes.fromhex(x["sig_der"]))
+        exp.append({"VALID": o.VALID, "ERR_HIGH_S": o.ERR_HIGH_S}[x["expect"]])
+    st = csp.VerifyBatch(keys, kidx, digs, sigs)
+    assert list(st) == exp
+    # msp/cert_test.go:70-97: after s -> N - s the 31 high-S signatures verify
+    sigs2 = [goasn1.marshal_ecdsa_signature(int(x["r"], 16), p256.N - int(x["s"], 16)) if x["expect"] == "ERR_HIGH_S" else s
+             for x, s in zip(fix, sigs)]
+    assert set(csp.VerifyBatch(keys, kidx, digs, sigs2)) == {o.VALID}
+
+
+def test_constructed_edge_cases(csp):
+    cases = vectors.build()
+    keys = [csp.KeyImport((c["qx"] % R, c["qy"] % R)) for c in cases]
+    st = csp.VerifyBatch(keys, list(range(len(cases))), [c["digest"] for c in cases], [c["sig"] for c in cases])
+    for c, got in zip(cases, st):
+        assert int(got) == vectors.expected_status(c), c["name"]
+
+
+def test_nil_key_empty_digest_statuses(csp):
+    k = csp.KeyImport((p256.GX, p256.GY))
+    good = goasn1.marshal_ecdsa_signature(5, 7)
+    st = csp.VerifyBatch([k, None], [0, 1, 0, 0, -1], [b"\x01" * 32, b"\x01" * 32, b"", b"\x01" * 32, b"\x01" * 32], [good, good, good, b"", good])
+    assert list(st) == [o.INVALID, o.ERR_NIL_KEY, o.ERR_EMPTY_DIGEST, o.ERR_EMPTY_SIG, o.ERR_NIL_KEY]
+
+
+# ---------------------------------------------------------------------------------------------------------
+# bccsp / msp interface behaviour (reads like bccsp/sw/ecdsa_test.go, bccsp/sw/impl_test.go, msp/msp_test.go)
+# ---------------------------------------------------------------------------------------------------------
+def test_verify_error_strings_match_reference(csp):
+    d = 0x1F2E3D4C
+    k = csp.KeyImport(p256.scalar_mult(d, (p256.GX, p256.GY)))
+    msg = b"hello world"                                   # bccsp/sw/ecdsa_test.go:47-56 uses the message as digest
+    r, s = p256.ecdsa_sign_lows(d, msg, 0xABCDEF)
+    sigma = goasn1.marshal_ecdsa_signature(r, s)
+    ok = o.P256PublicKey(k.x, k.y)
+    for key, sig, dig in ((k, sigma, msg), (k, None, msg), (k, b"", msg), (k, sigma, b""), (None, sigma, msg),
+                          (k, goasn1.marshal_ecdsa_signature(r, p256.HALF_N + 1), msg), (k, goasn1.marshal_ecdsa_signature(-1, 1), msg),
+                          (k, goasn1.marshal_ecdsa_signature(1, 0), msg), (k, sigma[1:], msg), (k, sigma, msg[1:]),
+                          (k, goasn1.marshal_ecdsa_signature(p256.N, s), msg)):
+        got = csp.Verify(key, sig, dig, None)
+        exp = o.csp_verify(ok if key is not None else None, sig, dig)
+        assert got[0] == exp[0]
+        if exp[1] is None:
+            assert got[1] is None
+        elif "asn1:" in exp[1]:
+            assert got[1].startswith("Failed verifing with opts [<nil>]: Failed unmashalling signature [failed unmashalling signature [asn1: ")
+        else:
+            assert got[1] == exp[1]
+    assert csp.Verify(k, sigma, msg, None) == (True, None)
+    valid, err = csp.Verify(k, goasn1.marshal_ecdsa_signature(r, p256.HALF_N + 1), msg, None)
+    assert not valid and "Invalid S. Must be smaller than half the order [" in err
+    assert "Unsupported 'VerifyKey' provided [" in csp.Verify(object(), sigma, msg, None)[1]
+
+
+def test_identity_verify(csp):
+    # msp/msp_test.go:494-625 TestSignAndVerify / _Failures / OtherHash / longMessage
+    d = 0x5EED5EED5EED
+    pk = csp.KeyImport(p256.scalar_mult(d, (p256.GX, p256.GY)))
+    import hashlib
+    for fam, h in ((pkg().bccsp.SHA2, hashlib.sha256), (pkg().bccsp.SHA3, hashlib.sha3_256)):
+        ident = pkg().bccsp.Identity(csp, pk, fam)
+        for msg in (b"foo", b"x" * 100000):
+            r, s = p256.ecdsa_sign_lows(d, h(msg).digest(), 0x1234567 + len(msg))
+            sig = goasn1.marshal_ecdsa_signature(r, s)
+            assert ident.Verify(msg, sig) is None
+            assert ident.Verify(msg[1:], sig) == "The signature is invalid"
+            assert ident.Verify(msg, sig[1:]).startswith("could not determine the validity of the signature: Failed verifing with opts")
+            assert o.identity_verify(o.P256PublicKey(pk.x, pk.y), msg, sig, fam) is None
+
+
+def test_fault_injection_never_reports_invalid(ctx):
+    w = workload.Workload(64, 2, seed=3)
+    b = pkg().binding
+    os.environ["FABGPU_FAULT_INJECT"] = "1"
+    try:
+        with pytest.raises(b.FabGpuError) as ei:
+            ctx.verify_p256_host(w.qx(), w.qy(), w.digest, w.r, w.s)
+        assert ei.value.code == b.E_INJECTED
+    finally:
+        del os.environ["FABGPU_FAULT_INJECT"]
+    mask, _ = ctx.verify_p256_host(w.qx(), w.qy(), w.digest, w.r, w.s)
+    assert (mask == 0xFFFFFFFF).all()
+
+
+def test_device_resident_entry_with_torch_stream(ctx):
+    import torch
+    w = workload.Workload(8192, 16, seed=31)
+    w.tamper_r(0.07)
+    exp = fast.valid_mask(fast.verify_batch(w.keys_xy, w.key_idx, w.digest, w.dig_off(), w.sigs, w.sig_off, nthreads=8))
+    dev = torch.device("cuda:0")
+    t = [torch.from_numpy(a).to(dev) for a in (w.qx(), w.qy(), w.digest, w.r, w.s)]
+    mask = torch.zeros(w.n // 32, dtype=torch.int32, device=dev)
+    st = torch.cuda.current_stream(dev)
+    ctx.verify_p256_device(*[x.data_ptr() for x in t], w.n, mask.data_ptr(), 0, st.cuda_stream)
+    st.synchronize()
+    assert (mask.cpu().numpy().view(np.uint32) == exp).all()

@@ -1,0 +1,48 @@
+"""The verify algorithm the CUDA kernel runs (fabric-mod_b200/csrc/ecdsa_verify.cuh: fixed-base table, Booth
+windows, complete Jacobian group law, inversion-free final check) compiled for the host and compared with the oracle.
+Runs on the GPU-less build box; the PTX limb primitives themselves are covered by tests/test_gpu_*.py."""
+import numpy as np
+
+from oracle import bccsp_sw as o
+from oracle import fast
+from tools import workload
+from util import be32, hash_to_e32, hostsim_verify, pkg
+import vectors
+
+V_INVALID, V_VALID, V_OFFCURVE = 0, 1, 2
+
+
+def test_constructed_edge_cases():
+    b = pkg().binding
+    for c in vectors.build():
+        exp = vectors.expected_status(c)
+        if c["expect"] is not None:
+            assert exp == c["expect"], "oracle disagrees with the construction: " + c["name"]
+        if len(c["sig"]) == 0:
+            continue
+        st, r, s = b.gate_signature(c["sig"])
+        if st != o.VALID:
+            assert st == exp, c["name"]
+            continue
+        out = hostsim_verify(be32(c["qx"] % (1 << 256)), be32(c["qy"] % (1 << 256)), hash_to_e32(c["digest"]),
+                             np.frombuffer(r, np.uint8), np.frombuffer(s, np.uint8))[0]
+        got = {V_VALID: o.VALID, V_INVALID: o.INVALID, V_OFFCURVE: o.ERR_OFF_CURVE}[int(out)]
+        assert got == exp, c["name"]
+
+
+def test_config1_1024_tuples():
+    # BASELINE.json configs[0]: 1 024 synthetic tuples, K = 16 keys, all valid
+    w = workload.Workload(1024, 16, seed=workload.DEFAULT_SEED, nthreads=4)
+    exp = fast.verify_batch(w.keys_xy, w.key_idx, w.digest, w.dig_off(), w.sigs, w.sig_off, nthreads=4)
+    assert (exp == o.VALID).all()
+    out = hostsim_verify(w.qx(), w.qy(), w.digest, w.r, w.s)
+    assert (out == V_VALID).all()
+
+
+def test_tampered_matches_oracle_bit_for_bit():
+    w = workload.Workload(768, 8, seed=7, nthreads=4)
+    w.tamper_r(frac=0.25)
+    exp = fast.verify_batch(w.keys_xy, w.key_idx, w.digest, w.dig_off(), w.sigs, w.sig_off, nthreads=4)
+    out = hostsim_verify(w.qx(), w.qy(), w.digest, w.r, w.s)
+    assert ((out == V_VALID) == (exp == o.VALID)).all()
+    assert 100 < int((exp != o.VALID).sum()) < 300
