@@ -283,7 +283,7 @@ int fabgpu_verify_p256_device(fabgpu_ctx* ctx, int dev_index, const void* d_qx, 
     if (fault_injected()) { ctx->last_error = "fault injected (FABGPU_FAULT_INJECT=1)"; return FABGPU_E_INJECTED; }
     Device& dv = ctx->devs[dev_index];
     CK(ctx, cudaSetDevice(dv.id));
-    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : dv.slot[0].stream;
+    cudaStream_t st = (cudaStream_t)cuda_stream;   // NULL is CUDA's default stream, exactly as in the runtime API
     return launch_verify(ctx, (const uint8_t*)d_qx, (const uint8_t*)d_qy, (const uint8_t*)d_e, (const uint8_t*)d_r,
                          (const uint8_t*)d_s, n, dv.gtab, (uint32_t*)d_mask, (uint32_t*)d_offcurve, st);
 }

@@ -11,7 +11,7 @@
  *
  * Conventions
  *   - plain pointers and sizes only; no CUDA or torch types.  `cuda_stream` arguments are a cudaStream_t
- *     passed as void* (NULL = the context's own stream).
+ *     passed as void* (NULL = CUDA's default stream, as in the runtime API).
  *   - every function returns FABGPU_OK (0) or a negative FABGPU_E_* code.  A negative code means "could not
  *     decide": the caller MUST fall back to the CPU provider for that batch.  A device fault is never
  *     reported as "signature invalid" (that would fork the ledger).
