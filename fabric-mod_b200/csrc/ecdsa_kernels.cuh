@@ -8,6 +8,9 @@ namespace fabgpu {
 #ifndef FAB_VERIFY_THREADS
 #define FAB_VERIFY_THREADS 128
 #endif
+#ifndef FAB_VERIFY_MINBLOCKS
+#define FAB_VERIFY_MINBLOCKS 1
+#endif
 
 // 32 big-endian bytes at a 16-byte aligned address -> limbs, as two 128-bit loads + byte permutes
 __device__ __forceinline__ u256 load_be32(const uint8_t* p)
@@ -35,7 +38,7 @@ __global__ void build_g_table_kernel(aff* gtab)
 
 // One signature per thread.  SoA inputs: n x 32 big-endian bytes each.  Output: bit i%32 of word i/32 is 1 iff
 // signature i is VALID; offcurve (optional) flags public keys that are not curve points.
-__global__ void __launch_bounds__(FAB_VERIFY_THREADS)
+__global__ void __launch_bounds__(FAB_VERIFY_THREADS, FAB_VERIFY_MINBLOCKS)
 ecdsa_verify_kernel(const uint8_t* __restrict__ qx, const uint8_t* __restrict__ qy, const uint8_t* __restrict__ e,
                     const uint8_t* __restrict__ r, const uint8_t* __restrict__ s, uint32_t n,
                     const aff* __restrict__ gtab, uint32_t* __restrict__ mask, uint32_t* __restrict__ offcurve)

@@ -198,7 +198,18 @@ FAB_D u256 fe_reduce(uint32_t* t)
     return r;
 }
 
-FAB_D u256 fe_mul_dev(const u256& a, const u256& b)
+// FAB_MUL_CALL=1 (default): one out-of-line copy of the multiplier, reached by a register-convention call, so that
+// the hot loop of the verify kernel (5 doublings + 1 addition = 56 field multiplications) fits the instruction cache
+// instead of inlining 56 x 2.7 KB.  ncu on the fully inlined build showed "no_instruction" as the top stall.
+#ifndef FAB_MUL_CALL
+#define FAB_MUL_CALL 1
+#endif
+#if FAB_MUL_CALL
+#define FAB_MUL_ATTR __device__ __noinline__
+#else
+#define FAB_MUL_ATTR __device__ __forceinline__
+#endif
+FAB_MUL_ATTR u256 fe_mul_dev(u256 a, u256 b)
 {
     uint32_t t[16];
     mul_8x8(t, a.v, b.v);

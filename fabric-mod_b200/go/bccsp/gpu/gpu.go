@@ -1,0 +1,201 @@
+// Copyright the fabgpu authors. SPDX-License-Identifier: Apache-2.0
+//
+// Package gpu is a bccsp.BCCSP provider that verifies ECDSA P-256 signatures on NVIDIA B200 GPUs.
+//
+// It follows the precedent of bccsp/pkcs11 (pkcs11.go:36-87,241-262): embed the software provider, override
+// KeyImport and Verify, delegate everything else.  The gates that precede the curve arithmetic are the
+// reference's own functions (utils.UnmarshalECDSASignature, utils.IsLowS), so error values are identical to
+// bccsp/sw by construction; only the call at bccsp/sw/ecdsa.go:56 (ecdsa.Verify) is replaced by the GPU.
+//
+// bccsp.BCCSP.Verify is synchronous and per-signature, while a GPU wants thousands of signatures per launch.
+// Verify therefore parks the calling goroutine on a request queue; an aggregator goroutine drains the queue into
+// the library's pinned SoA slot and issues one cgo call per batch (flush on MaxBatch or FlushMicros).  Raise
+// peer.validatorPoolSize (core/peer/config.go:255-258) so that enough transactions are in flight to fill batches.
+//
+// Safety rule (SURVEY.md section 5): a device error must never look like "invalid signature".  On any error the
+// affected requests are re-run on the embedded software provider.
+//
+// NOT COMPILED in this repository's build image (no Go toolchain); see INTEGRATION.md.
+package gpu
+
+import (
+	"crypto/ecdsa"
+	"crypto/elliptic"
+	"crypto/x509"
+	"fmt"
+	"sync/atomic"
+	"time"
+
+	"github.com/hyperledger/fabric/bccsp"
+	"github.com/hyperledger/fabric/bccsp/sw"
+	"github.com/hyperledger/fabric/bccsp/utils"
+	"github.com/pkg/errors"
+)
+
+// GPUOpts is the `GPU:` block of the BCCSP section in core.yaml (beside SW: and PKCS11:).
+type GPUOpts struct {
+	SecLevel    int    `mapstructure:"security" json:"security" yaml:"Security"`
+	HashFamily  string `mapstructure:"hash" json:"hash" yaml:"Hash"`
+	Devices     []int  `mapstructure:"devices" json:"devices" yaml:"Devices"`
+	MaxBatch    int    `mapstructure:"maxbatch" json:"maxbatch" yaml:"MaxBatch"`
+	FlushMicros int    `mapstructure:"flushmicros" json:"flushmicros" yaml:"FlushMicros"`
+}
+
+// ecdsaP256Key wraps the software provider's key and caches the affine coordinates next to it.
+type ecdsaP256Key struct {
+	bccsp.Key                  // the sw key: SKI, Bytes, ... are unchanged
+	pub       *ecdsa.PublicKey // parsed once at import
+	x, y      [32]byte
+}
+
+type request struct {
+	key     *ecdsaP256Key
+	r, s, e [32]byte
+	done    chan result
+}
+
+type result struct {
+	valid bool
+	err   error // non-nil only for "could not decide" -> caller falls back to sw
+}
+
+type impl struct {
+	bccsp.BCCSP // embedded software provider (fallback and every non-verify method)
+
+	dev       *device
+	reqs      chan *request
+	flush     time.Duration
+	Fallbacks uint64 // exported counters for the operations endpoint
+	Batches   uint64
+}
+
+// New returns the GPU provider.  keyStore is handed to the embedded software provider.
+func New(opts GPUOpts, keyStore bccsp.KeyStore) (bccsp.BCCSP, error) {
+	swCSP, err := sw.NewWithParams(opts.SecLevel, opts.HashFamily, keyStore)
+	if err != nil {
+		return nil, errors.Wrapf(err, "Failed initializing fallback SW BCCSP")
+	}
+	if opts.MaxBatch <= 0 {
+		opts.MaxBatch = 65536
+	}
+	if opts.FlushMicros <= 0 {
+		opts.FlushMicros = 200
+	}
+	dev, err := openDevice(opts.Devices, opts.MaxBatch)
+	if err != nil {
+		return nil, errors.Wrapf(err, "Failed initializing GPU BCCSP")
+	}
+	csp := &impl{BCCSP: swCSP, dev: dev, reqs: make(chan *request, 4*opts.MaxBatch), flush: time.Duration(opts.FlushMicros) * time.Microsecond}
+	go csp.aggregate()
+	return csp, nil
+}
+
+// KeyImport delegates to sw and, for ECDSA P-256 public keys, caches X||Y beside the imported key.
+func (csp *impl) KeyImport(raw interface{}, opts bccsp.KeyImportOpts) (bccsp.Key, error) {
+	k, err := csp.BCCSP.KeyImport(raw, opts)
+	if err != nil {
+		return nil, err
+	}
+	var pub *ecdsa.PublicKey
+	switch v := raw.(type) {
+	case *ecdsa.PublicKey:
+		pub = v
+	case *x509.Certificate:
+		pub, _ = v.PublicKey.(*ecdsa.PublicKey)
+	}
+	if pub == nil || pub.Curve != elliptic.P256() || !pub.Curve.IsOnCurve(pub.X, pub.Y) {
+		return k, nil // P-384, RSA, private keys, ...: stay on the software path (pkcs11.go:259-261 pattern)
+	}
+	gk := &ecdsaP256Key{Key: k, pub: pub}
+	pub.X.FillBytes(gk.x[:])
+	pub.Y.FillBytes(gk.y[:])
+	return gk, nil
+}
+
+// Verify has exactly sw.CSP.Verify's contract (bccsp/sw/impl.go:247-270).
+func (csp *impl) Verify(k bccsp.Key, signature, digest []byte, opts bccsp.SignerOpts) (bool, error) {
+	gk, ok := k.(*ecdsaP256Key)
+	if !ok {
+		return csp.BCCSP.Verify(k, signature, digest, opts)
+	}
+	if len(signature) == 0 {
+		return false, errors.New("Invalid signature. Cannot be empty.")
+	}
+	if len(digest) == 0 {
+		return false, errors.New("Invalid digest. Cannot be empty.")
+	}
+	// the reference's own gates, in the reference's order (bccsp/sw/ecdsa.go:41-54)
+	r, s, err := utils.UnmarshalECDSASignature(signature)
+	if err != nil {
+		return false, errors.Wrapf(fmt.Errorf("Failed unmashalling signature [%s]", err), "Failed verifing with opts [%v]", opts)
+	}
+	lowS, err := utils.IsLowS(gk.pub, s)
+	if err != nil {
+		return false, errors.Wrapf(err, "Failed verifing with opts [%v]", opts)
+	}
+	if !lowS {
+		return false, errors.Wrapf(fmt.Errorf("Invalid S. Must be smaller than half the order [%s][%s].", s, utils.GetCurveHalfOrdersAt(gk.pub.Curve)),
+			"Failed verifing with opts [%v]", opts)
+	}
+	if r.BitLen() > 256 {
+		return false, nil // r >= 2^256 > N: ecdsa.Verify returns false
+	}
+	req := &request{key: gk, done: make(chan result, 1)}
+	r.FillBytes(req.r[:])
+	s.FillBytes(req.s[:])
+	d := digest
+	if len(d) > 32 {
+		d = d[:32] // hashToInt keeps the leftmost 32 bytes for a 256-bit order
+	}
+	copy(req.e[32-len(d):], d)
+	csp.reqs <- req
+	res := <-req.done
+	if res.err != nil {
+		atomic.AddUint64(&csp.Fallbacks, 1)
+		return csp.BCCSP.Verify(gk.Key, signature, digest, opts) // never report a device fault as "invalid"
+	}
+	return res.valid, nil
+}
+
+// aggregate drains requests into pinned slot buffers and launches one batch per flush.
+func (csp *impl) aggregate() {
+	pending := make([]*request, 0, csp.dev.maxBatch)
+	slotIdx := 0
+	timer := time.NewTimer(time.Hour)
+	for {
+		first, ok := <-csp.reqs
+		if !ok {
+			return
+		}
+		pending = append(pending[:0], first)
+		timer.Reset(csp.flush)
+	fill:
+		for len(pending) < csp.dev.maxBatch {
+			select {
+			case rq := <-csp.reqs:
+				pending = append(pending, rq)
+			case <-timer.C:
+				break fill
+			}
+		}
+		sl := &csp.dev.slots[slotIdx]
+		for i, rq := range pending {
+			o := 32 * i
+			copy(sl.qx[o:o+32], rq.key.x[:])
+			copy(sl.qy[o:o+32], rq.key.y[:])
+			copy(sl.e[o:o+32], rq.e[:])
+			copy(sl.r[o:o+32], rq.r[:])
+			copy(sl.s[o:o+32], rq.s[:])
+		}
+		err := csp.dev.verify(slotIdx, len(pending))
+		atomic.AddUint64(&csp.Batches, 1)
+		for i, rq := range pending {
+			if err != nil || (sl.offcurve[i>>5]>>(uint(i)&31))&1 == 1 {
+				rq.done <- result{err: errors.New("gpu could not decide")}
+				continue
+			}
+			rq.done <- result{valid: (sl.mask[i>>5]>>(uint(i)&31))&1 == 1}
+		}
+		slotIdx = (slotIdx + 1) % len(csp.dev.slots)
+	}
+}

@@ -1,0 +1,48 @@
+"""Kernel-variant timing helper (development tool): python tools/kbench.py <lib.so> [batch ...]
+Times fabgpu_verify_p256_device on device-resident inputs with CUDA events; checks the mask is all-valid."""
+import importlib
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+pkg = importlib.import_module("fabric-mod_b200")
+from tools import workload  # noqa: E402
+
+
+def main():
+    lib = sys.argv[1]
+    batches = [int(x) for x in sys.argv[2:]] or [65536]
+    pkg.binding.LIB_PATH = os.path.abspath(lib)
+    pkg.binding._LIB = None
+    dev = torch.device("cuda:0")
+    nmax = max(batches)
+    w = workload.Workload(nmax, 64, seed=workload.DEFAULT_SEED + 2)
+    ctx = pkg.binding.Context(max_batch=nmax)
+    t = [torch.from_numpy(a).to(dev) for a in (w.qx(), w.qy(), w.digest, w.r, w.s)]
+    mask = torch.zeros(nmax // 32, dtype=torch.int32, device=dev)
+    st = torch.cuda.current_stream(dev)
+    for n in batches:
+        def go():
+            ctx.verify_p256_device(*[x.data_ptr() for x in t], n, mask.data_ptr(), 0, st.cuda_stream)
+        for _ in range(3):
+            go()
+        torch.cuda.synchronize()
+        assert bool((mask[: n // 32] == -1).all())
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 10
+        e0.record()
+        for _ in range(reps):
+            go()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        print("%-40s n=%7d  %8.3f ms  %8.2f Mverify/s" % (os.path.basename(lib), n, ms, n / ms / 1e3), flush=True)
+    ctx.close()
+
+
+if __name__ == "__main__":
+    main()
