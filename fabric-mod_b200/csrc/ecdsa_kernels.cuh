@@ -70,7 +70,9 @@ __global__ void fieldop_kernel(int op, const uint8_t* a, const uint8_t* b, int n
         case 2: z = fe_sub(x, y); break;
         case 3: z = sc_mul(x, y); break;
         case 4: z = fe_inv(x); break;
-        default: z = sc_inv_to_mont(x); break;
+        case 5: z = sc_inv_to_mont(x); break;
+        case 7: z = fe_sqr(x); break;
+        default: z = sc_inv_to_mont_safegcd(x); break;
     }
     u256_to_be(z, out + 32 * (size_t)i);
 }

@@ -12,9 +12,13 @@
 // The final comparison avoids the field inversion: R.x == r' * R.Z^2 for r' in {r, r+n (if < p)}.
 #pragma once
 #include "p256_point.cuh"
+#include "p256_modinv.cuh"
 
 #ifndef FAB_WG
 #define FAB_WG 8                      // window bits of the fixed-base table
+#endif
+#ifndef FAB_SAFEGCD
+#define FAB_SAFEGCD 1
 #endif
 #define FAB_G_WINDOWS ((256 + FAB_WG - 1) / FAB_WG)
 #define FAB_G_ENTRIES ((1 << FAB_WG) - 1)
@@ -96,7 +100,11 @@ FAB_HD uint32_t ecdsa_verify_one(const u256& qx, const u256& qy, const u256& e, 
     aff q; q.x = fe_to_mont(qx); q.y = fe_to_mont(qy);
     if (!aff_on_curve(q)) return V_OFFCURVE;
 
-    const u256 w = sc_inv_to_mont(s);                 // s^-1 * 2^256 mod n
+#if FAB_SAFEGCD
+    const u256 w = sc_inv_to_mont_safegcd(s);         // s^-1 * 2^256 mod n (division steps, p256_modinv.cuh)
+#else
+    const u256 w = sc_inv_to_mont(s);                 // s^-1 * 2^256 mod n (Fermat)
+#endif
     const u256 u1 = sc_mul(sc_reduce_once(e), w);     // e*w mod n, plain
     const u256 u2 = sc_mul(r, w);                     // r*w mod n, plain
 

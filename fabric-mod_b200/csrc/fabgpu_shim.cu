@@ -5,6 +5,9 @@
 
 #include <algorithm>
 #include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <memory>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -44,8 +47,57 @@ struct HostSlot {
 
 }  // namespace
 
+// Minimal fork-join pool for the host gates (DER parse + packing is ~40 ns/signature single-threaded, which would
+// otherwise cap the end-to-end rate near 20 M/s).
+class GatePool {
+public:
+    explicit GatePool(int n) : n_(n < 1 ? 1 : n) {
+        for (int t = 1; t < n_; t++) th_.emplace_back([this, t] { loop(t); });
+    }
+    ~GatePool() {
+        { std::lock_guard<std::mutex> lk(mu_); stop_ = true; gen_++; }
+        cv_.notify_all();
+        for (auto& t : th_) t.join();
+    }
+    int size() const { return n_; }
+    // runs fn(tid) for tid in [0, size) and returns when all are done
+    void run(const std::function<void(int)>& fn) {
+        if (n_ == 1) { fn(0); return; }
+        { std::lock_guard<std::mutex> lk(mu_); fn_ = &fn; pending_ = n_ - 1; gen_++; }
+        cv_.notify_all();
+        fn(0);
+        std::unique_lock<std::mutex> lk(mu_);
+        done_.wait(lk, [this] { return pending_ == 0; });
+    }
+private:
+    void loop(int tid) {
+        unsigned long long seen = 0;
+        for (;;) {
+            const std::function<void(int)>* fn;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [&] { return gen_ != seen; });
+                seen = gen_;
+                if (stop_) return;
+                fn = fn_;
+            }
+            (*fn)(tid);
+            { std::lock_guard<std::mutex> lk(mu_); if (--pending_ == 0) done_.notify_one(); }
+        }
+    }
+    int n_;
+    std::vector<std::thread> th_;
+    std::mutex mu_;
+    std::condition_variable cv_, done_;
+    const std::function<void(int)>* fn_ = nullptr;
+    int pending_ = 0;
+    unsigned long long gen_ = 0;
+    bool stop_ = false;
+};
+
 struct fabgpu_ctx {
     std::vector<Device> devs;
+    std::unique_ptr<GatePool> pool;
     HostSlot hslot[FABGPU_SLOTS];
     size_t max_batch = 0;      // per slot, whole context
     size_t dev_cap = 0;        // per device per slot (multiple of 32)
@@ -155,6 +207,12 @@ int init_impl(fabgpu_ctx* ctx, const int* device_ids, int n_dev, size_t max_batc
         if (id < 0 || id >= count) { ctx->last_error = "device id out of range"; return FABGPU_E_NO_DEVICE; }
     if (max_batch == 0) { ctx->last_error = "max_batch must be > 0"; return FABGPU_E_ARG; }
     ctx->max_batch = max_batch;
+    {
+        int hw = (int)std::thread::hardware_concurrency();
+        const char* ev = getenv("FABGPU_GATE_THREADS");
+        int want = ev ? atoi(ev) : std::min(hw > 0 ? hw : 1, 16);
+        ctx->pool.reset(new GatePool(want));
+    }
     ctx->dev_cap = round_up32((max_batch + ids.size() - 1) / ids.size());
     ctx->devs.resize(ids.size());
     const size_t words = ctx->dev_cap / 32;
@@ -300,48 +358,57 @@ int fabgpu_bccsp_verify_batch(fabgpu_ctx* ctx, const uint8_t* keys_xy, int K, co
                               const uint32_t* dig_off, const uint8_t* sigs, const uint32_t* sig_off, size_t n, uint8_t* status)
 {
     if (!ctx || (n && (!key_idx || !dig_off || !sig_off || !status))) return FABGPU_E_ARG;
-    // Chunks of at most max_batch survivors go through slot 0; gates run on the calling thread.
+    // Chunks of at most max_batch signatures go through slot 0.  Gates run on the context's host threads; a signature
+    // that fails a gate keeps its slot position with r = s = 0 (the kernel rejects it at once) so that packing needs
+    // no compaction and stays parallel.
     std::lock_guard<std::mutex> lk0(ctx->slot0_mu);
     HostSlot& hs = ctx->hslot[0];
-    std::vector<uint32_t> where;   // original index of each packed survivor
-    where.reserve(std::min(n, ctx->max_batch));
-    size_t i = 0;
-    while (i < n || !where.empty()) {
-        while (i < n && where.size() < ctx->max_batch) {
-            const int32_t ki = key_idx[i];
-            const size_t sl = sig_off[i + 1] - sig_off[i], dl = dig_off[i + 1] - dig_off[i];
-            uint8_t st;
-            if (ki < 0) st = FABGPU_ST_ERR_NIL_KEY;                    // bccsp/sw/impl.go:249-251
-            else if (sl == 0) st = FABGPU_ST_ERR_EMPTY_SIG;            // :252-254
-            else if (dl == 0) st = FABGPU_ST_ERR_EMPTY_DIGEST;         // :255-257
-            else if (ki >= K || !keys_xy) st = FABGPU_ST_ERR_UNSUPPORTED_KEY;
-            else {
-                host::Gate g;
-                host::gate_signature(sigs + sig_off[i], sl, g, false);
-                st = (uint8_t)g.status;
-                if (g.status == FABGPU_ST_VALID) {
-                    const size_t k = where.size();
-                    memcpy(hs.h_in[0] + 32 * k, keys_xy + 64 * (size_t)ki, 32);
-                    memcpy(hs.h_in[1] + 32 * k, keys_xy + 64 * (size_t)ki + 32, 32);
-                    host::hash_to_e(digests + dig_off[i], dl, hs.h_in[2] + 32 * k);
-                    memcpy(hs.h_in[3] + 32 * k, g.r, 32);
-                    memcpy(hs.h_in[4] + 32 * k, g.s, 32);
-                    where.push_back((uint32_t)i);
+    for (size_t base = 0; base < n; base += ctx->max_batch) {
+        const size_t cnt = std::min(ctx->max_batch, n - base);
+        const int T = ctx->pool->size();
+        std::atomic<size_t> asked{0};
+        ctx->pool->run([&](int tid) {
+            const size_t b = cnt * (size_t)tid / T, e = cnt * (size_t)(tid + 1) / T;
+            size_t mine = 0;
+            for (size_t k = b; k < e; k++) {
+                const size_t i = base + k;
+                const int32_t ki = key_idx[i];
+                const size_t sl = sig_off[i + 1] - sig_off[i], dl = dig_off[i + 1] - dig_off[i];
+                uint8_t st;
+                if (ki < 0) st = FABGPU_ST_ERR_NIL_KEY;                    // bccsp/sw/impl.go:249-251
+                else if (sl == 0) st = FABGPU_ST_ERR_EMPTY_SIG;            // :252-254
+                else if (dl == 0) st = FABGPU_ST_ERR_EMPTY_DIGEST;         // :255-257
+                else if (ki >= K || !keys_xy) st = FABGPU_ST_ERR_UNSUPPORTED_KEY;
+                else {
+                    host::Gate g;
+                    host::gate_signature(sigs + sig_off[i], sl, g, false);
+                    st = (uint8_t)g.status;
+                    if (g.status == FABGPU_ST_VALID) {
+                        memcpy(hs.h_in[0] + 32 * k, keys_xy + 64 * (size_t)ki, 32);
+                        memcpy(hs.h_in[1] + 32 * k, keys_xy + 64 * (size_t)ki + 32, 32);
+                        host::hash_to_e(digests + dig_off[i], dl, hs.h_in[2] + 32 * k);
+                        memcpy(hs.h_in[3] + 32 * k, g.r, 32);
+                        memcpy(hs.h_in[4] + 32 * k, g.s, 32);
+                        mine++;
+                    }
                 }
+                if (st != FABGPU_ST_VALID) { memset(hs.h_in[3] + 32 * k, 0, 32); memset(hs.h_in[4] + 32 * k, 0, 32); }
+                status[i] = st;
             }
-            status[i] = st;
-            i++;
-        }
-        if (!where.empty()) {
-            int rc = fabgpu_verify_p256(ctx, 0, where.size());
-            if (rc) return rc;
-            for (size_t k = 0; k < where.size(); k++) {
+            asked += mine;
+        });
+        if (asked.load() == 0) continue;
+        int rc = fabgpu_verify_p256(ctx, 0, cnt);
+        if (rc) return rc;
+        ctx->pool->run([&](int tid) {
+            const size_t b = cnt * (size_t)tid / T, e = cnt * (size_t)(tid + 1) / T;
+            for (size_t k = b; k < e; k++) {
+                if (status[base + k] != FABGPU_ST_VALID) continue;          // decided by a gate
                 const bool ok = (hs.h_mask[k >> 5] >> (k & 31)) & 1u;
                 const bool oc = (hs.h_off[k >> 5] >> (k & 31)) & 1u;
-                status[where[k]] = ok ? FABGPU_ST_VALID : (oc ? FABGPU_ST_ERR_OFF_CURVE : FABGPU_ST_INVALID);
+                status[base + k] = ok ? FABGPU_ST_VALID : (oc ? FABGPU_ST_ERR_OFF_CURVE : FABGPU_ST_INVALID);
             }
-            where.clear();
-        }
+        });
     }
     return FABGPU_OK;
 }

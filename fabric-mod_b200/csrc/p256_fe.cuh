@@ -216,6 +216,69 @@ FAB_MUL_ATTR u256 fe_mul_dev(u256 a, u256 b)
     return fe_reduce(t);
 }
 
+// acc[0 .. 2*CNT) += (a[0], a[2], ..., a[2*(CNT-1)]) * b laid end to end; carry -> acc[2*CNT]
+template <int CNT>
+FAB_D void ptx_mad_chain(uint32_t* acc, const uint32_t* a, uint32_t b)
+{
+    asm volatile("mad.lo.cc.u32 %0, %2, %3, %0; madc.hi.cc.u32 %1, %2, %3, %1;" : "+r"(acc[0]), "+r"(acc[1]) : "r"(a[0]), "r"(b));
+#pragma unroll
+    for (int k = 1; k < CNT; k++)
+        asm volatile("madc.lo.cc.u32 %0, %2, %3, %0; madc.hi.cc.u32 %1, %2, %3, %1;" : "+r"(acc[2 * k]), "+r"(acc[2 * k + 1]) : "r"(a[2 * k]), "r"(b));
+    asm volatile("addc.u32 %0, %0, 0;" : "+r"(acc[2 * CNT]));
+}
+
+// t[0..15] = a * a with 36 products instead of 64: the 28 off-diagonal products a_i a_j (i < j) are accumulated once
+// (same even/odd 64-bit column scheme as mul_8x8), doubled, and the 8 squares a_i^2 are added in one carry chain.
+FAB_D void sqr_8(uint32_t* t, const uint32_t* a)
+{
+    uint32_t E[18], O[18];
+#pragma unroll
+    for (int i = 0; i < 18; i++) { E[i] = 0; O[i] = 0; }
+    // row i multiplies a_i by a_j, j > i.  Product a_i a_j sits at word i+j: even -> E[i+j], odd -> O[i+j-1].
+    // j = i+1, i+3, ... (i+j odd) and j = i+2, i+4, ... (i+j even) are each one chain of consecutive 64-bit slots.
+    ptx_mad_chain<4>(O + 0, a + 1, a[0]);   // j = 1,3,5,7  words 1,3,5,7
+    ptx_mad_chain<3>(E + 2, a + 2, a[0]);   // j = 2,4,6    words 2,4,6
+    ptx_mad_chain<3>(O + 2, a + 2, a[1]);   // j = 2,4,6    words 3,5,7
+    ptx_mad_chain<3>(E + 4, a + 3, a[1]);   // j = 3,5,7    words 4,6,8
+    ptx_mad_chain<3>(O + 4, a + 3, a[2]);   // j = 3,5,7    words 5,7,9
+    ptx_mad_chain<2>(E + 6, a + 4, a[2]);   // j = 4,6      words 6,8
+    ptx_mad_chain<2>(O + 6, a + 4, a[3]);   // j = 4,6      words 7,9
+    ptx_mad_chain<2>(E + 8, a + 5, a[3]);   // j = 5,7      words 8,10
+    ptx_mad_chain<2>(O + 8, a + 5, a[4]);   // j = 5,7      words 9,11
+    ptx_mad_chain<1>(E + 10, a + 6, a[4]);  // j = 6        word 10
+    ptx_mad_chain<1>(O + 10, a + 6, a[5]);  // j = 6        word 11
+    ptx_mad_chain<1>(E + 12, a + 7, a[5]);  // j = 7        word 12
+    ptx_mad_chain<1>(O + 12, a + 7, a[6]);  // j = 7        word 13
+    // merge: off = E + (O << 32)   (word 0 is empty, word 15 at most a carry)
+    uint32_t off[16];
+    off[0] = 0;
+    off[1] = O[0];
+    off[2] = ptx_add_cc(E[2], O[1]);
+#pragma unroll
+    for (int i = 3; i < 16; i++) off[i] = ptx_addc_cc(E[i], O[i - 1]);
+    // double
+#pragma unroll
+    for (int i = 15; i > 0; i--) off[i] = (off[i] << 1) | (off[i - 1] >> 31);
+    // add the squares: a_i^2 at words 2i, 2i+1, one chain across all 16 words
+    t[0] = a[0] * a[0];
+    asm volatile("mad.hi.cc.u32 %0, %1, %1, %2;" : "=r"(t[1]) : "r"(a[0]), "r"(off[1]));
+#pragma unroll
+    for (int i = 1; i < 8; i++) {
+        asm volatile("madc.lo.cc.u32 %0, %1, %1, %2;" : "=r"(t[2 * i]) : "r"(a[i]), "r"(off[2 * i]));
+        asm volatile("madc.hi.cc.u32 %0, %1, %1, %2;" : "=r"(t[2 * i + 1]) : "r"(a[i]), "r"(off[2 * i + 1]));
+    }
+}
+
+#ifndef FAB_SQR
+#define FAB_SQR 1
+#endif
+FAB_MUL_ATTR u256 fe_sqr_dev(u256 a)
+{
+    uint32_t t[16];
+    sqr_8(t, a.v);
+    return fe_reduce(t);
+}
+
 FAB_D u256 fe_add_dev(const u256& a, const u256& b)
 {
     uint32_t s[8];
@@ -338,7 +401,14 @@ FAB_HD u256 fe_mul(const u256& a, const u256& b)
     return hostimpl::mont_reduce(t, p, 1u);
 #endif
 }
-FAB_HD u256 fe_sqr(const u256& a) { return fe_mul(a, a); }
+FAB_HD u256 fe_sqr(const u256& a)
+{
+#if defined(__CUDA_ARCH__) && FAB_SQR
+    return fe_sqr_dev(a);
+#else
+    return fe_mul(a, a);
+#endif
+}
 FAB_HD u256 fe_add(const u256& a, const u256& b)
 {
 #if defined(__CUDA_ARCH__)

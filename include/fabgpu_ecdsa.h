@@ -111,7 +111,8 @@ int fabgpu_bccsp_verify(fabgpu_ctx* ctx, const uint8_t* key_xy, const uint8_t* s
 int fabgpu_gate_signature(const uint8_t* sig, size_t sig_len, uint8_t r_out[32], uint8_t s_out[32]);
 
 /* ---- test / bring-up hooks ------------------------------------------------------------------------------ */
-/* Device field primitives on arrays (op: 0 fe_mul, 1 fe_add, 2 fe_sub, 3 sc_mul, 4 fe_inv, 5 sc_inv_to_mont). */
+/* Device field primitives on arrays (op: 0 fe_mul, 1 fe_add, 2 fe_sub, 3 sc_mul, 4 fe_inv,
+ * 5 sc_inv_to_mont by Fermat, 6 the same by division steps, 7 fe_sqr). */
 int fabgpu_test_fieldop(fabgpu_ctx* ctx, int op, const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out);
 /* Copies the device fixed-base table (entries x 64 bytes, Montgomery little-endian limbs) to `out`; returns the
  * byte size needed when out == NULL. */

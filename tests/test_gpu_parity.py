@@ -66,6 +66,15 @@ def test_field_primitives(ctx):
     a = [rnd.randrange(1, N) for _ in range(64)] + [1, N - 1, p256.HALF_N]
     A = np.stack([be32(x) for x in a])
     assert _ints(ctx.test_fieldop(5, A, A)) == [pow(x, -1, N) * R % N for x in a]
+    # division-step inversion (p256_modinv.cuh) on a wider sample, incl. small and structured values
+    a = [rnd.randrange(1, N) for _ in range(4000)] + [1, 2, 3, N - 1, N - 2, p256.HALF_N, 1 << 30, (1 << 30) - 1, 1 << 255] + \
+        [rnd.getrandbits(k) or 1 for k in range(1, 256)]
+    A = np.stack([be32(x) for x in a])
+    assert _ints(ctx.test_fieldop(6, A, A)) == [pow(x, -1, N) * R % N for x in a]
+    # dedicated squaring
+    a, _ = _operands(P, rnd, 4000)
+    A = np.stack([be32(x) for x in a])
+    assert _ints(ctx.test_fieldop(7, A, A)) == [x * x * rinv % P for x in a]
 
 
 def test_fixed_base_table(ctx):
