@@ -19,6 +19,8 @@ EXPORTS = [
     "fabgpu_host_buffers", "fabgpu_verify_p256", "fabgpu_verify_p256_async", "fabgpu_wait", "fabgpu_verify_p256_host",
     "fabgpu_verify_p256_device", "fabgpu_bccsp_verify_batch", "fabgpu_bccsp_verify", "fabgpu_gate_signature",
     "fabgpu_test_fieldop", "fabgpu_test_gtable", "fabgpu_launch_count",
+    "fabgpu_keys_register", "fabgpu_key_slot_capacity", "fabgpu_host_key_slots", "fabgpu_verify_p256_keyed",
+    "fabgpu_verify_p256_keyed_async", "fabgpu_verify_p256_device_keyed",
 ]
 
 
@@ -152,6 +154,34 @@ class Context:
         self._ck(lib().fabgpu_verify_p256_device(self._h, ctypes.c_int(dev_index), ctypes.c_void_p(d_qx), ctypes.c_void_p(d_qy),
                                                  ctypes.c_void_p(d_e), ctypes.c_void_p(d_r), ctypes.c_void_p(d_s), ctypes.c_size_t(n),
                                                  ctypes.c_void_p(d_mask), ctypes.c_void_p(d_off), ctypes.c_void_p(stream)))
+
+    # ---- per-key tables ---------------------------------------------------------------------------------
+    def keys_register(self, keys_xy):
+        """uint8[K,64] -> int32[K] table slots (-1 = no table)."""
+        keys_xy = np.ascontiguousarray(keys_xy, dtype=np.uint8).reshape(-1, 64)
+        slots = np.full(keys_xy.shape[0], -1, np.int32)
+        self._ck(lib().fabgpu_keys_register(self._h, _p(keys_xy), ctypes.c_int(keys_xy.shape[0]), _p(slots)))
+        return slots
+
+    def key_slot_capacity(self):
+        return int(lib().fabgpu_key_slot_capacity(self._h))
+
+    def host_key_slots(self, slot=0):
+        p = ctypes.POINTER(ctypes.c_int32)()
+        self._ck(lib().fabgpu_host_key_slots(self._h, ctypes.c_int(slot), ctypes.byref(p)))
+        return np.ctypeslib.as_array(p, shape=(self.max_batch,))
+
+    def verify_p256_keyed(self, slot, n):
+        self._ck(lib().fabgpu_verify_p256_keyed(self._h, ctypes.c_int(slot), ctypes.c_size_t(n)))
+
+    def verify_p256_keyed_async(self, slot, n):
+        self._ck(lib().fabgpu_verify_p256_keyed_async(self._h, ctypes.c_int(slot), ctypes.c_size_t(n)))
+
+    def verify_p256_device_keyed(self, all_cached, d_key_slot, d_qx, d_qy, d_e, d_r, d_s, n, d_mask, d_off=0, stream=0, dev_index=0):
+        self._ck(lib().fabgpu_verify_p256_device_keyed(self._h, ctypes.c_int(dev_index), ctypes.c_int(1 if all_cached else 0),
+                                                       ctypes.c_void_p(d_key_slot), ctypes.c_void_p(d_qx), ctypes.c_void_p(d_qy),
+                                                       ctypes.c_void_p(d_e), ctypes.c_void_p(d_r), ctypes.c_void_p(d_s), ctypes.c_size_t(n),
+                                                       ctypes.c_void_p(d_mask), ctypes.c_void_p(d_off), ctypes.c_void_p(stream)))
 
     # ---- bccsp level ------------------------------------------------------------------------------------
     def bccsp_verify_batch(self, keys_xy, key_idx, digests, dig_off, sigs, sig_off):

@@ -38,23 +38,75 @@ __global__ void build_g_table_kernel(aff* gtab)
 
 // One signature per thread.  SoA inputs: n x 32 big-endian bytes each.  Output: bit i%32 of word i/32 is 1 iff
 // signature i is VALID; offcurve (optional) flags public keys that are not curve points.
+// key_slot (optional): signatures whose key has a precomputed table (slot >= 0) were decided by
+// ecdsa_verify_cached_kernel; this kernel skips them and ORs its bits into the words that kernel wrote.
 __global__ void __launch_bounds__(FAB_VERIFY_THREADS, FAB_VERIFY_MINBLOCKS)
-ecdsa_verify_kernel(const uint8_t* __restrict__ qx, const uint8_t* __restrict__ qy, const uint8_t* __restrict__ e,
-                    const uint8_t* __restrict__ r, const uint8_t* __restrict__ s, uint32_t n,
+ecdsa_verify_kernel(const int32_t* __restrict__ key_slot, const uint8_t* __restrict__ qx, const uint8_t* __restrict__ qy,
+                    const uint8_t* __restrict__ e, const uint8_t* __restrict__ r, const uint8_t* __restrict__ s, uint32_t n,
                     const aff* __restrict__ gtab, uint32_t* __restrict__ mask, uint32_t* __restrict__ offcurve)
 {
     const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t res = V_INVALID;
-    if (idx < n) {
+    if (idx < n && (key_slot == nullptr || key_slot[idx] < 0)) {
         const size_t o = (size_t)idx * 32;
         res = ecdsa_verify_one(load_be32(qx + o), load_be32(qy + o), load_be32(e + o), load_be32(r + o), load_be32(s + o), gtab);
     }
     const uint32_t vmask = __ballot_sync(0xffffffffu, res == V_VALID);
     const uint32_t omask = __ballot_sync(0xffffffffu, res == V_OFFCURVE);
     if ((threadIdx.x & 31u) == 0 && idx < n) {
-        mask[idx >> 5] = vmask;
-        if (offcurve) offcurve[idx >> 5] = omask;
+        if (key_slot) { mask[idx >> 5] |= vmask; if (offcurve) offcurve[idx >> 5] |= omask; }
+        else { mask[idx >> 5] = vmask; if (offcurve) offcurve[idx >> 5] = omask; }
     }
+}
+
+#ifndef FAB_CACHED_THREADS
+#define FAB_CACHED_THREADS 128
+#endif
+#ifndef FAB_CACHED_MINBLOCKS
+#define FAB_CACHED_MINBLOCKS 1
+#endif
+// Signatures whose public key has a precomputed window table: both scalar multiplications are fixed-base
+// (2 x FAB_G_WINDOWS mixed additions gathered from L2-resident tables, no doublings).  Slot < 0 -> bit 0, left to
+// ecdsa_verify_kernel.  qtab: key_slot_capacity tables of FAB_G_WINDOWS*FAB_G_ENTRIES affine points.
+__global__ void __launch_bounds__(FAB_CACHED_THREADS, FAB_CACHED_MINBLOCKS)
+ecdsa_verify_cached_kernel(const int32_t* __restrict__ key_slot, const uint8_t* __restrict__ e, const uint8_t* __restrict__ r,
+                           const uint8_t* __restrict__ s, uint32_t n, const aff* __restrict__ gtab, const aff* __restrict__ qtab,
+                           uint32_t* __restrict__ mask, uint32_t* __restrict__ offcurve)
+{
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t res = V_INVALID;
+    if (idx < n) {
+        const int32_t slot = key_slot[idx];
+        if (slot >= 0) {
+            const size_t o = (size_t)idx * 32;
+            res = ecdsa_verify_one_cached(qtab + (size_t)slot * (FAB_G_WINDOWS * FAB_G_ENTRIES), load_be32(e + o), load_be32(r + o),
+                                          load_be32(s + o), gtab);
+        }
+    }
+    const uint32_t vmask = __ballot_sync(0xffffffffu, res == V_VALID);
+    if ((threadIdx.x & 31u) == 0 && idx < n) {
+        mask[idx >> 5] = vmask;
+        if (offcurve) offcurve[idx >> 5] = 0u;
+    }
+}
+
+// Key-table build: thread t builds window (t % FAB_G_WINDOWS) of key (t / FAB_G_WINDOWS) into the key's slot.
+// flags[k] = 1 when key k is a curve point (its table is valid), 0 otherwise (nothing is written for it).
+__global__ void build_key_tables_kernel(const uint8_t* __restrict__ keys_xy, const int32_t* __restrict__ slots, int nkeys,
+                                        aff* __restrict__ qtab, u256* __restrict__ scratch, uint32_t* __restrict__ flags)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nkeys * FAB_G_WINDOWS) return;
+    const int k = t / FAB_G_WINDOWS, j = t % FAB_G_WINDOWS;
+    const u256 x = load_be32(keys_xy + 64 * (size_t)k), y = load_be32(keys_xy + 64 * (size_t)k + 32);
+    const u256 p = fe_p();
+    bool ok = u256_lt(x, p) && u256_lt(y, p);
+    aff q;
+    if (ok) { q.x = fe_to_mont(x); q.y = fe_to_mont(y); ok = aff_on_curve(q); }
+    if (j == 0) flags[k] = ok ? 1u : 0u;
+    if (!ok) return;
+    u256* zs = scratch + (size_t)t * 2 * FAB_G_ENTRIES;
+    build_key_window(q, j, qtab + ((size_t)slots[k] * FAB_G_WINDOWS + j) * FAB_G_ENTRIES, zs, zs + FAB_G_ENTRIES);
 }
 
 // Unit-test hook: out[i] = op(a[i], b[i]) on the device primitives (tests/test_gpu_field.py).

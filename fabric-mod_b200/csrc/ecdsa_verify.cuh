@@ -87,6 +87,28 @@ FAB_HD jac add_fixed_base(jac r, const u256& k, const aff* gtab)
     return r;
 }
 
+// Accept iff acc != infinity and acc.x mod n == r, without leaving Jacobian coordinates:
+// X == r' * Z^2 for r' in {r, r + n (only when r + n < p)}.
+FAB_HD uint32_t final_check(const jac& acc, const u256& r)
+{
+    if (jac_is_infinity(acc)) return V_INVALID;       // Go: x == 0 && y == 0 -> false
+    const u256 n = sc_n();
+    const u256 z2 = fe_sqr(acc.Z);
+    if (u256_eq(fe_mul(fe_to_mont(r), z2), acc.X)) return V_VALID;
+    if (u256_lt(r, p_minus_n())) {                    // x mod n == r also when x = r + n < p
+        u256 rn; uint32_t c = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const uint32_t a = r.v[i], b = n.v[i];
+            const uint32_t t = a + b; const uint32_t c1 = t < a;
+            const uint32_t t2 = t + c; const uint32_t c2 = t2 < t;
+            rn.v[i] = t2; c = c1 | c2;
+        }
+        if (u256_eq(fe_mul(fe_to_mont(rn), z2), acc.X)) return V_VALID;
+    }
+    return V_INVALID;
+}
+
 // All five inputs are plain 256-bit integers (e already formed by hashToInt: leftmost 32 digest bytes, left-padded).
 FAB_HD uint32_t ecdsa_verify_one(const u256& qx, const u256& qy, const u256& e, const u256& r, const u256& s, const aff* gtab)
 {
@@ -112,28 +134,44 @@ FAB_HD uint32_t ecdsa_verify_one(const u256& qx, const u256& qy, const u256& e, 
     build_q_table(tab, q);
     jac acc = scalar_mul_var(u2, tab);
     acc = add_fixed_base(acc, u1, gtab);
-    if (jac_is_infinity(acc)) return V_INVALID;       // Go: x == 0 && y == 0 -> false
+    return final_check(acc, r);
+}
 
-    const u256 z2 = fe_sqr(acc.Z);
-    if (u256_eq(fe_mul(fe_to_mont(r), z2), acc.X)) return V_VALID;
-    if (u256_lt(r, p_minus_n())) {                    // x mod n == r also when x = r + n < p
-        u256 rn; uint32_t c = 0;
+// Same verification when the public key has a precomputed window table (fabgpu_keys_register): u2*Q becomes
+// fixed-base too -- 2 x FAB_G_WINDOWS mixed additions in total, no doublings, no per-signature table.  The key was
+// checked to be a curve point when its table was built.
+FAB_HD uint32_t ecdsa_verify_one_cached(const aff* qtab, const u256& e, const u256& r, const u256& s, const aff* gtab)
+{
+    const u256 n = sc_n();
+    if (u256_is_zero(r) || u256_is_zero(s) || !u256_lt(r, n) || !u256_lt(s, n)) return V_INVALID;
+#if FAB_SAFEGCD
+    const u256 w = sc_inv_to_mont_safegcd(s);
+#else
+    const u256 w = sc_inv_to_mont(s);
+#endif
+    const u256 u1 = sc_mul(sc_reduce_once(e), w);
+    const u256 u2 = sc_mul(r, w);
+    uint32_t k1[8], k2[8];
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
-            const uint32_t a = r.v[i], b = n.v[i];
-            const uint32_t t = a + b; const uint32_t c1 = t < a;
-            const uint32_t t2 = t + c; const uint32_t c2 = t2 < t;
-            rn.v[i] = t2; c = c1 | c2;
+    for (int i = 0; i < 8; i++) { k1[i] = u1.v[i]; k2[i] = u2.v[i]; }
+    jac acc = jac_infinity();
+    for (int j = 0; j < FAB_G_WINDOWS; j++) {
+        const uint32_t d1 = k1[0] & (uint32_t)FAB_G_ENTRIES, d2 = k2[0] & (uint32_t)FAB_G_ENTRIES;
+#pragma unroll
+        for (int i = 0; i < 7; i++) {
+            k1[i] = (k1[i] >> FAB_WG) | (k1[i + 1] << (32 - FAB_WG));
+            k2[i] = (k2[i] >> FAB_WG) | (k2[i + 1] << (32 - FAB_WG));
         }
-        if (u256_eq(fe_mul(fe_to_mont(rn), z2), acc.X)) return V_VALID;
+        k1[7] >>= FAB_WG; k2[7] >>= FAB_WG;
+        if (d1) acc = jac_add_aff(acc, gtab[(size_t)j * FAB_G_ENTRIES + (d1 - 1)]);
+        if (d2) acc = jac_add_aff(acc, qtab[(size_t)j * FAB_G_ENTRIES + (d2 - 1)]);
     }
-    return V_INVALID;
+    return final_check(acc, r);
 }
 
 // Fixed-base table entry (window j, digit d in 1..FAB_G_ENTRIES) = d * 2^(FAB_WG*j) * G, affine Montgomery.
-FAB_HD aff g_table_entry(int j, uint32_t d)
+FAB_HD aff table_entry(const aff& g, int j, uint32_t d)
 {
-    aff g; g.x = fe_gx_mont(); g.y = fe_gy_mont();
     jac acc = jac_infinity();
     // scalar = d << (FAB_WG*j): MSB-first double-and-add over d's bits, then FAB_WG*j doublings
     for (int b = FAB_WG - 1; b >= 0; b--) {
@@ -142,6 +180,38 @@ FAB_HD aff g_table_entry(int j, uint32_t d)
     }
     for (int t = 0; t < FAB_WG * j; t++) acc = jac_double(acc);
     return jac_to_aff(acc);
+}
+// Window j of a key's table, built by ONE thread: out[d-1] = d * 2^(FAB_WG*j) * q for d = 1..FAB_G_ENTRIES.
+// Chain of mixed additions from the affine base 2^(FAB_WG*j) q, then one shared inversion for the whole window
+// (Montgomery's trick).  zs / ps: scratch of FAB_G_ENTRIES elements each.  ~6 100 field multiplications.
+FAB_HD void build_key_window(const aff& q, int j, aff* out, u256* zs, u256* ps)
+{
+    jac b = jac_from_aff(q);
+    for (int t = 0; t < FAB_WG * j; t++) b = jac_double(b);
+    const aff base = jac_to_aff(b);
+    jac t = jac_from_aff(base);
+    u256 run = fe_one();
+    for (int d = 1; d <= FAB_G_ENTRIES; d++) {
+        if (d > 1) t = jac_add_aff(t, base);
+        out[d - 1].x = t.X; out[d - 1].y = t.Y;
+        zs[d - 1] = t.Z;
+        run = fe_mul(run, t.Z);
+        ps[d - 1] = run;                       // z_1 * ... * z_d
+    }
+    u256 inv = fe_inv(run);
+    for (int d = FAB_G_ENTRIES; d >= 1; d--) {
+        const u256 zi = (d > 1) ? fe_mul(inv, ps[d - 2]) : inv;      // 1 / z_d
+        if (d > 1) inv = fe_mul(inv, zs[d - 1]);
+        const u256 zi2 = fe_sqr(zi);
+        out[d - 1].x = fe_mul(out[d - 1].x, zi2);
+        out[d - 1].y = fe_mul(out[d - 1].y, fe_mul(zi2, zi));
+    }
+}
+
+FAB_HD aff g_table_entry(int j, uint32_t d)
+{
+    aff g; g.x = fe_gx_mont(); g.y = fe_gy_mont();
+    return table_entry(g, j, d);
 }
 
 }  // namespace fabgpu

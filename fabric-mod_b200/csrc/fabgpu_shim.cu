@@ -14,6 +14,7 @@
 #include <mutex>
 #include <string>
 #include <thread>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/fabgpu_ecdsa.h"
@@ -31,11 +32,13 @@ struct DevSlot {
     uint8_t* d_in[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // qx qy e r s
     uint32_t* d_mask = nullptr;
     uint32_t* d_off = nullptr;
+    int32_t* d_key_slot = nullptr;
 };
 
 struct Device {
     int id = 0;
     aff* gtab = nullptr;
+    aff* qtab = nullptr;      // key_slots tables of FAB_G_WINDOWS * FAB_G_ENTRIES points (per-key fixed-base tables)
     DevSlot slot[FABGPU_SLOTS];
 };
 
@@ -43,6 +46,7 @@ struct HostSlot {
     uint8_t* h_in[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     uint32_t* h_mask = nullptr;
     uint32_t* h_off = nullptr;
+    int32_t* h_key_slot = nullptr;
 };
 
 }  // namespace
@@ -105,6 +109,13 @@ struct fabgpu_ctx {
     std::mutex mu;         // guards enqueue/wait
     std::mutex slot0_mu;   // serialises the composite calls that stage through slot 0's pinned buffers
     std::atomic<unsigned long long> launches{0};
+    // per-key table cache (fabgpu_keys_register): 64-byte X||Y -> slot, least-recently-used eviction
+    int key_slots = 0;
+    std::unordered_map<std::string, int> key_map;
+    std::vector<std::string> slot_key;
+    std::vector<unsigned long long> slot_tick;
+    unsigned long long tick = 0;
+    int key_min_uses = 32;
 };
 
 namespace {
@@ -128,18 +139,38 @@ bool fault_injected()
 
 size_t round_up32(size_t x) { return (x + 31) / 32 * 32; }
 
-int launch_verify(fabgpu_ctx* ctx, const uint8_t* qx, const uint8_t* qy, const uint8_t* e, const uint8_t* r,
-                  const uint8_t* s, size_t n, const aff* gtab, uint32_t* mask, uint32_t* off, cudaStream_t st)
+// mode: 0 = no signature has a key table (generic kernel only), 1 = all have one (cached kernel only),
+//       2 = mixed (cached kernel, then the generic kernel fills in the rest)
+enum { MODE_GENERIC = 0, MODE_CACHED = 1, MODE_MIXED = 2 };
+
+int launch_verify(fabgpu_ctx* ctx, const Device& dv, int mode, const int32_t* key_slot, const uint8_t* qx, const uint8_t* qy,
+                  const uint8_t* e, const uint8_t* r, const uint8_t* s, size_t n, uint32_t* mask, uint32_t* off, cudaStream_t st)
 {
     if (n == 0) return FABGPU_OK;
-    const unsigned blocks = (unsigned)((n + FAB_VERIFY_THREADS - 1) / FAB_VERIFY_THREADS);
-    ecdsa_verify_kernel<<<blocks, FAB_VERIFY_THREADS, 0, st>>>(qx, qy, e, r, s, (uint32_t)n, gtab, mask, off);
-    ctx->launches++;
-    CK(ctx, cudaGetLastError());
+    if (mode != MODE_GENERIC) {
+        const unsigned blocks = (unsigned)((n + FAB_CACHED_THREADS - 1) / FAB_CACHED_THREADS);
+        ecdsa_verify_cached_kernel<<<blocks, FAB_CACHED_THREADS, 0, st>>>(key_slot, e, r, s, (uint32_t)n, dv.gtab, dv.qtab, mask, off);
+        ctx->launches++;
+        CK(ctx, cudaGetLastError());
+    }
+    if (mode != MODE_CACHED) {
+        const unsigned blocks = (unsigned)((n + FAB_VERIFY_THREADS - 1) / FAB_VERIFY_THREADS);
+        ecdsa_verify_kernel<<<blocks, FAB_VERIFY_THREADS, 0, st>>>(mode == MODE_MIXED ? key_slot : nullptr, qx, qy, e, r, s, (uint32_t)n,
+                                                                   dv.gtab, mask, off);
+        ctx->launches++;
+        CK(ctx, cudaGetLastError());
+    }
     return FABGPU_OK;
 }
 
-int enqueue_slot(fabgpu_ctx* ctx, int slot, size_t n)
+int slots_mode(const int32_t* ks, size_t n)
+{
+    bool any_c = false, any_g = false;
+    for (size_t i = 0; i < n; i++) { if (ks[i] >= 0) any_c = true; else any_g = true; }
+    return any_c ? (any_g ? MODE_MIXED : MODE_CACHED) : MODE_GENERIC;
+}
+
+int enqueue_slot(fabgpu_ctx* ctx, int slot, size_t n, bool keyed)
 {
     // contiguous 32-aligned ranges per device
     const size_t ndev = ctx->devs.size();
@@ -152,9 +183,13 @@ int enqueue_slot(fabgpu_ctx* ctx, int slot, size_t n)
         DevSlot& ds = dv.slot[slot];
         HostSlot& hs = ctx->hslot[slot];
         CK(ctx, cudaSetDevice(dv.id));
-        for (int a = 0; a < 5; a++)
+        const int mode = keyed ? slots_mode(hs.h_key_slot + begin, cnt) : MODE_GENERIC;
+        for (int a = (mode == MODE_CACHED ? 2 : 0); a < 5; a++)            // an all-cached range needs no Qx/Qy on the device
             CK(ctx, cudaMemcpyAsync(ds.d_in[a], hs.h_in[a] + 32 * begin, 32 * cnt, cudaMemcpyHostToDevice, ds.stream));
-        int rc = launch_verify(ctx, ds.d_in[0], ds.d_in[1], ds.d_in[2], ds.d_in[3], ds.d_in[4], cnt, dv.gtab, ds.d_mask, ds.d_off, ds.stream);
+        if (mode != MODE_GENERIC)
+            CK(ctx, cudaMemcpyAsync(ds.d_key_slot, hs.h_key_slot + begin, 4 * cnt, cudaMemcpyHostToDevice, ds.stream));
+        int rc = launch_verify(ctx, dv, mode, ds.d_key_slot, ds.d_in[0], ds.d_in[1], ds.d_in[2], ds.d_in[3], ds.d_in[4], cnt, ds.d_mask,
+                               ds.d_off, ds.stream);
         if (rc) return rc;
         const size_t words = (cnt + 31) / 32;
         CK(ctx, cudaMemcpyAsync(hs.h_mask + begin / 32, ds.d_mask, 4 * words, cudaMemcpyDeviceToHost, ds.stream));
@@ -177,7 +212,9 @@ void free_all(fabgpu_ctx* ctx)
     for (auto& dv : ctx->devs) {
         cudaSetDevice(dv.id);
         if (dv.gtab) cudaFree(dv.gtab);
+        if (dv.qtab) cudaFree(dv.qtab);
         for (auto& ds : dv.slot) {
+            if (ds.d_key_slot) cudaFree(ds.d_key_slot);
             for (auto& p : ds.d_in) if (p) cudaFree(p);
             if (ds.d_mask) cudaFree(ds.d_mask);
             if (ds.d_off) cudaFree(ds.d_off);
@@ -188,6 +225,7 @@ void free_all(fabgpu_ctx* ctx)
         for (auto& p : hs.h_in) if (p) cudaFreeHost(p);
         if (hs.h_mask) cudaFreeHost(hs.h_mask);
         if (hs.h_off) cudaFreeHost(hs.h_off);
+        if (hs.h_key_slot) cudaFreeHost(hs.h_key_slot);
     }
 }
 
@@ -212,6 +250,12 @@ int init_impl(fabgpu_ctx* ctx, const int* device_ids, int n_dev, size_t max_batc
         const char* ev = getenv("FABGPU_GATE_THREADS");
         int want = ev ? atoi(ev) : std::min(hw > 0 ? hw : 1, 16);
         ctx->pool.reset(new GatePool(want));
+        const char* ks = getenv("FABGPU_KEY_SLOTS");          // per-key tables are 510 KiB each, per device
+        ctx->key_slots = ks ? std::max(1, atoi(ks)) : 256;
+        ctx->slot_key.assign(ctx->key_slots, std::string());
+        ctx->slot_tick.assign(ctx->key_slots, 0ull);
+        const char* mu = getenv("FABGPU_KEY_MIN_USES");
+        ctx->key_min_uses = mu ? atoi(mu) : 32;
     }
     ctx->dev_cap = round_up32((max_batch + ids.size() - 1) / ids.size());
     ctx->devs.resize(ids.size());
@@ -222,11 +266,13 @@ int init_impl(fabgpu_ctx* ctx, const int* device_ids, int n_dev, size_t max_batc
         dv.id = ids[d];
         CK(ctx, cudaSetDevice(dv.id));
         CK(ctx, cudaMalloc(&dv.gtab, tab_entries * sizeof(aff)));
+        CK(ctx, cudaMalloc(&dv.qtab, (size_t)ctx->key_slots * tab_entries * sizeof(aff)));
         for (auto& ds : dv.slot) {
             CK(ctx, cudaStreamCreateWithFlags(&ds.stream, cudaStreamNonBlocking));
             for (auto& p : ds.d_in) CK(ctx, cudaMalloc(&p, 32 * ctx->dev_cap));
             CK(ctx, cudaMalloc(&ds.d_mask, 4 * words));
             CK(ctx, cudaMalloc(&ds.d_off, 4 * words));
+            CK(ctx, cudaMalloc(&ds.d_key_slot, 4 * ctx->dev_cap));
         }
         build_g_table_kernel<<<(unsigned)((tab_entries + 63) / 64), 64, 0, dv.slot[0].stream>>>(dv.gtab);
         ctx->launches++;
@@ -237,6 +283,8 @@ int init_impl(fabgpu_ctx* ctx, const int* device_ids, int n_dev, size_t max_batc
         for (auto& p : hs.h_in) CK(ctx, cudaHostAlloc(&p, 32 * round_up32(max_batch), cudaHostAllocPortable));
         CK(ctx, cudaHostAlloc(&hs.h_mask, 4 * hwords, cudaHostAllocPortable));
         CK(ctx, cudaHostAlloc(&hs.h_off, 4 * hwords, cudaHostAllocPortable));
+        CK(ctx, cudaHostAlloc(&hs.h_key_slot, 4 * round_up32(max_batch), cudaHostAllocPortable));
+        for (size_t i = 0; i < round_up32(max_batch); i++) hs.h_key_slot[i] = -1;
     }
     for (auto& dv : ctx->devs) {
         CK(ctx, cudaSetDevice(dv.id));
@@ -293,13 +341,89 @@ int fabgpu_host_buffers(fabgpu_ctx* ctx, int slot, uint8_t** qx, uint8_t** qy, u
     return FABGPU_OK;
 }
 
-int fabgpu_verify_p256_async(fabgpu_ctx* ctx, int slot, size_t n)
+static int verify_async_impl(fabgpu_ctx* ctx, int slot, size_t n, bool keyed)
 {
     if (!ctx || slot < 0 || slot >= FABGPU_SLOTS) return FABGPU_E_ARG;
     std::lock_guard<std::mutex> lk(ctx->mu);
     if (n > ctx->max_batch) { ctx->last_error = "n exceeds max_batch"; return FABGPU_E_ARG; }
     if (fault_injected()) { ctx->last_error = "fault injected (FABGPU_FAULT_INJECT=1)"; return FABGPU_E_INJECTED; }
-    return enqueue_slot(ctx, slot, n);
+    return enqueue_slot(ctx, slot, n, keyed);
+}
+
+int fabgpu_verify_p256_async(fabgpu_ctx* ctx, int slot, size_t n) { return verify_async_impl(ctx, slot, n, false); }
+int fabgpu_verify_p256_keyed_async(fabgpu_ctx* ctx, int slot, size_t n) { return verify_async_impl(ctx, slot, n, true); }
+
+int fabgpu_verify_p256_keyed(fabgpu_ctx* ctx, int slot, size_t n)
+{
+    int rc = fabgpu_verify_p256_keyed_async(ctx, slot, n);
+    if (rc) return rc;
+    return fabgpu_wait(ctx, slot);
+}
+
+int fabgpu_host_key_slots(fabgpu_ctx* ctx, int slot, int32_t** key_slot)
+{
+    if (!ctx || slot < 0 || slot >= FABGPU_SLOTS || !key_slot) return FABGPU_E_ARG;
+    *key_slot = ctx->hslot[slot].h_key_slot;
+    return FABGPU_OK;
+}
+
+int fabgpu_key_slot_capacity(const fabgpu_ctx* ctx) { return ctx ? ctx->key_slots : 0; }
+
+// Looks the keys up in the table cache and builds tables for the missing ones (one launch per device for the whole set).
+int fabgpu_keys_register(fabgpu_ctx* ctx, const uint8_t* keys_xy, int K, int32_t* slots_out)
+{
+    if (!ctx || K < 0 || (K && (!keys_xy || !slots_out))) return FABGPU_E_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    std::vector<int> fresh;                      // indices into keys_xy that need a table
+    std::vector<int32_t> fresh_slot;
+    std::vector<char> slot_taken(ctx->key_slots, 0);
+    ctx->tick++;
+    for (int k = 0; k < K; k++) {
+        std::string key((const char*)keys_xy + 64 * (size_t)k, 64);
+        auto it = ctx->key_map.find(key);
+        if (it != ctx->key_map.end()) { slots_out[k] = it->second; ctx->slot_tick[it->second] = ctx->tick; slot_taken[it->second] = 1; continue; }
+        // least recently used slot that this call has not touched
+        int best = -1;
+        for (int sl = 0; sl < ctx->key_slots; sl++)
+            if (!slot_taken[sl] && (best < 0 || ctx->slot_tick[sl] < ctx->slot_tick[best])) best = sl;
+        if (best < 0) { slots_out[k] = -1; continue; }            // more distinct keys in one call than slots: stays generic
+        if (!ctx->slot_key[best].empty()) ctx->key_map.erase(ctx->slot_key[best]);
+        ctx->slot_key[best] = key; ctx->key_map[key] = best; ctx->slot_tick[best] = ctx->tick; slot_taken[best] = 1;
+        slots_out[k] = best;
+        fresh.push_back(k); fresh_slot.push_back(best);
+    }
+    if (fresh.empty()) return FABGPU_OK;
+    const int F = (int)fresh.size();
+    std::vector<uint8_t> fk(64 * (size_t)F);
+    for (int i = 0; i < F; i++) memcpy(fk.data() + 64 * (size_t)i, keys_xy + 64 * (size_t)fresh[i], 64);
+    std::vector<uint32_t> flags(F, 0);
+    for (auto& dv : ctx->devs) {
+        CK(ctx, cudaSetDevice(dv.id));
+        // an evicted slot's table may still be read by a batch in flight: drain this device first (registration is rare)
+        for (auto& ds : dv.slot) CK(ctx, cudaStreamSynchronize(ds.stream));
+        uint8_t* d_keys = nullptr; int32_t* d_slots = nullptr; uint32_t* d_flags = nullptr; u256* d_scratch = nullptr;
+        const size_t threads = (size_t)F * FAB_G_WINDOWS;
+        CK(ctx, cudaMalloc(&d_keys, fk.size()));
+        CK(ctx, cudaMalloc(&d_slots, 4 * (size_t)F));
+        CK(ctx, cudaMalloc(&d_flags, 4 * (size_t)F));
+        CK(ctx, cudaMalloc(&d_scratch, threads * 2 * FAB_G_ENTRIES * sizeof(u256)));
+        CK(ctx, cudaMemcpy(d_keys, fk.data(), fk.size(), cudaMemcpyHostToDevice));
+        CK(ctx, cudaMemcpy(d_slots, fresh_slot.data(), 4 * (size_t)F, cudaMemcpyHostToDevice));
+        build_key_tables_kernel<<<(unsigned)((threads + 31) / 32), 32, 0, dv.slot[0].stream>>>(d_keys, d_slots, F, dv.qtab, d_scratch, d_flags);
+        ctx->launches++;
+        CK(ctx, cudaGetLastError());
+        CK(ctx, cudaStreamSynchronize(dv.slot[0].stream));
+        CK(ctx, cudaMemcpy(flags.data(), d_flags, 4 * (size_t)F, cudaMemcpyDeviceToHost));
+        cudaFree(d_keys); cudaFree(d_slots); cudaFree(d_flags); cudaFree(d_scratch);
+    }
+    for (int i = 0; i < F; i++) {
+        if (flags[i]) continue;                   // not a curve point: no table; the generic kernel reports it as off-curve
+        const int sl = fresh_slot[i];
+        ctx->key_map.erase(ctx->slot_key[sl]);
+        ctx->slot_key[sl].clear(); ctx->slot_tick[sl] = 0;
+        slots_out[fresh[i]] = -1;
+    }
+    return FABGPU_OK;
 }
 
 int fabgpu_wait(fabgpu_ctx* ctx, int slot)
@@ -342,8 +466,23 @@ int fabgpu_verify_p256_device(fabgpu_ctx* ctx, int dev_index, const void* d_qx, 
     Device& dv = ctx->devs[dev_index];
     CK(ctx, cudaSetDevice(dv.id));
     cudaStream_t st = (cudaStream_t)cuda_stream;   // NULL is CUDA's default stream, exactly as in the runtime API
-    return launch_verify(ctx, (const uint8_t*)d_qx, (const uint8_t*)d_qy, (const uint8_t*)d_e, (const uint8_t*)d_r,
-                         (const uint8_t*)d_s, n, dv.gtab, (uint32_t*)d_mask, (uint32_t*)d_offcurve, st);
+    return launch_verify(ctx, dv, MODE_GENERIC, nullptr, (const uint8_t*)d_qx, (const uint8_t*)d_qy, (const uint8_t*)d_e,
+                         (const uint8_t*)d_r, (const uint8_t*)d_s, n, (uint32_t*)d_mask, (uint32_t*)d_offcurve, st);
+}
+
+int fabgpu_verify_p256_device_keyed(fabgpu_ctx* ctx, int dev_index, int all_cached, const void* d_key_slot, const void* d_qx,
+                                    const void* d_qy, const void* d_e, const void* d_r, const void* d_s, size_t n, void* d_mask,
+                                    void* d_offcurve, void* cuda_stream)
+{
+    if (!ctx || dev_index < 0 || dev_index >= (int)ctx->devs.size()) return FABGPU_E_ARG;
+    if (n && (!d_key_slot || !d_e || !d_r || !d_s || !d_mask)) return FABGPU_E_ARG;
+    if (n && !all_cached && (!d_qx || !d_qy)) return FABGPU_E_ARG;
+    if (fault_injected()) { ctx->last_error = "fault injected (FABGPU_FAULT_INJECT=1)"; return FABGPU_E_INJECTED; }
+    Device& dv = ctx->devs[dev_index];
+    CK(ctx, cudaSetDevice(dv.id));
+    return launch_verify(ctx, dv, all_cached ? MODE_CACHED : MODE_MIXED, (const int32_t*)d_key_slot, (const uint8_t*)d_qx,
+                         (const uint8_t*)d_qy, (const uint8_t*)d_e, (const uint8_t*)d_r, (const uint8_t*)d_s, n, (uint32_t*)d_mask,
+                         (uint32_t*)d_offcurve, (cudaStream_t)cuda_stream);
 }
 
 int fabgpu_gate_signature(const uint8_t* sig, size_t sig_len, uint8_t r_out[32], uint8_t s_out[32])
@@ -363,6 +502,23 @@ int fabgpu_bccsp_verify_batch(fabgpu_ctx* ctx, const uint8_t* keys_xy, int K, co
     // no compaction and stays parallel.
     std::lock_guard<std::mutex> lk0(ctx->slot0_mu);
     HostSlot& hs = ctx->hslot[0];
+    // Keys that recur (>= key_min_uses signatures in this call) or already own a table use the fixed-base kernel;
+    // this is what KeyImport does once per identity in the Go provider.
+    std::vector<int32_t> slot_of(K > 0 ? K : 0, -1);
+    if (K > 0 && keys_xy && ctx->key_min_uses >= 0) {
+        std::vector<uint32_t> uses(K, 0);
+        for (size_t i = 0; i < n; i++) if (key_idx[i] >= 0 && key_idx[i] < K) uses[key_idx[i]]++;
+        std::vector<int> want;
+        for (int k = 0; k < K; k++) if (uses[k] >= (uint32_t)ctx->key_min_uses && uses[k] > 0) want.push_back(k);
+        if (!want.empty() && (int)want.size() <= ctx->key_slots) {
+            std::vector<uint8_t> wk(64 * want.size());
+            std::vector<int32_t> ws(want.size(), -1);
+            for (size_t i = 0; i < want.size(); i++) memcpy(wk.data() + 64 * i, keys_xy + 64 * (size_t)want[i], 64);
+            int rc = fabgpu_keys_register(ctx, wk.data(), (int)want.size(), ws.data());
+            if (rc) return rc;
+            for (size_t i = 0; i < want.size(); i++) slot_of[want[i]] = ws[i];
+        }
+    }
     for (size_t base = 0; base < n; base += ctx->max_batch) {
         const size_t cnt = std::min(ctx->max_batch, n - base);
         const int T = ctx->pool->size();
@@ -393,12 +549,13 @@ int fabgpu_bccsp_verify_batch(fabgpu_ctx* ctx, const uint8_t* keys_xy, int K, co
                     }
                 }
                 if (st != FABGPU_ST_VALID) { memset(hs.h_in[3] + 32 * k, 0, 32); memset(hs.h_in[4] + 32 * k, 0, 32); }
+                hs.h_key_slot[k] = (st == FABGPU_ST_VALID) ? slot_of[ki] : -1;
                 status[i] = st;
             }
             asked += mine;
         });
         if (asked.load() == 0) continue;
-        int rc = fabgpu_verify_p256(ctx, 0, cnt);
+        int rc = fabgpu_verify_p256_keyed(ctx, 0, cnt);
         if (rc) return rc;
         ctx->pool->run([&](int tid) {
             const size_t b = cnt * (size_t)tid / T, e = cnt * (size_t)(tid + 1) / T;

@@ -93,11 +93,32 @@ int fabgpu_verify_p256_device(fabgpu_ctx* ctx, int dev_index, const void* d_qx, 
                               const void* d_r, const void* d_s, size_t n, void* d_mask, void* d_offcurve,
                               void* cuda_stream);
 
+/* ---- per-key fixed-base tables (what KeyImport does once per identity) -----------
+ * Identities repeat heavily in Fabric (the reference caches them: msp/cache/cache.go:38-129; keys are imported once,
+ * bccsp/sw/keyimport.go:114-134, msp/mspimpl.go:420).  A registered key gets a window table on every device of the
+ * context, after which u2*Q is fixed-base like u1*G.  Results are identical to the generic kernel; only speed differs. */
+
+/* Looks up / builds tables for K keys (X||Y, 64 bytes each).  slots_out[k] >= 0 is the key's slot; -1 means "no table"
+ * (not a curve point, or more distinct keys than fabgpu_key_slot_capacity in one call) -- such signatures simply take
+ * the generic kernel.  Least-recently-used slots are recycled.  Capacity: env FABGPU_KEY_SLOTS (default 256). */
+int fabgpu_keys_register(fabgpu_ctx* ctx, const uint8_t* keys_xy, int K, int32_t* slots_out);
+int fabgpu_key_slot_capacity(const fabgpu_ctx* ctx);
+/* Pinned int32[max_batch] of one slot: key_slot[i] = table slot of signature i's key, or -1.  Only the _keyed entry
+ * points read it; a stale value would verify against the wrong key, so callers overwrite all n entries per batch. */
+int fabgpu_host_key_slots(fabgpu_ctx* ctx, int slot, int32_t** key_slot);
+int fabgpu_verify_p256_keyed(fabgpu_ctx* ctx, int slot, size_t n);
+int fabgpu_verify_p256_keyed_async(fabgpu_ctx* ctx, int slot, size_t n);
+/* Device-resident form.  all_cached != 0 promises every d_key_slot[i] >= 0 (d_qx/d_qy may then be NULL). */
+int fabgpu_verify_p256_device_keyed(fabgpu_ctx* ctx, int dev_index, int all_cached, const void* d_key_slot, const void* d_qx,
+                                    const void* d_qy, const void* d_e, const void* d_r, const void* d_s, size_t n,
+                                    void* d_mask, void* d_offcurve, void* cuda_stream);
+
 /* ---- bccsp level: raw DER signatures + digests + keys -> three-valued status (sw.CSP.Verify semantics) -- */
 
 /* keys_xy: K x 64 bytes (X || Y, big-endian).  key_idx[i] in [0,K), or < 0 for a nil key.  digests / sigs are
  * concatenations indexed by (n+1)-entry offset tables.  status[i] receives FABGPU_ST_*.  The host gates (DER per
- * Go encoding/asn1, positivity, low-S, r < 2^256) run on the CPU; survivors are verified on the GPU. */
+ * Go encoding/asn1, positivity, low-S, r < 2^256) run on the CPU; survivors are verified on the GPU.  Keys used by at
+ * least FABGPU_KEY_MIN_USES (env, default 32; negative disables) signatures of the call are registered automatically. */
 int fabgpu_bccsp_verify_batch(fabgpu_ctx* ctx, const uint8_t* keys_xy, int K, const int32_t* key_idx,
                               const uint8_t* digests, const uint32_t* dig_off, const uint8_t* sigs,
                               const uint32_t* sig_off, size_t n, uint8_t* status);

@@ -5,6 +5,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <vector>
+#include <utility>
 #include "../../fabric-mod_b200/csrc/ecdsa_verify.cuh"
 
 using namespace fabgpu;
@@ -39,6 +40,36 @@ void hostsim_verify_batch(const uint8_t* qx, const uint8_t* qy, const uint8_t* e
         size_t o = 32 * (size_t)i;
         out[i] = (uint8_t)ecdsa_verify_one(u256_from_be(qx + o), u256_from_be(qy + o), u256_from_be(e + o),
                                            u256_from_be(r + o), u256_from_be(s + o), g_tab.data());
+    }
+}
+
+// Same batch through the per-key-table path: one table per distinct key (built with build_key_window, as the device's
+// build_key_tables_kernel does), then ecdsa_verify_one_cached.  Keys that are not curve points are reported V_OFFCURVE.
+void hostsim_verify_batch_cached(const uint8_t* qx, const uint8_t* qy, const uint8_t* e, const uint8_t* r, const uint8_t* s, int n, uint8_t* out)
+{
+    hostsim_build_gtable();
+    std::vector<std::pair<std::vector<uint8_t>, std::vector<aff>>> cache;
+    std::vector<u256> zs(2 * FAB_G_ENTRIES);
+    for (int i = 0; i < n; i++) {
+        size_t o = 32 * (size_t)i;
+        std::vector<uint8_t> key(qx + o, qx + o + 32);
+        key.insert(key.end(), qy + o, qy + o + 32);
+        const std::vector<aff>* tab = nullptr;
+        for (auto& c : cache) if (c.first == key) tab = &c.second;
+        if (!tab) {
+            const u256 x = u256_from_be(qx + o), y = u256_from_be(qy + o);
+            aff q; bool ok = u256_lt(x, fe_p()) && u256_lt(y, fe_p());
+            if (ok) { q.x = fe_to_mont(x); q.y = fe_to_mont(y); ok = aff_on_curve(q); }
+            std::vector<aff> t;
+            if (ok) {
+                t.resize((size_t)FAB_G_WINDOWS * FAB_G_ENTRIES);
+                for (int j = 0; j < FAB_G_WINDOWS; j++) build_key_window(q, j, t.data() + (size_t)j * FAB_G_ENTRIES, zs.data(), zs.data() + FAB_G_ENTRIES);
+            }
+            cache.emplace_back(key, std::move(t));
+            tab = &cache.back().second;
+        }
+        if (tab->empty()) { out[i] = (uint8_t)V_OFFCURVE; continue; }
+        out[i] = (uint8_t)ecdsa_verify_one_cached(tab->data(), u256_from_be(e + o), u256_from_be(r + o), u256_from_be(s + o), g_tab.data());
     }
 }
 

@@ -255,3 +255,96 @@ def test_device_resident_entry_with_torch_stream(ctx):
     ctx.verify_p256_device(*[x.data_ptr() for x in t], w.n, mask.data_ptr(), 0, st.cuda_stream)
     st.synchronize()
     assert (mask.cpu().numpy().view(np.uint32) == exp).all()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# per-key fixed-base tables (fabgpu_keys_register + the _keyed entry points)
+# ---------------------------------------------------------------------------------------------------------
+def _fill(ctx, slot, w, key_slots):
+    hb = ctx.host_buffers(slot)
+    for name, arr in (("qx", w.qx()), ("qy", w.qy()), ("e", w.digest), ("r", w.r), ("s", w.s)):
+        hb[name][: w.n] = arr
+    ctx.host_key_slots(slot)[: w.n] = key_slots
+    return hb
+
+
+def test_key_tables_all_cached_and_mixed(ctx):
+    w = workload.Workload(16384, 32, seed=41)
+    w.tamper_r(0.05)
+    exp = fast.valid_mask(fast.verify_batch(w.keys_xy, w.key_idx, w.digest, w.dig_off(), w.sigs, w.sig_off, nthreads=8))
+    slots = ctx.keys_register(w.keys_xy)
+    assert (slots >= 0).all() and len(set(slots.tolist())) == 32
+    assert (ctx.keys_register(w.keys_xy) == slots).all()           # second lookup hits the cache
+    hb = _fill(ctx, 0, w, slots[w.key_idx])
+    ctx.verify_p256_keyed(0, w.n)
+    assert (hb["mask"][: w.n // 32] == exp).all() and not hb["offcurve"][: w.n // 32].any()
+    # mixed batch: signatures of odd keys take the generic kernel
+    hb = _fill(ctx, 1, w, np.where(w.key_idx % 2 == 0, slots[w.key_idx], -1))
+    ctx.verify_p256_keyed(1, w.n)
+    assert (hb["mask"][: w.n // 32] == exp).all()
+    # no key cached at all through the keyed entry point
+    hb = _fill(ctx, 0, w, np.full(w.n, -1, np.int32))
+    ctx.verify_p256_keyed(0, w.n)
+    assert (hb["mask"][: w.n // 32] == exp).all()
+    # ragged n
+    hb = _fill(ctx, 0, w, slots[w.key_idx])
+    ctx.verify_p256_keyed(0, 1000)
+    assert (mask_bits(hb["mask"], 1000) == mask_bits(exp, 1000)).all()
+
+
+def test_key_tables_device_resident(ctx):
+    import torch
+    w = workload.Workload(8192, 8, seed=43)
+    w.tamper_r(0.1)
+    exp = fast.valid_mask(fast.verify_batch(w.keys_xy, w.key_idx, w.digest, w.dig_off(), w.sigs, w.sig_off, nthreads=8))
+    slots = ctx.keys_register(w.keys_xy)
+    dev = torch.device("cuda:0")
+    t = [torch.from_numpy(a).to(dev) for a in (w.qx(), w.qy(), w.digest, w.r, w.s)]
+    ks = torch.from_numpy(slots[w.key_idx]).to(dev)
+    mask = torch.zeros(w.n // 32, dtype=torch.int32, device=dev)
+    st = torch.cuda.current_stream(dev)
+    ctx.verify_p256_device_keyed(True, ks.data_ptr(), 0, 0, t[2].data_ptr(), t[3].data_ptr(), t[4].data_ptr(), w.n, mask.data_ptr(), 0, st.cuda_stream)
+    st.synchronize()
+    assert (mask.cpu().numpy().view(np.uint32) == exp).all()
+
+
+def test_key_table_eviction_and_off_curve_keys():
+    os.environ["FABGPU_KEY_SLOTS"] = "4"
+    try:
+        c = pkg().binding.Context(max_batch=4096)
+    finally:
+        del os.environ["FABGPU_KEY_SLOTS"]
+    assert c.key_slot_capacity() == 4
+    w = workload.Workload(2048, 6, seed=47)
+    exp = fast.valid_mask(fast.verify_batch(w.keys_xy, w.key_idx, w.digest, w.dig_off(), w.sigs, w.sig_off, nthreads=8))
+    s1 = c.keys_register(w.keys_xy[:4])
+    assert sorted(s1.tolist()) == [0, 1, 2, 3]
+    s2 = c.keys_register(w.keys_xy[2:6])                  # keys 2,3 stay; 4,5 evict the two least recently used (0,1)
+    assert (s2[:2] == s1[2:4]).all() and sorted(s2[2:].tolist()) == sorted(s1[:2].tolist())
+    all6 = c.keys_register(w.keys_xy)                     # six keys, four slots: two stay generic
+    assert int((all6 < 0).sum()) == 2
+    hb = _fill(c, 0, w, all6[w.key_idx])
+    c.verify_p256_keyed(0, w.n)
+    assert (hb["mask"][: w.n // 32] == exp).all()
+    bad = w.keys_xy[:1].copy(); bad[0, 63] ^= 1           # not a curve point: no table
+    assert c.keys_register(bad)[0] == -1
+    c.close()
+
+
+def test_bccsp_batch_with_forced_key_tables():
+    """Every key registered (FABGPU_KEY_MIN_USES=1): statuses must equal the generic path's and the oracle's."""
+    os.environ["FABGPU_KEY_MIN_USES"] = "1"
+    try:
+        csp2 = pkg().bccsp.GPUCSP(max_batch=4096)
+    finally:
+        del os.environ["FABGPU_KEY_MIN_USES"]
+    cases = vectors.build()
+    keys = [csp2.KeyImport((c["qx"] % R, c["qy"] % R)) for c in cases]
+    st = csp2.VerifyBatch(keys, list(range(len(cases))), [c["digest"] for c in cases], [c["sig"] for c in cases])
+    for c, got in zip(cases, st):
+        assert int(got) == vectors.expected_status(c), c["name"]
+    w = workload.Workload(3000, 5, seed=53)
+    w.tamper_r(0.2)
+    exp = fast.verify_batch(w.keys_xy, w.key_idx, w.digest, w.dig_off(), w.sigs, w.sig_off, nthreads=8)
+    assert (csp2.ctx.bccsp_verify_batch(w.keys_xy, w.key_idx, w.digest, w.dig_off(), w.sigs, w.sig_off) == exp).all()
+    csp2.close()

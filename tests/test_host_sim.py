@@ -2,6 +2,7 @@
 windows, complete Jacobian group law, inversion-free final check) compiled for the host and compared with the oracle.
 Runs on the GPU-less build box; the PTX limb primitives themselves are covered by tests/test_gpu_*.py."""
 import numpy as np
+import pytest
 
 from oracle import bccsp_sw as o
 from oracle import fast
@@ -12,7 +13,8 @@ import vectors
 V_INVALID, V_VALID, V_OFFCURVE = 0, 1, 2
 
 
-def test_constructed_edge_cases():
+@pytest.mark.parametrize("cached", [False, True])
+def test_constructed_edge_cases(cached):
     b = pkg().binding
     for c in vectors.build():
         exp = vectors.expected_status(c)
@@ -25,7 +27,7 @@ def test_constructed_edge_cases():
             assert st == exp, c["name"]
             continue
         out = hostsim_verify(be32(c["qx"] % (1 << 256)), be32(c["qy"] % (1 << 256)), hash_to_e32(c["digest"]),
-                             np.frombuffer(r, np.uint8), np.frombuffer(s, np.uint8))[0]
+                             np.frombuffer(r, np.uint8), np.frombuffer(s, np.uint8), cached=cached)[0]
         got = {V_VALID: o.VALID, V_INVALID: o.INVALID, V_OFFCURVE: o.ERR_OFF_CURVE}[int(out)]
         assert got == exp, c["name"]
 
@@ -46,3 +48,6 @@ def test_tampered_matches_oracle_bit_for_bit():
     out = hostsim_verify(w.qx(), w.qy(), w.digest, w.r, w.s)
     assert ((out == V_VALID) == (exp == o.VALID)).all()
     assert 100 < int((exp != o.VALID).sum()) < 300
+    # the per-key-table path gives the same bits
+    out_c = hostsim_verify(w.qx(), w.qy(), w.digest, w.r, w.s, cached=True)
+    assert (out_c == out).all()

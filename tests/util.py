@@ -43,7 +43,7 @@ def hostsim():
         d = os.path.join(ROOT, "tests", "host_sim")
         so = os.path.join(d, "libhostsim.so")
         src = os.path.join(d, "hostsim.cpp")
-        hdrs = [os.path.join(ROOT, "fabric-mod_b200", "csrc", h) for h in ("p256_fe.cuh", "p256_point.cuh", "ecdsa_verify.cuh")]
+        hdrs = [os.path.join(ROOT, "fabric-mod_b200", "csrc", h) for h in ("p256_fe.cuh", "p256_point.cuh", "p256_modinv.cuh", "ecdsa_verify.cuh")]
         if not os.path.exists(so) or any(os.path.getmtime(so) < os.path.getmtime(f) for f in [src] + hdrs):
             subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", so, src])
         _HS = ctypes.CDLL(so)
@@ -51,11 +51,12 @@ def hostsim():
     return _HS
 
 
-def hostsim_verify(qx, qy, e, r, s):
+def hostsim_verify(qx, qy, e, r, s, cached=False):
     arrs = [np.ascontiguousarray(a, dtype=np.uint8).reshape(-1, 32) for a in (qx, qy, e, r, s)]
     n = arrs[0].shape[0]
     out = np.zeros(n, np.uint8)
-    hostsim().hostsim_verify_batch(*[a.ctypes.data_as(ctypes.c_void_p) for a in arrs], ctypes.c_int(n), out.ctypes.data_as(ctypes.c_void_p))
+    fn = hostsim().hostsim_verify_batch_cached if cached else hostsim().hostsim_verify_batch
+    fn(*[a.ctypes.data_as(ctypes.c_void_p) for a in arrs], ctypes.c_int(n), out.ctypes.data_as(ctypes.c_void_p))
     return out
 
 

@@ -25,9 +25,14 @@ def main():
     t = [torch.from_numpy(a).to(dev) for a in (w.qx(), w.qy(), w.digest, w.r, w.s)]
     mask = torch.zeros(nmax // 32, dtype=torch.int32, device=dev)
     st = torch.cuda.current_stream(dev)
-    for n in batches:
+    slots = ctx.keys_register(w.keys_xy)
+    ks = torch.from_numpy(slots[w.key_idx]).to(dev)
+    for mode, n in [(m, n) for n in batches for m in ("generic", "cached")]:
         def go():
-            ctx.verify_p256_device(*[x.data_ptr() for x in t], n, mask.data_ptr(), 0, st.cuda_stream)
+            if mode == "generic":
+                ctx.verify_p256_device(*[x.data_ptr() for x in t], n, mask.data_ptr(), 0, st.cuda_stream)
+            else:
+                ctx.verify_p256_device_keyed(True, ks.data_ptr(), 0, 0, t[2].data_ptr(), t[3].data_ptr(), t[4].data_ptr(), n, mask.data_ptr(), 0, st.cuda_stream)
         for _ in range(3):
             go()
         torch.cuda.synchronize()
@@ -40,7 +45,7 @@ def main():
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / reps
-        print("%-40s n=%7d  %8.3f ms  %8.2f Mverify/s" % (os.path.basename(lib), n, ms, n / ms / 1e3), flush=True)
+        print("%-32s %-8s n=%7d  %8.3f ms  %8.2f Mverify/s" % (os.path.basename(lib), mode, n, ms, n / ms / 1e3), flush=True)
     ctx.close()
 
 
