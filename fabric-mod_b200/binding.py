@@ -20,7 +20,7 @@ EXPORTS = [
     "fabgpu_verify_p256_device", "fabgpu_bccsp_verify_batch", "fabgpu_bccsp_verify", "fabgpu_gate_signature",
     "fabgpu_test_fieldop", "fabgpu_test_gtable", "fabgpu_launch_count",
     "fabgpu_keys_register", "fabgpu_key_slot_capacity", "fabgpu_host_key_slots", "fabgpu_verify_p256_keyed",
-    "fabgpu_verify_p256_keyed_async", "fabgpu_verify_p256_device_keyed",
+    "fabgpu_verify_p256_keyed_async", "fabgpu_verify_p256_device_keyed", "fabgpu_last_timing",
 ]
 
 
@@ -212,6 +212,12 @@ class Context:
                                            ctypes.byref(valid), err, ctypes.c_size_t(1024)))
         e = err.value.decode()
         return bool(valid.value), (e if e else None)
+
+    def last_timing(self):
+        """[key lookup, host gates, device, scatter] microseconds of the last bccsp_verify_batch call."""
+        out = (ctypes.c_double * 4)()
+        self._ck(lib().fabgpu_last_timing(self._h, out))
+        return [float(x) for x in out]
 
     # ---- test hooks -------------------------------------------------------------------------------------
     def test_fieldop(self, op, a, b):

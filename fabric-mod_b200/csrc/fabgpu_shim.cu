@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <atomic>
 #include <condition_variable>
 #include <functional>
@@ -20,6 +21,10 @@
 #include "../../include/fabgpu_ecdsa.h"
 #include "bccsp_host.hpp"
 #include "ecdsa_kernels.cuh"
+
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 
 using namespace fabgpu;
 
@@ -59,7 +64,7 @@ public:
         for (int t = 1; t < n_; t++) th_.emplace_back([this, t] { loop(t); });
     }
     ~GatePool() {
-        { std::lock_guard<std::mutex> lk(mu_); stop_ = true; gen_++; }
+        { std::lock_guard<std::mutex> lk(mu_); stop_ = true; gen_.fetch_add(1); }
         cv_.notify_all();
         for (auto& t : th_) t.join();
     }
@@ -67,26 +72,35 @@ public:
     // runs fn(tid) for tid in [0, size) and returns when all are done
     void run(const std::function<void(int)>& fn) {
         if (n_ == 1) { fn(0); return; }
-        { std::lock_guard<std::mutex> lk(mu_); fn_ = &fn; pending_ = n_ - 1; gen_++; }
+        { std::lock_guard<std::mutex> lk(mu_); fn_ = &fn; pending_.store(n_ - 1); gen_.fetch_add(1); }
         cv_.notify_all();
         fn(0);
+        for (int spin = 0; spin < 20000 && pending_.load(std::memory_order_acquire) != 0; spin++) cpu_relax();
+        if (pending_.load(std::memory_order_acquire) == 0) return;
         std::unique_lock<std::mutex> lk(mu_);
-        done_.wait(lk, [this] { return pending_ == 0; });
+        done_.wait(lk, [this] { return pending_.load() == 0; });
     }
 private:
+    static void cpu_relax() {
+#if defined(__SSE2__)
+        _mm_pause();
+#endif
+    }
+    // Workers spin briefly for the next job (back-to-back batches arrive within microseconds) before sleeping.
     void loop(int tid) {
         unsigned long long seen = 0;
         for (;;) {
+            for (int spin = 0; spin < 20000 && gen_.load(std::memory_order_acquire) == seen; spin++) cpu_relax();
             const std::function<void(int)>* fn;
             {
                 std::unique_lock<std::mutex> lk(mu_);
-                cv_.wait(lk, [&] { return gen_ != seen; });
-                seen = gen_;
+                cv_.wait(lk, [&] { return gen_.load() != seen; });
+                seen = gen_.load();
                 if (stop_) return;
                 fn = fn_;
             }
             (*fn)(tid);
-            { std::lock_guard<std::mutex> lk(mu_); if (--pending_ == 0) done_.notify_one(); }
+            if (pending_.fetch_sub(1, std::memory_order_acq_rel) == 1) { std::lock_guard<std::mutex> lk(mu_); done_.notify_one(); }
         }
     }
     int n_;
@@ -94,8 +108,8 @@ private:
     std::mutex mu_;
     std::condition_variable cv_, done_;
     const std::function<void(int)>* fn_ = nullptr;
-    int pending_ = 0;
-    unsigned long long gen_ = 0;
+    std::atomic<int> pending_{0};
+    std::atomic<unsigned long long> gen_{0};
     bool stop_ = false;
 };
 
@@ -116,6 +130,7 @@ struct fabgpu_ctx {
     std::vector<unsigned long long> slot_tick;
     unsigned long long tick = 0;
     int key_min_uses = 32;
+    double timing[4] = {0, 0, 0, 0};   // last fabgpu_bccsp_verify_batch: key lookup, host gates, device (H2D+kernel+D2H), scatter [us]
 };
 
 namespace {
@@ -138,6 +153,34 @@ bool fault_injected()
 }
 
 size_t round_up32(size_t x) { return (x + 31) / 32 * 32; }
+
+// 32-byte copy into a pinned staging buffer with streaming stores: the lines never become dirty in this core's cache,
+// so the H2D DMA that follows does not have to snoop 16+ cores across two sockets (measured: that snooping more than
+// doubled the copy phase when the gates ran multi-threaded).
+inline void stage32(uint8_t* dst, const uint8_t* src)
+{
+#if defined(__SSE2__)
+    const __m128i a = _mm_loadu_si128((const __m128i*)src), b = _mm_loadu_si128((const __m128i*)(src + 16));
+    _mm_stream_si128((__m128i*)dst, a);
+    _mm_stream_si128((__m128i*)(dst + 16), b);
+#else
+    memcpy(dst, src, 32);
+#endif
+}
+inline void stage_i32(int32_t* dst, int32_t v)
+{
+#if defined(__SSE2__)
+    _mm_stream_si32((int*)dst, v);
+#else
+    *dst = v;
+#endif
+}
+inline void stage_fence()
+{
+#if defined(__SSE2__)
+    _mm_sfence();
+#endif
+}
 
 // mode: 0 = no signature has a key table (generic kernel only), 1 = all have one (cached kernel only),
 //       2 = mixed (cached kernel, then the generic kernel fills in the rest)
@@ -497,13 +540,17 @@ int fabgpu_bccsp_verify_batch(fabgpu_ctx* ctx, const uint8_t* keys_xy, int K, co
                               const uint32_t* dig_off, const uint8_t* sigs, const uint32_t* sig_off, size_t n, uint8_t* status)
 {
     if (!ctx || (n && (!key_idx || !dig_off || !sig_off || !status))) return FABGPU_E_ARG;
-    // Chunks of at most max_batch signatures go through slot 0.  Gates run on the context's host threads; a signature
-    // that fails a gate keeps its slot position with r = s = 0 (the kernel rejects it at once) so that packing needs
-    // no compaction and stays parallel.
+    // Gates run on the context's host threads; a signature that fails a gate keeps its position with r = s = 0 (the
+    // kernel rejects it at once) so that packing needs no compaction and stays parallel.
     std::lock_guard<std::mutex> lk0(ctx->slot0_mu);
-    HostSlot& hs = ctx->hslot[0];
     // Keys that recur (>= key_min_uses signatures in this call) or already own a table use the fixed-base kernel;
     // this is what KeyImport does once per identity in the Go provider.
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto us = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+        return std::chrono::duration<double, std::micro>(b - a).count();
+    };
+    auto t_start = now();
+    ctx->timing[0] = ctx->timing[1] = ctx->timing[2] = ctx->timing[3] = 0;
     std::vector<int32_t> slot_of(K > 0 ? K : 0, -1);
     if (K > 0 && keys_xy && ctx->key_min_uses >= 0) {
         std::vector<uint32_t> uses(K, 0);
@@ -519,54 +566,104 @@ int fabgpu_bccsp_verify_batch(fabgpu_ctx* ctx, const uint8_t* keys_xy, int K, co
             for (size_t i = 0; i < want.size(); i++) slot_of[want[i]] = ws[i];
         }
     }
-    for (size_t base = 0; base < n; base += ctx->max_batch) {
-        const size_t cnt = std::min(ctx->max_batch, n - base);
-        const int T = ctx->pool->size();
+    ctx->timing[0] = us(t_start, now());
+    // The call is cut into chunks that alternate between the two pinned slots: while the GPU works on one chunk the
+    // host threads gate and pack the next, and the statuses of the chunk before are scattered.
+    const int T = ctx->pool->size();
+    size_t chunk = ctx->max_batch;
+    if (n > 16384) {
+        const char* ev = getenv("FABGPU_E2E_CHUNKS");
+        const size_t parts = ev ? (size_t)std::max(1, atoi(ev)) : 4;
+        chunk = std::min(ctx->max_batch, std::max((size_t)8192, round_up32((n + parts - 1) / parts)));
+    }
+    struct InFlight { bool active = false; size_t base = 0, cnt = 0; } fl[FABGPU_SLOTS];
+    auto retire = [&](int sl) -> int {
+        if (!fl[sl].active) return FABGPU_OK;
+        auto a = now();
+        int rc = fabgpu_wait(ctx, sl);
+        auto b = now();
+        ctx->timing[2] += us(a, b);
+        if (rc) return rc;
+        HostSlot& hsl = ctx->hslot[sl];
+        const size_t base = fl[sl].base, cnt = fl[sl].cnt;
+        ctx->pool->run([&](int tid) {
+            const size_t lo = cnt * (size_t)tid / T, hi = cnt * (size_t)(tid + 1) / T;
+            for (size_t k = lo; k < hi; k++) {
+                if (status[base + k] != FABGPU_ST_VALID) continue;          // decided by a gate
+                const bool ok = (hsl.h_mask[k >> 5] >> (k & 31)) & 1u;
+                const bool oc = (hsl.h_off[k >> 5] >> (k & 31)) & 1u;
+                status[base + k] = ok ? FABGPU_ST_VALID : (oc ? FABGPU_ST_ERR_OFF_CURVE : FABGPU_ST_INVALID);
+            }
+        });
+        fl[sl].active = false;
+        ctx->timing[3] += us(b, now());
+        return FABGPU_OK;
+    };
+    int sl = 0;
+    static const uint8_t kZero32[32] = {0};
+    for (size_t base = 0; base < n; base += chunk, sl = (sl + 1) % FABGPU_SLOTS) {
+        const size_t cnt = std::min(chunk, n - base);
+        int rc = retire(sl);
+        if (rc) return rc;
+        HostSlot& hs = ctx->hslot[sl];
         std::atomic<size_t> asked{0};
+        auto t0 = now();
         ctx->pool->run([&](int tid) {
             const size_t b = cnt * (size_t)tid / T, e = cnt * (size_t)(tid + 1) / T;
             size_t mine = 0;
             for (size_t k = b; k < e; k++) {
                 const size_t i = base + k;
                 const int32_t ki = key_idx[i];
-                const size_t sl = sig_off[i + 1] - sig_off[i], dl = dig_off[i + 1] - dig_off[i];
+                const size_t sl_ = sig_off[i + 1] - sig_off[i], dl = dig_off[i + 1] - dig_off[i];
                 uint8_t st;
                 if (ki < 0) st = FABGPU_ST_ERR_NIL_KEY;                    // bccsp/sw/impl.go:249-251
-                else if (sl == 0) st = FABGPU_ST_ERR_EMPTY_SIG;            // :252-254
+                else if (sl_ == 0) st = FABGPU_ST_ERR_EMPTY_SIG;           // :252-254
                 else if (dl == 0) st = FABGPU_ST_ERR_EMPTY_DIGEST;         // :255-257
                 else if (ki >= K || !keys_xy) st = FABGPU_ST_ERR_UNSUPPORTED_KEY;
                 else {
                     host::Gate g;
-                    host::gate_signature(sigs + sig_off[i], sl, g, false);
+                    host::gate_signature(sigs + sig_off[i], sl_, g, false);
                     st = (uint8_t)g.status;
                     if (g.status == FABGPU_ST_VALID) {
-                        memcpy(hs.h_in[0] + 32 * k, keys_xy + 64 * (size_t)ki, 32);
-                        memcpy(hs.h_in[1] + 32 * k, keys_xy + 64 * (size_t)ki + 32, 32);
-                        host::hash_to_e(digests + dig_off[i], dl, hs.h_in[2] + 32 * k);
-                        memcpy(hs.h_in[3] + 32 * k, g.r, 32);
-                        memcpy(hs.h_in[4] + 32 * k, g.s, 32);
+                        uint8_t ebuf[32];
+                        host::hash_to_e(digests + dig_off[i], dl, ebuf);
+                        if (slot_of[ki] < 0) {                               // the key-table kernel never reads Qx/Qy
+                            stage32(hs.h_in[0] + 32 * k, keys_xy + 64 * (size_t)ki);
+                            stage32(hs.h_in[1] + 32 * k, keys_xy + 64 * (size_t)ki + 32);
+                        }
+                        stage32(hs.h_in[2] + 32 * k, ebuf);
+                        stage32(hs.h_in[3] + 32 * k, g.r);
+                        stage32(hs.h_in[4] + 32 * k, g.s);
                         mine++;
                     }
                 }
-                if (st != FABGPU_ST_VALID) { memset(hs.h_in[3] + 32 * k, 0, 32); memset(hs.h_in[4] + 32 * k, 0, 32); }
-                hs.h_key_slot[k] = (st == FABGPU_ST_VALID) ? slot_of[ki] : -1;
+                if (st != FABGPU_ST_VALID) { stage32(hs.h_in[3] + 32 * k, kZero32); stage32(hs.h_in[4] + 32 * k, kZero32); }
+                stage_i32(hs.h_key_slot + k, (st == FABGPU_ST_VALID) ? slot_of[ki] : -1);
                 status[i] = st;
             }
+            stage_fence();
             asked += mine;
         });
+        auto t1 = now();
+        ctx->timing[1] += us(t0, t1);
         if (asked.load() == 0) continue;
-        int rc = fabgpu_verify_p256_keyed(ctx, 0, cnt);
+        rc = fabgpu_verify_p256_keyed_async(ctx, sl, cnt);
         if (rc) return rc;
-        ctx->pool->run([&](int tid) {
-            const size_t b = cnt * (size_t)tid / T, e = cnt * (size_t)(tid + 1) / T;
-            for (size_t k = b; k < e; k++) {
-                if (status[base + k] != FABGPU_ST_VALID) continue;          // decided by a gate
-                const bool ok = (hs.h_mask[k >> 5] >> (k & 31)) & 1u;
-                const bool oc = (hs.h_off[k >> 5] >> (k & 31)) & 1u;
-                status[base + k] = ok ? FABGPU_ST_VALID : (oc ? FABGPU_ST_ERR_OFF_CURVE : FABGPU_ST_INVALID);
-            }
-        });
+        fl[sl].active = true; fl[sl].base = base; fl[sl].cnt = cnt;
+        ctx->timing[2] += us(t1, now());
     }
+    // drain in launch order
+    for (int k = 0; k < FABGPU_SLOTS; k++, sl = (sl + 1) % FABGPU_SLOTS) {
+        int rc = retire(sl);
+        if (rc) return rc;
+    }
+    return FABGPU_OK;
+}
+
+int fabgpu_last_timing(const fabgpu_ctx* ctx, double out_us[4])
+{
+    if (!ctx || !out_us) return FABGPU_E_ARG;
+    for (int i = 0; i < 4; i++) out_us[i] = ctx->timing[i];
     return FABGPU_OK;
 }
 

@@ -138,6 +138,10 @@ int fabgpu_test_fieldop(fabgpu_ctx* ctx, int op, const uint8_t* a, const uint8_t
 /* Copies the device fixed-base table (entries x 64 bytes, Montgomery little-endian limbs) to `out`; returns the
  * byte size needed when out == NULL. */
 long fabgpu_test_gtable(fabgpu_ctx* ctx, uint8_t* out, size_t cap);
+/* Phase times of the last fabgpu_bccsp_verify_batch call, microseconds: [0] key-table lookup/registration,
+ * [1] host gates + packing, [2] H2D + kernels + D2H (enqueue to completion), [3] status scatter.  For metrics export
+ * (the reference only has a block-level histogram, gossip/metrics/metrics.go:187-194). */
+int fabgpu_last_timing(const fabgpu_ctx* ctx, double out_us[4]);
 /* Kernel launches issued by this context so far (bench.py's gpu_launches). */
 unsigned long long fabgpu_launch_count(const fabgpu_ctx* ctx);
 

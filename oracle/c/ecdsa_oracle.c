@@ -12,9 +12,10 @@
  *   IsLowS                       bccsp/utils/ecdsa.go:84-92 s <= N>>1
  *   [Go 1.14.4 crypto/ecdsa.Verify, not in tree; pinned Makefile:79] r,s < N; e = leftmost 32 bytes;
  *       w = s^-1; u1 = e w; u2 = r w; R = u1 G + u2 Q; R != inf; R.x mod N == r.
- * The curve arithmetic of the last step is delegated to OpenSSL libcrypto (ECDSA_do_verify,
- * nistz256 -- the same algorithm family Go's amd64 P-256 assembly was derived from); OpenSSL accepts
- * high-S and laxer DER, which is why the explicit gates above come first.  This file is cross-checked
+ * The steps of ecdsa.Verify are spelled out below with OpenSSL libcrypto primitives (BN_mod_inverse, BN_mod_mul,
+ * EC_POINT_mul = nistz256 -- the algorithm family Go's amd64 P-256 assembly was derived from).  Each worker thread owns
+ * its EC_GROUP, BN_CTX and imported keys, so threads share no OpenSSL object (ECDSA_do_verify on shared keys scaled
+ * badly on the 128-thread GPU hosts).  This file is cross-checked
  * against the pure-Python restatement and the golden X.509 fixtures in tests/test_oracle.py.
  *
  * Build: make -C oracle   (gcc -O2 -shared -fPIC ... -lcrypto -lpthread)
@@ -118,60 +119,68 @@ typedef struct {
     const uint8_t *digests; const uint32_t *dig_off;
     const uint8_t *sigs; const uint32_t *sig_off;
     int begin, end; uint8_t *status;
-    EC_KEY **keys; uint8_t *key_state; /* per-worker lazily imported keys: 0 unseen, 1 ok, 2 off-curve */
+    /* per-worker state: nothing below is shared between threads */
+    EC_GROUP *group; BN_CTX *ctx; BIGNUM *order, *half, *r, *s, *e, *w, *u1, *u2, *x;
+    EC_POINT *R; EC_POINT **keys; uint8_t *key_state; /* lazily imported keys: 0 unseen, 1 ok, 2 off-curve */
 } job_t;
 
-static BIGNUM *g_half_n = NULL;
-
-static uint8_t one_status(const job_t *j, int i, BN_CTX *ctx)
+static uint8_t one_status(job_t *j, int i)
 {
     int32_t ki = j->key_idx[i];
-    if (ki < 0) return ST_ERR_NIL_KEY;
+    if (ki < 0) return ST_ERR_NIL_KEY;                                   /* bccsp/sw/impl.go:249-251 */
     const uint8_t *sig = j->sigs + j->sig_off[i]; size_t siglen = j->sig_off[i + 1] - j->sig_off[i];
     const uint8_t *dg = j->digests + j->dig_off[i]; size_t dglen = j->dig_off[i + 1] - j->dig_off[i];
-    if (siglen == 0) return ST_ERR_EMPTY_SIG;
-    if (dglen == 0) return ST_ERR_EMPTY_DIGEST;
+    if (siglen == 0) return ST_ERR_EMPTY_SIG;                            /* :252-254 */
+    if (dglen == 0) return ST_ERR_EMPTY_DIGEST;                          /* :255-257 */
     if (ki >= j->K) return ST_ERR_UNSUPPORTED_KEY;
     asn1_int r, s;
-    if (unmarshal_sig(sig, siglen, &r, &s)) return ST_ERR_UNMARSHAL;
-    if (r.neg || is_zero_int(&r)) return ST_ERR_R_NOT_POSITIVE;
-    if (s.neg || is_zero_int(&s)) return ST_ERR_S_NOT_POSITIVE;
-    uint8_t st = ST_INVALID;
-    BIGNUM *br = BN_bin2bn(r.p, (int)r.len, NULL), *bs = BN_bin2bn(s.p, (int)s.len, NULL);
-    if (BN_cmp(bs, g_half_n) > 0) { st = ST_ERR_HIGH_S; goto done; }
-    if (j->key_state[ki] == 0) {             /* import once per worker, like KeyImport once per identity */
-        EC_KEY *ek = EC_KEY_new_by_curve_name(NID_X9_62_prime256v1);
+    if (unmarshal_sig(sig, siglen, &r, &s)) return ST_ERR_UNMARSHAL;     /* bccsp/utils/ecdsa.go:46-49 */
+    if (r.neg || is_zero_int(&r)) return ST_ERR_R_NOT_POSITIVE;          /* :59-61 */
+    if (s.neg || is_zero_int(&s)) return ST_ERR_S_NOT_POSITIVE;          /* :62-64 */
+    BN_bin2bn(r.p, (int)r.len, j->r);
+    BN_bin2bn(s.p, (int)s.len, j->s);
+    if (BN_cmp(j->s, j->half) > 0) return ST_ERR_HIGH_S;                 /* bccsp/sw/ecdsa.go:47-54 */
+    if (j->key_state[ki] == 0) {                                         /* import once per worker, like KeyImport per identity */
+        EC_POINT *q = EC_POINT_new(j->group);
         BIGNUM *x = BN_bin2bn(j->keys_xy + 64 * ki, 32, NULL), *y = BN_bin2bn(j->keys_xy + 64 * ki + 32, 32, NULL);
-        if (EC_KEY_set_public_key_affine_coordinates(ek, x, y) != 1) { EC_KEY_free(ek); ek = NULL; } /* off curve */
+        int ok = EC_POINT_set_affine_coordinates(j->group, q, x, y, j->ctx) == 1;   /* fails for off-curve points */
         BN_free(x); BN_free(y);
-        j->keys[ki] = ek; j->key_state[ki] = ek ? 1 : 2;
+        if (!ok) { EC_POINT_free(q); q = NULL; }
+        j->keys[ki] = q; j->key_state[ki] = q ? 1 : 2;
     }
-    if (j->key_state[ki] == 2) { st = ST_ERR_OFF_CURVE; goto done; }
-    {
-        ECDSA_SIG *es = ECDSA_SIG_new();
-        ECDSA_SIG_set0(es, br, bs); br = bs = NULL;
-        /* ECDSA_do_verify: 1 valid, 0 invalid (incl. r >= N), -1 error */
-        int rc = ECDSA_do_verify(dg, (int)dglen, es, j->keys[ki]);
-        st = (rc == 1) ? ST_VALID : ST_INVALID;
-        ECDSA_SIG_free(es);
-    }
-done:
-    if (br) BN_free(br);
-    if (bs) BN_free(bs);
-    (void)ctx;
-    return st;
+    if (j->key_state[ki] == 2) return ST_ERR_OFF_CURVE;
+    /* Go 1.14 ecdsa.Verify (reached at bccsp/sw/ecdsa.go:56) */
+    if (BN_cmp(j->r, j->order) >= 0 || BN_cmp(j->s, j->order) >= 0) return ST_INVALID;
+    BN_bin2bn(dg, (int)(dglen > 32 ? 32 : dglen), j->e);                 /* hashToInt */
+    if (!BN_mod_inverse(j->w, j->s, j->order, j->ctx)) return ST_INVALID;
+    BN_mod_mul(j->u1, j->e, j->w, j->order, j->ctx);
+    BN_mod_mul(j->u2, j->r, j->w, j->order, j->ctx);
+    if (!EC_POINT_mul(j->group, j->R, j->u1, j->keys[ki], j->u2, j->ctx)) return ST_INVALID;
+    if (EC_POINT_is_at_infinity(j->group, j->R)) return ST_INVALID;
+    if (!EC_POINT_get_affine_coordinates(j->group, j->R, j->x, NULL, j->ctx)) return ST_INVALID;
+    BN_nnmod(j->x, j->x, j->order, j->ctx);
+    return BN_cmp(j->x, j->r) == 0 ? ST_VALID : ST_INVALID;
 }
 
 static void *worker(void *arg)
 {
     job_t *j = (job_t *)arg;
-    BN_CTX *ctx = BN_CTX_new();
-    j->keys = (EC_KEY **)calloc(j->K > 0 ? j->K : 1, sizeof(EC_KEY *));
+    j->group = EC_GROUP_new_by_curve_name(NID_X9_62_prime256v1);
+    j->ctx = BN_CTX_new();
+    j->order = BN_new(); j->half = BN_new(); j->r = BN_new(); j->s = BN_new(); j->e = BN_new(); j->w = BN_new();
+    j->u1 = BN_new(); j->u2 = BN_new(); j->x = BN_new();
+    EC_GROUP_get_order(j->group, j->order, j->ctx);
+    BN_rshift1(j->half, j->order);                                       /* bccsp/utils/ecdsa.go:27-32 */
+    j->R = EC_POINT_new(j->group);
+    j->keys = (EC_POINT **)calloc(j->K > 0 ? j->K : 1, sizeof(EC_POINT *));
     j->key_state = (uint8_t *)calloc(j->K > 0 ? j->K : 1, 1);
-    for (int i = j->begin; i < j->end; i++) j->status[i] = one_status(j, i, ctx);
-    for (int k = 0; k < j->K; k++) if (j->keys[k]) EC_KEY_free(j->keys[k]);
+    for (int i = j->begin; i < j->end; i++) j->status[i] = one_status(j, i);
+    for (int k = 0; k < j->K; k++) if (j->keys[k]) EC_POINT_free(j->keys[k]);
     free(j->keys); free(j->key_state);
-    BN_CTX_free(ctx);
+    EC_POINT_free(j->R);
+    BN_free(j->order); BN_free(j->half); BN_free(j->r); BN_free(j->s); BN_free(j->e); BN_free(j->w);
+    BN_free(j->u1); BN_free(j->u2); BN_free(j->x);
+    BN_CTX_free(j->ctx); EC_GROUP_free(j->group);
     return NULL;
 }
 
@@ -183,21 +192,15 @@ int oracle_verify_batch(const uint8_t *keys_xy, int K, const int32_t *key_idx,
                         const uint8_t *sigs, const uint32_t *sig_off,
                         int n, uint8_t *status, int nthreads)
 {
-    if (!g_half_n) {
-        EC_GROUP *g = EC_GROUP_new_by_curve_name(NID_X9_62_prime256v1);
-        BIGNUM *h = BN_new();
-        EC_GROUP_get_order(g, h, NULL);
-        BN_rshift1(h, h);
-        g_half_n = h;
-        EC_GROUP_free(g);
-    }
     if (nthreads < 1) nthreads = 1;
     if (nthreads > n) nthreads = n > 0 ? n : 1;
     pthread_t *th = (pthread_t *)calloc(nthreads, sizeof(pthread_t));
     job_t *jobs = (job_t *)calloc(nthreads, sizeof(job_t));
     for (int t = 0; t < nthreads; t++) {
-        job_t jb = { keys_xy, K, key_idx, digests, dig_off, sigs, sig_off,
-                     (int)((long long)n * t / nthreads), (int)((long long)n * (t + 1) / nthreads), status, NULL, NULL };
+        job_t jb;
+        memset(&jb, 0, sizeof jb);
+        jb.keys_xy = keys_xy; jb.K = K; jb.key_idx = key_idx; jb.digests = digests; jb.dig_off = dig_off; jb.sigs = sigs; jb.sig_off = sig_off;
+        jb.begin = (int)((long long)n * t / nthreads); jb.end = (int)((long long)n * (t + 1) / nthreads); jb.status = status;
         jobs[t] = jb;
         if (nthreads == 1) worker(&jobs[t]);
         else pthread_create(&th[t], NULL, worker, &jobs[t]);

@@ -46,6 +46,22 @@ def main():
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / reps
         print("%-32s %-8s n=%7d  %8.3f ms  %8.2f Mverify/s" % (os.path.basename(lib), mode, n, ms, n / ms / 1e3), flush=True)
+    # pinned-slot path: H2D + kernel + D2H + sync per call (what fabgpu_verify_p256_keyed does), wall clock
+    import time
+    for n in batches:
+        hb = ctx.host_buffers(0)
+        for name, arr in (("qx", w.qx()), ("qy", w.qy()), ("e", w.digest), ("r", w.r), ("s", w.s)):
+            hb[name][:n] = arr[:n]
+        ctx.host_key_slots(0)[:n] = slots[w.key_idx][:n]
+        for keyed in (True, False):
+            f = (lambda: ctx.verify_p256_keyed(0, n)) if keyed else (lambda: ctx.verify_p256(0, n))
+            for _ in range(3):
+                f()
+            t0 = time.perf_counter()
+            for _ in range(10):
+                f()
+            ms = (time.perf_counter() - t0) / 10 * 1e3
+            print("%-32s slot-%-6s n=%7d  %8.3f ms wall per call" % (os.path.basename(lib), "keyed" if keyed else "plain", n, ms), flush=True)
     ctx.close()
 
 
