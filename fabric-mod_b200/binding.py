@@ -20,7 +20,7 @@ EXPORTS = [
     "fabgpu_verify_p256_device", "fabgpu_bccsp_verify_batch", "fabgpu_bccsp_verify", "fabgpu_gate_signature",
     "fabgpu_test_fieldop", "fabgpu_test_gtable", "fabgpu_launch_count",
     "fabgpu_keys_register", "fabgpu_key_slot_capacity", "fabgpu_host_key_slots", "fabgpu_verify_p256_keyed",
-    "fabgpu_verify_p256_keyed_async", "fabgpu_verify_p256_device_keyed", "fabgpu_last_timing",
+    "fabgpu_verify_p256_keyed_async", "fabgpu_verify_p256_device_keyed", "fabgpu_last_timing", "fabgpu_build_info",
 ]
 
 
@@ -64,6 +64,13 @@ def lib():
 
 def _p(a):
     return a.ctypes.data_as(ctypes.c_void_p) if a is not None else None
+
+
+def build_info():
+    """(window bits of the G table, window bits of the per-key tables) this library was compiled with."""
+    a, b = ctypes.c_int(0), ctypes.c_int(0)
+    lib().fabgpu_build_info(ctypes.byref(a), ctypes.byref(b))
+    return a.value, b.value
 
 
 def gate_signature(sig: bytes):

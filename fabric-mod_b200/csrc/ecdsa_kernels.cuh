@@ -5,11 +5,13 @@
 
 namespace fabgpu {
 
+// Launch shapes measured on B200 (tools/kbench.py, 64k and 256k batches): both kernels are pipe-bound, not
+// latency-bound, so occupancy variants differ by < 5 %; these were the best of the sweep.
 #ifndef FAB_VERIFY_THREADS
-#define FAB_VERIFY_THREADS 128
+#define FAB_VERIFY_THREADS 64
 #endif
 #ifndef FAB_VERIFY_MINBLOCKS
-#define FAB_VERIFY_MINBLOCKS 1
+#define FAB_VERIFY_MINBLOCKS 7
 #endif
 
 // 32 big-endian bytes at a 16-byte aligned address -> limbs, as two 128-bit loads + byte permutes
@@ -63,11 +65,11 @@ ecdsa_verify_kernel(const int32_t* __restrict__ key_slot, const uint8_t* __restr
 #define FAB_CACHED_THREADS 128
 #endif
 #ifndef FAB_CACHED_MINBLOCKS
-#define FAB_CACHED_MINBLOCKS 1
+#define FAB_CACHED_MINBLOCKS 4
 #endif
 // Signatures whose public key has a precomputed window table: both scalar multiplications are fixed-base
-// (2 x FAB_G_WINDOWS mixed additions gathered from L2-resident tables, no doublings).  Slot < 0 -> bit 0, left to
-// ecdsa_verify_kernel.  qtab: key_slot_capacity tables of FAB_G_WINDOWS*FAB_G_ENTRIES affine points.
+// (FAB_G_WINDOWS + FAB_Q_WINDOWS mixed additions gathered from L2-resident tables, no doublings).  Slot < 0 -> bit 0, left to
+// ecdsa_verify_kernel.  qtab: key_slot_capacity tables of FAB_Q_WINDOWS*FAB_Q_ENTRIES affine points.
 __global__ void __launch_bounds__(FAB_CACHED_THREADS, FAB_CACHED_MINBLOCKS)
 ecdsa_verify_cached_kernel(const int32_t* __restrict__ key_slot, const uint8_t* __restrict__ e, const uint8_t* __restrict__ r,
                            const uint8_t* __restrict__ s, uint32_t n, const aff* __restrict__ gtab, const aff* __restrict__ qtab,
@@ -79,7 +81,7 @@ ecdsa_verify_cached_kernel(const int32_t* __restrict__ key_slot, const uint8_t* 
         const int32_t slot = key_slot[idx];
         if (slot >= 0) {
             const size_t o = (size_t)idx * 32;
-            res = ecdsa_verify_one_cached(qtab + (size_t)slot * (FAB_G_WINDOWS * FAB_G_ENTRIES), load_be32(e + o), load_be32(r + o),
+            res = ecdsa_verify_one_cached(qtab + (size_t)slot * (FAB_Q_WINDOWS * FAB_Q_ENTRIES), load_be32(e + o), load_be32(r + o),
                                           load_be32(s + o), gtab);
         }
     }
@@ -90,14 +92,14 @@ ecdsa_verify_cached_kernel(const int32_t* __restrict__ key_slot, const uint8_t* 
     }
 }
 
-// Key-table build: thread t builds window (t % FAB_G_WINDOWS) of key (t / FAB_G_WINDOWS) into the key's slot.
+// Key-table build: thread t builds window (t % FAB_Q_WINDOWS) of key (t / FAB_Q_WINDOWS) into the key's slot.
 // flags[k] = 1 when key k is a curve point (its table is valid), 0 otherwise (nothing is written for it).
 __global__ void build_key_tables_kernel(const uint8_t* __restrict__ keys_xy, const int32_t* __restrict__ slots, int nkeys,
                                         aff* __restrict__ qtab, u256* __restrict__ scratch, uint32_t* __restrict__ flags)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= nkeys * FAB_G_WINDOWS) return;
-    const int k = t / FAB_G_WINDOWS, j = t % FAB_G_WINDOWS;
+    if (t >= nkeys * FAB_Q_WINDOWS) return;
+    const int k = t / FAB_Q_WINDOWS, j = t % FAB_Q_WINDOWS;
     const u256 x = load_be32(keys_xy + 64 * (size_t)k), y = load_be32(keys_xy + 64 * (size_t)k + 32);
     const u256 p = fe_p();
     bool ok = u256_lt(x, p) && u256_lt(y, p);
@@ -105,8 +107,8 @@ __global__ void build_key_tables_kernel(const uint8_t* __restrict__ keys_xy, con
     if (ok) { q.x = fe_to_mont(x); q.y = fe_to_mont(y); ok = aff_on_curve(q); }
     if (j == 0) flags[k] = ok ? 1u : 0u;
     if (!ok) return;
-    u256* zs = scratch + (size_t)t * 2 * FAB_G_ENTRIES;
-    build_key_window(q, j, qtab + ((size_t)slots[k] * FAB_G_WINDOWS + j) * FAB_G_ENTRIES, zs, zs + FAB_G_ENTRIES);
+    u256* zs = scratch + (size_t)t * 2 * FAB_Q_ENTRIES;
+    build_key_window(q, j, qtab + ((size_t)slots[k] * FAB_Q_WINDOWS + j) * FAB_Q_ENTRIES, zs, zs + FAB_Q_ENTRIES);
 }
 
 // Unit-test hook: out[i] = op(a[i], b[i]) on the device primitives (tests/test_gpu_field.py).

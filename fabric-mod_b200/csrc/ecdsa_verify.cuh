@@ -15,8 +15,13 @@
 #include "p256_modinv.cuh"
 
 #ifndef FAB_WG
-#define FAB_WG 8                      // window bits of the fixed-base table
+#define FAB_WG 16                     // window bits of the fixed-base table of G: 16 windows x 65 535 points = 64 MiB per
+#endif                                // device, 16 mixed additions for u1*G (measured: 8 -> 94 M/s, 12 -> 109, 16 -> 120)
+#ifndef FAB_WQ
+#define FAB_WQ 8                      // window bits of the per-key tables (510 KiB per key at 8)
 #endif
+#define FAB_Q_WINDOWS ((256 + FAB_WQ - 1) / FAB_WQ)
+#define FAB_Q_ENTRIES ((1 << FAB_WQ) - 1)
 #ifndef FAB_SAFEGCD
 #define FAB_SAFEGCD 1
 #endif
@@ -71,6 +76,16 @@ FAB_HD jac scalar_mul_var(const u256& k, const jac* tab)
     return r;
 }
 
+// Hint the table entry the NEXT window will need into the cache while the current addition runs (no register cost).
+FAB_HD void prefetch_entry(const aff* p)
+{
+#if defined(__CUDA_ARCH__) && defined(FAB_PREFETCH)   /* measured neutral-to-negative on B200 (L2 hit rates are already high): opt-in */
+    asm volatile("prefetch.global.L2 [%0];" :: "l"(p));
+#else
+    (void)p;
+#endif
+}
+
 // r += u1 * G using the fixed-base table gtab[window][digit-1] (affine, Montgomery form)
 FAB_HD jac add_fixed_base(jac r, const u256& k, const aff* gtab)
 {
@@ -82,6 +97,8 @@ FAB_HD jac add_fixed_base(jac r, const u256& k, const aff* gtab)
 #pragma unroll
         for (int i = 0; i < 7; i++) kk[i] = (kk[i] >> FAB_WG) | (kk[i + 1] << (32 - FAB_WG));
         kk[7] >>= FAB_WG;
+        const uint32_t dn = kk[0] & (uint32_t)FAB_G_ENTRIES;
+        if (dn && j + 1 < FAB_G_WINDOWS) prefetch_entry(gtab + (size_t)(j + 1) * FAB_G_ENTRIES + (dn - 1));
         if (d) r = jac_add_aff(r, gtab[(size_t)j * FAB_G_ENTRIES + (d - 1)]);
     }
     return r;
@@ -138,7 +155,7 @@ FAB_HD uint32_t ecdsa_verify_one(const u256& qx, const u256& qy, const u256& e, 
 }
 
 // Same verification when the public key has a precomputed window table (fabgpu_keys_register): u2*Q becomes
-// fixed-base too -- 2 x FAB_G_WINDOWS mixed additions in total, no doublings, no per-signature table.  The key was
+// fixed-base too -- FAB_G_WINDOWS + FAB_Q_WINDOWS mixed additions in total, no doublings, no per-signature table.  The key was
 // checked to be a curve point when its table was built.
 FAB_HD uint32_t ecdsa_verify_one_cached(const aff* qtab, const u256& e, const u256& r, const u256& s, const aff* gtab)
 {
@@ -151,47 +168,45 @@ FAB_HD uint32_t ecdsa_verify_one_cached(const aff* qtab, const u256& e, const u2
 #endif
     const u256 u1 = sc_mul(sc_reduce_once(e), w);
     const u256 u2 = sc_mul(r, w);
-    uint32_t k1[8], k2[8];
+    jac acc = add_fixed_base(jac_infinity(), u1, gtab);
+    uint32_t k2[8];
 #pragma unroll
-    for (int i = 0; i < 8; i++) { k1[i] = u1.v[i]; k2[i] = u2.v[i]; }
-    jac acc = jac_infinity();
-    for (int j = 0; j < FAB_G_WINDOWS; j++) {
-        const uint32_t d1 = k1[0] & (uint32_t)FAB_G_ENTRIES, d2 = k2[0] & (uint32_t)FAB_G_ENTRIES;
+    for (int i = 0; i < 8; i++) k2[i] = u2.v[i];
+    for (int j = 0; j < FAB_Q_WINDOWS; j++) {
+        const uint32_t d2 = k2[0] & (uint32_t)FAB_Q_ENTRIES;
 #pragma unroll
-        for (int i = 0; i < 7; i++) {
-            k1[i] = (k1[i] >> FAB_WG) | (k1[i + 1] << (32 - FAB_WG));
-            k2[i] = (k2[i] >> FAB_WG) | (k2[i + 1] << (32 - FAB_WG));
-        }
-        k1[7] >>= FAB_WG; k2[7] >>= FAB_WG;
-        if (d1) acc = jac_add_aff(acc, gtab[(size_t)j * FAB_G_ENTRIES + (d1 - 1)]);
-        if (d2) acc = jac_add_aff(acc, qtab[(size_t)j * FAB_G_ENTRIES + (d2 - 1)]);
+        for (int i = 0; i < 7; i++) k2[i] = (k2[i] >> FAB_WQ) | (k2[i + 1] << (32 - FAB_WQ));
+        k2[7] >>= FAB_WQ;
+        const uint32_t dn = k2[0] & (uint32_t)FAB_Q_ENTRIES;
+        if (dn && j + 1 < FAB_Q_WINDOWS) prefetch_entry(qtab + (size_t)(j + 1) * FAB_Q_ENTRIES + (dn - 1));
+        if (d2) acc = jac_add_aff(acc, qtab[(size_t)j * FAB_Q_ENTRIES + (d2 - 1)]);
     }
     return final_check(acc, r);
 }
 
 // Fixed-base table entry (window j, digit d in 1..FAB_G_ENTRIES) = d * 2^(FAB_WG*j) * G, affine Montgomery.
-FAB_HD aff table_entry(const aff& g, int j, uint32_t d)
+FAB_HD aff table_entry(const aff& g, int wbits, int j, uint32_t d)
 {
     jac acc = jac_infinity();
-    // scalar = d << (FAB_WG*j): MSB-first double-and-add over d's bits, then FAB_WG*j doublings
-    for (int b = FAB_WG - 1; b >= 0; b--) {
+    // scalar = d << (wbits*j): MSB-first double-and-add over d's bits, then wbits*j doublings
+    for (int b = wbits - 1; b >= 0; b--) {
         acc = jac_double(acc);
         if ((d >> b) & 1u) acc = jac_add_aff(acc, g);
     }
-    for (int t = 0; t < FAB_WG * j; t++) acc = jac_double(acc);
+    for (int t = 0; t < wbits * j; t++) acc = jac_double(acc);
     return jac_to_aff(acc);
 }
-// Window j of a key's table, built by ONE thread: out[d-1] = d * 2^(FAB_WG*j) * q for d = 1..FAB_G_ENTRIES.
+// Window j of a key's table, built by ONE thread: out[d-1] = d * 2^(FAB_WQ*j) * q for d = 1..FAB_Q_ENTRIES.
 // Chain of mixed additions from the affine base 2^(FAB_WG*j) q, then one shared inversion for the whole window
-// (Montgomery's trick).  zs / ps: scratch of FAB_G_ENTRIES elements each.  ~6 100 field multiplications.
+// (Montgomery's trick).  zs / ps: scratch of FAB_Q_ENTRIES elements each.  ~6 100 field multiplications.
 FAB_HD void build_key_window(const aff& q, int j, aff* out, u256* zs, u256* ps)
 {
     jac b = jac_from_aff(q);
-    for (int t = 0; t < FAB_WG * j; t++) b = jac_double(b);
+    for (int t = 0; t < FAB_WQ * j; t++) b = jac_double(b);
     const aff base = jac_to_aff(b);
     jac t = jac_from_aff(base);
     u256 run = fe_one();
-    for (int d = 1; d <= FAB_G_ENTRIES; d++) {
+    for (int d = 1; d <= FAB_Q_ENTRIES; d++) {
         if (d > 1) t = jac_add_aff(t, base);
         out[d - 1].x = t.X; out[d - 1].y = t.Y;
         zs[d - 1] = t.Z;
@@ -199,7 +214,7 @@ FAB_HD void build_key_window(const aff& q, int j, aff* out, u256* zs, u256* ps)
         ps[d - 1] = run;                       // z_1 * ... * z_d
     }
     u256 inv = fe_inv(run);
-    for (int d = FAB_G_ENTRIES; d >= 1; d--) {
+    for (int d = FAB_Q_ENTRIES; d >= 1; d--) {
         const u256 zi = (d > 1) ? fe_mul(inv, ps[d - 2]) : inv;      // 1 / z_d
         if (d > 1) inv = fe_mul(inv, zs[d - 1]);
         const u256 zi2 = fe_sqr(zi);
@@ -211,7 +226,7 @@ FAB_HD void build_key_window(const aff& q, int j, aff* out, u256* zs, u256* ps)
 FAB_HD aff g_table_entry(int j, uint32_t d)
 {
     aff g; g.x = fe_gx_mont(); g.y = fe_gy_mont();
-    return table_entry(g, j, d);
+    return table_entry(g, FAB_WG, j, d);
 }
 
 }  // namespace fabgpu

@@ -309,7 +309,7 @@ int init_impl(fabgpu_ctx* ctx, const int* device_ids, int n_dev, size_t max_batc
         dv.id = ids[d];
         CK(ctx, cudaSetDevice(dv.id));
         CK(ctx, cudaMalloc(&dv.gtab, tab_entries * sizeof(aff)));
-        CK(ctx, cudaMalloc(&dv.qtab, (size_t)ctx->key_slots * tab_entries * sizeof(aff)));
+        CK(ctx, cudaMalloc(&dv.qtab, (size_t)ctx->key_slots * FAB_Q_WINDOWS * FAB_Q_ENTRIES * sizeof(aff)));
         for (auto& ds : dv.slot) {
             CK(ctx, cudaStreamCreateWithFlags(&ds.stream, cudaStreamNonBlocking));
             for (auto& p : ds.d_in) CK(ctx, cudaMalloc(&p, 32 * ctx->dev_cap));
@@ -317,7 +317,7 @@ int init_impl(fabgpu_ctx* ctx, const int* device_ids, int n_dev, size_t max_batc
             CK(ctx, cudaMalloc(&ds.d_off, 4 * words));
             CK(ctx, cudaMalloc(&ds.d_key_slot, 4 * ctx->dev_cap));
         }
-        build_g_table_kernel<<<(unsigned)((tab_entries + 63) / 64), 64, 0, dv.slot[0].stream>>>(dv.gtab);
+        build_g_table_kernel<<<(unsigned)((tab_entries + 127) / 128), 128, 0, dv.slot[0].stream>>>(dv.gtab);
         ctx->launches++;
         CK(ctx, cudaGetLastError());
     }
@@ -445,11 +445,11 @@ int fabgpu_keys_register(fabgpu_ctx* ctx, const uint8_t* keys_xy, int K, int32_t
         // an evicted slot's table may still be read by a batch in flight: drain this device first (registration is rare)
         for (auto& ds : dv.slot) CK(ctx, cudaStreamSynchronize(ds.stream));
         uint8_t* d_keys = nullptr; int32_t* d_slots = nullptr; uint32_t* d_flags = nullptr; u256* d_scratch = nullptr;
-        const size_t threads = (size_t)F * FAB_G_WINDOWS;
+        const size_t threads = (size_t)F * FAB_Q_WINDOWS;
         CK(ctx, cudaMalloc(&d_keys, fk.size()));
         CK(ctx, cudaMalloc(&d_slots, 4 * (size_t)F));
         CK(ctx, cudaMalloc(&d_flags, 4 * (size_t)F));
-        CK(ctx, cudaMalloc(&d_scratch, threads * 2 * FAB_G_ENTRIES * sizeof(u256)));
+        CK(ctx, cudaMalloc(&d_scratch, threads * 2 * FAB_Q_ENTRIES * sizeof(u256)));
         CK(ctx, cudaMemcpy(d_keys, fk.data(), fk.size(), cudaMemcpyHostToDevice));
         CK(ctx, cudaMemcpy(d_slots, fresh_slot.data(), 4 * (size_t)F, cudaMemcpyHostToDevice));
         build_key_tables_kernel<<<(unsigned)((threads + 31) / 32), 32, 0, dv.slot[0].stream>>>(d_keys, d_slots, F, dv.qtab, d_scratch, d_flags);
@@ -658,6 +658,12 @@ int fabgpu_bccsp_verify_batch(fabgpu_ctx* ctx, const uint8_t* keys_xy, int K, co
         if (rc) return rc;
     }
     return FABGPU_OK;
+}
+
+void fabgpu_build_info(int* g_window_bits, int* key_window_bits)
+{
+    if (g_window_bits) *g_window_bits = FAB_WG;
+    if (key_window_bits) *key_window_bits = FAB_WQ;
 }
 
 int fabgpu_last_timing(const fabgpu_ctx* ctx, double out_us[4])

@@ -15,28 +15,28 @@ FAB_HD bool jac_is_infinity(const jac& p) { return u256_is_zero(p.Z); }
 FAB_HD jac jac_from_aff(const aff& a) { jac r; r.X = a.x; r.Y = a.y; r.Z = fe_one(); return r; }
 FAB_HD jac jac_neg(const jac& p) { jac r = p; r.Y = fe_neg(p.Y); return r; }
 
-// dbl-2001-b (a = -3): 3M + 5S.  Infinity in -> infinity out (Z3 = 2*Y1*Z1 = 0).
+// Doubling, a = -3: 4M + 4S + 12 additive ops.  Same quantities as dbl-2001-b (alpha = 3(X-delta)(X+delta),
+// X3 = alpha^2 - 8 beta, Y3 = alpha(4 beta - X3) - 8 gamma^2, Z3 = 2 Y Z) but Z3 is a product instead of
+// (Y+Z)^2 - gamma - delta and the multiples of beta/gamma reuse 2*gamma: the additive ops run on the alu pipe, which
+// ncu shows is the busier one, so trading one squaring for a multiplication and four fewer add/sub is a net win.
+// Infinity in -> infinity out (Z3 = 2*Y1*Z1 = 0).
 FAB_HD jac jac_double(const jac& p)
 {
     const u256 delta = fe_sqr(p.Z);
     const u256 gamma = fe_sqr(p.Y);
-    const u256 beta = fe_mul(p.X, gamma);
-    const u256 t0 = fe_sub(p.X, delta);
-    const u256 t1 = fe_add(p.X, delta);
-    const u256 t2 = fe_mul(t0, t1);
+    const u256 gamma2 = fe_dbl(gamma);                       // 2 Y^2
+    const u256 beta4 = fe_dbl(fe_mul(p.X, gamma2));          // 4 X Y^2
+    const u256 t2 = fe_mul(fe_sub(p.X, delta), fe_add(p.X, delta));
     const u256 alpha = fe_add(fe_dbl(t2), t2);
-    const u256 beta4 = fe_dbl(fe_dbl(beta));
     jac r;
     r.X = fe_sub(fe_sqr(alpha), fe_dbl(beta4));
-    const u256 yz = fe_add(p.Y, p.Z);
-    r.Z = fe_sub(fe_sub(fe_sqr(yz), gamma), delta);
-    const u256 g2 = fe_sqr(gamma);
-    const u256 g8 = fe_dbl(fe_dbl(fe_dbl(g2)));
+    r.Z = fe_dbl(fe_mul(p.Y, p.Z));
+    const u256 g8 = fe_dbl(fe_sqr(gamma2));                  // 2 * (2 Y^2)^2 = 8 Y^4
     r.Y = fe_sub(fe_mul(alpha, fe_sub(beta4, r.X)), g8);
     return r;
 }
 
-// add-2007-bl: 11M + 5S, with the exceptional cases resolved explicitly.
+// Addition (add-1998-cmo-2 shape): 12M + 4S + 7 additive ops, with the exceptional cases resolved explicitly.
 FAB_HD jac jac_add(const jac& p, const jac& q)
 {
     if (jac_is_infinity(p)) return q;
@@ -48,25 +48,22 @@ FAB_HD jac jac_add(const jac& p, const jac& q)
     const u256 s1 = fe_mul(fe_mul(p.Y, q.Z), z2z2);
     const u256 s2 = fe_mul(fe_mul(q.Y, p.Z), z1z1);
     const u256 h = fe_sub(u2, u1);
-    const u256 rr0 = fe_sub(s2, s1);
+    const u256 rr = fe_sub(s2, s1);
     if (u256_is_zero(h)) {
-        if (u256_is_zero(rr0)) return jac_double(p);   // same point
-        return jac_infinity();                          // opposite points
+        if (u256_is_zero(rr)) return jac_double(p);   // same point
+        return jac_infinity();                         // opposite points
     }
-    const u256 h2 = fe_dbl(h);
-    const u256 i = fe_sqr(h2);
-    const u256 j = fe_mul(h, i);
-    const u256 rr = fe_dbl(rr0);
-    const u256 v = fe_mul(u1, i);
+    const u256 hh = fe_sqr(h);
+    const u256 hhh = fe_mul(h, hh);
+    const u256 v = fe_mul(u1, hh);
     jac r;
-    r.X = fe_sub(fe_sub(fe_sqr(rr), j), fe_dbl(v));
-    r.Y = fe_sub(fe_mul(rr, fe_sub(v, r.X)), fe_dbl(fe_mul(s1, j)));
-    const u256 zs = fe_add(p.Z, q.Z);
-    r.Z = fe_mul(fe_sub(fe_sub(fe_sqr(zs), z1z1), z2z2), h);
+    r.X = fe_sub(fe_sub(fe_sqr(rr), hhh), fe_dbl(v));
+    r.Y = fe_sub(fe_mul(rr, fe_sub(v, r.X)), fe_mul(s1, hhh));
+    r.Z = fe_mul(fe_mul(p.Z, q.Z), h);
     return r;
 }
 
-// madd-2007-bl (Z2 = 1): 7M + 4S.
+// Mixed addition (madd-2004-hmv shape, Z2 = 1): 8M + 3S + 7 additive ops.
 FAB_HD jac jac_add_aff(const jac& p, const aff& q)
 {
     if (jac_is_infinity(p)) return jac_from_aff(q);
@@ -74,21 +71,18 @@ FAB_HD jac jac_add_aff(const jac& p, const aff& q)
     const u256 u2 = fe_mul(q.x, z1z1);
     const u256 s2 = fe_mul(fe_mul(q.y, p.Z), z1z1);
     const u256 h = fe_sub(u2, p.X);
-    const u256 rr0 = fe_sub(s2, p.Y);
+    const u256 rr = fe_sub(s2, p.Y);
     if (u256_is_zero(h)) {
-        if (u256_is_zero(rr0)) return jac_double(p);
+        if (u256_is_zero(rr)) return jac_double(p);
         return jac_infinity();
     }
     const u256 hh = fe_sqr(h);
-    const u256 i = fe_dbl(fe_dbl(hh));
-    const u256 j = fe_mul(h, i);
-    const u256 rr = fe_dbl(rr0);
-    const u256 v = fe_mul(p.X, i);
+    const u256 hhh = fe_mul(h, hh);
+    const u256 v = fe_mul(p.X, hh);
     jac r;
-    r.X = fe_sub(fe_sub(fe_sqr(rr), j), fe_dbl(v));
-    r.Y = fe_sub(fe_mul(rr, fe_sub(v, r.X)), fe_dbl(fe_mul(p.Y, j)));
-    const u256 zh = fe_add(p.Z, h);
-    r.Z = fe_sub(fe_sub(fe_sqr(zh), z1z1), hh);
+    r.X = fe_sub(fe_sub(fe_sqr(rr), hhh), fe_dbl(v));
+    r.Y = fe_sub(fe_mul(rr, fe_sub(v, r.X)), fe_mul(p.Y, hhh));
+    r.Z = fe_mul(p.Z, h);
     return r;
 }
 

@@ -142,6 +142,8 @@ long fabgpu_test_gtable(fabgpu_ctx* ctx, uint8_t* out, size_t cap);
  * [1] host gates + packing, [2] H2D + kernels + D2H (enqueue to completion), [3] status scatter.  For metrics export
  * (the reference only has a block-level histogram, gossip/metrics/metrics.go:187-194). */
 int fabgpu_last_timing(const fabgpu_ctx* ctx, double out_us[4]);
+/* Compile-time table shapes: window bits of the fixed-base table of G and of the per-key tables. */
+void fabgpu_build_info(int* g_window_bits, int* key_window_bits);
 /* Kernel launches issued by this context so far (bench.py's gpu_launches). */
 unsigned long long fabgpu_launch_count(const fabgpu_ctx* ctx);
 

@@ -49,7 +49,7 @@ void hostsim_verify_batch_cached(const uint8_t* qx, const uint8_t* qy, const uin
 {
     hostsim_build_gtable();
     std::vector<std::pair<std::vector<uint8_t>, std::vector<aff>>> cache;
-    std::vector<u256> zs(2 * FAB_G_ENTRIES);
+    std::vector<u256> zs(2 * FAB_Q_ENTRIES);
     for (int i = 0; i < n; i++) {
         size_t o = 32 * (size_t)i;
         std::vector<uint8_t> key(qx + o, qx + o + 32);
@@ -62,8 +62,8 @@ void hostsim_verify_batch_cached(const uint8_t* qx, const uint8_t* qy, const uin
             if (ok) { q.x = fe_to_mont(x); q.y = fe_to_mont(y); ok = aff_on_curve(q); }
             std::vector<aff> t;
             if (ok) {
-                t.resize((size_t)FAB_G_WINDOWS * FAB_G_ENTRIES);
-                for (int j = 0; j < FAB_G_WINDOWS; j++) build_key_window(q, j, t.data() + (size_t)j * FAB_G_ENTRIES, zs.data(), zs.data() + FAB_G_ENTRIES);
+                t.resize((size_t)FAB_Q_WINDOWS * FAB_Q_ENTRIES);
+                for (int j = 0; j < FAB_Q_WINDOWS; j++) build_key_window(q, j, t.data() + (size_t)j * FAB_Q_ENTRIES, zs.data(), zs.data() + FAB_Q_ENTRIES);
             }
             cache.emplace_back(key, std::move(t));
             tab = &cache.back().second;
