@@ -129,7 +129,7 @@ struct fabgpu_ctx {
     std::vector<std::string> slot_key;
     std::vector<unsigned long long> slot_tick;
     unsigned long long tick = 0;
-    int key_min_uses = 32;
+    int key_min_uses = 256;
     double timing[4] = {0, 0, 0, 0};   // last fabgpu_bccsp_verify_batch: key lookup, host gates, device (H2D+kernel+D2H), scatter [us]
 };
 
@@ -293,12 +293,12 @@ int init_impl(fabgpu_ctx* ctx, const int* device_ids, int n_dev, size_t max_batc
         const char* ev = getenv("FABGPU_GATE_THREADS");
         int want = ev ? atoi(ev) : std::min(hw > 0 ? hw : 1, 16);
         ctx->pool.reset(new GatePool(want));
-        const char* ks = getenv("FABGPU_KEY_SLOTS");          // per-key tables are 510 KiB each, per device
+        const char* ks = getenv("FABGPU_KEY_SLOTS");          // per-key tables are 5.5 MiB each (FAB_WQ = 12), per device
         ctx->key_slots = ks ? std::max(1, atoi(ks)) : 256;
         ctx->slot_key.assign(ctx->key_slots, std::string());
         ctx->slot_tick.assign(ctx->key_slots, 0ull);
         const char* mu = getenv("FABGPU_KEY_MIN_USES");
-        ctx->key_min_uses = mu ? atoi(mu) : 32;
+        ctx->key_min_uses = mu ? atoi(mu) : 256;           // a table costs about 300 generic verifications to build
     }
     ctx->dev_cap = round_up32((max_batch + ids.size() - 1) / ids.size());
     ctx->devs.resize(ids.size());

@@ -118,7 +118,7 @@ int fabgpu_verify_p256_device_keyed(fabgpu_ctx* ctx, int dev_index, int all_cach
 /* keys_xy: K x 64 bytes (X || Y, big-endian).  key_idx[i] in [0,K), or < 0 for a nil key.  digests / sigs are
  * concatenations indexed by (n+1)-entry offset tables.  status[i] receives FABGPU_ST_*.  The host gates (DER per
  * Go encoding/asn1, positivity, low-S, r < 2^256) run on the CPU; survivors are verified on the GPU.  Keys used by at
- * least FABGPU_KEY_MIN_USES (env, default 32; negative disables) signatures of the call are registered automatically. */
+ * least FABGPU_KEY_MIN_USES (env, default 256; negative disables) signatures of the call are registered automatically. */
 int fabgpu_bccsp_verify_batch(fabgpu_ctx* ctx, const uint8_t* keys_xy, int K, const int32_t* key_idx,
                               const uint8_t* digests, const uint32_t* dig_off, const uint8_t* sigs,
                               const uint32_t* sig_off, size_t n, uint8_t* status);
