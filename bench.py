@@ -255,6 +255,29 @@ def run_gpu(args):
     e2e_s = time.perf_counter() - t0
     assert (st == 0).all()
     e2e_phases = ctx.last_timing()
+
+    # ---- BASELINE.json configs[2]: block-validation replay, 10 k txs x 3 endorsements, 3-of-4 policy (rank 0 only) ----
+    block_replay = None
+    if rank == 0 and not args.no_block:
+        from tools import blockgen
+        net = blockgen.Network()
+        blk, binfo = blockgen.build_block(net, args.block_txs, 3, {}, seed=17)
+        ctx.msp_configure([(i.serialized, i.mspid, i.xy, i.valid) for i in net.msp_table], net.policy_n_of(3), net.principals, net.channel)
+        pinned = ctx.block_buffer(len(blk))
+        pinned[:] = np.frombuffer(blk, np.uint8)
+        for _ in range(3):
+            fl = ctx.validate_block(pinned, max_tx=args.block_txs)
+        assert fl.shape[0] == args.block_txs and not fl.any(), "block replay: not every transaction flag is VALID"
+        breps = 10
+        t0 = time.perf_counter()
+        for _ in range(breps):
+            fl = ctx.validate_block(pinned, max_tx=args.block_txs)
+        bms = (time.perf_counter() - t0) / breps * 1e3
+        ph = ctx.block_timing()
+        block_replay = {"workload": "configs[2]: %d txs x (1 creator + 3 endorsement) signatures, 3-of-4 policy, block of %d bytes in pinned host memory" % (args.block_txs, len(blk)),
+                        "api": "fabgpu_validate_block", "ms_per_block": bms, "tx_per_s": args.block_txs / bms * 1e3,
+                        "verifies_per_s": binfo["n_sigs"] / bms * 1e3, "all_flags_valid": True,
+                        "phases_us": {"parse_plan": ph[0], "host_gates": ph[1], "h2d_sha256_verify_d2h": ph[2], "policy_decisions": ph[3]}}
     clocks = sampler.stop() if rank == 0 else None      # sampled across the three timed loops (key-table, generic, e2e)
 
     # ---- max over ranks ---------------------------------------------------------------------------------------
@@ -303,7 +326,10 @@ def run_gpu(args):
             "cpu_baseline": {"value": cpu_v, "unit": "verifies/s", "cores": cores, "kind": "port",
                              "sample": "%d signatures in %.1f s through oracle/c (bccsp/sw gates + ecdsa.Verify steps on OpenSSL BN/EC primitives), %d of %d logical CPUs (best of all/half/quarter)" % (cpu_done, cpu_el, cores, os.cpu_count() or 1)},
             "clocks": clocks,
+            "block_replay": block_replay,
         }
+        if block_replay:
+            block_replay["cpu_port_ms_per_block_est"] = 4 * args.block_txs / cpu_v * 1e3
         print(json.dumps(out))
     ctx.close()
     if world > 1:
@@ -317,6 +343,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=65536, help="signatures per GPU per step")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--block-txs", type=int, default=10000, help="transactions in the block-replay leg (configs[2])")
+    ap.add_argument("--no-block", action="store_true", help="skip the block-replay leg")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

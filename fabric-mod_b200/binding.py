@@ -21,6 +21,7 @@ EXPORTS = [
     "fabgpu_test_fieldop", "fabgpu_test_gtable", "fabgpu_launch_count",
     "fabgpu_keys_register", "fabgpu_key_slot_capacity", "fabgpu_host_key_slots", "fabgpu_verify_p256_keyed",
     "fabgpu_verify_p256_keyed_async", "fabgpu_verify_p256_device_keyed", "fabgpu_last_timing", "fabgpu_build_info",
+    "fabgpu_msp_configure", "fabgpu_validate_block", "fabgpu_block_buffer", "fabgpu_block_timing", "fabgpu_sha256_segments",
 ]
 
 
@@ -219,6 +220,52 @@ class Context:
                                            ctypes.byref(valid), err, ctypes.c_size_t(1024)))
         e = err.value.decode()
         return bool(valid.value), (e if e else None)
+
+    # ---- block level ------------------------------------------------------------------------------------
+    def msp_configure(self, identities, policy_nodes, principals, channel):
+        """identities: list of (serialized: bytes, mspid: str, key_xy: 64 bytes, valid: bool)."""
+        def blob(items):
+            off = np.zeros(len(items) + 1, np.uint32)
+            off[1:] = np.cumsum([len(x) for x in items])
+            b = np.frombuffer(b"".join(items) or b"\x00", np.uint8)
+            return np.ascontiguousarray(b), off
+        idb, ido = blob([bytes(i[0]) for i in identities])
+        mb, mo = blob([i[1].encode() for i in identities])
+        keys = np.ascontiguousarray(np.frombuffer(b"".join(bytes(i[2]) for i in identities) or b"\x00" * 64, np.uint8))
+        valid = np.array([1 if i[3] else 0 for i in identities] or [0], np.uint8)
+        nodes = np.ascontiguousarray(policy_nodes, dtype=np.int32).reshape(-1, 4)
+        pbb, pbo = blob([p.encode() for p in principals])
+        self._ck(lib().fabgpu_msp_configure(self._h, _p(idb), _p(ido), _p(mb), _p(mo), _p(keys), _p(valid), ctypes.c_int(len(identities)),
+                                            _p(nodes), ctypes.c_int(nodes.shape[0]), _p(pbb), _p(pbo), ctypes.c_int(len(principals)),
+                                            ctypes.c_char_p(channel.encode())))
+
+    def block_buffer(self, nbytes):
+        """Pinned staging buffer (numpy view) for block bytes."""
+        p = ctypes.POINTER(ctypes.c_uint8)()
+        self._ck(lib().fabgpu_block_buffer(self._h, ctypes.c_size_t(nbytes), ctypes.byref(p)))
+        return np.ctypeslib.as_array(p, shape=(nbytes,))
+
+    def validate_block(self, block, max_tx=None):
+        """block: bytes or a uint8 numpy array (e.g. a slice of block_buffer()).  Returns the TRANSACTIONS_FILTER bytes."""
+        arr = np.frombuffer(block, np.uint8) if isinstance(block, (bytes, bytearray)) else block
+        cap = max_tx or max(16, arr.shape[0] // 64)
+        flags = np.full(cap, 254, np.uint8)
+        n = ctypes.c_size_t(0)
+        self._ck(lib().fabgpu_validate_block(self._h, _p(arr), ctypes.c_size_t(arr.shape[0]), _p(flags), ctypes.c_size_t(cap), ctypes.byref(n)))
+        return flags[: n.value]
+
+    def block_timing(self):
+        out = (ctypes.c_double * 5)()
+        self._ck(lib().fabgpu_block_timing(self._h, out))
+        return [float(x) for x in out]
+
+    def sha256_segments(self, buf, jobs):
+        """jobs: uint32[n,6] (off0,off1,off2,len0,len1,len2) -> uint8[n,32]."""
+        buf = np.ascontiguousarray(np.frombuffer(buf, np.uint8) if isinstance(buf, (bytes, bytearray)) else buf)
+        jobs = np.ascontiguousarray(jobs, dtype=np.uint32).reshape(-1, 6)
+        out = np.zeros((jobs.shape[0], 32), np.uint8)
+        self._ck(lib().fabgpu_sha256_segments(self._h, _p(buf), ctypes.c_size_t(buf.shape[0]), _p(jobs), ctypes.c_size_t(jobs.shape[0]), _p(out)))
+        return out
 
     def last_timing(self):
         """[key lookup, host gates, device, scatter] microseconds of the last bccsp_verify_batch call."""

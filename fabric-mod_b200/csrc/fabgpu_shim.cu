@@ -20,6 +20,8 @@
 
 #include "../../include/fabgpu_ecdsa.h"
 #include "bccsp_host.hpp"
+#include "blockval.hpp"
+#include "sha256.cuh"
 #include "ecdsa_kernels.cuh"
 
 #if defined(__SSE2__)
@@ -131,6 +133,25 @@ struct fabgpu_ctx {
     unsigned long long tick = 0;
     int key_min_uses = 256;
     double timing[4] = {0, 0, 0, 0};   // last fabgpu_bccsp_verify_batch: key lookup, host gates, device (H2D+kernel+D2H), scatter [us]
+    // block validation (fabgpu_msp_configure / fabgpu_validate_block), device 0 of the context
+    blockval::MspTable msp;
+    std::vector<blockval::PolicyNode> policy;
+    std::vector<std::string> principals;
+    std::string channel;
+    std::vector<int32_t> identity_slot;
+    struct BlockBufs {
+        uint8_t* d_block = nullptr; size_t block_cap = 0;
+        uint8_t* h_block = nullptr; size_t h_block_cap = 0;       // optional pinned staging the caller may fill directly
+        size_t job_cap = 0;                                       // signature jobs
+        size_t sha_cap = 0;                                       // all digests (signature jobs + 2 per transaction)
+        ShaJob* d_sha = nullptr; ShaJob* h_sha = nullptr;
+        uint8_t* d_dig = nullptr; uint8_t* h_dig = nullptr;       // h_dig: check digests only
+        uint8_t *d_r = nullptr, *d_s = nullptr, *d_qx = nullptr, *d_qy = nullptr;
+        uint8_t *h_r = nullptr, *h_s = nullptr, *h_qx = nullptr, *h_qy = nullptr;
+        int32_t *d_ks = nullptr, *h_ks = nullptr;
+        uint32_t *d_mask = nullptr, *d_off = nullptr, *h_mask = nullptr;
+    } bb;
+    double block_timing[5] = {0, 0, 0, 0, 0};   // plan, gates, device, decide, total [us]
 };
 
 namespace {
@@ -252,6 +273,14 @@ int wait_slot(fabgpu_ctx* ctx, int slot)
 
 void free_all(fabgpu_ctx* ctx)
 {
+    {
+        auto& bb = ctx->bb;
+        if (!ctx->devs.empty()) cudaSetDevice(ctx->devs[0].id);
+        void* dev_ptrs[] = {bb.d_block, bb.d_sha, bb.d_dig, bb.d_r, bb.d_s, bb.d_qx, bb.d_qy, bb.d_ks, bb.d_mask, bb.d_off};
+        for (void* p : dev_ptrs) if (p) cudaFree(p);
+        void* host_ptrs[] = {bb.h_block, bb.h_sha, bb.h_dig, bb.h_r, bb.h_s, bb.h_qx, bb.h_qy, bb.h_ks, bb.h_mask};
+        for (void* p : host_ptrs) if (p) cudaFreeHost(p);
+    }
     for (auto& dv : ctx->devs) {
         cudaSetDevice(dv.id);
         if (dv.gtab) cudaFree(dv.gtab);
@@ -335,6 +364,9 @@ int init_impl(fabgpu_ctx* ctx, const int* device_ids, int n_dev, size_t max_batc
     }
     return FABGPU_OK;
 }
+
+template <typename T> int grow_dev(fabgpu_ctx* ctx, T*& p, size_t bytes) { if (p) cudaFree(p); p = nullptr; CK(ctx, cudaMalloc(&p, bytes)); return FABGPU_OK; }
+template <typename T> int grow_host(fabgpu_ctx* ctx, T*& p, size_t bytes) { if (p) cudaFreeHost(p); p = nullptr; CK(ctx, cudaHostAlloc(&p, bytes, cudaHostAllocPortable)); return FABGPU_OK; }
 
 }  // namespace
 
@@ -700,6 +732,220 @@ int fabgpu_bccsp_verify(fabgpu_ctx* ctx, const uint8_t* key_xy, const uint8_t* s
     if (off & 1u) { ctx->last_error = "public key is not on P-256"; return FABGPU_E_ARG; }
     *valid = (int)(mask & 1u);
     return finish("");
+}
+
+// ---- block-level pre-pass -------------------------------------------------------------------------------------------
+
+int fabgpu_msp_configure(fabgpu_ctx* ctx, const uint8_t* id_blob, const uint32_t* id_off, const uint8_t* mspid_blob,
+                         const uint32_t* mspid_off, const uint8_t* keys_xy, const uint8_t* valid, int n_ids,
+                         const int32_t* policy_nodes, int n_nodes, const uint8_t* principal_blob, const uint32_t* principal_off,
+                         int n_principals, const char* channel_id)
+{
+    if (!ctx || n_ids < 0 || n_nodes < 0 || n_principals < 0 || !channel_id) return FABGPU_E_ARG;
+    if (n_ids && (!id_blob || !id_off || !mspid_blob || !mspid_off || !keys_xy || !valid)) return FABGPU_E_ARG;
+    {
+        std::lock_guard<std::mutex> lk0(ctx->slot0_mu);
+        ctx->msp = blockval::MspTable();
+        for (int i = 0; i < n_ids; i++) {
+            ctx->msp.by_bytes.emplace(std::string((const char*)id_blob + id_off[i], id_off[i + 1] - id_off[i]), i);
+            ctx->msp.mspid.emplace_back((const char*)mspid_blob + mspid_off[i], mspid_off[i + 1] - mspid_off[i]);
+        }
+        ctx->msp.keys_xy.assign(keys_xy, keys_xy + 64 * (size_t)n_ids);
+        ctx->msp.valid.assign(valid, valid + n_ids);
+        ctx->policy.clear();
+        for (int i = 0; i < n_nodes; i++)
+            ctx->policy.push_back({policy_nodes[4 * i], policy_nodes[4 * i + 1], policy_nodes[4 * i + 2], policy_nodes[4 * i + 3]});
+        for (const auto& nd : ctx->policy)
+            if (nd.type == 0 && (nd.first_child < 0 || nd.n_children < 0 || nd.first_child + nd.n_children > n_nodes)) {
+                ctx->last_error = "policy node children out of range"; return FABGPU_E_ARG;
+            }
+        ctx->principals.clear();
+        for (int i = 0; i < n_principals; i++)
+            ctx->principals.emplace_back((const char*)principal_blob + principal_off[i], principal_off[i + 1] - principal_off[i]);
+        ctx->channel = channel_id;
+        ctx->identity_slot.assign(n_ids, -1);
+    }
+    // identities are long-lived: give every key a table now (what KeyImport does when the MSP deserialises an identity)
+    if (n_ids > 0 && n_ids <= ctx->key_slots) {
+        int rc = fabgpu_keys_register(ctx, keys_xy, n_ids, ctx->identity_slot.data());
+        if (rc) return rc;
+    }
+    return FABGPU_OK;
+}
+
+int fabgpu_block_buffer(fabgpu_ctx* ctx, size_t bytes, uint8_t** out)
+{
+    if (!ctx || !out) return FABGPU_E_ARG;
+    std::lock_guard<std::mutex> lk0(ctx->slot0_mu);
+    auto& bb = ctx->bb;
+    CK(ctx, cudaSetDevice(ctx->devs[0].id));
+    if (bytes > bb.h_block_cap) { int rc = grow_host(ctx, bb.h_block, bytes); if (rc) return rc; bb.h_block_cap = bytes; }
+    *out = bb.h_block;
+    return FABGPU_OK;
+}
+
+int fabgpu_validate_block(fabgpu_ctx* ctx, const uint8_t* block, size_t block_len, uint8_t* flags, size_t flags_cap, size_t* n_tx_out)
+{
+    if (!ctx || !block || !flags || !n_tx_out) return FABGPU_E_ARG;
+    if (block_len >= (1ull << 32)) { ctx->last_error = "block larger than 4 GiB"; return FABGPU_E_ARG; }
+    if (fault_injected()) { ctx->last_error = "fault injected (FABGPU_FAULT_INJECT=1)"; return FABGPU_E_INJECTED; }
+    std::lock_guard<std::mutex> lk0(ctx->slot0_mu);
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto us = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+        return std::chrono::duration<double, std::micro>(b - a).count();
+    };
+    auto t0 = now();
+    Device& dv = ctx->devs[0];
+    DevSlot& ds = dv.slot[0];
+    auto& bb = ctx->bb;
+    CK(ctx, cudaSetDevice(dv.id));
+    // 1. the block goes to the device while the host parses it
+    if (block_len > bb.block_cap) { int rc = grow_dev(ctx, bb.d_block, block_len + (block_len >> 2)); if (rc) return rc; bb.block_cap = block_len + (block_len >> 2); }
+    CK(ctx, cudaMemcpyAsync(bb.d_block, block, block_len, cudaMemcpyHostToDevice, ds.stream));
+    // 2. plan: every signature the block needs, every digest the transaction checks need
+    blockval::BlockPlan plan;
+    const int TH = ctx->pool->size();
+    {
+        std::vector<blockval::Seg> envs;
+        if (!blockval::split_block(block, block_len, envs)) {
+            cudaStreamSynchronize(ds.stream);
+            ctx->last_error = "block does not parse";
+            return FABGPU_E_ARG;
+        }
+        plan.txs.assign(envs.size(), blockval::TxPlan());
+        std::vector<std::vector<blockval::SigJob>> parts(TH);
+        std::vector<size_t> bounds(TH + 1);
+        for (int k = 0; k <= TH; k++) bounds[k] = envs.size() * (size_t)k / TH;
+        ctx->pool->run([&](int tid) {
+            parts[tid].reserve((bounds[tid + 1] - bounds[tid]) * 4 + 4);
+            blockval::plan_range(block, envs, bounds[tid], bounds[tid + 1], ctx->msp, ctx->channel, plan.txs.data(), parts[tid]);
+        });
+        blockval::merge_plan(plan, parts, bounds);
+    }
+    const size_t T = plan.txs.size(), J = plan.jobs.size(), C = (size_t)plan.n_check, S = J + 2 * C;
+    *n_tx_out = T;
+    if (T > flags_cap) { cudaStreamSynchronize(ds.stream); ctx->last_error = "flags buffer too small"; return FABGPU_E_ARG; }
+    auto t1 = now();
+    if (J > bb.job_cap) {
+        const size_t cap = round_up32(J + (J >> 2) + 1024);
+        int rc = 0;
+        rc |= grow_dev(ctx, bb.d_r, 32 * cap); rc |= grow_dev(ctx, bb.d_s, 32 * cap); rc |= grow_dev(ctx, bb.d_qx, 32 * cap); rc |= grow_dev(ctx, bb.d_qy, 32 * cap);
+        rc |= grow_host(ctx, bb.h_r, 32 * cap); rc |= grow_host(ctx, bb.h_s, 32 * cap); rc |= grow_host(ctx, bb.h_qx, 32 * cap); rc |= grow_host(ctx, bb.h_qy, 32 * cap);
+        rc |= grow_dev(ctx, bb.d_ks, 4 * cap); rc |= grow_host(ctx, bb.h_ks, 4 * cap);
+        rc |= grow_dev(ctx, bb.d_mask, cap / 8 + 4); rc |= grow_dev(ctx, bb.d_off, cap / 8 + 4); rc |= grow_host(ctx, bb.h_mask, cap / 8 + 4);
+        if (rc) return FABGPU_E_CUDA;
+        bb.job_cap = cap;
+    }
+    if (S > bb.sha_cap) {
+        const size_t cap = S + (S >> 2) + 1024;
+        int rc = 0;
+        rc |= grow_dev(ctx, bb.d_sha, sizeof(ShaJob) * cap); rc |= grow_host(ctx, bb.h_sha, sizeof(ShaJob) * cap);
+        rc |= grow_dev(ctx, bb.d_dig, 32 * cap); rc |= grow_host(ctx, bb.h_dig, 32 * cap);
+        if (rc) return FABGPU_E_CUDA;
+        bb.sha_cap = cap;
+    }
+    // 3. host gates on every signature (DER, R > 0, S > 0, low-S, r < 2^256) + digest job descriptors
+    std::vector<uint8_t> gate_ok(J, 0);
+    bool all_slots = true;
+    for (size_t j = 0; j < J && all_slots; j++) all_slots = ctx->identity_slot[plan.jobs[j].identity] >= 0;
+    static const uint8_t kZero32[32] = {0};
+    ctx->pool->run([&](int tid) {
+        const size_t lo = J * (size_t)tid / TH, hi = J * (size_t)(tid + 1) / TH;
+        for (size_t j = lo; j < hi; j++) {
+            const blockval::SigJob& sj = plan.jobs[j];
+            host::Gate g;
+            host::gate_signature(block + sj.sig.off, sj.sig.len, g, false);
+            const bool ok = g.status == FABGPU_ST_VALID;
+            gate_ok[j] = ok;
+            stage32(bb.h_r + 32 * j, ok ? g.r : kZero32);
+            stage32(bb.h_s + 32 * j, ok ? g.s : kZero32);
+            stage_i32(bb.h_ks + j, ctx->identity_slot[sj.identity]);
+            if (!all_slots) {
+                stage32(bb.h_qx + 32 * j, ctx->msp.keys_xy.data() + 64 * (size_t)sj.identity);
+                stage32(bb.h_qy + 32 * j, ctx->msp.keys_xy.data() + 64 * (size_t)sj.identity + 32);
+            }
+            ShaJob& sh = bb.h_sha[j];
+            sh.off[0] = sj.msg[0].off; sh.len[0] = sj.msg[0].len; sh.off[1] = sj.msg[1].off; sh.len[1] = sj.msg[1].len; sh.off[2] = 0; sh.len[2] = 0;
+        }
+        const size_t tlo = T * (size_t)tid / TH, thi = T * (size_t)(tid + 1) / TH;
+        for (size_t t = tlo; t < thi; t++) {
+            const blockval::TxPlan& tx = plan.txs[t];
+            if (tx.check_job < 0) continue;
+            ShaJob& a = bb.h_sha[J + 2 * (size_t)tx.check_job];
+            ShaJob& b = bb.h_sha[J + 2 * (size_t)tx.check_job + 1];
+            a.off[0] = tx.txid_msg[0].off; a.len[0] = tx.txid_msg[0].len; a.off[1] = tx.txid_msg[1].off; a.len[1] = tx.txid_msg[1].len; a.off[2] = 0; a.len[2] = 0;
+            for (int k = 0; k < 3; k++) { b.off[k] = tx.phash_msg[k].off; b.len[k] = tx.phash_msg[k].len; }
+        }
+        stage_fence();
+    });
+    auto t2 = now();
+    // 4. device: digests of every signed message (and the check digests), then one verification batch
+    const size_t words = (J + 31) / 32;
+    if (S) {
+        CK(ctx, cudaMemcpyAsync(bb.d_sha, bb.h_sha, sizeof(ShaJob) * S, cudaMemcpyHostToDevice, ds.stream));
+        sha256_segments_kernel<<<(unsigned)((S + 127) / 128), 128, 0, ds.stream>>>(bb.d_block, bb.d_sha, (uint32_t)S, bb.d_dig);
+        ctx->launches++;
+        CK(ctx, cudaGetLastError());
+    }
+    if (J) {
+        CK(ctx, cudaMemcpyAsync(bb.d_r, bb.h_r, 32 * J, cudaMemcpyHostToDevice, ds.stream));
+        CK(ctx, cudaMemcpyAsync(bb.d_s, bb.h_s, 32 * J, cudaMemcpyHostToDevice, ds.stream));
+        CK(ctx, cudaMemcpyAsync(bb.d_ks, bb.h_ks, 4 * J, cudaMemcpyHostToDevice, ds.stream));
+        if (!all_slots) {
+            CK(ctx, cudaMemcpyAsync(bb.d_qx, bb.h_qx, 32 * J, cudaMemcpyHostToDevice, ds.stream));
+            CK(ctx, cudaMemcpyAsync(bb.d_qy, bb.h_qy, 32 * J, cudaMemcpyHostToDevice, ds.stream));
+        }
+        int rc = launch_verify(ctx, dv, all_slots ? MODE_CACHED : MODE_MIXED, bb.d_ks, bb.d_qx, bb.d_qy, bb.d_dig, bb.d_r, bb.d_s, J, bb.d_mask,
+                               bb.d_off, ds.stream);
+        if (rc) return rc;
+        CK(ctx, cudaMemcpyAsync(bb.h_mask, bb.d_mask, 4 * words, cudaMemcpyDeviceToHost, ds.stream));
+    }
+    if (C) CK(ctx, cudaMemcpyAsync(bb.h_dig, bb.d_dig + 32 * J, 64 * C, cudaMemcpyDeviceToHost, ds.stream));
+    CK(ctx, cudaStreamSynchronize(ds.stream));
+    auto t3 = now();
+    // 5. replay the reference's per-transaction decisions on the results
+    std::vector<uint8_t> sig_valid(J ? J : 1, 0);
+    for (size_t j = 0; j < J; j++) sig_valid[j] = gate_ok[j] && ((bb.h_mask[j >> 5] >> (j & 31)) & 1u);
+    // digests arrive as [txid_0, phash_0, txid_1, phash_1, ...]; decide_block wants two strided views
+    std::vector<uint8_t> txid_d(32 * (C ? C : 1)), phash_d(32 * (C ? C : 1));
+    for (size_t c = 0; c < C; c++) { memcpy(&txid_d[32 * c], bb.h_dig + 64 * c, 32); memcpy(&phash_d[32 * c], bb.h_dig + 64 * c + 32, 32); }
+    ctx->pool->run([&](int tid) {
+        blockval::decide_range(block, plan, ctx->msp, ctx->policy, ctx->principals, sig_valid.data(), txid_d.data(), phash_d.data(),
+                               T * (size_t)tid / TH, T * (size_t)(tid + 1) / TH, flags);
+    });
+    blockval::mark_duplicates(block, plan, flags);
+    auto t4 = now();
+    ctx->block_timing[0] = us(t0, t1); ctx->block_timing[1] = us(t1, t2); ctx->block_timing[2] = us(t2, t3); ctx->block_timing[3] = us(t3, t4);
+    ctx->block_timing[4] = us(t0, t4);
+    return FABGPU_OK;
+}
+
+int fabgpu_block_timing(const fabgpu_ctx* ctx, double out_us[5])
+{
+    if (!ctx || !out_us) return FABGPU_E_ARG;
+    for (int i = 0; i < 5; i++) out_us[i] = ctx->block_timing[i];
+    return FABGPU_OK;
+}
+
+// digests[j] = SHA-256(buf[off0..) || buf[off1..) || buf[off2..)) on the device; jobs: n x 6 uint32 (off0,off1,off2,len0,len1,len2)
+int fabgpu_sha256_segments(fabgpu_ctx* ctx, const uint8_t* buf, size_t buf_len, const uint32_t* jobs, size_t n, uint8_t* digests)
+{
+    if (!ctx || !buf || !jobs || !digests) return FABGPU_E_ARG;
+    std::lock_guard<std::mutex> lk0(ctx->slot0_mu);
+    Device& dv = ctx->devs[0];
+    CK(ctx, cudaSetDevice(dv.id));
+    uint8_t *d_buf = nullptr, *d_dig = nullptr; ShaJob* d_jobs = nullptr;
+    CK(ctx, cudaMalloc(&d_buf, buf_len ? buf_len : 1)); CK(ctx, cudaMalloc(&d_jobs, sizeof(ShaJob) * (n ? n : 1))); CK(ctx, cudaMalloc(&d_dig, 32 * (n ? n : 1)));
+    CK(ctx, cudaMemcpy(d_buf, buf, buf_len, cudaMemcpyHostToDevice));
+    CK(ctx, cudaMemcpy(d_jobs, jobs, sizeof(ShaJob) * n, cudaMemcpyHostToDevice));
+    if (n) {
+        sha256_segments_kernel<<<(unsigned)((n + 127) / 128), 128>>>(d_buf, d_jobs, (uint32_t)n, d_dig);
+        ctx->launches++;
+        CK(ctx, cudaGetLastError());
+    }
+    CK(ctx, cudaMemcpy(digests, d_dig, 32 * n, cudaMemcpyDeviceToHost));
+    cudaFree(d_buf); cudaFree(d_jobs); cudaFree(d_dig);
+    return FABGPU_OK;
 }
 
 int fabgpu_test_fieldop(fabgpu_ctx* ctx, int op, const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out)

@@ -131,6 +131,35 @@ int fabgpu_bccsp_verify(fabgpu_ctx* ctx, const uint8_t* key_xy, const uint8_t* s
  * passed, ask the GPU"; FABGPU_ST_INVALID means r >= 2^256 (cannot be < N). */
 int fabgpu_gate_signature(const uint8_t* sig, size_t sig_len, uint8_t r_out[32], uint8_t s_out[32]);
 
+/* ---- block level: the signature pre-pass of TxValidator.Validate ----
+ * One call verifies every signature of a serialized common.Block as ONE GPU batch -- creator signatures
+ * (core/common/validation/msgvalidation.go:26-64) and endorsement signatures (statebased/validator_keylevel.go:243-259,
+ * common/policies/policy.go:365-402) -- with the SHA-256 of each signed message computed on the device straight from the
+ * block bytes, then replays the reference's per-transaction decision order (msgvalidation.go:248-320, v20/validator.go:
+ * 300-455, cauthdsl.go:24-92, markTXIdDuplicates) and writes the TRANSACTIONS_FILTER bytes (peer.TxValidationCode).
+ * Outside the pre-pass, exactly as mocked in the reference's unit tests: ledger lookups, chaincode definitions, rw-sets,
+ * key-level policies.  Config transactions are flagged 254 (NOT_VALIDATED) and must be validated by the CPU validator. */
+
+/* Installs the MSP view and the endorsement policy used by fabgpu_validate_block.
+ * identities: n_ids serialized msp.SerializedIdentity byte strings (id_blob + (n_ids+1) offsets) exactly as they appear in
+ * SignatureHeader.creator / Endorsement.endorser, their MSP ids, P-256 keys (X||Y) and the outcome of identity.Validate().
+ * policy_nodes: n_nodes x 4 int32 (type, n, first_child, n_children); type 0 = NOutOf(n) over children
+ * [first_child, first_child + n_children), type 1 = SignedBy(principal n); node 0 is the root.  Principals are MSP ids
+ * (ROLE member).  Every identity's key gets a fixed-base table. */
+int fabgpu_msp_configure(fabgpu_ctx* ctx, const uint8_t* id_blob, const uint32_t* id_off, const uint8_t* mspid_blob,
+                         const uint32_t* mspid_off, const uint8_t* keys_xy, const uint8_t* valid, int n_ids,
+                         const int32_t* policy_nodes, int n_nodes, const uint8_t* principal_blob, const uint32_t* principal_off,
+                         int n_principals, const char* channel_id);
+/* flags[i] receives the validation code of transaction i; *n_tx_out the number of transactions. */
+int fabgpu_validate_block(fabgpu_ctx* ctx, const uint8_t* block, size_t block_len, uint8_t* flags, size_t flags_cap, size_t* n_tx_out);
+/* Optional pinned staging buffer for the block bytes (the H2D copy of a pageable buffer is several times slower). */
+int fabgpu_block_buffer(fabgpu_ctx* ctx, size_t bytes, uint8_t** out);
+/* Phase times of the last fabgpu_validate_block, microseconds: parse/plan, host gates, device, decisions, total. */
+int fabgpu_block_timing(const fabgpu_ctx* ctx, double out_us[5]);
+/* Device SHA-256 of messages given as up to three byte ranges of `buf` each: jobs = n x {off0,off1,off2,len0,len1,len2}
+ * (uint32); digests = n x 32 bytes.  (The hash msp identity.Verify computes first: msp/identities.go:178.) */
+int fabgpu_sha256_segments(fabgpu_ctx* ctx, const uint8_t* buf, size_t buf_len, const uint32_t* jobs, size_t n, uint8_t* digests);
+
 /* ---- test / bring-up hooks ------------------------------------------------------------------------------ */
 /* Device field primitives on arrays (op: 0 fe_mul, 1 fe_add, 2 fe_sub, 3 sc_mul, 4 fe_inv,
  * 5 sc_inv_to_mont by Fermat, 6 the same by division steps, 7 fe_sqr). */

@@ -1,0 +1,70 @@
+"""Host logic of the block pre-pass (fabric-mod_b200/csrc/blockval.cpp) against the oracle's restatement of the reference's
+validator (oracle/blockval.py), on the CPU: every fault class of tools/blockgen.py, policy-evaluator semantics, duplicates."""
+import numpy as np
+
+from oracle import blockval as ob
+from tools import blockgen
+from tools import fabricpb as pb
+import blockutil
+
+
+def test_fault_classes_match_oracle():
+    net = blockgen.Network()
+    faults = blockutil.fault_map(70)
+    assert set(faults.values()) == set(blockgen.FAULTS)
+    blk, info = blockgen.build_block(net, 70, 3, faults, seed=11, nthreads=2)
+    ids = blockutil.identities_of(net)
+    exp = ob.validate_block(blk, ids, net.channel, net.policy_n_of(3), net.principals)
+    got, njobs = blockutil.host_logic_flags(blk, ids, net.channel, net.policy_n_of(3), net.principals)
+    assert got.tolist() == exp.tolist()
+    seen = set(int(x) for x in exp)
+    assert {ob.VALID, ob.BAD_PAYLOAD, ob.BAD_COMMON_HEADER, ob.BAD_CREATOR_SIGNATURE, ob.INVALID_ENDORSER_TRANSACTION, ob.UNSUPPORTED_TX_PAYLOAD,
+            ob.BAD_PROPOSAL_TXID, ob.DUPLICATE_TXID, ob.ENDORSEMENT_POLICY_FAILURE, ob.TARGET_CHAIN_NOT_FOUND} <= seen
+    for t in range(70):
+        if t not in faults:
+            assert exp[t] == ob.VALID, t
+    assert exp[[t for t, f in faults.items() if f == "dup_txid"][0]] == ob.DUPLICATE_TXID
+
+
+def test_policy_thresholds_and_dedup():
+    # common/policies/policy_test.go:255-288 (two identical SignedData => one identity) and cauthdsl N-out-of semantics
+    net = blockgen.Network()
+    ids = blockutil.identities_of(net)
+    blk, _ = blockgen.build_block(net, 12, 3, {3: "dup_endorser", 5: "bad_endorsement_sig", 7: "unknown_endorser"}, seed=3, nthreads=2)
+    for n, expect_fail in ((2, []), (3, [3, 5, 7]), (4, list(range(12)))):
+        exp = ob.validate_block(blk, ids, net.channel, net.policy_n_of(n), net.principals)
+        got, _ = blockutil.host_logic_flags(blk, ids, net.channel, net.policy_n_of(n), net.principals)
+        assert got.tolist() == exp.tolist()
+        assert [t for t in range(12) if exp[t] == ob.ENDORSEMENT_POLICY_FAILURE] == expect_fail
+    # nested policy: AND(Org1, OR(Org2, Org3)) = NOutOf(2, [SignedBy 0, NOutOf(1, [SignedBy 1, SignedBy 2])])
+    nodes = np.array([(0, 2, 1, 2), (1, 0, 0, 0), (0, 1, 3, 2), (1, 1, 0, 0), (1, 2, 0, 0)], np.int32)
+    exp = ob.validate_block(blk, ids, net.channel, nodes, net.principals)
+    got, _ = blockutil.host_logic_flags(blk, ids, net.channel, nodes, net.principals)
+    assert got.tolist() == exp.tolist() and ob.VALID in exp and ob.ENDORSEMENT_POLICY_FAILURE in exp
+
+
+def test_structural_corner_cases():
+    net = blockgen.Network()
+    ids = blockutil.identities_of(net)
+    blk, _ = blockgen.build_block(net, 6, 3, {}, seed=5, nthreads=2)
+    envs = pb.parse(pb.parse(blk, ob.S_BLOCK)["data"], ob.S_BLOCKDATA)["data"]
+    good = envs[0]
+    variants = [
+        good,
+        b"",                                              # empty envelope bytes
+        b"\x0a\x05abc",                                   # truncated length-delimited field
+        pb.f_uint(1, 5),                                  # payload field with varint wire type
+        good + pb.f_bytes(9, b"unknown field is skipped"),
+        pb.f_bytes(1, b""),                               # empty payload
+        envs[1][: len(envs[1]) // 2],                     # cut in the middle
+        pb.f_bytes(2, b"sig-only"),
+    ]
+    blk2 = pb.block(9, variants)
+    exp = ob.validate_block(blk2, ids, net.channel, net.policy_n_of(3), net.principals)
+    got, _ = blockutil.host_logic_flags(blk2, ids, net.channel, net.policy_n_of(3), net.principals)
+    assert got.tolist() == exp.tolist()
+    assert exp[0] == ob.VALID and exp[4] == ob.DUPLICATE_TXID       # same transaction + an unknown field: parses, same tx id
+    assert exp[1] == ob.BAD_COMMON_HEADER and exp[5] == ob.BAD_COMMON_HEADER
+    # empty block
+    blk3 = pb.block(10, [])
+    assert blockutil.host_logic_flags(blk3, ids, net.channel, net.policy_n_of(3), net.principals)[0].tolist() == []

@@ -1,0 +1,90 @@
+"""GPU: device SHA-256 and the block-level pre-pass (fabgpu_validate_block) against hashlib and the oracle's block validator."""
+import hashlib
+import random
+
+import numpy as np
+import pytest
+
+from oracle import blockval as ob
+from tools import blockgen
+from util import pkg
+import blockutil
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = pkg().binding.Context(max_batch=8192)
+    yield c
+    c.close()
+
+
+def test_sha256_segments_vs_hashlib(ctx):
+    rnd = random.Random(9)
+    buf = bytes(rnd.getrandbits(8) for _ in range(20000))
+    jobs, exp = [], []
+    lens = [0, 1, 3, 4, 5, 31, 32, 33, 54, 55, 56, 57, 63, 64, 65, 119, 120, 127, 128, 129, 1000, 4097]
+    for la in lens:
+        for lb in (0, 1, 7, 64, 333):
+            for lc in (0, 5):
+                oa, ob_, oc = rnd.randrange(0, 9000), rnd.randrange(0, 9000), rnd.randrange(0, 9000)
+                jobs.append((oa, ob_, oc, la, lb, lc))
+                exp.append(hashlib.sha256(buf[oa:oa + la] + buf[ob_:ob_ + lb] + buf[oc:oc + lc]).digest())
+    got = ctx.sha256_segments(buf, np.array(jobs, np.uint32))
+    assert [bytes(g) for g in got] == exp
+
+
+def _configure(ctx, net, n):
+    ctx.msp_configure(blockutil.identities_of(net), net.policy_n_of(n), net.principals, net.channel)
+
+
+def test_block_fault_classes_match_oracle(ctx):
+    net = blockgen.Network()
+    faults = blockutil.fault_map(70)
+    blk, _ = blockgen.build_block(net, 70, 3, faults, seed=11)
+    exp = ob.validate_block(blk, blockutil.identities_of(net), net.channel, net.policy_n_of(3), net.principals)
+    _configure(ctx, net, 3)
+    got = ctx.validate_block(blk)
+    assert got.tolist() == exp.tolist()
+    assert len(set(exp.tolist())) >= 10
+    # other thresholds / nested policy reuse the same block
+    for n in (2, 4):
+        _configure(ctx, net, n)
+        assert ctx.validate_block(blk).tolist() == ob.validate_block(blk, blockutil.identities_of(net), net.channel, net.policy_n_of(n), net.principals).tolist()
+
+
+def test_block_2000_tx_mixed_and_pinned_buffer(ctx):
+    net = blockgen.Network(n_orgs=4, n_clients=3)
+    rnd = random.Random(4)
+    faults = {t: rnd.choice(blockgen.FAULTS) for t in rnd.sample(range(1, 2000), 240)}
+    blk, _ = blockgen.build_block(net, 2000, 3, faults, seed=13)
+    exp = ob.validate_block(blk, blockutil.identities_of(net), net.channel, net.policy_n_of(3), net.principals)
+    _configure(ctx, net, 3)
+    assert ctx.validate_block(blk).tolist() == exp.tolist()
+    pinned = ctx.block_buffer(len(blk))
+    pinned[:] = np.frombuffer(blk, np.uint8)
+    assert ctx.validate_block(pinned).tolist() == exp.tolist()
+    assert 1700 < int((exp == ob.VALID).sum()) < 1800
+
+
+def test_config3_block_replay_10k_tx(ctx):
+    # BASELINE.json configs[2]: 10 k synthetic txs x 3 endorsements, 3-of-4 policy: 40 000 verifications, every flag VALID
+    net = blockgen.Network()
+    blk, info = blockgen.build_block(net, 10000, 3, {}, seed=17)
+    assert info["n_sigs"] == 40000
+    _configure(ctx, net, 3)
+    pinned = ctx.block_buffer(len(blk))
+    pinned[:] = np.frombuffer(blk, np.uint8)
+    got = ctx.validate_block(pinned)
+    assert got.shape[0] == 10000 and (got == ob.VALID).all()
+    exp = ob.validate_block(blk, blockutil.identities_of(net), net.channel, net.policy_n_of(3), net.principals)
+    assert (exp == ob.VALID).all()
+    # one flipped byte inside one endorsement signature flips exactly that transaction
+    b = bytearray(blk)
+    marker = net.peers[1].serialized
+    pos = blk.index(marker, len(blk) // 2) + len(marker) + 10
+    b[pos] ^= 0x20
+    got2 = ctx.validate_block(bytes(b))
+    exp2 = ob.validate_block(bytes(b), blockutil.identities_of(net), net.channel, net.policy_n_of(3), net.principals)
+    assert got2.tolist() == exp2.tolist() and int((got2 != ob.VALID).sum()) == 1
