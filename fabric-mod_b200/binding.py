@@ -21,7 +21,7 @@ EXPORTS = [
     "fabgpu_test_fieldop", "fabgpu_test_gtable", "fabgpu_launch_count",
     "fabgpu_keys_register", "fabgpu_key_slot_capacity", "fabgpu_host_key_slots", "fabgpu_verify_p256_keyed",
     "fabgpu_verify_p256_keyed_async", "fabgpu_verify_p256_device_keyed", "fabgpu_last_timing", "fabgpu_build_info",
-    "fabgpu_msp_configure", "fabgpu_validate_block", "fabgpu_block_buffer", "fabgpu_block_timing", "fabgpu_sha256_segments",
+    "fabgpu_msp_configure", "fabgpu_validate_block", "fabgpu_validate_envelopes", "fabgpu_block_buffer", "fabgpu_block_timing", "fabgpu_sha256_segments",
 ]
 
 
@@ -252,6 +252,17 @@ class Context:
         flags = np.full(cap, 254, np.uint8)
         n = ctypes.c_size_t(0)
         self._ck(lib().fabgpu_validate_block(self._h, _p(arr), ctypes.c_size_t(arr.shape[0]), _p(flags), ctypes.c_size_t(cap), ctypes.byref(n)))
+        return flags[: n.value]
+
+    def validate_envelopes(self, blob, env_off):
+        """blob: uint8 array holding the envelopes back to back; env_off: uint32[n+1].  Returns the flags."""
+        arr = np.frombuffer(blob, np.uint8) if isinstance(blob, (bytes, bytearray)) else blob
+        env_off = np.ascontiguousarray(env_off, dtype=np.uint32)
+        n_env = env_off.shape[0] - 1
+        flags = np.full(max(n_env, 1), 254, np.uint8)
+        n = ctypes.c_size_t(0)
+        self._ck(lib().fabgpu_validate_envelopes(self._h, _p(arr), _p(env_off), ctypes.c_size_t(n_env), _p(flags), ctypes.c_size_t(max(n_env, 1)),
+                                                 ctypes.byref(n)))
         return flags[: n.value]
 
     def block_timing(self):

@@ -2,6 +2,9 @@
 #include "blockval.hpp"
 
 #include <cstring>
+#include <string_view>
+#include <algorithm>
+#include <unordered_map>
 
 namespace fabgpu { namespace blockval {
 
@@ -75,8 +78,7 @@ bool parse_msg(const uint8_t* base, Seg msg, const Want* wants, int nw, uint32_t
 
 int lookup_identity(const MspTable& msp, const uint8_t* base, Seg s)
 {
-    auto it = msp.by_bytes.find(std::string((const char*)base + s.off, s.len));
-    return it == msp.by_bytes.end() ? -1 : it->second;
+    return msp.find(base + s.off, s.len);
 }
 
 bool seg_equals(const uint8_t* base, Seg s, const std::string& str)
@@ -84,7 +86,7 @@ bool seg_equals(const uint8_t* base, Seg s, const std::string& str)
     return s.len == str.size() && memcmp(base + s.off, str.data(), s.len) == 0;
 }
 
-void plan_tx(const uint8_t* base, Seg env, const MspTable& msp, const std::string& channel, TxPlan& tx, std::vector<SigJob>& jobs)
+void plan_tx(const uint8_t* base, Seg env, const MspTable& msp, const std::string& channel, TxPlan& tx, JobPart& jobs)
 {
     // Envelope{payload=1, signature=2}: v20/validator.go:313-320.  Zero-length data unmarshals to an empty Envelope
     // (protoutil.GetEnvelopeFromBlock), whose empty Payload has no header -> BAD_COMMON_HEADER, like the reference.
@@ -114,8 +116,8 @@ void plan_tx(const uint8_t* base, Seg env, const MspTable& msp, const std::strin
     tx.creator_identity = lookup_identity(msp, base, creator);
     if (has_sig && signature.len > 0 && has_payload && payload.len > 0 && tx.creator_identity >= 0) {
         SigJob j; j.identity = tx.creator_identity; j.msg[0] = payload; j.sig = signature;
-        tx.creator_job = (int)jobs.size();
-        jobs.push_back(j);
+        tx.creator_job = (int)jobs.creators.size();
+        jobs.creators.push_back(j);
     }
     if (ht != 3) return;                                       // CONFIG / CONFIG_UPDATE: decided in decide_block
     tx.txid_ascii = txid;
@@ -153,8 +155,8 @@ void plan_tx(const uint8_t* base, Seg env, const MspTable& msp, const std::strin
         en.identity = lookup_identity(msp, base, endorser);
         if (en.identity >= 0 && esig.len > 0) {
             SigJob j; j.identity = en.identity; j.msg[0] = prp; j.msg[1] = endorser; j.sig = esig;
-            en.job = (int)jobs.size();
-            jobs.push_back(j);
+            en.job = (int)jobs.endorsements.size();
+            jobs.endorsements.push_back(j);
         }
         tx.ends.push_back(en);
     }
@@ -201,25 +203,27 @@ bool split_block(const uint8_t* block, size_t len, std::vector<Seg>& envs)
 }
 
 void plan_range(const uint8_t* block, const std::vector<Seg>& envs, size_t lo, size_t hi, const MspTable& msp, const std::string& channel,
-                TxPlan* txs, std::vector<SigJob>& local_jobs)
+                TxPlan* txs, JobPart& local)
 {
-    for (size_t i = lo; i < hi; i++) plan_tx(block, envs[i], msp, channel, txs[i], local_jobs);
+    for (size_t i = lo; i < hi; i++) plan_tx(block, envs[i], msp, channel, txs[i], local);
 }
 
-void merge_plan(BlockPlan& plan, std::vector<std::vector<SigJob>>& parts, const std::vector<size_t>& bounds)
+void merge_plan(BlockPlan& plan, std::vector<JobPart>& parts, const std::vector<size_t>& bounds)
 {
     plan.jobs.clear(); plan.n_check = 0; plan.has_config_tx = false;
-    size_t total = 0;
-    for (auto& p : parts) total += p.size();
-    plan.jobs.reserve(total);
+    size_t n_creators = 0, total = 0;
+    for (auto& p : parts) { n_creators += p.creators.size(); total += p.creators.size() + p.endorsements.size(); }
+    plan.jobs.resize(total);
+    size_t cbase = 0, ebase = n_creators;
     for (size_t part = 0; part < parts.size(); part++) {
-        const int base = (int)plan.jobs.size();
-        plan.jobs.insert(plan.jobs.end(), parts[part].begin(), parts[part].end());
+        std::copy(parts[part].creators.begin(), parts[part].creators.end(), plan.jobs.begin() + cbase);
+        std::copy(parts[part].endorsements.begin(), parts[part].endorsements.end(), plan.jobs.begin() + ebase);
         for (size_t t = bounds[part]; t < bounds[part + 1]; t++) {
             TxPlan& tx = plan.txs[t];
-            if (tx.creator_job >= 0) tx.creator_job += base;
-            for (auto& e : tx.ends) if (e.job >= 0) e.job += base;
+            if (tx.creator_job >= 0) tx.creator_job += (int)cbase;
+            for (auto& e : tx.ends) if (e.job >= 0) e.job += (int)ebase;
         }
+        cbase += parts[part].creators.size(); ebase += parts[part].endorsements.size();
     }
     for (auto& tx : plan.txs) {
         if (tx.early == TX_NOT_VALIDATED && tx.htype == 3) tx.check_job = plan.n_check++;
@@ -232,7 +236,7 @@ bool plan_block(const uint8_t* block, size_t len, const MspTable& msp, const std
     std::vector<Seg> envs;
     if (!split_block(block, len, envs)) return false;
     out.txs.assign(envs.size(), TxPlan());
-    std::vector<std::vector<SigJob>> parts(1);
+    std::vector<JobPart> parts(1);
     plan_range(block, envs, 0, envs.size(), msp, channel, out.txs.data(), parts[0]);
     merge_plan(out, parts, {0, envs.size()});
     return true;
@@ -240,7 +244,7 @@ bool plan_block(const uint8_t* block, size_t len, const MspTable& msp, const std
 
 void decide_range(const uint8_t* block, const BlockPlan& plan, const MspTable& msp, const std::vector<PolicyNode>& policy,
                   const std::vector<std::string>& principals, const uint8_t* sig_valid, const uint8_t* txid_digests,
-                  const uint8_t* phash_digests, size_t lo, size_t hi, uint8_t* flags)
+                  const uint8_t* phash_digests, size_t lo, size_t hi, uint8_t* flags, uint64_t* txid_hash)
 {
     std::vector<int> seen;
     std::vector<const std::string*> signer_msp;
@@ -285,19 +289,31 @@ void decide_range(const uint8_t* block, const BlockPlan& plan, const MspTable& m
             if (policy.empty() || !eval_policy(policy, principals, 0, signer_msp, used)) { code = TX_ENDORSEMENT_POLICY_FAILURE; break; }
         } while (false);
         flags[t] = code;
+        if (code == TX_VALID) {
+            uint64_t h = 1469598103934665603ull;
+            for (uint32_t k = 0; k < tx.txid_ascii.len; k++) h = (h ^ block[tx.txid_ascii.off + k]) * 1099511628211ull;
+            txid_hash[t] = h;
+        }
     }
 }
 
 // markTXIdDuplicates (v20/validator.go:283-297): among VALID transactions, a later one with an already seen tx id
-void mark_duplicates(const uint8_t* block, const BlockPlan& plan, uint8_t* flags)
+void mark_duplicates(const uint8_t* block, const BlockPlan& plan, const uint64_t* txid_hash, uint8_t* flags)
 {
-    std::unordered_map<std::string, char> seen;
+    std::unordered_multimap<uint64_t, uint32_t> seen;                      // tx-id hash -> first transaction that carried it
     seen.reserve(plan.txs.size() * 2);
     for (size_t t = 0; t < plan.txs.size(); t++) {
         if (flags[t] != TX_VALID) continue;
         const Seg id = plan.txs[t].txid_ascii;
         if (id.len == 0) continue;
-        if (!seen.emplace(std::string((const char*)block + id.off, id.len), 1).second) flags[t] = TX_DUPLICATE_TXID;
+        bool dup = false;
+        auto range = seen.equal_range(txid_hash[t]);
+        for (auto it = range.first; it != range.second && !dup; ++it) {
+            const Seg other = plan.txs[it->second].txid_ascii;            // equal hashes: confirm on the bytes
+            dup = other.len == id.len && memcmp(block + other.off, block + id.off, id.len) == 0;
+        }
+        if (dup) flags[t] = TX_DUPLICATE_TXID;
+        else seen.emplace(txid_hash[t], (uint32_t)t);
     }
 }
 
@@ -305,8 +321,9 @@ void decide_block(const uint8_t* block, const BlockPlan& plan, const MspTable& m
                   const std::vector<std::string>& principals, const uint8_t* sig_valid, const uint8_t* txid_digests,
                   const uint8_t* phash_digests, uint8_t* flags)
 {
-    decide_range(block, plan, msp, policy, principals, sig_valid, txid_digests, phash_digests, 0, plan.txs.size(), flags);
-    mark_duplicates(block, plan, flags);
+    std::vector<uint64_t> txid_hash(plan.txs.size() + 1, 0);
+    decide_range(block, plan, msp, policy, principals, sig_valid, txid_digests, phash_digests, 0, plan.txs.size(), flags, txid_hash.data());
+    mark_duplicates(block, plan, txid_hash.data(), flags);
 }
 
 } }  // namespace fabgpu::blockval

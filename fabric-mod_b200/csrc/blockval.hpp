@@ -18,6 +18,7 @@
 #pragma once
 #include <cstddef>
 #include <cstdint>
+#include <cstring>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -35,9 +36,31 @@ enum : uint8_t {
 struct Seg { uint32_t off = 0, len = 0; };                 // a byte range of the block buffer
 
 // The MSP as the validator sees it in steady state (msp/cache): serialized identity bytes -> index.
+// Serialized identities are ~900-byte strings that recur tens of thousands of times per block, so the lookup hashes a
+// 40-byte sample (length, head, tail) and confirms with one memcmp instead of hashing every byte.
 struct MspTable {
-    std::unordered_map<std::string, int> by_bytes;
+    std::vector<std::string> serialized;                    // identity i's wire bytes
+    std::unordered_multimap<uint64_t, int> by_sample;       // sample hash -> identity index
     std::vector<std::string> mspid;
+    static uint64_t sample_hash(const uint8_t* p, size_t n) {
+        uint64_t h = 1469598103934665603ull ^ n;
+        const size_t head = n < 16 ? n : 16, tail = n < 24 ? n : 24;
+        for (size_t i = 0; i < head; i++) h = (h ^ p[i]) * 1099511628211ull;
+        for (size_t i = n - tail; i < n; i++) h = (h ^ p[i]) * 1099511628211ull;
+        return h;
+    }
+    void add(const uint8_t* p, size_t n) {
+        by_sample.emplace(sample_hash(p, n), (int)serialized.size());
+        serialized.emplace_back((const char*)p, n);
+    }
+    int find(const uint8_t* p, size_t n) const {
+        auto range = by_sample.equal_range(sample_hash(p, n));
+        for (auto it = range.first; it != range.second; ++it) {
+            const std::string& s = serialized[it->second];
+            if (s.size() == n && memcmp(s.data(), p, n) == 0) return it->second;
+        }
+        return -1;
+    }
     std::vector<uint8_t> keys_xy;                           // 64 bytes per identity
     std::vector<uint8_t> valid;                             // identity.Validate() outcome
 };
@@ -79,13 +102,19 @@ struct BlockPlan {
 // Pieces for a multi-threaded caller: split the block into envelope ranges, plan disjoint transaction ranges with
 // thread-local job lists (job indices local to the list), then merge (rebases the indices, numbers the check jobs).
 bool split_block(const uint8_t* block, size_t len, std::vector<Seg>& envs);
+// Thread-local job lists: creator jobs and endorsement jobs are kept apart so that the merged list holds all creator
+// signatures first (their messages -- whole payloads -- are ~3x longer than endorsement messages; keeping the two classes
+// in separate warps keeps the SHA-256 kernel's lanes balanced).
+struct JobPart { std::vector<SigJob> creators, endorsements; };
 void plan_range(const uint8_t* block, const std::vector<Seg>& envs, size_t lo, size_t hi, const MspTable& msp, const std::string& channel,
-                TxPlan* txs, std::vector<SigJob>& local_jobs);
-void merge_plan(BlockPlan& plan, std::vector<std::vector<SigJob>>& parts, const std::vector<size_t>& bounds);
+                TxPlan* txs, JobPart& local);
+void merge_plan(BlockPlan& plan, std::vector<JobPart>& parts, const std::vector<size_t>& bounds);
 void decide_range(const uint8_t* block, const BlockPlan& plan, const MspTable& msp, const std::vector<PolicyNode>& policy,
                   const std::vector<std::string>& principals, const uint8_t* sig_valid, const uint8_t* txid_digests,
-                  const uint8_t* phash_digests, size_t lo, size_t hi, uint8_t* flags);
-void mark_duplicates(const uint8_t* block, const BlockPlan& plan, uint8_t* flags);
+                  const uint8_t* phash_digests, size_t lo, size_t hi, uint8_t* flags, uint64_t* txid_hash);
+// txid_hash[t]: 64-bit hash of transaction t's tx id, filled by decide_range (so the serial duplicate pass below does not
+// chase ten thousand cache lines of the block).
+void mark_duplicates(const uint8_t* block, const BlockPlan& plan, const uint64_t* txid_hash, uint8_t* flags);
 
 // Parses the block and builds the plan (single-threaded form).  Returns false when the outer Block / BlockData does not parse.
 bool plan_block(const uint8_t* block, size_t len, const MspTable& msp, const std::string& channel, BlockPlan& out);

@@ -320,7 +320,7 @@ int init_impl(fabgpu_ctx* ctx, const int* device_ids, int n_dev, size_t max_batc
     {
         int hw = (int)std::thread::hardware_concurrency();
         const char* ev = getenv("FABGPU_GATE_THREADS");
-        int want = ev ? atoi(ev) : std::min(hw > 0 ? hw : 1, 16);
+        int want = ev ? atoi(ev) : std::max(1, std::min(hw > 0 ? hw / 2 : 1, 32));   // gates and block parsing are latency-bound
         ctx->pool.reset(new GatePool(want));
         const char* ks = getenv("FABGPU_KEY_SLOTS");          // per-key tables are 5.5 MiB each (FAB_WQ = 12), per device
         ctx->key_slots = ks ? std::max(1, atoi(ks)) : 256;
@@ -747,7 +747,7 @@ int fabgpu_msp_configure(fabgpu_ctx* ctx, const uint8_t* id_blob, const uint32_t
         std::lock_guard<std::mutex> lk0(ctx->slot0_mu);
         ctx->msp = blockval::MspTable();
         for (int i = 0; i < n_ids; i++) {
-            ctx->msp.by_bytes.emplace(std::string((const char*)id_blob + id_off[i], id_off[i + 1] - id_off[i]), i);
+            ctx->msp.add(id_blob + id_off[i], id_off[i + 1] - id_off[i]);
             ctx->msp.mspid.emplace_back((const char*)mspid_blob + mspid_off[i], mspid_off[i + 1] - mspid_off[i]);
         }
         ctx->msp.keys_xy.assign(keys_xy, keys_xy + 64 * (size_t)n_ids);
@@ -784,7 +784,23 @@ int fabgpu_block_buffer(fabgpu_ctx* ctx, size_t bytes, uint8_t** out)
     return FABGPU_OK;
 }
 
+static int validate_impl(fabgpu_ctx* ctx, const uint8_t* block, size_t block_len, const uint32_t* env_off, size_t n_env, uint8_t* flags,
+                         size_t flags_cap, size_t* n_tx_out);
+
 int fabgpu_validate_block(fabgpu_ctx* ctx, const uint8_t* block, size_t block_len, uint8_t* flags, size_t flags_cap, size_t* n_tx_out)
+{
+    return validate_impl(ctx, block, block_len, nullptr, 0, flags, flags_cap, n_tx_out);
+}
+
+int fabgpu_validate_envelopes(fabgpu_ctx* ctx, const uint8_t* blob, const uint32_t* env_off, size_t n_env, uint8_t* flags, size_t flags_cap,
+                              size_t* n_tx_out)
+{
+    if (!env_off) return FABGPU_E_ARG;
+    return validate_impl(ctx, blob, env_off[n_env], env_off, n_env, flags, flags_cap, n_tx_out);
+}
+
+static int validate_impl(fabgpu_ctx* ctx, const uint8_t* block, size_t block_len, const uint32_t* env_off, size_t n_env, uint8_t* flags,
+                         size_t flags_cap, size_t* n_tx_out)
 {
     if (!ctx || !block || !flags || !n_tx_out) return FABGPU_E_ARG;
     if (block_len >= (1ull << 32)) { ctx->last_error = "block larger than 4 GiB"; return FABGPU_E_ARG; }
@@ -807,17 +823,21 @@ int fabgpu_validate_block(fabgpu_ctx* ctx, const uint8_t* block, size_t block_le
     const int TH = ctx->pool->size();
     {
         std::vector<blockval::Seg> envs;
-        if (!blockval::split_block(block, block_len, envs)) {
+        if (env_off) {                                    // the caller already holds Block.Data.Data as separate byte strings
+            envs.resize(n_env);
+            for (size_t i = 0; i < n_env; i++) { envs[i].off = env_off[i]; envs[i].len = env_off[i + 1] - env_off[i]; }
+        } else if (!blockval::split_block(block, block_len, envs)) {
             cudaStreamSynchronize(ds.stream);
             ctx->last_error = "block does not parse";
             return FABGPU_E_ARG;
         }
         plan.txs.assign(envs.size(), blockval::TxPlan());
-        std::vector<std::vector<blockval::SigJob>> parts(TH);
+        std::vector<blockval::JobPart> parts(TH);
         std::vector<size_t> bounds(TH + 1);
         for (int k = 0; k <= TH; k++) bounds[k] = envs.size() * (size_t)k / TH;
         ctx->pool->run([&](int tid) {
-            parts[tid].reserve((bounds[tid + 1] - bounds[tid]) * 4 + 4);
+            parts[tid].creators.reserve(bounds[tid + 1] - bounds[tid] + 4);
+            parts[tid].endorsements.reserve((bounds[tid + 1] - bounds[tid]) * 4 + 4);
             blockval::plan_range(block, envs, bounds[tid], bounds[tid + 1], ctx->msp, ctx->channel, plan.txs.data(), parts[tid]);
         });
         blockval::merge_plan(plan, parts, bounds);
@@ -909,11 +929,12 @@ int fabgpu_validate_block(fabgpu_ctx* ctx, const uint8_t* block, size_t block_le
     // digests arrive as [txid_0, phash_0, txid_1, phash_1, ...]; decide_block wants two strided views
     std::vector<uint8_t> txid_d(32 * (C ? C : 1)), phash_d(32 * (C ? C : 1));
     for (size_t c = 0; c < C; c++) { memcpy(&txid_d[32 * c], bb.h_dig + 64 * c, 32); memcpy(&phash_d[32 * c], bb.h_dig + 64 * c + 32, 32); }
+    std::vector<uint64_t> txid_hash(T + 1, 0);
     ctx->pool->run([&](int tid) {
         blockval::decide_range(block, plan, ctx->msp, ctx->policy, ctx->principals, sig_valid.data(), txid_d.data(), phash_d.data(),
-                               T * (size_t)tid / TH, T * (size_t)(tid + 1) / TH, flags);
+                               T * (size_t)tid / TH, T * (size_t)(tid + 1) / TH, flags, txid_hash.data());
     });
-    blockval::mark_duplicates(block, plan, flags);
+    blockval::mark_duplicates(block, plan, txid_hash.data(), flags);
     auto t4 = now();
     ctx->block_timing[0] = us(t0, t1); ctx->block_timing[1] = us(t1, t2); ctx->block_timing[2] = us(t2, t3); ctx->block_timing[3] = us(t3, t4);
     ctx->block_timing[4] = us(t0, t4);

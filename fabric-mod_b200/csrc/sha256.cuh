@@ -47,6 +47,64 @@ __device__ __forceinline__ void sha256_compress(uint32_t* h, uint32_t* w)
     h[0] += a; h[1] += b; h[2] += c; h[3] += d; h[4] += e; h[5] += f; h[6] += g; h[7] += hh;
 }
 
+// Streams message bytes into 16-word blocks.  The block buffer lives in local memory so that it can be indexed with a
+// run-time position (one STL per word, 16 LDL per compression); source bytes are fetched as aligned 32-bit words wherever
+// the segment allows (a segment may start at any byte offset of the block).
+struct ShaStream {
+    uint32_t h[8];
+    uint32_t wl[16];
+    uint32_t fillw;      // words in wl
+    uint64_t acc;        // pending bytes (nacc of them) in the low bits, most significant first
+    uint32_t nacc;
+
+    __device__ __forceinline__ void init()
+    {
+        h[0] = 0x6a09e667; h[1] = 0xbb67ae85; h[2] = 0x3c6ef372; h[3] = 0xa54ff53a; h[4] = 0x510e527f; h[5] = 0x9b05688c; h[6] = 0x1f83d9ab; h[7] = 0x5be0cd19;
+        fillw = 0; acc = 0; nacc = 0;
+    }
+    __device__ __forceinline__ void emit(uint32_t be_word)
+    {
+        wl[fillw++] = be_word;
+        if (fillw == 16) {
+            uint32_t w[16];
+#pragma unroll
+            for (int k = 0; k < 16; k++) w[k] = wl[k];
+            sha256_compress(h, w);
+            fillw = 0;
+        }
+    }
+    __device__ __forceinline__ void byte(uint32_t b)
+    {
+        acc = (acc << 8) | b;
+        if (++nacc == 4) { emit((uint32_t)acc); acc = 0; nacc = 0; }
+    }
+    __device__ __forceinline__ void word_le(uint32_t le)   // four message bytes as loaded from memory
+    {
+        const uint32_t be = __byte_perm(le, 0, 0x0123);
+        acc = (acc << 32) | be;
+        emit((uint32_t)(acc >> (8 * nacc)));
+        acc &= (1ull << (8 * nacc)) - 1ull;
+    }
+    __device__ __forceinline__ void feed(const uint8_t* __restrict__ p, uint32_t len)
+    {
+        uint32_t i = 0;
+        while (i < len && ((uintptr_t)(p + i) & 3u)) byte(p[i++]);
+        for (; i + 4 <= len; i += 4) word_le(__ldg(reinterpret_cast<const uint32_t*>(p + i)));
+        while (i < len) byte(p[i++]);
+    }
+    __device__ __forceinline__ void finish(uint64_t total_bytes, uint8_t* out)
+    {
+        byte(0x80);
+        while (nacc != 0) byte(0);
+        while (fillw != 14) emit(0);
+        emit((uint32_t)((total_bytes * 8) >> 32));
+        emit((uint32_t)(total_bytes * 8));
+        uint32_t* o = reinterpret_cast<uint32_t*>(out);
+#pragma unroll
+        for (int k = 0; k < 8; k++) o[k] = __byte_perm(h[k], 0, 0x0123);     // big-endian bytes
+    }
+};
+
 // digests[j] = SHA-256(buf[off0 .. off0+len0) || buf[off1 ..) || buf[off2 ..))
 __global__ void __launch_bounds__(128)
 sha256_segments_kernel(const uint8_t* __restrict__ buf, const ShaJob* __restrict__ jobs, uint32_t n, uint8_t* __restrict__ digests)
@@ -54,57 +112,11 @@ sha256_segments_kernel(const uint8_t* __restrict__ buf, const ShaJob* __restrict
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
     const ShaJob job = jobs[j];
-    uint32_t h[8] = {0x6a09e667, 0xbb67ae85, 0x3c6ef372, 0xa54ff53a, 0x510e527f, 0x9b05688c, 0x1f83d9ab, 0x5be0cd19};
-    uint32_t w[16];
-#pragma unroll
-    for (int i = 0; i < 16; i++) w[i] = 0;
-    const uint64_t total = (uint64_t)job.len[0] + job.len[1] + job.len[2];
-    uint32_t fill = 0;                       // bytes currently in w (0..63)
-    for (int sgi = 0; sgi < 3; sgi++) {
-        const uint8_t* p = buf + job.off[sgi];
-        const uint32_t len = job.len[sgi];
-        uint32_t i = 0;
-        // byte steps until the block buffer is word aligned, then whole big-endian words from 4 byte loads
-        while (i < len) {
-            if ((fill & 3u) == 0 && i + 4 <= len) {
-                const uint32_t word = ((uint32_t)p[i] << 24) | ((uint32_t)p[i + 1] << 16) | ((uint32_t)p[i + 2] << 8) | (uint32_t)p[i + 3];
-                // w[] is indexed with a run-time value: keep it in a switch-free form via the fill counter
-#pragma unroll
-                for (int k = 0; k < 16; k++) if ((fill >> 2) == (uint32_t)k) w[k] = word;
-                fill += 4; i += 4;
-            } else {
-                const uint32_t byte = p[i];
-                const uint32_t sh = 24 - 8 * (fill & 3u);
-#pragma unroll
-                for (int k = 0; k < 16; k++) if ((fill >> 2) == (uint32_t)k) w[k] |= byte << sh;
-                fill += 1; i += 1;
-            }
-            if (fill == 64) {
-                sha256_compress(h, w);
-#pragma unroll
-                for (int k = 0; k < 16; k++) w[k] = 0;
-                fill = 0;
-            }
-        }
-    }
-    // padding: 0x80, zeros, 64-bit big-endian bit length
-    {
-        const uint32_t sh = 24 - 8 * (fill & 3u);
-#pragma unroll
-        for (int k = 0; k < 16; k++) if ((fill >> 2) == (uint32_t)k) w[k] |= 0x80u << sh;
-        if (fill >= 56) {
-            sha256_compress(h, w);
-#pragma unroll
-            for (int k = 0; k < 16; k++) w[k] = 0;
-        }
-        const uint64_t bits = total * 8;
-        w[14] = (uint32_t)(bits >> 32);
-        w[15] = (uint32_t)bits;
-        sha256_compress(h, w);
-    }
-    uint32_t* out = reinterpret_cast<uint32_t*>(digests + 32 * (size_t)j);
-#pragma unroll
-    for (int k = 0; k < 8; k++) out[k] = __byte_perm(h[k], 0, 0x0123);      // big-endian bytes
+    ShaStream st;
+    st.init();
+#pragma unroll 1
+    for (int sgi = 0; sgi < 3; sgi++) st.feed(buf + job.off[sgi], job.len[sgi]);
+    st.finish((uint64_t)job.len[0] + job.len[1] + job.len[2], digests + 32 * (size_t)j);
 }
 
 }  // namespace fabgpu

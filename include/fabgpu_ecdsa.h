@@ -152,6 +152,10 @@ int fabgpu_msp_configure(fabgpu_ctx* ctx, const uint8_t* id_blob, const uint32_t
                          int n_principals, const char* channel_id);
 /* flags[i] receives the validation code of transaction i; *n_tx_out the number of transactions. */
 int fabgpu_validate_block(fabgpu_ctx* ctx, const uint8_t* block, size_t block_len, uint8_t* flags, size_t flags_cap, size_t* n_tx_out);
+/* Same for a caller that already holds Block.Data.Data as separate byte strings (the Go validator does): `blob` is their
+ * concatenation, env_off the (n_env+1)-entry offset table.  Saves the serial walk over the length-prefixed envelopes. */
+int fabgpu_validate_envelopes(fabgpu_ctx* ctx, const uint8_t* blob, const uint32_t* env_off, size_t n_env, uint8_t* flags, size_t flags_cap,
+                              size_t* n_tx_out);
 /* Optional pinned staging buffer for the block bytes (the H2D copy of a pageable buffer is several times slower). */
 int fabgpu_block_buffer(fabgpu_ctx* ctx, size_t bytes, uint8_t** out);
 /* Phase times of the last fabgpu_validate_block, microseconds: parse/plan, host gates, device, decisions, total. */

@@ -9,6 +9,7 @@
 using namespace fabgpu::blockval;
 
 struct Handle {
+    std::vector<uint64_t> th;
     MspTable msp; std::vector<PolicyNode> policy; std::vector<std::string> principals; std::string channel;
     BlockPlan plan; std::vector<uint8_t> block;
 };
@@ -21,7 +22,7 @@ void* bv_new(const uint8_t* id_blob, const uint32_t* id_off, const uint8_t* mspi
 {
     Handle* h = new Handle();
     for (int i = 0; i < n_ids; i++) {
-        h->msp.by_bytes.emplace(std::string((const char*)id_blob + id_off[i], id_off[i + 1] - id_off[i]), i);
+        h->msp.add(id_blob + id_off[i], id_off[i + 1] - id_off[i]);
         h->msp.mspid.emplace_back((const char*)mspid_blob + mspid_off[i], mspid_off[i + 1] - mspid_off[i]);
     }
     h->msp.keys_xy.assign(keys_xy, keys_xy + 64 * (size_t)n_ids);

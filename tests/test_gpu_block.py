@@ -58,10 +58,11 @@ def test_block_2000_tx_mixed_and_pinned_buffer(ctx):
     net = blockgen.Network(n_orgs=4, n_clients=3)
     rnd = random.Random(4)
     faults = {t: rnd.choice(blockgen.FAULTS) for t in rnd.sample(range(1, 2000), 240)}
-    blk, _ = blockgen.build_block(net, 2000, 3, faults, seed=13)
+    blk, binfo = blockgen.build_block(net, 2000, 3, faults, seed=13)
     exp = ob.validate_block(blk, blockutil.identities_of(net), net.channel, net.policy_n_of(3), net.principals)
     _configure(ctx, net, 3)
     assert ctx.validate_block(blk).tolist() == exp.tolist()
+    assert ctx.validate_envelopes(binfo["env_blob"], binfo["env_off"]).tolist() == exp.tolist()      # Block.Data.Data form
     pinned = ctx.block_buffer(len(blk))
     pinned[:] = np.frombuffer(blk, np.uint8)
     assert ctx.validate_block(pinned).tolist() == exp.tolist()

@@ -160,4 +160,7 @@ def build_block(net: Network, n_tx: int, n_endorsements: int = 3, faults=None, s
         if f == "bad_payload":
             env = pb.f_bytes(1, b"\xff\xff\xff\xff garbage that is not a Payload") + pb.f_bytes(2, sg)
         envs.append(env)
-    return pb.block(number, envs), dict(n_tx=n_tx, faults=dict(faults), n_sigs=n_tx * (1 + n_endorsements))
+    env_off = np.zeros(len(envs) + 1, np.uint32)
+    env_off[1:] = np.cumsum([len(e) for e in envs])
+    return pb.block(number, envs), dict(n_tx=n_tx, faults=dict(faults), n_sigs=n_tx * (1 + n_endorsements),
+                                        env_blob=b"".join(envs), env_off=env_off)   # Block.Data.Data as the Go validator holds it
