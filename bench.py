@@ -38,6 +38,7 @@ ALG_BYTES_PER_VERIFY = 160.125          # 5 x 32 B in, 1
 ALG_MACS_PER_VERIFY = 217600            # 3 400 modular multiplications x 64 MACs (generic kernel)
 ALG_MACS_PER_VERIFY_CACHED = 421 * 64   # key-table kernel: (16 + 22) mixed additions x 11 + 3 field multiplications, x 64 MACs
 KEYS = 64
+NCU_DRAM_BYTES_PER_LAUNCH_64K = 221519872 + 7569664   # ecdsa_verify_cached_kernel, profiles/r1_final_cached_ncu_summary.txt
 
 
 def _peaks():
@@ -157,6 +158,8 @@ def run_gpu(args):
     if world != args.gpus:
         if world == 1 and args.gpus > 1:
             raise SystemExit("launch with torch.distributed.run --nproc-per-node %d for --gpus %d" % (args.gpus, args.gpus))
+    if world > 1 and "FABGPU_GATE_THREADS" not in os.environ:       # ranks share the host: split its threads between them
+        os.environ["FABGPU_GATE_THREADS"] = str(max(4, (os.cpu_count() or 8) // (2 * world)))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -315,7 +318,11 @@ def run_gpu(args):
                         "ms_per_step": gen_ms / gsteps, "steps": gsteps},
             "key_tables": {"keys": KEYS, "register_ms_once": key_register_ms,
                            "what": "fabgpu_keys_register builds a 5.5 MiB window table per public key (what KeyImport does once per identity)"},
-            "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak, "traffic": None,
+            "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
+                         "traffic": (NCU_DRAM_BYTES_PER_LAUNCH_64K if B == 65536 else None),
+                         "traffic_note": "dram read+write of one launch at batch 65536 from profiles/r1_final_cached_ncu_summary.txt; it exceeds the "
+                                         "algorithmic 10.5 MB because the kernel gathers 38 table points (64 B each) per signature from 430 MB of "
+                                         "window tables by design -- that is what replaces 255 doublings",
                          "peak_source": peak_src, "kernel": "ecdsa_verify_cached_kernel",
                          "note": "integer-issue bound, not HBM bound: see roofline_int"},
             "roofline_int": {"bound": "int32 mac (fma pipe)", "kernel": "ecdsa_verify_cached_kernel", "achieved": ach_macs / 1e12,

@@ -89,6 +89,15 @@ struct ShaStream {
     {
         uint32_t i = 0;
         while (i < len && ((uintptr_t)(p + i) & 3u)) byte(p[i++]);
+        // 64 bytes at a time: all sixteen loads are issued before any is consumed (ncu showed the one-load-at-a-time
+        // form stalled on long_scoreboard 4.2 cycles per issue)
+        for (; i + 64 <= len; i += 64) {
+            uint32_t t[16];
+#pragma unroll
+            for (int k = 0; k < 16; k++) t[k] = __ldg(reinterpret_cast<const uint32_t*>(p + i) + k);
+#pragma unroll
+            for (int k = 0; k < 16; k++) word_le(t[k]);
+        }
         for (; i + 4 <= len; i += 4) word_le(__ldg(reinterpret_cast<const uint32_t*>(p + i)));
         while (i < len) byte(p[i++]);
     }
