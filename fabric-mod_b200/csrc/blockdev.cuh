@@ -1,0 +1,438 @@
+// Device-side block pre-pass: the same walk, gates and decisions as blockval.cpp / bccsp_host.cpp, written once as
+// host+device code so that (a) the GPU runs it with one thread per transaction straight on the block bytes that are in
+// HBM anyway (block pre-pass, DER / low-S gates on the device) and (b) tests can run
+// the identical code on the CPU-only build box (tests/host_sim/blockdev_host.cpp).
+//
+// Reference semantics restated here (see blockval.hpp for the full list):
+//   ValidateTransaction / checkSignatureFromCreator / validateEndorserTransaction   core/common/validation/msgvalidation.go:26-320
+//   KeyLevelValidator signature set        core/common/validation/statebased/validator_keylevel.go:243-259
+//   SignatureSetToValidIdentities          common/policies/policy.go:365-402
+//   cauthdsl evaluator                     common/cauthdsl/cauthdsl.go:24-92
+//   UnmarshalECDSASignature / IsLowS       bccsp/utils/ecdsa.go:43-92 (Go encoding/asn1 DER rules)
+// No STL, no allocation: everything is offsets into the block buffer and fixed-size records.
+#pragma once
+#include <stdint.h>
+#include <string.h>
+
+#if defined(__CUDACC__)
+#define BD_HD __host__ __device__ __forceinline__
+#else
+#define BD_HD inline
+#endif
+
+namespace fabgpu { namespace bdev {
+
+enum : uint8_t {
+    TXC_VALID = 0, TXC_BAD_PAYLOAD = 2, TXC_BAD_COMMON_HEADER = 3, TXC_BAD_CREATOR_SIGNATURE = 4, TXC_INVALID_ENDORSER_TRANSACTION = 5,
+    TXC_UNSUPPORTED_TX_PAYLOAD = 7, TXC_BAD_PROPOSAL_TXID = 8, TXC_DUPLICATE_TXID = 9, TXC_ENDORSEMENT_POLICY_FAILURE = 10,
+    TXC_TARGET_CHAIN_NOT_FOUND = 14, TXC_NOT_VALIDATED = 254, TXC_INVALID_OTHER_REASON = 255
+};
+
+#define BD_MAX_ENDS 16          // endorsements per transaction handled on the device; more -> that transaction is left to the CPU
+
+struct Seg { uint32_t off, len; };
+
+// ---- MSP view on the device --------------------------------------------------------------------------------------------
+struct MspDev {
+    const uint8_t* id_blob;       // serialized identities back to back
+    const uint32_t* id_off;       // n_ids + 1
+    const int32_t* key_slot;      // per identity: key-table slot or -1
+    const uint8_t* valid;         // per identity: identity.Validate()
+    const int32_t* msp_code;      // per identity: code of its MSP id (equal ids <=> equal codes)
+    const uint8_t* keys_xy;       // per identity: X || Y (64 bytes), for signatures whose key has no table
+    const uint64_t* ht_hash;      // open-addressing table, size ht_size (power of two); 0 = empty
+    const int32_t* ht_idx;
+    uint32_t ht_size;
+    int32_t n_ids;
+};
+
+BD_HD uint64_t sample_hash(const uint8_t* p, uint32_t n)
+{
+    uint64_t h = 1469598103934665603ull ^ n;
+    const uint32_t head = n < 16 ? n : 16, tail = n < 24 ? n : 24;
+    for (uint32_t i = 0; i < head; i++) h = (h ^ p[i]) * 1099511628211ull;
+    for (uint32_t i = n - tail; i < n; i++) h = (h ^ p[i]) * 1099511628211ull;
+    return h ? h : 1;
+}
+
+BD_HD bool bytes_equal(const uint8_t* a, const uint8_t* b, uint32_t n)
+{
+    for (uint32_t i = 0; i < n; i++) if (a[i] != b[i]) return false;
+    return true;
+}
+
+BD_HD int32_t msp_find(const MspDev& m, const uint8_t* p, uint32_t n)
+{
+    if (m.ht_size == 0) return -1;
+    const uint64_t h = sample_hash(p, n);
+    for (uint32_t probe = 0, pos = (uint32_t)h & (m.ht_size - 1); probe < m.ht_size; probe++, pos = (pos + 1) & (m.ht_size - 1)) {
+        const uint64_t k = m.ht_hash[pos];
+        if (k == 0) return -1;
+        if (k != h) continue;
+        const int32_t i = m.ht_idx[pos];
+        const uint32_t len = m.id_off[i + 1] - m.id_off[i];
+        if (len == n && bytes_equal(m.id_blob + m.id_off[i], p, n)) return i;
+    }
+    return -1;
+}
+
+// ---- protobuf wire reader ------------------------------------------------------------------------------------------------
+struct Reader {
+    const uint8_t* base; uint32_t pos, end; bool ok;
+    BD_HD bool varint(uint64_t& v)
+    {
+        v = 0;
+        for (int shift = 0; shift < 70; shift += 7) {
+            if (pos >= end) { ok = false; return false; }
+            const uint8_t c = base[pos++];
+            v |= (uint64_t)(c & 0x7f) << shift;
+            if (!(c & 0x80)) return true;
+        }
+        ok = false; return false;
+    }
+    BD_HD bool next(uint32_t& field, uint32_t& wt, uint64_t& val, Seg& bytes)
+    {
+        if (pos >= end) return false;
+        uint64_t key;
+        if (!varint(key)) return false;
+        field = (uint32_t)(key >> 3); wt = (uint32_t)(key & 7);
+        if (field == 0) { ok = false; return false; }
+        if (wt == 0) return varint(val);
+        if (wt == 1) { if (end - pos < 8) { ok = false; return false; } pos += 8; return true; }
+        if (wt == 5) { if (end - pos < 4) { ok = false; return false; } pos += 4; return true; }
+        if (wt == 2) {
+            uint64_t ln;
+            if (!varint(ln)) return false;
+            if ((uint64_t)(end - pos) < ln) { ok = false; return false; }
+            bytes.off = pos; bytes.len = (uint32_t)ln; pos += (uint32_t)ln;
+            return true;
+        }
+        ok = false; return false;
+    }
+};
+
+// Up to 3 selected length-delimited fields (last occurrence wins) and up to 2 varint fields of one message.
+struct Sel { uint32_t f[3]; Seg s[3]; bool present[3]; uint32_t uf[2]; uint64_t uv[2]; };
+
+BD_HD bool parse_sel(const uint8_t* base, Seg msg, Sel& sel)
+{
+    Reader r; r.base = base; r.pos = msg.off; r.end = msg.off + msg.len; r.ok = true;
+    for (int i = 0; i < 3; i++) { sel.s[i].off = 0; sel.s[i].len = 0; sel.present[i] = false; }
+    sel.uv[0] = sel.uv[1] = 0;
+    uint32_t f, wt; uint64_t v = 0; Seg b; b.off = b.len = 0;
+    while (r.next(f, wt, v, b)) {
+        bool hit = false;
+        for (int i = 0; i < 2 && !hit; i++) if (sel.uf[i] && sel.uf[i] == f) { if (wt != 0) return false; sel.uv[i] = v; hit = true; }
+        for (int i = 0; i < 3 && !hit; i++) if (sel.f[i] && sel.f[i] == f) { if (wt != 2) return false; sel.s[i] = b; sel.present[i] = true; hit = true; }
+    }
+    return r.ok;
+}
+BD_HD Sel make_sel(uint32_t f0, uint32_t f1 = 0, uint32_t f2 = 0, uint32_t u0 = 0, uint32_t u1 = 0)
+{
+    Sel s; s.f[0] = f0; s.f[1] = f1; s.f[2] = f2; s.uf[0] = u0; s.uf[1] = u1; return s;
+}
+
+// ---- DER gate (Go encoding/asn1 rules; bccsp/utils/ecdsa.go:43-92, bccsp/sw/ecdsa.go:42-54) -----------------------------
+// Returns true when every gate passes (r, s written as 32 big-endian bytes).  false covers unmarshal errors, R <= 0,
+// S <= 0, high S and r >= 2^256: at block level all of those make identity.Verify fail alike.
+BD_HD bool der_tag_len(const uint8_t* b, uint32_t n, uint32_t& off, uint32_t& cls, bool& compound, uint32_t& tag, uint32_t& length)
+{
+    if (off >= n) return false;
+    uint8_t c = b[off++];
+    cls = c >> 6; compound = (c & 0x20) != 0; tag = c & 0x1f;
+    if (tag == 0x1f) {
+        uint64_t t = 0; int shifted = 0;
+        for (;;) {
+            if (off >= n || shifted == 5) return false;
+            c = b[off++];
+            if (shifted == 0 && c == 0x80) return false;
+            t = (t << 7) | (c & 0x7f); shifted++;
+            if (!(c & 0x80)) break;
+        }
+        if (t > 0x7fffffffull || t < 0x1f) return false;
+        tag = (uint32_t)t;
+    }
+    if (off >= n) return false;
+    c = b[off++];
+    if (!(c & 0x80)) { length = c & 0x7f; return true; }
+    const int nb = c & 0x7f;
+    if (nb == 0) return false;
+    uint32_t L = 0;
+    for (int i = 0; i < nb; i++) {
+        if (off >= n) return false;
+        c = b[off++];
+        if (L >= (1u << 23)) return false;
+        L = (L << 8) | c;
+        if (L == 0) return false;
+    }
+    if (L < 0x80) return false;
+    length = L;
+    return true;
+}
+
+BD_HD bool der_int(const uint8_t* b, uint32_t n, uint32_t& off, uint32_t& vo, uint32_t& vl)
+{
+    if (off == n) return false;
+    uint32_t cls, tag, len; bool compound;
+    if (!der_tag_len(b, n, off, cls, compound, tag, len)) return false;
+    if ((uint64_t)off + len > n) return false;
+    if (cls != 0 || tag != 2 || compound || len == 0) return false;
+    const uint8_t* p = b + off;
+    if (len > 1 && ((p[0] == 0 && !(p[1] & 0x80)) || (p[0] == 0xff && (p[1] & 0x80)))) return false;
+    vo = off; vl = len; off += len;
+    return true;
+}
+
+BD_HD bool gate_signature(const uint8_t* sig, uint32_t n, uint8_t* r32, uint8_t* s32)
+{
+    const uint8_t half[32] = {0x7F, 0xFF, 0xFF, 0xFF, 0x80, 0x00, 0x00, 0x00, 0x7F, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF,
+                              0xDE, 0x73, 0x7D, 0x56, 0xD3, 0x8B, 0xCF, 0x42, 0x79, 0xDC, 0xE5, 0x61, 0x7E, 0x31, 0x92, 0xA8};
+    if (n == 0) return false;
+    uint32_t off = 0, cls, tag, len; bool compound;
+    if (!der_tag_len(sig, n, off, cls, compound, tag, len)) return false;
+    if ((uint64_t)off + len > n) return false;
+    if (cls != 0 || tag != 16 || !compound) return false;
+    const uint8_t* inner = sig + off;
+    uint32_t io = 0, ro, rl, so, sl;
+    if (!der_int(inner, len, io, ro, rl)) return false;
+    if (!der_int(inner, len, io, so, sl)) return false;
+    const uint8_t* rp = inner + ro; const uint8_t* sp = inner + so;
+    if (rp[0] & 0x80) return false;                               // R negative
+    if (sp[0] & 0x80) return false;                               // S negative
+    while (rl > 0 && *rp == 0) { rp++; rl--; }
+    while (sl > 0 && *sp == 0) { sp++; sl--; }
+    if (rl == 0 || sl == 0) return false;                         // R == 0 / S == 0
+    if (sl > 32 || rl > 32) return false;                         // s > N/2 for sure; r >= 2^256 can never be < N
+    for (int i = 0; i < 32; i++) { r32[i] = 0; s32[i] = 0; }
+    for (uint32_t i = 0; i < rl; i++) r32[32 - rl + i] = rp[i];
+    for (uint32_t i = 0; i < sl; i++) s32[32 - sl + i] = sp[i];
+    for (int i = 0; i < 32; i++) {                                // s <= N >> 1
+        if (s32[i] < half[i]) break;
+        if (s32[i] > half[i]) return false;
+    }
+    return true;
+}
+
+// ---- per-transaction plan --------------------------------------------------------------------------------------------------
+struct ShaJobD { uint32_t off[3]; uint32_t len[3]; };
+
+struct TxDev {
+    uint8_t early;                 // decided by structure alone, else TXC_NOT_VALIDATED
+    uint8_t htype;
+    uint8_t endorser_parse_ok, channel_ok, endorsements_parse_ok, overflow;
+    uint8_t n_ends;
+    uint8_t pad;
+    int32_t creator_identity;      // -1 unknown
+    int32_t creator_has_job;       // creator job index is the transaction index when 1
+    Seg txid_ascii;
+    Seg phash_claimed;
+    int32_t end_identity[BD_MAX_ENDS];
+    int32_t end_job[BD_MAX_ENDS];  // -1: nothing to verify for that endorsement
+};
+
+// Everything plan_tx writes for one transaction besides TxDev: job records live in caller-provided arrays.
+struct JobArrays {
+    ShaJobD* sha;                  // [J_cap + 2 T]: signature messages, then (txid, proposal hash) per transaction
+    uint8_t* r; uint8_t* s;        // [J_cap x 32]
+    int32_t* key_slot;             // [J_cap]
+    int32_t* identity;             // [J_cap]
+    uint8_t* qx; uint8_t* qy;      // [J_cap x 32] or null: filled only for keys without a table (generic kernel)
+    uint8_t* gate_ok;              // [J_cap]
+    uint32_t J_cap;                // capacity; creator jobs occupy [0, T), endorsement jobs [T, T + n_end)
+    uint32_t T;
+};
+
+BD_HD void job_fill(const uint8_t* base, const MspDev& msp, JobArrays& ja, uint32_t j, int32_t identity, Seg m0, Seg m1, Seg sig)
+{
+    ShaJobD& sh = ja.sha[j];
+    sh.off[0] = m0.off; sh.len[0] = m0.len; sh.off[1] = m1.off; sh.len[1] = m1.len; sh.off[2] = 0; sh.len[2] = 0;
+    const bool ok = gate_signature(base + sig.off, sig.len, ja.r + 32 * (size_t)j, ja.s + 32 * (size_t)j);
+    if (!ok) for (int i = 0; i < 32; i++) { ja.r[32 * (size_t)j + i] = 0; ja.s[32 * (size_t)j + i] = 0; }
+    ja.gate_ok[j] = ok ? 1 : 0;
+    ja.identity[j] = identity;
+    const int32_t slot = msp.key_slot[identity];
+    ja.key_slot[j] = slot;
+    if (slot < 0 && ja.qx) {
+        for (int i = 0; i < 32; i++) { ja.qx[32 * (size_t)j + i] = msp.keys_xy[64 * (size_t)identity + i]; ja.qy[32 * (size_t)j + i] = msp.keys_xy[64 * (size_t)identity + 32 + i]; }
+    }
+}
+
+// alloc_end(n) must return the first index of n fresh endorsement-job slots (atomicAdd on the device, a counter on the host)
+template <typename Alloc>
+BD_HD void plan_tx(const uint8_t* base, Seg env, uint32_t t, const MspDev& msp, const uint8_t* channel, uint32_t channel_len,
+                   TxDev& tx, JobArrays& ja, Alloc alloc_end)
+{
+    tx.early = TXC_NOT_VALIDATED; tx.htype = 0; tx.endorser_parse_ok = 0; tx.channel_ok = 0; tx.endorsements_parse_ok = 1; tx.overflow = 0;
+    tx.n_ends = 0; tx.pad = 0; tx.creator_identity = -1; tx.creator_has_job = 0;
+    tx.txid_ascii.off = tx.txid_ascii.len = 0; tx.phash_claimed.off = tx.phash_claimed.len = 0;
+    // creator slot t and the two check slots default to "nothing"
+    {
+        ShaJobD z; for (int k = 0; k < 3; k++) { z.off[k] = 0; z.len[k] = 0; }
+        ja.sha[t] = z; ja.sha[ja.J_cap + 2 * t] = z; ja.sha[ja.J_cap + 2 * t + 1] = z;
+        for (int i = 0; i < 32; i++) { ja.r[32 * (size_t)t + i] = 0; ja.s[32 * (size_t)t + i] = 0; }
+        ja.gate_ok[t] = 0; ja.identity[t] = -1; ja.key_slot[t] = -1;
+    }
+    Sel e = make_sel(1, 2);                                           // Envelope{payload=1, signature=2}
+    if (!parse_sel(base, env, e)) { tx.early = TXC_INVALID_OTHER_REASON; return; }
+    const Seg payload = e.s[0], signature = e.s[1];
+    Sel p = make_sel(1, 2);                                           // Payload{header=1, data=2}
+    if (!parse_sel(base, payload, p)) { tx.early = TXC_BAD_PAYLOAD; return; }
+    if (!p.present[0]) { tx.early = TXC_BAD_COMMON_HEADER; return; }
+    const Seg data = p.s[1]; const bool has_data = p.present[1];
+    Sel h = make_sel(1, 2);                                           // Header{channel_header=1, signature_header=2}
+    if (!parse_sel(base, p.s[0], h)) { tx.early = TXC_BAD_COMMON_HEADER; return; }
+    const Seg chdr_b = h.s[0], shdr_b = h.s[1]; const bool has_chdr = h.present[0];
+    Sel ch = make_sel(4, 5, 0, 1, 6);                                 // ChannelHeader{type=1, channel_id=4, tx_id=5, epoch=6}
+    if (!parse_sel(base, chdr_b, ch)) { tx.early = TXC_BAD_COMMON_HEADER; return; }
+    Sel sh = make_sel(1, 2);                                          // SignatureHeader{creator=1, nonce=2}
+    if (!parse_sel(base, shdr_b, sh)) { tx.early = TXC_BAD_COMMON_HEADER; return; }
+    const Seg creator = sh.s[0], nonce = sh.s[1];
+    const uint32_t ht = (uint32_t)ch.uv[0];
+    if (!(ht == 1 || ht == 2 || ht == 3) || ch.uv[1] != 0 || nonce.len == 0 || creator.len == 0) { tx.early = TXC_BAD_COMMON_HEADER; return; }
+    tx.htype = (uint8_t)ht;
+    tx.creator_identity = msp_find(msp, base + creator.off, creator.len);
+    if (signature.len > 0 && payload.len > 0 && tx.creator_identity >= 0) {
+        Seg none; none.off = none.len = 0;
+        job_fill(base, msp, ja, t, tx.creator_identity, payload, none, signature);
+        tx.creator_has_job = 1;
+    }
+    if (ht != 3) return;
+    tx.txid_ascii = ch.s[1];
+    { ShaJobD& a = ja.sha[ja.J_cap + 2 * t]; a.off[0] = nonce.off; a.len[0] = nonce.len; a.off[1] = creator.off; a.len[1] = creator.len; }
+    tx.channel_ok = (ch.s[0].len == channel_len && bytes_equal(base + ch.s[0].off, channel, channel_len)) ? 1 : 0;
+    if (!has_data) return;
+    // Transaction{repeated actions=1}: exactly one
+    Seg action0; action0.off = action0.len = 0; uint32_t n_actions = 0;
+    {
+        Reader r; r.base = base; r.pos = data.off; r.end = data.off + data.len; r.ok = true;
+        uint32_t f, wt; uint64_t v; Seg b;
+        while (r.next(f, wt, v, b)) { if (f == 1) { if (wt != 2) { r.ok = false; break; } action0 = b; n_actions++; } }
+        if (!r.ok || n_actions != 1) return;
+    }
+    Sel ta = make_sel(1, 2);                                          // TransactionAction{header=1, payload=2}
+    if (!parse_sel(base, action0, ta)) return;
+    Sel ah = make_sel(1, 2);
+    if (!parse_sel(base, ta.s[0], ah) || ah.s[1].len == 0 || ah.s[0].len == 0) return;
+    Sel cap = make_sel(1, 2);                                         // ChaincodeActionPayload{chaincode_proposal_payload=1, action=2}
+    if (!parse_sel(base, ta.s[1], cap) || !cap.present[1]) return;
+    // ChaincodeEndorsedAction{proposal_response_payload=1, repeated endorsements=2}: first pass finds prp and counts
+    Seg prp; prp.off = prp.len = 0; uint32_t n_end = 0;
+    {
+        Reader r; r.base = base; r.pos = cap.s[1].off; r.end = cap.s[1].off + cap.s[1].len; r.ok = true;
+        uint32_t f, wt; uint64_t v; Seg b;
+        while (r.next(f, wt, v, b)) {
+            if (f == 1) { if (wt != 2) { r.ok = false; break; } prp = b; }
+            else if (f == 2) { if (wt != 2) { r.ok = false; break; } n_end++; }
+        }
+        if (!r.ok) return;
+    }
+    Sel pr = make_sel(1);                                             // ProposalResponsePayload{proposal_hash=1}
+    if (!parse_sel(base, prp, pr)) return;
+    if (!has_chdr || !ta.present[0] || !cap.present[0]) return;       // GetProposalHash2 "nil arguments"
+    { ShaJobD& b = ja.sha[ja.J_cap + 2 * t + 1];
+      b.off[0] = chdr_b.off; b.len[0] = chdr_b.len; b.off[1] = ta.s[0].off; b.len[1] = ta.s[0].len; b.off[2] = cap.s[0].off; b.len[2] = cap.s[0].len; }
+    tx.phash_claimed = pr.s[0];
+    tx.endorser_parse_ok = 1;
+    if (n_end > BD_MAX_ENDS) { tx.overflow = 1; return; }
+    // second pass over the endorsements: Endorsement{endorser=1, signature=2}
+    Seg ends[BD_MAX_ENDS]; Seg sigs[BD_MAX_ENDS]; uint32_t n_jobs = 0, k = 0;
+    {
+        Reader r; r.base = base; r.pos = cap.s[1].off; r.end = cap.s[1].off + cap.s[1].len; r.ok = true;
+        uint32_t f, wt; uint64_t v; Seg b;
+        while (r.next(f, wt, v, b)) {
+            if (f != 2) continue;
+            Sel en = make_sel(1, 2);
+            if (!parse_sel(base, b, en)) { tx.endorsements_parse_ok = 0; break; }
+            const int32_t idn = msp_find(msp, base + en.s[0].off, en.s[0].len);
+            tx.end_identity[k] = idn;
+            ends[k] = en.s[0]; sigs[k] = en.s[1];
+            tx.end_job[k] = (idn >= 0 && en.s[1].len > 0) ? 0 : -1;
+            if (tx.end_job[k] == 0) n_jobs++;
+            k++;
+        }
+    }
+    tx.n_ends = (uint8_t)k;
+    if (n_jobs) {
+        uint32_t j = alloc_end(n_jobs);
+        for (uint32_t i = 0; i < k; i++) {
+            if (tx.end_job[i] < 0) continue;
+            if (j >= ja.J_cap) { tx.overflow = 1; tx.end_job[i] = -1; continue; }
+            job_fill(base, msp, ja, j, tx.end_identity[i], prp, ends[i], sigs[i]);
+            tx.end_job[i] = (int32_t)j;
+            j++;
+        }
+    }
+}
+
+// ---- policy evaluator: cauthdsl.go:24-92, `used` as a bit mask over at most BD_MAX_ENDS signers --------------------------
+struct PolicyDev { const int32_t* nodes; int32_t n_nodes; const int32_t* principal_code; int32_t n_principals; };
+
+BD_HD bool eval_policy(const PolicyDev& pol, int idx, const int32_t* signer_code, int n_signers, uint32_t& used, int depth)
+{
+    if (idx < 0 || idx >= pol.n_nodes || depth > 12) return false;
+    const int32_t type = pol.nodes[4 * idx], n = pol.nodes[4 * idx + 1], first = pol.nodes[4 * idx + 2], cnt = pol.nodes[4 * idx + 3];
+    if (type == 0) {
+        int verified = 0;
+        for (int c = first; c < first + cnt; c++) {
+            uint32_t scratch = used;
+            if (eval_policy(pol, c, signer_code, n_signers, scratch, depth + 1)) { verified++; used = scratch; }
+        }
+        return verified >= n;
+    }
+    if (n < 0 || n >= pol.n_principals) return false;
+    const int32_t want = pol.principal_code[n];
+    for (int i = 0; i < n_signers; i++) {
+        if (used & (1u << i)) continue;
+        if (signer_code[i] < 0 || signer_code[i] != want) continue;
+        used |= 1u << i;
+        return true;
+    }
+    return false;
+}
+
+// ---- per-transaction decision ---------------------------------------------------------------------------------------------
+// sig_ok(j): signature job j verified (gate and curve).  digests: 32 bytes per SHA job (same indexing as JobArrays::sha).
+template <typename SigOk>
+BD_HD uint8_t decide_tx(const uint8_t* base, const TxDev& tx, uint32_t t, const MspDev& msp, const PolicyDev& pol, SigOk sig_ok,
+                        const uint8_t* digests, uint32_t J_cap, uint64_t* txid_hash_out)
+{
+    const char hex[] = "0123456789abcdef";
+    if (tx.early != TXC_NOT_VALIDATED) return tx.early;
+    const bool creator_ok = tx.creator_identity >= 0 && msp.valid[tx.creator_identity] && tx.creator_has_job && sig_ok(t);
+    if (!creator_ok) return TXC_BAD_CREATOR_SIGNATURE;
+    if (tx.htype == 1) return TXC_NOT_VALIDATED;                      // config transaction: CPU validator
+    if (tx.htype != 3) return TXC_UNSUPPORTED_TX_PAYLOAD;
+    {
+        const uint8_t* dg = digests + 32 * (size_t)(J_cap + 2 * t);
+        bool same = tx.txid_ascii.len == 64;
+        for (int k = 0; same && k < 32; k++)
+            same = base[tx.txid_ascii.off + 2 * k] == (uint8_t)hex[dg[k] >> 4] && base[tx.txid_ascii.off + 2 * k + 1] == (uint8_t)hex[dg[k] & 15];
+        if (!same) return TXC_BAD_PROPOSAL_TXID;
+    }
+    if (!tx.endorser_parse_ok) return TXC_INVALID_ENDORSER_TRANSACTION;
+    if (tx.phash_claimed.len != 32 || !bytes_equal(base + tx.phash_claimed.off, digests + 32 * (size_t)(J_cap + 2 * t + 1), 32))
+        return TXC_INVALID_ENDORSER_TRANSACTION;
+    if (!tx.channel_ok) return TXC_TARGET_CHAIN_NOT_FOUND;
+    if (tx.overflow) return TXC_NOT_VALIDATED;                        // more endorsements than the device handles: CPU validator
+    if (!tx.endorsements_parse_ok) return TXC_INVALID_OTHER_REASON;
+    int32_t seen[BD_MAX_ENDS]; int32_t signer_code[BD_MAX_ENDS]; int n_seen = 0;
+    for (int i = 0; i < tx.n_ends; i++) {
+        const int32_t idn = tx.end_identity[i];
+        if (idn < 0) continue;
+        bool dup = false;
+        for (int s = 0; s < n_seen; s++) if (seen[s] == idn) { dup = true; break; }
+        if (dup) continue;
+        if (tx.end_job[i] < 0 || !sig_ok((uint32_t)tx.end_job[i])) continue;
+        seen[n_seen] = idn;
+        signer_code[n_seen] = msp.valid[idn] ? msp.msp_code[idn] : -1;
+        n_seen++;
+    }
+    uint32_t used = 0;
+    if (pol.n_nodes == 0 || !eval_policy(pol, 0, signer_code, n_seen, used, 0)) return TXC_ENDORSEMENT_POLICY_FAILURE;
+    uint64_t hsh = 1469598103934665603ull;
+    for (uint32_t k = 0; k < tx.txid_ascii.len; k++) hsh = (hsh ^ base[tx.txid_ascii.off + k]) * 1099511628211ull;
+    *txid_hash_out = hsh;
+    return TXC_VALID;
+}
+
+} }  // namespace fabgpu::bdev

@@ -22,6 +22,7 @@
 #include "bccsp_host.hpp"
 #include "blockval.hpp"
 #include "sha256.cuh"
+#include "blockdev_kernels.cuh"
 #include "ecdsa_kernels.cuh"
 
 #if defined(__SSE2__)
@@ -152,6 +153,20 @@ struct fabgpu_ctx {
         uint32_t *d_mask = nullptr, *d_off = nullptr, *h_mask = nullptr;
     } bb;
     double block_timing[5] = {0, 0, 0, 0, 0};   // plan, gates, device, decide, total [us]
+    // device-side copy of the MSP view / policy (block_plan_kernel, block_decide_kernel)
+    struct DevMsp {
+        uint8_t *id_blob = nullptr, *valid = nullptr, *keys_xy = nullptr, *channel = nullptr;
+        uint32_t* id_off = nullptr; int32_t *key_slot = nullptr, *msp_code = nullptr, *ht_idx = nullptr, *nodes = nullptr, *principal_code = nullptr;
+        uint64_t* ht_hash = nullptr; uint32_t ht_size = 0; int32_t n_ids = 0, n_nodes = 0, n_principals = 0; uint32_t channel_len = 0;
+        bool all_slots = true;
+    } dm;
+    struct DevBlock {
+        size_t tx_cap = 0, j_cap = 0;
+        uint32_t* d_env_off = nullptr; bdev::TxDev* d_txs = nullptr; bdev::ShaJobD* d_sha = nullptr; uint8_t *d_r = nullptr, *d_s = nullptr, *d_qx = nullptr,
+        *d_qy = nullptr, *d_gate = nullptr, *d_dig = nullptr, *d_flags = nullptr; int32_t *d_ks = nullptr, *d_ident = nullptr; uint32_t *d_mask = nullptr,
+        *d_off = nullptr, *d_counter = nullptr; uint64_t* d_hash = nullptr; bdev::Seg* d_seg = nullptr;
+        uint8_t* h_flags = nullptr; uint64_t* h_hash = nullptr; bdev::Seg* h_seg = nullptr; uint32_t* h_counter = nullptr; uint32_t* h_env_off = nullptr;
+    } db;
 };
 
 namespace {
@@ -280,6 +295,13 @@ void free_all(fabgpu_ctx* ctx)
         for (void* p : dev_ptrs) if (p) cudaFree(p);
         void* host_ptrs[] = {bb.h_block, bb.h_sha, bb.h_dig, bb.h_r, bb.h_s, bb.h_qx, bb.h_qy, bb.h_ks, bb.h_mask};
         for (void* p : host_ptrs) if (p) cudaFreeHost(p);
+        auto& dm = ctx->dm; auto& db = ctx->db;
+        void* dev2[] = {dm.id_blob, dm.valid, dm.keys_xy, dm.channel, dm.id_off, dm.key_slot, dm.msp_code, dm.ht_idx, dm.nodes, dm.principal_code, dm.ht_hash,
+                        db.d_env_off, db.d_txs, db.d_sha, db.d_r, db.d_s, db.d_qx, db.d_qy, db.d_gate, db.d_dig, db.d_flags, db.d_ks, db.d_ident, db.d_mask, db.d_off,
+                        db.d_counter, db.d_hash, db.d_seg};
+        for (void* p : dev2) if (p) cudaFree(p);
+        void* host2[] = {db.h_flags, db.h_hash, db.h_seg, db.h_counter, db.h_env_off};
+        for (void* p : host2) if (p) cudaFreeHost(p);
     }
     for (auto& dv : ctx->devs) {
         cudaSetDevice(dv.id);
@@ -736,6 +758,57 @@ int fabgpu_bccsp_verify(fabgpu_ctx* ctx, const uint8_t* key_xy, const uint8_t* s
 
 // ---- block-level pre-pass -------------------------------------------------------------------------------------------
 
+// Device copy of the MSP view and the policy for block_plan_kernel / block_decide_kernel (device 0 of the context).
+static int upload_msp(fabgpu_ctx* ctx, const uint8_t* id_blob, const uint32_t* id_off, const uint8_t* keys_xy, const uint8_t* valid, int n_ids,
+                      const int32_t* policy_nodes, int n_nodes)
+{
+    std::lock_guard<std::mutex> lk0(ctx->slot0_mu);
+    auto& dm = ctx->dm;
+    CK(ctx, cudaSetDevice(ctx->devs[0].id));
+    void* old[] = {dm.id_blob, dm.valid, dm.keys_xy, dm.channel, dm.id_off, dm.key_slot, dm.msp_code, dm.ht_idx, dm.nodes, dm.principal_code, dm.ht_hash};
+    for (void* p : old) if (p) cudaFree(p);
+    dm = fabgpu_ctx::DevMsp();
+    // MSP-id codes: equal strings <=> equal codes, shared between identities and policy principals
+    std::unordered_map<std::string, int32_t> codes;
+    auto code_of = [&](const std::string& sname) { auto it = codes.find(sname); if (it != codes.end()) return it->second; int32_t c = (int32_t)codes.size(); codes[sname] = c; return c; };
+    std::vector<int32_t> msp_code(n_ids > 0 ? n_ids : 1, -1), pcode(ctx->principals.size() ? ctx->principals.size() : 1, -1);
+    for (int i = 0; i < n_ids; i++) msp_code[i] = code_of(ctx->msp.mspid[i]);
+    for (size_t i = 0; i < ctx->principals.size(); i++) pcode[i] = code_of(ctx->principals[i]);
+    uint32_t hsz = 8; while (hsz < (uint32_t)(4 * n_ids + 8)) hsz <<= 1;
+    std::vector<uint64_t> hh(hsz, 0); std::vector<int32_t> hi(hsz, -1);
+    for (int i = 0; i < n_ids; i++) {
+        const uint64_t hv = bdev::sample_hash(id_blob + id_off[i], id_off[i + 1] - id_off[i]);
+        uint32_t pos = (uint32_t)hv & (hsz - 1);
+        while (hh[pos] != 0) pos = (pos + 1) & (hsz - 1);
+        hh[pos] = hv; hi[pos] = i;
+    }
+    dm.all_slots = true;
+    for (int i = 0; i < n_ids; i++) if (ctx->identity_slot[i] < 0) dm.all_slots = false;
+    auto up = [&](auto*& dst, const void* src, size_t bytes) -> int {
+        CK(ctx, cudaMalloc(&dst, bytes ? bytes : 4));
+        if (bytes) CK(ctx, cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice));
+        return FABGPU_OK;
+    };
+    const size_t blob_len = n_ids ? id_off[n_ids] : 0;
+    int rc = 0;
+    rc |= up(dm.id_blob, id_blob, blob_len);
+    rc |= up(dm.id_off, id_off, 4 * (size_t)(n_ids + 1) * (n_ids ? 1 : 0));
+    rc |= up(dm.valid, valid, (size_t)n_ids);
+    rc |= up(dm.keys_xy, keys_xy, 64 * (size_t)n_ids);
+    rc |= up(dm.key_slot, ctx->identity_slot.data(), 4 * (size_t)n_ids);
+    rc |= up(dm.msp_code, msp_code.data(), 4 * (size_t)n_ids);
+    rc |= up(dm.ht_hash, hh.data(), 8 * (size_t)hsz);
+    rc |= up(dm.ht_idx, hi.data(), 4 * (size_t)hsz);
+    rc |= up(dm.nodes, policy_nodes, 16 * (size_t)n_nodes);
+    rc |= up(dm.principal_code, pcode.data(), 4 * ctx->principals.size());
+    rc |= up(dm.channel, ctx->channel.data(), ctx->channel.size());
+    if (rc) return FABGPU_E_CUDA;
+    dm.ht_size = n_ids ? hsz : 0; dm.n_ids = n_ids; dm.n_nodes = n_nodes; dm.n_principals = (int32_t)ctx->principals.size();
+    dm.channel_len = (uint32_t)ctx->channel.size();
+    return FABGPU_OK;
+}
+
+
 int fabgpu_msp_configure(fabgpu_ctx* ctx, const uint8_t* id_blob, const uint32_t* id_off, const uint8_t* mspid_blob,
                          const uint32_t* mspid_off, const uint8_t* keys_xy, const uint8_t* valid, int n_ids,
                          const int32_t* policy_nodes, int n_nodes, const uint8_t* principal_blob, const uint32_t* principal_off,
@@ -770,7 +843,7 @@ int fabgpu_msp_configure(fabgpu_ctx* ctx, const uint8_t* id_blob, const uint32_t
         int rc = fabgpu_keys_register(ctx, keys_xy, n_ids, ctx->identity_slot.data());
         if (rc) return rc;
     }
-    return FABGPU_OK;
+    return upload_msp(ctx, id_blob, id_off, keys_xy, valid, n_ids, policy_nodes, n_nodes);
 }
 
 int fabgpu_block_buffer(fabgpu_ctx* ctx, size_t bytes, uint8_t** out)
@@ -786,6 +859,114 @@ int fabgpu_block_buffer(fabgpu_ctx* ctx, size_t bytes, uint8_t** out)
 
 static int validate_impl(fabgpu_ctx* ctx, const uint8_t* block, size_t block_len, const uint32_t* env_off, size_t n_env, uint8_t* flags,
                          size_t flags_cap, size_t* n_tx_out);
+
+// Device path of the block pre-pass: the host only copies bytes in and flags out (and marks duplicate tx ids).
+//   H2D block + envelope offsets -> block_plan_kernel (walk, identity lookup, DER gates, job emission)
+//   -> sha256_segments_kernel (signed messages + check digests) -> one verify launch -> block_decide_kernel -> D2H flags.
+static int validate_device(fabgpu_ctx* ctx, const uint8_t* block, size_t block_len, const uint32_t* env_off, size_t n_env, uint8_t* flags,
+                           size_t flags_cap, size_t* n_tx_out)
+{
+    std::lock_guard<std::mutex> lk0(ctx->slot0_mu);
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto us = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+        return std::chrono::duration<double, std::micro>(b - a).count();
+    };
+    auto t0 = now();
+    Device& dv = ctx->devs[0];
+    DevSlot& ds = dv.slot[0];
+    auto& bb = ctx->bb; auto& db = ctx->db; auto& dm = ctx->dm;
+    CK(ctx, cudaSetDevice(dv.id));
+    if (block_len > bb.block_cap) { int rc = grow_dev(ctx, bb.d_block, block_len + (block_len >> 2)); if (rc) return rc; bb.block_cap = block_len + (block_len >> 2); }
+    CK(ctx, cudaMemcpyAsync(bb.d_block, block, block_len, cudaMemcpyHostToDevice, ds.stream));
+    std::vector<uint32_t> split;
+    if (!env_off) {                                           // serialized common.Block: find the envelopes (serial, length-prefixed)
+        std::vector<blockval::Seg> envs;
+        if (!blockval::split_block(block, block_len, envs)) { cudaStreamSynchronize(ds.stream); ctx->last_error = "block does not parse"; return FABGPU_E_ARG; }
+        // envelopes of a Block are not contiguous (each carries a field header): pass (offset, length) pairs as 2 T + ... -> use an offsets
+        // table with explicit ends by giving every envelope its own [off, off+len) through a doubled table
+        n_env = envs.size();
+        split.resize(2 * n_env + 2);
+        for (size_t i = 0; i < n_env; i++) { split[2 * i] = envs[i].off; split[2 * i + 1] = envs[i].off + envs[i].len; }
+    }
+    const size_t T = n_env;
+    *n_tx_out = T;
+    if (T > flags_cap) { cudaStreamSynchronize(ds.stream); ctx->last_error = "flags buffer too small"; return FABGPU_E_ARG; }
+    if (T == 0) { CK(ctx, cudaStreamSynchronize(ds.stream)); return FABGPU_OK; }
+    const size_t J_cap = T * (1 + BD_MAX_ENDS);
+    if (T > db.tx_cap) {
+        const size_t tc = T + (T >> 2) + 256, jc = tc * (1 + BD_MAX_ENDS);
+        int rc = 0;
+        rc |= grow_dev(ctx, db.d_env_off, 8 * (tc + 1)); rc |= grow_dev(ctx, db.d_txs, sizeof(bdev::TxDev) * tc);
+        rc |= grow_dev(ctx, db.d_sha, sizeof(bdev::ShaJobD) * (jc + 2 * tc)); rc |= grow_dev(ctx, db.d_dig, 32 * (jc + 2 * tc));
+        rc |= grow_dev(ctx, db.d_r, 32 * jc); rc |= grow_dev(ctx, db.d_s, 32 * jc); rc |= grow_dev(ctx, db.d_qx, 32 * jc); rc |= grow_dev(ctx, db.d_qy, 32 * jc);
+        rc |= grow_dev(ctx, db.d_gate, jc); rc |= grow_dev(ctx, db.d_ks, 4 * jc); rc |= grow_dev(ctx, db.d_ident, 4 * jc);
+        rc |= grow_dev(ctx, db.d_mask, jc / 8 + 8); rc |= grow_dev(ctx, db.d_off, jc / 8 + 8); rc |= grow_dev(ctx, db.d_counter, 16);
+        rc |= grow_dev(ctx, db.d_flags, tc); rc |= grow_dev(ctx, db.d_hash, 8 * tc); rc |= grow_dev(ctx, db.d_seg, 8 * tc);
+        rc |= grow_host(ctx, db.h_flags, tc); rc |= grow_host(ctx, db.h_hash, 8 * tc); rc |= grow_host(ctx, db.h_seg, 8 * tc);
+        rc |= grow_host(ctx, db.h_counter, 16); rc |= grow_host(ctx, db.h_env_off, 8 * (tc + 1));
+        if (rc) return FABGPU_E_CUDA;
+        db.tx_cap = tc; db.j_cap = jc;
+    }
+    // envelope table on the device: pairs (begin, end) so that both entry points share one kernel
+    for (size_t i = 0; i < T; i++) {
+        db.h_env_off[2 * i] = env_off ? env_off[i] : split[2 * i];
+        db.h_env_off[2 * i + 1] = env_off ? env_off[i + 1] : split[2 * i + 1];
+    }
+    CK(ctx, cudaMemcpyAsync(db.d_env_off, db.h_env_off, 8 * T, cudaMemcpyHostToDevice, ds.stream));
+    CK(ctx, cudaMemsetAsync(db.d_counter, 0, 16, ds.stream));
+    auto t1 = now();
+    bdev::MspDev m; m.id_blob = dm.id_blob; m.id_off = dm.id_off; m.key_slot = dm.key_slot; m.valid = dm.valid; m.msp_code = dm.msp_code;
+    m.keys_xy = dm.keys_xy; m.ht_hash = dm.ht_hash; m.ht_idx = dm.ht_idx; m.ht_size = dm.ht_size; m.n_ids = dm.n_ids;
+    bdev::PolicyDev pol; pol.nodes = dm.nodes; pol.n_nodes = dm.n_nodes; pol.principal_code = dm.principal_code; pol.n_principals = dm.n_principals;
+    bdev::JobArrays ja; ja.sha = db.d_sha; ja.r = db.d_r; ja.s = db.d_s; ja.key_slot = db.d_ks; ja.identity = db.d_ident; ja.qx = dm.all_slots ? nullptr : db.d_qx;
+    ja.qy = dm.all_slots ? nullptr : db.d_qy; ja.gate_ok = db.d_gate; ja.J_cap = (uint32_t)J_cap; ja.T = (uint32_t)T;
+    const unsigned tb = (unsigned)((T + 127) / 128);
+    bdev::block_plan_kernel<<<tb, 128, 0, ds.stream>>>(bb.d_block, db.d_env_off, (uint32_t)T, m, dm.channel, dm.channel_len, db.d_txs, ja, db.d_counter);
+    ctx->launches++;
+    CK(ctx, cudaGetLastError());
+    CK(ctx, cudaMemcpyAsync(db.h_counter, db.d_counter, 4, cudaMemcpyDeviceToHost, ds.stream));
+    CK(ctx, cudaStreamSynchronize(ds.stream));
+    const size_t n_end = std::min((size_t)db.h_counter[0], J_cap - T);
+    const size_t J = T + n_end;
+    auto t2 = now();
+    // digests: signature messages [0, J) and the check pairs [J_cap, J_cap + 2T)
+    sha256_segments_kernel<<<(unsigned)((J + 127) / 128), 128, 0, ds.stream>>>(bb.d_block, reinterpret_cast<const ShaJob*>(db.d_sha), (uint32_t)J, db.d_dig);
+    sha256_segments_kernel<<<(unsigned)((2 * T + 127) / 128), 128, 0, ds.stream>>>(bb.d_block, reinterpret_cast<const ShaJob*>(db.d_sha + J_cap), (uint32_t)(2 * T),
+                                                                                 db.d_dig + 32 * J_cap);
+    ctx->launches += 2;
+    CK(ctx, cudaGetLastError());
+    int rc = launch_verify(ctx, dv, dm.all_slots ? MODE_CACHED : MODE_MIXED, db.d_ks, db.d_qx, db.d_qy, db.d_dig, db.d_r, db.d_s, J, db.d_mask, db.d_off, ds.stream);
+    if (rc) return rc;
+    bdev::block_decide_kernel<<<tb, 128, 0, ds.stream>>>(bb.d_block, db.d_txs, (uint32_t)T, m, pol, db.d_mask, db.d_gate, db.d_dig, (uint32_t)J_cap, db.d_flags,
+                                                         db.d_hash, db.d_seg);
+    ctx->launches++;
+    CK(ctx, cudaGetLastError());
+    CK(ctx, cudaMemcpyAsync(db.h_flags, db.d_flags, T, cudaMemcpyDeviceToHost, ds.stream));
+    CK(ctx, cudaMemcpyAsync(db.h_hash, db.d_hash, 8 * T, cudaMemcpyDeviceToHost, ds.stream));
+    CK(ctx, cudaMemcpyAsync(db.h_seg, db.d_seg, 8 * T, cudaMemcpyDeviceToHost, ds.stream));
+    CK(ctx, cudaStreamSynchronize(ds.stream));
+    auto t3 = now();
+    // markTXIdDuplicates (v20/validator.go:283-297) on the host: among VALID transactions, a later one with an already seen tx id
+    memcpy(flags, db.h_flags, T);
+    std::unordered_multimap<uint64_t, uint32_t> seen;
+    seen.reserve(T * 2);
+    for (size_t t = 0; t < T; t++) {
+        if (flags[t] != blockval::TX_VALID) continue;
+        const bdev::Seg id = db.h_seg[t];
+        bool dup = false;
+        auto range = seen.equal_range(db.h_hash[t]);
+        for (auto it = range.first; it != range.second && !dup; ++it) {
+            const bdev::Seg o = db.h_seg[it->second];
+            dup = o.len == id.len && memcmp(block + o.off, block + id.off, id.len) == 0;
+        }
+        if (dup) flags[t] = blockval::TX_DUPLICATE_TXID; else seen.emplace(db.h_hash[t], (uint32_t)t);
+    }
+    auto t4 = now();
+    ctx->block_timing[0] = us(t0, t1); ctx->block_timing[1] = us(t1, t2); ctx->block_timing[2] = us(t2, t3); ctx->block_timing[3] = us(t3, t4);
+    ctx->block_timing[4] = us(t0, t4);
+    return FABGPU_OK;
+}
+
 
 int fabgpu_validate_block(fabgpu_ctx* ctx, const uint8_t* block, size_t block_len, uint8_t* flags, size_t flags_cap, size_t* n_tx_out)
 {
@@ -805,6 +986,10 @@ static int validate_impl(fabgpu_ctx* ctx, const uint8_t* block, size_t block_len
     if (!ctx || !block || !flags || !n_tx_out) return FABGPU_E_ARG;
     if (block_len >= (1ull << 32)) { ctx->last_error = "block larger than 4 GiB"; return FABGPU_E_ARG; }
     if (fault_injected()) { ctx->last_error = "fault injected (FABGPU_FAULT_INJECT=1)"; return FABGPU_E_INJECTED; }
+    {
+        const char* hp = getenv("FABGPU_BLOCK_HOST");            // "1": parse / gate / decide on host threads (blockval.cpp) instead of on the device
+        if (!(hp && hp[0] == '1')) return validate_device(ctx, block, block_len, env_off, n_env, flags, flags_cap, n_tx_out);
+    }
     std::lock_guard<std::mutex> lk0(ctx->slot0_mu);
     auto now = [] { return std::chrono::steady_clock::now(); };
     auto us = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {

@@ -68,3 +68,73 @@ def test_structural_corner_cases():
     # empty block
     blk3 = pb.block(10, [])
     assert blockutil.host_logic_flags(blk3, ids, net.channel, net.policy_n_of(3), net.principals)[0].tolist() == []
+
+
+# ---- the device-side implementation of the same logic (blockdev.cuh), executed on the host ---------------------------------
+def _envs(blk):
+    envs = pb.parse(pb.parse(blk, ob.S_BLOCK)["data"] or b"", ob.S_BLOCKDATA)["data"]
+    off = np.zeros(len(envs) + 1, np.uint32)
+    off[1:] = np.cumsum([len(e) for e in envs])
+    return b"".join(envs), off
+
+
+def test_device_logic_fault_classes_match_oracle():
+    net = blockgen.Network()
+    faults = blockutil.fault_map(70)
+    blk, info = blockgen.build_block(net, 70, 3, faults, seed=11, nthreads=2)
+    ids = blockutil.identities_of(net)
+    for n in (2, 3, 4):
+        exp = ob.validate_block(blk, ids, net.channel, net.policy_n_of(n), net.principals)
+        got = blockutil.device_logic_flags(info["env_blob"], info["env_off"], ids, net.channel, net.policy_n_of(n), net.principals)
+        assert got.tolist() == exp.tolist(), n
+    nodes = np.array([(0, 2, 1, 2), (1, 0, 0, 0), (0, 1, 3, 2), (1, 1, 0, 0), (1, 2, 0, 0)], np.int32)
+    exp = ob.validate_block(blk, ids, net.channel, nodes, net.principals)
+    assert blockutil.device_logic_flags(info["env_blob"], info["env_off"], ids, net.channel, nodes, net.principals).tolist() == exp.tolist()
+
+
+def test_device_logic_structural_corner_cases():
+    net = blockgen.Network()
+    ids = blockutil.identities_of(net)
+    blk, _ = blockgen.build_block(net, 6, 3, {}, seed=5, nthreads=2)
+    envs = pb.parse(pb.parse(blk, ob.S_BLOCK)["data"], ob.S_BLOCKDATA)["data"]
+    good = envs[0]
+    variants = [good, b"", b"\x0a\x05abc", pb.f_uint(1, 5), good + pb.f_bytes(9, b"unknown field is skipped"), pb.f_bytes(1, b""),
+                envs[1][: len(envs[1]) // 2], pb.f_bytes(2, b"sig-only"), envs[2], envs[3]]
+    blk2 = pb.block(9, variants)
+    exp = ob.validate_block(blk2, ids, net.channel, net.policy_n_of(3), net.principals)
+    blob, off = _envs(blk2)
+    assert blockutil.device_logic_flags(blob, off, ids, net.channel, net.policy_n_of(3), net.principals).tolist() == exp.tolist()
+    assert blockutil.device_logic_flags(b"", np.zeros(1, np.uint32), ids, net.channel, net.policy_n_of(3), net.principals).tolist() == []
+
+
+def test_device_der_gate_matches_host_gate_fuzz():
+    import random
+    from oracle import goasn1, p256
+    from util import pkg
+    b = pkg().binding
+    rnd = random.Random(77)
+    seeds = [goasn1.marshal_ecdsa_signature(rnd.getrandbits(256), rnd.getrandbits(255)) for _ in range(30)]
+    seeds += [goasn1.marshal_ecdsa_signature(rnd.getrandbits(8 * k), rnd.getrandbits(8 * j)) for k in (1, 31, 33, 40) for j in (1, 31, 32, 33)]
+    seeds += [goasn1.marshal_ecdsa_signature(5, p256.HALF_N), goasn1.marshal_ecdsa_signature(5, p256.HALF_N + 1), goasn1.marshal_ecdsa_signature(-5, 7),
+              goasn1.marshal_ecdsa_signature(0, 7), goasn1.marshal_ecdsa_signature(7, 0), b"", b"\x30\x00"]
+    n = 0
+    for sd in seeds:
+        for it in range(120):
+            m = bytearray(sd)
+            if it:
+                for _ in range(rnd.choice((1, 1, 2, 3))):
+                    op = rnd.random()
+                    if op < 0.6 and m:
+                        m[rnd.randrange(len(m))] = rnd.getrandbits(8)
+                    elif op < 0.8 and m:
+                        del m[rnd.randrange(len(m))]
+                    else:
+                        m.insert(rnd.randrange(len(m) + 1), rnd.getrandbits(8))
+            sig = bytes(m)
+            st, r, s = b.gate_signature(sig)
+            ok, r2, s2 = blockutil.device_gate(sig)
+            assert ok == (st == b.ST_VALID), sig.hex()
+            if ok:
+                assert (r, s) == (r2, s2)
+            n += 1
+    assert n > 5000
