@@ -266,7 +266,7 @@ class Context:
         return flags[: n.value]
 
     def block_timing(self):
-        out = (ctypes.c_double * 5)()
+        out = (ctypes.c_double * 10)()
         self._ck(lib().fabgpu_block_timing(self._h, out))
         return [float(x) for x in out]
 

@@ -7,7 +7,7 @@ namespace fabgpu { namespace bdev {
 
 // Walks every envelope, looks identities up, gates every DER signature and emits the SHA-256 / verify jobs.
 // Creator jobs sit at the transaction's own index; endorsement jobs are appended after them through one atomic counter.
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(32)
 block_plan_kernel(const uint8_t* __restrict__ block, const uint32_t* __restrict__ env_off, uint32_t T, MspDev msp, const uint8_t* __restrict__ channel,
                   uint32_t channel_len, TxDev* __restrict__ txs, JobArrays ja, uint32_t* __restrict__ n_end)
 {

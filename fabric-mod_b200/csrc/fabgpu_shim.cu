@@ -152,7 +152,8 @@ struct fabgpu_ctx {
         int32_t *d_ks = nullptr, *h_ks = nullptr;
         uint32_t *d_mask = nullptr, *d_off = nullptr, *h_mask = nullptr;
     } bb;
-    double block_timing[5] = {0, 0, 0, 0, 0};   // plan, gates, device, decide, total [us]
+    double block_timing[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // host phases [0..4] (see fabgpu_block_timing), device stages [5..9]
+    cudaEvent_t bev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     // device-side copy of the MSP view / policy (block_plan_kernel, block_decide_kernel)
     struct DevMsp {
         uint8_t *id_blob = nullptr, *valid = nullptr, *keys_xy = nullptr, *channel = nullptr;
@@ -785,7 +786,7 @@ static int upload_msp(fabgpu_ctx* ctx, const uint8_t* id_blob, const uint32_t* i
     dm.all_slots = true;
     for (int i = 0; i < n_ids; i++) if (ctx->identity_slot[i] < 0) dm.all_slots = false;
     auto up = [&](auto*& dst, const void* src, size_t bytes) -> int {
-        CK(ctx, cudaMalloc(&dst, bytes ? bytes : 4));
+        CK(ctx, cudaMalloc(&dst, bytes + 8));                 // slack: word-wise readers may touch the aligned word past the end
         if (bytes) CK(ctx, cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice));
         return FABGPU_OK;
     };
@@ -877,7 +878,12 @@ static int validate_device(fabgpu_ctx* ctx, const uint8_t* block, size_t block_l
     auto& bb = ctx->bb; auto& db = ctx->db; auto& dm = ctx->dm;
     CK(ctx, cudaSetDevice(dv.id));
     if (block_len > bb.block_cap) { int rc = grow_dev(ctx, bb.d_block, block_len + (block_len >> 2)); if (rc) return rc; bb.block_cap = block_len + (block_len >> 2); }
+    const char* evs = getenv("FABGPU_BLOCK_EVENTS");          // "1": time the device stages with CUDA events (diagnostics)
+    const bool use_ev = evs && evs[0] == '1';
+    if (use_ev) for (auto& e : ctx->bev) if (!e) CK(ctx, cudaEventCreate(&e));
+    if (use_ev) CK(ctx, cudaEventRecord(ctx->bev[0], ds.stream));
     CK(ctx, cudaMemcpyAsync(bb.d_block, block, block_len, cudaMemcpyHostToDevice, ds.stream));
+    if (use_ev) CK(ctx, cudaEventRecord(ctx->bev[1], ds.stream));
     std::vector<uint32_t> split;
     if (!env_off) {                                           // serialized common.Block: find the envelopes (serial, length-prefixed)
         std::vector<blockval::Seg> envs;
@@ -921,9 +927,10 @@ static int validate_device(fabgpu_ctx* ctx, const uint8_t* block, size_t block_l
     bdev::JobArrays ja; ja.sha = db.d_sha; ja.r = db.d_r; ja.s = db.d_s; ja.key_slot = db.d_ks; ja.identity = db.d_ident; ja.qx = dm.all_slots ? nullptr : db.d_qx;
     ja.qy = dm.all_slots ? nullptr : db.d_qy; ja.gate_ok = db.d_gate; ja.J_cap = (uint32_t)J_cap; ja.T = (uint32_t)T;
     const unsigned tb = (unsigned)((T + 127) / 128);
-    bdev::block_plan_kernel<<<tb, 128, 0, ds.stream>>>(bb.d_block, db.d_env_off, (uint32_t)T, m, dm.channel, dm.channel_len, db.d_txs, ja, db.d_counter);
+    bdev::block_plan_kernel<<<(unsigned)((T + 31) / 32), 32, 0, ds.stream>>>(bb.d_block, db.d_env_off, (uint32_t)T, m, dm.channel, dm.channel_len, db.d_txs, ja, db.d_counter);
     ctx->launches++;
     CK(ctx, cudaGetLastError());
+    if (use_ev) CK(ctx, cudaEventRecord(ctx->bev[2], ds.stream));
     CK(ctx, cudaMemcpyAsync(db.h_counter, db.d_counter, 4, cudaMemcpyDeviceToHost, ds.stream));
     CK(ctx, cudaStreamSynchronize(ds.stream));
     const size_t n_end = std::min((size_t)db.h_counter[0], J_cap - T);
@@ -935,12 +942,15 @@ static int validate_device(fabgpu_ctx* ctx, const uint8_t* block, size_t block_l
                                                                                  db.d_dig + 32 * J_cap);
     ctx->launches += 2;
     CK(ctx, cudaGetLastError());
+    if (use_ev) CK(ctx, cudaEventRecord(ctx->bev[3], ds.stream));
     int rc = launch_verify(ctx, dv, dm.all_slots ? MODE_CACHED : MODE_MIXED, db.d_ks, db.d_qx, db.d_qy, db.d_dig, db.d_r, db.d_s, J, db.d_mask, db.d_off, ds.stream);
     if (rc) return rc;
+    if (use_ev) CK(ctx, cudaEventRecord(ctx->bev[4], ds.stream));
     bdev::block_decide_kernel<<<tb, 128, 0, ds.stream>>>(bb.d_block, db.d_txs, (uint32_t)T, m, pol, db.d_mask, db.d_gate, db.d_dig, (uint32_t)J_cap, db.d_flags,
                                                          db.d_hash, db.d_seg);
     ctx->launches++;
     CK(ctx, cudaGetLastError());
+    if (use_ev) CK(ctx, cudaEventRecord(ctx->bev[5], ds.stream));
     CK(ctx, cudaMemcpyAsync(db.h_flags, db.d_flags, T, cudaMemcpyDeviceToHost, ds.stream));
     CK(ctx, cudaMemcpyAsync(db.h_hash, db.d_hash, 8 * T, cudaMemcpyDeviceToHost, ds.stream));
     CK(ctx, cudaMemcpyAsync(db.h_seg, db.d_seg, 8 * T, cudaMemcpyDeviceToHost, ds.stream));
@@ -964,6 +974,7 @@ static int validate_device(fabgpu_ctx* ctx, const uint8_t* block, size_t block_l
     auto t4 = now();
     ctx->block_timing[0] = us(t0, t1); ctx->block_timing[1] = us(t1, t2); ctx->block_timing[2] = us(t2, t3); ctx->block_timing[3] = us(t3, t4);
     ctx->block_timing[4] = us(t0, t4);
+    for (int k = 0; k < 5; k++) { float ms = 0; if (use_ev) cudaEventElapsedTime(&ms, ctx->bev[k], ctx->bev[k + 1]); ctx->block_timing[5 + k] = 1e3 * ms; }
     return FABGPU_OK;
 }
 
@@ -1126,10 +1137,10 @@ static int validate_impl(fabgpu_ctx* ctx, const uint8_t* block, size_t block_len
     return FABGPU_OK;
 }
 
-int fabgpu_block_timing(const fabgpu_ctx* ctx, double out_us[5])
+int fabgpu_block_timing(const fabgpu_ctx* ctx, double out_us[10])
 {
     if (!ctx || !out_us) return FABGPU_E_ARG;
-    for (int i = 0; i < 5; i++) out_us[i] = ctx->block_timing[i];
+    for (int i = 0; i < 10; i++) out_us[i] = ctx->block_timing[i];
     return FABGPU_OK;
 }
 

@@ -47,85 +47,67 @@ __device__ __forceinline__ void sha256_compress(uint32_t* h, uint32_t* w)
     h[0] += a; h[1] += b; h[2] += c; h[3] += d; h[4] += e; h[5] += f; h[6] += g; h[7] += hh;
 }
 
-// Streams message bytes into 16-word blocks.  The block buffer lives in local memory so that it can be indexed with a
-// run-time position (one STL per word, 16 LDL per compression); source bytes are fetched as aligned 32-bit words wherever
-// the segment allows (a segment may start at any byte offset of the block).
-struct ShaStream {
-    uint32_t h[8];
-    uint32_t wl[16];
-    uint32_t fillw;      // words in wl
-    uint64_t acc;        // pending bytes (nacc of them) in the low bits, most significant first
-    uint32_t nacc;
+// Byte x of the padded message: the three ranges back to back, then 0x80, zeros and the 64-bit big-endian bit length.
+__device__ __forceinline__ uint32_t sha_msg_byte(const uint8_t* __restrict__ buf, const ShaJob& job, uint64_t total, uint64_t padded, uint64_t x)
+{
+    if (x < total) {
+        uint64_t y = x;
+        if (y < job.len[0]) return buf[job.off[0] + y];
+        y -= job.len[0];
+        if (y < job.len[1]) return buf[job.off[1] + y];
+        y -= job.len[1];
+        return buf[job.off[2] + y];
+    }
+    if (x == total) return 0x80u;
+    if (x >= padded - 8) return (uint32_t)(((total * 8) >> (8 * (padded - 1 - x))) & 0xff);
+    return 0u;
+}
 
-    __device__ __forceinline__ void init()
-    {
-        h[0] = 0x6a09e667; h[1] = 0xbb67ae85; h[2] = 0x3c6ef372; h[3] = 0xa54ff53a; h[4] = 0x510e527f; h[5] = 0x9b05688c; h[6] = 0x1f83d9ab; h[7] = 0x5be0cd19;
-        fillw = 0; acc = 0; nacc = 0;
-    }
-    __device__ __forceinline__ void emit(uint32_t be_word)
-    {
-        wl[fillw++] = be_word;
-        if (fillw == 16) {
-            uint32_t w[16];
-#pragma unroll
-            for (int k = 0; k < 16; k++) w[k] = wl[k];
-            sha256_compress(h, w);
-            fillw = 0;
-        }
-    }
-    __device__ __forceinline__ void byte(uint32_t b)
-    {
-        acc = (acc << 8) | b;
-        if (++nacc == 4) { emit((uint32_t)acc); acc = 0; nacc = 0; }
-    }
-    __device__ __forceinline__ void word_le(uint32_t le)   // four message bytes as loaded from memory
-    {
-        const uint32_t be = __byte_perm(le, 0, 0x0123);
-        acc = (acc << 32) | be;
-        emit((uint32_t)(acc >> (8 * nacc)));
-        acc &= (1ull << (8 * nacc)) - 1ull;
-    }
-    __device__ __forceinline__ void feed(const uint8_t* __restrict__ p, uint32_t len)
-    {
-        uint32_t i = 0;
-        while (i < len && ((uintptr_t)(p + i) & 3u)) byte(p[i++]);
-        // 64 bytes at a time: all sixteen loads are issued before any is consumed (ncu showed the one-load-at-a-time
-        // form stalled on long_scoreboard 4.2 cycles per issue)
-        for (; i + 64 <= len; i += 64) {
-            uint32_t t[16];
-#pragma unroll
-            for (int k = 0; k < 16; k++) t[k] = __ldg(reinterpret_cast<const uint32_t*>(p + i) + k);
-#pragma unroll
-            for (int k = 0; k < 16; k++) word_le(t[k]);
-        }
-        for (; i + 4 <= len; i += 4) word_le(__ldg(reinterpret_cast<const uint32_t*>(p + i)));
-        while (i < len) byte(p[i++]);
-    }
-    __device__ __forceinline__ void finish(uint64_t total_bytes, uint8_t* out)
-    {
-        byte(0x80);
-        while (nacc != 0) byte(0);
-        while (fillw != 14) emit(0);
-        emit((uint32_t)((total_bytes * 8) >> 32));
-        emit((uint32_t)(total_bytes * 8));
-        uint32_t* o = reinterpret_cast<uint32_t*>(out);
-#pragma unroll
-        for (int k = 0; k < 8; k++) o[k] = __byte_perm(h[k], 0, 0x0123);     // big-endian bytes
-    }
-};
-
-// digests[j] = SHA-256(buf[off0 .. off0+len0) || buf[off1 ..) || buf[off2 ..))
+// digests[j] = SHA-256(buf[off0 .. off0+len0) || buf[off1 ..) || buf[off2 ..)).  One thread per message, the sixteen message
+// words of a block stay in registers: a 64-byte block that lies inside one range is fetched as 17 aligned 32-bit loads
+// (issued together) and re-aligned with funnel shifts, whatever the byte offset of the range; blocks that straddle two
+// ranges or contain padding are assembled byte by byte (at most three or four per message).
+// `buf` must be readable 4 bytes past the last range (the block buffer is allocated with slack).
 __global__ void __launch_bounds__(128)
 sha256_segments_kernel(const uint8_t* __restrict__ buf, const ShaJob* __restrict__ jobs, uint32_t n, uint8_t* __restrict__ digests)
 {
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
     const ShaJob job = jobs[j];
-    ShaStream st;
-    st.init();
+    uint32_t h[8] = {0x6a09e667, 0xbb67ae85, 0x3c6ef372, 0xa54ff53a, 0x510e527f, 0x9b05688c, 0x1f83d9ab, 0x5be0cd19};
+    const uint64_t total = (uint64_t)job.len[0] + job.len[1] + job.len[2];
+    const uint64_t padded = (total + 9 + 63) / 64 * 64;
+    const uint64_t e0 = job.len[0], e1 = e0 + job.len[1];
+    for (uint64_t o = 0; o < padded; o += 64) {
+        uint32_t w[16];
+        // which range holds [o, o+64) entirely, if any
+        const uint8_t* src = nullptr;
+        if (o + 64 <= e0) src = buf + job.off[0] + o;
+        else if (o >= e0 && o + 64 <= e1) src = buf + job.off[1] + (o - e0);
+        else if (o >= e1 && o + 64 <= total) src = buf + job.off[2] + (o - e1);
+        if (src) {
+            const uint32_t sh = 8u * (uint32_t)((uintptr_t)src & 3u);
+            const uint32_t* p32 = reinterpret_cast<const uint32_t*>((uintptr_t)src & ~(uintptr_t)3);
+            uint32_t x[17];
+#pragma unroll
+            for (int k = 0; k < 17; k++) x[k] = __ldg(p32 + k);
+#pragma unroll
+            for (int k = 0; k < 16; k++) w[k] = __byte_perm(__funnelshift_r(x[k], x[k + 1], sh), 0, 0x0123);
+        } else {
 #pragma unroll 1
-    for (int sgi = 0; sgi < 3; sgi++) st.feed(buf + job.off[sgi], job.len[sgi]);
-    st.finish((uint64_t)job.len[0] + job.len[1] + job.len[2], digests + 32 * (size_t)j);
+            for (int k = 0; k < 16; k++) {
+                uint32_t v = 0;
+                for (int b = 0; b < 4; b++) v = (v << 8) | sha_msg_byte(buf, job, total, padded, o + 4 * k + b);
+                // w[k] with a run-time k: select without dynamic indexing
+#pragma unroll
+                for (int q = 0; q < 16; q++) if (q == k) w[q] = v;
+            }
+        }
+        sha256_compress(h, w);
+    }
+    uint32_t* out = reinterpret_cast<uint32_t*>(digests + 32 * (size_t)j);
+#pragma unroll
+    for (int k = 0; k < 8; k++) out[k] = __byte_perm(h[k], 0, 0x0123);      // big-endian bytes
 }
 
 }  // namespace fabgpu
