@@ -63,13 +63,15 @@ FAB_HD jac jac_add(const jac& p, const jac& q)
     return r;
 }
 
-// Mixed addition (madd-2004-hmv shape, Z2 = 1): 8M + 3S + 7 additive ops.
+// Mixed addition (madd-2004-hmv shape, Z2 = 1): 8M + 3S + 7 additive ops.  Independent products are issued in pairs
+// (fe_mul2) so that one warp keeps both integer pipes busier.
 FAB_HD jac jac_add_aff(const jac& p, const aff& q)
 {
     if (jac_is_infinity(p)) return jac_from_aff(q);
     const u256 z1z1 = fe_sqr(p.Z);
-    const u256 u2 = fe_mul(q.x, z1z1);
-    const u256 s2 = fe_mul(fe_mul(q.y, p.Z), z1z1);
+    u256 u2, yz;
+    fe_mul2(q.x, z1z1, q.y, p.Z, u2, yz);                 // U2 = X2 Z1^2 ; Y2 Z1
+    const u256 s2 = fe_mul(yz, z1z1);
     const u256 h = fe_sub(u2, p.X);
     const u256 rr = fe_sub(s2, p.Y);
     if (u256_is_zero(h)) {
@@ -77,11 +79,13 @@ FAB_HD jac jac_add_aff(const jac& p, const aff& q)
         return jac_infinity();
     }
     const u256 hh = fe_sqr(h);
-    const u256 hhh = fe_mul(h, hh);
-    const u256 v = fe_mul(p.X, hh);
+    u256 hhh, v;
+    fe_mul2(h, hh, p.X, hh, hhh, v);                      // H^3 ; V = X1 H^2
     jac r;
     r.X = fe_sub(fe_sub(fe_sqr(rr), hhh), fe_dbl(v));
-    r.Y = fe_sub(fe_mul(rr, fe_sub(v, r.X)), fe_mul(p.Y, hhh));
+    u256 t, yh;
+    fe_mul2(rr, fe_sub(v, r.X), p.Y, hhh, t, yh);         // r (V - X3) ; Y1 H^3
+    r.Y = fe_sub(t, yh);
     r.Z = fe_mul(p.Z, h);
     return r;
 }
