@@ -30,6 +30,7 @@ type device struct {
 type slot struct {
 	qx, qy, e, r, s []byte
 	mask, offcurve  []uint32
+	keySlot         []int32 // per signature: table slot of its key (fabgpu_keys_register) or -1
 }
 
 func openDevice(deviceIDs []int, maxBatch int) (*device, error) {
@@ -60,6 +61,12 @@ func openDevice(deviceIDs []int, maxBatch int) (*device, error) {
 			s:    unsafe.Slice((*byte)(unsafe.Pointer(s)), n),
 			mask: unsafe.Slice((*uint32)(unsafe.Pointer(mask)), words), offcurve: unsafe.Slice((*uint32)(unsafe.Pointer(off)), words),
 		}
+		var ks *C.int32_t
+		if rc := C.fabgpu_host_key_slots(d.ctx, C.int(i), &ks); rc != C.FABGPU_OK {
+			d.close()
+			return nil, fmt.Errorf("fabgpu_host_key_slots failed [%d]", int(rc))
+		}
+		d.slots[i].keySlot = unsafe.Slice((*int32)(unsafe.Pointer(ks)), maxBatch)
 	}
 	return d, nil
 }
@@ -71,10 +78,20 @@ func (d *device) close() {
 	}
 }
 
-// verify runs H2D + kernel + D2H for the first n tuples of slot i.  One cgo call per batch, never per signature.
+// verify runs H2D + kernel(s) + D2H for the first n tuples of slot i (key slots included).  One cgo call per batch,
+// never per signature.
 func (d *device) verify(i, n int) error {
-	if rc := C.fabgpu_verify_p256(d.ctx, C.int(i), C.size_t(n)); rc != C.FABGPU_OK {
-		return fmt.Errorf("fabgpu_verify_p256 failed [%d]: %s", int(rc), C.GoString(C.fabgpu_last_error(d.ctx)))
+	if rc := C.fabgpu_verify_p256_keyed(d.ctx, C.int(i), C.size_t(n)); rc != C.FABGPU_OK {
+		return fmt.Errorf("fabgpu_verify_p256_keyed failed [%d]: %s", int(rc), C.GoString(C.fabgpu_last_error(d.ctx)))
 	}
 	return nil
+}
+
+// registerKey builds (or finds) the fixed-base table of one public key; -1 means "no table" and is always usable.
+func (d *device) registerKey(xy *[64]byte) int32 {
+	var s C.int32_t = -1
+	if rc := C.fabgpu_keys_register(d.ctx, (*C.uint8_t)(unsafe.Pointer(&xy[0])), 1, &s); rc != C.FABGPU_OK {
+		return -1
+	}
+	return int32(s)
 }

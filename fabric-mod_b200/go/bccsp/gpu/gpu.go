@@ -46,6 +46,7 @@ type ecdsaP256Key struct {
 	bccsp.Key                  // the sw key: SKI, Bytes, ... are unchanged
 	pub       *ecdsa.PublicKey // parsed once at import
 	x, y      [32]byte
+	slot      int32 // fixed-base table slot on the device(s), -1 if none (fabgpu_keys_register)
 }
 
 type request struct {
@@ -109,6 +110,11 @@ func (csp *impl) KeyImport(raw interface{}, opts bccsp.KeyImportOpts) (bccsp.Key
 	gk := &ecdsaP256Key{Key: k, pub: pub}
 	pub.X.FillBytes(gk.x[:])
 	pub.Y.FillBytes(gk.y[:])
+	// identities are imported once and verified many times (msp/cache): precompute the key's window table now
+	var xy [64]byte
+	copy(xy[:32], gk.x[:])
+	copy(xy[32:], gk.y[:])
+	gk.slot = csp.dev.registerKey(&xy)
 	return gk, nil
 }
 
@@ -186,6 +192,7 @@ func (csp *impl) aggregate() {
 			copy(sl.e[o:o+32], rq.e[:])
 			copy(sl.r[o:o+32], rq.r[:])
 			copy(sl.s[o:o+32], rq.s[:])
+			sl.keySlot[i] = rq.key.slot // every entry is rewritten per batch: a stale slot would verify against the wrong key
 		}
 		err := csp.dev.verify(slotIdx, len(pending))
 		atomic.AddUint64(&csp.Batches, 1)
