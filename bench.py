@@ -187,7 +187,7 @@ def run_gpu(args):
     # The provider registers a key once, when the identity is imported (KeyImport); steady-state batches then run the
     # key-table kernel.  `value` is that steady state; `value_generic` is the kernel for never-seen keys.
     t0 = time.perf_counter()
-    slots = ctx.keys_register(w.keys_xy)
+    slots = ctx.keys_register(w.keys_xy) & 0xFFF          # device-resident API takes raw slot indices
     key_register_ms = (time.perf_counter() - t0) * 1e3
     assert (slots >= 0).all()
     kslots = [torch.from_numpy(np.ascontiguousarray(slots[w.key_idx][np.roll(np.arange(B), 997 * k)])).to(dev) for k in range(ROT)]

@@ -131,6 +131,7 @@ struct fabgpu_ctx {
     std::unordered_map<std::string, int> key_map;
     std::vector<std::string> slot_key;
     std::vector<unsigned long long> slot_tick;
+    std::vector<uint32_t> slot_gen;          // bumped whenever a slot is recycled: handles carry the generation they were issued under
     unsigned long long tick = 0;
     int key_min_uses = 256;
     double timing[4] = {0, 0, 0, 0};   // last fabgpu_bccsp_verify_batch: key lookup, host gates, device (H2D+kernel+D2H), scatter [us]
@@ -243,6 +244,18 @@ int launch_verify(fabgpu_ctx* ctx, const Device& dv, int mode, const int32_t* ke
     return FABGPU_OK;
 }
 
+// A key handle is (generation << 12) | slot.  A handle issued before its slot was recycled no longer matches the slot's
+// generation and silently degrades to "no table" (-1): the generic kernel then verifies against the Qx/Qy the caller
+// supplied, so a stale handle can cost speed but never correctness.
+inline int32_t make_handle(const fabgpu_ctx* ctx, int sl) { return (int32_t)(((ctx->slot_gen[sl] & 0x7ffffu) << 12) | (uint32_t)sl); }
+inline int32_t handle_to_slot(const fabgpu_ctx* ctx, int32_t h)
+{
+    if (h < 0) return -1;
+    const int sl = h & 0xfff;
+    if (sl >= ctx->key_slots || ((uint32_t)h >> 12) != (ctx->slot_gen[sl] & 0x7ffffu) || ctx->slot_key[sl].empty()) return -1;
+    return sl;
+}
+
 int slots_mode(const int32_t* ks, size_t n)
 {
     bool any_c = false, any_g = false;
@@ -263,6 +276,7 @@ int enqueue_slot(fabgpu_ctx* ctx, int slot, size_t n, bool keyed)
         DevSlot& ds = dv.slot[slot];
         HostSlot& hs = ctx->hslot[slot];
         CK(ctx, cudaSetDevice(dv.id));
+        if (keyed) for (size_t i = begin; i < end; i++) hs.h_key_slot[i] = handle_to_slot(ctx, hs.h_key_slot[i]);   // handles -> live slots
         const int mode = keyed ? slots_mode(hs.h_key_slot + begin, cnt) : MODE_GENERIC;
         for (int a = (mode == MODE_CACHED ? 2 : 0); a < 5; a++)            // an all-cached range needs no Qx/Qy on the device
             CK(ctx, cudaMemcpyAsync(ds.d_in[a], hs.h_in[a] + 32 * begin, 32 * cnt, cudaMemcpyHostToDevice, ds.stream));
@@ -349,6 +363,8 @@ int init_impl(fabgpu_ctx* ctx, const int* device_ids, int n_dev, size_t max_batc
         ctx->key_slots = ks ? std::max(1, atoi(ks)) : 256;
         ctx->slot_key.assign(ctx->key_slots, std::string());
         ctx->slot_tick.assign(ctx->key_slots, 0ull);
+        ctx->slot_gen.assign(ctx->key_slots, 0u);
+        if (ctx->key_slots > 4096) ctx->key_slots = 4096;     // a handle keeps 12 bits for the slot
         const char* mu = getenv("FABGPU_KEY_MIN_USES");
         ctx->key_min_uses = mu ? atoi(mu) : 256;           // a table costs about 300 generic verifications to build
     }
@@ -479,15 +495,15 @@ int fabgpu_keys_register(fabgpu_ctx* ctx, const uint8_t* keys_xy, int K, int32_t
     for (int k = 0; k < K; k++) {
         std::string key((const char*)keys_xy + 64 * (size_t)k, 64);
         auto it = ctx->key_map.find(key);
-        if (it != ctx->key_map.end()) { slots_out[k] = it->second; ctx->slot_tick[it->second] = ctx->tick; slot_taken[it->second] = 1; continue; }
+        if (it != ctx->key_map.end()) { slots_out[k] = make_handle(ctx, it->second); ctx->slot_tick[it->second] = ctx->tick; slot_taken[it->second] = 1; continue; }
         // least recently used slot that this call has not touched
         int best = -1;
         for (int sl = 0; sl < ctx->key_slots; sl++)
             if (!slot_taken[sl] && (best < 0 || ctx->slot_tick[sl] < ctx->slot_tick[best])) best = sl;
         if (best < 0) { slots_out[k] = -1; continue; }            // more distinct keys in one call than slots: stays generic
-        if (!ctx->slot_key[best].empty()) ctx->key_map.erase(ctx->slot_key[best]);
+        if (!ctx->slot_key[best].empty()) { ctx->key_map.erase(ctx->slot_key[best]); ctx->slot_gen[best]++; }   // old handles die here
         ctx->slot_key[best] = key; ctx->key_map[key] = best; ctx->slot_tick[best] = ctx->tick; slot_taken[best] = 1;
-        slots_out[k] = best;
+        slots_out[k] = make_handle(ctx, best);
         fresh.push_back(k); fresh_slot.push_back(best);
     }
     if (fresh.empty()) return FABGPU_OK;
@@ -518,7 +534,7 @@ int fabgpu_keys_register(fabgpu_ctx* ctx, const uint8_t* keys_xy, int K, int32_t
         if (flags[i]) continue;                   // not a curve point: no table; the generic kernel reports it as off-curve
         const int sl = fresh_slot[i];
         ctx->key_map.erase(ctx->slot_key[sl]);
-        ctx->slot_key[sl].clear(); ctx->slot_tick[sl] = 0;
+        ctx->slot_key[sl].clear(); ctx->slot_tick[sl] = 0; ctx->slot_gen[sl]++;
         slots_out[fresh[i]] = -1;
     }
     return FABGPU_OK;
@@ -784,7 +800,8 @@ static int upload_msp(fabgpu_ctx* ctx, const uint8_t* id_blob, const uint32_t* i
         hh[pos] = hv; hi[pos] = i;
     }
     dm.all_slots = true;
-    for (int i = 0; i < n_ids; i++) if (ctx->identity_slot[i] < 0) dm.all_slots = false;
+    std::vector<int32_t> raw_slot(n_ids > 0 ? n_ids : 1, -1);
+    for (int i = 0; i < n_ids; i++) { raw_slot[i] = handle_to_slot(ctx, ctx->identity_slot[i]); if (raw_slot[i] < 0) dm.all_slots = false; }
     auto up = [&](auto*& dst, const void* src, size_t bytes) -> int {
         CK(ctx, cudaMalloc(&dst, bytes + 8));                 // slack: word-wise readers may touch the aligned word past the end
         if (bytes) CK(ctx, cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice));
@@ -796,7 +813,7 @@ static int upload_msp(fabgpu_ctx* ctx, const uint8_t* id_blob, const uint32_t* i
     rc |= up(dm.id_off, id_off, 4 * (size_t)(n_ids + 1) * (n_ids ? 1 : 0));
     rc |= up(dm.valid, valid, (size_t)n_ids);
     rc |= up(dm.keys_xy, keys_xy, 64 * (size_t)n_ids);
-    rc |= up(dm.key_slot, ctx->identity_slot.data(), 4 * (size_t)n_ids);
+    rc |= up(dm.key_slot, raw_slot.data(), 4 * (size_t)n_ids);
     rc |= up(dm.msp_code, msp_code.data(), 4 * (size_t)n_ids);
     rc |= up(dm.ht_hash, hh.data(), 8 * (size_t)hsz);
     rc |= up(dm.ht_idx, hi.data(), 4 * (size_t)hsz);
@@ -877,6 +894,19 @@ static int validate_device(fabgpu_ctx* ctx, const uint8_t* block, size_t block_l
     DevSlot& ds = dv.slot[0];
     auto& bb = ctx->bb; auto& db = ctx->db; auto& dm = ctx->dm;
     CK(ctx, cudaSetDevice(dv.id));
+    {   // identities' key tables may have been recycled by other registrations since fabgpu_msp_configure: re-issue them
+        bool stale = false;
+        for (size_t i = 0; i < ctx->identity_slot.size() && !stale; i++) stale = ctx->identity_slot[i] >= 0 && handle_to_slot(ctx, ctx->identity_slot[i]) < 0;
+        if (stale) {
+            const int n_ids = (int)ctx->identity_slot.size();
+            int rc = fabgpu_keys_register(ctx, ctx->msp.keys_xy.data(), n_ids, ctx->identity_slot.data());
+            if (rc) return rc;
+            std::vector<int32_t> raw(n_ids, -1);
+            dm.all_slots = true;
+            for (int i = 0; i < n_ids; i++) { raw[i] = handle_to_slot(ctx, ctx->identity_slot[i]); if (raw[i] < 0) dm.all_slots = false; }
+            CK(ctx, cudaMemcpy(dm.key_slot, raw.data(), 4 * (size_t)n_ids, cudaMemcpyHostToDevice));
+        }
+    }
     if (block_len > bb.block_cap) { int rc = grow_dev(ctx, bb.d_block, block_len + (block_len >> 2)); if (rc) return rc; bb.block_cap = block_len + (block_len >> 2); }
     const char* evs = getenv("FABGPU_BLOCK_EVENTS");          // "1": time the device stages with CUDA events (diagnostics)
     const bool use_ev = evs && evs[0] == '1';
@@ -1063,7 +1093,7 @@ static int validate_impl(fabgpu_ctx* ctx, const uint8_t* block, size_t block_len
     // 3. host gates on every signature (DER, R > 0, S > 0, low-S, r < 2^256) + digest job descriptors
     std::vector<uint8_t> gate_ok(J, 0);
     bool all_slots = true;
-    for (size_t j = 0; j < J && all_slots; j++) all_slots = ctx->identity_slot[plan.jobs[j].identity] >= 0;
+    for (size_t j = 0; j < J && all_slots; j++) all_slots = handle_to_slot(ctx, ctx->identity_slot[plan.jobs[j].identity]) >= 0;
     static const uint8_t kZero32[32] = {0};
     ctx->pool->run([&](int tid) {
         const size_t lo = J * (size_t)tid / TH, hi = J * (size_t)(tid + 1) / TH;
@@ -1075,7 +1105,7 @@ static int validate_impl(fabgpu_ctx* ctx, const uint8_t* block, size_t block_len
             gate_ok[j] = ok;
             stage32(bb.h_r + 32 * j, ok ? g.r : kZero32);
             stage32(bb.h_s + 32 * j, ok ? g.s : kZero32);
-            stage_i32(bb.h_ks + j, ctx->identity_slot[sj.identity]);
+            stage_i32(bb.h_ks + j, handle_to_slot(ctx, ctx->identity_slot[sj.identity]));
             if (!all_slots) {
                 stage32(bb.h_qx + 32 * j, ctx->msp.keys_xy.data() + 64 * (size_t)sj.identity);
                 stage32(bb.h_qy + 32 * j, ctx->msp.keys_xy.data() + 64 * (size_t)sj.identity + 32);

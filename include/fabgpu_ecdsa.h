@@ -98,17 +98,22 @@ int fabgpu_verify_p256_device(fabgpu_ctx* ctx, int dev_index, const void* d_qx, 
  * bccsp/sw/keyimport.go:114-134, msp/mspimpl.go:420).  A registered key gets a window table on every device of the
  * context, after which u2*Q is fixed-base like u1*G.  Results are identical to the generic kernel; only speed differs. */
 
-/* Looks up / builds tables for K keys (X||Y, 64 bytes each).  slots_out[k] >= 0 is the key's slot; -1 means "no table"
- * (not a curve point, or more distinct keys than fabgpu_key_slot_capacity in one call) -- such signatures simply take
- * the generic kernel.  Least-recently-used slots are recycled.  Capacity: env FABGPU_KEY_SLOTS (default 256). */
+/* Looks up / builds tables for K keys (X||Y, 64 bytes each).  slots_out[k] >= 0 is the key's HANDLE
+ * ((generation << 12) | slot); -1 means "no table" (not a curve point, or more distinct keys than
+ * fabgpu_key_slot_capacity in one call) -- such signatures simply take the generic kernel.  Least-recently-used slots are
+ * recycled; a handle issued before its slot was recycled is detected by the pinned-slot entry points and treated as -1,
+ * so a stale handle costs speed, never correctness.  Capacity: env FABGPU_KEY_SLOTS (default 256, at most 4096). */
 int fabgpu_keys_register(fabgpu_ctx* ctx, const uint8_t* keys_xy, int K, int32_t* slots_out);
 int fabgpu_key_slot_capacity(const fabgpu_ctx* ctx);
-/* Pinned int32[max_batch] of one slot: key_slot[i] = table slot of signature i's key, or -1.  Only the _keyed entry
- * points read it; a stale value would verify against the wrong key, so callers overwrite all n entries per batch. */
+/* Pinned int32[max_batch] of one slot: key_slot[i] = handle of signature i's key (from fabgpu_keys_register), or -1.
+ * Only the _keyed entry points read it (they replace handles by live slot indices in place); callers overwrite all n
+ * entries per batch and still fill Qx/Qy, which the generic kernel uses whenever a handle is -1 or stale. */
 int fabgpu_host_key_slots(fabgpu_ctx* ctx, int slot, int32_t** key_slot);
 int fabgpu_verify_p256_keyed(fabgpu_ctx* ctx, int slot, size_t n);
 int fabgpu_verify_p256_keyed_async(fabgpu_ctx* ctx, int slot, size_t n);
-/* Device-resident form.  all_cached != 0 promises every d_key_slot[i] >= 0 (d_qx/d_qy may then be NULL). */
+/* Device-resident form: d_key_slot holds raw slot indices (handle & 0xfff) that the caller obtained from
+ * fabgpu_keys_register and knows to be live (no registration since).  all_cached != 0 promises every d_key_slot[i] >= 0
+ * (d_qx/d_qy may then be NULL). */
 int fabgpu_verify_p256_device_keyed(fabgpu_ctx* ctx, int dev_index, int all_cached, const void* d_key_slot, const void* d_qx,
                                     const void* d_qy, const void* d_e, const void* d_r, const void* d_s, size_t n,
                                     void* d_mask, void* d_offcurve, void* cuda_stream);

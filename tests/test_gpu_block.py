@@ -89,3 +89,30 @@ def test_config3_block_replay_10k_tx(ctx):
     got2 = ctx.validate_block(bytes(b))
     exp2 = ob.validate_block(bytes(b), blockutil.identities_of(net), net.channel, net.policy_n_of(3), net.principals)
     assert got2.tolist() == exp2.tolist() and int((got2 != ob.VALID).sum()) == 1
+
+
+def test_block_survives_key_table_eviction():
+    """Identity tables recycled by unrelated registrations between fabgpu_msp_configure and a block: still exact."""
+    import os
+    from tools import workload
+    os.environ["FABGPU_KEY_SLOTS"] = "8"
+    try:
+        c = pkg().binding.Context(max_batch=4096)
+    finally:
+        del os.environ["FABGPU_KEY_SLOTS"]
+    net = blockgen.Network()
+    faults = blockutil.fault_map(60)
+    blk, binfo = blockgen.build_block(net, 60, 3, faults, seed=23)
+    exp = ob.validate_block(blk, blockutil.identities_of(net), net.channel, net.policy_n_of(3), net.principals)
+    c.msp_configure(blockutil.identities_of(net), net.policy_n_of(3), net.principals, net.channel)
+    assert c.validate_envelopes(binfo["env_blob"], binfo["env_off"]).tolist() == exp.tolist()
+    other = workload.Workload(64, 8, seed=99)
+    assert (c.keys_register(other.keys_xy) >= 0).all()          # evicts every identity's table
+    assert c.validate_envelopes(binfo["env_blob"], binfo["env_off"]).tolist() == exp.tolist()
+    os.environ["FABGPU_BLOCK_HOST"] = "1"
+    try:
+        c.keys_register(other.keys_xy)
+        assert c.validate_block(blk).tolist() == exp.tolist()   # host-walk path with stale handles -> generic kernel
+    finally:
+        del os.environ["FABGPU_BLOCK_HOST"]
+    c.close()

@@ -299,7 +299,7 @@ def test_key_tables_device_resident(ctx):
     slots = ctx.keys_register(w.keys_xy)
     dev = torch.device("cuda:0")
     t = [torch.from_numpy(a).to(dev) for a in (w.qx(), w.qy(), w.digest, w.r, w.s)]
-    ks = torch.from_numpy(slots[w.key_idx]).to(dev)
+    ks = torch.from_numpy((slots & 0xFFF)[w.key_idx]).to(dev)      # raw slot indices for the device-resident API
     mask = torch.zeros(w.n // 32, dtype=torch.int32, device=dev)
     st = torch.cuda.current_stream(dev)
     ctx.verify_p256_device_keyed(True, ks.data_ptr(), 0, 0, t[2].data_ptr(), t[3].data_ptr(), t[4].data_ptr(), w.n, mask.data_ptr(), 0, st.cuda_stream)
@@ -319,7 +319,15 @@ def test_key_table_eviction_and_off_curve_keys():
     s1 = c.keys_register(w.keys_xy[:4])
     assert sorted(s1.tolist()) == [0, 1, 2, 3]
     s2 = c.keys_register(w.keys_xy[2:6])                  # keys 2,3 stay; 4,5 evict the two least recently used (0,1)
-    assert (s2[:2] == s1[2:4]).all() and sorted(s2[2:].tolist()) == sorted(s1[:2].tolist())
+    assert (s2[:2] == s1[2:4]).all() and sorted((s2[2:] & 0xFFF).tolist()) == sorted(s1[:2].tolist())
+    assert (s2[2:] >> 12 == 1).all()                      # recycled slots carry a new generation
+    # handles of the evicted keys 0 and 1 are stale now: the keyed entry point must fall back to the generic kernel for
+    # them (correct answers), never read the tables that now belong to keys 4 and 5
+    stale = np.concatenate([s1[:2], s2])                  # handles for keys 0..5, the first two stale
+    hb = _fill(c, 0, w, stale[w.key_idx])
+    c.verify_p256_keyed(0, w.n)
+    assert (hb["mask"][: w.n // 32] == exp).all()
+    assert (c.host_key_slots(0)[: w.n][w.key_idx < 2] == -1).all()
     all6 = c.keys_register(w.keys_xy)                     # six keys, four slots: two stay generic
     assert int((all6 < 0).sum()) == 2
     hb = _fill(c, 0, w, all6[w.key_idx])

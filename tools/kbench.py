@@ -25,7 +25,7 @@ def main():
     t = [torch.from_numpy(a).to(dev) for a in (w.qx(), w.qy(), w.digest, w.r, w.s)]
     mask = torch.zeros(nmax // 32, dtype=torch.int32, device=dev)
     st = torch.cuda.current_stream(dev)
-    slots = ctx.keys_register(w.keys_xy)
+    slots = ctx.keys_register(w.keys_xy) & 0xFFF          # device-resident API takes raw slot indices
     ks = torch.from_numpy(slots[w.key_idx]).to(dev)
     for mode, n in [(m, n) for n in batches for m in ("generic", "cached")]:
         def go():

@@ -12,7 +12,7 @@ w = workload.Workload(n, 64, seed=workload.DEFAULT_SEED + 2)
 ctx = pkg.binding.Context(max_batch=n)
 dev = torch.device("cuda:0")
 t = [torch.from_numpy(a).to(dev) for a in (w.qx(), w.qy(), w.digest, w.r, w.s)]
-slots = ctx.keys_register(w.keys_xy)
+slots = ctx.keys_register(w.keys_xy) & 0xFFF          # device-resident API takes raw slot indices
 ks = torch.from_numpy(slots[w.key_idx]).to(dev)
 mask = torch.zeros(n // 32, dtype=torch.int32, device=dev)
 st = torch.cuda.current_stream(dev)
