@@ -355,3 +355,29 @@ def test_bccsp_batch_with_forced_key_tables():
     exp = fast.verify_batch(w.keys_xy, w.key_idx, w.digest, w.dig_off(), w.sigs, w.sig_off, nthreads=8)
     assert (csp2.ctx.bccsp_verify_batch(w.keys_xy, w.key_idx, w.digest, w.dig_off(), w.sigs, w.sig_off) == exp).all()
     csp2.close()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# one context driving several GPUs (what the Go provider does: Devices: [0..7] in core.yaml)
+# ---------------------------------------------------------------------------------------------------------
+def test_multi_device_context_splits_batch():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs at least 2 GPUs")
+    ndev = min(torch.cuda.device_count(), 4)
+    c = pkg().binding.Context(max_batch=1 << 17, device_ids=list(range(ndev)))
+    assert c.device_count() == ndev
+    # BASELINE.json configs[4] shape at reduced size: 5 % tampered r, exact-match bitmask (generic kernel, then key tables)
+    w = workload.Workload(100000 + 77, 64, seed=workload.DEFAULT_SEED + 5)        # ragged: not a multiple of 32 * ndev
+    w.tamper_r(0.05)
+    exp = fast.valid_mask(fast.verify_batch(w.keys_xy, w.key_idx, w.digest, w.dig_off(), w.sigs, w.sig_off, nthreads=os.cpu_count()))
+    mask, off = c.verify_p256_host(w.qx(), w.qy(), w.digest, w.r, w.s)
+    assert (mask == exp).all() and not off.any()
+    handles = c.keys_register(w.keys_xy)                                          # tables on every device of the context
+    assert (handles >= 0).all()
+    hb = _fill(c, 1, w, handles[w.key_idx])
+    c.verify_p256_keyed(1, w.n)
+    assert (hb["mask"][: exp.shape[0]] == exp).all()
+    st = c.bccsp_verify_batch(w.keys_xy, w.key_idx, w.digest, w.dig_off(), w.sigs, w.sig_off)
+    assert (fast.valid_mask(st) == exp).all()
+    c.close()
