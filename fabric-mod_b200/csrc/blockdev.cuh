@@ -204,34 +204,44 @@ BD_HD bool der_int(const uint8_t* b, uint32_t n, uint32_t& off, uint32_t& vo, ui
     return true;
 }
 
-BD_HD bool gate_signature(const uint8_t* sig, uint32_t n, uint8_t* r32, uint8_t* s32)
+// Gate outcome as the status code of include/fabgpu_ecdsa.h: 0 = every gate passed (ask the curve arithmetic),
+// 1 = (false, nil) because r >= 2^256, 5 = unmarshal error, 6 / 7 = R / S not positive, 8 = high S.
+// Order of checks as in bccsp/sw/ecdsa.go:41-54: unmarshal, R > 0, S > 0, then low-S, then ecdsa.Verify's range checks.
+BD_HD int gate_signature_status(const uint8_t* sig, uint32_t n, uint8_t* r32, uint8_t* s32)
 {
     const uint8_t half[32] = {0x7F, 0xFF, 0xFF, 0xFF, 0x80, 0x00, 0x00, 0x00, 0x7F, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF,
                               0xDE, 0x73, 0x7D, 0x56, 0xD3, 0x8B, 0xCF, 0x42, 0x79, 0xDC, 0xE5, 0x61, 0x7E, 0x31, 0x92, 0xA8};
-    if (n == 0) return false;
+    if (n == 0) return 5;
     uint32_t off = 0, cls, tag, len; bool compound;
-    if (!der_tag_len(sig, n, off, cls, compound, tag, len)) return false;
-    if ((uint64_t)off + len > n) return false;
-    if (cls != 0 || tag != 16 || !compound) return false;
+    if (!der_tag_len(sig, n, off, cls, compound, tag, len)) return 5;
+    if ((uint64_t)off + len > n) return 5;
+    if (cls != 0 || tag != 16 || !compound) return 5;
     const uint8_t* inner = sig + off;
     uint32_t io = 0, ro, rl, so, sl;
-    if (!der_int(inner, len, io, ro, rl)) return false;
-    if (!der_int(inner, len, io, so, sl)) return false;
+    if (!der_int(inner, len, io, ro, rl)) return 5;
+    if (!der_int(inner, len, io, so, sl)) return 5;
     const uint8_t* rp = inner + ro; const uint8_t* sp = inner + so;
-    if (rp[0] & 0x80) return false;                               // R negative
-    if (sp[0] & 0x80) return false;                               // S negative
+    const bool r_neg = (rp[0] & 0x80) != 0, s_neg = (sp[0] & 0x80) != 0;
     while (rl > 0 && *rp == 0) { rp++; rl--; }
     while (sl > 0 && *sp == 0) { sp++; sl--; }
-    if (rl == 0 || sl == 0) return false;                         // R == 0 / S == 0
-    if (sl > 32 || rl > 32) return false;                         // s > N/2 for sure; r >= 2^256 can never be < N
-    for (int i = 0; i < 32; i++) { r32[i] = 0; s32[i] = 0; }
-    for (uint32_t i = 0; i < rl; i++) r32[32 - rl + i] = rp[i];
+    if (r_neg || rl == 0) return 6;                               // R must be larger than zero
+    if (s_neg || sl == 0) return 7;                               // S must be larger than zero
+    if (sl > 32) return 8;                                        // s >= 2^256 > N/2
+    for (int i = 0; i < 32; i++) s32[i] = 0;
     for (uint32_t i = 0; i < sl; i++) s32[32 - sl + i] = sp[i];
     for (int i = 0; i < 32; i++) {                                // s <= N >> 1
         if (s32[i] < half[i]) break;
-        if (s32[i] > half[i]) return false;
+        if (s32[i] > half[i]) return 8;
     }
-    return true;
+    if (rl > 32) return 1;                                        // r >= 2^256 can never be < N: (false, nil)
+    for (int i = 0; i < 32; i++) r32[i] = 0;
+    for (uint32_t i = 0; i < rl; i++) r32[32 - rl + i] = rp[i];
+    return 0;
+}
+
+BD_HD bool gate_signature(const uint8_t* sig, uint32_t n, uint8_t* r32, uint8_t* s32)
+{
+    return gate_signature_status(sig, n, r32, s32) == 0;
 }
 
 // ---- per-transaction plan --------------------------------------------------------------------------------------------------

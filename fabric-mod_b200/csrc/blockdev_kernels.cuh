@@ -31,4 +31,59 @@ block_decide_kernel(const uint8_t* __restrict__ block, const TxDev* __restrict__
     txid_seg[t] = txs[t].txid_ascii;
 }
 
+// ---- bccsp-level batch with the gates on the device ------------------------------------------
+// One thread per signature: sw.CSP.Verify's argument gates (bccsp/sw/impl.go:249-257), UnmarshalECDSASignature + IsLowS
+// (bccsp/utils/ecdsa.go:43-92) and hashToInt, straight from the raw DER / digest blobs.  pre[i] = 0 hands the signature to
+// the verify kernel; any other value is already the final FABGPU_ST_* status.
+__global__ void __launch_bounds__(128)
+bccsp_gate_kernel(const uint8_t* __restrict__ sigs, const uint32_t* __restrict__ sig_off, const uint8_t* __restrict__ digs,
+                  const uint32_t* __restrict__ dig_off, const int32_t* __restrict__ key_idx, const int32_t* __restrict__ slot_of,
+                  const uint8_t* __restrict__ keys_xy, int32_t K, uint32_t n, uint8_t* __restrict__ r, uint8_t* __restrict__ s,
+                  uint8_t* __restrict__ e, int32_t* __restrict__ key_slot, uint8_t* __restrict__ qx, uint8_t* __restrict__ qy,
+                  uint8_t* __restrict__ pre)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int32_t ki = key_idx[i];
+    const uint32_t so = sig_off[i], sl = sig_off[i + 1] - so, dof = dig_off[i], dl = dig_off[i + 1] - dof;
+    uint8_t rr[32], ss[32];
+    int st;
+    if (ki < 0) st = 2;                       // nil key
+    else if (sl == 0) st = 3;                 // empty signature
+    else if (dl == 0) st = 4;                 // empty digest
+    else if (ki >= K) st = 9;                 // not a key of the table
+    else st = gate_signature_status(sigs + so, sl, rr, ss);
+    uint32_t* r4 = reinterpret_cast<uint32_t*>(r + 32 * (size_t)i);
+    uint32_t* s4 = reinterpret_cast<uint32_t*>(s + 32 * (size_t)i);
+    if (st != 0) {
+        for (int k = 0; k < 8; k++) { r4[k] = 0; s4[k] = 0; }
+        key_slot[i] = -1;
+        pre[i] = (uint8_t)st;
+        return;
+    }
+    for (int k = 0; k < 32; k++) { r[32 * (size_t)i + k] = rr[k]; s[32 * (size_t)i + k] = ss[k]; }
+    // hashToInt for a 256-bit order: leftmost min(len, 32) bytes, left-padded
+    const uint32_t take = dl > 32 ? 32 : dl;
+    for (uint32_t k = 0; k < 32 - take; k++) e[32 * (size_t)i + k] = 0;
+    for (uint32_t k = 0; k < take; k++) e[32 * (size_t)i + 32 - take + k] = digs[dof + k];
+    const int32_t slot = slot_of[ki];
+    key_slot[i] = slot;
+    if (slot < 0 && qx) {
+        for (int k = 0; k < 32; k++) { qx[32 * (size_t)i + k] = keys_xy[64 * (size_t)ki + k]; qy[32 * (size_t)i + k] = keys_xy[64 * (size_t)ki + 32 + k]; }
+    }
+    pre[i] = 0;
+}
+
+__global__ void __launch_bounds__(256)
+bccsp_status_kernel(const uint8_t* __restrict__ pre, const uint32_t* __restrict__ mask, const uint32_t* __restrict__ off, uint32_t n,
+                    uint8_t* __restrict__ status)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint8_t p = pre[i];
+    if (p != 0) { status[i] = p; return; }
+    const bool ok = (mask[i >> 5] >> (i & 31)) & 1u, oc = (off[i >> 5] >> (i & 31)) & 1u;
+    status[i] = ok ? 0 : (oc ? 10 : 1);       // VALID / ERR_OFF_CURVE / INVALID
+}
+
 } }  // namespace fabgpu::bdev

@@ -162,6 +162,14 @@ struct fabgpu_ctx {
         uint64_t* ht_hash = nullptr; uint32_t ht_size = 0; int32_t n_ids = 0, n_nodes = 0, n_principals = 0; uint32_t channel_len = 0;
         bool all_slots = true;
     } dm;
+    struct GateBufs {                          // fabgpu_bccsp_verify_batch with device-side gates
+        size_t n_cap = 0, sig_cap = 0, dig_cap = 0, k_cap = 0;
+        uint8_t *h_sigs = nullptr, *h_digs = nullptr, *h_keys = nullptr, *h_status = nullptr; uint32_t *h_sig_off = nullptr, *h_dig_off = nullptr;
+        int32_t *h_kidx = nullptr, *h_slot_of = nullptr;
+        uint8_t *d_sigs = nullptr, *d_digs = nullptr, *d_keys = nullptr, *d_status = nullptr, *d_pre = nullptr, *d_r = nullptr, *d_s = nullptr, *d_e = nullptr,
+        *d_qx = nullptr, *d_qy = nullptr; uint32_t *d_sig_off = nullptr, *d_dig_off = nullptr, *d_mask = nullptr, *d_off = nullptr;
+        int32_t *d_kidx = nullptr, *d_slot_of = nullptr, *d_ks = nullptr;
+    } gb;
     struct DevBlock {
         size_t tx_cap = 0, j_cap = 0;
         uint32_t* d_env_off = nullptr; bdev::TxDev* d_txs = nullptr; bdev::ShaJobD* d_sha = nullptr; uint8_t *d_r = nullptr, *d_s = nullptr, *d_qx = nullptr,
@@ -211,6 +219,18 @@ inline void stage_i32(int32_t* dst, int32_t v)
     _mm_stream_si32((int*)dst, v);
 #else
     *dst = v;
+#endif
+}
+// bytes -> pinned staging with streaming stores (16-byte aligned body), see stage32
+inline void stage_copy(uint8_t* dst, const uint8_t* src, size_t n)
+{
+#if defined(__SSE2__)
+    size_t i = 0;
+    while (i < n && ((uintptr_t)(dst + i) & 15u)) { dst[i] = src[i]; i++; }
+    for (; i + 16 <= n; i += 16) _mm_stream_si128((__m128i*)(dst + i), _mm_loadu_si128((const __m128i*)(src + i)));
+    for (; i < n; i++) dst[i] = src[i];
+#else
+    memcpy(dst, src, n);
 #endif
 }
 inline void stage_fence()
@@ -317,6 +337,12 @@ void free_all(fabgpu_ctx* ctx)
         for (void* p : dev2) if (p) cudaFree(p);
         void* host2[] = {db.h_flags, db.h_hash, db.h_seg, db.h_counter, db.h_env_off};
         for (void* p : host2) if (p) cudaFreeHost(p);
+        auto& gb = ctx->gb;
+        void* dev3[] = {gb.d_sigs, gb.d_digs, gb.d_keys, gb.d_status, gb.d_pre, gb.d_r, gb.d_s, gb.d_e, gb.d_qx, gb.d_qy, gb.d_sig_off, gb.d_dig_off, gb.d_mask, gb.d_off,
+                        gb.d_kidx, gb.d_slot_of, gb.d_ks};
+        for (void* p : dev3) if (p) cudaFree(p);
+        void* host3[] = {gb.h_sigs, gb.h_digs, gb.h_keys, gb.h_status, gb.h_sig_off, gb.h_dig_off, gb.h_kidx, gb.h_slot_of};
+        for (void* p : host3) if (p) cudaFreeHost(p);
     }
     for (auto& dv : ctx->devs) {
         cudaSetDevice(dv.id);
@@ -607,6 +633,87 @@ int fabgpu_gate_signature(const uint8_t* sig, size_t sig_len, uint8_t r_out[32],
     return g.status;
 }
 
+
+// fabgpu_bccsp_verify_batch with the gates on the device: the host only stages the raw blobs into pinned memory
+// (parallel streaming copies) and reads one status byte per signature back.  Device 0 of the context.
+static int bccsp_batch_device(fabgpu_ctx* ctx, const uint8_t* keys_xy, int K, const int32_t* key_idx, const uint8_t* digests,
+                              const uint32_t* dig_off, const uint8_t* sigs, const uint32_t* sig_off, size_t n, uint8_t* status,
+                              const std::vector<int32_t>& slot_of)
+{
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto us = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+        return std::chrono::duration<double, std::micro>(b - a).count();
+    };
+    auto t0 = now();
+    Device& dv = ctx->devs[0];
+    DevSlot& ds = dv.slot[0];
+    auto& gb = ctx->gb;
+    CK(ctx, cudaSetDevice(dv.id));
+    const size_t sig_bytes = sig_off[n], dig_bytes = dig_off[n];
+    int rc = 0;
+    if (n > gb.n_cap) {
+        const size_t c = round_up32(n + (n >> 2) + 1024);
+        rc |= grow_host(ctx, gb.h_sig_off, 4 * (c + 1)); rc |= grow_host(ctx, gb.h_dig_off, 4 * (c + 1)); rc |= grow_host(ctx, gb.h_kidx, 4 * c);
+        rc |= grow_host(ctx, gb.h_status, c);
+        rc |= grow_dev(ctx, gb.d_sig_off, 4 * (c + 1)); rc |= grow_dev(ctx, gb.d_dig_off, 4 * (c + 1)); rc |= grow_dev(ctx, gb.d_kidx, 4 * c);
+        rc |= grow_dev(ctx, gb.d_status, c); rc |= grow_dev(ctx, gb.d_pre, c); rc |= grow_dev(ctx, gb.d_r, 32 * c); rc |= grow_dev(ctx, gb.d_s, 32 * c);
+        rc |= grow_dev(ctx, gb.d_e, 32 * c); rc |= grow_dev(ctx, gb.d_qx, 32 * c); rc |= grow_dev(ctx, gb.d_qy, 32 * c); rc |= grow_dev(ctx, gb.d_ks, 4 * c);
+        rc |= grow_dev(ctx, gb.d_mask, c / 8 + 8); rc |= grow_dev(ctx, gb.d_off, c / 8 + 8);
+        if (rc) return FABGPU_E_CUDA;
+        gb.n_cap = c;
+    }
+    if (sig_bytes > gb.sig_cap) { const size_t c = sig_bytes + (sig_bytes >> 2) + 4096; rc |= grow_host(ctx, gb.h_sigs, c); rc |= grow_dev(ctx, gb.d_sigs, c); if (rc) return FABGPU_E_CUDA; gb.sig_cap = c; }
+    if (dig_bytes > gb.dig_cap) { const size_t c = dig_bytes + (dig_bytes >> 2) + 4096; rc |= grow_host(ctx, gb.h_digs, c); rc |= grow_dev(ctx, gb.d_digs, c); if (rc) return FABGPU_E_CUDA; gb.dig_cap = c; }
+    if ((size_t)K > gb.k_cap) {
+        const size_t c = (size_t)K + 64;
+        rc |= grow_host(ctx, gb.h_keys, 64 * c); rc |= grow_host(ctx, gb.h_slot_of, 4 * c); rc |= grow_dev(ctx, gb.d_keys, 64 * c); rc |= grow_dev(ctx, gb.d_slot_of, 4 * c);
+        if (rc) return FABGPU_E_CUDA;
+        gb.k_cap = c;
+    }
+    // stage: every host thread copies its slice of each array
+    const int T = ctx->pool->size();
+    bool all_slots = K > 0;
+    for (int k = 0; k < K; k++) { gb.h_slot_of[k] = handle_to_slot(ctx, slot_of[k]); if (gb.h_slot_of[k] < 0) all_slots = false; }
+    if (K > 0) memcpy(gb.h_keys, keys_xy, 64 * (size_t)K);
+    ctx->pool->run([&](int tid) {
+        auto slice = [&](size_t total, size_t& lo, size_t& hi) { lo = total * (size_t)tid / T; hi = total * (size_t)(tid + 1) / T; };
+        size_t lo, hi;
+        slice(sig_bytes, lo, hi); stage_copy(gb.h_sigs + lo, sigs + lo, hi - lo);
+        slice(dig_bytes, lo, hi); stage_copy(gb.h_digs + lo, digests + lo, hi - lo);
+        slice(4 * (n + 1), lo, hi); stage_copy((uint8_t*)gb.h_sig_off + lo, (const uint8_t*)sig_off + lo, hi - lo);
+        slice(4 * (n + 1), lo, hi); stage_copy((uint8_t*)gb.h_dig_off + lo, (const uint8_t*)dig_off + lo, hi - lo);
+        slice(4 * n, lo, hi); stage_copy((uint8_t*)gb.h_kidx + lo, (const uint8_t*)key_idx + lo, hi - lo);
+        stage_fence();
+    });
+    auto t1 = now();
+    cudaStream_t st = ds.stream;
+    CK(ctx, cudaMemcpyAsync(gb.d_sigs, gb.h_sigs, sig_bytes, cudaMemcpyHostToDevice, st));
+    CK(ctx, cudaMemcpyAsync(gb.d_digs, gb.h_digs, dig_bytes, cudaMemcpyHostToDevice, st));
+    CK(ctx, cudaMemcpyAsync(gb.d_sig_off, gb.h_sig_off, 4 * (n + 1), cudaMemcpyHostToDevice, st));
+    CK(ctx, cudaMemcpyAsync(gb.d_dig_off, gb.h_dig_off, 4 * (n + 1), cudaMemcpyHostToDevice, st));
+    CK(ctx, cudaMemcpyAsync(gb.d_kidx, gb.h_kidx, 4 * n, cudaMemcpyHostToDevice, st));
+    if (K > 0) {
+        CK(ctx, cudaMemcpyAsync(gb.d_keys, gb.h_keys, 64 * (size_t)K, cudaMemcpyHostToDevice, st));
+        CK(ctx, cudaMemcpyAsync(gb.d_slot_of, gb.h_slot_of, 4 * (size_t)K, cudaMemcpyHostToDevice, st));
+    }
+    bdev::bccsp_gate_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(gb.d_sigs, gb.d_sig_off, gb.d_digs, gb.d_dig_off, gb.d_kidx, gb.d_slot_of, gb.d_keys, K,
+                                                                        (uint32_t)n, gb.d_r, gb.d_s, gb.d_e, gb.d_ks, all_slots ? nullptr : gb.d_qx,
+                                                                        all_slots ? nullptr : gb.d_qy, gb.d_pre);
+    ctx->launches++;
+    CK(ctx, cudaGetLastError());
+    rc = launch_verify(ctx, dv, all_slots ? MODE_CACHED : MODE_MIXED, gb.d_ks, gb.d_qx, gb.d_qy, gb.d_e, gb.d_r, gb.d_s, n, gb.d_mask, gb.d_off, st);
+    if (rc) return rc;
+    bdev::bccsp_status_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(gb.d_pre, gb.d_mask, gb.d_off, (uint32_t)n, gb.d_status);
+    ctx->launches++;
+    CK(ctx, cudaGetLastError());
+    CK(ctx, cudaMemcpyAsync(gb.h_status, gb.d_status, n, cudaMemcpyDeviceToHost, st));
+    CK(ctx, cudaStreamSynchronize(st));
+    auto t2 = now();
+    memcpy(status, gb.h_status, n);
+    ctx->timing[1] = us(t0, t1); ctx->timing[2] = us(t1, t2); ctx->timing[3] = us(t2, now());
+    return FABGPU_OK;
+}
+
 int fabgpu_bccsp_verify_batch(fabgpu_ctx* ctx, const uint8_t* keys_xy, int K, const int32_t* key_idx, const uint8_t* digests,
                               const uint32_t* dig_off, const uint8_t* sigs, const uint32_t* sig_off, size_t n, uint8_t* status)
 {
@@ -638,6 +745,14 @@ int fabgpu_bccsp_verify_batch(fabgpu_ctx* ctx, const uint8_t* keys_xy, int K, co
         }
     }
     ctx->timing[0] = us(t_start, now());
+    {
+        // Default: gates on the device (one context device; a multi-device context keeps the host-gated split below).
+        const char* dg = getenv("FABGPU_BCCSP_HOST_GATES");
+        if (!(dg && dg[0] == '1') && ctx->devs.size() == 1 && n > 0 && n < (1u << 27) && sig_off[n] < (1u << 31) && dig_off[n] < (1u << 31)) {
+            if (fault_injected()) { ctx->last_error = "fault injected (FABGPU_FAULT_INJECT=1)"; return FABGPU_E_INJECTED; }
+            return bccsp_batch_device(ctx, keys_xy, K, key_idx, digests, dig_off, sigs, sig_off, n, status, slot_of);
+        }
+    }
     // The call is cut into chunks that alternate between the two pinned slots: while the GPU works on one chunk the
     // host threads gate and pack the next, and the statuses of the chunk before are scattered.
     const int T = ctx->pool->size();

@@ -164,8 +164,10 @@ def device_logic_flags(env_blob, env_off, identities, channel, nodes, principals
 
 
 def device_gate(sig: bytes):
+    """-> (ok, r32, s32, status) from the device-side gate functions run on the host."""
     L = bd_lib()
     r = (ctypes.c_uint8 * 32)(); s = (ctypes.c_uint8 * 32)()
     buf = (ctypes.c_uint8 * max(1, len(sig))).from_buffer_copy(sig if sig else b"\x00")
     ok = L.bd_gate(buf, ctypes.c_uint32(len(sig)), r, s)
-    return bool(ok), bytes(r), bytes(s)
+    st = L.bd_gate_status(buf, ctypes.c_uint32(len(sig)), r, s)
+    return bool(ok), bytes(r), bytes(s), int(st)

@@ -106,5 +106,6 @@ void bd_decide(void* p, const uint8_t* sig_ok, const uint8_t* check_digests, uin
 }
 // the device DER gate alone
 int bd_gate(const uint8_t* sig, uint32_t n, uint8_t* r, uint8_t* s) { return gate_signature(sig, n, r, s) ? 1 : 0; }
+int bd_gate_status(const uint8_t* sig, uint32_t n, uint8_t* r, uint8_t* s) { return gate_signature_status(sig, n, r, s); }
 
 }  // extern "C"

@@ -132,8 +132,10 @@ def test_device_der_gate_matches_host_gate_fuzz():
                         m.insert(rnd.randrange(len(m) + 1), rnd.getrandbits(8))
             sig = bytes(m)
             st, r, s = b.gate_signature(sig)
-            ok, r2, s2 = blockutil.device_gate(sig)
+            ok, r2, s2, dst = blockutil.device_gate(sig)
             assert ok == (st == b.ST_VALID), sig.hex()
+            if sig:
+                assert dst == st, sig.hex()                     # same status code as the host gate, error kinds included
             if ok:
                 assert (r, s) == (r2, s2)
             n += 1
