@@ -313,7 +313,8 @@ def run_gpu(args):
                        "wall_ms_incl_flush": wall_ms},
             "e2e": {"value": n_total * e2e_steps / (e2e_ms * 1e-3), "unit": "verifies/s", "h2d_bytes_per_step": 160 * B, "d2h_bytes_per_step": 8 * (B // 32),
                     "api": "fabgpu_bccsp_verify_batch (raw DER signatures + digests + keys in host memory -> status bytes)", "steps": e2e_steps,
-                    "last_call_phases_us": {"key_lookup": e2e_phases[0], "host_gates": e2e_phases[1], "h2d_kernel_d2h": e2e_phases[2], "scatter": e2e_phases[3]}},
+                    "last_call_phases_us": {"key_lookup": e2e_phases[0], "host_staging_copy": e2e_phases[1], "h2d_gate_verify_status_d2h": e2e_phases[2], "status_copy": e2e_phases[3]},
+                    "gates": "on the device (bccsp_gate_kernel); FABGPU_BCCSP_HOST_GATES=1 selects the host-thread gates"},
             "gpu_launches": int(launches),
             "value_generic": value_generic,
             "generic": {"what": "ecdsa_verify_kernel: no per-key table (first sight of a key); 255 doublings + 52 additions per signature",

@@ -61,11 +61,18 @@ bccsp_gate_kernel(const uint8_t* __restrict__ sigs, const uint32_t* __restrict__
         pre[i] = (uint8_t)st;
         return;
     }
-    for (int k = 0; k < 32; k++) { r[32 * (size_t)i + k] = rr[k]; s[32 * (size_t)i + k] = ss[k]; }
     // hashToInt for a 256-bit order: leftmost min(len, 32) bytes, left-padded
+    uint8_t ee[32];
     const uint32_t take = dl > 32 ? 32 : dl;
-    for (uint32_t k = 0; k < 32 - take; k++) e[32 * (size_t)i + k] = 0;
-    for (uint32_t k = 0; k < take; k++) e[32 * (size_t)i + 32 - take + k] = digs[dof + k];
+    for (uint32_t k = 0; k < 32 - take; k++) ee[k] = 0;
+    for (uint32_t k = 0; k < take; k++) ee[32 - take + k] = digs[dof + k];
+    uint32_t* e4 = reinterpret_cast<uint32_t*>(e + 32 * (size_t)i);
+#pragma unroll
+    for (int k = 0; k < 8; k++) {                                 // 32-bit stores instead of 96 byte stores
+        r4[k] = (uint32_t)rr[4 * k] | ((uint32_t)rr[4 * k + 1] << 8) | ((uint32_t)rr[4 * k + 2] << 16) | ((uint32_t)rr[4 * k + 3] << 24);
+        s4[k] = (uint32_t)ss[4 * k] | ((uint32_t)ss[4 * k + 1] << 8) | ((uint32_t)ss[4 * k + 2] << 16) | ((uint32_t)ss[4 * k + 3] << 24);
+        e4[k] = (uint32_t)ee[4 * k] | ((uint32_t)ee[4 * k + 1] << 8) | ((uint32_t)ee[4 * k + 2] << 16) | ((uint32_t)ee[4 * k + 3] << 24);
+    }
     const int32_t slot = slot_of[ki];
     key_slot[i] = slot;
     if (slot < 0 && qx) {
