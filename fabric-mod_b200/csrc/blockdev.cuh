@@ -280,35 +280,22 @@ struct JobArrays {
     uint32_t T;
 };
 
-BD_HD void job_fill(const uint8_t* base, const MspDev& msp, JobArrays& ja, uint32_t j, int32_t identity, Seg m0, Seg m1, Seg sig)
-{
-    ShaJobD& sh = ja.sha[j];
-    sh.off[0] = m0.off; sh.len[0] = m0.len; sh.off[1] = m1.off; sh.len[1] = m1.len; sh.off[2] = 0; sh.len[2] = 0;
-    const bool ok = gate_signature(base + sig.off, sig.len, ja.r + 32 * (size_t)j, ja.s + 32 * (size_t)j);
-    if (!ok) for (int i = 0; i < 32; i++) { ja.r[32 * (size_t)j + i] = 0; ja.s[32 * (size_t)j + i] = 0; }
-    ja.gate_ok[j] = ok ? 1 : 0;
-    ja.identity[j] = identity;
-    const int32_t slot = msp.key_slot[identity];
-    ja.key_slot[j] = slot;
-    if (slot < 0 && ja.qx) {
-        for (int i = 0; i < 32; i++) { ja.qx[32 * (size_t)j + i] = msp.keys_xy[64 * (size_t)identity + i]; ja.qy[32 * (size_t)j + i] = msp.keys_xy[64 * (size_t)identity + 32 + i]; }
-    }
-}
+// What the walk leaves for one signature; identity lookup and DER gate are done per job by resolve_job (four times
+// more threads than transactions: the walk alone exposed too little parallelism -- ncu: 2 warps/SM, issue active 3 %).
+struct RawJob { Seg ident; Seg sig; uint32_t tx; int32_t k; };   // k = -1: creator signature, else endorsement index; tx = 0xffffffff: unused slot
 
 // alloc_end(n) must return the first index of n fresh endorsement-job slots (atomicAdd on the device, a counter on the host)
 template <typename Alloc>
-BD_HD void plan_tx(const uint8_t* base, Seg env, uint32_t t, const MspDev& msp, const uint8_t* channel, uint32_t channel_len,
-                   TxDev& tx, JobArrays& ja, Alloc alloc_end)
+BD_HD void walk_tx(const uint8_t* base, Seg env, uint32_t t, const uint8_t* channel, uint32_t channel_len, TxDev& tx, RawJob* raw,
+                   JobArrays& ja, Alloc alloc_end)
 {
     tx.early = TXC_NOT_VALIDATED; tx.htype = 0; tx.endorser_parse_ok = 0; tx.channel_ok = 0; tx.endorsements_parse_ok = 1; tx.overflow = 0;
     tx.n_ends = 0; tx.pad = 0; tx.creator_identity = -1; tx.creator_has_job = 0;
     tx.txid_ascii.off = tx.txid_ascii.len = 0; tx.phash_claimed.off = tx.phash_claimed.len = 0;
-    // creator slot t and the two check slots default to "nothing"
     {
         ShaJobD z; for (int k = 0; k < 3; k++) { z.off[k] = 0; z.len[k] = 0; }
         ja.sha[t] = z; ja.sha[ja.J_cap + 2 * t] = z; ja.sha[ja.J_cap + 2 * t + 1] = z;
-        for (int i = 0; i < 32; i++) { ja.r[32 * (size_t)t + i] = 0; ja.s[32 * (size_t)t + i] = 0; }
-        ja.gate_ok[t] = 0; ja.identity[t] = -1; ja.key_slot[t] = -1;
+        raw[t].tx = 0xffffffffu; raw[t].k = -1;
     }
     Sel e = make_sel(1, 2);                                           // Envelope{payload=1, signature=2}
     if (!parse_sel(base, env, e)) { tx.early = TXC_INVALID_OTHER_REASON; return; }
@@ -328,10 +315,9 @@ BD_HD void plan_tx(const uint8_t* base, Seg env, uint32_t t, const MspDev& msp, 
     const uint32_t ht = (uint32_t)ch.uv[0];
     if (!(ht == 1 || ht == 2 || ht == 3) || ch.uv[1] != 0 || nonce.len == 0 || creator.len == 0) { tx.early = TXC_BAD_COMMON_HEADER; return; }
     tx.htype = (uint8_t)ht;
-    tx.creator_identity = msp_find(msp, base + creator.off, creator.len);
-    if (signature.len > 0 && payload.len > 0 && tx.creator_identity >= 0) {
-        Seg none; none.off = none.len = 0;
-        job_fill(base, msp, ja, t, tx.creator_identity, payload, none, signature);
+    if (signature.len > 0 && payload.len > 0) {                       // creator job: slot t (identity resolved per job)
+        raw[t].ident = creator; raw[t].sig = signature; raw[t].tx = t; raw[t].k = -1;
+        ShaJobD& sj = ja.sha[t]; sj.off[0] = payload.off; sj.len[0] = payload.len;
         tx.creator_has_job = 1;
     }
     if (ht != 3) return;
@@ -339,8 +325,7 @@ BD_HD void plan_tx(const uint8_t* base, Seg env, uint32_t t, const MspDev& msp, 
     { ShaJobD& a = ja.sha[ja.J_cap + 2 * t]; a.off[0] = nonce.off; a.len[0] = nonce.len; a.off[1] = creator.off; a.len[1] = creator.len; }
     tx.channel_ok = (ch.s[0].len == channel_len && bytes_equal(base + ch.s[0].off, channel, channel_len)) ? 1 : 0;
     if (!has_data) return;
-    // Transaction{repeated actions=1}: exactly one
-    Seg action0; action0.off = action0.len = 0; uint32_t n_actions = 0;
+    Seg action0; action0.off = action0.len = 0; uint32_t n_actions = 0;   // Transaction{repeated actions=1}: exactly one
     {
         Reader r; r.base = base; r.pos = data.off; r.end = data.off + data.len; r.ok = true;
         uint32_t f, wt; uint64_t v; Seg b;
@@ -353,8 +338,7 @@ BD_HD void plan_tx(const uint8_t* base, Seg env, uint32_t t, const MspDev& msp, 
     if (!parse_sel(base, ta.s[0], ah) || ah.s[1].len == 0 || ah.s[0].len == 0) return;
     Sel cap = make_sel(1, 2);                                         // ChaincodeActionPayload{chaincode_proposal_payload=1, action=2}
     if (!parse_sel(base, ta.s[1], cap) || !cap.present[1]) return;
-    // ChaincodeEndorsedAction{proposal_response_payload=1, repeated endorsements=2}: first pass finds prp and counts
-    Seg prp; prp.off = prp.len = 0; uint32_t n_end = 0;
+    Seg prp; prp.off = prp.len = 0; uint32_t n_end = 0;               // ChaincodeEndorsedAction{prp=1, repeated endorsements=2}
     {
         Reader r; r.base = base; r.pos = cap.s[1].off; r.end = cap.s[1].off + cap.s[1].len; r.ok = true;
         uint32_t f, wt; uint64_t v; Seg b;
@@ -372,19 +356,18 @@ BD_HD void plan_tx(const uint8_t* base, Seg env, uint32_t t, const MspDev& msp, 
     tx.phash_claimed = pr.s[0];
     tx.endorser_parse_ok = 1;
     if (n_end > BD_MAX_ENDS) { tx.overflow = 1; return; }
-    // second pass over the endorsements: Endorsement{endorser=1, signature=2}
     Seg ends[BD_MAX_ENDS]; Seg sigs[BD_MAX_ENDS]; uint32_t n_jobs = 0, k = 0;
     {
         Reader r; r.base = base; r.pos = cap.s[1].off; r.end = cap.s[1].off + cap.s[1].len; r.ok = true;
         uint32_t f, wt; uint64_t v; Seg b;
         while (r.next(f, wt, v, b)) {
             if (f != 2) continue;
-            Sel en = make_sel(1, 2);
+            Sel en = make_sel(1, 2);                                  // Endorsement{endorser=1, signature=2}
             if (!parse_sel(base, b, en)) { tx.endorsements_parse_ok = 0; break; }
-            const int32_t idn = msp_find(msp, base + en.s[0].off, en.s[0].len);
-            tx.end_identity[k] = idn;
             ends[k] = en.s[0]; sigs[k] = en.s[1];
-            tx.end_job[k] = (idn >= 0 && en.s[1].len > 0) ? 0 : -1;
+            tx.end_identity[k] = -1;
+            // an endorsement without signature bytes can never verify: whatever its identity, it contributes nothing
+            tx.end_job[k] = (en.s[1].len > 0) ? 0 : -1;
             if (tx.end_job[k] == 0) n_jobs++;
             k++;
         }
@@ -395,10 +378,40 @@ BD_HD void plan_tx(const uint8_t* base, Seg env, uint32_t t, const MspDev& msp, 
         for (uint32_t i = 0; i < k; i++) {
             if (tx.end_job[i] < 0) continue;
             if (j >= ja.J_cap) { tx.overflow = 1; tx.end_job[i] = -1; continue; }
-            job_fill(base, msp, ja, j, tx.end_identity[i], prp, ends[i], sigs[i]);
+            raw[j].ident = ends[i]; raw[j].sig = sigs[i]; raw[j].tx = t; raw[j].k = (int32_t)i;
+            ShaJobD& sj = ja.sha[j];
+            sj.off[0] = prp.off; sj.len[0] = prp.len; sj.off[1] = ends[i].off; sj.len[1] = ends[i].len; sj.off[2] = 0; sj.len[2] = 0;
             tx.end_job[i] = (int32_t)j;
             j++;
         }
+    }
+}
+
+// One signature job: identity lookup in the MSP table, DER / low-S gate, operands for the verify kernel, and the identity
+// index written back into the transaction record (distinct fields per job: no two jobs write the same word).
+BD_HD void resolve_job(const uint8_t* base, uint32_t j, const RawJob* raw, const MspDev& msp, JobArrays& ja, TxDev* txs)
+{
+    const RawJob rj = raw[j];
+    int32_t identity = -1;
+    bool ok = false;
+    uint8_t rr[32], ss[32];
+    if (rj.tx != 0xffffffffu) {
+        identity = msp_find(msp, base + rj.ident.off, rj.ident.len);
+        if (rj.k < 0) txs[rj.tx].creator_identity = identity; else txs[rj.tx].end_identity[rj.k] = identity;
+        if (identity >= 0) ok = gate_signature(base + rj.sig.off, rj.sig.len, rr, ss);
+    }
+    uint32_t* r4 = reinterpret_cast<uint32_t*>(ja.r + 32 * (size_t)j);
+    uint32_t* s4 = reinterpret_cast<uint32_t*>(ja.s + 32 * (size_t)j);
+    for (int k = 0; k < 8; k++) {
+        r4[k] = ok ? ((uint32_t)rr[4 * k] | ((uint32_t)rr[4 * k + 1] << 8) | ((uint32_t)rr[4 * k + 2] << 16) | ((uint32_t)rr[4 * k + 3] << 24)) : 0u;
+        s4[k] = ok ? ((uint32_t)ss[4 * k] | ((uint32_t)ss[4 * k + 1] << 8) | ((uint32_t)ss[4 * k + 2] << 16) | ((uint32_t)ss[4 * k + 3] << 24)) : 0u;
+    }
+    ja.gate_ok[j] = ok ? 1 : 0;
+    ja.identity[j] = identity;
+    const int32_t slot = (identity >= 0 && ok) ? msp.key_slot[identity] : -1;
+    ja.key_slot[j] = slot;
+    if (identity >= 0 && ok && slot < 0 && ja.qx) {
+        for (int i = 0; i < 32; i++) { ja.qx[32 * (size_t)j + i] = msp.keys_xy[64 * (size_t)identity + i]; ja.qy[32 * (size_t)j + i] = msp.keys_xy[64 * (size_t)identity + 32 + i]; }
     }
 }
 

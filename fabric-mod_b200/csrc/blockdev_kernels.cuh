@@ -5,16 +5,25 @@
 
 namespace fabgpu { namespace bdev {
 
-// Walks every envelope, looks identities up, gates every DER signature and emits the SHA-256 / verify jobs.
+// Walks every envelope (one thread per transaction): structure checks, SHA-256 job descriptors, raw signature jobs.
 // Creator jobs sit at the transaction's own index; endorsement jobs are appended after them through one atomic counter.
 __global__ void __launch_bounds__(32)
-block_plan_kernel(const uint8_t* __restrict__ block, const uint32_t* __restrict__ env_off, uint32_t T, MspDev msp, const uint8_t* __restrict__ channel,
-                  uint32_t channel_len, TxDev* __restrict__ txs, JobArrays ja, uint32_t* __restrict__ n_end)
+block_walk_kernel(const uint8_t* __restrict__ block, const uint32_t* __restrict__ env_off, uint32_t T, const uint8_t* __restrict__ channel,
+                  uint32_t channel_len, TxDev* __restrict__ txs, RawJob* __restrict__ raw, JobArrays ja, uint32_t* __restrict__ n_end)
 {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= T) return;
     Seg env; env.off = env_off[2 * t]; env.len = env_off[2 * t + 1] - env_off[2 * t];      // (begin, end) pairs
-    plan_tx(block, env, t, msp, channel, channel_len, txs[t], ja, [&](uint32_t n) { return T + atomicAdd(n_end, n); });
+    walk_tx(block, env, t, channel, channel_len, txs[t], raw, ja, [&](uint32_t n) { return T + atomicAdd(n_end, n); });
+}
+
+// One thread per signature job: identity lookup, DER / low-S gate, verify operands.
+__global__ void __launch_bounds__(64)
+block_resolve_kernel(const uint8_t* __restrict__ block, const RawJob* __restrict__ raw, uint32_t J, MspDev msp, JobArrays ja, TxDev* __restrict__ txs)
+{
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= J) return;
+    resolve_job(block, j, raw, msp, ja, txs);
 }
 
 // Replays the reference's decision order for every transaction on the verification bitmask and the digests.

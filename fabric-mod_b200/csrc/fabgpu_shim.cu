@@ -172,7 +172,7 @@ struct fabgpu_ctx {
     } gb;
     struct DevBlock {
         size_t tx_cap = 0, j_cap = 0;
-        uint32_t* d_env_off = nullptr; bdev::TxDev* d_txs = nullptr; bdev::ShaJobD* d_sha = nullptr; uint8_t *d_r = nullptr, *d_s = nullptr, *d_qx = nullptr,
+        uint32_t* d_env_off = nullptr; bdev::TxDev* d_txs = nullptr; bdev::RawJob* d_raw = nullptr; bdev::ShaJobD* d_sha = nullptr; uint8_t *d_r = nullptr, *d_s = nullptr, *d_qx = nullptr,
         *d_qy = nullptr, *d_gate = nullptr, *d_dig = nullptr, *d_flags = nullptr; int32_t *d_ks = nullptr, *d_ident = nullptr; uint32_t *d_mask = nullptr,
         *d_off = nullptr, *d_counter = nullptr; uint64_t* d_hash = nullptr; bdev::Seg* d_seg = nullptr;
         uint8_t* h_flags = nullptr; uint64_t* h_hash = nullptr; bdev::Seg* h_seg = nullptr; uint32_t* h_counter = nullptr; uint32_t* h_env_off = nullptr;
@@ -332,7 +332,7 @@ void free_all(fabgpu_ctx* ctx)
         for (void* p : host_ptrs) if (p) cudaFreeHost(p);
         auto& dm = ctx->dm; auto& db = ctx->db;
         void* dev2[] = {dm.id_blob, dm.valid, dm.keys_xy, dm.channel, dm.id_off, dm.key_slot, dm.msp_code, dm.ht_idx, dm.nodes, dm.principal_code, dm.ht_hash,
-                        db.d_env_off, db.d_txs, db.d_sha, db.d_r, db.d_s, db.d_qx, db.d_qy, db.d_gate, db.d_dig, db.d_flags, db.d_ks, db.d_ident, db.d_mask, db.d_off,
+                        db.d_env_off, db.d_txs, db.d_raw, db.d_sha, db.d_r, db.d_s, db.d_qx, db.d_qy, db.d_gate, db.d_dig, db.d_flags, db.d_ks, db.d_ident, db.d_mask, db.d_off,
                         db.d_counter, db.d_hash, db.d_seg};
         for (void* p : dev2) if (p) cudaFree(p);
         void* host2[] = {db.h_flags, db.h_hash, db.h_seg, db.h_counter, db.h_env_off};
@@ -994,7 +994,7 @@ static int validate_impl(fabgpu_ctx* ctx, const uint8_t* block, size_t block_len
                          size_t flags_cap, size_t* n_tx_out);
 
 // Device path of the block pre-pass: the host only copies bytes in and flags out (and marks duplicate tx ids).
-//   H2D block + envelope offsets -> block_plan_kernel (walk, identity lookup, DER gates, job emission)
+//   H2D block + envelope offsets -> block_walk_kernel (per transaction) -> block_resolve_kernel (per signature: identity lookup, DER gates)
 //   -> sha256_segments_kernel (signed messages + check digests) -> one verify launch -> block_decide_kernel -> D2H flags.
 static int validate_device(fabgpu_ctx* ctx, const uint8_t* block, size_t block_len, const uint32_t* env_off, size_t n_env, uint8_t* flags,
                            size_t flags_cap, size_t* n_tx_out)
@@ -1048,6 +1048,7 @@ static int validate_device(fabgpu_ctx* ctx, const uint8_t* block, size_t block_l
         const size_t tc = T + (T >> 2) + 256, jc = tc * (1 + BD_MAX_ENDS);
         int rc = 0;
         rc |= grow_dev(ctx, db.d_env_off, 8 * (tc + 1)); rc |= grow_dev(ctx, db.d_txs, sizeof(bdev::TxDev) * tc);
+        rc |= grow_dev(ctx, db.d_raw, sizeof(bdev::RawJob) * jc);
         rc |= grow_dev(ctx, db.d_sha, sizeof(bdev::ShaJobD) * (jc + 2 * tc)); rc |= grow_dev(ctx, db.d_dig, 32 * (jc + 2 * tc));
         rc |= grow_dev(ctx, db.d_r, 32 * jc); rc |= grow_dev(ctx, db.d_s, 32 * jc); rc |= grow_dev(ctx, db.d_qx, 32 * jc); rc |= grow_dev(ctx, db.d_qy, 32 * jc);
         rc |= grow_dev(ctx, db.d_gate, jc); rc |= grow_dev(ctx, db.d_ks, 4 * jc); rc |= grow_dev(ctx, db.d_ident, 4 * jc);
@@ -1072,7 +1073,8 @@ static int validate_device(fabgpu_ctx* ctx, const uint8_t* block, size_t block_l
     bdev::JobArrays ja; ja.sha = db.d_sha; ja.r = db.d_r; ja.s = db.d_s; ja.key_slot = db.d_ks; ja.identity = db.d_ident; ja.qx = dm.all_slots ? nullptr : db.d_qx;
     ja.qy = dm.all_slots ? nullptr : db.d_qy; ja.gate_ok = db.d_gate; ja.J_cap = (uint32_t)J_cap; ja.T = (uint32_t)T;
     const unsigned tb = (unsigned)((T + 127) / 128);
-    bdev::block_plan_kernel<<<(unsigned)((T + 31) / 32), 32, 0, ds.stream>>>(bb.d_block, db.d_env_off, (uint32_t)T, m, dm.channel, dm.channel_len, db.d_txs, ja, db.d_counter);
+    bdev::block_walk_kernel<<<(unsigned)((T + 31) / 32), 32, 0, ds.stream>>>(bb.d_block, db.d_env_off, (uint32_t)T, dm.channel, dm.channel_len, db.d_txs, db.d_raw, ja,
+                                                                          db.d_counter);
     ctx->launches++;
     CK(ctx, cudaGetLastError());
     if (use_ev) CK(ctx, cudaEventRecord(ctx->bev[2], ds.stream));
@@ -1080,6 +1082,9 @@ static int validate_device(fabgpu_ctx* ctx, const uint8_t* block, size_t block_l
     CK(ctx, cudaStreamSynchronize(ds.stream));
     const size_t n_end = std::min((size_t)db.h_counter[0], J_cap - T);
     const size_t J = T + n_end;
+    bdev::block_resolve_kernel<<<(unsigned)((J + 63) / 64), 64, 0, ds.stream>>>(bb.d_block, db.d_raw, (uint32_t)J, m, ja, db.d_txs);
+    ctx->launches++;
+    CK(ctx, cudaGetLastError());
     auto t2 = now();
     // digests: signature messages [0, J) and the check pairs [J_cap, J_cap + 2T)
     sha256_segments_kernel<<<(unsigned)((J + 127) / 128), 128, 0, ds.stream>>>(bb.d_block, reinterpret_cast<const ShaJob*>(db.d_sha), (uint32_t)J, db.d_dig);

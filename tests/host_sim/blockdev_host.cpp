@@ -14,7 +14,7 @@ struct H {
     std::vector<uint8_t> id_blob; std::vector<uint32_t> id_off; std::vector<int32_t> key_slot, msp_code, ht_idx, nodes, principal_code;
     std::vector<uint8_t> valid; std::vector<uint64_t> ht_hash; std::string channel;
     std::vector<uint8_t> block; std::vector<uint32_t> env_off;
-    std::vector<TxDev> txs; std::vector<ShaJobD> sha; std::vector<uint8_t> r, s, gate_ok; std::vector<int32_t> jks, jid;
+    std::vector<TxDev> txs; std::vector<RawJob> raw; std::vector<ShaJobD> sha; std::vector<uint8_t> r, s, gate_ok; std::vector<int32_t> jks, jid;
     uint32_t T = 0, J_cap = 0, n_end = 0;
     MspDev msp() const {
         MspDev m; m.id_blob = id_blob.data(); m.id_off = id_off.data(); m.key_slot = key_slot.data(); m.valid = valid.data(); m.msp_code = msp_code.data();
@@ -55,15 +55,17 @@ int bd_plan(void* p, const uint8_t* blob, const uint32_t* env_off, int n_env)
     h->block.assign(blob, blob + env_off[n_env]); h->env_off.assign(env_off, env_off + n_env + 1);
     h->T = (uint32_t)n_env; h->J_cap = h->T * (1 + BD_MAX_ENDS); h->n_end = 0;
     h->txs.assign(h->T, TxDev()); h->sha.assign(h->J_cap + 2 * h->T, ShaJobD());
+    { RawJob dead; dead.ident.off = dead.ident.len = dead.sig.off = dead.sig.len = 0; dead.tx = 0xffffffffu; dead.k = -1; h->raw.assign(h->J_cap, dead); }
     h->r.assign(32 * (size_t)h->J_cap, 0); h->s.assign(32 * (size_t)h->J_cap, 0); h->gate_ok.assign(h->J_cap, 0); h->jks.assign(h->J_cap, -1); h->jid.assign(h->J_cap, -1);
     JobArrays ja; ja.sha = h->sha.data(); ja.r = h->r.data(); ja.s = h->s.data(); ja.key_slot = h->jks.data(); ja.identity = h->jid.data();
     ja.qx = nullptr; ja.qy = nullptr; ja.gate_ok = h->gate_ok.data(); ja.J_cap = h->J_cap; ja.T = h->T;
     const MspDev m = h->msp();
     for (uint32_t t = 0; t < h->T; t++) {
         Seg env; env.off = env_off[t]; env.len = env_off[t + 1] - env_off[t];
-        plan_tx(h->block.data(), env, t, m, (const uint8_t*)h->channel.data(), (uint32_t)h->channel.size(), h->txs[t], ja,
+        walk_tx(h->block.data(), env, t, (const uint8_t*)h->channel.data(), (uint32_t)h->channel.size(), h->txs[t], h->raw.data(), ja,
                 [&](uint32_t n) { uint32_t b = h->T + h->n_end; h->n_end += n; return b; });
     }
+    for (uint32_t j = 0; j < h->T + h->n_end; j++) resolve_job(h->block.data(), j, h->raw.data(), m, ja, h->txs.data());
     return (int)h->n_end;
 }
 // job j (0 <= j < T + n_end): identity (-1 unused), gate_ok, r, s, message segments (6 uint32)
