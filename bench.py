@@ -282,7 +282,8 @@ def run_gpu(args):
         block_replay = {"workload": "configs[2]: %d txs x (1 creator + 3 endorsement) signatures, 3-of-4 policy, block of %d bytes in pinned host memory" % (args.block_txs, len(blk)),
                         "api": "fabgpu_validate_envelopes", "ms_per_block": bms, "tx_per_s": args.block_txs / bms * 1e3,
                         "verifies_per_s": binfo["n_sigs"] / bms * 1e3, "all_flags_valid": True,
-                        "device_stage_us": {"h2d_block": ph[5], "block_plan_kernel": ph[6], "sha256_segments_kernel": ph[7], "verify_kernel": ph[8], "block_decide_kernel": ph[9]},
+                        "device_stage_us": {"chunked_h2d_overlapped_with_walk_creator_resolve_and_sha256": ph[5], "endorsement_resolve_and_sha256": ph[7], "verify_kernel": ph[8],
+                                            "block_decide_kernel": ph[9]},
                         "host_us": {"enqueue": ph[0], "wait_copy_and_plan": ph[1], "wait_digests_verify_decide": ph[2], "duplicate_txid_pass": ph[3]}}
     clocks = sampler.stop() if rank == 0 else None      # sampled across the three timed loops (key-table, generic, e2e)
 

@@ -8,22 +8,25 @@ namespace fabgpu { namespace bdev {
 // Walks every envelope (one thread per transaction): structure checks, SHA-256 job descriptors, raw signature jobs.
 // Creator jobs sit at the transaction's own index; endorsement jobs are appended after them through one atomic counter.
 __global__ void __launch_bounds__(32)
-block_walk_kernel(const uint8_t* __restrict__ block, const uint32_t* __restrict__ env_off, uint32_t T, const uint8_t* __restrict__ channel,
-                  uint32_t channel_len, TxDev* __restrict__ txs, RawJob* __restrict__ raw, JobArrays ja, uint32_t* __restrict__ n_end)
+block_walk_kernel(const uint8_t* __restrict__ block, const uint32_t* __restrict__ env_off, uint32_t t0, uint32_t count, uint32_t T,
+                  const uint8_t* __restrict__ channel, uint32_t channel_len, TxDev* __restrict__ txs, RawJob* __restrict__ raw, JobArrays ja,
+                  uint32_t* __restrict__ n_end)
 {
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= T) return;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;      // transactions [t0, t0 + count) of the T in the block
+    if (i >= count) return;
+    const uint32_t t = t0 + i;
     Seg env; env.off = env_off[2 * t]; env.len = env_off[2 * t + 1] - env_off[2 * t];      // (begin, end) pairs
     walk_tx(block, env, t, channel, channel_len, txs[t], raw, ja, [&](uint32_t n) { return T + atomicAdd(n_end, n); });
 }
 
 // One thread per signature job: identity lookup, DER / low-S gate, verify operands.
 __global__ void __launch_bounds__(64)
-block_resolve_kernel(const uint8_t* __restrict__ block, const RawJob* __restrict__ raw, uint32_t J, MspDev msp, JobArrays ja, TxDev* __restrict__ txs)
+block_resolve_kernel(const uint8_t* __restrict__ block, const RawJob* __restrict__ raw, uint32_t j0, uint32_t count, MspDev msp, JobArrays ja,
+                     TxDev* __restrict__ txs)
 {
-    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= J) return;
-    resolve_job(block, j, raw, msp, ja, txs);
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;      // jobs [j0, j0 + count)
+    if (i >= count) return;
+    resolve_job(block, j0 + i, raw, msp, ja, txs);
 }
 
 // Replays the reference's decision order for every transaction on the verification bitmask and the digests.

@@ -155,6 +155,8 @@ struct fabgpu_ctx {
     } bb;
     double block_timing[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // host phases [0..4] (see fabgpu_block_timing), device stages [5..9]
     cudaEvent_t bev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    std::vector<uint64_t> dup_keys; std::vector<uint32_t> dup_idx;   // scratch of the duplicate-tx-id pass
+    std::vector<cudaEvent_t> chunk_ev;
     // device-side copy of the MSP view / policy (block_plan_kernel, block_decide_kernel)
     struct DevMsp {
         uint8_t *id_blob = nullptr, *valid = nullptr, *keys_xy = nullptr, *channel = nullptr;
@@ -1027,8 +1029,6 @@ static int validate_device(fabgpu_ctx* ctx, const uint8_t* block, size_t block_l
     const bool use_ev = evs && evs[0] == '1';
     if (use_ev) for (auto& e : ctx->bev) if (!e) CK(ctx, cudaEventCreate(&e));
     if (use_ev) CK(ctx, cudaEventRecord(ctx->bev[0], ds.stream));
-    CK(ctx, cudaMemcpyAsync(bb.d_block, block, block_len, cudaMemcpyHostToDevice, ds.stream));
-    if (use_ev) CK(ctx, cudaEventRecord(ctx->bev[1], ds.stream));
     std::vector<uint32_t> split;
     if (!env_off) {                                           // serialized common.Block: find the envelopes (serial, length-prefixed)
         std::vector<blockval::Seg> envs;
@@ -1073,25 +1073,47 @@ static int validate_device(fabgpu_ctx* ctx, const uint8_t* block, size_t block_l
     bdev::JobArrays ja; ja.sha = db.d_sha; ja.r = db.d_r; ja.s = db.d_s; ja.key_slot = db.d_ks; ja.identity = db.d_ident; ja.qx = dm.all_slots ? nullptr : db.d_qx;
     ja.qy = dm.all_slots ? nullptr : db.d_qy; ja.gate_ok = db.d_gate; ja.J_cap = (uint32_t)J_cap; ja.T = (uint32_t)T;
     const unsigned tb = (unsigned)((T + 127) / 128);
-    bdev::block_walk_kernel<<<(unsigned)((T + 31) / 32), 32, 0, ds.stream>>>(bb.d_block, db.d_env_off, (uint32_t)T, dm.channel, dm.channel_len, db.d_txs, db.d_raw, ja,
-                                                                          db.d_counter);
-    ctx->launches++;
-    CK(ctx, cudaGetLastError());
+    // The block is copied in chunks on a second stream; as soon as a chunk has landed, the compute stream walks its
+    // transactions, resolves their creator signatures and hashes their payloads and check digests, so that all of this hides
+    // behind the remaining copies.  Endorsement jobs are numbered through one counter, known only after the last walk.
+    cudaStream_t cs = dv.slot[1].stream;                      // copy stream
+    const char* ce = getenv("FABGPU_BLOCK_CHUNKS");
+    size_t chunks = ce ? (size_t)std::max(1, atoi(ce)) : (T >= 2048 ? 4 : 1);
+    if (chunks > 16) chunks = 16;
+    while (ctx->chunk_ev.size() < chunks) { cudaEvent_t e; CK(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); ctx->chunk_ev.push_back(e); }
+    CK(ctx, cudaEventRecord(ctx->chunk_ev[0], ds.stream));    // the env table / counter reset above precede everything
+    CK(ctx, cudaStreamWaitEvent(cs, ctx->chunk_ev[0], 0));
+    for (size_t c = 0; c < chunks; c++) {
+        const size_t lo = T * c / chunks, hi = T * (c + 1) / chunks;
+        if (hi == lo) continue;
+        const size_t b_lo = (c == 0) ? 0 : db.h_env_off[2 * lo], b_hi = (c + 1 == chunks) ? block_len : db.h_env_off[2 * hi];
+        CK(ctx, cudaMemcpyAsync(bb.d_block + b_lo, block + b_lo, b_hi - b_lo, cudaMemcpyHostToDevice, cs));
+        CK(ctx, cudaEventRecord(ctx->chunk_ev[c], cs));
+        CK(ctx, cudaStreamWaitEvent(ds.stream, ctx->chunk_ev[c], 0));
+        const uint32_t cnt = (uint32_t)(hi - lo);
+        bdev::block_walk_kernel<<<(cnt + 31) / 32, 32, 0, ds.stream>>>(bb.d_block, db.d_env_off, (uint32_t)lo, cnt, (uint32_t)T, dm.channel, dm.channel_len,
+                                                                    db.d_txs, db.d_raw, ja, db.d_counter);
+        bdev::block_resolve_kernel<<<(cnt + 63) / 64, 64, 0, ds.stream>>>(bb.d_block, db.d_raw, (uint32_t)lo, cnt, m, ja, db.d_txs);      // creator jobs
+        sha256_segments_kernel<<<(cnt + 127) / 128, 128, 0, ds.stream>>>(bb.d_block, reinterpret_cast<const ShaJob*>(db.d_sha) + lo, cnt, db.d_dig + 32 * lo);
+        sha256_segments_kernel<<<(2 * cnt + 127) / 128, 128, 0, ds.stream>>>(bb.d_block, reinterpret_cast<const ShaJob*>(db.d_sha + J_cap) + 2 * lo, 2 * cnt,
+                                                                          db.d_dig + 32 * (J_cap + 2 * lo));
+        ctx->launches += 4;
+        CK(ctx, cudaGetLastError());
+    }
+    if (use_ev) CK(ctx, cudaEventRecord(ctx->bev[1], ds.stream));
     if (use_ev) CK(ctx, cudaEventRecord(ctx->bev[2], ds.stream));
     CK(ctx, cudaMemcpyAsync(db.h_counter, db.d_counter, 4, cudaMemcpyDeviceToHost, ds.stream));
     CK(ctx, cudaStreamSynchronize(ds.stream));
     const size_t n_end = std::min((size_t)db.h_counter[0], J_cap - T);
     const size_t J = T + n_end;
-    bdev::block_resolve_kernel<<<(unsigned)((J + 63) / 64), 64, 0, ds.stream>>>(bb.d_block, db.d_raw, (uint32_t)J, m, ja, db.d_txs);
-    ctx->launches++;
-    CK(ctx, cudaGetLastError());
     auto t2 = now();
-    // digests: signature messages [0, J) and the check pairs [J_cap, J_cap + 2T)
-    sha256_segments_kernel<<<(unsigned)((J + 127) / 128), 128, 0, ds.stream>>>(bb.d_block, reinterpret_cast<const ShaJob*>(db.d_sha), (uint32_t)J, db.d_dig);
-    sha256_segments_kernel<<<(unsigned)((2 * T + 127) / 128), 128, 0, ds.stream>>>(bb.d_block, reinterpret_cast<const ShaJob*>(db.d_sha + J_cap), (uint32_t)(2 * T),
-                                                                                 db.d_dig + 32 * J_cap);
-    ctx->launches += 2;
-    CK(ctx, cudaGetLastError());
+    if (n_end) {                                              // endorsement jobs [T, T + n_end)
+        bdev::block_resolve_kernel<<<(unsigned)((n_end + 63) / 64), 64, 0, ds.stream>>>(bb.d_block, db.d_raw, (uint32_t)T, (uint32_t)n_end, m, ja, db.d_txs);
+        sha256_segments_kernel<<<(unsigned)((n_end + 127) / 128), 128, 0, ds.stream>>>(bb.d_block, reinterpret_cast<const ShaJob*>(db.d_sha) + T, (uint32_t)n_end,
+                                                                                     db.d_dig + 32 * T);
+        ctx->launches += 2;
+        CK(ctx, cudaGetLastError());
+    }
     if (use_ev) CK(ctx, cudaEventRecord(ctx->bev[3], ds.stream));
     int rc = launch_verify(ctx, dv, dm.all_slots ? MODE_CACHED : MODE_MIXED, db.d_ks, db.d_qx, db.d_qy, db.d_dig, db.d_r, db.d_s, J, db.d_mask, db.d_off, ds.stream);
     if (rc) return rc;
@@ -1108,18 +1130,26 @@ static int validate_device(fabgpu_ctx* ctx, const uint8_t* block, size_t block_l
     auto t3 = now();
     // markTXIdDuplicates (v20/validator.go:283-297) on the host: among VALID transactions, a later one with an already seen tx id
     memcpy(flags, db.h_flags, T);
-    std::unordered_multimap<uint64_t, uint32_t> seen;
-    seen.reserve(T * 2);
-    for (size_t t = 0; t < T; t++) {
-        if (flags[t] != blockval::TX_VALID) continue;
-        const bdev::Seg id = db.h_seg[t];
-        bool dup = false;
-        auto range = seen.equal_range(db.h_hash[t]);
-        for (auto it = range.first; it != range.second && !dup; ++it) {
-            const bdev::Seg o = db.h_seg[it->second];
-            dup = o.len == id.len && memcmp(block + o.off, block + id.off, id.len) == 0;
+    {
+        // flat open-addressing table keyed by the 64-bit tx-id hash (0 = empty); equal hashes are confirmed on the bytes
+        size_t cap = 16; while (cap < 4 * T) cap <<= 1;
+        ctx->dup_keys.assign(cap, 0); ctx->dup_idx.resize(cap);
+        uint64_t* keys = ctx->dup_keys.data(); uint32_t* idx = ctx->dup_idx.data();
+        for (size_t t = 0; t < T; t++) {
+            if (flags[t] != blockval::TX_VALID) continue;
+            const bdev::Seg id = db.h_seg[t];
+            const uint64_t h = db.h_hash[t] ? db.h_hash[t] : 1;
+            bool dup = false;
+            size_t pos = (size_t)h & (cap - 1);
+            for (;; pos = (pos + 1) & (cap - 1)) {
+                if (keys[pos] == 0) break;
+                if (keys[pos] != h) continue;
+                const bdev::Seg o = db.h_seg[idx[pos]];
+                if (o.len == id.len && memcmp(block + o.off, block + id.off, id.len) == 0) { dup = true; break; }
+            }
+            if (dup) flags[t] = blockval::TX_DUPLICATE_TXID;
+            else { keys[pos] = h; idx[pos] = (uint32_t)t; }
         }
-        if (dup) flags[t] = blockval::TX_DUPLICATE_TXID; else seen.emplace(db.h_hash[t], (uint32_t)t);
     }
     auto t4 = now();
     ctx->block_timing[0] = us(t0, t1); ctx->block_timing[1] = us(t1, t2); ctx->block_timing[2] = us(t2, t3); ctx->block_timing[3] = us(t3, t4);

@@ -165,7 +165,8 @@ int fabgpu_validate_envelopes(fabgpu_ctx* ctx, const uint8_t* blob, const uint32
 int fabgpu_block_buffer(fabgpu_ctx* ctx, size_t bytes, uint8_t** out);
 /* Times of the last fabgpu_validate_block / _envelopes, microseconds.  [0..4] host wall clock: enqueue, wait for copy + plan
  * kernel, wait for digests + verification + decisions, duplicate-tx-id pass, total.  [5..9] CUDA-event times of the device
- * stages: H2D of the block, block_plan_kernel, sha256_segments_kernel (x2), verify kernel(s), block_decide_kernel. */
+ * stages (FABGPU_BLOCK_EVENTS=1): chunked H2D overlapped with walk / creator resolve / SHA-256, (unused), endorsement
+ * resolve + SHA-256, verify kernel(s), block_decide_kernel. */
 int fabgpu_block_timing(const fabgpu_ctx* ctx, double out_us[10]);
 /* Device SHA-256 of messages given as up to three byte ranges of `buf` each: jobs = n x {off0,off1,off2,len0,len1,len2}
  * (uint32); digests = n x 32 bytes.  (The hash msp identity.Verify computes first: msp/identities.go:178.) */

@@ -26,6 +26,6 @@ for th, ev in ((16, "0"), (16, "1")):
         ctx.validate_envelopes(pinned, eo); acc += np.array(ctx.block_timing())
     t0 = t0 + (time.perf_counter() - t1)
     ms = (time.perf_counter() - t0) / 10 * 1e3
-    print("threads %3d: %.2f ms/block  host us: enqueue %.0f wait-plan %.0f wait-rest %.0f dup %.0f | device us: h2d %.0f plan %.0f sha %.0f verify %.0f decide %.0f"
+    print("threads %3d: %.2f ms/block  host us: enqueue %.0f wait-plan %.0f wait-rest %.0f dup %.0f | device us: copy+walk+hash(overlapped) %.0f - %.0f tail-resolve+sha %.0f verify %.0f decide %.0f"
           % (th, ms, *(acc[:4] / 10), *(acc[5:10] / 10)), flush=True)
     ctx.close()
