@@ -1073,12 +1073,14 @@ static int validate_device(fabgpu_ctx* ctx, const uint8_t* block, size_t block_l
     bdev::JobArrays ja; ja.sha = db.d_sha; ja.r = db.d_r; ja.s = db.d_s; ja.key_slot = db.d_ks; ja.identity = db.d_ident; ja.qx = dm.all_slots ? nullptr : db.d_qx;
     ja.qy = dm.all_slots ? nullptr : db.d_qy; ja.gate_ok = db.d_gate; ja.J_cap = (uint32_t)J_cap; ja.T = (uint32_t)T;
     const unsigned tb = (unsigned)((T + 127) / 128);
-    // The block is copied in chunks on a second stream; as soon as a chunk has landed, the compute stream walks its
-    // transactions, resolves their creator signatures and hashes their payloads and check digests, so that all of this hides
-    // behind the remaining copies.  Endorsement jobs are numbered through one counter, known only after the last walk.
+    // The block can be copied in chunks on a second stream (FABGPU_BLOCK_CHUNKS), each chunk's walk / creator resolve /
+    // SHA-256 starting as soon as its bytes have landed.  Measured on B200: NOT a win (1 chunk 1.93 ms, 4 chunks 2.27 ms,
+    // 8 chunks 3.52 ms per 10k-tx block) -- hashing a 4.6 KB payload is ~250 us of dependent rounds per thread however few
+    // threads a launch has, so per-chunk launches serialise that latency instead of hiding it.  Default: one chunk.
+    // Endorsement jobs are numbered through one counter, known only after the last walk.
     cudaStream_t cs = dv.slot[1].stream;                      // copy stream
     const char* ce = getenv("FABGPU_BLOCK_CHUNKS");
-    size_t chunks = ce ? (size_t)std::max(1, atoi(ce)) : (T >= 2048 ? 4 : 1);
+    size_t chunks = ce ? (size_t)std::max(1, atoi(ce)) : 1;
     if (chunks > 16) chunks = 16;
     while (ctx->chunk_ev.size() < chunks) { cudaEvent_t e; CK(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); ctx->chunk_ev.push_back(e); }
     CK(ctx, cudaEventRecord(ctx->chunk_ev[0], ds.stream));    // the env table / counter reset above precede everything
