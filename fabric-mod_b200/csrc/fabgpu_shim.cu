@@ -675,7 +675,10 @@ static int bccsp_batch_device(fabgpu_ctx* ctx, const uint8_t* keys_xy, int K, co
     // stage: every host thread copies its slice of each array
     const int T = ctx->pool->size();
     bool all_slots = K > 0;
-    for (int k = 0; k < K; k++) { gb.h_slot_of[k] = handle_to_slot(ctx, slot_of[k]); if (gb.h_slot_of[k] < 0) all_slots = false; }
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu);              // the slot table may be changing under a concurrent fabgpu_keys_register
+        for (int k = 0; k < K; k++) { gb.h_slot_of[k] = handle_to_slot(ctx, slot_of[k]); if (gb.h_slot_of[k] < 0) all_slots = false; }
+    }
     if (K > 0) memcpy(gb.h_keys, keys_xy, 64 * (size_t)K);
     ctx->pool->run([&](int tid) {
         auto slice = [&](size_t total, size_t& lo, size_t& hi) { lo = total * (size_t)tid / T; hi = total * (size_t)(tid + 1) / T; };
@@ -1013,7 +1016,10 @@ static int validate_device(fabgpu_ctx* ctx, const uint8_t* block, size_t block_l
     CK(ctx, cudaSetDevice(dv.id));
     {   // identities' key tables may have been recycled by other registrations since fabgpu_msp_configure: re-issue them
         bool stale = false;
-        for (size_t i = 0; i < ctx->identity_slot.size() && !stale; i++) stale = ctx->identity_slot[i] >= 0 && handle_to_slot(ctx, ctx->identity_slot[i]) < 0;
+        {
+            std::lock_guard<std::mutex> lk(ctx->mu);
+            for (size_t i = 0; i < ctx->identity_slot.size() && !stale; i++) stale = ctx->identity_slot[i] >= 0 && handle_to_slot(ctx, ctx->identity_slot[i]) < 0;
+        }
         if (stale) {
             const int n_ids = (int)ctx->identity_slot.size();
             int rc = fabgpu_keys_register(ctx, ctx->msp.keys_xy.data(), n_ids, ctx->identity_slot.data());
