@@ -2,13 +2,15 @@
 //
 // Restates, for the GPU, what the reference reaches at bccsp/sw/ecdsa.go:56 -- Go 1.14 crypto/ecdsa.Verify:
 //   r,s in [1,n-1]  ->  w = s^-1 mod n  ->  u1 = e*w, u2 = r*w  ->  R = u1*G + u2*Q  ->  R != inf and R.x mod n == r.
-// The DER parse, positivity and low-S gates (bccsp/utils/ecdsa.go:43-92, bccsp/sw/ecdsa.go:42-54) run on the host
-// before the batch is packed (see bccsp_host.cpp); the kernel still enforces the range checks itself.
+// The DER parse, positivity and low-S gates (bccsp/utils/ecdsa.go:43-92, bccsp/sw/ecdsa.go:42-54) run before these
+// functions -- in bccsp_gate_kernel / block_resolve_kernel (blockdev.cuh) or on host threads (bccsp_host.cpp); the
+// functions below still enforce the range checks r, s in [1, n-1] themselves.
 //
 // Scalar multiplication layout (B200-first, not Go's CombinedMult):
-//   u1*G : fixed-base, FAB_WG-bit unsigned windows over a precomputed affine table that lives in L2
-//          (256/FAB_WG mixed additions, no doublings);
-//   u2*Q : signed 5-bit Booth windows (52 of them), 16-entry Jacobian table of 1Q..16Q per signature.
+//   u1*G : fixed-base, FAB_WG-bit unsigned windows over a precomputed affine table in HBM/L2
+//          (ceil(256/FAB_WG) mixed additions, no doublings);
+//   u2*Q : keys with a table (ecdsa_verify_one_cached): FAB_WQ-bit unsigned windows over the key's own table;
+//          keys without (ecdsa_verify_one): signed 5-bit Booth windows, 16-entry Jacobian table of 1Q..16Q per signature.
 // The final comparison avoids the field inversion: R.x == r' * R.Z^2 for r' in {r, r+n (if < p)}.
 #pragma once
 #include "p256_point.cuh"
