@@ -36,9 +36,17 @@ if ROOT not in sys.path:
 METRIC = "ECDSA-P256 verifies/sec"
 ALG_BYTES_PER_VERIFY = 160.125          # 5 x 32 B in, 1 bit out
 ALG_MACS_PER_VERIFY = 217600            # 3 400 modular multiplications x 64 MACs (generic kernel)
-ALG_MACS_PER_VERIFY_CACHED = 421 * 64   # key-table kernel: (16 + 22) mixed additions x 11 + 3 field multiplications, x 64 MACs
+
+
+def alg_macs_cached(wg, wq):
+    """key-table kernel: one mixed addition (8M + 3S = 11 field multiplications) per window of both tables + 3 for the final
+    check, 64 32x32 MACs per field multiplication (the scalar inversion and the reductions are not counted)."""
+    windows = (256 + wg - 1) // wg + (256 + wq - 1) // wq
+    return (11 * windows + 3) * 64
+
+
 KEYS = 64
-NCU_DRAM_BYTES_PER_LAUNCH_64K = 221519872 + 7569664   # ecdsa_verify_cached_kernel, profiles/r1_final_cached_ncu_summary.txt
+NCU_DRAM_BYTES_PER_LAUNCH_64K = None   # ecdsa_verify_cached_kernel, profiles/r1_final_cached_ncu_summary.txt (dram read + write)
 
 
 def _peaks():
@@ -245,19 +253,39 @@ def run_gpu(args):
     assert bool((full == -1).all())
 
     # ---- end-to-end leg: raw DER + digests + keys in host memory through the bccsp-level C-ABI call ----------
-    e2e_steps = max(3, min(args.steps, 10))
+    # Headline form: the two halves of the call (fabgpu_bccsp_verify_batch_async / _wait) on alternating slots, two batches
+    # in flight -- every step still stages its host buffers, copies them H2D, runs gate + verify + status kernels and reads the
+    # status bytes back D2H inside the timed region; the copies of step k+1 overlap the kernels of step k.  The one-call
+    # synchronous form is timed beside it.
+    e2e_steps = max(4, min(args.steps, 20))
     dig_off = w.dig_off()
+    e2e_args = (w.keys_xy, w.key_idx, w.digest, dig_off, w.sigs, w.sig_off)
     for _ in range(2):
-        st = ctx.bccsp_verify_batch(w.keys_xy, w.key_idx, w.digest, dig_off, w.sigs, w.sig_off)
+        st = ctx.bccsp_verify_batch(*e2e_args)
     assert (st == 0).all()
     sync_all()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        st = ctx.bccsp_verify_batch(w.keys_xy, w.key_idx, w.digest, dig_off, w.sigs, w.sig_off)
+        st = ctx.bccsp_verify_batch(*e2e_args)
     torch.cuda.synchronize(dev)
-    e2e_s = time.perf_counter() - t0
+    e2e_sync_s = time.perf_counter() - t0
     assert (st == 0).all()
     e2e_phases = ctx.last_timing()
+    st_out = [np.full(B, 255, np.uint8) for _ in range(2)]
+    for k in range(2):                                                   # warm both slots (first use allocates their buffers)
+        ctx.bccsp_verify_batch_wait(k, ctx.bccsp_verify_batch_async(k, *e2e_args), st_out[k])
+    sync_all()
+    t0 = time.perf_counter()
+    for k in range(e2e_steps):
+        ctx.bccsp_verify_batch_async(k & 1, *e2e_args)
+        if k > 0:
+            ctx.bccsp_verify_batch_wait((k - 1) & 1, B, st_out[(k - 1) & 1])
+    ctx.bccsp_verify_batch_wait((e2e_steps - 1) & 1, B, st_out[(e2e_steps - 1) & 1])
+    torch.cuda.synchronize(dev)
+    e2e_s = time.perf_counter() - t0
+    assert (st_out[0] == 0).all() and (st_out[1] == 0).all()
+    e2e_h2d = int(w.sig_off[B]) + int(dig_off[B]) + 4 * (B + 1) * 2 + 4 * B + 68 * KEYS
+    e2e_d2h = B
 
     # ---- BASELINE.json configs[2]: block-validation replay, 10 k txs x 3 endorsements, 3-of-4 policy (rank 0 only) ----
     block_replay = None
@@ -288,10 +316,10 @@ def run_gpu(args):
     clocks = sampler.stop() if rank == 0 else None      # sampled across the three timed loops (key-table, generic, e2e)
 
     # ---- max over ranks ---------------------------------------------------------------------------------------
-    times = torch.tensor([dev_ms, e2e_s * 1e3, wall * 1e3, gen_ms, key_register_ms], dtype=torch.float64, device=dev)
+    times = torch.tensor([dev_ms, e2e_s * 1e3, wall * 1e3, gen_ms, key_register_ms, e2e_sync_s * 1e3], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms, wall_ms, gen_ms, key_register_ms = [float(x) for x in times.tolist()]
+    dev_ms, e2e_ms, wall_ms, gen_ms, key_register_ms, e2e_sync_ms = [float(x) for x in times.tolist()]
 
     if rank == 0:
         hbm_peak, peak_src, sm_max = _peaks()
@@ -299,7 +327,10 @@ def run_gpu(args):
         per_launch_s = dev_ms * 1e-3 / args.steps
         ach_gbs = B * ALG_BYTES_PER_VERIFY / per_launch_s / 1e9
         mac_peak = 148 * 4 * 16 * sm_max * 1e6                  # 148 SMs x 4 SMSP x 16 lanes/clk (IMAD, rt 2)
-        ach_macs = B * ALG_MACS_PER_VERIFY_CACHED / per_launch_s
+        wg, wq = pkg.binding.build_info()
+        macs_cached = alg_macs_cached(wg, wq)
+        n_gather = (256 + wg - 1) // wg + (256 + wq - 1) // wq
+        ach_macs = B * macs_cached / per_launch_s
         gen_launch_s = gen_ms * 1e-3 / gsteps
         value_generic = n_total / gen_launch_s
         cores = best_thread_count(w)
@@ -312,8 +343,10 @@ def run_gpu(args):
                        "batch_per_gpu": B, "global_batch": n_total, "parallelism": "batch split x%d + NCCL all-gather of the bitmask" % world,
                        "timing": "per-step CUDA events on the launch stream, summed; L2 flushed (256 MiB fill) between steps; %d rotating input buffers" % ROT,
                        "wall_ms_incl_flush": wall_ms},
-            "e2e": {"value": n_total * e2e_steps / (e2e_ms * 1e-3), "unit": "verifies/s", "h2d_bytes_per_step": 160 * B, "d2h_bytes_per_step": 8 * (B // 32),
-                    "api": "fabgpu_bccsp_verify_batch (raw DER signatures + digests + keys in host memory -> status bytes)", "steps": e2e_steps,
+            "e2e": {"value": n_total * e2e_steps / (e2e_ms * 1e-3), "unit": "verifies/s", "h2d_bytes_per_step": e2e_h2d * world, "d2h_bytes_per_step": e2e_d2h * world,
+                    "api": "fabgpu_bccsp_verify_batch_async + _wait on alternating slots, 2 batches in flight (raw DER signatures + digests + keys in pageable host memory -> status bytes)",
+                    "steps": e2e_steps,
+                    "sync_value": n_total * e2e_steps / (e2e_sync_ms * 1e-3), "sync_api": "fabgpu_bccsp_verify_batch, one blocking call per step",
                     "last_call_phases_us": {"key_lookup": e2e_phases[0], "host_staging_copy": e2e_phases[1], "h2d_gate_verify_status_d2h": e2e_phases[2], "status_copy": e2e_phases[3]},
                     "gates": "on the device (bccsp_gate_kernel); FABGPU_BCCSP_HOST_GATES=1 selects the host-thread gates"},
             "gpu_launches": int(launches),
@@ -321,17 +354,18 @@ def run_gpu(args):
             "generic": {"what": "ecdsa_verify_kernel: no per-key table (first sight of a key); 255 doublings + 52 additions per signature",
                         "ms_per_step": gen_ms / gsteps, "steps": gsteps},
             "key_tables": {"keys": KEYS, "register_ms_once": key_register_ms,
-                           "what": "fabgpu_keys_register builds a 5.5 MiB window table per public key (what KeyImport does once per identity)"},
+                           "what": "fabgpu_keys_register builds a %d-bit window table (%.1f MiB) per public key -- what KeyImport does once per identity" % (wq, ((256 + wq - 1) // wq) * ((1 << wq) - 1) * 64 / 2**20)},
             "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
                          "traffic": (NCU_DRAM_BYTES_PER_LAUNCH_64K if B == 65536 else None),
                          "traffic_note": "dram read+write of one launch at batch 65536 from profiles/r1_final_cached_ncu_summary.txt; it exceeds the "
-                                         "algorithmic 10.5 MB because the kernel gathers 38 table points (64 B each) per signature from 430 MB of "
-                                         "window tables by design -- that is what replaces 255 doublings",
+                                         "algorithmic 10.5 MB because the kernel gathers %d table points (64 B each) per signature from HBM-resident "
+                                         "window tables (%.1f GB for G, %.0f MiB per key) by design -- that is what replaces 255 doublings" % (
+                                             n_gather, ((256 + wg - 1) // wg) * ((1 << wg) - 1) * 64 / 1e9, ((256 + wq - 1) // wq) * ((1 << wq) - 1) * 64 / 2**20),
                          "peak_source": peak_src, "kernel": "ecdsa_verify_cached_kernel",
                          "note": "integer-issue bound, not HBM bound: see roofline_int"},
             "roofline_int": {"bound": "int32 mac (fma pipe)", "kernel": "ecdsa_verify_cached_kernel", "achieved": ach_macs / 1e12,
                              "peak": mac_peak / 1e12, "unit": "TMAC/s", "frac": ach_macs / mac_peak,
-                             "macs_per_verify": ALG_MACS_PER_VERIFY_CACHED,
+                             "macs_per_verify": macs_cached,
                              "peak_source": "model: 148 SM x 64 IMAD/clk x %d MHz" % int(sm_max),
                              "generic_kernel": {"achieved": B * ALG_MACS_PER_VERIFY / gen_launch_s / 1e12,
                                                 "frac": B * ALG_MACS_PER_VERIFY / gen_launch_s / mac_peak, "macs_per_verify": ALG_MACS_PER_VERIFY}},

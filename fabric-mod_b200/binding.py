@@ -6,7 +6,8 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libfabgpu_ecdsa.so")
+# FABGPU_LIB: development knob, points the binding at another build of the same library (kernel A/B runs)
+LIB_PATH = os.environ.get("FABGPU_LIB") or os.path.join(_HERE, "lib", "libfabgpu_ecdsa.so")
 SLOTS = 2
 
 OK, E_NO_DEVICE, E_CUDA, E_ARG, E_INJECTED = 0, -1, -2, -3, -4
@@ -18,10 +19,11 @@ EXPORTS = [
     "fabgpu_init", "fabgpu_destroy", "fabgpu_last_error", "fabgpu_device_count", "fabgpu_max_batch",
     "fabgpu_host_buffers", "fabgpu_verify_p256", "fabgpu_verify_p256_async", "fabgpu_wait", "fabgpu_verify_p256_host",
     "fabgpu_verify_p256_device", "fabgpu_bccsp_verify_batch", "fabgpu_bccsp_verify", "fabgpu_gate_signature",
-    "fabgpu_test_fieldop", "fabgpu_test_gtable", "fabgpu_launch_count",
+    "fabgpu_test_fieldop", "fabgpu_test_table_entries", "fabgpu_launch_count",
     "fabgpu_keys_register", "fabgpu_key_slot_capacity", "fabgpu_host_key_slots", "fabgpu_verify_p256_keyed",
     "fabgpu_verify_p256_keyed_async", "fabgpu_verify_p256_device_keyed", "fabgpu_last_timing", "fabgpu_build_info",
     "fabgpu_msp_configure", "fabgpu_validate_block", "fabgpu_validate_envelopes", "fabgpu_block_buffer", "fabgpu_block_timing", "fabgpu_sha256_segments",
+    "fabgpu_bccsp_verify_batch_async", "fabgpu_bccsp_verify_batch_wait",
 ]
 
 
@@ -55,7 +57,6 @@ def lib():
         L.fabgpu_max_batch.argtypes = [ctypes.c_void_p]
         L.fabgpu_launch_count.restype = ctypes.c_ulonglong
         L.fabgpu_launch_count.argtypes = [ctypes.c_void_p]
-        L.fabgpu_test_gtable.restype = ctypes.c_long
         L.fabgpu_destroy.argtypes = [ctypes.c_void_p]
         L.fabgpu_destroy.restype = None
         L.fabgpu_device_count.argtypes = [ctypes.c_void_p]
@@ -192,21 +193,39 @@ class Context:
                                                        ctypes.c_void_p(d_mask), ctypes.c_void_p(d_off), ctypes.c_void_p(stream)))
 
     # ---- bccsp level ------------------------------------------------------------------------------------
-    def bccsp_verify_batch(self, keys_xy, key_idx, digests, dig_off, sigs, sig_off):
+    @staticmethod
+    def _batch_args(keys_xy, key_idx, digests, dig_off, sigs, sig_off):
         keys_xy = np.ascontiguousarray(keys_xy, dtype=np.uint8).reshape(-1, 64)
         key_idx = np.ascontiguousarray(key_idx, dtype=np.int32)
         digests = np.ascontiguousarray(digests, dtype=np.uint8).reshape(-1)
         sigs = np.ascontiguousarray(sigs, dtype=np.uint8).reshape(-1)
         dig_off = np.ascontiguousarray(dig_off, dtype=np.uint32)
         sig_off = np.ascontiguousarray(sig_off, dtype=np.uint32)
-        n = key_idx.shape[0]
-        status = np.full(max(n, 1), 255, np.uint8)
         if digests.size == 0:
             digests = np.zeros(1, np.uint8)
         if sigs.size == 0:
             sigs = np.zeros(1, np.uint8)
+        return keys_xy, key_idx, digests, dig_off, sigs, sig_off
+
+    def bccsp_verify_batch(self, keys_xy, key_idx, digests, dig_off, sigs, sig_off):
+        keys_xy, key_idx, digests, dig_off, sigs, sig_off = self._batch_args(keys_xy, key_idx, digests, dig_off, sigs, sig_off)
+        n = key_idx.shape[0]
+        status = np.full(max(n, 1), 255, np.uint8)
         self._ck(lib().fabgpu_bccsp_verify_batch(self._h, _p(keys_xy), ctypes.c_int(keys_xy.shape[0]), _p(key_idx), _p(digests), _p(dig_off),
                                                  _p(sigs), _p(sig_off), ctypes.c_size_t(n), _p(status)))
+        return status[:n]
+
+    def bccsp_verify_batch_async(self, slot, keys_xy, key_idx, digests, dig_off, sigs, sig_off):
+        """First half of bccsp_verify_batch on one of the FABGPU_SLOTS slots; returns n for the matching _wait."""
+        keys_xy, key_idx, digests, dig_off, sigs, sig_off = self._batch_args(keys_xy, key_idx, digests, dig_off, sigs, sig_off)
+        n = key_idx.shape[0]
+        self._ck(lib().fabgpu_bccsp_verify_batch_async(self._h, ctypes.c_int(slot), _p(keys_xy), ctypes.c_int(keys_xy.shape[0]), _p(key_idx),
+                                                       _p(digests), _p(dig_off), _p(sigs), _p(sig_off), ctypes.c_size_t(n)))
+        return n
+
+    def bccsp_verify_batch_wait(self, slot, n, out=None):
+        status = out if out is not None else np.full(max(n, 1), 255, np.uint8)
+        self._ck(lib().fabgpu_bccsp_verify_batch_wait(self._h, ctypes.c_int(slot), _p(status), ctypes.c_size_t(n)))
         return status[:n]
 
     def bccsp_verify(self, key_xy, sig, digest):
@@ -292,10 +311,10 @@ class Context:
         self._ck(lib().fabgpu_test_fieldop(self._h, ctypes.c_int(op), _p(a), _p(b), ctypes.c_size_t(a.shape[0]), _p(out)))
         return out
 
-    def test_gtable(self):
-        size = lib().fabgpu_test_gtable(self._h, None, ctypes.c_size_t(0))
-        out = np.zeros(size, np.uint8)
-        got = lib().fabgpu_test_gtable(self._h, _p(out), ctypes.c_size_t(size))
-        if got != size:
-            raise FabGpuError(int(got), self.last_error())
-        return out
+    def test_table_entries(self, key_slot, window, digit):
+        """Sampled window-table entries (key_slot < 0: generator table) -> (n, 16) little-endian u32 limbs, X then Y, Montgomery form."""
+        window = np.ascontiguousarray(window, dtype=np.uint32)
+        digit = np.ascontiguousarray(digit, dtype=np.uint32)
+        out = np.zeros((window.shape[0], 64), np.uint8)
+        self._ck(lib().fabgpu_test_table_entries(self._h, ctypes.c_int(key_slot), _p(window), _p(digit), ctypes.c_size_t(window.shape[0]), _p(out)))
+        return out.view("<u4").reshape(-1, 16)

@@ -111,6 +111,58 @@ __global__ void build_key_tables_kernel(const uint8_t* __restrict__ keys_xy, con
     build_key_window(q, j, qtab + ((size_t)slots[k] * FAB_Q_WINDOWS + j) * FAB_Q_ENTRIES, zs, zs + FAB_Q_ENTRIES);
 }
 
+// Two-level table build (build_window_chunk in ecdsa_verify.cuh), shared by the per-key tables and the generator's table.
+// Stage 1: thread ((k * windows + j) * 2 + h) builds the 2^(wbits/2) - 1 multiples of 2^(wbits j + h wbits/2) P_k into
+//   small[thread][.]; scratch: 2 * (2^(wbits/2) - 1) field elements per thread.  keys_xy == NULL: one "key", P = G.
+//   flags[k] = 1 when key k is a curve point, 0 otherwise (nothing is built for it).
+__global__ void small_tables_kernel(const uint8_t* __restrict__ keys_xy, int nkeys, int wbits, int windows, aff* __restrict__ small,
+                                    u256* __restrict__ scratch, uint32_t* __restrict__ flags)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nkeys * windows * 2) return;
+    const int k = t / (windows * 2), j = (t / 2) % windows, h = t & 1;
+    const int half = wbits / 2, nsmall = (1 << half) - 1;
+    aff q;
+    if (keys_xy) {
+        const u256 x = load_be32(keys_xy + 64 * (size_t)k), y = load_be32(keys_xy + 64 * (size_t)k + 32);
+        const u256 p = fe_p();
+        bool ok = u256_lt(x, p) && u256_lt(y, p);
+        if (ok) { q.x = fe_to_mont(x); q.y = fe_to_mont(y); ok = aff_on_curve(q); }
+        if (j == 0 && h == 0) flags[k] = ok ? 1u : 0u;
+        if (!ok) return;
+    } else { q.x = fe_gx_mont(); q.y = fe_gy_mont(); }
+    u256* zs = scratch + (size_t)t * 2 * nsmall;
+    build_multiples(q, wbits * j + h * half, nsmall, small + (size_t)t * nsmall, zs, zs + nsmall);
+}
+
+// Stage 2: thread ((k * windows + j) * chunks + c) writes FAB_TAB_CHUNK consecutive entries of table slots[k] (slot 0 when
+// slots == NULL): one mixed addition each plus one shared inversion.  Runs after stage 1 on the same stream.
+__global__ void __launch_bounds__(128)
+full_tables_kernel(const aff* __restrict__ small, const int32_t* __restrict__ slots, const uint32_t* __restrict__ flags, int nkeys, int wbits,
+                   int windows, aff* __restrict__ tab)
+{
+    const uint32_t entries = (1u << wbits) - 1u, chunks = (entries + FAB_TAB_CHUNK - 1) / FAB_TAB_CHUNK;
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (size_t)nkeys * windows * chunks) return;
+    const uint32_t c = (uint32_t)(t % chunks);
+    const int j = (int)((t / chunks) % windows), k = (int)(t / ((size_t)chunks * windows));
+    if (flags && !flags[k]) return;
+    const int half = wbits / 2, nsmall = (1 << half) - 1;
+    const aff* lo = small + ((size_t)(k * windows + j) * 2) * nsmall;
+    const uint32_t x0 = 1u + c * FAB_TAB_CHUNK;
+    const int count = (int)min((uint32_t)FAB_TAB_CHUNK, entries - x0 + 1u);
+    const size_t slot = slots ? (size_t)slots[k] : 0;
+    build_window_chunk(lo, lo + nsmall, half, x0, count, tab + (slot * windows + j) * (size_t)entries);
+}
+
+// Test hook: out[i] = entry (window[i], digit[i]) of a table (digit >= 1).
+__global__ void table_entries_kernel(const aff* __restrict__ tab, int wbits, const uint32_t* __restrict__ window, const uint32_t* __restrict__ digit,
+                                     uint32_t n, aff* __restrict__ out)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = tab[(size_t)window[i] * ((1u << wbits) - 1u) + (digit[i] - 1u)];
+}
+
 // Unit-test hook: out[i] = op(a[i], b[i]) on the device primitives (tests/test_gpu_field.py).
 __global__ void fieldop_kernel(int op, const uint8_t* a, const uint8_t* b, int n, uint8_t* out)
 {

@@ -17,11 +17,11 @@
 #include "p256_modinv.cuh"
 
 #ifndef FAB_WG
-#define FAB_WG 16                     // window bits of the fixed-base table of G: 16 windows x 65 535 points = 64 MiB per
-#endif                                // device, 16 mixed additions for u1*G (measured: 8 -> 94 M/s, 12 -> 109, 16 -> 120)
+#define FAB_WG 22                     // window bits of the fixed-base table of G: 12 windows x 4 194 303 points = 3.2 GB per
+#endif                                // device, 12 mixed additions for u1*G (measured at 64k with FAB_WQ 16: 16 -> 165 M/s, 20 -> 179, 22 -> 184)
 #ifndef FAB_WQ
-#define FAB_WQ 12                     // window bits of the per-key tables: 22 windows x 4 095 points = 5.5 MiB per key,
-#endif                                // 22 mixed additions for u2*Q (measured at 64k: 8 -> 120 M/s, 10 -> 130, 12 -> 141)
+#define FAB_WQ 16                     // window bits of the per-key tables: 16 windows x 65 535 points = 64 MiB per key,
+#endif                                // 16 mixed additions for u2*Q (measured at 64k: 8 -> 120 M/s, 10 -> 130, 12 -> 144, 16 -> 166)
 #define FAB_Q_WINDOWS ((256 + FAB_WQ - 1) / FAB_WQ)
 #define FAB_Q_ENTRIES ((1 << FAB_WQ) - 1)
 #ifndef FAB_SAFEGCD
@@ -198,17 +198,16 @@ FAB_HD aff table_entry(const aff& g, int wbits, int j, uint32_t d)
     for (int t = 0; t < wbits * j; t++) acc = jac_double(acc);
     return jac_to_aff(acc);
 }
-// Window j of a key's table, built by ONE thread: out[d-1] = d * 2^(FAB_WQ*j) * q for d = 1..FAB_Q_ENTRIES.
-// Chain of mixed additions from the affine base 2^(FAB_WG*j) q, then one shared inversion for the whole window
-// (Montgomery's trick).  zs / ps: scratch of FAB_Q_ENTRIES elements each.  ~6 100 field multiplications.
-FAB_HD void build_key_window(const aff& q, int j, aff* out, u256* zs, u256* ps)
+// out[d-1] = d * 2^shift * q for d = 1..count, built by ONE thread: chain of mixed additions from the affine base
+// 2^shift q, then one shared inversion for the whole chain (Montgomery's trick).  zs / ps: scratch of `count` elements each.
+FAB_HD void build_multiples(const aff& q, int shift, int count, aff* out, u256* zs, u256* ps)
 {
     jac b = jac_from_aff(q);
-    for (int t = 0; t < FAB_WQ * j; t++) b = jac_double(b);
+    for (int t = 0; t < shift; t++) b = jac_double(b);
     const aff base = jac_to_aff(b);
     jac t = jac_from_aff(base);
     u256 run = fe_one();
-    for (int d = 1; d <= FAB_Q_ENTRIES; d++) {
+    for (int d = 1; d <= count; d++) {
         if (d > 1) t = jac_add_aff(t, base);
         out[d - 1].x = t.X; out[d - 1].y = t.Y;
         zs[d - 1] = t.Z;
@@ -216,12 +215,58 @@ FAB_HD void build_key_window(const aff& q, int j, aff* out, u256* zs, u256* ps)
         ps[d - 1] = run;                       // z_1 * ... * z_d
     }
     u256 inv = fe_inv(run);
-    for (int d = FAB_Q_ENTRIES; d >= 1; d--) {
+    for (int d = count; d >= 1; d--) {
         const u256 zi = (d > 1) ? fe_mul(inv, ps[d - 2]) : inv;      // 1 / z_d
         if (d > 1) inv = fe_mul(inv, zs[d - 1]);
         const u256 zi2 = fe_sqr(zi);
         out[d - 1].x = fe_mul(out[d - 1].x, zi2);
         out[d - 1].y = fe_mul(out[d - 1].y, fe_mul(zi2, zi));
+    }
+}
+
+// Window j of a key's table in one go (small windows): out[d-1] = d * 2^(FAB_WQ*j) * q, d = 1..FAB_Q_ENTRIES.
+FAB_HD void build_key_window(const aff& q, int j, aff* out, u256* zs, u256* ps)
+{
+    build_multiples(q, FAB_WQ * j, FAB_Q_ENTRIES, out, zs, ps);
+}
+
+// Wide windows (>= 14 bits) are built in two levels: with h = w / 2, entry x = hi * 2^h + lo of window j is
+//   hi * (2^h B_j) + lo * B_j,   B_j = 2^(w j) P,
+// i.e. ONE mixed addition of two points from two small tables (2^h - 1 multiples each, built by build_multiples).
+// A thread produces FAB_TAB_CHUNK consecutive entries and shares one inversion among them.  Used for the per-key
+// tables (P = Q) and for the generator's table (P = G).
+#ifndef FAB_Q_TWO_LEVEL
+#define FAB_Q_TWO_LEVEL ((FAB_WQ >= 14) && (FAB_WQ % 2 == 0))
+#endif
+#ifndef FAB_G_TWO_LEVEL
+#define FAB_G_TWO_LEVEL ((FAB_WG >= 14) && (FAB_WG % 2 == 0))
+#endif
+#define FAB_TAB_CHUNK 64
+// lo[d-1] = d B_j, hi[d-1] = d 2^half B_j (affine); writes out[x-1] for x in [x0, x0 + count), count <= FAB_TAB_CHUNK
+FAB_HD void build_window_chunk(const aff* lo, const aff* hi, int half, uint32_t x0, int count, aff* out)
+{
+    u256 zs[FAB_TAB_CHUNK], ps[FAB_TAB_CHUNK];
+    const uint32_t lomask = (1u << half) - 1u;
+    u256 run = fe_one();
+    for (int k = 0; k < count; k++) {
+        const uint32_t x = x0 + (uint32_t)k, h = x >> half, l = x & lomask;
+        jac p;
+        if (h == 0) p = jac_from_aff(lo[l - 1]);
+        else if (l == 0) p = jac_from_aff(hi[h - 1]);
+        else p = jac_add_aff(jac_from_aff(hi[h - 1]), lo[l - 1]);
+        out[x - 1].x = p.X; out[x - 1].y = p.Y;
+        zs[k] = p.Z;
+        run = fe_mul(run, p.Z);
+        ps[k] = run;
+    }
+    u256 inv = fe_inv(run);
+    for (int k = count - 1; k >= 0; k--) {
+        const u256 zi = (k > 0) ? fe_mul(inv, ps[k - 1]) : inv;
+        if (k > 0) inv = fe_mul(inv, zs[k]);
+        const u256 zi2 = fe_sqr(zi);
+        const uint32_t x = x0 + (uint32_t)k;
+        out[x - 1].x = fe_mul(out[x - 1].x, zi2);
+        out[x - 1].y = fe_mul(out[x - 1].y, fe_mul(zi2, zi));
     }
 }
 

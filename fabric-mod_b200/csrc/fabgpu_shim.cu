@@ -124,6 +124,7 @@ struct fabgpu_ctx {
     size_t dev_cap = 0;        // per device per slot (multiple of 32)
     std::string last_error;
     std::mutex mu;         // guards enqueue/wait
+    std::mutex sync_mu;    // one synchronous fabgpu_bccsp_verify_batch at a time
     std::mutex slot0_mu;   // serialises the composite calls that stage through slot 0's pinned buffers
     std::atomic<unsigned long long> launches{0};
     // per-key table cache (fabgpu_keys_register): 64-byte X||Y -> slot, least-recently-used eviction
@@ -171,7 +172,12 @@ struct fabgpu_ctx {
         uint8_t *d_sigs = nullptr, *d_digs = nullptr, *d_keys = nullptr, *d_status = nullptr, *d_pre = nullptr, *d_r = nullptr, *d_s = nullptr, *d_e = nullptr,
         *d_qx = nullptr, *d_qy = nullptr; uint32_t *d_sig_off = nullptr, *d_dig_off = nullptr, *d_mask = nullptr, *d_off = nullptr;
         int32_t *d_kidx = nullptr, *d_slot_of = nullptr, *d_ks = nullptr;
-    } gb;
+        // fabgpu_bccsp_verify_batch_async .. _wait: what is in flight on this slot
+        bool busy = false; bool on_device = false; size_t n = 0;
+        std::vector<uint8_t> done_status;       // statuses of a batch that could not take the device-gate path (finished at submit time)
+        std::chrono::steady_clock::time_point t_submit;
+    } gb[FABGPU_SLOTS];
+    std::mutex gb_mu[FABGPU_SLOTS];
     struct DevBlock {
         size_t tx_cap = 0, j_cap = 0;
         uint32_t* d_env_off = nullptr; bdev::TxDev* d_txs = nullptr; bdev::RawJob* d_raw = nullptr; bdev::ShaJobD* d_sha = nullptr; uint8_t *d_r = nullptr, *d_s = nullptr, *d_qx = nullptr,
@@ -339,12 +345,13 @@ void free_all(fabgpu_ctx* ctx)
         for (void* p : dev2) if (p) cudaFree(p);
         void* host2[] = {db.h_flags, db.h_hash, db.h_seg, db.h_counter, db.h_env_off};
         for (void* p : host2) if (p) cudaFreeHost(p);
-        auto& gb = ctx->gb;
+        for (auto& gb : ctx->gb) {
         void* dev3[] = {gb.d_sigs, gb.d_digs, gb.d_keys, gb.d_status, gb.d_pre, gb.d_r, gb.d_s, gb.d_e, gb.d_qx, gb.d_qy, gb.d_sig_off, gb.d_dig_off, gb.d_mask, gb.d_off,
                         gb.d_kidx, gb.d_slot_of, gb.d_ks};
         for (void* p : dev3) if (p) cudaFree(p);
         void* host3[] = {gb.h_sigs, gb.h_digs, gb.h_keys, gb.h_status, gb.h_sig_off, gb.h_dig_off, gb.h_kidx, gb.h_slot_of};
         for (void* p : host3) if (p) cudaFreeHost(p);
+        }
     }
     for (auto& dv : ctx->devs) {
         cudaSetDevice(dv.id);
@@ -413,9 +420,26 @@ int init_impl(fabgpu_ctx* ctx, const int* device_ids, int n_dev, size_t max_batc
             CK(ctx, cudaMalloc(&ds.d_off, 4 * words));
             CK(ctx, cudaMalloc(&ds.d_key_slot, 4 * ctx->dev_cap));
         }
+#if FAB_G_TWO_LEVEL
+        {
+            aff* d_small = nullptr; u256* d_scratch = nullptr;
+            const size_t nsmall = ((size_t)1 << (FAB_WG / 2)) - 1;
+            const size_t threads = (size_t)FAB_G_WINDOWS * 2;
+            CK(ctx, cudaMalloc(&d_scratch, threads * 2 * nsmall * sizeof(u256)));
+            CK(ctx, cudaMalloc(&d_small, threads * nsmall * sizeof(aff)));
+            small_tables_kernel<<<(unsigned)((threads + 31) / 32), 32, 0, dv.slot[0].stream>>>(nullptr, 1, FAB_WG, FAB_G_WINDOWS, d_small, d_scratch, nullptr);
+            const size_t threads2 = (size_t)FAB_G_WINDOWS * ((FAB_G_ENTRIES + FAB_TAB_CHUNK - 1) / FAB_TAB_CHUNK);
+            full_tables_kernel<<<(unsigned)((threads2 + 127) / 128), 128, 0, dv.slot[0].stream>>>(d_small, nullptr, nullptr, 1, FAB_WG, FAB_G_WINDOWS, dv.gtab);
+            ctx->launches += 2;
+            CK(ctx, cudaGetLastError());
+            CK(ctx, cudaStreamSynchronize(dv.slot[0].stream));
+            cudaFree(d_small); cudaFree(d_scratch);
+        }
+#else
         build_g_table_kernel<<<(unsigned)((tab_entries + 127) / 128), 128, 0, dv.slot[0].stream>>>(dv.gtab);
         ctx->launches++;
         CK(ctx, cudaGetLastError());
+#endif
     }
     const size_t hwords = (round_up32(max_batch) / 32) + ids.size();
     for (auto& hs : ctx->hslot) {
@@ -544,18 +568,33 @@ int fabgpu_keys_register(fabgpu_ctx* ctx, const uint8_t* keys_xy, int K, int32_t
         // an evicted slot's table may still be read by a batch in flight: drain this device first (registration is rare)
         for (auto& ds : dv.slot) CK(ctx, cudaStreamSynchronize(ds.stream));
         uint8_t* d_keys = nullptr; int32_t* d_slots = nullptr; uint32_t* d_flags = nullptr; u256* d_scratch = nullptr;
-        const size_t threads = (size_t)F * FAB_Q_WINDOWS;
         CK(ctx, cudaMalloc(&d_keys, fk.size()));
         CK(ctx, cudaMalloc(&d_slots, 4 * (size_t)F));
         CK(ctx, cudaMalloc(&d_flags, 4 * (size_t)F));
-        CK(ctx, cudaMalloc(&d_scratch, threads * 2 * FAB_Q_ENTRIES * sizeof(u256)));
         CK(ctx, cudaMemcpy(d_keys, fk.data(), fk.size(), cudaMemcpyHostToDevice));
         CK(ctx, cudaMemcpy(d_slots, fresh_slot.data(), 4 * (size_t)F, cudaMemcpyHostToDevice));
+#if FAB_Q_TWO_LEVEL
+        aff* d_small = nullptr;
+        const size_t nsmall = ((size_t)1 << (FAB_WQ / 2)) - 1;
+        const size_t threads = (size_t)F * FAB_Q_WINDOWS * 2;
+        CK(ctx, cudaMalloc(&d_scratch, threads * 2 * nsmall * sizeof(u256)));
+        CK(ctx, cudaMalloc(&d_small, threads * nsmall * sizeof(aff)));
+        small_tables_kernel<<<(unsigned)((threads + 31) / 32), 32, 0, dv.slot[0].stream>>>(d_keys, F, FAB_WQ, FAB_Q_WINDOWS, d_small, d_scratch, d_flags);
+        const size_t threads2 = (size_t)F * FAB_Q_WINDOWS * ((FAB_Q_ENTRIES + FAB_TAB_CHUNK - 1) / FAB_TAB_CHUNK);
+        full_tables_kernel<<<(unsigned)((threads2 + 127) / 128), 128, 0, dv.slot[0].stream>>>(d_small, d_slots, d_flags, F, FAB_WQ, FAB_Q_WINDOWS, dv.qtab);
+        ctx->launches += 2;
+#else
+        const size_t threads = (size_t)F * FAB_Q_WINDOWS;
+        CK(ctx, cudaMalloc(&d_scratch, threads * 2 * FAB_Q_ENTRIES * sizeof(u256)));
         build_key_tables_kernel<<<(unsigned)((threads + 31) / 32), 32, 0, dv.slot[0].stream>>>(d_keys, d_slots, F, dv.qtab, d_scratch, d_flags);
         ctx->launches++;
+#endif
         CK(ctx, cudaGetLastError());
         CK(ctx, cudaStreamSynchronize(dv.slot[0].stream));
         CK(ctx, cudaMemcpy(flags.data(), d_flags, 4 * (size_t)F, cudaMemcpyDeviceToHost));
+#if FAB_Q_TWO_LEVEL
+        cudaFree(d_small);
+#endif
         cudaFree(d_keys); cudaFree(d_slots); cudaFree(d_flags); cudaFree(d_scratch);
     }
     for (int i = 0; i < F; i++) {
@@ -638,9 +677,11 @@ int fabgpu_gate_signature(const uint8_t* sig, size_t sig_len, uint8_t r_out[32],
 
 // fabgpu_bccsp_verify_batch with the gates on the device: the host only stages the raw blobs into pinned memory
 // (parallel streaming copies) and reads one status byte per signature back.  Device 0 of the context.
-static int bccsp_batch_device(fabgpu_ctx* ctx, const uint8_t* keys_xy, int K, const int32_t* key_idx, const uint8_t* digests,
-                              const uint32_t* dig_off, const uint8_t* sigs, const uint32_t* sig_off, size_t n, uint8_t* status,
-                              const std::vector<int32_t>& slot_of)
+// Device-gated batch, first half: stage into the slot's pinned buffers and enqueue copies + three kernels + the status
+// read-back on the slot's stream.  Returns without waiting; the caller's buffers are no longer referenced.
+static int bccsp_device_submit(fabgpu_ctx* ctx, int slot, const uint8_t* keys_xy, int K, const int32_t* key_idx, const uint8_t* digests,
+                               const uint32_t* dig_off, const uint8_t* sigs, const uint32_t* sig_off, size_t n,
+                               const std::vector<int32_t>& slot_of)
 {
     auto now = [] { return std::chrono::steady_clock::now(); };
     auto us = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
@@ -648,8 +689,8 @@ static int bccsp_batch_device(fabgpu_ctx* ctx, const uint8_t* keys_xy, int K, co
     };
     auto t0 = now();
     Device& dv = ctx->devs[0];
-    DevSlot& ds = dv.slot[0];
-    auto& gb = ctx->gb;
+    DevSlot& ds = dv.slot[slot];
+    auto& gb = ctx->gb[slot];
     CK(ctx, cudaSetDevice(dv.id));
     const size_t sig_bytes = sig_off[n], dig_bytes = dig_off[n];
     int rc = 0;
@@ -712,52 +753,123 @@ static int bccsp_batch_device(fabgpu_ctx* ctx, const uint8_t* keys_xy, int K, co
     ctx->launches++;
     CK(ctx, cudaGetLastError());
     CK(ctx, cudaMemcpyAsync(gb.h_status, gb.d_status, n, cudaMemcpyDeviceToHost, st));
-    CK(ctx, cudaStreamSynchronize(st));
+    gb.t_submit = t1;
+    ctx->timing[1] = us(t0, t1);
+    return FABGPU_OK;
+}
+
+// Second half: wait for the slot's stream and hand the statuses out.
+static int bccsp_device_finish(fabgpu_ctx* ctx, int slot, uint8_t* status)
+{
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto us = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+        return std::chrono::duration<double, std::micro>(b - a).count();
+    };
+    auto& gb = ctx->gb[slot];
+    CK(ctx, cudaSetDevice(ctx->devs[0].id));
+    CK(ctx, cudaStreamSynchronize(ctx->devs[0].slot[slot].stream));
     auto t2 = now();
-    memcpy(status, gb.h_status, n);
-    ctx->timing[1] = us(t0, t1); ctx->timing[2] = us(t1, t2); ctx->timing[3] = us(t2, now());
+    memcpy(status, gb.h_status, gb.n);
+    ctx->timing[2] = us(gb.t_submit, t2); ctx->timing[3] = us(t2, now());
+    return FABGPU_OK;
+}
+
+// Keys that recur (>= key_min_uses signatures in this call) or already own a table use the fixed-base kernel; this is what
+// KeyImport does once per identity in the Go provider.  slot_of[k]: handle of key k's table or -1.
+static int resolve_key_tables(fabgpu_ctx* ctx, const uint8_t* keys_xy, int K, const int32_t* key_idx, size_t n, std::vector<int32_t>& slot_of)
+{
+    slot_of.assign(K > 0 ? K : 0, -1);
+    if (!(K > 0 && keys_xy && ctx->key_min_uses >= 0)) return FABGPU_OK;
+    std::vector<uint32_t> uses(K, 0);
+    for (size_t i = 0; i < n; i++) if (key_idx[i] >= 0 && key_idx[i] < K) uses[key_idx[i]]++;
+    std::vector<int> want;
+    for (int k = 0; k < K; k++) if (uses[k] >= (uint32_t)ctx->key_min_uses && uses[k] > 0) want.push_back(k);
+    if (want.empty() || (int)want.size() > ctx->key_slots) return FABGPU_OK;
+    std::vector<uint8_t> wk(64 * want.size());
+    std::vector<int32_t> ws(want.size(), -1);
+    for (size_t i = 0; i < want.size(); i++) memcpy(wk.data() + 64 * i, keys_xy + 64 * (size_t)want[i], 64);
+    int rc = fabgpu_keys_register(ctx, wk.data(), (int)want.size(), ws.data());
+    if (rc) return rc;
+    for (size_t i = 0; i < want.size(); i++) slot_of[want[i]] = ws[i];
+    return FABGPU_OK;
+}
+
+// Default: gates on the device (one context device; a multi-device context keeps the host-gated split).
+static bool device_gates_apply(const fabgpu_ctx* ctx, const uint32_t* dig_off, const uint32_t* sig_off, size_t n)
+{
+    const char* dg = getenv("FABGPU_BCCSP_HOST_GATES");
+    return !(dg && dg[0] == '1') && ctx->devs.size() == 1 && n > 0 && n < (1u << 27) && sig_off[n] < (1u << 31) && dig_off[n] < (1u << 31);
+}
+
+static int bccsp_batch_hostgated(fabgpu_ctx* ctx, const uint8_t* keys_xy, int K, const int32_t* key_idx, const uint8_t* digests,
+                                 const uint32_t* dig_off, const uint8_t* sigs, const uint32_t* sig_off, size_t n, uint8_t* status,
+                                 const std::vector<int32_t>& slot_of);
+
+int fabgpu_bccsp_verify_batch_async(fabgpu_ctx* ctx, int slot, const uint8_t* keys_xy, int K, const int32_t* key_idx, const uint8_t* digests,
+                                    const uint32_t* dig_off, const uint8_t* sigs, const uint32_t* sig_off, size_t n)
+{
+    if (!ctx || slot < 0 || slot >= FABGPU_SLOTS || (n && (!key_idx || !dig_off || !sig_off))) return FABGPU_E_ARG;
+    std::lock_guard<std::mutex> lk(ctx->gb_mu[slot]);
+    std::lock_guard<std::mutex> lk0(ctx->slot0_mu);       // host threads (staging pool) and the key cache: one submitter at a time
+    auto& gb = ctx->gb[slot];
+    if (gb.busy) { ctx->last_error = "slot already holds a batch: call fabgpu_bccsp_verify_batch_wait first"; return FABGPU_E_ARG; }
+    auto t_start = std::chrono::steady_clock::now();
+    ctx->timing[0] = ctx->timing[1] = ctx->timing[2] = ctx->timing[3] = 0;
+    std::vector<int32_t> slot_of;
+    int rc = resolve_key_tables(ctx, keys_xy, K, key_idx, n, slot_of);
+    if (rc) return rc;
+    ctx->timing[0] = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_start).count();
+    if (fault_injected()) { ctx->last_error = "fault injected (FABGPU_FAULT_INJECT=1)"; return FABGPU_E_INJECTED; }
+    gb.n = n;
+    if (device_gates_apply(ctx, dig_off, sig_off, n)) {
+        rc = bccsp_device_submit(ctx, slot, keys_xy, K, key_idx, digests, dig_off, sigs, sig_off, n, slot_of);
+        if (rc) { cudaStreamSynchronize(ctx->devs[0].slot[slot].stream); return rc; }
+        gb.on_device = true;
+    } else {
+        // host-gated split (several devices, or FABGPU_BCCSP_HOST_GATES=1): it pipelines internally over both pinned SoA
+        // slots, so it completes here and _wait only hands the statuses out
+        gb.done_status.assign(n, 0);
+        if (n) { rc = bccsp_batch_hostgated(ctx, keys_xy, K, key_idx, digests, dig_off, sigs, sig_off, n, gb.done_status.data(), slot_of); if (rc) return rc; }
+        gb.on_device = false;
+    }
+    gb.busy = true;
+    return FABGPU_OK;
+}
+
+int fabgpu_bccsp_verify_batch_wait(fabgpu_ctx* ctx, int slot, uint8_t* status, size_t n)
+{
+    if (!ctx || slot < 0 || slot >= FABGPU_SLOTS) return FABGPU_E_ARG;
+    std::lock_guard<std::mutex> lk(ctx->gb_mu[slot]);
+    auto& gb = ctx->gb[slot];
+    if (!gb.busy) { ctx->last_error = "no batch in flight on this slot"; return FABGPU_E_ARG; }
+    if (n != gb.n || (n && !status)) { ctx->last_error = "status buffer does not match the submitted batch"; return FABGPU_E_ARG; }
+    gb.busy = false;
+    if (gb.on_device) return bccsp_device_finish(ctx, slot, status);
+    if (n) memcpy(status, gb.done_status.data(), n);
     return FABGPU_OK;
 }
 
 int fabgpu_bccsp_verify_batch(fabgpu_ctx* ctx, const uint8_t* keys_xy, int K, const int32_t* key_idx, const uint8_t* digests,
                               const uint32_t* dig_off, const uint8_t* sigs, const uint32_t* sig_off, size_t n, uint8_t* status)
 {
-    if (!ctx || (n && (!key_idx || !dig_off || !sig_off || !status))) return FABGPU_E_ARG;
-    // Gates run on the context's host threads; a signature that fails a gate keeps its position with r = s = 0 (the
-    // kernel rejects it at once) so that packing needs no compaction and stays parallel.
-    std::lock_guard<std::mutex> lk0(ctx->slot0_mu);
-    // Keys that recur (>= key_min_uses signatures in this call) or already own a table use the fixed-base kernel;
-    // this is what KeyImport does once per identity in the Go provider.
+    if (!ctx || (n && !status)) return FABGPU_E_ARG;
+    // one synchronous caller at a time; slot 0 of the async pair
+    std::lock_guard<std::mutex> lk(ctx->sync_mu);
+    int rc = fabgpu_bccsp_verify_batch_async(ctx, 0, keys_xy, K, key_idx, digests, dig_off, sigs, sig_off, n);
+    if (rc) return rc;
+    return fabgpu_bccsp_verify_batch_wait(ctx, 0, status, n);
+}
+
+// Host-gated form.  Gates run on the context's host threads; a signature that fails a gate keeps its position with
+// r = s = 0 (the kernel rejects it at once) so that packing needs no compaction and stays parallel.
+static int bccsp_batch_hostgated(fabgpu_ctx* ctx, const uint8_t* keys_xy, int K, const int32_t* key_idx, const uint8_t* digests,
+                                 const uint32_t* dig_off, const uint8_t* sigs, const uint32_t* sig_off, size_t n, uint8_t* status,
+                                 const std::vector<int32_t>& slot_of)
+{
     auto now = [] { return std::chrono::steady_clock::now(); };
     auto us = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
         return std::chrono::duration<double, std::micro>(b - a).count();
     };
-    auto t_start = now();
-    ctx->timing[0] = ctx->timing[1] = ctx->timing[2] = ctx->timing[3] = 0;
-    std::vector<int32_t> slot_of(K > 0 ? K : 0, -1);
-    if (K > 0 && keys_xy && ctx->key_min_uses >= 0) {
-        std::vector<uint32_t> uses(K, 0);
-        for (size_t i = 0; i < n; i++) if (key_idx[i] >= 0 && key_idx[i] < K) uses[key_idx[i]]++;
-        std::vector<int> want;
-        for (int k = 0; k < K; k++) if (uses[k] >= (uint32_t)ctx->key_min_uses && uses[k] > 0) want.push_back(k);
-        if (!want.empty() && (int)want.size() <= ctx->key_slots) {
-            std::vector<uint8_t> wk(64 * want.size());
-            std::vector<int32_t> ws(want.size(), -1);
-            for (size_t i = 0; i < want.size(); i++) memcpy(wk.data() + 64 * i, keys_xy + 64 * (size_t)want[i], 64);
-            int rc = fabgpu_keys_register(ctx, wk.data(), (int)want.size(), ws.data());
-            if (rc) return rc;
-            for (size_t i = 0; i < want.size(); i++) slot_of[want[i]] = ws[i];
-        }
-    }
-    ctx->timing[0] = us(t_start, now());
-    {
-        // Default: gates on the device (one context device; a multi-device context keeps the host-gated split below).
-        const char* dg = getenv("FABGPU_BCCSP_HOST_GATES");
-        if (!(dg && dg[0] == '1') && ctx->devs.size() == 1 && n > 0 && n < (1u << 27) && sig_off[n] < (1u << 31) && dig_off[n] < (1u << 31)) {
-            if (fault_injected()) { ctx->last_error = "fault injected (FABGPU_FAULT_INJECT=1)"; return FABGPU_E_INJECTED; }
-            return bccsp_batch_device(ctx, keys_xy, K, key_idx, digests, dig_off, sigs, sig_off, n, status, slot_of);
-        }
-    }
     // The call is cut into chunks that alternate between the two pinned slots: while the GPU works on one chunk the
     // host threads gate and pack the next, and the statuses of the chunk before are scattered.
     const int T = ctx->pool->size();
@@ -1371,14 +1483,25 @@ int fabgpu_test_fieldop(fabgpu_ctx* ctx, int op, const uint8_t* a, const uint8_t
     return FABGPU_OK;
 }
 
-long fabgpu_test_gtable(fabgpu_ctx* ctx, uint8_t* out, size_t cap)
+int fabgpu_test_table_entries(fabgpu_ctx* ctx, int key_slot, const uint32_t* window, const uint32_t* digit, size_t n, uint8_t* out)
 {
-    const size_t bytes = (size_t)FAB_G_WINDOWS * FAB_G_ENTRIES * sizeof(aff);
-    if (!out) return (long)bytes;
-    if (!ctx || cap < bytes) return FABGPU_E_ARG;
-    CK(ctx, cudaSetDevice(ctx->devs[0].id));
-    CK(ctx, cudaMemcpy(out, ctx->devs[0].gtab, bytes, cudaMemcpyDeviceToHost));
-    return (long)bytes;
+    if (!ctx || !window || !digit || !out || key_slot >= ctx->key_slots) return FABGPU_E_ARG;
+    const int wbits = key_slot < 0 ? FAB_WG : FAB_WQ, windows = key_slot < 0 ? FAB_G_WINDOWS : FAB_Q_WINDOWS;
+    for (size_t i = 0; i < n; i++)
+        if (window[i] >= (uint32_t)windows || digit[i] == 0 || digit[i] >= (1u << wbits)) return FABGPU_E_ARG;
+    if (n == 0) return FABGPU_OK;
+    Device& dv = ctx->devs[0];
+    CK(ctx, cudaSetDevice(dv.id));
+    const aff* tab = key_slot < 0 ? dv.gtab : dv.qtab + (size_t)key_slot * FAB_Q_WINDOWS * FAB_Q_ENTRIES;
+    uint32_t *d_w = nullptr, *d_d = nullptr; aff* d_out = nullptr;
+    CK(ctx, cudaMalloc(&d_w, 4 * n)); CK(ctx, cudaMalloc(&d_d, 4 * n)); CK(ctx, cudaMalloc(&d_out, sizeof(aff) * n));
+    CK(ctx, cudaMemcpy(d_w, window, 4 * n, cudaMemcpyHostToDevice));
+    CK(ctx, cudaMemcpy(d_d, digit, 4 * n, cudaMemcpyHostToDevice));
+    table_entries_kernel<<<(unsigned)((n + 127) / 128), 128>>>(tab, wbits, d_w, d_d, (uint32_t)n, d_out);
+    CK(ctx, cudaGetLastError());
+    CK(ctx, cudaMemcpy(out, d_out, sizeof(aff) * n, cudaMemcpyDeviceToHost));
+    cudaFree(d_w); cudaFree(d_d); cudaFree(d_out);
+    return FABGPU_OK;
 }
 
 }  // extern "C"

@@ -127,6 +127,15 @@ int fabgpu_verify_p256_device_keyed(fabgpu_ctx* ctx, int dev_index, int all_cach
 int fabgpu_bccsp_verify_batch(fabgpu_ctx* ctx, const uint8_t* keys_xy, int K, const int32_t* key_idx,
                               const uint8_t* digests, const uint32_t* dig_off, const uint8_t* sigs,
                               const uint32_t* sig_off, size_t n, uint8_t* status);
+/* The same call in two halves, for a caller that keeps the GPU fed (the Go provider's aggregator): _async stages the
+ * batch into the slot's pinned buffers and enqueues copies + kernels + the status read-back on the slot's stream, then
+ * returns -- the caller's arrays are not referenced afterwards; _wait blocks until that batch is done and writes its n
+ * status bytes.  With the FABGPU_SLOTS slots used alternately, the copies of batch i+1 overlap the kernels of batch i.
+ * A slot holds one batch at a time (FABGPU_E_ARG otherwise); fabgpu_bccsp_verify_batch itself is _async + _wait on slot 0. */
+int fabgpu_bccsp_verify_batch_async(fabgpu_ctx* ctx, int slot, const uint8_t* keys_xy, int K, const int32_t* key_idx,
+                                    const uint8_t* digests, const uint32_t* dig_off, const uint8_t* sigs,
+                                    const uint32_t* sig_off, size_t n);
+int fabgpu_bccsp_verify_batch_wait(fabgpu_ctx* ctx, int slot, uint8_t* status, size_t n);
 /* Single call with the reference's exact error strings (sw.CSP.Verify).  key_xy == NULL is the nil key.
  * *valid and err (NUL-terminated, truncated to errcap) mirror the Go (bool, error) pair; err[0] == 0 is nil. */
 int fabgpu_bccsp_verify(fabgpu_ctx* ctx, const uint8_t* key_xy, const uint8_t* sig, size_t sig_len,
@@ -176,9 +185,10 @@ int fabgpu_sha256_segments(fabgpu_ctx* ctx, const uint8_t* buf, size_t buf_len, 
 /* Device field primitives on arrays (op: 0 fe_mul, 1 fe_add, 2 fe_sub, 3 sc_mul, 4 fe_inv,
  * 5 sc_inv_to_mont by Fermat, 6 the same by division steps, 7 fe_sqr). */
 int fabgpu_test_fieldop(fabgpu_ctx* ctx, int op, const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out);
-/* Copies the device fixed-base table (entries x 64 bytes, Montgomery little-endian limbs) to `out`; returns the
- * byte size needed when out == NULL. */
-long fabgpu_test_gtable(fabgpu_ctx* ctx, uint8_t* out, size_t cap);
+/* Sampled entries of a device window table: out[i] (64 bytes: X then Y, Montgomery form, little-endian 32-bit limbs) =
+ * entry (window[i], digit[i]) = digit * 2^(w * window) * P, digit in [1, 2^w).  key_slot < 0: the generator's table
+ * (w = g_window_bits of fabgpu_build_info); otherwise the table in that raw key slot (w = key_window_bits). */
+int fabgpu_test_table_entries(fabgpu_ctx* ctx, int key_slot, const uint32_t* window, const uint32_t* digit, size_t n, uint8_t* out);
 /* Phase times of the last fabgpu_bccsp_verify_batch call, microseconds: [0] key-table lookup/registration,
  * [1] host gates + packing, [2] H2D + kernels + D2H (enqueue to completion), [3] status scatter.  For metrics export
  * (the reference only has a block-level histogram, gossip/metrics/metrics.go:187-194). */

@@ -4,6 +4,7 @@
 // are checked on the GPU by tests/test_gpu_field.py.
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <vector>
 #include <utility>
 #include "../../fabric-mod_b200/csrc/ecdsa_verify.cuh"
@@ -63,6 +64,18 @@ void hostsim_verify_batch_cached(const uint8_t* qx, const uint8_t* qy, const uin
             std::vector<aff> t;
             if (ok) {
                 t.resize((size_t)FAB_Q_WINDOWS * FAB_Q_ENTRIES);
+                if (FAB_Q_TWO_LEVEL) {      // same two-level build as small_tables_kernel + full_tables_kernel
+                    const int half = FAB_WQ / 2, nsmall = (1 << half) - 1;
+                    std::vector<aff> lo(nsmall), hi(nsmall);
+                    for (int j = 0; j < FAB_Q_WINDOWS; j++) {
+                        build_multiples(q, FAB_WQ * j, nsmall, lo.data(), zs.data(), zs.data() + nsmall);
+                        build_multiples(q, FAB_WQ * j + half, nsmall, hi.data(), zs.data(), zs.data() + nsmall);
+                        for (uint32_t x0 = 1; x0 <= (uint32_t)FAB_Q_ENTRIES; x0 += FAB_TAB_CHUNK) {
+                            const int cnt = (int)std::min<uint32_t>(FAB_TAB_CHUNK, (uint32_t)FAB_Q_ENTRIES - x0 + 1);
+                            build_window_chunk(lo.data(), hi.data(), half, x0, cnt, t.data() + (size_t)j * FAB_Q_ENTRIES);
+                        }
+                    }
+                } else
                 for (int j = 0; j < FAB_Q_WINDOWS; j++) build_key_window(q, j, t.data() + (size_t)j * FAB_Q_ENTRIES, zs.data(), zs.data() + FAB_Q_ENTRIES);
             }
             cache.emplace_back(key, std::move(t));

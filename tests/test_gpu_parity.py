@@ -76,23 +76,45 @@ def test_field_primitives(ctx):
     assert _ints(ctx.test_fieldop(7, A, A)) == [x * x * rinv % P for x in a]
 
 
-def test_fixed_base_table(ctx):
-    """Sampled entries of the device-built table == oracle scalar multiplication (entry (j, d) = d * 2^(w j) * G)."""
-    wg, _ = pkg().binding.build_info()
-    tab = ctx.test_gtable()
-    ent = tab.view("<u4").reshape(-1, 16)
-    per = (1 << wg) - 1
-    nwin = (256 + wg - 1) // wg
-    assert ent.shape[0] == per * nwin
+def _table_picks(w, rnd):
+    """(window, digit) samples that hit the corners of the two-level build: digits below 2^(w/2) (low table only), multiples of
+    2^(w/2) (high table only), chunk boundaries (64 entries per thread), the last entry, the top window's largest useful digit."""
+    per = (1 << w) - 1
+    nwin = (256 + w - 1) // w
+    half = 1 << (w // 2)
+    top = min(per, (1 << (256 - w * (nwin - 1))) - 1)
+    picks = [(0, 1), (0, per), (nwin - 1, 1), (nwin - 1, top), (1, half - 1), (1, half), (1, half + 1), (2, 3 * half), (0, 64), (0, 65),
+             (3, per - 62), (3, per - 63), (nwin - 2, per - 1), (1, 2 * half - 1)]
+    picks += [(rnd.randrange(nwin), rnd.randrange(1, per + 1)) for _ in range(20)]
+    return [(j, min(d, top) if j == nwin - 1 else d) for j, d in picks]
+
+
+def _check_entries(ent, picks, w, base):
     rinv = pow(R, -1, p256.P)
-    rnd = random.Random(3)
-    picks = [(0, 1), (0, per), (nwin - 1, 1), (nwin - 1, min(per, (1 << (256 - wg * (nwin - 1))) - 1))] + \
-            [(rnd.randrange(nwin), rnd.randrange(1, per + 1)) for _ in range(12)]
-    for j, d in picks:
-        row = ent[j * per + d - 1]
+    for (j, d), row in zip(picks, ent):
         x = sum(int(row[i]) << (32 * i) for i in range(8)) * rinv % p256.P
         y = sum(int(row[8 + i]) << (32 * i) for i in range(8)) * rinv % p256.P
-        assert (x, y) == p256.scalar_mult((d << (wg * j)) % p256.N, (p256.GX, p256.GY)), (j, d)
+        assert (x, y) == p256.scalar_mult((d << (w * j)) % p256.N, base), (j, d)
+
+
+def test_fixed_base_table(ctx):
+    """Sampled entries of the device-built generator table == oracle scalar multiplication (entry (j, d) = d * 2^(w j) * G)."""
+    wg, _ = pkg().binding.build_info()
+    picks = _table_picks(wg, random.Random(3))
+    ent = ctx.test_table_entries(-1, [j for j, _ in picks], [d for _, d in picks])
+    _check_entries(ent, picks, wg, (p256.GX, p256.GY))
+
+
+def test_key_table_entries(ctx):
+    """The same for a per-key table (fabgpu_keys_register): entry (j, d) = d * 2^(w j) * Q."""
+    _, wq = pkg().binding.build_info()
+    w = workload.Workload(32, 2, seed=91)
+    slots = ctx.keys_register(w.keys_xy) & 0xFFF
+    for k in range(2):
+        q = (from_be(w.keys_xy[k, :32]), from_be(w.keys_xy[k, 32:]))
+        picks = _table_picks(wq, random.Random(4 + k))
+        ent = ctx.test_table_entries(int(slots[k]), [j for j, _ in picks], [d for _, d in picks])
+        _check_entries(ent, picks, wq, q)
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -355,6 +377,43 @@ def test_bccsp_batch_with_forced_key_tables():
     exp = fast.verify_batch(w.keys_xy, w.key_idx, w.digest, w.dig_off(), w.sigs, w.sig_off, nthreads=8)
     assert (csp2.ctx.bccsp_verify_batch(w.keys_xy, w.key_idx, w.digest, w.dig_off(), w.sigs, w.sig_off) == exp).all()
     csp2.close()
+
+
+def test_bccsp_batch_async_two_slots_in_flight():
+    """fabgpu_bccsp_verify_batch_async / _wait: two different batches in flight on the two slots, several rounds; each
+    slot's statuses must equal the oracle's for ITS batch (no cross-talk between the slots' buffers), in either gate mode."""
+    c = pkg().binding.Context(max_batch=8192)
+    ws = []
+    for k, (n, keys, seed) in enumerate([(5000, 3, 71), (3777, 400, 72)]):       # second batch: most keys below the table threshold
+        w = workload.Workload(n, keys, seed=seed)
+        w.tamper_r(0.1 + 0.2 * k)
+        exp = fast.verify_batch(w.keys_xy, w.key_idx, w.digest, w.dig_off(), w.sigs, w.sig_off, nthreads=8)
+        ws.append((w, exp))
+    for host_gates in ("0", "1"):
+        os.environ["FABGPU_BCCSP_HOST_GATES"] = host_gates
+        try:
+            for rnd in range(3):
+                order = (0, 1) if rnd % 2 == 0 else (1, 0)
+                ns = {}
+                for sl in order:
+                    w = ws[sl][0]
+                    ns[sl] = c.bccsp_verify_batch_async(sl, w.keys_xy, w.key_idx, w.digest, w.dig_off(), w.sigs, w.sig_off)
+                with pytest.raises(pkg().binding.FabGpuError):                  # a slot holds one batch at a time
+                    w = ws[0][0]
+                    c.bccsp_verify_batch_async(0, w.keys_xy, w.key_idx, w.digest, w.dig_off(), w.sigs, w.sig_off)
+                for sl in order:
+                    got = c.bccsp_verify_batch_wait(sl, ns[sl])
+                    assert (got == ws[sl][1]).all(), (host_gates, rnd, sl)
+            with pytest.raises(pkg().binding.FabGpuError):                      # nothing in flight
+                c.bccsp_verify_batch_wait(0, 1)
+        finally:
+            del os.environ["FABGPU_BCCSP_HOST_GATES"]
+    # the blocking call still works after async use, and an empty batch goes through both halves
+    w, exp = ws[0]
+    assert (c.bccsp_verify_batch(w.keys_xy, w.key_idx, w.digest, w.dig_off(), w.sigs, w.sig_off) == exp).all()
+    n0 = c.bccsp_verify_batch_async(1, w.keys_xy, np.zeros(0, np.int32), np.zeros(0, np.uint8), np.zeros(1, np.uint32), np.zeros(0, np.uint8), np.zeros(1, np.uint32))
+    assert n0 == 0 and c.bccsp_verify_batch_wait(1, 0).shape[0] == 0
+    c.close()
 
 
 # ---------------------------------------------------------------------------------------------------------

@@ -46,7 +46,7 @@ def hostsim():
         hdrs = [os.path.join(ROOT, "fabric-mod_b200", "csrc", h) for h in ("p256_fe.cuh", "p256_point.cuh", "p256_modinv.cuh", "ecdsa_verify.cuh")]
         if not os.path.exists(so) or any(os.path.getmtime(so) < os.path.getmtime(f) for f in [src] + hdrs):
             # host build of the table would take minutes at the product's 16-bit G windows; the algorithm is window-size generic
-            subprocess.check_call(["g++", "-O2", "-std=c++17", "-DFAB_WG=8", "-DFAB_WQ=8", "-shared", "-fPIC", "-o", so, src])
+            subprocess.check_call(["g++", "-O2", "-std=c++17", "-DFAB_WG=8", "-DFAB_WQ=8", "-DFAB_Q_TWO_LEVEL=1", "-shared", "-fPIC", "-o", so, src])
         _HS = ctypes.CDLL(so)
         _HS.hostsim_gtable.restype = ctypes.c_size_t
     return _HS

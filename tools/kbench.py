@@ -25,7 +25,10 @@ def main():
     t = [torch.from_numpy(a).to(dev) for a in (w.qx(), w.qy(), w.digest, w.r, w.s)]
     mask = torch.zeros(nmax // 32, dtype=torch.int32, device=dev)
     st = torch.cuda.current_stream(dev)
+    import time
+    t0 = time.perf_counter()
     slots = ctx.keys_register(w.keys_xy) & 0xFFF          # device-resident API takes raw slot indices
+    print("%-32s keys_register(64 keys) %.1f ms" % (os.path.basename(lib), (time.perf_counter() - t0) * 1e3), flush=True)
     ks = torch.from_numpy(slots[w.key_idx]).to(dev)
     for mode, n in [(m, n) for n in batches for m in ("generic", "cached")]:
         def go():
