@@ -46,7 +46,8 @@ def alg_macs_cached(wg, wq):
 
 
 KEYS = 64
-NCU_DRAM_BYTES_PER_LAUNCH_64K = None   # ecdsa_verify_cached_kernel, profiles/r1_final_cached_ncu_summary.txt (dram read + write)
+NCU_DRAM_BYTES_PER_LAUNCH_64K = 233449984 + 8335360   # ecdsa_verify_cached_kernel, profiles/r1_final_cached_ncu_summary.txt (dram read + write)
+NCU_FMAHEAVY_BUSY = 0.5685              # sm__pipe_fmaheavy_cycles_active, % of elapsed, same capture: the binding unit of that kernel
 
 
 def _peaks():
@@ -257,7 +258,7 @@ def run_gpu(args):
     # in flight -- every step still stages its host buffers, copies them H2D, runs gate + verify + status kernels and reads the
     # status bytes back D2H inside the timed region; the copies of step k+1 overlap the kernels of step k.  The one-call
     # synchronous form is timed beside it.
-    e2e_steps = max(4, min(args.steps, 20))
+    e2e_steps = max(4, min(args.steps, 40))
     dig_off = w.dig_off()
     e2e_args = (w.keys_xy, w.key_idx, w.digest, dig_off, w.sigs, w.sig_off)
     for _ in range(2):
@@ -366,6 +367,9 @@ def run_gpu(args):
             "roofline_int": {"bound": "int32 mac (fma pipe)", "kernel": "ecdsa_verify_cached_kernel", "achieved": ach_macs / 1e12,
                              "peak": mac_peak / 1e12, "unit": "TMAC/s", "frac": ach_macs / mac_peak,
                              "macs_per_verify": macs_cached,
+                             "binding_unit": {"name": "fmaheavy pipe (IMAD / IMAD.WIDE)", "busy_frac_of_elapsed_ncu": NCU_FMAHEAVY_BUSY,
+                                              "note": "the multiplier's carry-chained wide MAC issues at 31 /clk/SM, half the plain IMAD.WIDE rate "
+                                                      "(profiles/microbench/int_pipe_b200.txt); with it the pipe is 57 % busy over the launch, ALU pipe 41 %"},
                              "peak_source": "model: 148 SM x 64 IMAD/clk x %d MHz" % int(sm_max),
                              "generic_kernel": {"achieved": B * ALG_MACS_PER_VERIFY / gen_launch_s / 1e12,
                                                 "frac": B * ALG_MACS_PER_VERIFY / gen_launch_s / mac_peak, "macs_per_verify": ALG_MACS_PER_VERIFY}},

@@ -68,7 +68,7 @@ ecdsa_verify_kernel(const int32_t* __restrict__ key_slot, const uint8_t* __restr
 #define FAB_CACHED_MINBLOCKS 4
 #endif
 // Signatures whose public key has a precomputed window table: both scalar multiplications are fixed-base
-// (FAB_G_WINDOWS + FAB_Q_WINDOWS mixed additions gathered from L2-resident tables, no doublings).  Slot < 0 -> bit 0, left to
+// (FAB_G_WINDOWS + FAB_Q_WINDOWS mixed additions gathered from HBM-resident tables, no doublings).  Slot < 0 -> bit 0, left to
 // ecdsa_verify_kernel.  qtab: key_slot_capacity tables of FAB_Q_WINDOWS*FAB_Q_ENTRIES affine points.
 __global__ void __launch_bounds__(FAB_CACHED_THREADS, FAB_CACHED_MINBLOCKS)
 ecdsa_verify_cached_kernel(const int32_t* __restrict__ key_slot, const uint8_t* __restrict__ e, const uint8_t* __restrict__ r,

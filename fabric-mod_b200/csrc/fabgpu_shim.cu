@@ -394,12 +394,23 @@ int init_impl(fabgpu_ctx* ctx, const int* device_ids, int n_dev, size_t max_batc
         const char* ev = getenv("FABGPU_GATE_THREADS");
         int want = ev ? atoi(ev) : std::max(1, std::min(hw > 0 ? hw / 2 : 1, 32));   // gates and block parsing are latency-bound
         ctx->pool.reset(new GatePool(want));
-        const char* ks = getenv("FABGPU_KEY_SLOTS");          // per-key tables are 5.5 MiB each (FAB_WQ = 12), per device
+        // Per-key tables are 64 MiB each (FAB_WQ = 16), per device.  The request (default 256 = 16 GiB of a B200's 180 GB) is
+        // capped so that the tables never take more than half of the smallest device's free memory.
+        const char* ks = getenv("FABGPU_KEY_SLOTS");
         ctx->key_slots = ks ? std::max(1, atoi(ks)) : 256;
+        if (ctx->key_slots > 4096) ctx->key_slots = 4096;     // a handle keeps 12 bits for the slot
+        const size_t per_key = (size_t)FAB_Q_WINDOWS * FAB_Q_ENTRIES * sizeof(aff);
+        for (int id : ids) {
+            size_t free_b = 0, total_b = 0;
+            CK(ctx, cudaSetDevice(id));
+            CK(ctx, cudaMemGetInfo(&free_b, &total_b));
+            const size_t g_bytes = (size_t)FAB_G_WINDOWS * FAB_G_ENTRIES * sizeof(aff);
+            const size_t room = free_b > 2 * g_bytes ? (free_b - 2 * g_bytes) / 2 : 0;
+            ctx->key_slots = (int)std::max<size_t>(1, std::min<size_t>((size_t)ctx->key_slots, room / per_key));
+        }
         ctx->slot_key.assign(ctx->key_slots, std::string());
         ctx->slot_tick.assign(ctx->key_slots, 0ull);
         ctx->slot_gen.assign(ctx->key_slots, 0u);
-        if (ctx->key_slots > 4096) ctx->key_slots = 4096;     // a handle keeps 12 bits for the slot
         const char* mu = getenv("FABGPU_KEY_MIN_USES");
         ctx->key_min_uses = mu ? atoi(mu) : 256;           // a table costs about 300 generic verifications to build
     }

@@ -436,6 +436,36 @@ FAB_HD u256 fe_sqr(const u256& a)
     return fe_mul(a, a);
 #endif
 }
+// The same three operations expanded in place (INL = true, device only): for a loop whose body is ONE point addition the
+// expansion fits the instruction cache, saves the argument moves of 8 calls and lets the scheduler overlap independent
+// products.  INL = false (and every host build) goes through the shared out-of-line copies above.
+template <bool INL> FAB_HD u256 fe_mul_t(const u256& a, const u256& b)
+{
+#if defined(__CUDA_ARCH__)
+    if (INL) { uint32_t t[16]; mul_8x8(t, a.v, b.v); return fe_reduce(t); }
+#endif
+    return fe_mul(a, b);
+}
+template <bool INL> FAB_HD u256 fe_sqr_t(const u256& a)
+{
+#if defined(__CUDA_ARCH__)
+    if (INL) { uint32_t t[16]; sqr_8(t, a.v); return fe_reduce(t); }
+#endif
+    return fe_sqr(a);
+}
+template <bool INL> FAB_HD void fe_mul2_t(const u256& a0, const u256& b0, const u256& a1, const u256& b1, u256& r0, u256& r1)
+{
+#if defined(__CUDA_ARCH__)
+    if (INL) {
+        uint32_t t0[16], t1[16];
+        mul_8x8(t0, a0.v, b0.v);
+        mul_8x8(t1, a1.v, b1.v);
+        r0 = fe_reduce(t0); r1 = fe_reduce(t1);
+        return;
+    }
+#endif
+    fe_mul2(a0, b0, a1, b1, r0, r1);
+}
 FAB_HD u256 fe_add(const u256& a, const u256& b)
 {
 #if defined(__CUDA_ARCH__)

@@ -63,32 +63,43 @@ FAB_HD jac jac_add(const jac& p, const jac& q)
     return r;
 }
 
+// The two exceptional cases of an addition whose H = 0: same point -> doubling, opposite points -> infinity.  Out of line:
+// never taken on honest inputs, and the doubling must not be expanded into the caller's loop body.
+#if defined(__CUDA_ARCH__)
+__device__ __noinline__
+#else
+inline
+#endif
+jac jac_add_h_zero(const jac& p, const u256& rr)
+{
+    if (u256_is_zero(rr)) return jac_double(p);
+    return jac_infinity();
+}
+
 // Mixed addition (madd-2004-hmv shape, Z2 = 1): 8M + 3S + 7 additive ops.  Independent products are issued in pairs
-// (fe_mul2) so that one warp keeps both integer pipes busier.
-FAB_HD jac jac_add_aff(const jac& p, const aff& q)
+// (fe_mul2) so that one warp keeps both integer pipes busier.  INL: field multiplications expanded in place (fe_mul_t).
+template <bool INL> FAB_HD jac jac_add_aff_t(const jac& p, const aff& q)
 {
     if (jac_is_infinity(p)) return jac_from_aff(q);
-    const u256 z1z1 = fe_sqr(p.Z);
+    const u256 z1z1 = fe_sqr_t<INL>(p.Z);
     u256 u2, yz;
-    fe_mul2(q.x, z1z1, q.y, p.Z, u2, yz);                 // U2 = X2 Z1^2 ; Y2 Z1
-    const u256 s2 = fe_mul(yz, z1z1);
+    fe_mul2_t<INL>(q.x, z1z1, q.y, p.Z, u2, yz);          // U2 = X2 Z1^2 ; Y2 Z1
+    const u256 s2 = fe_mul_t<INL>(yz, z1z1);
     const u256 h = fe_sub(u2, p.X);
     const u256 rr = fe_sub(s2, p.Y);
-    if (u256_is_zero(h)) {
-        if (u256_is_zero(rr)) return jac_double(p);
-        return jac_infinity();
-    }
-    const u256 hh = fe_sqr(h);
+    if (u256_is_zero(h)) return jac_add_h_zero(p, rr);
+    const u256 hh = fe_sqr_t<INL>(h);
     u256 hhh, v;
-    fe_mul2(h, hh, p.X, hh, hhh, v);                      // H^3 ; V = X1 H^2
+    fe_mul2_t<INL>(h, hh, p.X, hh, hhh, v);               // H^3 ; V = X1 H^2
     jac r;
-    r.X = fe_sub(fe_sub(fe_sqr(rr), hhh), fe_dbl(v));
+    r.X = fe_sub(fe_sub(fe_sqr_t<INL>(rr), hhh), fe_dbl(v));
     u256 t, yh;
-    fe_mul2(rr, fe_sub(v, r.X), p.Y, hhh, t, yh);         // r (V - X3) ; Y1 H^3
+    fe_mul2_t<INL>(rr, fe_sub(v, r.X), p.Y, hhh, t, yh);  // r (V - X3) ; Y1 H^3
     r.Y = fe_sub(t, yh);
-    r.Z = fe_mul(p.Z, h);
+    r.Z = fe_mul_t<INL>(p.Z, h);
     return r;
 }
+FAB_HD jac jac_add_aff(const jac& p, const aff& q) { return jac_add_aff_t<false>(p, q); }
 
 // y^2 == x^3 - 3x + b  (x, y already in Montgomery form and < p)
 FAB_HD bool aff_on_curve(const aff& a)

@@ -78,11 +78,18 @@ func (d *device) close() {
 	}
 }
 
-// verify runs H2D + kernel(s) + D2H for the first n tuples of slot i (key slots included).  One cgo call per batch,
-// never per signature.
-func (d *device) verify(i, n int) error {
-	if rc := C.fabgpu_verify_p256_keyed(d.ctx, C.int(i), C.size_t(n)); rc != C.FABGPU_OK {
-		return fmt.Errorf("fabgpu_verify_p256_keyed failed [%d]: %s", int(rc), C.GoString(C.fabgpu_last_error(d.ctx)))
+// enqueue starts H2D + kernel(s) + D2H for the first n tuples of slot i (key slots included) on the slot's stream and
+// returns; wait blocks until that batch is complete.  One cgo call per batch and phase, never per signature.
+func (d *device) enqueue(i, n int) error {
+	if rc := C.fabgpu_verify_p256_keyed_async(d.ctx, C.int(i), C.size_t(n)); rc != C.FABGPU_OK {
+		return fmt.Errorf("fabgpu_verify_p256_keyed_async failed [%d]: %s", int(rc), C.GoString(C.fabgpu_last_error(d.ctx)))
+	}
+	return nil
+}
+
+func (d *device) wait(i int) error {
+	if rc := C.fabgpu_wait(d.ctx, C.int(i)); rc != C.FABGPU_OK {
+		return fmt.Errorf("fabgpu_wait failed [%d]: %s", int(rc), C.GoString(C.fabgpu_last_error(d.ctx)))
 	}
 	return nil
 }

@@ -163,17 +163,32 @@ func (csp *impl) Verify(k bccsp.Key, signature, digest []byte, opts bccsp.Signer
 	return res.valid, nil
 }
 
-// aggregate drains requests into pinned slot buffers and launches one batch per flush.
+// aggregate drains requests into the pinned buffers of a free slot and enqueues one batch per flush; complete (below)
+// waits for batches in launch order and answers the callers.  With the two slots of a context, the host fills and copies
+// batch k+1 while the GPU verifies batch k.
+type batch struct {
+	slot    int
+	pending []*request
+	err     error
+}
+
 func (csp *impl) aggregate() {
-	pending := make([]*request, 0, csp.dev.maxBatch)
-	slotIdx := 0
+	free := make(chan int, len(csp.dev.slots))
+	for i := range csp.dev.slots {
+		free <- i
+	}
+	inflight := make(chan *batch, len(csp.dev.slots))
+	go csp.complete(inflight, free)
+	defer close(inflight)
 	timer := time.NewTimer(time.Hour)
 	for {
 		first, ok := <-csp.reqs
 		if !ok {
 			return
 		}
-		pending = append(pending[:0], first)
+		slotIdx := <-free // blocks only when both slots are still on the device
+		pending := make([]*request, 0, csp.dev.maxBatch)
+		pending = append(pending, first)
 		timer.Reset(csp.flush)
 	fill:
 		for len(pending) < csp.dev.maxBatch {
@@ -194,15 +209,27 @@ func (csp *impl) aggregate() {
 			copy(sl.s[o:o+32], rq.s[:])
 			sl.keySlot[i] = rq.key.slot // every entry is rewritten per batch: a stale slot would verify against the wrong key
 		}
-		err := csp.dev.verify(slotIdx, len(pending))
+		b := &batch{slot: slotIdx, pending: pending}
+		b.err = csp.dev.enqueue(slotIdx, len(pending)) // H2D + kernels + D2H on the slot's stream; returns at once
 		atomic.AddUint64(&csp.Batches, 1)
-		for i, rq := range pending {
+		inflight <- b
+	}
+}
+
+func (csp *impl) complete(inflight <-chan *batch, free chan<- int) {
+	for b := range inflight {
+		err := b.err
+		if err == nil {
+			err = csp.dev.wait(b.slot)
+		}
+		sl := &csp.dev.slots[b.slot]
+		for i, rq := range b.pending {
 			if err != nil || (sl.offcurve[i>>5]>>(uint(i)&31))&1 == 1 {
 				rq.done <- result{err: errors.New("gpu could not decide")}
 				continue
 			}
 			rq.done <- result{valid: (sl.mask[i>>5]>>(uint(i)&31))&1 == 1}
 		}
-		slotIdx = (slotIdx + 1) % len(csp.dev.slots)
+		free <- b.slot
 	}
 }
