@@ -143,7 +143,7 @@ def run_reference(args):
     el = time.perf_counter() - t0
     assert (st == 0).all()
     v = args.steps * w.n / el
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "verifies/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 limbs (256-bit modular integer)",
         "data": "synthetic",
@@ -151,7 +151,7 @@ def run_reference(args):
         "cpu_baseline": {"value": v, "unit": "verifies/s", "cores": cores, "kind": "port",
                          "sample": "%d steps x %d signatures through oracle/c (bccsp/sw gates + ecdsa.Verify steps on OpenSSL BN/EC primitives), %d of %d logical CPUs (best of all/half/quarter)" % (args.steps, w.n, cores, os.cpu_count() or 1)},
         "e2e": {"value": v, "unit": "verifies/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    })
 
 
 def run_gpu(args):
@@ -380,7 +380,7 @@ def run_gpu(args):
         }
         if block_replay:
             block_replay["cpu_port_ms_per_block_est"] = 4 * args.block_txs / cpu_v * 1e3
-        print(json.dumps(out))
+        emit(out)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
@@ -396,10 +396,30 @@ def main():
     ap.add_argument("--block-txs", type=int, default=10000, help="transactions in the block-replay leg (configs[2])")
     ap.add_argument("--no-block", action="store_true", help="skip the block-replay leg")
     args = ap.parse_args()
+    # The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version line on the first
+    # collective), so everything but the result goes to stderr: fd 1 is pointed at fd 2 for the duration of the run and the
+    # JSON line is written to the saved descriptor.
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    global _RESULT_FD
+    _RESULT_FD = saved
     if args.impl == "reference":
         run_reference(args)
     else:
         run_gpu(args)
+
+
+_RESULT_FD = None
+
+
+def emit(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(line.decode()); sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_RESULT_FD, line)
 
 
 if __name__ == "__main__":
