@@ -24,6 +24,7 @@ EXPORTS = [
     "fabgpu_verify_p256_keyed_async", "fabgpu_verify_p256_device_keyed", "fabgpu_last_timing", "fabgpu_build_info",
     "fabgpu_msp_configure", "fabgpu_validate_block", "fabgpu_validate_envelopes", "fabgpu_block_buffer", "fabgpu_block_timing", "fabgpu_sha256_segments",
     "fabgpu_bccsp_verify_batch_async", "fabgpu_bccsp_verify_batch_wait",
+    "fabgpu_validate_block_async", "fabgpu_validate_envelopes_async", "fabgpu_validate_wait", "fabgpu_block_buffer_slot",
 ]
 
 
@@ -258,11 +259,38 @@ class Context:
                                             _p(nodes), ctypes.c_int(nodes.shape[0]), _p(pbb), _p(pbo), ctypes.c_int(len(principals)),
                                             ctypes.c_char_p(channel.encode())))
 
-    def block_buffer(self, nbytes):
-        """Pinned staging buffer (numpy view) for block bytes."""
+    def block_buffer(self, nbytes, slot=0):
+        """Pinned staging buffer (numpy view) for block bytes; one per slot."""
         p = ctypes.POINTER(ctypes.c_uint8)()
-        self._ck(lib().fabgpu_block_buffer(self._h, ctypes.c_size_t(nbytes), ctypes.byref(p)))
+        self._ck(lib().fabgpu_block_buffer_slot(self._h, ctypes.c_int(slot), ctypes.c_size_t(nbytes), ctypes.byref(p)))
         return np.ctypeslib.as_array(p, shape=(nbytes,))
+
+    def validate_envelopes_async(self, slot, blob, env_off):
+        """First half of validate_envelopes on one of the FABGPU_SLOTS slots.  `blob` must stay alive and unchanged until
+        validate_wait(slot) returns (it is kept referenced here).  Returns the number of envelopes."""
+        arr = np.frombuffer(blob, np.uint8) if isinstance(blob, (bytes, bytearray)) else blob
+        env_off = np.ascontiguousarray(env_off, dtype=np.uint32)
+        n_env = env_off.shape[0] - 1
+        self._inflight = getattr(self, "_inflight", {})
+        self._inflight[slot] = (arr, env_off)
+        self._ck(lib().fabgpu_validate_envelopes_async(self._h, ctypes.c_int(slot), _p(arr), _p(env_off), ctypes.c_size_t(n_env)))
+        return n_env
+
+    def validate_block_async(self, slot, block):
+        arr = np.frombuffer(block, np.uint8) if isinstance(block, (bytes, bytearray)) else block
+        self._inflight = getattr(self, "_inflight", {})
+        self._inflight[slot] = (arr,)
+        self._ck(lib().fabgpu_validate_block_async(self._h, ctypes.c_int(slot), _p(arr), ctypes.c_size_t(arr.shape[0])))
+        return max(16, arr.shape[0] // 2)
+
+    def validate_wait(self, slot, max_tx):
+        flags = np.full(max(max_tx, 1), 254, np.uint8)
+        n = ctypes.c_size_t(0)
+        try:
+            self._ck(lib().fabgpu_validate_wait(self._h, ctypes.c_int(slot), _p(flags), ctypes.c_size_t(flags.shape[0]), ctypes.byref(n)))
+        finally:
+            getattr(self, "_inflight", {}).pop(slot, None)
+        return flags[: n.value]
 
     def validate_block(self, block, max_tx=None):
         """block: bytes or a uint8 numpy array (e.g. a slice of block_buffer()).  Returns the TRANSACTIONS_FILTER bytes."""

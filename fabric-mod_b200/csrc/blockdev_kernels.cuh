@@ -22,8 +22,9 @@ block_walk_kernel(const uint8_t* __restrict__ block, const uint32_t* __restrict_
 // One thread per signature job: identity lookup, DER / low-S gate, verify operands.
 __global__ void __launch_bounds__(64)
 block_resolve_kernel(const uint8_t* __restrict__ block, const RawJob* __restrict__ raw, uint32_t j0, uint32_t count, MspDev msp, JobArrays ja,
-                     TxDev* __restrict__ txs)
+                     TxDev* __restrict__ txs, const uint32_t* __restrict__ count_dev = nullptr)
 {
+    if (count_dev) count = min(count, *count_dev);                 // endorsement jobs: as many as the walk emitted
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;      // jobs [j0, j0 + count)
     if (i >= count) return;
     resolve_job(block, j0 + i, raw, msp, ja, txs);

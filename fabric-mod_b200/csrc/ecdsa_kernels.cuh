@@ -45,8 +45,10 @@ __global__ void build_g_table_kernel(aff* gtab)
 __global__ void __launch_bounds__(FAB_VERIFY_THREADS, FAB_VERIFY_MINBLOCKS)
 ecdsa_verify_kernel(const int32_t* __restrict__ key_slot, const uint8_t* __restrict__ qx, const uint8_t* __restrict__ qy,
                     const uint8_t* __restrict__ e, const uint8_t* __restrict__ r, const uint8_t* __restrict__ s, uint32_t n,
-                    const aff* __restrict__ gtab, uint32_t* __restrict__ mask, uint32_t* __restrict__ offcurve)
+                    const aff* __restrict__ gtab, uint32_t* __restrict__ mask, uint32_t* __restrict__ offcurve,
+                    const uint32_t* __restrict__ n_dev, uint32_t n_base)
 {
+    if (n_dev) n = min(n, n_base + *n_dev);      // batch size decided by an earlier kernel of the stream (block path): n is the launch bound
     const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t res = V_INVALID;
     if (idx < n && (key_slot == nullptr || key_slot[idx] < 0)) {
@@ -73,8 +75,9 @@ ecdsa_verify_kernel(const int32_t* __restrict__ key_slot, const uint8_t* __restr
 __global__ void __launch_bounds__(FAB_CACHED_THREADS, FAB_CACHED_MINBLOCKS)
 ecdsa_verify_cached_kernel(const int32_t* __restrict__ key_slot, const uint8_t* __restrict__ e, const uint8_t* __restrict__ r,
                            const uint8_t* __restrict__ s, uint32_t n, const aff* __restrict__ gtab, const aff* __restrict__ qtab,
-                           uint32_t* __restrict__ mask, uint32_t* __restrict__ offcurve)
+                           uint32_t* __restrict__ mask, uint32_t* __restrict__ offcurve, const uint32_t* __restrict__ n_dev, uint32_t n_base)
 {
+    if (n_dev) n = min(n, n_base + *n_dev);
     const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t res = V_INVALID;
     if (idx < n) {

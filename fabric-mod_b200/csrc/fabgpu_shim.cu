@@ -125,6 +125,7 @@ struct fabgpu_ctx {
     std::string last_error;
     std::mutex mu;         // guards enqueue/wait
     std::mutex sync_mu;    // one synchronous fabgpu_bccsp_verify_batch at a time
+    std::mutex sync_blk_mu;   // one synchronous fabgpu_validate_block / _envelopes at a time
     std::mutex slot0_mu;   // serialises the composite calls that stage through slot 0's pinned buffers
     std::atomic<unsigned long long> launches{0};
     // per-key table cache (fabgpu_keys_register): 64-byte X||Y -> slot, least-recently-used eviction
@@ -153,11 +154,9 @@ struct fabgpu_ctx {
         uint8_t *h_r = nullptr, *h_s = nullptr, *h_qx = nullptr, *h_qy = nullptr;
         int32_t *d_ks = nullptr, *h_ks = nullptr;
         uint32_t *d_mask = nullptr, *d_off = nullptr, *h_mask = nullptr;
-    } bb;
+    } bbs[FABGPU_SLOTS];          // [0] also serves the host-thread path (FABGPU_BLOCK_HOST=1)
     double block_timing[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // host phases [0..4] (see fabgpu_block_timing), device stages [5..9]
-    cudaEvent_t bev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     std::vector<uint64_t> dup_keys; std::vector<uint32_t> dup_idx;   // scratch of the duplicate-tx-id pass
-    std::vector<cudaEvent_t> chunk_ev;
     // device-side copy of the MSP view / policy (block_plan_kernel, block_decide_kernel)
     struct DevMsp {
         uint8_t *id_blob = nullptr, *valid = nullptr, *keys_xy = nullptr, *channel = nullptr;
@@ -184,7 +183,13 @@ struct fabgpu_ctx {
         *d_qy = nullptr, *d_gate = nullptr, *d_dig = nullptr, *d_flags = nullptr; int32_t *d_ks = nullptr, *d_ident = nullptr; uint32_t *d_mask = nullptr,
         *d_off = nullptr, *d_counter = nullptr; uint64_t* d_hash = nullptr; bdev::Seg* d_seg = nullptr;
         uint8_t* h_flags = nullptr; uint64_t* h_hash = nullptr; bdev::Seg* h_seg = nullptr; uint32_t* h_counter = nullptr; uint32_t* h_env_off = nullptr;
-    } db;
+        // the block in flight on this slot (fabgpu_validate_*_async .. fabgpu_validate_wait)
+        bool busy = false, on_device = false, use_ev = false; size_t T = 0; const uint8_t* block = nullptr;
+        std::vector<uint8_t> done_flags;         // host-thread path: finished at submit time
+        std::chrono::steady_clock::time_point t0, t1;
+        cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    } dbs[FABGPU_SLOTS];
+    std::mutex blk_mu[FABGPU_SLOTS];
 };
 
 namespace {
@@ -252,20 +257,22 @@ inline void stage_fence()
 //       2 = mixed (cached kernel, then the generic kernel fills in the rest)
 enum { MODE_GENERIC = 0, MODE_CACHED = 1, MODE_MIXED = 2 };
 
+// n_dev / n_base (block path): the batch is [0, min(n, n_base + *n_dev)) with *n_dev written by an earlier kernel of the stream.
 int launch_verify(fabgpu_ctx* ctx, const Device& dv, int mode, const int32_t* key_slot, const uint8_t* qx, const uint8_t* qy,
-                  const uint8_t* e, const uint8_t* r, const uint8_t* s, size_t n, uint32_t* mask, uint32_t* off, cudaStream_t st)
+                  const uint8_t* e, const uint8_t* r, const uint8_t* s, size_t n, uint32_t* mask, uint32_t* off, cudaStream_t st,
+                  const uint32_t* n_dev = nullptr, uint32_t n_base = 0)
 {
     if (n == 0) return FABGPU_OK;
     if (mode != MODE_GENERIC) {
         const unsigned blocks = (unsigned)((n + FAB_CACHED_THREADS - 1) / FAB_CACHED_THREADS);
-        ecdsa_verify_cached_kernel<<<blocks, FAB_CACHED_THREADS, 0, st>>>(key_slot, e, r, s, (uint32_t)n, dv.gtab, dv.qtab, mask, off);
+        ecdsa_verify_cached_kernel<<<blocks, FAB_CACHED_THREADS, 0, st>>>(key_slot, e, r, s, (uint32_t)n, dv.gtab, dv.qtab, mask, off, n_dev, n_base);
         ctx->launches++;
         CK(ctx, cudaGetLastError());
     }
     if (mode != MODE_CACHED) {
         const unsigned blocks = (unsigned)((n + FAB_VERIFY_THREADS - 1) / FAB_VERIFY_THREADS);
         ecdsa_verify_kernel<<<blocks, FAB_VERIFY_THREADS, 0, st>>>(mode == MODE_MIXED ? key_slot : nullptr, qx, qy, e, r, s, (uint32_t)n,
-                                                                   dv.gtab, mask, off);
+                                                                   dv.gtab, mask, off, n_dev, n_base);
         ctx->launches++;
         CK(ctx, cudaGetLastError());
     }
@@ -332,19 +339,24 @@ int wait_slot(fabgpu_ctx* ctx, int slot)
 void free_all(fabgpu_ctx* ctx)
 {
     {
-        auto& bb = ctx->bb;
         if (!ctx->devs.empty()) cudaSetDevice(ctx->devs[0].id);
-        void* dev_ptrs[] = {bb.d_block, bb.d_sha, bb.d_dig, bb.d_r, bb.d_s, bb.d_qx, bb.d_qy, bb.d_ks, bb.d_mask, bb.d_off};
-        for (void* p : dev_ptrs) if (p) cudaFree(p);
-        void* host_ptrs[] = {bb.h_block, bb.h_sha, bb.h_dig, bb.h_r, bb.h_s, bb.h_qx, bb.h_qy, bb.h_ks, bb.h_mask};
-        for (void* p : host_ptrs) if (p) cudaFreeHost(p);
-        auto& dm = ctx->dm; auto& db = ctx->db;
-        void* dev2[] = {dm.id_blob, dm.valid, dm.keys_xy, dm.channel, dm.id_off, dm.key_slot, dm.msp_code, dm.ht_idx, dm.nodes, dm.principal_code, dm.ht_hash,
-                        db.d_env_off, db.d_txs, db.d_raw, db.d_sha, db.d_r, db.d_s, db.d_qx, db.d_qy, db.d_gate, db.d_dig, db.d_flags, db.d_ks, db.d_ident, db.d_mask, db.d_off,
-                        db.d_counter, db.d_hash, db.d_seg};
+        for (auto& bb : ctx->bbs) {
+            void* dev_ptrs[] = {bb.d_block, bb.d_sha, bb.d_dig, bb.d_r, bb.d_s, bb.d_qx, bb.d_qy, bb.d_ks, bb.d_mask, bb.d_off};
+            for (void* p : dev_ptrs) if (p) cudaFree(p);
+            void* host_ptrs[] = {bb.h_block, bb.h_sha, bb.h_dig, bb.h_r, bb.h_s, bb.h_qx, bb.h_qy, bb.h_ks, bb.h_mask};
+            for (void* p : host_ptrs) if (p) cudaFreeHost(p);
+        }
+        auto& dm = ctx->dm;
+        void* dev2[] = {dm.id_blob, dm.valid, dm.keys_xy, dm.channel, dm.id_off, dm.key_slot, dm.msp_code, dm.ht_idx, dm.nodes, dm.principal_code, dm.ht_hash};
         for (void* p : dev2) if (p) cudaFree(p);
-        void* host2[] = {db.h_flags, db.h_hash, db.h_seg, db.h_counter, db.h_env_off};
-        for (void* p : host2) if (p) cudaFreeHost(p);
+        for (auto& db : ctx->dbs) {
+            void* dev4[] = {db.d_env_off, db.d_txs, db.d_raw, db.d_sha, db.d_r, db.d_s, db.d_qx, db.d_qy, db.d_gate, db.d_dig, db.d_flags, db.d_ks, db.d_ident, db.d_mask, db.d_off,
+                            db.d_counter, db.d_hash, db.d_seg};
+            for (void* p : dev4) if (p) cudaFree(p);
+            void* host2[] = {db.h_flags, db.h_hash, db.h_seg, db.h_counter, db.h_env_off};
+            for (void* p : host2) if (p) cudaFreeHost(p);
+            for (auto& e : db.ev) if (e) cudaEventDestroy(e);
+        }
         for (auto& gb : ctx->gb) {
         void* dev3[] = {gb.d_sigs, gb.d_digs, gb.d_keys, gb.d_status, gb.d_pre, gb.d_r, gb.d_s, gb.d_e, gb.d_qx, gb.d_qy, gb.d_sig_off, gb.d_dig_off, gb.d_mask, gb.d_off,
                         gb.d_kidx, gb.d_slot_of, gb.d_ks};
@@ -1107,35 +1119,33 @@ int fabgpu_msp_configure(fabgpu_ctx* ctx, const uint8_t* id_blob, const uint32_t
     return upload_msp(ctx, id_blob, id_off, keys_xy, valid, n_ids, policy_nodes, n_nodes);
 }
 
-int fabgpu_block_buffer(fabgpu_ctx* ctx, size_t bytes, uint8_t** out)
+int fabgpu_block_buffer_slot(fabgpu_ctx* ctx, int slot, size_t bytes, uint8_t** out)
 {
-    if (!ctx || !out) return FABGPU_E_ARG;
-    std::lock_guard<std::mutex> lk0(ctx->slot0_mu);
-    auto& bb = ctx->bb;
+    if (!ctx || !out || slot < 0 || slot >= FABGPU_SLOTS) return FABGPU_E_ARG;
+    std::lock_guard<std::mutex> lk(ctx->blk_mu[slot]);
+    auto& bb = ctx->bbs[slot];
     CK(ctx, cudaSetDevice(ctx->devs[0].id));
-    if (bytes > bb.h_block_cap) { int rc = grow_host(ctx, bb.h_block, bytes); if (rc) return rc; bb.h_block_cap = bytes; }
+    if (bytes > bb.h_block_cap) {
+        if (ctx->dbs[slot].busy) { ctx->last_error = "slot holds a block in flight"; return FABGPU_E_ARG; }
+        int rc = grow_host(ctx, bb.h_block, bytes); if (rc) return rc; bb.h_block_cap = bytes;
+    }
     *out = bb.h_block;
     return FABGPU_OK;
 }
-
-static int validate_impl(fabgpu_ctx* ctx, const uint8_t* block, size_t block_len, const uint32_t* env_off, size_t n_env, uint8_t* flags,
-                         size_t flags_cap, size_t* n_tx_out);
+int fabgpu_block_buffer(fabgpu_ctx* ctx, size_t bytes, uint8_t** out) { return fabgpu_block_buffer_slot(ctx, 0, bytes, out); }
 
 // Device path of the block pre-pass: the host only copies bytes in and flags out (and marks duplicate tx ids).
 //   H2D block + envelope offsets -> block_walk_kernel (per transaction) -> block_resolve_kernel (per signature: identity lookup, DER gates)
 //   -> sha256_segments_kernel (signed messages + check digests) -> one verify launch -> block_decide_kernel -> D2H flags.
-static int validate_device(fabgpu_ctx* ctx, const uint8_t* block, size_t block_len, const uint32_t* env_off, size_t n_env, uint8_t* flags,
-                           size_t flags_cap, size_t* n_tx_out)
+// Everything is enqueued on the slot's stream in one go: the number of endorsement jobs (known only after the walk) stays
+// on the device -- the later launches are sized for the worst case and read the count themselves.
+static int block_submit(fabgpu_ctx* ctx, int slot, const uint8_t* block, size_t block_len, const uint32_t* env_off, size_t n_env)
 {
-    std::lock_guard<std::mutex> lk0(ctx->slot0_mu);
     auto now = [] { return std::chrono::steady_clock::now(); };
-    auto us = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
-        return std::chrono::duration<double, std::micro>(b - a).count();
-    };
-    auto t0 = now();
     Device& dv = ctx->devs[0];
-    DevSlot& ds = dv.slot[0];
-    auto& bb = ctx->bb; auto& db = ctx->db; auto& dm = ctx->dm;
+    DevSlot& ds = dv.slot[slot];
+    auto& bb = ctx->bbs[slot]; auto& db = ctx->dbs[slot]; auto& dm = ctx->dm;
+    db.t0 = now();
     CK(ctx, cudaSetDevice(dv.id));
     {   // identities' key tables may have been recycled by other registrations since fabgpu_msp_configure: re-issue them
         bool stale = false;
@@ -1145,7 +1155,7 @@ static int validate_device(fabgpu_ctx* ctx, const uint8_t* block, size_t block_l
         }
         if (stale) {
             const int n_ids = (int)ctx->identity_slot.size();
-            int rc = fabgpu_keys_register(ctx, ctx->msp.keys_xy.data(), n_ids, ctx->identity_slot.data());
+            int rc = fabgpu_keys_register(ctx, ctx->msp.keys_xy.data(), n_ids, ctx->identity_slot.data());     // drains every stream first
             if (rc) return rc;
             std::vector<int32_t> raw(n_ids, -1);
             dm.all_slots = true;
@@ -1155,23 +1165,20 @@ static int validate_device(fabgpu_ctx* ctx, const uint8_t* block, size_t block_l
     }
     if (block_len > bb.block_cap) { int rc = grow_dev(ctx, bb.d_block, block_len + (block_len >> 2)); if (rc) return rc; bb.block_cap = block_len + (block_len >> 2); }
     const char* evs = getenv("FABGPU_BLOCK_EVENTS");          // "1": time the device stages with CUDA events (diagnostics)
-    const bool use_ev = evs && evs[0] == '1';
-    if (use_ev) for (auto& e : ctx->bev) if (!e) CK(ctx, cudaEventCreate(&e));
-    if (use_ev) CK(ctx, cudaEventRecord(ctx->bev[0], ds.stream));
+    db.use_ev = evs && evs[0] == '1';
+    if (db.use_ev) for (auto& e : db.ev) if (!e) CK(ctx, cudaEventCreate(&e));
+    if (db.use_ev) CK(ctx, cudaEventRecord(db.ev[0], ds.stream));
     std::vector<uint32_t> split;
     if (!env_off) {                                           // serialized common.Block: find the envelopes (serial, length-prefixed)
         std::vector<blockval::Seg> envs;
-        if (!blockval::split_block(block, block_len, envs)) { cudaStreamSynchronize(ds.stream); ctx->last_error = "block does not parse"; return FABGPU_E_ARG; }
-        // envelopes of a Block are not contiguous (each carries a field header): pass (offset, length) pairs as 2 T + ... -> use an offsets
-        // table with explicit ends by giving every envelope its own [off, off+len) through a doubled table
+        if (!blockval::split_block(block, block_len, envs)) { ctx->last_error = "block does not parse"; return FABGPU_E_ARG; }
         n_env = envs.size();
         split.resize(2 * n_env + 2);
         for (size_t i = 0; i < n_env; i++) { split[2 * i] = envs[i].off; split[2 * i + 1] = envs[i].off + envs[i].len; }
     }
     const size_t T = n_env;
-    *n_tx_out = T;
-    if (T > flags_cap) { cudaStreamSynchronize(ds.stream); ctx->last_error = "flags buffer too small"; return FABGPU_E_ARG; }
-    if (T == 0) { CK(ctx, cudaStreamSynchronize(ds.stream)); return FABGPU_OK; }
+    db.T = T; db.block = block;
+    if (T == 0) return FABGPU_OK;
     const size_t J_cap = T * (1 + BD_MAX_ENDS);
     if (T > db.tx_cap) {
         const size_t tc = T + (T >> 2) + 256, jc = tc * (1 + BD_MAX_ENDS);
@@ -1193,73 +1200,65 @@ static int validate_device(fabgpu_ctx* ctx, const uint8_t* block, size_t block_l
         db.h_env_off[2 * i] = env_off ? env_off[i] : split[2 * i];
         db.h_env_off[2 * i + 1] = env_off ? env_off[i + 1] : split[2 * i + 1];
     }
-    CK(ctx, cudaMemcpyAsync(db.d_env_off, db.h_env_off, 8 * T, cudaMemcpyHostToDevice, ds.stream));
-    CK(ctx, cudaMemsetAsync(db.d_counter, 0, 16, ds.stream));
-    auto t1 = now();
+    cudaStream_t st = ds.stream;
+    CK(ctx, cudaMemcpyAsync(db.d_env_off, db.h_env_off, 8 * T, cudaMemcpyHostToDevice, st));
+    CK(ctx, cudaMemsetAsync(db.d_counter, 0, 16, st));
     bdev::MspDev m; m.id_blob = dm.id_blob; m.id_off = dm.id_off; m.key_slot = dm.key_slot; m.valid = dm.valid; m.msp_code = dm.msp_code;
     m.keys_xy = dm.keys_xy; m.ht_hash = dm.ht_hash; m.ht_idx = dm.ht_idx; m.ht_size = dm.ht_size; m.n_ids = dm.n_ids;
     bdev::PolicyDev pol; pol.nodes = dm.nodes; pol.n_nodes = dm.n_nodes; pol.principal_code = dm.principal_code; pol.n_principals = dm.n_principals;
     bdev::JobArrays ja; ja.sha = db.d_sha; ja.r = db.d_r; ja.s = db.d_s; ja.key_slot = db.d_ks; ja.identity = db.d_ident; ja.qx = dm.all_slots ? nullptr : db.d_qx;
     ja.qy = dm.all_slots ? nullptr : db.d_qy; ja.gate_ok = db.d_gate; ja.J_cap = (uint32_t)J_cap; ja.T = (uint32_t)T;
-    const unsigned tb = (unsigned)((T + 127) / 128);
-    // The block can be copied in chunks on a second stream (FABGPU_BLOCK_CHUNKS), each chunk's walk / creator resolve /
-    // SHA-256 starting as soon as its bytes have landed.  Measured on B200: NOT a win (1 chunk 1.93 ms, 4 chunks 2.27 ms,
-    // 8 chunks 3.52 ms per 10k-tx block) -- hashing a 4.6 KB payload is ~250 us of dependent rounds per thread however few
-    // threads a launch has, so per-chunk launches serialise that latency instead of hiding it.  Default: one chunk.
-    // Endorsement jobs are numbered through one counter, known only after the last walk.
-    cudaStream_t cs = dv.slot[1].stream;                      // copy stream
-    const char* ce = getenv("FABGPU_BLOCK_CHUNKS");
-    size_t chunks = ce ? (size_t)std::max(1, atoi(ce)) : 1;
-    if (chunks > 16) chunks = 16;
-    while (ctx->chunk_ev.size() < chunks) { cudaEvent_t e; CK(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); ctx->chunk_ev.push_back(e); }
-    CK(ctx, cudaEventRecord(ctx->chunk_ev[0], ds.stream));    // the env table / counter reset above precede everything
-    CK(ctx, cudaStreamWaitEvent(cs, ctx->chunk_ev[0], 0));
-    for (size_t c = 0; c < chunks; c++) {
-        const size_t lo = T * c / chunks, hi = T * (c + 1) / chunks;
-        if (hi == lo) continue;
-        const size_t b_lo = (c == 0) ? 0 : db.h_env_off[2 * lo], b_hi = (c + 1 == chunks) ? block_len : db.h_env_off[2 * hi];
-        CK(ctx, cudaMemcpyAsync(bb.d_block + b_lo, block + b_lo, b_hi - b_lo, cudaMemcpyHostToDevice, cs));
-        CK(ctx, cudaEventRecord(ctx->chunk_ev[c], cs));
-        CK(ctx, cudaStreamWaitEvent(ds.stream, ctx->chunk_ev[c], 0));
-        const uint32_t cnt = (uint32_t)(hi - lo);
-        bdev::block_walk_kernel<<<(cnt + 31) / 32, 32, 0, ds.stream>>>(bb.d_block, db.d_env_off, (uint32_t)lo, cnt, (uint32_t)T, dm.channel, dm.channel_len,
-                                                                    db.d_txs, db.d_raw, ja, db.d_counter);
-        bdev::block_resolve_kernel<<<(cnt + 63) / 64, 64, 0, ds.stream>>>(bb.d_block, db.d_raw, (uint32_t)lo, cnt, m, ja, db.d_txs);      // creator jobs
-        sha256_segments_kernel<<<(cnt + 127) / 128, 128, 0, ds.stream>>>(bb.d_block, reinterpret_cast<const ShaJob*>(db.d_sha) + lo, cnt, db.d_dig + 32 * lo);
-        sha256_segments_kernel<<<(2 * cnt + 127) / 128, 128, 0, ds.stream>>>(bb.d_block, reinterpret_cast<const ShaJob*>(db.d_sha + J_cap) + 2 * lo, 2 * cnt,
-                                                                          db.d_dig + 32 * (J_cap + 2 * lo));
-        ctx->launches += 4;
-        CK(ctx, cudaGetLastError());
-    }
-    if (use_ev) CK(ctx, cudaEventRecord(ctx->bev[1], ds.stream));
-    if (use_ev) CK(ctx, cudaEventRecord(ctx->bev[2], ds.stream));
-    CK(ctx, cudaMemcpyAsync(db.h_counter, db.d_counter, 4, cudaMemcpyDeviceToHost, ds.stream));
-    CK(ctx, cudaStreamSynchronize(ds.stream));
-    const size_t n_end = std::min((size_t)db.h_counter[0], J_cap - T);
-    const size_t J = T + n_end;
-    auto t2 = now();
-    if (n_end) {                                              // endorsement jobs [T, T + n_end)
-        bdev::block_resolve_kernel<<<(unsigned)((n_end + 63) / 64), 64, 0, ds.stream>>>(bb.d_block, db.d_raw, (uint32_t)T, (uint32_t)n_end, m, ja, db.d_txs);
-        sha256_segments_kernel<<<(unsigned)((n_end + 127) / 128), 128, 0, ds.stream>>>(bb.d_block, reinterpret_cast<const ShaJob*>(db.d_sha) + T, (uint32_t)n_end,
-                                                                                     db.d_dig + 32 * T);
-        ctx->launches += 2;
-        CK(ctx, cudaGetLastError());
-    }
-    if (use_ev) CK(ctx, cudaEventRecord(ctx->bev[3], ds.stream));
-    int rc = launch_verify(ctx, dv, dm.all_slots ? MODE_CACHED : MODE_MIXED, db.d_ks, db.d_qx, db.d_qy, db.d_dig, db.d_r, db.d_s, J, db.d_mask, db.d_off, ds.stream);
+    const uint32_t cnt = (uint32_t)T, E_cap = (uint32_t)(J_cap - T);
+    // One copy, then the walk.  (Copying in chunks with a walk per chunk was measured slower on B200 -- 1 chunk 1.93 ms, 4 chunks
+    // 2.27 ms, 8 chunks 3.52 ms per 10k-tx block: hashing a 4.6 KB payload is ~250 us of dependent rounds per thread however few
+    // threads a launch has, so per-chunk launches serialise that latency.  What hides the copy is the NEXT block's copy running
+    // under this block's kernels: the two slots.)
+    CK(ctx, cudaMemcpyAsync(bb.d_block, block, block_len, cudaMemcpyHostToDevice, st));
+    bdev::block_walk_kernel<<<(cnt + 31) / 32, 32, 0, st>>>(bb.d_block, db.d_env_off, 0u, cnt, cnt, dm.channel, dm.channel_len, db.d_txs, db.d_raw, ja, db.d_counter);
+    bdev::block_resolve_kernel<<<(cnt + 63) / 64, 64, 0, st>>>(bb.d_block, db.d_raw, 0u, cnt, m, ja, db.d_txs);                      // creator jobs
+    sha256_segments_kernel<<<(cnt + 127) / 128, 128, 0, st>>>(bb.d_block, reinterpret_cast<const ShaJob*>(db.d_sha), cnt, db.d_dig);
+    sha256_segments_kernel<<<(2 * cnt + 127) / 128, 128, 0, st>>>(bb.d_block, reinterpret_cast<const ShaJob*>(db.d_sha + J_cap), 2 * cnt, db.d_dig + 32 * J_cap);
+    ctx->launches += 4;
+    CK(ctx, cudaGetLastError());
+    if (db.use_ev) CK(ctx, cudaEventRecord(db.ev[1], st));
+    if (db.use_ev) CK(ctx, cudaEventRecord(db.ev[2], st));
+    // endorsement jobs [T, T + *d_counter): launches sized for the worst case, the kernels stop at the device-side count
+    bdev::block_resolve_kernel<<<(E_cap + 63) / 64, 64, 0, st>>>(bb.d_block, db.d_raw, cnt, E_cap, m, ja, db.d_txs, db.d_counter);
+    sha256_segments_kernel<<<(E_cap + 127) / 128, 128, 0, st>>>(bb.d_block, reinterpret_cast<const ShaJob*>(db.d_sha) + T, E_cap, db.d_dig + 32 * T, db.d_counter);
+    ctx->launches += 2;
+    CK(ctx, cudaGetLastError());
+    if (db.use_ev) CK(ctx, cudaEventRecord(db.ev[3], st));
+    int rc = launch_verify(ctx, dv, dm.all_slots ? MODE_CACHED : MODE_MIXED, db.d_ks, db.d_qx, db.d_qy, db.d_dig, db.d_r, db.d_s, J_cap, db.d_mask, db.d_off, st,
+                           db.d_counter, cnt);
     if (rc) return rc;
-    if (use_ev) CK(ctx, cudaEventRecord(ctx->bev[4], ds.stream));
-    bdev::block_decide_kernel<<<tb, 128, 0, ds.stream>>>(bb.d_block, db.d_txs, (uint32_t)T, m, pol, db.d_mask, db.d_gate, db.d_dig, (uint32_t)J_cap, db.d_flags,
-                                                         db.d_hash, db.d_seg);
+    if (db.use_ev) CK(ctx, cudaEventRecord(db.ev[4], st));
+    bdev::block_decide_kernel<<<(cnt + 127) / 128, 128, 0, st>>>(bb.d_block, db.d_txs, cnt, m, pol, db.d_mask, db.d_gate, db.d_dig, (uint32_t)J_cap, db.d_flags,
+                                                               db.d_hash, db.d_seg);
     ctx->launches++;
     CK(ctx, cudaGetLastError());
-    if (use_ev) CK(ctx, cudaEventRecord(ctx->bev[5], ds.stream));
-    CK(ctx, cudaMemcpyAsync(db.h_flags, db.d_flags, T, cudaMemcpyDeviceToHost, ds.stream));
-    CK(ctx, cudaMemcpyAsync(db.h_hash, db.d_hash, 8 * T, cudaMemcpyDeviceToHost, ds.stream));
-    CK(ctx, cudaMemcpyAsync(db.h_seg, db.d_seg, 8 * T, cudaMemcpyDeviceToHost, ds.stream));
-    CK(ctx, cudaStreamSynchronize(ds.stream));
+    if (db.use_ev) CK(ctx, cudaEventRecord(db.ev[5], st));
+    CK(ctx, cudaMemcpyAsync(db.h_flags, db.d_flags, T, cudaMemcpyDeviceToHost, st));
+    CK(ctx, cudaMemcpyAsync(db.h_hash, db.d_hash, 8 * T, cudaMemcpyDeviceToHost, st));
+    CK(ctx, cudaMemcpyAsync(db.h_seg, db.d_seg, 8 * T, cudaMemcpyDeviceToHost, st));
+    db.t1 = now();
+    return FABGPU_OK;
+}
+
+// Waits for the slot's block and finishes on the host: markTXIdDuplicates (v20/validator.go:283-297) -- among VALID
+// transactions, a later one with an already seen tx id.  Reads the caller's block bytes to confirm equal hashes.
+static int block_finish(fabgpu_ctx* ctx, int slot, uint8_t* flags)
+{
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto us = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+        return std::chrono::duration<double, std::micro>(b - a).count();
+    };
+    auto& db = ctx->dbs[slot];
+    const size_t T = db.T;
+    const uint8_t* block = db.block;
+    CK(ctx, cudaSetDevice(ctx->devs[0].id));
+    CK(ctx, cudaStreamSynchronize(ctx->devs[0].slot[slot].stream));
     auto t3 = now();
-    // markTXIdDuplicates (v20/validator.go:283-297) on the host: among VALID transactions, a later one with an already seen tx id
+    if (T == 0) return FABGPU_OK;
     memcpy(flags, db.h_flags, T);
     {
         // flat open-addressing table keyed by the 64-bit tx-id hash (0 = empty); equal hashes are confirmed on the bytes
@@ -1283,35 +1282,104 @@ static int validate_device(fabgpu_ctx* ctx, const uint8_t* block, size_t block_l
         }
     }
     auto t4 = now();
-    ctx->block_timing[0] = us(t0, t1); ctx->block_timing[1] = us(t1, t2); ctx->block_timing[2] = us(t2, t3); ctx->block_timing[3] = us(t3, t4);
-    ctx->block_timing[4] = us(t0, t4);
-    for (int k = 0; k < 5; k++) { float ms = 0; if (use_ev) cudaEventElapsedTime(&ms, ctx->bev[k], ctx->bev[k + 1]); ctx->block_timing[5 + k] = 1e3 * ms; }
+    ctx->block_timing[0] = us(db.t0, db.t1); ctx->block_timing[1] = 0; ctx->block_timing[2] = us(db.t1, t3); ctx->block_timing[3] = us(t3, t4);
+    ctx->block_timing[4] = us(db.t0, t4);
+    for (int k = 0; k < 5; k++) { float ms = 0; if (db.use_ev) cudaEventElapsedTime(&ms, db.ev[k], db.ev[k + 1]); ctx->block_timing[5 + k] = 1e3 * ms; }
     return FABGPU_OK;
 }
 
+static int validate_host(fabgpu_ctx* ctx, const uint8_t* block, size_t block_len, const uint32_t* env_off, size_t n_env, uint8_t* flags,
+                         size_t flags_cap, size_t* n_tx_out);
+
+// serialized: 1 = `block` is a serialized common.Block (env_off unused), 0 = concatenated envelopes with an offset table
+static int validate_submit(fabgpu_ctx* ctx, int slot, const uint8_t* block, size_t block_len, const uint32_t* env_off, size_t n_env)
+{
+    if (!ctx || !block || slot < 0 || slot >= FABGPU_SLOTS) return FABGPU_E_ARG;
+    if (block_len >= (1ull << 32)) { ctx->last_error = "block larger than 4 GiB"; return FABGPU_E_ARG; }
+    std::lock_guard<std::mutex> lk(ctx->blk_mu[slot]);
+    auto& db = ctx->dbs[slot];
+    if (db.busy) { ctx->last_error = "slot already holds a block: call fabgpu_validate_wait first"; return FABGPU_E_ARG; }
+    if (fault_injected()) { ctx->last_error = "fault injected (FABGPU_FAULT_INJECT=1)"; return FABGPU_E_INJECTED; }
+    const char* hp = getenv("FABGPU_BLOCK_HOST");            // "1": parse / gate / decide on host threads (blockval.cpp) instead of on the device
+    int rc;
+    if (hp && hp[0] == '1') {
+        // the host-thread path is synchronous: it completes here and _wait only hands the flags out
+        if (slot != 0 && ctx->dbs[0].busy) { ctx->last_error = "the host-thread path shares slot 0's buffers: wait for slot 0 first"; return FABGPU_E_ARG; }
+        size_t cap = env_off ? n_env : block_len / 2 + 16, n_tx = 0;      // an envelope entry of a Block is at least two bytes
+        db.done_flags.assign(cap ? cap : 1, 0);
+        rc = validate_host(ctx, block, block_len, env_off, n_env, db.done_flags.data(), db.done_flags.size(), &n_tx);
+        if (rc) return rc;
+        db.T = n_tx; db.on_device = false;
+    } else {
+        std::lock_guard<std::mutex> lk0(ctx->slot0_mu);      // key-cache / MSP state: one submitter at a time
+        rc = block_submit(ctx, slot, block, block_len, env_off, n_env);
+        if (rc) { cudaStreamSynchronize(ctx->devs[0].slot[slot].stream); return rc; }
+        db.on_device = true;
+    }
+    db.busy = true;
+    return FABGPU_OK;
+}
+
+int fabgpu_validate_block_async(fabgpu_ctx* ctx, int slot, const uint8_t* block, size_t block_len)
+{
+    return validate_submit(ctx, slot, block, block_len, nullptr, 0);
+}
+
+int fabgpu_validate_envelopes_async(fabgpu_ctx* ctx, int slot, const uint8_t* blob, const uint32_t* env_off, size_t n_env)
+{
+    if (!env_off && n_env) return FABGPU_E_ARG;
+    if (n_env == 0) {                                         // nothing to do, but keep the slot protocol
+        if (!ctx || slot < 0 || slot >= FABGPU_SLOTS) return FABGPU_E_ARG;
+        std::lock_guard<std::mutex> lk(ctx->blk_mu[slot]);
+        auto& db = ctx->dbs[slot];
+        if (db.busy) { ctx->last_error = "slot already holds a block: call fabgpu_validate_wait first"; return FABGPU_E_ARG; }
+        db.T = 0; db.on_device = false; db.done_flags.clear(); db.busy = true;
+        return FABGPU_OK;
+    }
+    return validate_submit(ctx, slot, blob, env_off[n_env], env_off, n_env);
+}
+
+int fabgpu_validate_wait(fabgpu_ctx* ctx, int slot, uint8_t* flags, size_t flags_cap, size_t* n_tx_out)
+{
+    if (!ctx || slot < 0 || slot >= FABGPU_SLOTS || !n_tx_out) return FABGPU_E_ARG;
+    std::lock_guard<std::mutex> lk(ctx->blk_mu[slot]);
+    auto& db = ctx->dbs[slot];
+    if (!db.busy) { ctx->last_error = "no block in flight on this slot"; return FABGPU_E_ARG; }
+    db.busy = false;
+    *n_tx_out = db.T;
+    if (db.T > flags_cap || (db.T && !flags)) {
+        if (db.on_device) cudaStreamSynchronize(ctx->devs[0].slot[slot].stream);
+        ctx->last_error = "flags buffer too small";
+        return FABGPU_E_ARG;
+    }
+    if (db.on_device) return block_finish(ctx, slot, flags);
+    if (db.T) memcpy(flags, db.done_flags.data(), db.T);
+    return FABGPU_OK;
+}
 
 int fabgpu_validate_block(fabgpu_ctx* ctx, const uint8_t* block, size_t block_len, uint8_t* flags, size_t flags_cap, size_t* n_tx_out)
 {
-    return validate_impl(ctx, block, block_len, nullptr, 0, flags, flags_cap, n_tx_out);
+    if (!ctx || !block || !flags || !n_tx_out) return FABGPU_E_ARG;
+    std::lock_guard<std::mutex> lk(ctx->sync_blk_mu);
+    int rc = fabgpu_validate_block_async(ctx, 0, block, block_len);
+    if (rc) return rc;
+    return fabgpu_validate_wait(ctx, 0, flags, flags_cap, n_tx_out);
 }
 
 int fabgpu_validate_envelopes(fabgpu_ctx* ctx, const uint8_t* blob, const uint32_t* env_off, size_t n_env, uint8_t* flags, size_t flags_cap,
                               size_t* n_tx_out)
 {
-    if (!env_off) return FABGPU_E_ARG;
-    return validate_impl(ctx, blob, env_off[n_env], env_off, n_env, flags, flags_cap, n_tx_out);
+    if (!ctx || !blob || !env_off || !flags || !n_tx_out) return FABGPU_E_ARG;
+    std::lock_guard<std::mutex> lk(ctx->sync_blk_mu);
+    int rc = fabgpu_validate_envelopes_async(ctx, 0, blob, env_off, n_env);
+    if (rc) return rc;
+    return fabgpu_validate_wait(ctx, 0, flags, flags_cap, n_tx_out);
 }
 
-static int validate_impl(fabgpu_ctx* ctx, const uint8_t* block, size_t block_len, const uint32_t* env_off, size_t n_env, uint8_t* flags,
+// Host-thread form of the pre-pass (FABGPU_BLOCK_HOST=1): blockval.cpp walks / gates / decides, the GPU hashes and verifies.
+static int validate_host(fabgpu_ctx* ctx, const uint8_t* block, size_t block_len, const uint32_t* env_off, size_t n_env, uint8_t* flags,
                          size_t flags_cap, size_t* n_tx_out)
 {
-    if (!ctx || !block || !flags || !n_tx_out) return FABGPU_E_ARG;
-    if (block_len >= (1ull << 32)) { ctx->last_error = "block larger than 4 GiB"; return FABGPU_E_ARG; }
-    if (fault_injected()) { ctx->last_error = "fault injected (FABGPU_FAULT_INJECT=1)"; return FABGPU_E_INJECTED; }
-    {
-        const char* hp = getenv("FABGPU_BLOCK_HOST");            // "1": parse / gate / decide on host threads (blockval.cpp) instead of on the device
-        if (!(hp && hp[0] == '1')) return validate_device(ctx, block, block_len, env_off, n_env, flags, flags_cap, n_tx_out);
-    }
     std::lock_guard<std::mutex> lk0(ctx->slot0_mu);
     auto now = [] { return std::chrono::steady_clock::now(); };
     auto us = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
@@ -1320,7 +1388,7 @@ static int validate_impl(fabgpu_ctx* ctx, const uint8_t* block, size_t block_len
     auto t0 = now();
     Device& dv = ctx->devs[0];
     DevSlot& ds = dv.slot[0];
-    auto& bb = ctx->bb;
+    auto& bb = ctx->bbs[0];
     CK(ctx, cudaSetDevice(dv.id));
     // 1. the block goes to the device while the host parses it
     if (block_len > bb.block_cap) { int rc = grow_dev(ctx, bb.d_block, block_len + (block_len >> 2)); if (rc) return rc; bb.block_cap = block_len + (block_len >> 2); }

@@ -69,8 +69,10 @@ __device__ __forceinline__ uint32_t sha_msg_byte(const uint8_t* __restrict__ buf
 // ranges or contain padding are assembled byte by byte (at most three or four per message).
 // `buf` must be readable 4 bytes past the last range (the block buffer is allocated with slack).
 __global__ void __launch_bounds__(128)
-sha256_segments_kernel(const uint8_t* __restrict__ buf, const ShaJob* __restrict__ jobs, uint32_t n, uint8_t* __restrict__ digests)
+sha256_segments_kernel(const uint8_t* __restrict__ buf, const ShaJob* __restrict__ jobs, uint32_t n, uint8_t* __restrict__ digests,
+                       const uint32_t* __restrict__ n_dev = nullptr)
 {
+    if (n_dev) n = min(n, *n_dev);               // message count produced by an earlier kernel of the stream; n is the launch bound
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
     const ShaJob job = jobs[j];

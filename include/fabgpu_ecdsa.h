@@ -170,12 +170,21 @@ int fabgpu_validate_block(fabgpu_ctx* ctx, const uint8_t* block, size_t block_le
  * concatenation, env_off the (n_env+1)-entry offset table.  Saves the serial walk over the length-prefixed envelopes. */
 int fabgpu_validate_envelopes(fabgpu_ctx* ctx, const uint8_t* blob, const uint32_t* env_off, size_t n_env, uint8_t* flags, size_t flags_cap,
                               size_t* n_tx_out);
-/* Optional pinned staging buffer for the block bytes (the H2D copy of a pageable buffer is several times slower). */
-int fabgpu_block_buffer(fabgpu_ctx* ctx, size_t bytes, uint8_t** out);
-/* Times of the last fabgpu_validate_block / _envelopes, microseconds.  [0..4] host wall clock: enqueue, wait for copy + plan
- * kernel, wait for digests + verification + decisions, duplicate-tx-id pass, total.  [5..9] CUDA-event times of the device
- * stages (FABGPU_BLOCK_EVENTS=1): chunked H2D overlapped with walk / creator resolve / SHA-256, (unused), endorsement
- * resolve + SHA-256, verify kernel(s), block_decide_kernel. */
+/* Both calls in two halves over the FABGPU_SLOTS slots, for a committer that keeps two blocks in flight: _async enqueues
+ * the copy and every kernel of the block on the slot's stream and returns; fabgpu_validate_wait blocks until the slot's
+ * block is done, runs the duplicate-tx-id pass and writes the flags.  The block bytes must stay valid and unchanged until
+ * the wait returns (they are copied by DMA and read again by the duplicate pass).  While the GPU works on block k, the
+ * copy of block k+1 proceeds: the PCIe transfer (the largest single phase of a block) is hidden across blocks.
+ * fabgpu_validate_block / _envelopes are _async + _wait on slot 0. */
+int fabgpu_validate_block_async(fabgpu_ctx* ctx, int slot, const uint8_t* block, size_t block_len);
+int fabgpu_validate_envelopes_async(fabgpu_ctx* ctx, int slot, const uint8_t* blob, const uint32_t* env_off, size_t n_env);
+int fabgpu_validate_wait(fabgpu_ctx* ctx, int slot, uint8_t* flags, size_t flags_cap, size_t* n_tx_out);
+/* Optional pinned staging buffer for the block bytes (the H2D copy of a pageable buffer is several times slower); one per slot. */
+int fabgpu_block_buffer(fabgpu_ctx* ctx, size_t bytes, uint8_t** out);                      /* slot 0 */
+int fabgpu_block_buffer_slot(fabgpu_ctx* ctx, int slot, size_t bytes, uint8_t** out);
+/* Times of the last completed block, microseconds.  [0..4] host wall clock: enqueue, (unused), wait for the device,
+ * duplicate-tx-id pass, total from submit to flags.  [5..9] CUDA-event times of the device stages (FABGPU_BLOCK_EVENTS=1):
+ * H2D + walk + creator resolve + SHA-256, (unused), endorsement resolve + SHA-256, verify kernel(s), block_decide_kernel. */
 int fabgpu_block_timing(const fabgpu_ctx* ctx, double out_us[10]);
 /* Device SHA-256 of messages given as up to three byte ranges of `buf` each: jobs = n x {off0,off1,off2,len0,len1,len2}
  * (uint32); digests = n x 32 bytes.  (The hash msp identity.Verify computes first: msp/identities.go:178.) */

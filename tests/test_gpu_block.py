@@ -116,3 +116,39 @@ def test_block_survives_key_table_eviction():
     finally:
         del os.environ["FABGPU_BLOCK_HOST"]
     c.close()
+
+
+def test_two_blocks_in_flight(ctx):
+    """fabgpu_validate_*_async / fabgpu_validate_wait: two different blocks on the two slots at once, several rounds, both entry
+    forms; each slot returns the oracle's flags for ITS block (separate device buffers, counters and pinned staging per slot)."""
+    net = blockgen.Network(n_orgs=4, n_clients=3)
+    ids = blockutil.identities_of(net)
+    _configure(ctx, net, 3)
+    blocks = []
+    for k, (ntx, nfault, seed) in enumerate([(900, 120, 31), (333, 60, 32)]):
+        rnd = random.Random(seed)
+        faults = {t: rnd.choice(blockgen.FAULTS) for t in rnd.sample(range(1, ntx), nfault)}
+        blk, info = blockgen.build_block(net, ntx, 3, faults, seed=seed)
+        exp = ob.validate_block(blk, ids, net.channel, net.policy_n_of(3), net.principals)
+        blob = np.frombuffer(info["env_blob"], np.uint8)
+        pinned = ctx.block_buffer(blob.shape[0], slot=k)
+        pinned[:] = blob
+        blocks.append((blk, pinned, info["env_off"], exp))
+    binding = pkg().binding
+    for rnd_i in range(4):
+        order = (0, 1) if rnd_i % 2 == 0 else (1, 0)
+        caps = {}
+        for sl in order:
+            blk, pinned, eoff, _ = blocks[sl]
+            caps[sl] = ctx.validate_envelopes_async(sl, pinned, eoff) if rnd_i < 2 else ctx.validate_block_async(sl, blk)
+        with pytest.raises(binding.FabGpuError):                              # a slot holds one block at a time
+            ctx.validate_envelopes_async(0, blocks[0][1], blocks[0][2])
+        for sl in order:
+            got = ctx.validate_wait(sl, caps[sl])
+            assert got.tolist() == blocks[sl][3].tolist(), (rnd_i, sl)
+    with pytest.raises(binding.FabGpuError):                                  # nothing in flight
+        ctx.validate_wait(1, 16)
+    # the blocking calls still work afterwards, and an empty envelope list goes through both halves
+    assert ctx.validate_envelopes(blocks[1][1], blocks[1][2]).tolist() == blocks[1][3].tolist()
+    assert ctx.validate_envelopes_async(1, np.zeros(1, np.uint8), np.zeros(1, np.uint32)) == 0
+    assert ctx.validate_wait(1, 1).shape[0] == 0
