@@ -238,6 +238,31 @@ def run_gpu(args):
     launches = ctx.launch_count() - launches0
     dev_ms = sum(a.elapsed_time(b) for a, b in ev)
     assert bool((full == -1).all())
+    # The same kernel with several batches in flight (one stream per batch, inputs resident, no flush): a 64k batch is 512 CTAs
+    # on 592 resident CTA slots, so a launch on its own leaves part of the machine idle in its tail; concurrent streams fill it.
+    # This is the regime the pipelined end-to-end call runs in, and why e2e can exceed the one-batch-at-a-time `value`.
+    cstreams = [torch.cuda.Stream(device=dev) for _ in range(pkg.binding.SLOTS)]
+    cmasks = [torch.zeros(words, dtype=torch.int32, device=dev) for _ in cstreams]
+    csteps = max(len(cstreams), args.steps)
+    def cstep(k):
+        t = bufs[k % ROT]
+        ctx.verify_p256_device_keyed(True, kslots[k % ROT].data_ptr(), 0, 0, t[2].data_ptr(), t[3].data_ptr(), t[4].data_ptr(), B,
+                                     cmasks[k % len(cstreams)].data_ptr(), 0, cstreams[k % len(cstreams)].cuda_stream)
+    for k in range(len(cstreams)):
+        cstep(k)
+    sync_all()
+    c0 = torch.cuda.Event(enable_timing=True)
+    cends = [torch.cuda.Event(enable_timing=True) for _ in cstreams]
+    c0.record(stream)
+    for cs in cstreams:
+        cs.wait_event(c0)
+    for k in range(csteps):
+        cstep(k)
+    for cs, e in zip(cstreams, cends):
+        e.record(cs)
+    sync_all()
+    conc_ms = max(c0.elapsed_time(e) for e in cends)
+    assert all(bool((m == -1).all()) for m in cmasks)
     # generic kernel (no key tables), same hygiene, fewer steps
     gsteps = max(3, min(args.steps, 10))
     for k in range(2):
@@ -254,7 +279,7 @@ def run_gpu(args):
     assert bool((full == -1).all())
 
     # ---- end-to-end leg: raw DER + digests + keys in host memory through the bccsp-level C-ABI call ----------
-    # Headline form: the two halves of the call (fabgpu_bccsp_verify_batch_async / _wait) on alternating slots, two batches
+    # Headline form: the two halves of the call (fabgpu_bccsp_verify_batch_async / _wait) round-robin over the slots, one batch per slot
     # in flight -- every step still stages its host buffers, copies them H2D, runs gate + verify + status kernels and reads the
     # status bytes back D2H inside the timed region; the copies of step k+1 overlap the kernels of step k.  The one-call
     # synchronous form is timed beside it.
@@ -272,19 +297,21 @@ def run_gpu(args):
     e2e_sync_s = time.perf_counter() - t0
     assert (st == 0).all()
     e2e_phases = ctx.last_timing()
-    st_out = [np.full(B, 255, np.uint8) for _ in range(2)]
-    for k in range(2):                                                   # warm both slots (first use allocates their buffers)
+    S = pkg.binding.SLOTS                                                # batches in flight
+    st_out = [np.full(B, 255, np.uint8) for _ in range(S)]
+    for k in range(S):                                                   # warm every slot (first use allocates its buffers)
         ctx.bccsp_verify_batch_wait(k, ctx.bccsp_verify_batch_async(k, *e2e_args), st_out[k])
     sync_all()
     t0 = time.perf_counter()
     for k in range(e2e_steps):
-        ctx.bccsp_verify_batch_async(k & 1, *e2e_args)
-        if k > 0:
-            ctx.bccsp_verify_batch_wait((k - 1) & 1, B, st_out[(k - 1) & 1])
-    ctx.bccsp_verify_batch_wait((e2e_steps - 1) & 1, B, st_out[(e2e_steps - 1) & 1])
+        if k >= S:
+            ctx.bccsp_verify_batch_wait(k % S, B, st_out[k % S])        # the slot's previous batch (k - S)
+        ctx.bccsp_verify_batch_async(k % S, *e2e_args)
+    for k in range(max(0, e2e_steps - S), e2e_steps):
+        ctx.bccsp_verify_batch_wait(k % S, B, st_out[k % S])
     torch.cuda.synchronize(dev)
     e2e_s = time.perf_counter() - t0
-    assert (st_out[0] == 0).all() and (st_out[1] == 0).all()
+    assert all((o == 0).all() for o in st_out)
     e2e_h2d = int(w.sig_off[B]) + int(dig_off[B]) + 4 * (B + 1) * 2 + 4 * B + 68 * KEYS
     e2e_d2h = B
 
@@ -308,27 +335,31 @@ def run_gpu(args):
             fl = ctx.validate_envelopes(pinned, eoff)
         bms_single = (time.perf_counter() - t0) / breps * 1e3
         ph = ctx.block_timing()
-        # two blocks in flight (fabgpu_validate_envelopes_async / fabgpu_validate_wait on alternating slots, one pinned buffer per
+        # several blocks in flight (fabgpu_validate_envelopes_async / fabgpu_validate_wait round-robin over the slots, one pinned buffer per
         # slot): the PCIe copy of block k+1 runs under the kernels of block k.  Every block is copied, walked, hashed, verified
         # and decided inside the timed region.
-        pinned2 = ctx.block_buffer(len(eblob), slot=1)
-        pinned2[:] = np.frombuffer(eblob, np.uint8)
-        bufs = (pinned, pinned2)
+        bufs = [pinned]
+        for k in range(1, S):
+            pb = ctx.block_buffer(len(eblob), slot=k)
+            pb[:] = np.frombuffer(eblob, np.uint8)
+            bufs.append(pb)
         os.environ["FABGPU_BLOCK_EVENTS"] = "0"
-        for k in range(2):
+        for k in range(S):
             ctx.validate_envelopes_async(k, bufs[k], eoff)
             assert not ctx.validate_wait(k, args.block_txs).any()
-        breps2 = 20
+        breps2 = 30
+        fls = []
         t0 = time.perf_counter()
         for k in range(breps2):
-            ctx.validate_envelopes_async(k & 1, bufs[k & 1], eoff)
-            if k > 0:
-                fl = ctx.validate_wait((k - 1) & 1, args.block_txs)
-        fl2 = ctx.validate_wait((breps2 - 1) & 1, args.block_txs)
+            if k >= S:
+                fls.append(ctx.validate_wait(k % S, args.block_txs))
+            ctx.validate_envelopes_async(k % S, bufs[k % S], eoff)
+        for k in range(max(0, breps2 - S), breps2):
+            fls.append(ctx.validate_wait(k % S, args.block_txs))
         bms = (time.perf_counter() - t0) / breps2 * 1e3
-        assert not fl.any() and not fl2.any()
+        assert len(fls) == breps2 and not any(f.any() for f in fls)
         block_replay = {"workload": "configs[2]: %d txs x (1 creator + 3 endorsement) signatures, 3-of-4 policy, block of %d bytes in pinned host memory" % (args.block_txs, len(blk)),
-                        "api": "fabgpu_validate_envelopes_async + fabgpu_validate_wait, two blocks in flight", "ms_per_block": bms, "tx_per_s": args.block_txs / bms * 1e3,
+                        "api": "fabgpu_validate_envelopes_async + fabgpu_validate_wait, %d blocks in flight" % S, "ms_per_block": bms, "tx_per_s": args.block_txs / bms * 1e3,
                         "verifies_per_s": binfo["n_sigs"] / bms * 1e3, "all_flags_valid": True,
                         "single_call": {"api": "fabgpu_validate_envelopes (one blocking call per block)", "ms_per_block": bms_single,
                                         "tx_per_s": args.block_txs / bms_single * 1e3},
@@ -338,10 +369,10 @@ def run_gpu(args):
     clocks = sampler.stop() if rank == 0 else None      # sampled across the three timed loops (key-table, generic, e2e)
 
     # ---- max over ranks ---------------------------------------------------------------------------------------
-    times = torch.tensor([dev_ms, e2e_s * 1e3, wall * 1e3, gen_ms, key_register_ms, e2e_sync_s * 1e3], dtype=torch.float64, device=dev)
+    times = torch.tensor([dev_ms, e2e_s * 1e3, wall * 1e3, gen_ms, key_register_ms, e2e_sync_s * 1e3, conc_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms, wall_ms, gen_ms, key_register_ms, e2e_sync_ms = [float(x) for x in times.tolist()]
+    dev_ms, e2e_ms, wall_ms, gen_ms, key_register_ms, e2e_sync_ms, conc_ms = [float(x) for x in times.tolist()]
 
     if rank == 0:
         hbm_peak, peak_src, sm_max = _peaks()
@@ -366,12 +397,15 @@ def run_gpu(args):
                        "timing": "per-step CUDA events on the launch stream, summed; L2 flushed (256 MiB fill) between steps; %d rotating input buffers" % ROT,
                        "wall_ms_incl_flush": wall_ms},
             "e2e": {"value": n_total * e2e_steps / (e2e_ms * 1e-3), "unit": "verifies/s", "h2d_bytes_per_step": e2e_h2d * world, "d2h_bytes_per_step": e2e_d2h * world,
-                    "api": "fabgpu_bccsp_verify_batch_async + _wait on alternating slots, 2 batches in flight (raw DER signatures + digests + keys in pageable host memory -> status bytes)",
+                    "api": "fabgpu_bccsp_verify_batch_async + _wait over the context's %d slots, that many batches in flight (raw DER signatures + digests + keys in pageable host memory -> status bytes)" % pkg.binding.SLOTS,
                     "steps": e2e_steps,
                     "sync_value": n_total * e2e_steps / (e2e_sync_ms * 1e-3), "sync_api": "fabgpu_bccsp_verify_batch, one blocking call per step",
                     "last_call_phases_us": {"key_lookup": e2e_phases[0], "host_staging_copy": e2e_phases[1], "h2d_gate_verify_status_d2h": e2e_phases[2], "status_copy": e2e_phases[3]},
                     "gates": "on the device (bccsp_gate_kernel); FABGPU_BCCSP_HOST_GATES=1 selects the host-thread gates"},
             "gpu_launches": int(launches),
+            "value_concurrent": {"value": n_total * csteps / (conc_ms * 1e-3), "unit": "verifies/s", "steps": csteps,
+                                 "what": "same kernel, device-resident inputs, %d batches in flight on %d streams, no L2 flush: the regime of the pipelined e2e call "
+                                         "(a single 64k launch fills 512 of 592 resident CTA slots)" % (pkg.binding.SLOTS, pkg.binding.SLOTS)},
             "value_generic": value_generic,
             "generic": {"what": "ecdsa_verify_kernel: no per-key table (first sight of a key); 255 doublings + 52 additions per signature",
                         "ms_per_step": gen_ms / gsteps, "steps": gsteps},

@@ -1212,7 +1212,7 @@ static int block_submit(fabgpu_ctx* ctx, int slot, const uint8_t* block, size_t 
     // One copy, then the walk.  (Copying in chunks with a walk per chunk was measured slower on B200 -- 1 chunk 1.93 ms, 4 chunks
     // 2.27 ms, 8 chunks 3.52 ms per 10k-tx block: hashing a 4.6 KB payload is ~250 us of dependent rounds per thread however few
     // threads a launch has, so per-chunk launches serialise that latency.  What hides the copy is the NEXT block's copy running
-    // under this block's kernels: the two slots.)
+    // under this block's kernels: the slots.)
     CK(ctx, cudaMemcpyAsync(bb.d_block, block, block_len, cudaMemcpyHostToDevice, st));
     bdev::block_walk_kernel<<<(cnt + 31) / 32, 32, 0, st>>>(bb.d_block, db.d_env_off, 0u, cnt, cnt, dm.channel, dm.channel_len, db.d_txs, db.d_raw, ja, db.d_counter);
     bdev::block_resolve_kernel<<<(cnt + 63) / 64, 64, 0, st>>>(bb.d_block, db.d_raw, 0u, cnt, m, ja, db.d_txs);                      // creator jobs

@@ -164,7 +164,7 @@ func (csp *impl) Verify(k bccsp.Key, signature, digest []byte, opts bccsp.Signer
 }
 
 // aggregate drains requests into the pinned buffers of a free slot and enqueues one batch per flush; complete (below)
-// waits for batches in launch order and answers the callers.  With the two slots of a context, the host fills and copies
+// waits for batches in launch order and answers the callers.  With the slots of a context (FABGPU_SLOTS = 3), the host fills and copies
 // batch k+1 while the GPU verifies batch k.
 type batch struct {
 	slot    int

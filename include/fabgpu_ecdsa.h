@@ -69,7 +69,7 @@ const char* fabgpu_last_error(const fabgpu_ctx* ctx);
 int fabgpu_device_count(const fabgpu_ctx* ctx);
 size_t fabgpu_max_batch(const fabgpu_ctx* ctx);
 
-#define FABGPU_SLOTS 2
+#define FABGPU_SLOTS 3
 
 /* ---- leaf: pre-gated SoA tuples -> bitmask (replaces the crypto/ecdsa.Verify call at bccsp/sw/ecdsa.go:56) */
 
@@ -130,7 +130,7 @@ int fabgpu_bccsp_verify_batch(fabgpu_ctx* ctx, const uint8_t* keys_xy, int K, co
 /* The same call in two halves, for a caller that keeps the GPU fed (the Go provider's aggregator): _async stages the
  * batch into the slot's pinned buffers and enqueues copies + kernels + the status read-back on the slot's stream, then
  * returns -- the caller's arrays are not referenced afterwards; _wait blocks until that batch is done and writes its n
- * status bytes.  With the FABGPU_SLOTS slots used alternately, the copies of batch i+1 overlap the kernels of batch i.
+ * status bytes.  With the FABGPU_SLOTS slots used round-robin, the staging and copies of the next batches overlap the kernels of batch i.
  * A slot holds one batch at a time (FABGPU_E_ARG otherwise); fabgpu_bccsp_verify_batch itself is _async + _wait on slot 0. */
 int fabgpu_bccsp_verify_batch_async(fabgpu_ctx* ctx, int slot, const uint8_t* keys_xy, int K, const int32_t* key_idx,
                                     const uint8_t* digests, const uint32_t* dig_off, const uint8_t* sigs,
@@ -170,7 +170,7 @@ int fabgpu_validate_block(fabgpu_ctx* ctx, const uint8_t* block, size_t block_le
  * concatenation, env_off the (n_env+1)-entry offset table.  Saves the serial walk over the length-prefixed envelopes. */
 int fabgpu_validate_envelopes(fabgpu_ctx* ctx, const uint8_t* blob, const uint32_t* env_off, size_t n_env, uint8_t* flags, size_t flags_cap,
                               size_t* n_tx_out);
-/* Both calls in two halves over the FABGPU_SLOTS slots, for a committer that keeps two blocks in flight: _async enqueues
+/* Both calls in two halves over the FABGPU_SLOTS slots, for a committer that keeps several blocks in flight: _async enqueues
  * the copy and every kernel of the block on the slot's stream and returns; fabgpu_validate_wait blocks until the slot's
  * block is done, runs the duplicate-tx-id pass and writes the flags.  The block bytes must stay valid and unchanged until
  * the wait returns (they are copied by DMA and read again by the duplicate pass).  While the GPU works on block k, the
