@@ -156,7 +156,6 @@ struct fabgpu_ctx {
         uint32_t *d_mask = nullptr, *d_off = nullptr, *h_mask = nullptr;
     } bbs[FABGPU_SLOTS];          // [0] also serves the host-thread path (FABGPU_BLOCK_HOST=1)
     double block_timing[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // host phases [0..4] (see fabgpu_block_timing), device stages [5..9]
-    std::vector<uint64_t> dup_keys; std::vector<uint32_t> dup_idx;   // scratch of the duplicate-tx-id pass
     // device-side copy of the MSP view / policy (block_plan_kernel, block_decide_kernel)
     struct DevMsp {
         uint8_t *id_blob = nullptr, *valid = nullptr, *keys_xy = nullptr, *channel = nullptr;
@@ -186,6 +185,7 @@ struct fabgpu_ctx {
         // the block in flight on this slot (fabgpu_validate_*_async .. fabgpu_validate_wait)
         bool busy = false, on_device = false, use_ev = false; size_t T = 0; const uint8_t* block = nullptr;
         std::vector<uint8_t> done_flags;         // host-thread path: finished at submit time
+        std::vector<uint64_t> dup_keys; std::vector<uint32_t> dup_idx;   // scratch of the duplicate-tx-id pass (per slot: waits may run concurrently)
         std::chrono::steady_clock::time_point t0, t1;
         cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     } dbs[FABGPU_SLOTS];
@@ -1263,8 +1263,8 @@ static int block_finish(fabgpu_ctx* ctx, int slot, uint8_t* flags)
     {
         // flat open-addressing table keyed by the 64-bit tx-id hash (0 = empty); equal hashes are confirmed on the bytes
         size_t cap = 16; while (cap < 4 * T) cap <<= 1;
-        ctx->dup_keys.assign(cap, 0); ctx->dup_idx.resize(cap);
-        uint64_t* keys = ctx->dup_keys.data(); uint32_t* idx = ctx->dup_idx.data();
+        db.dup_keys.assign(cap, 0); db.dup_idx.resize(cap);
+        uint64_t* keys = db.dup_keys.data(); uint32_t* idx = db.dup_idx.data();
         for (size_t t = 0; t < T; t++) {
             if (flags[t] != blockval::TX_VALID) continue;
             const bdev::Seg id = db.h_seg[t];

@@ -23,6 +23,7 @@ import (
 	"crypto/elliptic"
 	"crypto/x509"
 	"fmt"
+	"math/big"
 	"sync/atomic"
 	"time"
 
@@ -46,7 +47,21 @@ type ecdsaP256Key struct {
 	bccsp.Key                  // the sw key: SKI, Bytes, ... are unchanged
 	pub       *ecdsa.PublicKey // parsed once at import
 	x, y      [32]byte
-	slot      int32 // fixed-base table slot on the device(s), -1 if none (fabgpu_keys_register)
+	slot      int32  // handle of the key's fixed-base table on the device(s), -1 if none (fabgpu_keys_register); atomic
+	uses      uint32 // verifications requested with this key; atomic
+}
+
+// A key gets its 64 MiB window table once it has been used this often: identities the MSP imports but that sign rarely
+// (or once) stay on the generic kernel instead of evicting the tables of the busy ones.
+const tableAfterUses = 512
+
+// fill32 writes v as 32 big-endian bytes (big.Int.FillBytes needs Go 1.15; the reference builds with 1.14).
+func fill32(dst *[32]byte, v *big.Int) {
+	b := v.Bytes()
+	for i := range dst {
+		dst[i] = 0
+	}
+	copy(dst[32-len(b):], b)
 }
 
 type request struct {
@@ -91,7 +106,8 @@ func New(opts GPUOpts, keyStore bccsp.KeyStore) (bccsp.BCCSP, error) {
 	return csp, nil
 }
 
-// KeyImport delegates to sw and, for ECDSA P-256 public keys, caches X||Y beside the imported key.
+// KeyImport delegates to sw and, for ECDSA P-256 public keys, caches X||Y beside the imported key (the window table follows
+// after tableAfterUses verifications).
 func (csp *impl) KeyImport(raw interface{}, opts bccsp.KeyImportOpts) (bccsp.Key, error) {
 	k, err := csp.BCCSP.KeyImport(raw, opts)
 	if err != nil {
@@ -107,15 +123,18 @@ func (csp *impl) KeyImport(raw interface{}, opts bccsp.KeyImportOpts) (bccsp.Key
 	if pub == nil || pub.Curve != elliptic.P256() || !pub.Curve.IsOnCurve(pub.X, pub.Y) {
 		return k, nil // P-384, RSA, private keys, ...: stay on the software path (pkcs11.go:259-261 pattern)
 	}
-	gk := &ecdsaP256Key{Key: k, pub: pub}
-	pub.X.FillBytes(gk.x[:])
-	pub.Y.FillBytes(gk.y[:])
-	// identities are imported once and verified many times (msp/cache): precompute the key's window table now
+	gk := &ecdsaP256Key{Key: k, pub: pub, slot: -1}
+	fill32(&gk.x, pub.X)
+	fill32(&gk.y, pub.Y)
+	return gk, nil
+}
+
+// registerTable builds the key's window table on the device(s) (about 0.3-2 ms of GPU time, once).
+func (csp *impl) registerTable(gk *ecdsaP256Key) {
 	var xy [64]byte
 	copy(xy[:32], gk.x[:])
 	copy(xy[32:], gk.y[:])
-	gk.slot = csp.dev.registerKey(&xy)
-	return gk, nil
+	atomic.StoreInt32(&gk.slot, csp.dev.registerKey(&xy))
 }
 
 // Verify has exactly sw.CSP.Verify's contract (bccsp/sw/impl.go:247-270).
@@ -146,9 +165,12 @@ func (csp *impl) Verify(k bccsp.Key, signature, digest []byte, opts bccsp.Signer
 	if r.BitLen() > 256 {
 		return false, nil // r >= 2^256 > N: ecdsa.Verify returns false
 	}
+	if atomic.AddUint32(&gk.uses, 1) == tableAfterUses {
+		go csp.registerTable(gk) // identities are verified many times (msp/cache keeps them): worth a table from here on
+	}
 	req := &request{key: gk, done: make(chan result, 1)}
-	r.FillBytes(req.r[:])
-	s.FillBytes(req.s[:])
+	fill32(&req.r, r)
+	fill32(&req.s, s)
 	d := digest
 	if len(d) > 32 {
 		d = d[:32] // hashToInt keeps the leftmost 32 bytes for a 256-bit order
@@ -207,7 +229,7 @@ func (csp *impl) aggregate() {
 			copy(sl.e[o:o+32], rq.e[:])
 			copy(sl.r[o:o+32], rq.r[:])
 			copy(sl.s[o:o+32], rq.s[:])
-			sl.keySlot[i] = rq.key.slot // every entry is rewritten per batch: a stale slot would verify against the wrong key
+			sl.keySlot[i] = atomic.LoadInt32(&rq.key.slot) // every entry is rewritten per batch; stale handles degrade to the generic kernel
 		}
 		b := &batch{slot: slotIdx, pending: pending}
 		b.err = csp.dev.enqueue(slotIdx, len(pending)) // H2D + kernels + D2H on the slot's stream; returns at once
