@@ -64,10 +64,10 @@ ecdsa_verify_kernel(const int32_t* __restrict__ key_slot, const uint8_t* __restr
 }
 
 #ifndef FAB_CACHED_THREADS
-#define FAB_CACHED_THREADS 128
+#define FAB_CACHED_THREADS 512        // largest CTA the kernel may be launched with (launch_verify picks 128 / 256 / 512)
 #endif
 #ifndef FAB_CACHED_MINBLOCKS
-#define FAB_CACHED_MINBLOCKS 4
+#define FAB_CACHED_MINBLOCKS 1        // 512 threads x 128 registers = one CTA per SM; four CTAs of 128 threads fit as well
 #endif
 // Signatures whose public key has a precomputed window table: both scalar multiplications are fixed-base
 // (FAB_G_WINDOWS + FAB_Q_WINDOWS mixed additions gathered from HBM-resident tables, no doublings).  Slot < 0 -> bit 0, left to

@@ -46,6 +46,7 @@ struct DevSlot {
 struct Device {
     int id = 0;
     aff* gtab = nullptr;
+    int sms = 148;            // multiprocessors (launch shapes)
     aff* qtab = nullptr;      // key_slots tables of FAB_G_WINDOWS * FAB_G_ENTRIES points (per-key fixed-base tables)
     DevSlot slot[FABGPU_SLOTS];
 };
@@ -264,8 +265,16 @@ int launch_verify(fabgpu_ctx* ctx, const Device& dv, int mode, const int32_t* ke
 {
     if (n == 0) return FABGPU_OK;
     if (mode != MODE_GENERIC) {
-        const unsigned blocks = (unsigned)((n + FAB_CACHED_THREADS - 1) / FAB_CACHED_THREADS);
-        ecdsa_verify_cached_kernel<<<blocks, FAB_CACHED_THREADS, 0, st>>>(key_slot, e, r, s, (uint32_t)n, dv.gtab, dv.qtab, mask, off, n_dev, n_base);
+        // CTA shape (the kernel allows up to FAB_CACHED_THREADS = 512 threads at 128 registers, i.e. one such CTA per SM).
+        // Measured on B200 (profiles/r1_kbench_table_widths.txt): a batch that fits one wave of 512-thread CTAs (64k: 128 CTAs)
+        // finishes in 0.315 ms against 0.346 ms as 512 CTAs of 128 threads; beyond one wave 256-thread CTAs quantise best
+        // (256k: 231 M/s against 223 / 212 for 128 / 512); below ~12 warps per SM small CTAs spread over all SMs win
+        // (fewer warps per scheduler = lower latency per warp), and so they do when the batch size is only an upper bound.
+        unsigned threads = 128;
+        const size_t sms = (size_t)dv.sms;
+        if (!n_dev && n > sms * 384) threads = (n <= sms * FAB_CACHED_THREADS) ? FAB_CACHED_THREADS : 256;
+        const unsigned blocks = (unsigned)((n + threads - 1) / threads);
+        ecdsa_verify_cached_kernel<<<blocks, threads, 0, st>>>(key_slot, e, r, s, (uint32_t)n, dv.gtab, dv.qtab, mask, off, n_dev, n_base);
         ctx->launches++;
         CK(ctx, cudaGetLastError());
     }
@@ -434,6 +443,7 @@ int init_impl(fabgpu_ctx* ctx, const int* device_ids, int n_dev, size_t max_batc
         Device& dv = ctx->devs[d];
         dv.id = ids[d];
         CK(ctx, cudaSetDevice(dv.id));
+        CK(ctx, cudaDeviceGetAttribute(&dv.sms, cudaDevAttrMultiProcessorCount, dv.id));
         CK(ctx, cudaMalloc(&dv.gtab, tab_entries * sizeof(aff)));
         CK(ctx, cudaMalloc(&dv.qtab, (size_t)ctx->key_slots * FAB_Q_WINDOWS * FAB_Q_ENTRIES * sizeof(aff)));
         for (auto& ds : dv.slot) {
