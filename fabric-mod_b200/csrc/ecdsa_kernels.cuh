@@ -80,6 +80,15 @@ ecdsa_verify_cached_kernel(const int32_t* __restrict__ key_slot, const uint8_t* 
     if (n_dev) n = min(n, n_base + *n_dev);
     const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t res = V_INVALID;
+#if FAB_CTA_SYNC
+    {
+        const int32_t slot = idx < n ? key_slot[idx] : -1;
+        const bool live = slot >= 0;
+        const size_t o = live ? (size_t)idx * 32 : 0;
+        res = ecdsa_verify_one_cached(qtab + (size_t)(live ? slot : 0) * (FAB_Q_WINDOWS * FAB_Q_ENTRIES), load_be32(e + o), load_be32(r + o),
+                                      load_be32(s + o), gtab, live);
+    }
+#else
     if (idx < n) {
         const int32_t slot = key_slot[idx];
         if (slot >= 0) {
@@ -88,6 +97,7 @@ ecdsa_verify_cached_kernel(const int32_t* __restrict__ key_slot, const uint8_t* 
                                           load_be32(s + o), gtab);
         }
     }
+#endif
     const uint32_t vmask = __ballot_sync(0xffffffffu, res == V_VALID);
     if ((threadIdx.x & 31u) == 0 && idx < n) {
         mask[idx >> 5] = vmask;

@@ -160,6 +160,28 @@ def test_config5_tampered_mask_exact(ctx):
     assert bits[picked].sum() == 0 and 1200 < len(picked) < 2100
 
 
+def test_config4_one_million_signatures_full_size():
+    """BASELINE.json configs[3] / [4] at FULL size on whatever GPUs the box has: 1 048 576 signatures, 256 keys, 5 % tampered r,
+    through the bccsp-level call (raw DER in, status bytes out; key tables built on first sight) and through the pre-gated SoA
+    leaf (bitmask out).  Exact equality with the C oracle, plus the size-independent properties: no tampered signature is
+    accepted, every untouched one is, and the number of set mask bits is N minus the number tampered."""
+    import torch
+    n = 1 << 20
+    w = workload.Workload(n, 256, seed=workload.DEFAULT_SEED + 4, nthreads=os.cpu_count())
+    picked = w.tamper_r(0.05)
+    exp = fast.verify_batch(w.keys_xy, w.key_idx, w.digest, w.dig_off(), w.sigs, w.sig_off, nthreads=os.cpu_count())
+    assert int((exp != o.VALID).sum()) == len(picked) and 50000 < len(picked) < 55000
+    ndev = min(torch.cuda.device_count(), 8)
+    c = pkg().binding.Context(max_batch=n, device_ids=list(range(ndev)))
+    st = c.bccsp_verify_batch(w.keys_xy, w.key_idx, w.digest, w.dig_off(), w.sigs, w.sig_off)
+    assert (st == exp).all()
+    mask, off = c.verify_p256_host(w.qx(), w.qy(), w.digest, w.r, w.s)
+    bits = mask_bits(mask, n)
+    assert not off.any() and (mask == fast.valid_mask(exp)).all()
+    assert int(bits.sum()) == n - len(picked) and bits[picked].sum() == 0
+    c.close()
+
+
 def test_async_slots_and_pinned_buffers(ctx):
     w = workload.Workload(4096, 8, seed=21)
     w.tamper_r(0.1)
