@@ -8,10 +8,10 @@ namespace fabgpu {
 // Launch shapes measured on B200 (tools/kbench.py, 64k and 256k batches): both kernels are pipe-bound, not
 // latency-bound, so occupancy variants differ by < 5 %; these were the best of the sweep.
 #ifndef FAB_VERIFY_THREADS
-#define FAB_VERIFY_THREADS 64
+#define FAB_VERIFY_THREADS 448        // largest CTA of the generic kernel (launch_verify picks 64 / 256 / 448 by batch size)
 #endif
 #ifndef FAB_VERIFY_MINBLOCKS
-#define FAB_VERIFY_MINBLOCKS 7
+#define FAB_VERIFY_MINBLOCKS 1
 #endif
 
 // 32 big-endian bytes at a 16-byte aligned address -> limbs, as two 128-bit loads + byte permutes
@@ -80,15 +80,6 @@ ecdsa_verify_cached_kernel(const int32_t* __restrict__ key_slot, const uint8_t* 
     if (n_dev) n = min(n, n_base + *n_dev);
     const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t res = V_INVALID;
-#if FAB_CTA_SYNC
-    {
-        const int32_t slot = idx < n ? key_slot[idx] : -1;
-        const bool live = slot >= 0;
-        const size_t o = live ? (size_t)idx * 32 : 0;
-        res = ecdsa_verify_one_cached(qtab + (size_t)(live ? slot : 0) * (FAB_Q_WINDOWS * FAB_Q_ENTRIES), load_be32(e + o), load_be32(r + o),
-                                      load_be32(s + o), gtab, live);
-    }
-#else
     if (idx < n) {
         const int32_t slot = key_slot[idx];
         if (slot >= 0) {
@@ -97,7 +88,6 @@ ecdsa_verify_cached_kernel(const int32_t* __restrict__ key_slot, const uint8_t* 
                                           load_be32(s + o), gtab);
         }
     }
-#endif
     const uint32_t vmask = __ballot_sync(0xffffffffu, res == V_VALID);
     if ((threadIdx.x & 31u) == 0 && idx < n) {
         mask[idx >> 5] = vmask;

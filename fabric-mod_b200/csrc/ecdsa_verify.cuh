@@ -163,29 +163,17 @@ FAB_HD uint32_t ecdsa_verify_one(const u256& qx, const u256& qy, const u256& e, 
 // Same verification when the public key has a precomputed window table (fabgpu_keys_register): u2*Q becomes
 // fixed-base too -- FAB_G_WINDOWS + FAB_Q_WINDOWS mixed additions in total, no doublings, no per-signature table.  The key was
 // checked to be a curve point when its table was built.
-// `live` = false: the thread has no signature (past the end of the batch, or its key has no table) but still walks the loop,
-// because with FAB_CTA_SYNC every thread of the CTA meets at a barrier per window (keeps the CTA's warps on the same
-// instruction-cache lines of the expanded point addition).
-#ifndef FAB_CTA_SYNC
-#define FAB_CTA_SYNC 0
-#endif
-FAB_HD uint32_t ecdsa_verify_one_cached(const aff* qtab, const u256& e, const u256& r, const u256& s, const aff* gtab, bool live = true)
+FAB_HD uint32_t ecdsa_verify_one_cached(const aff* qtab, const u256& e, const u256& r, const u256& s, const aff* gtab)
 {
     const u256 n = sc_n();
-    const bool ok = live && !(u256_is_zero(r) || u256_is_zero(s) || !u256_lt(r, n) || !u256_lt(s, n));
-#if !FAB_CTA_SYNC
-    if (!ok) return V_INVALID;
-#endif
-    u256 u1 = u256_zero(), u2 = u256_zero();
-    if (ok) {
+    if (u256_is_zero(r) || u256_is_zero(s) || !u256_lt(r, n) || !u256_lt(s, n)) return V_INVALID;
 #if FAB_SAFEGCD
-        const u256 w = sc_inv_to_mont_safegcd(s);
+    const u256 w = sc_inv_to_mont_safegcd(s);
 #else
-        const u256 w = sc_inv_to_mont(s);
+    const u256 w = sc_inv_to_mont(s);
 #endif
-        u1 = sc_mul(sc_reduce_once(e), w);
-        u2 = sc_mul(r, w);
-    }
+    const u256 u1 = sc_mul(sc_reduce_once(e), w);
+    const u256 u2 = sc_mul(r, w);
     // One loop over both tables -- 12 windows of u1 in the generator's table, then 16 windows of u2 in the key's table -- so that
     // the kernel holds a single copy of the point addition (expanded in place when FAB_CACHED_INLINE).
     jac acc = jac_infinity();
@@ -199,17 +187,13 @@ FAB_HD uint32_t ecdsa_verify_one_cached(const aff* qtab, const u256& e, const u2
         const int windows = t ? FAB_Q_WINDOWS : FAB_G_WINDOWS;
 #pragma unroll 1
         for (int j = 0; j < windows; j++) {
-#if FAB_CTA_SYNC && defined(__CUDA_ARCH__)
-            __syncthreads();
-#endif
             const uint32_t d = kk[0] & entries;
 #pragma unroll
             for (int i = 0; i < 7; i++) kk[i] = (kk[i] >> wbits) | (kk[i + 1] << (32u - wbits));
             kk[7] >>= wbits;
-            if (d) acc = jac_add_aff_t<FAB_CACHED_INLINE != 0>(acc, tab[(size_t)j * entries + (d - 1)]);   // d == 0 for every thread that is not ok
+            if (d) acc = jac_add_aff_t<FAB_CACHED_INLINE != 0>(acc, tab[(size_t)j * entries + (d - 1)]);
         }
     }
-    if (!ok) return V_INVALID;
     return final_check(acc, r);
 }
 
