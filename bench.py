@@ -301,16 +301,21 @@ def run_gpu(args):
     st_out = [np.full(B, 255, np.uint8) for _ in range(S)]
     for k in range(S):                                                   # warm every slot (first use allocates its buffers)
         ctx.bccsp_verify_batch_wait(k, ctx.bccsp_verify_batch_async(k, *e2e_args), st_out[k])
-    sync_all()
-    t0 = time.perf_counter()
-    for k in range(e2e_steps):
-        if k >= S:
-            ctx.bccsp_verify_batch_wait(k % S, B, st_out[k % S])        # the slot's previous batch (k - S)
-        ctx.bccsp_verify_batch_async(k % S, *e2e_args)
-    for k in range(max(0, e2e_steps - S), e2e_steps):
-        ctx.bccsp_verify_batch_wait(k % S, B, st_out[k % S])
-    torch.cuda.synchronize(dev)
-    e2e_s = time.perf_counter() - t0
+    # The pipelined loop is host-paced (staging threads, Python) and the boxes are shared: it is timed five times and the MEDIAN
+    # repetition is reported (all five are in the JSON line).
+    e2e_reps = []
+    for rep in range(5):
+        sync_all()
+        t0 = time.perf_counter()
+        for k in range(e2e_steps):
+            if k >= S:
+                ctx.bccsp_verify_batch_wait(k % S, B, st_out[k % S])    # the slot's previous batch (k - S)
+            ctx.bccsp_verify_batch_async(k % S, *e2e_args)
+        for k in range(max(0, e2e_steps - S), e2e_steps):
+            ctx.bccsp_verify_batch_wait(k % S, B, st_out[k % S])
+        torch.cuda.synchronize(dev)
+        e2e_reps.append(time.perf_counter() - t0)
+    e2e_s = sorted(e2e_reps)[len(e2e_reps) // 2]
     assert all((o == 0).all() for o in st_out)
     e2e_h2d = int(w.sig_off[B]) + int(dig_off[B]) + 4 * (B + 1) * 2 + 4 * B + 68 * KEYS
     e2e_d2h = B
@@ -398,7 +403,7 @@ def run_gpu(args):
                        "wall_ms_incl_flush": wall_ms},
             "e2e": {"value": n_total * e2e_steps / (e2e_ms * 1e-3), "unit": "verifies/s", "h2d_bytes_per_step": e2e_h2d * world, "d2h_bytes_per_step": e2e_d2h * world,
                     "api": "fabgpu_bccsp_verify_batch_async + _wait over the context's %d slots, that many batches in flight (raw DER signatures + digests + keys in pageable host memory -> status bytes)" % pkg.binding.SLOTS,
-                    "steps": e2e_steps,
+                    "steps": e2e_steps, "repetitions_verifies_per_s": [n_total * e2e_steps / t for t in e2e_reps], "reported": "median repetition (max over ranks)",
                     "sync_value": n_total * e2e_steps / (e2e_sync_ms * 1e-3), "sync_api": "fabgpu_bccsp_verify_batch, one blocking call per step",
                     "last_call_phases_us": {"key_lookup": e2e_phases[0], "host_staging_copy": e2e_phases[1], "h2d_gate_verify_status_d2h": e2e_phases[2], "status_copy": e2e_phases[3]},
                     "gates": "on the device (bccsp_gate_kernel); FABGPU_BCCSP_HOST_GATES=1 selects the host-thread gates"},
