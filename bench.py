@@ -46,8 +46,8 @@ def alg_macs_cached(wg, wq):
 
 
 KEYS = 64
-NCU_DRAM_BYTES_PER_LAUNCH_64K = 233449984 + 8335360   # ecdsa_verify_cached_kernel, profiles/r1_final_cached_ncu_summary.txt (dram read + write)
-NCU_FMAHEAVY_BUSY = 0.5685              # sm__pipe_fmaheavy_cycles_active, % of elapsed, same capture: the binding unit of that kernel
+NCU_DRAM_BYTES_PER_LAUNCH_64K = 231995648 + 6491392   # ecdsa_verify_cached_kernel, profiles/r1_final_cached_ncu_summary.txt (dram read + write)
+NCU_FMAHEAVY_BUSY = 0.6222              # sm__pipe_fmaheavy_cycles_active, % of elapsed, same capture: the binding unit of that kernel
 
 
 def _peaks():
@@ -429,7 +429,8 @@ def run_gpu(args):
                              "macs_per_verify": macs_cached,
                              "binding_unit": {"name": "fmaheavy pipe (IMAD / IMAD.WIDE)", "busy_frac_of_elapsed_ncu": NCU_FMAHEAVY_BUSY,
                                               "note": "the multiplier's carry-chained wide MAC issues at 31 /clk/SM, half the plain IMAD.WIDE rate "
-                                                      "(profiles/microbench/int_pipe_b200.txt); with it the pipe is 57 % busy over the launch, ALU pipe 41 %"},
+                                                      "(profiles/microbench/int_pipe_b200.txt); averaged over all 148 SMs the pipe is 62 % busy over the launch "
+                                                      "(72 % on the 128 SMs the 128 CTAs of 512 threads occupy), ALU pipe 45 % (52 %)"},
                              "peak_source": "model: 148 SM x 64 IMAD/clk x %d MHz" % int(sm_max),
                              "generic_kernel": {"achieved": B * ALG_MACS_PER_VERIFY / gen_launch_s / 1e12,
                                                 "frac": B * ALG_MACS_PER_VERIFY / gen_launch_s / mac_peak, "macs_per_verify": ALG_MACS_PER_VERIFY}},
