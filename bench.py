@@ -178,6 +178,9 @@ def run_gpu(args):
     n_total = B * world
     # this rank's slice of the synthetic workload (rank-seeded so ranks do not verify identical bytes)
     w = workload.Workload(B, KEYS, seed=workload.DEFAULT_SEED + 2 + 1000 * rank)
+    # one process per GPU shares the host: give each rank's staging pool its share of the cores (the pool spins briefly before
+    # sleeping; eight ranks with the default 32 threads each would oversubscribe a 128-thread host)
+    os.environ.setdefault("FABGPU_GATE_THREADS", str(max(4, min(32, (os.cpu_count() or 8) // (2 * world)))))
     ctx = pkg.binding.Context(max_batch=B, device_ids=[local])
 
     # ---- device-resident leg: ROT distinct input buffers, L2 flushed between steps ---------------------------

@@ -53,12 +53,13 @@ bccsp_gate_kernel(const uint8_t* __restrict__ sigs, const uint32_t* __restrict__
                   const uint32_t* __restrict__ dig_off, const int32_t* __restrict__ key_idx, const int32_t* __restrict__ slot_of,
                   const uint8_t* __restrict__ keys_xy, int32_t K, uint32_t n, uint8_t* __restrict__ r, uint8_t* __restrict__ s,
                   uint8_t* __restrict__ e, int32_t* __restrict__ key_slot, uint8_t* __restrict__ qx, uint8_t* __restrict__ qy,
-                  uint8_t* __restrict__ pre)
+                  uint8_t* __restrict__ pre, uint32_t sig_base, uint32_t dig_base)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int32_t ki = key_idx[i];
-    const uint32_t so = sig_off[i], sl = sig_off[i + 1] - so, dof = dig_off[i], dl = dig_off[i + 1] - dof;
+    // the offset tables are the caller's (absolute); `sigs` / `digs` hold the bytes from sig_base / dig_base on (a chunk of a call)
+    const uint32_t so = sig_off[i] - sig_base, sl = sig_off[i + 1] - sig_off[i], dof = dig_off[i] - dig_base, dl = dig_off[i + 1] - dig_off[i];
     uint8_t rr[32], ss[32];
     int st;
     if (ki < 0) st = 2;                       // nil key

@@ -729,7 +729,9 @@ static int bccsp_device_submit(fabgpu_ctx* ctx, int slot, const uint8_t* keys_xy
     DevSlot& ds = dv.slot[slot];
     auto& gb = ctx->gb[slot];
     CK(ctx, cudaSetDevice(dv.id));
-    const size_t sig_bytes = sig_off[n], dig_bytes = dig_off[n];
+    // sig_off / dig_off may be a window of a longer table (a chunk of a call): bytes [off[0], off[n]) of the blobs belong to it
+    const uint32_t sig_base = sig_off[0], dig_base = dig_off[0];
+    const size_t sig_bytes = sig_off[n] - sig_base, dig_bytes = dig_off[n] - dig_base;
     int rc = 0;
     if (n > gb.n_cap) {
         const size_t c = round_up32(n + (n >> 2) + 1024);
@@ -761,8 +763,8 @@ static int bccsp_device_submit(fabgpu_ctx* ctx, int slot, const uint8_t* keys_xy
     ctx->pool->run([&](int tid) {
         auto slice = [&](size_t total, size_t& lo, size_t& hi) { lo = total * (size_t)tid / T; hi = total * (size_t)(tid + 1) / T; };
         size_t lo, hi;
-        slice(sig_bytes, lo, hi); stage_copy(gb.h_sigs + lo, sigs + lo, hi - lo);
-        slice(dig_bytes, lo, hi); stage_copy(gb.h_digs + lo, digests + lo, hi - lo);
+        slice(sig_bytes, lo, hi); stage_copy(gb.h_sigs + lo, sigs + sig_base + lo, hi - lo);
+        slice(dig_bytes, lo, hi); stage_copy(gb.h_digs + lo, digests + dig_base + lo, hi - lo);
         slice(4 * (n + 1), lo, hi); stage_copy((uint8_t*)gb.h_sig_off + lo, (const uint8_t*)sig_off + lo, hi - lo);
         slice(4 * (n + 1), lo, hi); stage_copy((uint8_t*)gb.h_dig_off + lo, (const uint8_t*)dig_off + lo, hi - lo);
         slice(4 * n, lo, hi); stage_copy((uint8_t*)gb.h_kidx + lo, (const uint8_t*)key_idx + lo, hi - lo);
@@ -781,7 +783,7 @@ static int bccsp_device_submit(fabgpu_ctx* ctx, int slot, const uint8_t* keys_xy
     }
     bdev::bccsp_gate_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(gb.d_sigs, gb.d_sig_off, gb.d_digs, gb.d_dig_off, gb.d_kidx, gb.d_slot_of, gb.d_keys, K,
                                                                         (uint32_t)n, gb.d_r, gb.d_s, gb.d_e, gb.d_ks, all_slots ? nullptr : gb.d_qx,
-                                                                        all_slots ? nullptr : gb.d_qy, gb.d_pre);
+                                                                        all_slots ? nullptr : gb.d_qy, gb.d_pre, sig_base, dig_base);
     ctx->launches++;
     CK(ctx, cudaGetLastError());
     rc = launch_verify(ctx, dv, all_slots ? MODE_CACHED : MODE_MIXED, gb.d_ks, gb.d_qx, gb.d_qy, gb.d_e, gb.d_r, gb.d_s, n, gb.d_mask, gb.d_off, st);
@@ -790,7 +792,7 @@ static int bccsp_device_submit(fabgpu_ctx* ctx, int slot, const uint8_t* keys_xy
     ctx->launches++;
     CK(ctx, cudaGetLastError());
     CK(ctx, cudaMemcpyAsync(gb.h_status, gb.d_status, n, cudaMemcpyDeviceToHost, st));
-    gb.t_submit = t1;
+    gb.t_submit = t1; gb.n = n;
     ctx->timing[1] = us(t0, t1);
     return FABGPU_OK;
 }
@@ -889,9 +891,40 @@ int fabgpu_bccsp_verify_batch_wait(fabgpu_ctx* ctx, int slot, uint8_t* status, s
 int fabgpu_bccsp_verify_batch(fabgpu_ctx* ctx, const uint8_t* keys_xy, int K, const int32_t* key_idx, const uint8_t* digests,
                               const uint32_t* dig_off, const uint8_t* sigs, const uint32_t* sig_off, size_t n, uint8_t* status)
 {
-    if (!ctx || (n && !status)) return FABGPU_E_ARG;
-    // one synchronous caller at a time; slot 0 of the async pair
-    std::lock_guard<std::mutex> lk(ctx->sync_mu);
+    if (!ctx || (n && (!status || !key_idx || !dig_off || !sig_off))) return FABGPU_E_ARG;
+    std::lock_guard<std::mutex> lk(ctx->sync_mu);        // one synchronous caller at a time
+    // A large call is cut into one chunk per slot: the copy of chunk c+1 runs under the kernels of chunk c and all chunks' verify
+    // launches are resident together (they fill the machine like one launch).  Needs every slot free; otherwise, and for
+    // small calls, the whole batch goes through slot 0.
+    if (n >= 24576 && device_gates_apply(ctx, dig_off, sig_off, n)) {
+        std::unique_lock<std::mutex> l[FABGPU_SLOTS];
+        bool all_free = true;
+        for (int c = 0; c < FABGPU_SLOTS; c++) { l[c] = std::unique_lock<std::mutex>(ctx->gb_mu[c]); all_free = all_free && !ctx->gb[c].busy; }
+        if (all_free) {
+            size_t lo[FABGPU_SLOTS + 1];
+            for (int c = 0; c <= FABGPU_SLOTS; c++) lo[c] = n * (size_t)c / FABGPU_SLOTS;
+            int submitted = 0, rc = FABGPU_OK;
+            {
+                std::lock_guard<std::mutex> lk0(ctx->slot0_mu);
+                auto t_start = std::chrono::steady_clock::now();
+                ctx->timing[0] = ctx->timing[1] = ctx->timing[2] = ctx->timing[3] = 0;
+                std::vector<int32_t> slot_of;
+                rc = resolve_key_tables(ctx, keys_xy, K, key_idx, n, slot_of);
+                ctx->timing[0] = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_start).count();
+                if (!rc && fault_injected()) { ctx->last_error = "fault injected (FABGPU_FAULT_INJECT=1)"; rc = FABGPU_E_INJECTED; }
+                for (int c = 0; c < FABGPU_SLOTS && !rc; c++) {
+                    rc = bccsp_device_submit(ctx, c, keys_xy, K, key_idx + lo[c], digests, dig_off + lo[c], sigs, sig_off + lo[c], lo[c + 1] - lo[c], slot_of);
+                    if (!rc) submitted++;
+                }
+            }
+            for (int c = 0; c < submitted; c++) {                       // drain what was enqueued even after an error
+                int rc2 = bccsp_device_finish(ctx, c, status + lo[c]);
+                if (!rc) rc = rc2;
+            }
+            if (rc && submitted < FABGPU_SLOTS) cudaStreamSynchronize(ctx->devs[0].slot[submitted < FABGPU_SLOTS ? submitted : 0].stream);
+            return rc;
+        }
+    }
     int rc = fabgpu_bccsp_verify_batch_async(ctx, 0, keys_xy, K, key_idx, digests, dig_off, sigs, sig_off, n);
     if (rc) return rc;
     return fabgpu_bccsp_verify_batch_wait(ctx, 0, status, n);

@@ -401,6 +401,34 @@ def test_bccsp_batch_with_forced_key_tables():
     csp2.close()
 
 
+def test_bccsp_batch_large_call_is_chunked_over_the_slots():
+    """A blocking fabgpu_bccsp_verify_batch call of >= 24576 signatures is cut into one chunk per slot (offset tables windowed,
+    blobs rebased on the device): statuses must equal the oracle's across the chunk boundaries, with damaged DER, empty
+    signatures / digests and nil keys sprinkled in, and while another thread's async batch occupies a slot (single-slot path)."""
+    c = pkg().binding.Context(max_batch=1 << 16)
+    w = workload.Workload(40003, 7, seed=77)
+    w.tamper_r(0.07)
+    rnd = random.Random(5)
+    sigs = bytearray(w.sigs.tobytes())
+    for i in rnd.sample(range(w.n), 900):                    # damage one byte of the DER header / integer headers / body
+        o_ = int(w.sig_off[i]); ln = int(w.sig_off[i + 1]) - o_
+        sigs[o_ + rnd.choice([0, 1, 2, 3, 4, ln - 1, rnd.randrange(ln)])] ^= 1 << rnd.randrange(8)
+    sigs = np.frombuffer(bytes(sigs), np.uint8)
+    kidx = w.key_idx.copy()
+    kidx[rnd.sample(range(w.n), 50)] = -1                    # nil keys
+    kidx[rnd.sample(range(w.n), 50)] = 7                     # not a key of the table
+    exp = fast.verify_batch(w.keys_xy, kidx, w.digest, w.dig_off(), sigs, w.sig_off, nthreads=os.cpu_count())
+    assert len(set(exp.tolist())) >= 6
+    got = c.bccsp_verify_batch(w.keys_xy, kidx, w.digest, w.dig_off(), sigs, w.sig_off)
+    assert (got == exp).all()
+    # a slot is taken by an async batch: the blocking call must still be exact (it then goes through slot 0 alone)
+    small = workload.Workload(2000, 2, seed=78)
+    nn = c.bccsp_verify_batch_async(2, small.keys_xy, small.key_idx, small.digest, small.dig_off(), small.sigs, small.sig_off)
+    assert (c.bccsp_verify_batch(w.keys_xy, kidx, w.digest, w.dig_off(), sigs, w.sig_off) == exp).all()
+    assert (c.bccsp_verify_batch_wait(2, nn) == 0).all()
+    c.close()
+
+
 def test_bccsp_batch_async_two_slots_in_flight():
     """fabgpu_bccsp_verify_batch_async / _wait: two different batches in flight on the two slots, several rounds; each
     slot's statuses must equal the oracle's for ITS batch (no cross-talk between the slots' buffers), in either gate mode."""
