@@ -921,7 +921,7 @@ int fabgpu_bccsp_verify_batch(fabgpu_ctx* ctx, const uint8_t* keys_xy, int K, co
                 int rc2 = bccsp_device_finish(ctx, c, status + lo[c]);
                 if (!rc) rc = rc2;
             }
-            if (rc && submitted < FABGPU_SLOTS) cudaStreamSynchronize(ctx->devs[0].slot[submitted < FABGPU_SLOTS ? submitted : 0].stream);
+            if (rc && submitted < FABGPU_SLOTS) cudaStreamSynchronize(ctx->devs[0].slot[submitted].stream);   // a submit that failed half-way
             return rc;
         }
     }
