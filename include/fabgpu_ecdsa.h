@@ -121,9 +121,11 @@ int fabgpu_verify_p256_device_keyed(fabgpu_ctx* ctx, int dev_index, int all_cach
 /* ---- bccsp level: raw DER signatures + digests + keys -> three-valued status (sw.CSP.Verify semantics) -- */
 
 /* keys_xy: K x 64 bytes (X || Y, big-endian).  key_idx[i] in [0,K), or < 0 for a nil key.  digests / sigs are
- * concatenations indexed by (n+1)-entry offset tables.  status[i] receives FABGPU_ST_*.  The host gates (DER per
- * Go encoding/asn1, positivity, low-S, r < 2^256) run on the CPU; survivors are verified on the GPU.  Keys used by at
- * least FABGPU_KEY_MIN_USES (env, default 256; negative disables) signatures of the call are registered automatically. */
+ * concatenations indexed by (n+1)-entry offset tables.  status[i] receives FABGPU_ST_*.  The gates (DER per Go
+ * encoding/asn1, positivity, low-S, r < 2^256) run in a kernel in front of the verify kernel (on the context's host
+ * threads for multi-device contexts or with FABGPU_BCCSP_HOST_GATES=1); survivors are verified.  Keys used by at least
+ * FABGPU_KEY_MIN_USES (env, default 256; negative disables) signatures of the call get a window table automatically.
+ * A call of >= 24576 signatures is cut into one chunk per slot internally when all slots are free. */
 int fabgpu_bccsp_verify_batch(fabgpu_ctx* ctx, const uint8_t* keys_xy, int K, const int32_t* key_idx,
                               const uint8_t* digests, const uint32_t* dig_off, const uint8_t* sigs,
                               const uint32_t* sig_off, size_t n, uint8_t* status);
@@ -199,7 +201,8 @@ int fabgpu_test_fieldop(fabgpu_ctx* ctx, int op, const uint8_t* a, const uint8_t
  * (w = g_window_bits of fabgpu_build_info); otherwise the table in that raw key slot (w = key_window_bits). */
 int fabgpu_test_table_entries(fabgpu_ctx* ctx, int key_slot, const uint32_t* window, const uint32_t* digit, size_t n, uint8_t* out);
 /* Phase times of the last fabgpu_bccsp_verify_batch call, microseconds: [0] key-table lookup/registration,
- * [1] host gates + packing, [2] H2D + kernels + D2H (enqueue to completion), [3] status scatter.  For metrics export
+ * [1] staging copy into pinned memory (host gates + packing on the host-gated path), [2] H2D + kernels + D2H (enqueue to
+ * completion), [3] status copy-out.  For metrics export
  * (the reference only has a block-level histogram, gossip/metrics/metrics.go:187-194). */
 int fabgpu_last_timing(const fabgpu_ctx* ctx, double out_us[4]);
 /* Compile-time table shapes: window bits of the fixed-base table of G and of the per-key tables. */
