@@ -1084,6 +1084,8 @@ static int upload_msp(fabgpu_ctx* ctx, const uint8_t* id_blob, const uint32_t* i
     std::lock_guard<std::mutex> lk0(ctx->slot0_mu);
     auto& dm = ctx->dm;
     CK(ctx, cudaSetDevice(ctx->devs[0].id));
+    // blocks already enqueued on a slot were launched with the OLD tables (passed by value): let them finish before those go away
+    for (auto& ds : ctx->devs[0].slot) CK(ctx, cudaStreamSynchronize(ds.stream));
     void* old[] = {dm.id_blob, dm.valid, dm.keys_xy, dm.channel, dm.id_off, dm.key_slot, dm.msp_code, dm.ht_idx, dm.nodes, dm.principal_code, dm.ht_hash};
     for (void* p : old) if (p) cudaFree(p);
     dm = fabgpu_ctx::DevMsp();
