@@ -46,6 +46,12 @@ def alg_macs_cached(wg, wq):
 
 
 KEYS = 64
+
+
+def workload_string(B):
+    """config.workload, identical for both arms (the driver compares the two strings)."""
+    return "configs[1]: %d-signature batch per step and GPU, %d keys, SHA-256 digests of 1 KiB messages, low-S DER signatures" % (B, KEYS)
+
 NCU_DRAM_BYTES_PER_LAUNCH_64K = 231995648 + 6491392   # ecdsa_verify_cached_kernel, profiles/r1_final_cached_ncu_summary.txt (dram read + write)
 NCU_FMAHEAVY_BUSY = 0.6222              # sm__pipe_fmaheavy_cycles_active, % of elapsed, same capture: the binding unit of that kernel
 
@@ -147,7 +153,8 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": v, "unit": "verifies/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 limbs (256-bit modular integer)",
         "data": "synthetic",
-        "config": {"workload": "configs[1]: %d-signature batch, %d keys, SHA-256 digests, low-S DER signatures" % (w.n, KEYS), "batch_per_step": w.n},
+        "config": {"workload": workload_string(w.n), "batch_per_step": w.n,
+                   "note": "the CPU arm runs on rank 0 only and verifies one batch per step whatever --gpus says (the GPU arm verifies one batch per GPU per step); both are rates"},
         "cpu_baseline": {"value": v, "unit": "verifies/s", "cores": cores, "kind": "port",
                          "sample": "%d steps x %d signatures through oracle/c (bccsp/sw gates + ecdsa.Verify steps on OpenSSL BN/EC primitives), %d of %d logical CPUs (best of all/half/quarter)" % (args.steps, w.n, cores, os.cpu_count() or 1)},
         "e2e": {"value": v, "unit": "verifies/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -376,6 +383,50 @@ def run_gpu(args):
                         "host_us": {"enqueue": ph[0], "wait_for_device": ph[2], "duplicate_txid_pass": ph[3]}}
     clocks = sampler.stop() if rank == 0 else None      # sampled across the three timed loops (key-table, generic, e2e)
 
+    # ---- parity at the named multi-GPU shape (BASELINE.json configs[3] on 8 GPUs, configs[4] on 4; untimed) ----------------
+    # Every rank verifies ITS contiguous shard of a batch with 5 % tampered r (+ the adversarial tail of tests/vectors.py on the
+    # last rank) through the bccsp-level C-ABI call, the validity bitmask is all-gathered over NCCL exactly as in the timed
+    # legs, and rank 0 compares it bit for bit with the oracle's C port run over all shards.
+    parity = None
+    if not args.no_parity:
+        from tools import parity_workload as pw
+        p_total, p_keys, p_name = pw.named_shape(world)
+        shard = pw.Shard(rank, world, p_total, p_keys)
+        st_shard = ctx.bccsp_verify_batch(*shard.args())
+        p_words = sharding.shard_words(p_total, world)
+        lw = np.zeros(p_words, np.uint32)
+        bits = (st_shard == 0).astype(np.uint8)
+        lw[: (shard.n + 31) // 32] = np.packbits(np.concatenate([bits, np.zeros((-shard.n) % 32, np.uint8)]).reshape(-1, 32), axis=1, bitorder="little").view("<u4").reshape(-1)
+        full_mask = sharding.allgather_mask(torch.from_numpy(lw.view(np.int32)).to(dev), p_total, world).cpu().numpy().view(np.uint32)
+        st_dev = torch.from_numpy(st_shard).to(dev)
+        if world > 1:
+            st_all = torch.empty(p_total, dtype=torch.uint8, device=dev)
+            dist.all_gather_into_tensor(st_all, st_dev)
+        else:
+            st_all = st_dev
+        st_all = st_all.cpu().numpy()
+        if rank == 0:
+            from oracle import fast
+            ncpu = os.cpu_count() or 8
+            exp, n_tamper, tail = [], 0, []
+            for rk in range(world):
+                sh = shard if rk == rank else pw.Shard(rk, world, p_total, p_keys)
+                exp.append(pw.oracle_status(sh, min(ncpu, 64)))
+                n_tamper += int(len(sh.tampered))
+                tail += sh.tail
+            exp = np.concatenate(exp)
+            exp_mask = fast.valid_mask(exp)
+            parity = {"workload": p_name + ", 5 % of r tampered (one bit), adversarial tail of tests/vectors.py on the last shard",
+                      "n": int(p_total), "shards": world, "tampered": n_tamper, "tail_cases": len(tail),
+                      "zeros": int(p_total - int((exp == 0).sum())), "mask_zeros_gpu": int(p_total - int(np.unpackbits(full_mask.view(np.uint8)).sum())),
+                      "mask_equals_oracle": bool((full_mask == exp_mask).all()), "status_equals_oracle": bool((st_all == exp).all()),
+                      "false_accepts": int(((st_all == 0) & (exp != 0)).sum()), "false_rejects": int(((st_all != 0) & (exp == 0)).sum()),
+                      "collective": "all_gather_into_tensor of the uint32 mask words (%s), then of the status bytes" % ("NCCL" if world > 1 else "single rank"),
+                      "oracle": "oracle/c (bccsp/sw gates + ecdsa.Verify steps on OpenSSL primitives); tail cross-checked with oracle/bccsp_sw.py"}
+            assert parity["mask_equals_oracle"] and parity["status_equals_oracle"], "parity leg: GPU bitmask differs from the oracle: %r" % (parity,)
+        sync_all()
+
+
     # ---- max over ranks ---------------------------------------------------------------------------------------
     times = torch.tensor([dev_ms, e2e_s * 1e3, wall * 1e3, gen_ms, key_register_ms, e2e_sync_s * 1e3, conc_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -400,7 +451,7 @@ def run_gpu(args):
             "metric": METRIC, "value": value, "unit": "verifies/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32 limbs (256-bit modular integer)", "data": "synthetic",
-            "config": {"workload": "configs[1]: %d-signature batch per GPU, %d keys, SHA-256 digests of 1 KiB messages, low-S DER signatures" % (B, KEYS),
+            "config": {"workload": workload_string(B),
                        "batch_per_gpu": B, "global_batch": n_total, "parallelism": "batch split x%d + NCCL all-gather of the bitmask" % world,
                        "timing": "per-step CUDA events on the launch stream, summed; L2 flushed (256 MiB fill) between steps; %d rotating input buffers" % ROT,
                        "wall_ms_incl_flush": wall_ms},
@@ -441,6 +492,7 @@ def run_gpu(args):
                              "sample": "%d signatures in %.1f s through oracle/c (bccsp/sw gates + ecdsa.Verify steps on OpenSSL BN/EC primitives), %d of %d logical CPUs (best of all/half/quarter)" % (cpu_done, cpu_el, cores, os.cpu_count() or 1)},
             "clocks": clocks,
             "block_replay": block_replay,
+            "parity": parity,
         }
         if block_replay:
             block_replay["cpu_port_ms_per_block_est"] = 4 * args.block_txs / cpu_v * 1e3
@@ -459,6 +511,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--block-txs", type=int, default=10000, help="transactions in the block-replay leg (configs[2])")
     ap.add_argument("--no-block", action="store_true", help="skip the block-replay leg")
+    ap.add_argument("--no-parity", action="store_true", help="skip the (untimed) named-shape parity leg")
     args = ap.parse_args()
     # The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version line on the first
     # collective), so everything but the result goes to stderr: fd 1 is pointed at fd 2 for the duration of the run and the

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include "ecdsa_verify.cuh"
+#include "ecdsa_batchaffine.cuh"
 
 namespace fabgpu {
 
@@ -87,6 +88,99 @@ ecdsa_verify_cached_kernel(const int32_t* __restrict__ key_slot, const uint8_t* 
             res = ecdsa_verify_one_cached(qtab + (size_t)slot * (FAB_Q_WINDOWS * FAB_Q_ENTRIES), load_be32(e + o), load_be32(r + o),
                                           load_be32(s + o), gtab);
         }
+    }
+    const uint32_t vmask = __ballot_sync(0xffffffffu, res == V_VALID);
+    if ((threadIdx.x & 31u) == 0 && idx < n) {
+        mask[idx >> 5] = vmask;
+        if (offcurve) offcurve[idx >> 5] = 0u;
+    }
+}
+
+// ---- batch-affine key-table kernel (ecdsa_batchaffine.cuh) ----
+#ifndef FAB_BA_THREADS
+#define FAB_BA_THREADS 256            // signatures (= threads) per CTA; the shared inversion is amortised over this many
+#endif
+#ifndef FAB_BA_MINBLOCKS
+#define FAB_BA_MINBLOCKS 2
+#endif
+#ifndef FAB_BA_INVWARPS
+#define FAB_BA_INVWARPS 1             // warps that run the shared inversion of a round (each lane: THREADS / (32 INVWARPS) values)
+#endif
+
+// One exchange round: every thread contributes v, the round's inverter warps invert all FAB_BA_THREADS values with Montgomery's
+// trick (ba_inverse_lane), every thread gets its own inverse back.  exa / exb: 8 x FAB_BA_THREADS words each, [limb][thread].
+template <bool MODN> __device__ __forceinline__ u256 ba_cta_inverse(const u256& v, uint32_t* exa, uint32_t* exb, int round)
+{
+    constexpr int T = FAB_BA_THREADS, W = T / 32, K = FAB_BA_INVWARPS, V = T / (32 * K);
+    const int tid = threadIdx.x;
+#pragma unroll
+    for (int l = 0; l < 8; l++) exa[l * T + tid] = v.v[l];
+    __syncthreads();
+    const int first = (round * K + (int)blockIdx.x) % W;
+    const int rank = ((tid >> 5) - first + W) % W;             // this warp's position among the round's inverter warps
+    if (rank < K) {
+        const int g = rank * 32 + (tid & 31);                  // handles values g, g + 32 K, g + 64 K, ...
+        ba_inverse_lane<MODN>(exa + g, exb + g, V, 32 * K, T);
+    }
+    __syncthreads();
+    u256 r;
+#pragma unroll
+    for (int l = 0; l < 8; l++) r.v[l] = exa[l * T + tid];
+    return r;
+}
+
+// The complete per-signature routine for the (never expected) zero-denominator case; out of line, shares nothing with the hot path.
+__device__ __noinline__ uint32_t ba_fallback_verify(const aff* qtab, const uint8_t* e, const uint8_t* r, const uint8_t* s, const aff* gtab)
+{
+    return ecdsa_verify_one_cached(qtab, load_be32(e), load_be32(r), load_be32(s), gtab);
+}
+
+// Same contract as ecdsa_verify_cached_kernel (one signature per thread, SoA inputs, ballot mask out); the CTA must be
+// FAB_BA_THREADS wide.  Three exchange rounds: s^-1 mod n, the denominators of level 1, the denominators of level 2.
+__global__ void __launch_bounds__(FAB_BA_THREADS, FAB_BA_MINBLOCKS)
+ecdsa_verify_ba_kernel(const int32_t* __restrict__ key_slot, const uint8_t* __restrict__ e, const uint8_t* __restrict__ r,
+                       const uint8_t* __restrict__ s, uint32_t n, const aff* __restrict__ gtab, const aff* __restrict__ qtab,
+                       uint32_t* __restrict__ mask, uint32_t* __restrict__ offcurve, const uint32_t* __restrict__ n_dev, uint32_t n_base)
+{
+    constexpr int T = FAB_BA_THREADS;
+    __shared__ uint32_t dig[FAB_BA_NP * T];
+    __shared__ uint32_t exa[8 * T], exb[8 * T];
+    if (n_dev) n = min(n, n_base + *n_dev);
+    const uint32_t idx = blockIdx.x * T + threadIdx.x;
+    const size_t o = (size_t)idx * 32;
+    const aff* qt = qtab;
+    bool ok = false;
+    u256 ev, rv, sv;
+    if (idx < n) {
+        const int32_t slot = key_slot[idx];
+        if (slot >= 0) {
+            qt = qtab + (size_t)slot * (FAB_Q_WINDOWS * FAB_Q_ENTRIES);
+            ev = load_be32(e + o); rv = load_be32(r + o); sv = load_be32(s + o);
+            ok = ba_range_ok(rv, sv);
+        }
+    }
+    uint32_t* mydig = dig + threadIdx.x;
+    const u256 w = ba_cta_inverse<true>(ok ? sv : u256_const(1, 0, 0, 0, 0, 0, 0, 0), exa, exb, 0);
+    BaScratch sc;
+    uint32_t exc = 0;
+    u256 c = fe_one();
+    if (ok) {
+        ba_scalars(ev, rv, w, mydig, T);
+        c = ba_forward<true>(FAB_BA_N1, gtab, qt, mydig, T, nullptr, 0u, sc.pre, exc);
+    }
+    u256 inv = ba_cta_inverse<false>(c, exa, exb, 1);
+    uint32_t m1 = 0;
+    jac acc = jac_infinity();
+    c = fe_one();
+    if (ok) {
+        m1 = ba_backward<true, false>(FAB_BA_N1, inv, gtab, qt, mydig, T, nullptr, 0u, sc.pre, sc.pts, acc);
+        c = ba_forward<false>(FAB_BA_N2, gtab, qt, mydig, T, sc.pts, m1, sc.pre, exc);
+    }
+    inv = ba_cta_inverse<false>(c, exa, exb, 2);
+    uint32_t res = V_INVALID;
+    if (ok) {
+        ba_backward<false, true>(FAB_BA_N2, inv, gtab, qt, mydig, T, sc.pts, m1, sc.pre, nullptr, acc);
+        res = exc ? ba_fallback_verify(qt, e + o, r + o, s + o, gtab) : final_check(acc, load_be32(r + o));
     }
     const uint32_t vmask = __ballot_sync(0xffffffffu, res == V_VALID);
     if ((threadIdx.x & 31u) == 0 && idx < n) {

@@ -13,6 +13,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <shared_mutex>
 #include <string>
 #include <thread>
 #include <unordered_map>
@@ -124,7 +125,11 @@ struct fabgpu_ctx {
     size_t max_batch = 0;      // per slot, whole context
     size_t dev_cap = 0;        // per device per slot (multiple of 32)
     std::string last_error;
-    std::mutex mu;         // guards enqueue/wait
+    std::mutex mu;         // guards enqueue and the key-table bookkeeping
+    // Key-table slots: whoever turns handles into raw slot numbers and then enqueues kernels that read those slots' tables holds this
+    // SHARED from the resolution to the last enqueue; fabgpu_keys_register holds it EXCLUSIVE while it recycles slots (it then drains
+    // every stream before rebuilding a table), so a slot cannot change hands between "resolved" and "enqueued".  Order: tab_mu, then mu.
+    std::shared_mutex tab_mu;
     std::mutex sync_mu;    // one synchronous fabgpu_bccsp_verify_batch at a time
     std::mutex sync_blk_mu;   // one synchronous fabgpu_validate_block / _envelopes at a time
     std::mutex slot0_mu;   // serialises the composite calls that stage through slot 0's pinned buffers
@@ -137,6 +142,7 @@ struct fabgpu_ctx {
     std::vector<uint32_t> slot_gen;          // bumped whenever a slot is recycled: handles carry the generation they were issued under
     unsigned long long tick = 0;
     int key_min_uses = 256;
+    int cached_kernel = 1;     // key-table kernel: 1 = batch-affine (ecdsa_verify_ba_kernel), 0 = Jacobian chain (ecdsa_verify_cached_kernel); FABGPU_CACHED_KERNEL
     double timing[4] = {0, 0, 0, 0};   // last fabgpu_bccsp_verify_batch: key lookup, host gates, device (H2D+kernel+D2H), scatter [us]
     // block validation (fabgpu_msp_configure / fabgpu_validate_block), device 0 of the context
     blockval::MspTable msp;
@@ -270,11 +276,17 @@ int launch_verify(fabgpu_ctx* ctx, const Device& dv, int mode, const int32_t* ke
         // finishes in 0.315 ms against 0.346 ms as 512 CTAs of 128 threads; beyond one wave 256-thread CTAs quantise best
         // (256k: 231 M/s against 223 / 212 for 128 / 512); below ~12 warps per SM small CTAs spread over all SMs win
         // (fewer warps per scheduler = lower latency per warp), and so they do when the batch size is only an upper bound.
+        if (ctx->cached_kernel == 1) {
+            // batch-affine accumulation with CTA-shared inversions (ecdsa_batchaffine.cuh): fixed CTA width
+            const unsigned blocks = (unsigned)((n + FAB_BA_THREADS - 1) / FAB_BA_THREADS);
+            ecdsa_verify_ba_kernel<<<blocks, FAB_BA_THREADS, 0, st>>>(key_slot, e, r, s, (uint32_t)n, dv.gtab, dv.qtab, mask, off, n_dev, n_base);
+        } else {
         unsigned threads = 128;
         const size_t sms = (size_t)dv.sms;
         if (!n_dev && n > sms * 384) threads = (n <= sms * FAB_CACHED_THREADS) ? FAB_CACHED_THREADS : 256;
         const unsigned blocks = (unsigned)((n + threads - 1) / threads);
         ecdsa_verify_cached_kernel<<<blocks, threads, 0, st>>>(key_slot, e, r, s, (uint32_t)n, dv.gtab, dv.qtab, mask, off, n_dev, n_base);
+        }
         ctx->launches++;
         CK(ctx, cudaGetLastError());
     }
@@ -438,6 +450,8 @@ int init_impl(fabgpu_ctx* ctx, const int* device_ids, int n_dev, size_t max_batc
         ctx->slot_gen.assign(ctx->key_slots, 0u);
         const char* mu = getenv("FABGPU_KEY_MIN_USES");
         ctx->key_min_uses = mu ? atoi(mu) : 256;           // a table costs about 300 generic verifications to build
+        const char* ck = getenv("FABGPU_CACHED_KERNEL");
+        if (ck) ctx->cached_kernel = (ck[0] == 'j' || ck[0] == '0') ? 0 : 1;      // "jac" / "0": the Jacobian-chain kernel
     }
     ctx->dev_cap = round_up32((max_batch + ids.size() - 1) / ids.size());
     ctx->devs.resize(ids.size());
@@ -493,6 +507,13 @@ int init_impl(fabgpu_ctx* ctx, const int* device_ids, int n_dev, size_t max_batc
     return FABGPU_OK;
 }
 
+// device temporaries released on every path (fabgpu_keys_register)
+struct DevTmp {
+    std::vector<void*> p;
+    ~DevTmp() { for (void* q : p) if (q) cudaFree(q); }
+    template <typename T> cudaError_t alloc(T*& out, size_t bytes) { void* q = nullptr; cudaError_t e = cudaMalloc(&q, bytes); out = (T*)q; if (e == cudaSuccess) p.push_back(q); return e; }
+};
+
 template <typename T> int grow_dev(fabgpu_ctx* ctx, T*& p, size_t bytes) { if (p) cudaFree(p); p = nullptr; CK(ctx, cudaMalloc(&p, bytes)); return FABGPU_OK; }
 template <typename T> int grow_host(fabgpu_ctx* ctx, T*& p, size_t bytes) { if (p) cudaFreeHost(p); p = nullptr; CK(ctx, cudaHostAlloc(&p, bytes, cudaHostAllocPortable)); return FABGPU_OK; }
 
@@ -547,6 +568,7 @@ int fabgpu_host_buffers(fabgpu_ctx* ctx, int slot, uint8_t** qx, uint8_t** qy, u
 static int verify_async_impl(fabgpu_ctx* ctx, int slot, size_t n, bool keyed)
 {
     if (!ctx || slot < 0 || slot >= FABGPU_SLOTS) return FABGPU_E_ARG;
+    std::shared_lock<std::shared_mutex> rl(ctx->tab_mu);     // handles -> slots -> enqueue, see fabgpu_ctx::tab_mu
     std::lock_guard<std::mutex> lk(ctx->mu);
     if (n > ctx->max_batch) { ctx->last_error = "n exceeds max_batch"; return FABGPU_E_ARG; }
     if (fault_injected()) { ctx->last_error = "fault injected (FABGPU_FAULT_INJECT=1)"; return FABGPU_E_INJECTED; }
@@ -576,6 +598,22 @@ int fabgpu_key_slot_capacity(const fabgpu_ctx* ctx) { return ctx ? ctx->key_slot
 int fabgpu_keys_register(fabgpu_ctx* ctx, const uint8_t* keys_xy, int K, int32_t* slots_out)
 {
     if (!ctx || K < 0 || (K && (!keys_xy || !slots_out))) return FABGPU_E_ARG;
+    // Fast path under the shared lock: every key already owns a table (the steady state of KeyImport / resolve_key_tables).
+    {
+        std::shared_lock<std::shared_mutex> rl(ctx->tab_mu);
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        bool all = true;
+        for (int k = 0; k < K && all; k++) all = ctx->key_map.count(std::string((const char*)keys_xy + 64 * (size_t)k, 64)) != 0;
+        if (all) {
+            ctx->tick++;
+            for (int k = 0; k < K; k++) {
+                const int sl = ctx->key_map[std::string((const char*)keys_xy + 64 * (size_t)k, 64)];
+                slots_out[k] = make_handle(ctx, sl); ctx->slot_tick[sl] = ctx->tick;
+            }
+            return FABGPU_OK;
+        }
+    }
+    std::unique_lock<std::shared_mutex> wl(ctx->tab_mu);
     std::lock_guard<std::mutex> lk(ctx->mu);
     std::vector<int> fresh;                      // indices into keys_xy that need a table
     std::vector<int32_t> fresh_slot;
@@ -590,9 +628,12 @@ int fabgpu_keys_register(fabgpu_ctx* ctx, const uint8_t* keys_xy, int K, int32_t
         for (int sl = 0; sl < ctx->key_slots; sl++)
             if (!slot_taken[sl] && (best < 0 || ctx->slot_tick[sl] < ctx->slot_tick[best])) best = sl;
         if (best < 0) { slots_out[k] = -1; continue; }            // more distinct keys in one call than slots: stays generic
-        if (!ctx->slot_key[best].empty()) { ctx->key_map.erase(ctx->slot_key[best]); ctx->slot_gen[best]++; }   // old handles die here
-        ctx->slot_key[best] = key; ctx->key_map[key] = best; ctx->slot_tick[best] = ctx->tick; slot_taken[best] = 1;
-        slots_out[k] = make_handle(ctx, best);
+        // The slot's old owner loses it NOW (its handles die with the generation bump), but the new key is mapped only after
+        // its table exists on every device: a failure below leaves the slot empty, never pointing at another key's table.
+        if (!ctx->slot_key[best].empty()) { ctx->key_map.erase(ctx->slot_key[best]); ctx->slot_key[best].clear(); }
+        ctx->slot_gen[best]++;
+        ctx->slot_tick[best] = ctx->tick; slot_taken[best] = 1;
+        slots_out[k] = -1;
         fresh.push_back(k); fresh_slot.push_back(best);
     }
     if (fresh.empty()) return FABGPU_OK;
@@ -600,46 +641,49 @@ int fabgpu_keys_register(fabgpu_ctx* ctx, const uint8_t* keys_xy, int K, int32_t
     std::vector<uint8_t> fk(64 * (size_t)F);
     for (int i = 0; i < F; i++) memcpy(fk.data() + 64 * (size_t)i, keys_xy + 64 * (size_t)fresh[i], 64);
     std::vector<uint32_t> flags(F, 0);
-    for (auto& dv : ctx->devs) {
+    auto build_on = [&](Device& dv) -> int {
+        DevTmp tmp;
         CK(ctx, cudaSetDevice(dv.id));
         // an evicted slot's table may still be read by a batch in flight: drain this device first (registration is rare)
         for (auto& ds : dv.slot) CK(ctx, cudaStreamSynchronize(ds.stream));
+        CK(ctx, cudaDeviceSynchronize());            // launches on caller streams (fabgpu_verify_p256_device_keyed) as well
         uint8_t* d_keys = nullptr; int32_t* d_slots = nullptr; uint32_t* d_flags = nullptr; u256* d_scratch = nullptr;
-        CK(ctx, cudaMalloc(&d_keys, fk.size()));
-        CK(ctx, cudaMalloc(&d_slots, 4 * (size_t)F));
-        CK(ctx, cudaMalloc(&d_flags, 4 * (size_t)F));
+        CK(ctx, tmp.alloc(d_keys, fk.size()));
+        CK(ctx, tmp.alloc(d_slots, 4 * (size_t)F));
+        CK(ctx, tmp.alloc(d_flags, 4 * (size_t)F));
         CK(ctx, cudaMemcpy(d_keys, fk.data(), fk.size(), cudaMemcpyHostToDevice));
         CK(ctx, cudaMemcpy(d_slots, fresh_slot.data(), 4 * (size_t)F, cudaMemcpyHostToDevice));
 #if FAB_Q_TWO_LEVEL
         aff* d_small = nullptr;
         const size_t nsmall = ((size_t)1 << (FAB_WQ / 2)) - 1;
         const size_t threads = (size_t)F * FAB_Q_WINDOWS * 2;
-        CK(ctx, cudaMalloc(&d_scratch, threads * 2 * nsmall * sizeof(u256)));
-        CK(ctx, cudaMalloc(&d_small, threads * nsmall * sizeof(aff)));
+        CK(ctx, tmp.alloc(d_scratch, threads * 2 * nsmall * sizeof(u256)));
+        CK(ctx, tmp.alloc(d_small, threads * nsmall * sizeof(aff)));
         small_tables_kernel<<<(unsigned)((threads + 31) / 32), 32, 0, dv.slot[0].stream>>>(d_keys, F, FAB_WQ, FAB_Q_WINDOWS, d_small, d_scratch, d_flags);
         const size_t threads2 = (size_t)F * FAB_Q_WINDOWS * ((FAB_Q_ENTRIES + FAB_TAB_CHUNK - 1) / FAB_TAB_CHUNK);
         full_tables_kernel<<<(unsigned)((threads2 + 127) / 128), 128, 0, dv.slot[0].stream>>>(d_small, d_slots, d_flags, F, FAB_WQ, FAB_Q_WINDOWS, dv.qtab);
         ctx->launches += 2;
 #else
         const size_t threads = (size_t)F * FAB_Q_WINDOWS;
-        CK(ctx, cudaMalloc(&d_scratch, threads * 2 * FAB_Q_ENTRIES * sizeof(u256)));
+        CK(ctx, tmp.alloc(d_scratch, threads * 2 * FAB_Q_ENTRIES * sizeof(u256)));
         build_key_tables_kernel<<<(unsigned)((threads + 31) / 32), 32, 0, dv.slot[0].stream>>>(d_keys, d_slots, F, dv.qtab, d_scratch, d_flags);
         ctx->launches++;
 #endif
         CK(ctx, cudaGetLastError());
         CK(ctx, cudaStreamSynchronize(dv.slot[0].stream));
         CK(ctx, cudaMemcpy(flags.data(), d_flags, 4 * (size_t)F, cudaMemcpyDeviceToHost));
-#if FAB_Q_TWO_LEVEL
-        cudaFree(d_small);
-#endif
-        cudaFree(d_keys); cudaFree(d_slots); cudaFree(d_flags); cudaFree(d_scratch);
+        return FABGPU_OK;
+    };
+    for (auto& dv : ctx->devs) {
+        const int rc = build_on(dv);
+        if (rc) return rc;                        // nothing was committed: the recycled slots stay empty (handles -1), the keys stay generic
     }
     for (int i = 0; i < F; i++) {
-        if (flags[i]) continue;                   // not a curve point: no table; the generic kernel reports it as off-curve
+        if (!flags[i]) continue;                  // not a curve point: no table; the generic kernel reports it as off-curve
         const int sl = fresh_slot[i];
-        ctx->key_map.erase(ctx->slot_key[sl]);
-        ctx->slot_key[sl].clear(); ctx->slot_tick[sl] = 0; ctx->slot_gen[sl]++;
-        slots_out[fresh[i]] = -1;
+        std::string key((const char*)fk.data() + 64 * (size_t)i, 64);
+        ctx->slot_key[sl] = key; ctx->key_map[key] = sl;
+        slots_out[fresh[i]] = make_handle(ctx, sl);
     }
     return FABGPU_OK;
 }
@@ -647,8 +691,18 @@ int fabgpu_keys_register(fabgpu_ctx* ctx, const uint8_t* keys_xy, int K, int32_t
 int fabgpu_wait(fabgpu_ctx* ctx, int slot)
 {
     if (!ctx || slot < 0 || slot >= FABGPU_SLOTS) return FABGPU_E_ARG;
-    std::lock_guard<std::mutex> lk(ctx->mu);
-    return wait_slot(ctx, slot);
+    // No context lock: waiting on one slot's streams must not block the enqueue of another slot (the provider's aggregator
+    // fills slot k+1 while slot k runs).  Stream handles are immutable after fabgpu_init; errors go to a local string first.
+    for (auto& dv : ctx->devs) {
+        cudaError_t e = cudaSetDevice(dv.id);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(dv.slot[slot].stream);
+        if (e != cudaSuccess) {
+            std::lock_guard<std::mutex> lk(ctx->mu);
+            ctx->last_error = std::string("cudaStreamSynchronize failed: ") + cudaGetErrorString(e);
+            return FABGPU_E_CUDA;
+        }
+    }
+    return FABGPU_OK;
 }
 
 int fabgpu_verify_p256(fabgpu_ctx* ctx, int slot, size_t n)
@@ -735,6 +789,7 @@ static int bccsp_device_submit(fabgpu_ctx* ctx, int slot, const uint8_t* keys_xy
     int rc = 0;
     if (n > gb.n_cap) {
         const size_t c = round_up32(n + (n >> 2) + 1024);
+        gb.n_cap = 0;
         rc |= grow_host(ctx, gb.h_sig_off, 4 * (c + 1)); rc |= grow_host(ctx, gb.h_dig_off, 4 * (c + 1)); rc |= grow_host(ctx, gb.h_kidx, 4 * c);
         rc |= grow_host(ctx, gb.h_status, c);
         rc |= grow_dev(ctx, gb.d_sig_off, 4 * (c + 1)); rc |= grow_dev(ctx, gb.d_dig_off, 4 * (c + 1)); rc |= grow_dev(ctx, gb.d_kidx, 4 * c);
@@ -744,10 +799,11 @@ static int bccsp_device_submit(fabgpu_ctx* ctx, int slot, const uint8_t* keys_xy
         if (rc) return FABGPU_E_CUDA;
         gb.n_cap = c;
     }
-    if (sig_bytes > gb.sig_cap) { const size_t c = sig_bytes + (sig_bytes >> 2) + 4096; rc |= grow_host(ctx, gb.h_sigs, c); rc |= grow_dev(ctx, gb.d_sigs, c); if (rc) return FABGPU_E_CUDA; gb.sig_cap = c; }
-    if (dig_bytes > gb.dig_cap) { const size_t c = dig_bytes + (dig_bytes >> 2) + 4096; rc |= grow_host(ctx, gb.h_digs, c); rc |= grow_dev(ctx, gb.d_digs, c); if (rc) return FABGPU_E_CUDA; gb.dig_cap = c; }
+    if (sig_bytes > gb.sig_cap) { const size_t c = sig_bytes + (sig_bytes >> 2) + 4096; gb.sig_cap = 0; rc |= grow_host(ctx, gb.h_sigs, c); rc |= grow_dev(ctx, gb.d_sigs, c); if (rc) return FABGPU_E_CUDA; gb.sig_cap = c; }
+    if (dig_bytes > gb.dig_cap) { const size_t c = dig_bytes + (dig_bytes >> 2) + 4096; gb.dig_cap = 0; rc |= grow_host(ctx, gb.h_digs, c); rc |= grow_dev(ctx, gb.d_digs, c); if (rc) return FABGPU_E_CUDA; gb.dig_cap = c; }
     if ((size_t)K > gb.k_cap) {
         const size_t c = (size_t)K + 64;
+        gb.k_cap = 0;
         rc |= grow_host(ctx, gb.h_keys, 64 * c); rc |= grow_host(ctx, gb.h_slot_of, 4 * c); rc |= grow_dev(ctx, gb.d_keys, 64 * c); rc |= grow_dev(ctx, gb.d_slot_of, 4 * c);
         if (rc) return FABGPU_E_CUDA;
         gb.k_cap = c;
@@ -755,8 +811,9 @@ static int bccsp_device_submit(fabgpu_ctx* ctx, int slot, const uint8_t* keys_xy
     // stage: every host thread copies its slice of each array
     const int T = ctx->pool->size();
     bool all_slots = K > 0;
+    std::shared_lock<std::shared_mutex> rl(ctx->tab_mu);      // held until the verify kernel is enqueued: the slots cannot be recycled in between
     {
-        std::lock_guard<std::mutex> lk(ctx->mu);              // the slot table may be changing under a concurrent fabgpu_keys_register
+        std::lock_guard<std::mutex> lk(ctx->mu);
         for (int k = 0; k < K; k++) { gb.h_slot_of[k] = handle_to_slot(ctx, slot_of[k]); if (gb.h_slot_of[k] < 0) all_slots = false; }
     }
     if (K > 0) memcpy(gb.h_keys, keys_xy, 64 * (size_t)K);
@@ -1000,10 +1057,10 @@ static int bccsp_batch_hostgated(fabgpu_ctx* ctx, const uint8_t* keys_xy, int K,
                     if (g.status == FABGPU_ST_VALID) {
                         uint8_t ebuf[32];
                         host::hash_to_e(digests + dig_off[i], dl, ebuf);
-                        if (slot_of[ki] < 0) {                               // the key-table kernel never reads Qx/Qy
-                            stage32(hs.h_in[0] + 32 * k, keys_xy + 64 * (size_t)ki);
-                            stage32(hs.h_in[1] + 32 * k, keys_xy + 64 * (size_t)ki + 32);
-                        }
+                        // Qx / Qy are staged even for keys with a table: the handle is resolved again at enqueue time and, had
+                        // the slot been recycled by then, the generic kernel verifies against these (never against stale bytes)
+                        stage32(hs.h_in[0] + 32 * k, keys_xy + 64 * (size_t)ki);
+                        stage32(hs.h_in[1] + 32 * k, keys_xy + 64 * (size_t)ki + 32);
                         stage32(hs.h_in[2] + 32 * k, ebuf);
                         stage32(hs.h_in[3] + 32 * k, g.r);
                         stage32(hs.h_in[4] + 32 * k, g.s);
@@ -1196,23 +1253,40 @@ static int block_submit(fabgpu_ctx* ctx, int slot, const uint8_t* block, size_t 
     auto& bb = ctx->bbs[slot]; auto& db = ctx->dbs[slot]; auto& dm = ctx->dm;
     db.t0 = now();
     CK(ctx, cudaSetDevice(dv.id));
-    {   // identities' key tables may have been recycled by other registrations since fabgpu_msp_configure: re-issue them
-        bool stale = false;
-        {
+    // Identities' key tables may have been recycled by other registrations since fabgpu_msp_configure: re-issue them.  From the
+    // check to the last enqueue of this block the slot table is held shared (fabgpu_ctx::tab_mu): a concurrent
+    // fabgpu_keys_register waits, so dm.key_slot's raw slots stay the tables of these identities for the whole launch sequence.
+    std::shared_lock<std::shared_mutex> rl(ctx->tab_mu);
+    {
+        auto any_stale = [&] {
             std::lock_guard<std::mutex> lk(ctx->mu);
-            for (size_t i = 0; i < ctx->identity_slot.size() && !stale; i++) stale = ctx->identity_slot[i] >= 0 && handle_to_slot(ctx, ctx->identity_slot[i]) < 0;
-        }
-        if (stale) {
+            for (size_t i = 0; i < ctx->identity_slot.size(); i++)
+                if (ctx->identity_slot[i] >= 0 && handle_to_slot(ctx, ctx->identity_slot[i]) < 0) return true;
+            return false;
+        };
+        if (any_stale()) {
+            rl.unlock();
             const int n_ids = (int)ctx->identity_slot.size();
-            int rc = fabgpu_keys_register(ctx, ctx->msp.keys_xy.data(), n_ids, ctx->identity_slot.data());     // drains every stream first
+            int rc = fabgpu_keys_register(ctx, ctx->msp.keys_xy.data(), n_ids, ctx->identity_slot.data());     // exclusive; drains every stream first
             if (rc) return rc;
+            rl.lock();
             std::vector<int32_t> raw(n_ids, -1);
             dm.all_slots = true;
-            for (int i = 0; i < n_ids; i++) { raw[i] = handle_to_slot(ctx, ctx->identity_slot[i]); if (raw[i] < 0) dm.all_slots = false; }
+            {
+                std::lock_guard<std::mutex> lk(ctx->mu);      // a handle recycled again in the gap resolves to -1: that identity goes through the generic kernel
+                for (int i = 0; i < n_ids; i++) { raw[i] = handle_to_slot(ctx, ctx->identity_slot[i]); if (raw[i] < 0) dm.all_slots = false; }
+            }
+            // submitters are serialised by slot0_mu and the registration drained the device: no kernel is reading dm.key_slot now
             CK(ctx, cudaMemcpy(dm.key_slot, raw.data(), 4 * (size_t)n_ids, cudaMemcpyHostToDevice));
         }
     }
-    if (block_len > bb.block_cap) { int rc = grow_dev(ctx, bb.d_block, block_len + (block_len >> 2)); if (rc) return rc; bb.block_cap = block_len + (block_len >> 2); }
+    if (block_len > bb.block_cap) {
+        const size_t want = block_len + (block_len >> 2);
+        bb.block_cap = 0;                                   // a failed grow leaves no buffer: do not remember the old capacity
+        int rc = grow_dev(ctx, bb.d_block, want + 64);      // slack: word-wise readers (bytes_equal, the SHA loader) touch the aligned words past the end
+        if (rc) return rc;
+        bb.block_cap = want;
+    }
     const char* evs = getenv("FABGPU_BLOCK_EVENTS");          // "1": time the device stages with CUDA events (diagnostics)
     db.use_ev = evs && evs[0] == '1';
     if (db.use_ev) for (auto& e : db.ev) if (!e) CK(ctx, cudaEventCreate(&e));
@@ -1232,9 +1306,10 @@ static int block_submit(fabgpu_ctx* ctx, int slot, const uint8_t* block, size_t 
     if (T > db.tx_cap) {
         const size_t tc = T + (T >> 2) + 256, jc = tc * (1 + BD_MAX_ENDS);
         int rc = 0;
+        db.tx_cap = 0; db.j_cap = 0;                        // reset first: after a partial failure the pointers are gone
         rc |= grow_dev(ctx, db.d_env_off, 8 * (tc + 1)); rc |= grow_dev(ctx, db.d_txs, sizeof(bdev::TxDev) * tc);
         rc |= grow_dev(ctx, db.d_raw, sizeof(bdev::RawJob) * jc);
-        rc |= grow_dev(ctx, db.d_sha, sizeof(bdev::ShaJobD) * (jc + 2 * tc)); rc |= grow_dev(ctx, db.d_dig, 32 * (jc + 2 * tc));
+        rc |= grow_dev(ctx, db.d_sha, sizeof(bdev::ShaJobD) * (jc + 2 * tc)); rc |= grow_dev(ctx, db.d_dig, 32 * (jc + 2 * tc) + 64);
         rc |= grow_dev(ctx, db.d_r, 32 * jc); rc |= grow_dev(ctx, db.d_s, 32 * jc); rc |= grow_dev(ctx, db.d_qx, 32 * jc); rc |= grow_dev(ctx, db.d_qy, 32 * jc);
         rc |= grow_dev(ctx, db.d_gate, jc); rc |= grow_dev(ctx, db.d_ks, 4 * jc); rc |= grow_dev(ctx, db.d_ident, 4 * jc);
         rc |= grow_dev(ctx, db.d_mask, jc / 8 + 8); rc |= grow_dev(ctx, db.d_off, jc / 8 + 8); rc |= grow_dev(ctx, db.d_counter, 16);
@@ -1345,6 +1420,11 @@ static int validate_submit(fabgpu_ctx* ctx, int slot, const uint8_t* block, size
 {
     if (!ctx || !block || slot < 0 || slot >= FABGPU_SLOTS) return FABGPU_E_ARG;
     if (block_len >= (1ull << 32)) { ctx->last_error = "block larger than 4 GiB"; return FABGPU_E_ARG; }
+    if (env_off) {                                            // the table must be non-decreasing and stay inside the blob
+        for (size_t i = 0; i < n_env; i++)
+            if (env_off[i] > env_off[i + 1]) { ctx->last_error = "envelope offsets are not non-decreasing"; return FABGPU_E_ARG; }
+        if (n_env && env_off[n_env] > block_len) { ctx->last_error = "envelope offsets exceed the blob length"; return FABGPU_E_ARG; }
+    }
     std::lock_guard<std::mutex> lk(ctx->blk_mu[slot]);
     auto& db = ctx->dbs[slot];
     if (db.busy) { ctx->last_error = "slot already holds a block: call fabgpu_validate_wait first"; return FABGPU_E_ARG; }
@@ -1440,7 +1520,13 @@ static int validate_host(fabgpu_ctx* ctx, const uint8_t* block, size_t block_len
     auto& bb = ctx->bbs[0];
     CK(ctx, cudaSetDevice(dv.id));
     // 1. the block goes to the device while the host parses it
-    if (block_len > bb.block_cap) { int rc = grow_dev(ctx, bb.d_block, block_len + (block_len >> 2)); if (rc) return rc; bb.block_cap = block_len + (block_len >> 2); }
+    if (block_len > bb.block_cap) {
+        const size_t want = block_len + (block_len >> 2);
+        bb.block_cap = 0;                                   // a failed grow leaves no buffer: do not remember the old capacity
+        int rc = grow_dev(ctx, bb.d_block, want + 64);      // slack: word-wise readers (bytes_equal, the SHA loader) touch the aligned words past the end
+        if (rc) return rc;
+        bb.block_cap = want;
+    }
     CK(ctx, cudaMemcpyAsync(bb.d_block, block, block_len, cudaMemcpyHostToDevice, ds.stream));
     // 2. plan: every signature the block needs, every digest the transaction checks need
     blockval::BlockPlan plan;

@@ -52,15 +52,29 @@ FAB_HD u256 s30_to_u256(const s30x9& a)
     return r;
 }
 
-// n in 30-bit limbs, and n^-1 mod 2^30
-FAB_HD s30x9 s30_n()
-{
-    s30x9 r;
-    r.v[0] = 0x3c632551; r.v[1] = 0x0ee72b0b; r.v[2] = 0x3179e84f; r.v[3] = 0x39beab69; r.v[4] = 0x3fffffbc;
-    r.v[5] = 0x3fffffff; r.v[6] = 0x00000fff; r.v[7] = 0x3fffc000; r.v[8] = 0x0000ffff;
-    return r;
-}
-#define FAB_NINV30 0x11ff43b1u
+// The modulus in 30-bit limbs and its inverse mod 2^30: the group order n (s^-1 of a signature) and the field prime p
+// (the shared inversion of the batch-affine point additions, ecdsa_batchaffine.cuh).
+struct ModN {
+    static FAB_HD s30x9 m()
+    {
+        s30x9 r;
+        r.v[0] = 0x3c632551; r.v[1] = 0x0ee72b0b; r.v[2] = 0x3179e84f; r.v[3] = 0x39beab69; r.v[4] = 0x3fffffbc;
+        r.v[5] = 0x3fffffff; r.v[6] = 0x00000fff; r.v[7] = 0x3fffc000; r.v[8] = 0x0000ffff;
+        return r;
+    }
+    static constexpr uint32_t inv30 = 0x11ff43b1u;
+};
+struct ModP {
+    static FAB_HD s30x9 m()
+    {
+        s30x9 r;
+        r.v[0] = 0x3fffffff; r.v[1] = 0x3fffffff; r.v[2] = 0x3fffffff; r.v[3] = 0x0000003f; r.v[4] = 0x00000000;
+        r.v[5] = 0x00000000; r.v[6] = 0x00001000; r.v[7] = 0x3fffc000; r.v[8] = 0x0000ffff;
+        return r;
+    }
+    static constexpr uint32_t inv30 = 0x3fffffffu;      // p == -1 (mod 2^96)
+};
+FAB_HD s30x9 s30_n() { return ModN::m(); }
 
 // 30 division steps on the low words; returns the new delta and the matrix t = (u, v, q, r) with
 //   2^30 * (f', g') = (u f + v g, q f + r g).
@@ -103,10 +117,10 @@ FAB_HD void update_fg30(s30x9& f, s30x9& g, const int32_t* t)
     g.v[8] = (int32_t)cg;
 }
 
-// (d, e) <- (u d + v e, q d + r e) / 2^30 mod n, keeping d, e in (-2n, n)
-FAB_HD void update_de30(s30x9& d, s30x9& e, const int32_t* t)
+// (d, e) <- (u d + v e, q d + r e) / 2^30 mod m, keeping d, e in (-2m, m)
+template <class MOD> FAB_HD void update_de30(s30x9& d, s30x9& e, const int32_t* t)
 {
-    const s30x9 m = s30_n();
+    const s30x9 m = MOD::m();
     const int32_t u = t[0], v = t[1], q = t[2], r = t[3];
     const int32_t sd = d.v[8] >> 31, se = e.v[8] >> 31;          // all-ones when negative
     int32_t md = (u & sd) + (v & se);                             // adds n to a negative d / e before the linear map
@@ -114,8 +128,8 @@ FAB_HD void update_de30(s30x9& d, s30x9& e, const int32_t* t)
     int64_t cd = (int64_t)u * d.v[0] + (int64_t)v * e.v[0];
     int64_t ce = (int64_t)q * d.v[0] + (int64_t)r * e.v[0];
     // choose the multiples of n that clear the low 30 bits
-    md -= (int32_t)((FAB_NINV30 * (uint32_t)cd + (uint32_t)md) & FAB_M30);
-    me -= (int32_t)((FAB_NINV30 * (uint32_t)ce + (uint32_t)me) & FAB_M30);
+    md -= (int32_t)((MOD::inv30 * (uint32_t)cd + (uint32_t)md) & FAB_M30);
+    me -= (int32_t)((MOD::inv30 * (uint32_t)ce + (uint32_t)me) & FAB_M30);
     cd += (int64_t)m.v[0] * md;
     ce += (int64_t)m.v[0] * me;
     cd >>= 30; ce >>= 30;
@@ -130,10 +144,10 @@ FAB_HD void update_de30(s30x9& d, s30x9& e, const int32_t* t)
     e.v[8] = (int32_t)ce;
 }
 
-// a in (-2n, n), optionally negated, brought to [0, n)
-FAB_HD s30x9 normalize30(const s30x9& a, bool negate)
+// a in (-2m, m), optionally negated, brought to [0, m)
+template <class MOD> FAB_HD s30x9 normalize30(const s30x9& a, bool negate)
 {
-    const s30x9 m = s30_n();
+    const s30x9 m = MOD::m();
     s30x9 r = a;
     if (negate) {
 #pragma unroll
@@ -168,10 +182,10 @@ FAB_HD s30x9 normalize30(const s30x9& a, bool negate)
     return r;
 }
 
-// s in [1, n-1]  ->  s^-1 mod n (plain integer, not Montgomery)
-FAB_HD u256 sc_inv_safegcd(const u256& s)
+// s in [1, m-1]  ->  s^-1 mod m (plain integer, not Montgomery)
+template <class MOD> FAB_HD u256 inv_safegcd(const u256& s)
 {
-    s30x9 f = s30_n(), g = s30_from_u256(s);
+    s30x9 f = MOD::m(), g = s30_from_u256(s);
     s30x9 d, e;
 #pragma unroll
     for (int i = 0; i < 9; i++) { d.v[i] = 0; e.v[i] = 0; }
@@ -180,7 +194,7 @@ FAB_HD u256 sc_inv_safegcd(const u256& s)
     for (int it = 0; it < 25; it++) {          // 25 * 30 = 750 >= 741, the proven bound for 256-bit inputs
         int32_t t[4];
         delta = divsteps30(delta, (uint32_t)f.v[0] | ((uint32_t)f.v[1] << 30), (uint32_t)g.v[0] | ((uint32_t)g.v[1] << 30), t);
-        update_de30(d, e, t);
+        update_de30<MOD>(d, e, t);
         update_fg30(f, g, t);
         int32_t nz = 0;
 #pragma unroll
@@ -188,8 +202,18 @@ FAB_HD u256 sc_inv_safegcd(const u256& s)
         if (nz == 0) break;
     }
     // f = +-1 ; s^-1 = f * d
-    const s30x9 r = normalize30(d, f.v[8] < 0);
+    const s30x9 r = normalize30<MOD>(d, f.v[8] < 0);
     return s30_to_u256(r);
+}
+
+FAB_HD u256 sc_inv_safegcd(const u256& s) { return inv_safegcd<ModN>(s); }
+
+// Field inversion by the same division steps: a R in -> a^-1 R out (Montgomery form on both sides).  The plain inverse of the
+// residue a R is a^-1 R^-1; one Montgomery product with R^3 restores the domain.  ~5x cheaper than the Fermat ladder fe_inv.
+FAB_HD u256 fe_inv_safegcd(const u256& a)
+{
+    const u256 r3 = u256_const(0x0000000au, 0xfffffffdu, 0xfffffff7u, 0xffffffedu, 0xfffffffcu, 0x00000005u, 0x00000001u, 0x00000018u);
+    return fe_mul(inv_safegcd<ModP>(a), r3);
 }
 
 // plain in -> Montgomery out, the contract of sc_inv_to_mont

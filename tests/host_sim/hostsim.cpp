@@ -8,6 +8,7 @@
 #include <vector>
 #include <utility>
 #include "../../fabric-mod_b200/csrc/ecdsa_verify.cuh"
+#include "../../fabric-mod_b200/csrc/ecdsa_batchaffine.cuh"
 
 using namespace fabgpu;
 
@@ -86,6 +87,96 @@ void hostsim_verify_batch_cached(const uint8_t* qx, const uint8_t* qy, const uin
     }
 }
 
+// The batch-affine path (ecdsa_batchaffine.cuh) with the CTA exchange replayed on the host: signatures are taken in groups of
+// GROUP "threads"; each of GROUP / V "lanes" runs ba_inverse_lane over V strided values, exactly as the inverter warp of
+// ecdsa_verify_ba_kernel does.  Keys are given as tables built by the same code as hostsim_verify_batch_cached.
+}  // extern "C"
+
+static const std::vector<aff>* ba_key_table(std::vector<std::pair<std::vector<uint8_t>, std::vector<aff>>>& cache, const uint8_t* qx, const uint8_t* qy)
+{
+    std::vector<uint8_t> key(qx, qx + 32);
+    key.insert(key.end(), qy, qy + 32);
+    for (auto& c : cache) if (c.first == key) return &c.second;
+    const u256 x = u256_from_be(qx), y = u256_from_be(qy);
+    aff q; bool ok = u256_lt(x, fe_p()) && u256_lt(y, fe_p());
+    if (ok) { q.x = fe_to_mont(x); q.y = fe_to_mont(y); ok = aff_on_curve(q); }
+    std::vector<aff> t;
+    if (ok) {
+        std::vector<u256> zs(2 * FAB_Q_ENTRIES);
+        t.resize((size_t)FAB_Q_WINDOWS * FAB_Q_ENTRIES);
+        for (int j = 0; j < FAB_Q_WINDOWS; j++) build_key_window(q, j, t.data() + (size_t)j * FAB_Q_ENTRIES, zs.data(), zs.data() + FAB_Q_ENTRIES);
+    }
+    cache.emplace_back(key, std::move(t));
+    return &cache.back().second;
+}
+
+template <bool MODN> static void ba_exchange(std::vector<u256>& vals, int V)
+{
+    // [limb][thread] layout like the kernel's shared-memory buffers
+    const int T = (int)vals.size(), lanes = T / V;
+    std::vector<uint32_t> exa(8 * T), exb(8 * T);
+    for (int t = 0; t < T; t++) for (int l = 0; l < 8; l++) exa[l * T + t] = vals[t].v[l];
+    for (int g = 0; g < lanes; g++) ba_inverse_lane<MODN>(exa.data() + g, exb.data() + g, V, lanes, T);
+    for (int t = 0; t < T; t++) for (int l = 0; l < 8; l++) vals[t].v[l] = exa[l * T + t];
+}
+
+extern "C" {
+
+void hostsim_verify_batch_ba(const uint8_t* qx, const uint8_t* qy, const uint8_t* e, const uint8_t* r, const uint8_t* s, int n, uint8_t* out)
+{
+    hostsim_build_gtable();
+    const int GROUP = 64, V = 8;
+    std::vector<std::pair<std::vector<uint8_t>, std::vector<aff>>> cache;
+    cache.reserve(4096);
+    for (int base = 0; base < n; base += GROUP) {
+        struct Th { bool ok = false; const aff* qt = nullptr; u256 ev, rv, sv; BaScratch sc; uint32_t dig[FAB_BA_NP]; uint32_t exc = 0, m1 = 0; jac acc; };
+        std::vector<Th> th(GROUP);
+        std::vector<u256> vals(GROUP);
+        for (int t = 0; t < GROUP; t++) {
+            vals[t] = u256_const(1, 0, 0, 0, 0, 0, 0, 0);
+            const int i = base + t;
+            if (i >= n) continue;
+            const size_t o = 32 * (size_t)i;
+            const std::vector<aff>* tab = ba_key_table(cache, qx + o, qy + o);
+            if (tab->empty()) { out[i] = (uint8_t)V_OFFCURVE; continue; }
+            out[i] = (uint8_t)V_INVALID;
+            Th& h = th[t];
+            h.qt = tab->data();
+            h.ev = u256_from_be(e + o); h.rv = u256_from_be(r + o); h.sv = u256_from_be(s + o);
+            h.ok = ba_range_ok(h.rv, h.sv);
+            if (h.ok) vals[t] = h.sv;
+        }
+        ba_exchange<true>(vals, V);
+        for (int t = 0; t < GROUP; t++) {
+            Th& h = th[t];
+            u256 c = fe_one();
+            if (h.ok) {
+                ba_scalars(h.ev, h.rv, vals[t], h.dig, 1);
+                c = ba_forward<true>(FAB_BA_N1, g_tab.data(), h.qt, h.dig, 1, nullptr, 0u, h.sc.pre, h.exc);
+            }
+            vals[t] = c;
+        }
+        ba_exchange<false>(vals, V);
+        for (int t = 0; t < GROUP; t++) {
+            Th& h = th[t];
+            u256 c = fe_one();
+            h.acc = jac_infinity();
+            if (h.ok) {
+                h.m1 = ba_backward<true, false>(FAB_BA_N1, vals[t], g_tab.data(), h.qt, h.dig, 1, nullptr, 0u, h.sc.pre, h.sc.pts, h.acc);
+                c = ba_forward<false>(FAB_BA_N2, g_tab.data(), h.qt, h.dig, 1, h.sc.pts, h.m1, h.sc.pre, h.exc);
+            }
+            vals[t] = c;
+        }
+        ba_exchange<false>(vals, V);
+        for (int t = 0; t < GROUP; t++) {
+            Th& h = th[t];
+            if (!h.ok) continue;
+            ba_backward<false, true>(FAB_BA_N2, vals[t], g_tab.data(), h.qt, h.dig, 1, h.sc.pts, h.m1, h.sc.pre, nullptr, h.acc);
+            out[base + t] = (uint8_t)(h.exc ? ecdsa_verify_one_cached(h.qt, h.ev, h.rv, h.sv, g_tab.data()) : final_check(h.acc, h.rv));
+        }
+    }
+}
+
 // field / scalar unit hooks: op 0 fe_mul, 1 fe_add, 2 fe_sub, 3 sc_mul, 4 fe_inv, 5 sc_inv_to_mont (b ignored for 4,5)
 void hostsim_fieldop(int op, const uint8_t* a, const uint8_t* b, int n, uint8_t* out)
 {
@@ -98,6 +189,7 @@ void hostsim_fieldop(int op, const uint8_t* a, const uint8_t* b, int n, uint8_t*
             case 3: z = sc_mul(x, y); break;
             case 4: z = fe_inv(x); break;
             case 5: z = sc_inv_to_mont(x); break;
+            case 8: z = fe_inv_safegcd(x); break;
         case 7: z = fe_sqr(x); break;
         default: z = sc_inv_to_mont_safegcd(x); break;
         }

@@ -471,10 +471,12 @@ def test_bccsp_batch_async_two_slots_in_flight():
 # ---------------------------------------------------------------------------------------------------------
 def test_multi_device_context_splits_batch():
     import torch
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs at least 2 GPUs")
     ndev = min(torch.cuda.device_count(), 4)
-    c = pkg().binding.Context(max_batch=1 << 17, device_ids=list(range(ndev)))
+    # On a 1-GPU box the context is given device 0 twice: two device entries (own streams, tables and buffers), so the split /
+    # per-device launch / mask reassembly logic runs exactly as it does over distinct GPUs.
+    ids = list(range(ndev)) if ndev >= 2 else [0, 0]
+    ndev = len(ids)
+    c = pkg().binding.Context(max_batch=1 << 17, device_ids=ids)
     assert c.device_count() == ndev
     # BASELINE.json configs[4] shape at reduced size: 5 % tampered r, exact-match bitmask (generic kernel, then key tables)
     w = workload.Workload(100000 + 77, 64, seed=workload.DEFAULT_SEED + 5)        # ragged: not a multiple of 32 * ndev

@@ -13,7 +13,7 @@ import vectors
 V_INVALID, V_VALID, V_OFFCURVE = 0, 1, 2
 
 
-@pytest.mark.parametrize("cached", [False, True])
+@pytest.mark.parametrize("cached", [False, True, "ba"])
 def test_constructed_edge_cases(cached):
     b = pkg().binding
     for c in vectors.build():
@@ -27,7 +27,7 @@ def test_constructed_edge_cases(cached):
             assert st == exp, c["name"]
             continue
         out = hostsim_verify(be32(c["qx"] % (1 << 256)), be32(c["qy"] % (1 << 256)), hash_to_e32(c["digest"]),
-                             np.frombuffer(r, np.uint8), np.frombuffer(s, np.uint8), cached=cached)[0]
+                             np.frombuffer(r, np.uint8), np.frombuffer(s, np.uint8), cached=cached is True, ba=cached == "ba")[0]
         got = {V_VALID: o.VALID, V_INVALID: o.INVALID, V_OFFCURVE: o.ERR_OFF_CURVE}[int(out)]
         assert got == exp, c["name"]
 
@@ -51,3 +51,29 @@ def test_tampered_matches_oracle_bit_for_bit():
     # the per-key-table path gives the same bits
     out_c = hostsim_verify(w.qx(), w.qy(), w.digest, w.r, w.s, cached=True)
     assert (out_c == out).all()
+    # and so does the batch-affine accumulation with its shared inversions (groups of 64 with a ragged tail: 768 + 37)
+    out_b = hostsim_verify(w.qx(), w.qy(), w.digest, w.r, w.s, ba=True)
+    assert (out_b == out).all()
+    k = 37
+    out_b2 = hostsim_verify(w.qx()[:k], w.qy()[:k], w.digest[:k], w.r[:k], w.s[:k], ba=True)
+    assert (out_b2 == out[:k]).all()
+
+
+def test_field_inversion_by_division_steps():
+    """fe_inv_safegcd (the shared inversion of the batch-affine levels) against the Fermat ladder and Python."""
+    import ctypes
+    from util import hostsim, from_be
+    rng = np.random.default_rng(11)
+    p = (1 << 256) - (1 << 224) + (1 << 192) + (1 << 96) - 1
+    xs = [1, 2, p - 1, p - 2, (1 << 255), 3] + [int.from_bytes(rng.bytes(32), "big") % (p - 1) + 1 for _ in range(60)]
+    a = np.concatenate([be32(x) for x in xs])
+    outs = []
+    for op in (4, 8):
+        out = np.zeros_like(a)
+        hostsim().hostsim_fieldop(ctypes.c_int(op), a.ctypes.data_as(ctypes.c_void_p), a.ctypes.data_as(ctypes.c_void_p), ctypes.c_int(len(xs)),
+                                  out.ctypes.data_as(ctypes.c_void_p))
+        outs.append(out.reshape(-1, 32))
+    assert (outs[0] == outs[1]).all()
+    R = 1 << 256
+    for x, o_ in zip(xs, outs[1]):          # Montgomery in / out: x = a R  ->  a^-1 R = R^2 / x
+        assert from_be(o_) == (R * R * pow(x, -1, p)) % p

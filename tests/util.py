@@ -43,7 +43,7 @@ def hostsim():
         d = os.path.join(ROOT, "tests", "host_sim")
         so = os.path.join(d, "libhostsim.so")
         src = os.path.join(d, "hostsim.cpp")
-        hdrs = [os.path.join(ROOT, "fabric-mod_b200", "csrc", h) for h in ("p256_fe.cuh", "p256_point.cuh", "p256_modinv.cuh", "ecdsa_verify.cuh")]
+        hdrs = [os.path.join(ROOT, "fabric-mod_b200", "csrc", h) for h in ("p256_fe.cuh", "p256_point.cuh", "p256_modinv.cuh", "ecdsa_verify.cuh", "ecdsa_batchaffine.cuh")]
         if not os.path.exists(so) or any(os.path.getmtime(so) < os.path.getmtime(f) for f in [src] + hdrs):
             # host build of the table would take minutes at the product's 16-bit G windows; the algorithm is window-size generic
             subprocess.check_call(["g++", "-O2", "-std=c++17", "-DFAB_WG=8", "-DFAB_WQ=8", "-DFAB_Q_TWO_LEVEL=1", "-shared", "-fPIC", "-o", so, src])
@@ -52,11 +52,11 @@ def hostsim():
     return _HS
 
 
-def hostsim_verify(qx, qy, e, r, s, cached=False):
+def hostsim_verify(qx, qy, e, r, s, cached=False, ba=False):
     arrs = [np.ascontiguousarray(a, dtype=np.uint8).reshape(-1, 32) for a in (qx, qy, e, r, s)]
     n = arrs[0].shape[0]
     out = np.zeros(n, np.uint8)
-    fn = hostsim().hostsim_verify_batch_cached if cached else hostsim().hostsim_verify_batch
+    fn = hostsim().hostsim_verify_batch_ba if ba else (hostsim().hostsim_verify_batch_cached if cached else hostsim().hostsim_verify_batch)
     fn(*[a.ctypes.data_as(ctypes.c_void_p) for a in arrs], ctypes.c_int(n), out.ctypes.data_as(ctypes.c_void_p))
     return out
 
