@@ -96,6 +96,104 @@ ecdsa_verify_cached_kernel(const int32_t* __restrict__ key_slot, const uint8_t* 
     }
 }
 
+// ---- lane-split variant of the Jacobian-chain kernel (the "warp-cooperative" shape of BASELINE.json's north_star, measured) ----
+// LANES adjacent lanes share one signature BY WINDOWS: lane l accumulates windows l, l + LANES, l + 2 LANES, ... of the 12 + 16
+// table windows into its own Jacobian partial sum (no carry ever crosses a lane), the partial sums are tree-combined with the
+// complete addition through shuffles, lane 0 of the group runs the final check.  w = s^-1 and u1, u2 are computed by every lane
+// of the group (in SIMT that costs the same as computing them in one lane and broadcasting).  Thread count x LANES, chain length
+// per thread / LANES: profiles/r2_lane_split.txt has the measurement against one signature per thread.
+#ifndef FAB_LANES_THREADS
+#define FAB_LANES_THREADS 256
+#endif
+template <int LANES>
+__global__ void __launch_bounds__(FAB_LANES_THREADS, 2)
+ecdsa_verify_lanes_kernel(const int32_t* __restrict__ key_slot, const uint8_t* __restrict__ e, const uint8_t* __restrict__ r,
+                          const uint8_t* __restrict__ s, uint32_t n, const aff* __restrict__ gtab, const aff* __restrict__ qtab,
+                          uint32_t* __restrict__ mask, uint32_t* __restrict__ offcurve)
+{
+    constexpr int T = FAB_LANES_THREADS, SIGS = T / LANES, NW = FAB_G_WINDOWS + FAB_Q_WINDOWS, STEPS = (NW + LANES - 1) / LANES;
+    __shared__ uint32_t dig[(STEPS * LANES) * SIGS];           // [window][signature of the CTA]: table entry index or FAB_BA_INF
+    const int lane = threadIdx.x % LANES, sg = threadIdx.x / LANES;
+    const uint32_t idx = blockIdx.x * SIGS + sg;
+    bool ok = false;
+    const aff* qt = qtab;
+    u256 rv;
+    if (idx < n) {
+        const int32_t slot = key_slot[idx];
+        if (slot >= 0) {
+            const size_t o = (size_t)idx * 32;
+            qt = qtab + (size_t)slot * (FAB_Q_WINDOWS * FAB_Q_ENTRIES);
+            rv = load_be32(r + o);
+            const u256 sv = load_be32(s + o);
+            ok = ba_range_ok(rv, sv);
+            if (ok) {
+                const u256 w = sc_inv_to_mont_safegcd(sv);
+                const u256 u1 = sc_mul(sc_reduce_once(load_be32(e + o)), w), u2 = sc_mul(rv, w);
+                if (lane == 0) {                                   // one lane publishes the digits of all windows
+                    uint32_t kk[8];
+#pragma unroll
+                    for (int i = 0; i < 8; i++) kk[i] = u1.v[i];
+#pragma unroll
+                    for (int j = 0; j < FAB_G_WINDOWS; j++) {
+                        const uint32_t d = kk[0] & (uint32_t)FAB_G_ENTRIES;
+#pragma unroll
+                        for (int i = 0; i < 7; i++) kk[i] = (kk[i] >> FAB_WG) | (kk[i + 1] << (32 - FAB_WG));
+                        kk[7] >>= FAB_WG;
+                        dig[j * SIGS + sg] = d ? (uint32_t)j * (uint32_t)FAB_G_ENTRIES + (d - 1u) : FAB_BA_INF;
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; i++) kk[i] = u2.v[i];
+#pragma unroll
+                    for (int j = 0; j < FAB_Q_WINDOWS; j++) {
+                        const uint32_t d = kk[0] & (uint32_t)FAB_Q_ENTRIES;
+#pragma unroll
+                        for (int i = 0; i < 7; i++) kk[i] = (kk[i] >> FAB_WQ) | (kk[i + 1] << (32 - FAB_WQ));
+                        kk[7] >>= FAB_WQ;
+                        dig[(FAB_G_WINDOWS + j) * SIGS + sg] = d ? (uint32_t)j * (uint32_t)FAB_Q_ENTRIES + (d - 1u) : FAB_BA_INF;
+                    }
+                    for (int j = NW; j < STEPS * LANES; j++) dig[j * SIGS + sg] = FAB_BA_INF;
+                }
+            }
+        }
+    }
+    __syncwarp();                                                  // a group never straddles a warp (LANES divides 32)
+    jac acc = jac_infinity();
+    if (ok) {
+#pragma unroll 1
+        for (int t = 0; t < STEPS; t++) {
+            const int j = t * LANES + lane;
+            const uint32_t di = dig[j * SIGS + sg];
+            if (di != FAB_BA_INF) acc = jac_add_aff_t<FAB_CACHED_INLINE != 0>(acc, (j < FAB_G_WINDOWS ? gtab : qt)[di]);
+        }
+    }
+    // tree-combine the partial sums of the group's lanes
+#pragma unroll
+    for (int d = 1; d < LANES; d <<= 1) {
+        jac o;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            o.X.v[i] = __shfl_xor_sync(0xffffffffu, acc.X.v[i], d);
+            o.Y.v[i] = __shfl_xor_sync(0xffffffffu, acc.Y.v[i], d);
+            o.Z.v[i] = __shfl_xor_sync(0xffffffffu, acc.Z.v[i], d);
+        }
+        if (ok && (lane & (2 * d - 1)) == 0) acc = jac_add(acc, o);
+    }
+    const uint32_t res = (ok && lane == 0) ? final_check(acc, rv) : V_INVALID;
+    const uint32_t b = __ballot_sync(0xffffffffu, res == V_VALID);
+    // bits of lanes 0, LANES, 2 LANES, ... -> 32 / LANES consecutive mask bits
+    uint32_t packed = 0;
+#pragma unroll
+    for (int k = 0; k < 32 / LANES; k++) packed |= ((b >> (k * LANES)) & 1u) << k;
+    if ((threadIdx.x & 31u) == 0) {
+        const uint32_t first = blockIdx.x * SIGS + (threadIdx.x / LANES);     // first signature of this warp
+        if (first < n) {
+            if (LANES == 2) { reinterpret_cast<uint16_t*>(mask)[first >> 4] = (uint16_t)packed; if (offcurve) reinterpret_cast<uint16_t*>(offcurve)[first >> 4] = 0; }
+            else if (LANES == 4) { reinterpret_cast<uint8_t*>(mask)[first >> 3] = (uint8_t)packed; if (offcurve) reinterpret_cast<uint8_t*>(offcurve)[first >> 3] = 0; }
+            else { mask[first >> 5] = packed; if (offcurve) offcurve[first >> 5] = 0; }
+        }
+    }
+}
+
 // ---- batch-affine key-table kernel (ecdsa_batchaffine.cuh) ----
 #ifndef FAB_BA_THREADS
 #define FAB_BA_THREADS 256            // signatures (= threads) per CTA; the shared inversion is amortised over this many

@@ -276,7 +276,14 @@ int launch_verify(fabgpu_ctx* ctx, const Device& dv, int mode, const int32_t* ke
         // finishes in 0.315 ms against 0.346 ms as 512 CTAs of 128 threads; beyond one wave 256-thread CTAs quantise best
         // (256k: 231 M/s against 223 / 212 for 128 / 512); below ~12 warps per SM small CTAs spread over all SMs win
         // (fewer warps per scheduler = lower latency per warp), and so they do when the batch size is only an upper bound.
-        if (ctx->cached_kernel == 1) {
+        if (ctx->cached_kernel == 2 || ctx->cached_kernel == 4) {
+            // lane-split Jacobian chain (measurement variant): 2 or 4 lanes per signature
+            const unsigned sigs = FAB_LANES_THREADS / (unsigned)ctx->cached_kernel, blocks = (unsigned)((n + sigs - 1) / sigs);
+            uint32_t nn = (uint32_t)n;
+            if (n_dev) { ctx->last_error = "the lane-split kernel has no device-side batch size"; return FABGPU_E_ARG; }
+            if (ctx->cached_kernel == 2) ecdsa_verify_lanes_kernel<2><<<blocks, FAB_LANES_THREADS, 0, st>>>(key_slot, e, r, s, nn, dv.gtab, dv.qtab, mask, off);
+            else ecdsa_verify_lanes_kernel<4><<<blocks, FAB_LANES_THREADS, 0, st>>>(key_slot, e, r, s, nn, dv.gtab, dv.qtab, mask, off);
+        } else if (ctx->cached_kernel == 1) {
             // batch-affine accumulation with CTA-shared inversions (ecdsa_batchaffine.cuh): fixed CTA width
             const unsigned blocks = (unsigned)((n + FAB_BA_THREADS - 1) / FAB_BA_THREADS);
             ecdsa_verify_ba_kernel<<<blocks, FAB_BA_THREADS, 0, st>>>(key_slot, e, r, s, (uint32_t)n, dv.gtab, dv.qtab, mask, off, n_dev, n_base);
@@ -451,7 +458,7 @@ int init_impl(fabgpu_ctx* ctx, const int* device_ids, int n_dev, size_t max_batc
         const char* mu = getenv("FABGPU_KEY_MIN_USES");
         ctx->key_min_uses = mu ? atoi(mu) : 256;           // a table costs about 300 generic verifications to build
         const char* ck = getenv("FABGPU_CACHED_KERNEL");
-        if (ck) ctx->cached_kernel = (ck[0] == 'j' || ck[0] == '0') ? 0 : 1;      // "jac" / "0": the Jacobian-chain kernel
+        if (ck) ctx->cached_kernel = (ck[0] == 'j' || ck[0] == '0') ? 0 : (ck[0] == 'l' ? (ck[1] == '4' ? 4 : 2) : 1);   // "jac" / "0": the Jacobian-chain kernel; "l2" / "l4": its lane-split variant
     }
     ctx->dev_cap = round_up32((max_batch + ids.size() - 1) / ids.size());
     ctx->devs.resize(ids.size());

@@ -3,8 +3,8 @@
 //
 // Factory of the GPU provider, the twin of bccsp/factory/pkcs11factory.go.  Selected with
 //     peer.BCCSP.Default: GPU          (sampleconfig/core.yaml:297-319)
-// NOT COMPILED in this repository's build image (no Go toolchain); see INTEGRATION.md for the three-line
-// change to initFactories / GetBCCSPFromOpts (bccsp/factory/pkcs11.go:38-96) that registers it.
+// Compiled only with `-tags gpu` (it pulls in cgo and libfabgpu_ecdsa.so); registers itself with the hook of gpuhook.go,
+// which initFactories / GetBCCSPFromOpts consult in both the pkcs11 and the nopkcs11 build (patches/bccsp-factory-gpu.patch).
 
 package factory
 
@@ -15,9 +15,9 @@ import (
 	"github.com/pkg/errors"
 )
 
-const GPUBasedFactoryName = "GPU"
-
 type GPUFactory struct{}
+
+func init() { gpuFactory = &GPUFactory{} }
 
 func (f *GPUFactory) Name() string { return GPUBasedFactoryName }
 

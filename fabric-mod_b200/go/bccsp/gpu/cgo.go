@@ -1,4 +1,5 @@
 // Copyright the fabgpu authors. SPDX-License-Identifier: Apache-2.0
+// +build gpu
 //
 // cgo binding of include/fabgpu_ecdsa.h (libfabgpu_ecdsa.so).  NOT COMPILED in the build image of this
 // repository (it has no Go toolchain); shipped as the reference-side binding a maintainer adds under
@@ -56,20 +57,26 @@ func openDevice(deviceIDs []int, maxBatch int) (*device, error) {
 		}
 		n := maxBatch * 32
 		d.slots[i] = slot{
-			qx: unsafe.Slice((*byte)(unsafe.Pointer(qx)), n), qy: unsafe.Slice((*byte)(unsafe.Pointer(qy)), n),
-			e: unsafe.Slice((*byte)(unsafe.Pointer(e)), n), r: unsafe.Slice((*byte)(unsafe.Pointer(r)), n),
-			s:    unsafe.Slice((*byte)(unsafe.Pointer(s)), n),
-			mask: unsafe.Slice((*uint32)(unsafe.Pointer(mask)), words), offcurve: unsafe.Slice((*uint32)(unsafe.Pointer(off)), words),
+			qx: cBytes(unsafe.Pointer(qx), n), qy: cBytes(unsafe.Pointer(qy), n),
+			e: cBytes(unsafe.Pointer(e), n), r: cBytes(unsafe.Pointer(r), n), s: cBytes(unsafe.Pointer(s), n),
+			mask: cUint32s(unsafe.Pointer(mask), words), offcurve: cUint32s(unsafe.Pointer(off), words),
 		}
 		var ks *C.int32_t
 		if rc := C.fabgpu_host_key_slots(d.ctx, C.int(i), &ks); rc != C.FABGPU_OK {
 			d.close()
 			return nil, fmt.Errorf("fabgpu_host_key_slots failed [%d]", int(rc))
 		}
-		d.slots[i].keySlot = unsafe.Slice((*int32)(unsafe.Pointer(ks)), maxBatch)
+		d.slots[i].keySlot = cInt32s(unsafe.Pointer(ks), maxBatch)
 	}
 	return d, nil
 }
+
+// Go views of C-owned (pinned) memory.  The reference builds with Go 1.14.4 (Makefile:79): unsafe.Slice (Go 1.17) is not
+// available, so the views are made the pre-1.17 way -- cast to a pointer to a huge array type, then slice with a capacity.
+// The array types only bound the index arithmetic; nothing of that size is allocated.
+func cBytes(p unsafe.Pointer, n int) []byte     { return (*[1 << 40]byte)(p)[:n:n] }
+func cUint32s(p unsafe.Pointer, n int) []uint32 { return (*[1 << 38]uint32)(p)[:n:n] }
+func cInt32s(p unsafe.Pointer, n int) []int32   { return (*[1 << 38]int32)(p)[:n:n] }
 
 func (d *device) close() {
 	if d.ctx != nil {
@@ -101,4 +108,27 @@ func (d *device) registerKey(xy *[64]byte) int32 {
 		return -1
 	}
 	return int32(s)
+}
+
+// verifyBatch is the bccsp-level batch entry point (fabgpu_bccsp_verify_batch): raw DER signatures, digests and keys in Go
+// memory (borrowed for the call; the library stages them into its own pinned buffers), one status byte per signature out.
+// Used by the block pre-pass (prepass.go).  keysXY: K x 64 bytes; keyIdx[i] names signature i's key.
+func (d *device) verifyBatch(keysXY []byte, keyIdx []int32, digests []byte, digOff []uint32, sigs []byte, sigOff []uint32, status []byte) error {
+	n := len(keyIdx)
+	if n == 0 {
+		return nil
+	}
+	if len(sigs) == 0 {
+		sigs = []byte{0}
+	}
+	if len(digests) == 0 {
+		digests = []byte{0}
+	}
+	rc := C.fabgpu_bccsp_verify_batch(d.ctx, (*C.uint8_t)(unsafe.Pointer(&keysXY[0])), C.int(len(keysXY)/64), (*C.int32_t)(unsafe.Pointer(&keyIdx[0])),
+		(*C.uint8_t)(unsafe.Pointer(&digests[0])), (*C.uint32_t)(unsafe.Pointer(&digOff[0])),
+		(*C.uint8_t)(unsafe.Pointer(&sigs[0])), (*C.uint32_t)(unsafe.Pointer(&sigOff[0])), C.size_t(n), (*C.uint8_t)(unsafe.Pointer(&status[0])))
+	if rc != C.FABGPU_OK {
+		return fmt.Errorf("fabgpu_bccsp_verify_batch failed [%d]: %s", int(rc), C.GoString(C.fabgpu_last_error(d.ctx)))
+	}
+	return nil
 }

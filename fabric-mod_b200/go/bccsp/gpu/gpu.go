@@ -1,4 +1,5 @@
 // Copyright the fabgpu authors. SPDX-License-Identifier: Apache-2.0
+// +build gpu
 //
 // Package gpu is a bccsp.BCCSP provider that verifies ECDSA P-256 signatures on NVIDIA B200 GPUs.
 //
@@ -32,15 +33,6 @@ import (
 	"github.com/hyperledger/fabric/bccsp/utils"
 	"github.com/pkg/errors"
 )
-
-// GPUOpts is the `GPU:` block of the BCCSP section in core.yaml (beside SW: and PKCS11:).
-type GPUOpts struct {
-	SecLevel    int    `mapstructure:"security" json:"security" yaml:"Security"`
-	HashFamily  string `mapstructure:"hash" json:"hash" yaml:"Hash"`
-	Devices     []int  `mapstructure:"devices" json:"devices" yaml:"Devices"`
-	MaxBatch    int    `mapstructure:"maxbatch" json:"maxbatch" yaml:"MaxBatch"`
-	FlushMicros int    `mapstructure:"flushmicros" json:"flushmicros" yaml:"FlushMicros"`
-}
 
 // ecdsaP256Key wraps the software provider's key and caches the affine coordinates next to it.
 type ecdsaP256Key struct {
@@ -81,8 +73,10 @@ type impl struct {
 	dev       *device
 	reqs      chan *request
 	flush     time.Duration
-	Fallbacks uint64 // exported counters for the operations endpoint
+	results   *resultCache // verdicts of the block pre-pass (prepass.go), consulted before anything is queued
+	Fallbacks uint64       // exported counters for the operations endpoint
 	Batches   uint64
+	CacheHits uint64
 }
 
 // New returns the GPU provider.  keyStore is handed to the embedded software provider.
@@ -101,7 +95,8 @@ func New(opts GPUOpts, keyStore bccsp.KeyStore) (bccsp.BCCSP, error) {
 	if err != nil {
 		return nil, errors.Wrapf(err, "Failed initializing GPU BCCSP")
 	}
-	csp := &impl{BCCSP: swCSP, dev: dev, reqs: make(chan *request, 4*opts.MaxBatch), flush: time.Duration(opts.FlushMicros) * time.Microsecond}
+	csp := &impl{BCCSP: swCSP, dev: dev, reqs: make(chan *request, 4*opts.MaxBatch), flush: time.Duration(opts.FlushMicros) * time.Microsecond,
+		results: newResultCache(opts.ResultCacheEntries)}
 	go csp.aggregate()
 	return csp, nil
 }
@@ -115,18 +110,67 @@ func (csp *impl) KeyImport(raw interface{}, opts bccsp.KeyImportOpts) (bccsp.Key
 	}
 	var pub *ecdsa.PublicKey
 	switch v := raw.(type) {
-	case *ecdsa.PublicKey:
+	case *ecdsa.PublicKey: // ECDSAGoPublicKeyImportOpts (bccsp/sw/keyimport.go:94-112)
 		pub = v
-	case *x509.Certificate:
+	case *x509.Certificate: // X509PublicKeyImportOpts (bccsp/sw/keyimport.go:114-134): ECDSA certificates only reach this point
 		pub, _ = v.PublicKey.(*ecdsa.PublicKey)
 	}
+	if pub == nil {
+		// ECDSAPKIXPublicKeyImportOpts (DER bytes) and ECDSAPrivateKeyImportOpts: sw parsed the bytes; recover the point from
+		// the key it built.  A private key verifies with its public half (ecdsaPrivateKeyVerifier, bccsp/sw/ecdsa.go:65-69).
+		pub = publicHalf(k)
+	}
 	if pub == nil || pub.Curve != elliptic.P256() || !pub.Curve.IsOnCurve(pub.X, pub.Y) {
-		return k, nil // P-384, RSA, private keys, ...: stay on the software path (pkcs11.go:259-261 pattern)
+		return k, nil // P-384, RSA, AES, ...: stay on the software path (pkcs11.go:259-261 pattern)
 	}
 	gk := &ecdsaP256Key{Key: k, pub: pub, slot: -1}
 	fill32(&gk.x, pub.X)
 	fill32(&gk.y, pub.Y)
 	return gk, nil
+}
+
+// publicHalf returns the ECDSA public key behind an sw key object (public or private), nil for anything else.  The sw key
+// types are unexported; PublicKey() + Bytes() (PKIX DER, bccsp/sw/ecdsakey.go:60-66,101-110) is their public surface.
+func publicHalf(k bccsp.Key) *ecdsa.PublicKey {
+	pk, err := k.PublicKey()
+	if err != nil {
+		return nil
+	}
+	der, err := pk.Bytes()
+	if err != nil {
+		return nil
+	}
+	parsed, err := x509.ParsePKIXPublicKey(der)
+	if err != nil {
+		return nil
+	}
+	pub, _ := parsed.(*ecdsa.PublicKey)
+	return pub
+}
+
+// The wrapper type is this provider's own: every method that hands a key to the embedded software provider unwraps it first
+// (sw dispatches on reflect.TypeOf(key), bccsp/sw/impl.go:205-270).
+func unwrap(k bccsp.Key) bccsp.Key {
+	if gk, ok := k.(*ecdsaP256Key); ok {
+		return gk.Key
+	}
+	return k
+}
+
+func (csp *impl) Sign(k bccsp.Key, digest []byte, opts bccsp.SignerOpts) ([]byte, error) {
+	return csp.BCCSP.Sign(unwrap(k), digest, opts)
+}
+
+func (csp *impl) KeyDeriv(k bccsp.Key, opts bccsp.KeyDerivOpts) (bccsp.Key, error) {
+	return csp.BCCSP.KeyDeriv(unwrap(k), opts)
+}
+
+func (csp *impl) Encrypt(k bccsp.Key, plaintext []byte, opts bccsp.EncrypterOpts) ([]byte, error) {
+	return csp.BCCSP.Encrypt(unwrap(k), plaintext, opts)
+}
+
+func (csp *impl) Decrypt(k bccsp.Key, ciphertext []byte, opts bccsp.DecrypterOpts) ([]byte, error) {
+	return csp.BCCSP.Decrypt(unwrap(k), ciphertext, opts)
 }
 
 // registerTable builds the key's window table on the device(s) (about 0.3-2 ms of GPU time, once).
@@ -164,6 +208,11 @@ func (csp *impl) Verify(k bccsp.Key, signature, digest []byte, opts bccsp.Signer
 	}
 	if r.BitLen() > 256 {
 		return false, nil // r >= 2^256 > N: ecdsa.Verify returns false
+	}
+	// a verdict the block pre-pass already obtained for exactly this (key, digest, signature): no queueing, no GPU round trip
+	if valid, hit := csp.results.lookup(&gk.x, &gk.y, digest, signature); hit {
+		atomic.AddUint64(&csp.CacheHits, 1)
+		return valid, nil
 	}
 	if atomic.AddUint32(&gk.uses, 1) == tableAfterUses {
 		go csp.registerTable(gk) // identities are verified many times (msp/cache keeps them): worth a table from here on
@@ -208,9 +257,17 @@ func (csp *impl) aggregate() {
 		if !ok {
 			return
 		}
-		slotIdx := <-free // blocks only when both slots are still on the device
+		slotIdx := <-free // blocks only when every slot is still on the device
 		pending := make([]*request, 0, csp.dev.maxBatch)
 		pending = append(pending, first)
+		// Reset is only defined on a stopped, drained timer: a tick left over from a batch that filled up before its deadline
+		// would otherwise flush this batch at once with one or two requests in it.
+		if !timer.Stop() {
+			select {
+			case <-timer.C:
+			default:
+			}
+		}
 		timer.Reset(csp.flush)
 	fill:
 		for len(pending) < csp.dev.maxBatch {
