@@ -23,7 +23,7 @@ EXPORTS = [
     "fabgpu_keys_register", "fabgpu_key_slot_capacity", "fabgpu_host_key_slots", "fabgpu_verify_p256_keyed",
     "fabgpu_verify_p256_keyed_async", "fabgpu_verify_p256_device_keyed", "fabgpu_last_timing", "fabgpu_build_info",
     "fabgpu_msp_configure", "fabgpu_validate_block", "fabgpu_validate_envelopes", "fabgpu_block_buffer", "fabgpu_block_timing", "fabgpu_sha256_segments",
-    "fabgpu_bccsp_verify_batch_async", "fabgpu_bccsp_verify_batch_wait",
+    "fabgpu_bccsp_verify_batch_async", "fabgpu_bccsp_verify_batch_wait", "fabgpu_bccsp_batch_buffers", "fabgpu_bccsp_verify_batch_inplace_async",
     "fabgpu_validate_block_async", "fabgpu_validate_envelopes_async", "fabgpu_validate_wait", "fabgpu_block_buffer_slot",
 ]
 
@@ -228,6 +228,32 @@ class Context:
         status = out if out is not None else np.full(max(n, 1), 255, np.uint8)
         self._ck(lib().fabgpu_bccsp_verify_batch_wait(self._h, ctypes.c_int(slot), _p(status), ctypes.c_size_t(n)))
         return status[:n]
+
+    def bccsp_batch_buffers(self, slot, n_cap, sig_bytes_cap, dig_bytes_cap, k_cap):
+        """numpy views (no copy) of the slot's pinned batch buffers: dict keys_xy uint8[k_cap,64], key_idx int32[n_cap], digests uint8[dig_bytes_cap],
+        dig_off uint32[n_cap+1], sigs uint8[sig_bytes_cap], sig_off uint32[n_cap+1].  Fill them, then bccsp_verify_batch_inplace_async."""
+        pk, pd, ps = (ctypes.POINTER(ctypes.c_uint8)() for _ in range(3))
+        pi = ctypes.POINTER(ctypes.c_int32)()
+        pdo, pso = ctypes.POINTER(ctypes.c_uint32)(), ctypes.POINTER(ctypes.c_uint32)()
+        self._ck(lib().fabgpu_bccsp_batch_buffers(self._h, ctypes.c_int(slot), ctypes.c_size_t(n_cap), ctypes.c_size_t(sig_bytes_cap), ctypes.c_size_t(dig_bytes_cap),
+                                                  ctypes.c_int(k_cap), ctypes.byref(pk), ctypes.byref(pi), ctypes.byref(pd), ctypes.byref(pdo), ctypes.byref(ps), ctypes.byref(pso)))
+        A = np.ctypeslib.as_array
+        return {"keys_xy": A(pk, shape=(max(k_cap, 1), 64)), "key_idx": A(pi, shape=(max(n_cap, 1),)), "digests": A(pd, shape=(max(dig_bytes_cap, 1),)),
+                "dig_off": A(pdo, shape=(n_cap + 1,)), "sigs": A(ps, shape=(max(sig_bytes_cap, 1),)), "sig_off": A(pso, shape=(n_cap + 1,))}
+
+    def bccsp_fill_batch_buffers(self, slot, keys_xy, key_idx, digests, dig_off, sigs, sig_off):
+        """Convenience: reserve + copy a batch into the slot's pinned buffers once; returns (K, n) for bccsp_verify_batch_inplace_async."""
+        keys_xy, key_idx, digests, dig_off, sigs, sig_off = self._batch_args(keys_xy, key_idx, digests, dig_off, sigs, sig_off)
+        n, K = key_idx.shape[0], keys_xy.shape[0]
+        hb = self.bccsp_batch_buffers(slot, n, int(sig_off[n]), int(dig_off[n]), K)
+        hb["keys_xy"][:K] = keys_xy; hb["key_idx"][:n] = key_idx
+        hb["digests"][: int(dig_off[n])] = digests[: int(dig_off[n])]; hb["dig_off"][: n + 1] = dig_off
+        hb["sigs"][: int(sig_off[n])] = sigs[: int(sig_off[n])]; hb["sig_off"][: n + 1] = sig_off
+        return K, n
+
+    def bccsp_verify_batch_inplace_async(self, slot, K, n):
+        self._ck(lib().fabgpu_bccsp_verify_batch_inplace_async(self._h, ctypes.c_int(slot), ctypes.c_int(K), ctypes.c_size_t(n)))
+        return n
 
     def bccsp_verify(self, key_xy, sig, digest):
         """One sw.CSP.Verify call -> (valid: bool, err: str|None) with the reference's error strings."""

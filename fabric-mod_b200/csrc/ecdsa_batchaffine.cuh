@@ -74,11 +74,13 @@ FAB_HD void ba_digits(const u256& u1, const u256& u2, uint32_t* dig, int stride)
     }
 }
 
-// Operand `leaf` of a level: FIRST = a table entry named by the digit array, otherwise a level-1 result.
-template <bool FIRST> FAB_HD const aff* ba_operand(int leaf, const aff* gtab, const aff* qtab, const uint32_t* dig, int stride, const aff* pts,
-                                                   uint32_t infmask, bool& inf)
+// Operand `leaf` of a level: first = a table entry named by the digit array, otherwise a level-1 result.  (Runtime flags, not
+// template parameters: the kernel holds ONE copy of each pass and loops over the levels -- the first version, with a copy per
+// level and per modulus, was 212 KB of code.)
+FAB_HD const aff* ba_operand(bool first, int leaf, const aff* gtab, const aff* qtab, const uint32_t* dig, int stride, const aff* pts,
+                             uint32_t infmask, bool& inf)
 {
-    if (FIRST) {
+    if (first) {
         const uint32_t idx = dig[leaf * stride];
         inf = idx == FAB_BA_INF;
         return (leaf < FAB_BA_NGP ? gtab : qtab) + (inf ? 0u : idx);
@@ -89,36 +91,57 @@ template <bool FIRST> FAB_HD const aff* ba_operand(int leaf, const aff* gtab, co
 
 // Forward pass of one level: pre[k] = d_0 ... d_k with d_k = x(2k+1) - x(2k) (1 where an operand is infinity); returns the product
 // of all n denominators.  exc is set when two finite operands share their x (see the header: cannot happen for reduced scalars).
-template <bool FIRST> FAB_HD u256 ba_forward(int n, const aff* gtab, const aff* qtab, const uint32_t* dig, int stride, const aff* pts,
-                                             uint32_t infmask, u256* pre, uint32_t& exc)
+// The operands of addition k+1 are loaded before the multiplication of addition k is issued (software pipelining: the table
+// gathers are DRAM / L2 round trips, and with ~3 warps per scheduler nothing else would cover them).
+FAB_HD u256 ba_forward(bool first, int n, const aff* gtab, const aff* qtab, const uint32_t* dig, int stride, const aff* pts,
+                       uint32_t infmask, u256* pre, uint32_t& exc)
 {
     u256 c = fe_one();
+    bool fa, fb;
+    const aff* pa = ba_operand(first, 0, gtab, qtab, dig, stride, pts, infmask, fa);
+    const aff* pb = ba_operand(first, 1, gtab, qtab, dig, stride, pts, infmask, fb);
+    u256 xa = pa->x, xb = pb->x;
     for (int k = 0; k < n; k++) {
-        bool fa, fb;
-        const aff* pa = ba_operand<FIRST>(2 * k, gtab, qtab, dig, stride, pts, infmask, fa);
-        const aff* pb = ba_operand<FIRST>(2 * k + 1, gtab, qtab, dig, stride, pts, infmask, fb);
-        u256 dx = fe_sub(pb->x, pa->x);
+        bool nfa = false, nfb = false;
+        u256 nxa = xa, nxb = xb;
+        if (k + 1 < n) {
+            const aff* na = ba_operand(first, 2 * k + 2, gtab, qtab, dig, stride, pts, infmask, nfa);
+            const aff* nb = ba_operand(first, 2 * k + 3, gtab, qtab, dig, stride, pts, infmask, nfb);
+            nxa = na->x; nxb = nb->x;
+        }
+        u256 dx = fe_sub(xb, xa);
         const bool z = u256_is_zero(dx);
         if (fa || fb) dx = fe_one();
         else if (z) { exc = 1u; dx = fe_one(); }
         c = (k == 0) ? dx : fe_mul(c, dx);
         pre[k] = c;
+        xa = nxa; xb = nxb; fa = nfa; fb = nfb;
     }
     return c;
 }
 
 // Backward pass: inv = (d_0 ... d_{n-1})^-1.  Walks k = n-1 .. 0, peels 1/d_k off the running inverse, finishes the affine
-// addition and either stores the result (level 1: out[k], infinity flags returned) or adds it to the Jacobian accumulator
-// (last level).
-template <bool FIRST, bool LAST> FAB_HD uint32_t ba_backward(int n, u256 inv, const aff* gtab, const aff* qtab, const uint32_t* dig, int stride,
-                                                            const aff* pts, uint32_t infmask, const u256* pre, aff* out, jac& acc)
+// addition and either stores the result (out[k], infinity flags returned) or, on the last level, adds it to the Jacobian
+// accumulator.  Same pipelining: the operands of addition k-1 are requested before the five multiplications of addition k.
+FAB_HD uint32_t ba_backward(bool first, bool last, int n, u256 inv, const aff* gtab, const aff* qtab, const uint32_t* dig, int stride,
+                            const aff* pts, uint32_t infmask, const u256* pre, aff* out, jac& acc)
 {
     uint32_t outmask = 0;
+    bool fa, fb;
+    aff a, b;
+    {
+        const aff* pa = ba_operand(first, 2 * n - 2, gtab, qtab, dig, stride, pts, infmask, fa);
+        const aff* pb = ba_operand(first, 2 * n - 1, gtab, qtab, dig, stride, pts, infmask, fb);
+        a = *pa; b = *pb;
+    }
     for (int k = n - 1; k >= 0; k--) {
-        bool fa, fb;
-        const aff* pa = ba_operand<FIRST>(2 * k, gtab, qtab, dig, stride, pts, infmask, fa);
-        const aff* pb = ba_operand<FIRST>(2 * k + 1, gtab, qtab, dig, stride, pts, infmask, fb);
-        const aff a = *pa, b = *pb;
+        bool nfa = false, nfb = false;
+        aff na = a, nb = b;
+        if (k > 0) {
+            const aff* pa = ba_operand(first, 2 * k - 2, gtab, qtab, dig, stride, pts, infmask, nfa);
+            const aff* pb = ba_operand(first, 2 * k - 1, gtab, qtab, dig, stride, pts, infmask, nfb);
+            na = *pa; nb = *pb;
+        }
         u256 dx = fe_sub(b.x, a.x);
         if (fa || fb || u256_is_zero(dx)) dx = fe_one();
         u256 di;                                            // 1 / d_k
@@ -134,23 +157,23 @@ template <bool FIRST, bool LAST> FAB_HD uint32_t ba_backward(int n, u256 inv, co
         if (fa) s = b;
         else if (fb) s = a;
         const bool finf = fa && fb;
-        if (LAST) {
+        if (last) {
             if (!finf) acc = jac_add_aff(acc, s);
         } else {
             out[k] = s;
             outmask |= (finf ? 1u : 0u) << k;
         }
+        a = na; b = nb; fa = nfa; fb = nfb;
     }
     return outmask;
 }
 
 // Montgomery's trick over V values held in a strided array (one lane of the CTA's inverter warp; on the host: one call per
-// group).  MODN: values are plain scalars s in [1, n-1] and the results are s^-1 R mod n (the Montgomery form sc_mul wants);
-// otherwise values are field elements a R and the results a^-1 R.  val[j * vstride] is replaced by its inverse; tmp[j * vstride]
-// is scratch.
-template <bool MODN> FAB_HD void ba_inverse_lane(uint32_t* val, uint32_t* tmp, int V, int vstride, int lstride)
+// group).  modn: values are plain scalars s in [1, n-1] and the results are s^-1 R mod n (the Montgomery form sc_mul wants);
+// otherwise values are field elements a R and the results a^-1 R.  Element j, limb l lives at [j * vstride + l * lstride];
+// val[] is replaced by the inverses, tmp[] is scratch of the same shape.
+FAB_HD void ba_inverse_lane(bool modn, uint32_t* val, uint32_t* tmp, int V, int vstride, int lstride)
 {
-    // element j, limb l lives at [j * vstride + l * lstride]
     u256 c;
 #pragma unroll
     for (int l = 0; l < 8; l++) c.v[l] = val[l * lstride];
@@ -160,17 +183,19 @@ template <bool MODN> FAB_HD void ba_inverse_lane(uint32_t* val, uint32_t* tmp, i
         u256 v;
 #pragma unroll
         for (int l = 0; l < 8; l++) v.v[l] = val[j * vstride + l * lstride];
-        c = MODN ? sc_mul(c, v) : fe_mul(c, v);
+        c = modn ? sc_mul(c, v) : fe_mul(c, v);
     }
-    // MODN: c = s_0 ... s_{V-1} R^-(V-1); its plain inverse times R (one product with R^2) is what the peeling below needs.
-    // field: c = a_0 ... a_{V-1} R; fe_inv_safegcd keeps the Montgomery domain.
-    u256 inv = MODN ? sc_mul(inv_safegcd<ModN>(c), sc_r2()) : fe_inv_safegcd(c);
+    // modn:  c = s_0 ... s_{V-1} R^-(V-1); its plain inverse times R (one product with R^2) is what the peeling below needs.
+    // field: c = a_0 ... a_{V-1} R; the plain inverse of that residue is (a_0 ...)^-1 R^-1, one product with R^3 restores a^-1 R.
+    const u256 r3p = u256_const(0x0000000au, 0xfffffffdu, 0xfffffff7u, 0xffffffedu, 0xfffffffcu, 0x00000005u, 0x00000001u, 0x00000018u);
+    u256 inv = inv_safegcd_rt(c, modn ? 0 : 1);
+    inv = modn ? sc_mul(inv, sc_r2()) : fe_mul(inv, r3p);
     for (int j = V - 1; j >= 1; j--) {
         u256 p, v;
 #pragma unroll
         for (int l = 0; l < 8; l++) { p.v[l] = tmp[(j - 1) * vstride + l * lstride]; v.v[l] = val[j * vstride + l * lstride]; }
-        const u256 o = MODN ? sc_mul(inv, p) : fe_mul(inv, p);
-        inv = MODN ? sc_mul(inv, v) : fe_mul(inv, v);
+        const u256 o = modn ? sc_mul(inv, p) : fe_mul(inv, p);
+        inv = modn ? sc_mul(inv, v) : fe_mul(inv, v);
 #pragma unroll
         for (int l = 0; l < 8; l++) val[j * vstride + l * lstride] = o.v[l];
     }

@@ -204,12 +204,25 @@ ecdsa_verify_lanes_kernel(const int32_t* __restrict__ key_slot, const uint8_t* _
 #ifndef FAB_BA_INVWARPS
 #define FAB_BA_INVWARPS 1             // warps that run the shared inversion of a round (each lane: THREADS / (32 INVWARPS) values)
 #endif
+#ifndef FAB_BA_SMS
+#define FAB_BA_SMS 148
+#endif
+#ifndef FAB_BA_STAGGER_NS
+#define FAB_BA_STAGGER_NS 0           // CTAs that share an SM start this many ns apart (x their index modulo the residency): while one
+#endif                                // CTA waits for its inverter warp, the other is in a compute phase instead of waiting in step
+
+// The shared inversion of one exchange round, run by the lanes of the round's inverter warp(s): out of line, ONE copy for the
+// three rounds and both moduli.
+__device__ __noinline__ void ba_inverter(bool modn, uint32_t* val, uint32_t* tmp)
+{
+    ba_inverse_lane(modn, val, tmp, FAB_BA_THREADS / (32 * FAB_BA_INVWARPS), 32 * FAB_BA_INVWARPS, FAB_BA_THREADS);
+}
 
 // One exchange round: every thread contributes v, the round's inverter warps invert all FAB_BA_THREADS values with Montgomery's
 // trick (ba_inverse_lane), every thread gets its own inverse back.  exa / exb: 8 x FAB_BA_THREADS words each, [limb][thread].
-template <bool MODN> __device__ __forceinline__ u256 ba_cta_inverse(const u256& v, uint32_t* exa, uint32_t* exb, int round)
+__device__ __forceinline__ u256 ba_cta_inverse(bool modn, const u256& v, uint32_t* exa, uint32_t* exb, int round)
 {
-    constexpr int T = FAB_BA_THREADS, W = T / 32, K = FAB_BA_INVWARPS, V = T / (32 * K);
+    constexpr int T = FAB_BA_THREADS, W = T / 32, K = FAB_BA_INVWARPS;
     const int tid = threadIdx.x;
 #pragma unroll
     for (int l = 0; l < 8; l++) exa[l * T + tid] = v.v[l];
@@ -218,7 +231,7 @@ template <bool MODN> __device__ __forceinline__ u256 ba_cta_inverse(const u256& 
     const int rank = ((tid >> 5) - first + W) % W;             // this warp's position among the round's inverter warps
     if (rank < K) {
         const int g = rank * 32 + (tid & 31);                  // handles values g, g + 32 K, g + 64 K, ...
-        ba_inverse_lane<MODN>(exa + g, exb + g, V, 32 * K, T);
+        ba_inverter(modn, exa + g, exb + g);
     }
     __syncthreads();
     u256 r;
@@ -244,42 +257,46 @@ ecdsa_verify_ba_kernel(const int32_t* __restrict__ key_slot, const uint8_t* __re
     __shared__ uint32_t dig[FAB_BA_NP * T];
     __shared__ uint32_t exa[8 * T], exb[8 * T];
     if (n_dev) n = min(n, n_base + *n_dev);
+#if FAB_BA_STAGGER_NS > 0
+    {   // CTAs are handed to SMs round-robin: blockIdx / (number of SMs) is this CTA's position among its SM's residents
+        const unsigned pos = (blockIdx.x / FAB_BA_SMS) % FAB_BA_MINBLOCKS;
+        if (pos) __nanosleep(pos * FAB_BA_STAGGER_NS);
+    }
+#endif
     const uint32_t idx = blockIdx.x * T + threadIdx.x;
     const size_t o = (size_t)idx * 32;
     const aff* qt = qtab;
     bool ok = false;
-    u256 ev, rv, sv;
+    u256 v = u256_const(1, 0, 0, 0, 0, 0, 0, 0);
     if (idx < n) {
         const int32_t slot = key_slot[idx];
         if (slot >= 0) {
             qt = qtab + (size_t)slot * (FAB_Q_WINDOWS * FAB_Q_ENTRIES);
-            ev = load_be32(e + o); rv = load_be32(r + o); sv = load_be32(s + o);
-            ok = ba_range_ok(rv, sv);
+            const u256 sv = load_be32(s + o);
+            ok = ba_range_ok(load_be32(r + o), sv);
+            if (ok) v = sv;
         }
     }
     uint32_t* mydig = dig + threadIdx.x;
-    const u256 w = ba_cta_inverse<true>(ok ? sv : u256_const(1, 0, 0, 0, 0, 0, 0, 0), exa, exb, 0);
+    v = ba_cta_inverse(true, v, exa, exb, 0);                 // w = s^-1 R mod n
     BaScratch sc;
-    uint32_t exc = 0;
-    u256 c = fe_one();
-    if (ok) {
-        ba_scalars(ev, rv, w, mydig, T);
-        c = ba_forward<true>(FAB_BA_N1, gtab, qt, mydig, T, nullptr, 0u, sc.pre, exc);
-    }
-    u256 inv = ba_cta_inverse<false>(c, exa, exb, 1);
-    uint32_t m1 = 0;
+    uint32_t exc = 0, m1 = 0;
     jac acc = jac_infinity();
-    c = fe_one();
-    if (ok) {
-        m1 = ba_backward<true, false>(FAB_BA_N1, inv, gtab, qt, mydig, T, nullptr, 0u, sc.pre, sc.pts, acc);
-        c = ba_forward<false>(FAB_BA_N2, gtab, qt, mydig, T, sc.pts, m1, sc.pre, exc);
+    if (ok) ba_scalars(load_be32(e + o), load_be32(r + o), v, mydig, T);
+#pragma unroll 1
+    for (int level = 0; level < 2; level++) {
+        const bool first = level == 0;
+        const int cnt = first ? FAB_BA_N1 : FAB_BA_N2;
+        u256 c = fe_one();
+        if (ok) c = ba_forward(first, cnt, gtab, qt, mydig, T, sc.pts, m1, sc.pre, exc);
+        c = ba_cta_inverse(false, c, exa, exb, 1 + level);
+        if (ok) {
+            const uint32_t m = ba_backward(first, !first, cnt, c, gtab, qt, mydig, T, sc.pts, m1, sc.pre, sc.pts, acc);
+            if (first) m1 = m;
+        }
     }
-    inv = ba_cta_inverse<false>(c, exa, exb, 2);
     uint32_t res = V_INVALID;
-    if (ok) {
-        ba_backward<false, true>(FAB_BA_N2, inv, gtab, qt, mydig, T, sc.pts, m1, sc.pre, nullptr, acc);
-        res = exc ? ba_fallback_verify(qt, e + o, r + o, s + o, gtab) : final_check(acc, load_be32(r + o));
-    }
+    if (ok) res = exc ? ba_fallback_verify(qt, e + o, r + o, s + o, gtab) : final_check(acc, load_be32(r + o));
     const uint32_t vmask = __ballot_sync(0xffffffffu, res == V_VALID);
     if ((threadIdx.x & 31u) == 0 && idx < n) {
         mask[idx >> 5] = vmask;

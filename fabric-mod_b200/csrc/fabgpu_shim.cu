@@ -469,6 +469,13 @@ int init_impl(fabgpu_ctx* ctx, const int* device_ids, int n_dev, size_t max_batc
         dv.id = ids[d];
         CK(ctx, cudaSetDevice(dv.id));
         CK(ctx, cudaDeviceGetAttribute(&dv.sms, cudaDevAttrMultiProcessorCount, dv.id));
+        {   // Table gathers read 64-byte points at random addresses: by default the L2 fetches 128 bytes around a miss (two sectors'
+            // worth of DRAM traffic per point).  FABGPU_L2_FETCH = 32 / 64 / 128 sets cudaLimitMaxL2FetchGranularity; default 64.
+            const char* fg = getenv("FABGPU_L2_FETCH");
+            const size_t want = fg ? (size_t)atoi(fg) : 64;
+            if (want == 32 || want == 64 || want == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, want);   // a hint: failure is not an error
+            (void)cudaGetLastError();
+        }
         CK(ctx, cudaMalloc(&dv.gtab, tab_entries * sizeof(aff)));
         CK(ctx, cudaMalloc(&dv.qtab, (size_t)ctx->key_slots * FAB_Q_WINDOWS * FAB_Q_ENTRIES * sizeof(aff)));
         for (auto& ds : dv.slot) {
@@ -637,8 +644,7 @@ int fabgpu_keys_register(fabgpu_ctx* ctx, const uint8_t* keys_xy, int K, int32_t
         if (best < 0) { slots_out[k] = -1; continue; }            // more distinct keys in one call than slots: stays generic
         // The slot's old owner loses it NOW (its handles die with the generation bump), but the new key is mapped only after
         // its table exists on every device: a failure below leaves the slot empty, never pointing at another key's table.
-        if (!ctx->slot_key[best].empty()) { ctx->key_map.erase(ctx->slot_key[best]); ctx->slot_key[best].clear(); }
-        ctx->slot_gen[best]++;
+        if (!ctx->slot_key[best].empty()) { ctx->key_map.erase(ctx->slot_key[best]); ctx->slot_key[best].clear(); ctx->slot_gen[best]++; }
         ctx->slot_tick[best] = ctx->tick; slot_taken[best] = 1;
         slots_out[k] = -1;
         fresh.push_back(k); fresh_slot.push_back(best);
@@ -777,22 +783,10 @@ int fabgpu_gate_signature(const uint8_t* sig, size_t sig_len, uint8_t r_out[32],
 // (parallel streaming copies) and reads one status byte per signature back.  Device 0 of the context.
 // Device-gated batch, first half: stage into the slot's pinned buffers and enqueue copies + three kernels + the status
 // read-back on the slot's stream.  Returns without waiting; the caller's buffers are no longer referenced.
-static int bccsp_device_submit(fabgpu_ctx* ctx, int slot, const uint8_t* keys_xy, int K, const int32_t* key_idx, const uint8_t* digests,
-                               const uint32_t* dig_off, const uint8_t* sigs, const uint32_t* sig_off, size_t n,
-                               const std::vector<int32_t>& slot_of)
+// Grows the slot's pinned + device buffers of the device-gated batch path to the given capacities.
+static int gate_bufs_reserve(fabgpu_ctx* ctx, int slot, size_t n, size_t sig_bytes, size_t dig_bytes, size_t K)
 {
-    auto now = [] { return std::chrono::steady_clock::now(); };
-    auto us = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
-        return std::chrono::duration<double, std::micro>(b - a).count();
-    };
-    auto t0 = now();
-    Device& dv = ctx->devs[0];
-    DevSlot& ds = dv.slot[slot];
     auto& gb = ctx->gb[slot];
-    CK(ctx, cudaSetDevice(dv.id));
-    // sig_off / dig_off may be a window of a longer table (a chunk of a call): bytes [off[0], off[n]) of the blobs belong to it
-    const uint32_t sig_base = sig_off[0], dig_base = dig_off[0];
-    const size_t sig_bytes = sig_off[n] - sig_base, dig_bytes = dig_off[n] - dig_base;
     int rc = 0;
     if (n > gb.n_cap) {
         const size_t c = round_up32(n + (n >> 2) + 1024);
@@ -808,13 +802,35 @@ static int bccsp_device_submit(fabgpu_ctx* ctx, int slot, const uint8_t* keys_xy
     }
     if (sig_bytes > gb.sig_cap) { const size_t c = sig_bytes + (sig_bytes >> 2) + 4096; gb.sig_cap = 0; rc |= grow_host(ctx, gb.h_sigs, c); rc |= grow_dev(ctx, gb.d_sigs, c); if (rc) return FABGPU_E_CUDA; gb.sig_cap = c; }
     if (dig_bytes > gb.dig_cap) { const size_t c = dig_bytes + (dig_bytes >> 2) + 4096; gb.dig_cap = 0; rc |= grow_host(ctx, gb.h_digs, c); rc |= grow_dev(ctx, gb.d_digs, c); if (rc) return FABGPU_E_CUDA; gb.dig_cap = c; }
-    if ((size_t)K > gb.k_cap) {
-        const size_t c = (size_t)K + 64;
+    if (K > gb.k_cap) {
+        const size_t c = K + 64;
         gb.k_cap = 0;
         rc |= grow_host(ctx, gb.h_keys, 64 * c); rc |= grow_host(ctx, gb.h_slot_of, 4 * c); rc |= grow_dev(ctx, gb.d_keys, 64 * c); rc |= grow_dev(ctx, gb.d_slot_of, 4 * c);
         if (rc) return FABGPU_E_CUDA;
         gb.k_cap = c;
     }
+    return FABGPU_OK;
+}
+
+// inplace: the batch already lies in the slot's pinned buffers (fabgpu_bccsp_batch_buffers): nothing is staged.
+static int bccsp_device_submit(fabgpu_ctx* ctx, int slot, const uint8_t* keys_xy, int K, const int32_t* key_idx, const uint8_t* digests,
+                               const uint32_t* dig_off, const uint8_t* sigs, const uint32_t* sig_off, size_t n,
+                               const std::vector<int32_t>& slot_of, bool inplace = false)
+{
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto us = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+        return std::chrono::duration<double, std::micro>(b - a).count();
+    };
+    auto t0 = now();
+    Device& dv = ctx->devs[0];
+    DevSlot& ds = dv.slot[slot];
+    auto& gb = ctx->gb[slot];
+    CK(ctx, cudaSetDevice(dv.id));
+    // sig_off / dig_off may be a window of a longer table (a chunk of a call): bytes [off[0], off[n]) of the blobs belong to it
+    const uint32_t sig_base = sig_off[0], dig_base = dig_off[0];
+    const size_t sig_bytes = sig_off[n] - sig_base, dig_bytes = dig_off[n] - dig_base;
+    int rc = gate_bufs_reserve(ctx, slot, n, sig_bytes, dig_bytes, (size_t)(K > 0 ? K : 0));
+    if (rc) return rc;
     // stage: every host thread copies its slice of each array
     const int T = ctx->pool->size();
     bool all_slots = K > 0;
@@ -823,8 +839,8 @@ static int bccsp_device_submit(fabgpu_ctx* ctx, int slot, const uint8_t* keys_xy
         std::lock_guard<std::mutex> lk(ctx->mu);
         for (int k = 0; k < K; k++) { gb.h_slot_of[k] = handle_to_slot(ctx, slot_of[k]); if (gb.h_slot_of[k] < 0) all_slots = false; }
     }
-    if (K > 0) memcpy(gb.h_keys, keys_xy, 64 * (size_t)K);
-    ctx->pool->run([&](int tid) {
+    if (K > 0 && !inplace) memcpy(gb.h_keys, keys_xy, 64 * (size_t)K);
+    if (!inplace) ctx->pool->run([&](int tid) {
         auto slice = [&](size_t total, size_t& lo, size_t& hi) { lo = total * (size_t)tid / T; hi = total * (size_t)(tid + 1) / T; };
         size_t lo, hi;
         slice(sig_bytes, lo, hi); stage_copy(gb.h_sigs + lo, sigs + sig_base + lo, hi - lo);
@@ -935,6 +951,50 @@ int fabgpu_bccsp_verify_batch_async(fabgpu_ctx* ctx, int slot, const uint8_t* ke
         if (n) { rc = bccsp_batch_hostgated(ctx, keys_xy, K, key_idx, digests, dig_off, sigs, sig_off, n, gb.done_status.data(), slot_of); if (rc) return rc; }
         gb.on_device = false;
     }
+    gb.busy = true;
+    return FABGPU_OK;
+}
+
+int fabgpu_bccsp_batch_buffers(fabgpu_ctx* ctx, int slot, size_t n_cap, size_t sig_bytes_cap, size_t dig_bytes_cap, int k_cap, uint8_t** keys_xy,
+                               int32_t** key_idx, uint8_t** digests, uint32_t** dig_off, uint8_t** sigs, uint32_t** sig_off)
+{
+    if (!ctx || slot < 0 || slot >= FABGPU_SLOTS || k_cap < 0 || !keys_xy || !key_idx || !digests || !dig_off || !sigs || !sig_off) return FABGPU_E_ARG;
+    if (ctx->devs.size() != 1) { ctx->last_error = "the in-place batch form runs the gates on the device: single-device contexts only"; return FABGPU_E_ARG; }
+    std::lock_guard<std::mutex> lk(ctx->gb_mu[slot]);
+    auto& gb = ctx->gb[slot];
+    if (gb.busy) { ctx->last_error = "slot holds a batch in flight"; return FABGPU_E_ARG; }
+    CK(ctx, cudaSetDevice(ctx->devs[0].id));
+    int rc = gate_bufs_reserve(ctx, slot, n_cap, sig_bytes_cap, dig_bytes_cap, (size_t)k_cap);
+    if (rc) return rc;
+    *keys_xy = gb.h_keys; *key_idx = gb.h_kidx; *digests = gb.h_digs; *dig_off = gb.h_dig_off; *sigs = gb.h_sigs; *sig_off = gb.h_sig_off;
+    return FABGPU_OK;
+}
+
+int fabgpu_bccsp_verify_batch_inplace_async(fabgpu_ctx* ctx, int slot, int K, size_t n)
+{
+    if (!ctx || slot < 0 || slot >= FABGPU_SLOTS || K < 0) return FABGPU_E_ARG;
+    std::lock_guard<std::mutex> lk(ctx->gb_mu[slot]);
+    std::lock_guard<std::mutex> lk0(ctx->slot0_mu);
+    auto& gb = ctx->gb[slot];
+    if (gb.busy) { ctx->last_error = "slot already holds a batch: call fabgpu_bccsp_verify_batch_wait first"; return FABGPU_E_ARG; }
+    if (n > gb.n_cap || (size_t)K > gb.k_cap || !gb.h_sig_off) { ctx->last_error = "batch exceeds the capacities given to fabgpu_bccsp_batch_buffers"; return FABGPU_E_ARG; }
+    if (n && (gb.h_sig_off[0] != 0 || gb.h_dig_off[0] != 0 || gb.h_sig_off[n] > gb.sig_cap || gb.h_dig_off[n] > gb.dig_cap)) {
+        ctx->last_error = "offset tables must start at 0 and stay inside the buffers"; return FABGPU_E_ARG;
+    }
+    if (!device_gates_apply(ctx, gb.h_dig_off, gb.h_sig_off, n) && n) { ctx->last_error = "the in-place batch form needs the device gates"; return FABGPU_E_ARG; }
+    auto t_start = std::chrono::steady_clock::now();
+    ctx->timing[0] = ctx->timing[1] = ctx->timing[2] = ctx->timing[3] = 0;
+    std::vector<int32_t> slot_of;
+    int rc = resolve_key_tables(ctx, gb.h_keys, K, gb.h_kidx, n, slot_of);
+    if (rc) return rc;
+    ctx->timing[0] = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_start).count();
+    if (fault_injected()) { ctx->last_error = "fault injected (FABGPU_FAULT_INJECT=1)"; return FABGPU_E_INJECTED; }
+    gb.n = n;
+    if (n) {
+        rc = bccsp_device_submit(ctx, slot, gb.h_keys, K, gb.h_kidx, gb.h_digs, gb.h_dig_off, gb.h_sigs, gb.h_sig_off, n, slot_of, true);
+        if (rc) { cudaStreamSynchronize(ctx->devs[0].slot[slot].stream); return rc; }
+        gb.on_device = true;
+    } else { gb.done_status.clear(); gb.on_device = false; }
     gb.busy = true;
     return FABGPU_OK;
 }

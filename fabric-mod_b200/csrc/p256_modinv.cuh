@@ -222,4 +222,106 @@ FAB_HD u256 sc_inv_to_mont_safegcd(const u256& s)
     return sc_mul(sc_inv_safegcd(s), sc_r2());
 }
 
+// ---- one compiled copy for both moduli (device code size): the modulus comes from a small table instead of a template ----
+// row 0: n, row 1: p; [0..8] = 30-bit limbs, [9] = modulus^-1 mod 2^30
+#define FAB_MODTAB_INIT {{0x3c632551, 0x0ee72b0b, 0x3179e84f, 0x39beab69, 0x3fffffbc, 0x3fffffff, 0x00000fff, 0x3fffc000, 0x0000ffff, 0x11ff43b1}, \
+                         {0x3fffffff, 0x3fffffff, 0x3fffffff, 0x0000003f, 0x00000000, 0x00000000, 0x00001000, 0x3fffc000, 0x0000ffff, 0x3fffffff}}
+#if defined(__CUDACC__)
+__constant__ int32_t c_modtab[2][10] = FAB_MODTAB_INIT;
+#endif
+static const int32_t h_modtab[2][10] = FAB_MODTAB_INIT;
+#if defined(__CUDA_ARCH__)
+#define FAB_MODTAB c_modtab
+#else
+#define FAB_MODTAB h_modtab
+#endif
+struct ModRT {
+    int which;
+    FAB_HD s30x9 m() const { s30x9 r; for (int i = 0; i < 9; i++) r.v[i] = FAB_MODTAB[which][i]; return r; }
+    FAB_HD uint32_t inv30() const { return (uint32_t)FAB_MODTAB[which][9]; }
+};
+
+FAB_HD void update_de30_rt(s30x9& d, s30x9& e, const int32_t* t, const s30x9& m, uint32_t minv)
+{
+    const int32_t u = t[0], v = t[1], q = t[2], r = t[3];
+    const int32_t sd = d.v[8] >> 31, se = e.v[8] >> 31;
+    int32_t md = (u & sd) + (v & se);
+    int32_t me = (q & sd) + (r & se);
+    int64_t cd = (int64_t)u * d.v[0] + (int64_t)v * e.v[0];
+    int64_t ce = (int64_t)q * d.v[0] + (int64_t)r * e.v[0];
+    md -= (int32_t)((minv * (uint32_t)cd + (uint32_t)md) & FAB_M30);
+    me -= (int32_t)((minv * (uint32_t)ce + (uint32_t)me) & FAB_M30);
+    cd += (int64_t)m.v[0] * md;
+    ce += (int64_t)m.v[0] * me;
+    cd >>= 30; ce >>= 30;
+#pragma unroll
+    for (int i = 1; i < 9; i++) {
+        cd += (int64_t)u * d.v[i] + (int64_t)v * e.v[i] + (int64_t)m.v[i] * md;
+        ce += (int64_t)q * d.v[i] + (int64_t)r * e.v[i] + (int64_t)m.v[i] * me;
+        d.v[i - 1] = (int32_t)(cd & FAB_M30); cd >>= 30;
+        e.v[i - 1] = (int32_t)(ce & FAB_M30); ce >>= 30;
+    }
+    d.v[8] = (int32_t)cd;
+    e.v[8] = (int32_t)ce;
+}
+
+FAB_HD s30x9 normalize30_rt(const s30x9& a, bool negate, const s30x9& m)
+{
+    s30x9 r = a;
+    if (negate) {
+#pragma unroll
+        for (int i = 0; i < 9; i++) r.v[i] = -r.v[i];
+    }
+    for (int pass = 0; pass < 3; pass++) {
+        int32_t c = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) { r.v[i] += c; c = r.v[i] >> 30; r.v[i] &= FAB_M30; }
+        r.v[8] += c;
+        if (r.v[8] < 0) {
+#pragma unroll
+            for (int i = 0; i < 9; i++) r.v[i] += m.v[i];
+        } else {
+            bool ge = true, decided = false;
+#pragma unroll
+            for (int i = 8; i >= 0; i--) {
+                if (!decided && r.v[i] != m.v[i]) { ge = r.v[i] > m.v[i]; decided = true; }
+            }
+            if (ge) {
+#pragma unroll
+                for (int i = 0; i < 9; i++) r.v[i] -= m.v[i];
+            }
+        }
+    }
+    int32_t c = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) { r.v[i] += c; c = r.v[i] >> 30; r.v[i] &= FAB_M30; }
+    r.v[8] += c;
+    return r;
+}
+
+// a in [1, m-1] -> a^-1 mod m, m = n (which = 0) or p (which = 1)
+FAB_HD u256 inv_safegcd_rt(const u256& a, int which)
+{
+    ModRT mod; mod.which = which;
+    const s30x9 m = mod.m();
+    const uint32_t minv = mod.inv30();
+    s30x9 f = m, g = s30_from_u256(a);
+    s30x9 d, e;
+#pragma unroll
+    for (int i = 0; i < 9; i++) { d.v[i] = 0; e.v[i] = 0; }
+    e.v[0] = 1;
+    int32_t delta = 1;
+    for (int it = 0; it < 25; it++) {
+        int32_t t[4];
+        delta = divsteps30(delta, (uint32_t)f.v[0] | ((uint32_t)f.v[1] << 30), (uint32_t)g.v[0] | ((uint32_t)g.v[1] << 30), t);
+        update_de30_rt(d, e, t, m, minv);
+        update_fg30(f, g, t);
+        int32_t nz = 0;
+#pragma unroll
+        for (int i = 0; i < 9; i++) nz |= g.v[i];
+        if (nz == 0) break;
+    }
+    return s30_to_u256(normalize30_rt(d, f.v[8] < 0, m));
+}
+
 }  // namespace fabgpu

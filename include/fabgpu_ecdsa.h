@@ -138,6 +138,16 @@ int fabgpu_bccsp_verify_batch_async(fabgpu_ctx* ctx, int slot, const uint8_t* ke
                                     const uint8_t* digests, const uint32_t* dig_off, const uint8_t* sigs,
                                     const uint32_t* sig_off, size_t n);
 int fabgpu_bccsp_verify_batch_wait(fabgpu_ctx* ctx, int slot, uint8_t* status, size_t n);
+/* Zero-copy form of the pair above (what the Go provider's block pre-pass and bench.py's e2e leg use): the library hands out
+ * the slot's PINNED staging buffers, the caller writes the batch there -- keys (K x 64 B), key index per signature, digest and
+ * DER blobs with their offset tables (offsets start at 0) -- and _inplace_async enqueues the copies and kernels straight from
+ * them; no second host copy, no staging threads.  The buffers stay valid (and keep their contents) until a later
+ * fabgpu_bccsp_batch_buffers call asks for larger capacities; they must not be rewritten while the slot's batch is in flight.
+ * Single-device contexts; completion and statuses through fabgpu_bccsp_verify_batch_wait. */
+int fabgpu_bccsp_batch_buffers(fabgpu_ctx* ctx, int slot, size_t n_cap, size_t sig_bytes_cap, size_t dig_bytes_cap, int k_cap,
+                               uint8_t** keys_xy, int32_t** key_idx, uint8_t** digests, uint32_t** dig_off, uint8_t** sigs,
+                               uint32_t** sig_off);
+int fabgpu_bccsp_verify_batch_inplace_async(fabgpu_ctx* ctx, int slot, int K, size_t n);
 /* Single call with the reference's exact error strings (sw.CSP.Verify).  key_xy == NULL is the nil key.
  * *valid and err (NUL-terminated, truncated to errcap) mirror the Go (bool, error) pair; err[0] == 0 is nil. */
 int fabgpu_bccsp_verify(fabgpu_ctx* ctx, const uint8_t* key_xy, const uint8_t* sig, size_t sig_len,

@@ -110,13 +110,13 @@ static const std::vector<aff>* ba_key_table(std::vector<std::pair<std::vector<ui
     return &cache.back().second;
 }
 
-template <bool MODN> static void ba_exchange(std::vector<u256>& vals, int V)
+static void ba_exchange(bool modn, std::vector<u256>& vals, int V)
 {
     // [limb][thread] layout like the kernel's shared-memory buffers
     const int T = (int)vals.size(), lanes = T / V;
     std::vector<uint32_t> exa(8 * T), exb(8 * T);
     for (int t = 0; t < T; t++) for (int l = 0; l < 8; l++) exa[l * T + t] = vals[t].v[l];
-    for (int g = 0; g < lanes; g++) ba_inverse_lane<MODN>(exa.data() + g, exb.data() + g, V, lanes, T);
+    for (int g = 0; g < lanes; g++) ba_inverse_lane(modn, exa.data() + g, exb.data() + g, V, lanes, T);
     for (int t = 0; t < T; t++) for (int l = 0; l < 8; l++) vals[t].v[l] = exa[l * T + t];
 }
 
@@ -146,32 +146,32 @@ void hostsim_verify_batch_ba(const uint8_t* qx, const uint8_t* qy, const uint8_t
             h.ok = ba_range_ok(h.rv, h.sv);
             if (h.ok) vals[t] = h.sv;
         }
-        ba_exchange<true>(vals, V);
+        ba_exchange(true, vals, V);
         for (int t = 0; t < GROUP; t++) {
             Th& h = th[t];
             u256 c = fe_one();
             if (h.ok) {
                 ba_scalars(h.ev, h.rv, vals[t], h.dig, 1);
-                c = ba_forward<true>(FAB_BA_N1, g_tab.data(), h.qt, h.dig, 1, nullptr, 0u, h.sc.pre, h.exc);
+                c = ba_forward(true, FAB_BA_N1, g_tab.data(), h.qt, h.dig, 1, nullptr, 0u, h.sc.pre, h.exc);
             }
             vals[t] = c;
         }
-        ba_exchange<false>(vals, V);
+        ba_exchange(false, vals, V);
         for (int t = 0; t < GROUP; t++) {
             Th& h = th[t];
             u256 c = fe_one();
             h.acc = jac_infinity();
             if (h.ok) {
-                h.m1 = ba_backward<true, false>(FAB_BA_N1, vals[t], g_tab.data(), h.qt, h.dig, 1, nullptr, 0u, h.sc.pre, h.sc.pts, h.acc);
-                c = ba_forward<false>(FAB_BA_N2, g_tab.data(), h.qt, h.dig, 1, h.sc.pts, h.m1, h.sc.pre, h.exc);
+                h.m1 = ba_backward(true, false, FAB_BA_N1, vals[t], g_tab.data(), h.qt, h.dig, 1, nullptr, 0u, h.sc.pre, h.sc.pts, h.acc);
+                c = ba_forward(false, FAB_BA_N2, g_tab.data(), h.qt, h.dig, 1, h.sc.pts, h.m1, h.sc.pre, h.exc);
             }
             vals[t] = c;
         }
-        ba_exchange<false>(vals, V);
+        ba_exchange(false, vals, V);
         for (int t = 0; t < GROUP; t++) {
             Th& h = th[t];
             if (!h.ok) continue;
-            ba_backward<false, true>(FAB_BA_N2, vals[t], g_tab.data(), h.qt, h.dig, 1, h.sc.pts, h.m1, h.sc.pre, nullptr, h.acc);
+            ba_backward(false, true, FAB_BA_N2, vals[t], g_tab.data(), h.qt, h.dig, 1, h.sc.pts, h.m1, h.sc.pre, nullptr, h.acc);
             out[base + t] = (uint8_t)(h.exc ? ecdsa_verify_one_cached(h.qt, h.ev, h.rv, h.sv, g_tab.data()) : final_check(h.acc, h.rv));
         }
     }

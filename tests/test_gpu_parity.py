@@ -466,6 +466,30 @@ def test_bccsp_batch_async_two_slots_in_flight():
     c.close()
 
 
+def test_bccsp_batch_inplace_pinned_buffers_match_the_copying_form():
+    """fabgpu_bccsp_batch_buffers + fabgpu_bccsp_verify_batch_inplace_async: the batch is written straight into the slot's pinned
+    buffers; statuses must equal the staging form's and the oracle's, slot after slot, including a ragged adversarial tail."""
+    from tools import parity_workload as pw
+    c = pkg().binding.Context(max_batch=8192)
+    sh = pw.Shard(0, 1, 6000, 12, nthreads=8)                        # 5 % tampered r + the tests/vectors.py tail (ragged digests, bad DER)
+    exp = pw.oracle_status(sh, 8)
+    ref = c.bccsp_verify_batch(*sh.args())
+    assert (ref == exp).all()
+    for slot in range(pkg().binding.SLOTS):
+        K, n = c.bccsp_fill_batch_buffers(slot, *sh.args())
+        assert n == sh.n
+        c.bccsp_verify_batch_inplace_async(slot, K, n)
+    for slot in range(pkg().binding.SLOTS):
+        got = c.bccsp_verify_batch_wait(slot, sh.n)
+        assert (got == exp).all(), slot
+    # resubmitting a slot reuses the bytes it holds; an oversized batch is refused
+    c.bccsp_verify_batch_inplace_async(0, K, 100)
+    assert (c.bccsp_verify_batch_wait(0, 100) == exp[:100]).all()
+    with pytest.raises(pkg().binding.FabGpuError):
+        c.bccsp_verify_batch_inplace_async(1, K, 1 << 20)
+    c.close()
+
+
 # ---------------------------------------------------------------------------------------------------------
 # one context driving several GPUs (what the Go provider does: Devices: [0..7] in core.yaml)
 # ---------------------------------------------------------------------------------------------------------

@@ -30,7 +30,9 @@ def main():
     slots = ctx.keys_register(w.keys_xy) & 0xFFF          # device-resident API takes raw slot indices
     print("%-32s keys_register(64 keys) %.1f ms" % (os.path.basename(lib), (time.perf_counter() - t0) * 1e3), flush=True)
     ks = torch.from_numpy(slots[w.key_idx]).to(dev)
-    for mode, n in [(m, n) for n in batches for m in ("generic", "cached")]:
+    only = os.environ.get("KBENCH_ONLY")                      # "cached": the key-table kernel only (variant sweeps)
+    modes = ("cached",) if only == "cached" else ("generic", "cached")
+    for mode, n in [(m, n) for n in batches for m in modes]:
         def go():
             if mode == "generic":
                 ctx.verify_p256_device(*[x.data_ptr() for x in t], n, mask.data_ptr(), 0, st.cuda_stream)
@@ -51,7 +53,7 @@ def main():
         print("%-32s %-8s n=%7d  %8.3f ms  %8.2f Mverify/s" % (os.path.basename(lib), mode, n, ms, n / ms / 1e3), flush=True)
     # pinned-slot path: H2D + kernel + D2H + sync per call (what fabgpu_verify_p256_keyed does), wall clock
     import time
-    for n in batches:
+    for n in ([] if only else batches):
         hb = ctx.host_buffers(0)
         for name, arr in (("qx", w.qx()), ("qy", w.qy()), ("e", w.digest), ("r", w.r), ("s", w.s)):
             hb[name][:n] = arr[:n]
