@@ -232,8 +232,16 @@ def run_gpu(args):
     assert (slots >= 0).all()
     kslots = [torch.from_numpy(np.ascontiguousarray(slots[w.key_idx][np.roll(np.arange(B), 997 * k)])).to(dev) for k in range(ROT)]
 
-    def step(k, generic=False):
+    # N > 1: the bitmask is reassembled by the library's own exchange over peer memory (P2P stores from the verify kernel's epilogue,
+    # fabgpu_verify_p256_device_keyed_allgather); the NCCL all-gather stays available (--collective nccl) and is timed beside it.
+    peer = None
+    if world > 1 and args.collective == "p2p":
+        peer = sharding.PeerMaskExchange(ctx, n_total, world, rank, dev)
+
+    def step(k, generic=False, nccl=False):
         t = bufs[k % ROT]
+        if peer is not None and not generic and not nccl:
+            return peer.verify(True, kslots[k % ROT].data_ptr(), 0, 0, t[2].data_ptr(), t[3].data_ptr(), t[4].data_ptr(), B, stream.cuda_stream)
         if generic:
             ctx.verify_p256_device(t[0].data_ptr(), t[1].data_ptr(), t[2].data_ptr(), t[3].data_ptr(), t[4].data_ptr(), B,
                                    local_mask.data_ptr(), 0, stream.cuda_stream)
@@ -294,6 +302,21 @@ def run_gpu(args):
     sync_all()
     conc_ms = max(c0.elapsed_time(e) for e in cends)
     assert all(bool((m == -1).all()) for m in cmasks)
+    # the same timed loop with the NCCL all-gather instead of the peer-memory exchange (comparison; N > 1 only)
+    nccl_ms = 0.0
+    if peer is not None:
+        for k in range(args.warmup):
+            full = step(k, nccl=True)
+        nev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        sync_all()
+        for k in range(args.steps):
+            flush.fill_(k & 0xFF)
+            nev[k][0].record(stream)
+            full = step(k, nccl=True)
+            nev[k][1].record(stream)
+        sync_all()
+        nccl_ms = sum(a.elapsed_time(b_) for a, b_ in nev)
+        assert bool((full == -1).all())
     # generic kernel (no key tables), same hygiene, fewer steps
     gsteps = max(3, min(args.steps, 10))
     for k in range(2):
@@ -465,10 +488,10 @@ def run_gpu(args):
 
 
     # ---- max over ranks ---------------------------------------------------------------------------------------
-    times = torch.tensor([dev_ms, e2e_s * 1e3, wall * 1e3, gen_ms, key_register_ms, e2e_sync_s * 1e3, conc_ms, e2e_pageable_s * 1e3], dtype=torch.float64, device=dev)
+    times = torch.tensor([dev_ms, e2e_s * 1e3, wall * 1e3, gen_ms, key_register_ms, e2e_sync_s * 1e3, conc_ms, e2e_pageable_s * 1e3, nccl_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms, wall_ms, gen_ms, key_register_ms, e2e_sync_ms, conc_ms, e2e_pageable_ms = [float(x) for x in times.tolist()]
+    dev_ms, e2e_ms, wall_ms, gen_ms, key_register_ms, e2e_sync_ms, conc_ms, e2e_pageable_ms, nccl_ms = [float(x) for x in times.tolist()]
 
     if rank == 0:
         hbm_peak, peak_src, sm_max = _peaks()
@@ -489,7 +512,10 @@ def run_gpu(args):
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32 limbs (256-bit modular integer)", "data": "synthetic",
             "config": {"workload": workload_string(B),
-                       "batch_per_gpu": B, "global_batch": n_total, "parallelism": "batch split x%d + NCCL all-gather of the bitmask" % world,
+                       "batch_per_gpu": B, "global_batch": n_total,
+                       "parallelism": ("batch split x%d + bitmask exchanged over peer memory (P2P stores from the verify kernel's epilogue, fabgpu_peer_mask_*)" % world) if peer is not None
+                                      else ("batch split x%d + NCCL all-gather of the bitmask" % world),
+                       "value_with_nccl_allgather": (n_total * args.steps / (nccl_ms * 1e-3)) if nccl_ms else None,
                        "timing": "per-step CUDA events on the launch stream, summed; L2 flushed (256 MiB fill) between steps; %d rotating input buffers" % ROT,
                        "wall_ms_incl_flush": wall_ms, "rank0_numa_pinning": numa},
             "e2e": {"value": n_total * e2e_steps / (e2e_ms * 1e-3), "unit": "verifies/s", "h2d_bytes_per_step": e2e_h2d * world, "d2h_bytes_per_step": e2e_d2h * world,
@@ -537,6 +563,9 @@ def run_gpu(args):
         if block_replay:
             block_replay["cpu_port_ms_per_block_est"] = 4 * args.block_txs / cpu_v * 1e3
         emit(out)
+    if peer is not None:
+        sync_all()
+        peer.close()
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
@@ -552,6 +581,7 @@ def main():
     ap.add_argument("--block-txs", type=int, default=10000, help="transactions in the block-replay leg (configs[2])")
     ap.add_argument("--no-block", action="store_true", help="skip the block-replay leg")
     ap.add_argument("--no-parity", action="store_true", help="skip the (untimed) named-shape parity leg")
+    ap.add_argument("--collective", default="p2p", choices=["p2p", "nccl"], help="N > 1: how the bitmask is reassembled in the timed loop")
     args = ap.parse_args()
     # The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version line on the first
     # collective), so everything but the result goes to stderr: fd 1 is pointed at fd 2 for the duration of the run and the

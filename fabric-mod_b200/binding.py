@@ -24,6 +24,7 @@ EXPORTS = [
     "fabgpu_verify_p256_keyed_async", "fabgpu_verify_p256_device_keyed", "fabgpu_last_timing", "fabgpu_build_info",
     "fabgpu_msp_configure", "fabgpu_validate_block", "fabgpu_validate_envelopes", "fabgpu_block_buffer", "fabgpu_block_timing", "fabgpu_sha256_segments",
     "fabgpu_bccsp_verify_batch_async", "fabgpu_bccsp_verify_batch_wait", "fabgpu_bccsp_batch_buffers", "fabgpu_bccsp_verify_batch_inplace_async",
+    "fabgpu_peer_mask_create", "fabgpu_peer_mask_open", "fabgpu_peer_mask_close", "fabgpu_verify_p256_device_keyed_allgather",
     "fabgpu_validate_block_async", "fabgpu_validate_envelopes_async", "fabgpu_validate_wait", "fabgpu_block_buffer_slot",
 ]
 
@@ -192,6 +193,27 @@ class Context:
                                                        ctypes.c_void_p(d_key_slot), ctypes.c_void_p(d_qx), ctypes.c_void_p(d_qy),
                                                        ctypes.c_void_p(d_e), ctypes.c_void_p(d_r), ctypes.c_void_p(d_s), ctypes.c_size_t(n),
                                                        ctypes.c_void_p(d_mask), ctypes.c_void_p(d_off), ctypes.c_void_p(stream)))
+
+    # ---- bitmask exchange over peer memory (one process per GPU) ------------------------------------------
+    def peer_mask_create(self, world, rank, words_per_rank, dev_index=0):
+        h = np.zeros(64, np.uint8)
+        self._ck(lib().fabgpu_peer_mask_create(self._h, ctypes.c_int(dev_index), ctypes.c_int(world), ctypes.c_int(rank), ctypes.c_size_t(words_per_rank), _p(h)))
+        return h
+
+    def peer_mask_open(self, handles, dev_index=0):
+        handles = np.ascontiguousarray(handles, dtype=np.uint8).reshape(-1)
+        self._ck(lib().fabgpu_peer_mask_open(self._h, ctypes.c_int(dev_index), _p(handles)))
+
+    def peer_mask_close(self, dev_index=0):
+        self._ck(lib().fabgpu_peer_mask_close(self._h, ctypes.c_int(dev_index)))
+
+    def verify_p256_device_keyed_allgather(self, all_cached, d_key_slot, d_qx, d_qy, d_e, d_r, d_s, n, step, stream=0, dev_index=0):
+        """Returns the device pointer (int) of the assembled world x words_per_rank mask words of this step."""
+        out = ctypes.c_void_p(0)
+        self._ck(lib().fabgpu_verify_p256_device_keyed_allgather(self._h, ctypes.c_int(dev_index), ctypes.c_int(1 if all_cached else 0), ctypes.c_void_p(d_key_slot),
+                                                                 ctypes.c_void_p(d_qx), ctypes.c_void_p(d_qy), ctypes.c_void_p(d_e), ctypes.c_void_p(d_r),
+                                                                 ctypes.c_void_p(d_s), ctypes.c_size_t(n), ctypes.c_uint32(step), ctypes.byref(out), ctypes.c_void_p(stream)))
+        return int(out.value or 0)
 
     # ---- bccsp level ------------------------------------------------------------------------------------
     @staticmethod

@@ -89,6 +89,10 @@ FAB_HD const aff* ba_operand(bool first, int leaf, const aff* gtab, const aff* q
     return pts + leaf;
 }
 
+#ifndef FAB_BA_PREFETCH
+#define FAB_BA_PREFETCH 0             // 1: request the operands of the next addition before the multiplications of the current one.  Measured on
+#endif                                // B200 (profiles/r2_ba_sweeps.txt): 4 % SLOWER -- the extra live registers spill; the default is off
+#if FAB_BA_PREFETCH
 // Forward pass of one level: pre[k] = d_0 ... d_k with d_k = x(2k+1) - x(2k) (1 where an operand is infinity); returns the product
 // of all n denominators.  exc is set when two finite operands share their x (see the header: cannot happen for reduced scalars).
 // The operands of addition k+1 are loaded before the multiplication of addition k is issued (software pipelining: the table
@@ -168,6 +172,61 @@ FAB_HD uint32_t ba_backward(bool first, bool last, int n, u256 inv, const aff* g
     return outmask;
 }
 
+#else
+FAB_HD u256 ba_forward(bool first, int n, const aff* gtab, const aff* qtab, const uint32_t* dig, int stride, const aff* pts,
+                       uint32_t infmask, u256* pre, uint32_t& exc)
+{
+    u256 c = fe_one();
+    for (int k = 0; k < n; k++) {
+        bool fa, fb;
+        const aff* pa = ba_operand(first, 2 * k, gtab, qtab, dig, stride, pts, infmask, fa);
+        const aff* pb = ba_operand(first, 2 * k + 1, gtab, qtab, dig, stride, pts, infmask, fb);
+        u256 dx = fe_sub(pb->x, pa->x);
+        const bool z = u256_is_zero(dx);
+        if (fa || fb) dx = fe_one();
+        else if (z) { exc = 1u; dx = fe_one(); }
+        c = (k == 0) ? dx : fe_mul(c, dx);
+        pre[k] = c;
+    }
+    return c;
+}
+
+FAB_HD uint32_t ba_backward(bool first, bool last, int n, u256 inv, const aff* gtab, const aff* qtab, const uint32_t* dig, int stride,
+                            const aff* pts, uint32_t infmask, const u256* pre, aff* out, jac& acc)
+{
+    uint32_t outmask = 0;
+    for (int k = n - 1; k >= 0; k--) {
+        bool fa, fb;
+        const aff* pa = ba_operand(first, 2 * k, gtab, qtab, dig, stride, pts, infmask, fa);
+        const aff* pb = ba_operand(first, 2 * k + 1, gtab, qtab, dig, stride, pts, infmask, fb);
+        const aff a = *pa, b = *pb;
+        u256 dx = fe_sub(b.x, a.x);
+        if (fa || fb || u256_is_zero(dx)) dx = fe_one();
+        u256 di;                                            // 1 / d_k
+        if (k > 0) {
+            u256 nx;
+            fe_mul2(inv, pre[k - 1], inv, dx, di, nx);
+            inv = nx;
+        } else di = inv;
+        const u256 lam = fe_mul(fe_sub(b.y, a.y), di);
+        aff s;
+        s.x = fe_sub(fe_sub(fe_sqr(lam), a.x), b.x);
+        s.y = fe_sub(fe_mul(lam, fe_sub(a.x, s.x)), a.y);
+        if (fa) s = b;
+        else if (fb) s = a;
+        const bool finf = fa && fb;
+        if (last) {
+            if (!finf) acc = jac_add_aff(acc, s);
+        } else {
+            out[k] = s;
+            outmask |= (finf ? 1u : 0u) << k;
+        }
+    }
+    return outmask;
+}
+
+#endif
+
 // Montgomery's trick over V values held in a strided array (one lane of the CTA's inverter warp; on the host: one call per
 // group).  modn: values are plain scalars s in [1, n-1] and the results are s^-1 R mod n (the Montgomery form sc_mul wants);
 // otherwise values are field elements a R and the results a^-1 R.  Element j, limb l lives at [j * vstride + l * lstride];
@@ -201,6 +260,19 @@ FAB_HD void ba_inverse_lane(bool modn, uint32_t* val, uint32_t* tmp, int V, int 
     }
 #pragma unroll
     for (int l = 0; l < 8; l++) val[l * lstride] = inv.v[l];
+}
+
+// Montgomery's trick over the TWO values of one thread (ecdsa_verify_ba2_kernel: a thread carries two signatures and shares
+// each inversion between them -- no exchange through shared memory, no barrier).  Same domains as ba_inverse_lane.
+FAB_HD void ba_inverse_pair(bool modn, u256& a, u256& b)
+{
+    const u256 r3p = u256_const(0x0000000au, 0xfffffffdu, 0xfffffff7u, 0xffffffedu, 0xfffffffcu, 0x00000005u, 0x00000001u, 0x00000018u);
+    const u256 c = modn ? sc_mul(a, b) : fe_mul(a, b);
+    u256 inv = inv_safegcd_rt(c, modn ? 0 : 1);
+    inv = modn ? sc_mul(inv, sc_r2()) : fe_mul(inv, r3p);
+    const u256 ia = modn ? sc_mul(inv, b) : fe_mul(inv, b);
+    const u256 ib = modn ? sc_mul(inv, a) : fe_mul(inv, a);
+    a = ia; b = ib;
 }
 
 // r, s in [1, n-1] (Go: r.Sign() <= 0 || s.Sign() <= 0 -> false; r >= N || s >= N -> false)

@@ -194,6 +194,66 @@ ecdsa_verify_lanes_kernel(const int32_t* __restrict__ key_slot, const uint8_t* _
     }
 }
 
+// ---- validity-bitmask exchange over peer memory (one process per GPU) -----------------------------------
+// Every rank owns a receive buffer (cudaMalloc'ed, exported through CUDA IPC, mapped by all peers): `gens` generations of
+// world x words_per_rank mask words, then world step flags.  The verify kernel's epilogue stores each warp's ballot word into
+// the buffer of EVERY rank (plain st.global on peer-mapped addresses: P2P writes over NVLink / NVSwitch); the last CTA to finish
+// publishes the step number into every rank's flag array; peer_wait_kernel (same stream) then spins until the flags of all ranks
+// have reached the step, i.e. until the whole bitmask has landed locally.  No NCCL call on the data path.
+#define FAB_PEER_MAX 8
+struct PeerOut {
+    uint32_t* buf[FAB_PEER_MAX];   // every rank's receive buffer as mapped in THIS process (buf[rank] is the local one)
+    uint32_t* done;                // local counter of finished CTAs (device memory, zero between launches)
+    uint32_t world, rank;
+    uint32_t words_per_rank;       // mask words each rank contributes
+    uint32_t gen_off;              // word offset of this step's generation inside a buffer
+    uint32_t flag_off;             // word offset of the flag array inside a buffer
+    uint32_t step;                 // published when this rank's words are all written
+};
+
+__device__ __forceinline__ void peer_store_word(const PeerOut& po, uint32_t word_index, uint32_t v)
+{
+    const uint32_t at = po.gen_off + po.rank * po.words_per_rank + word_index;
+    for (uint32_t p = 0; p < po.world; p++) po.buf[p][at] = v;
+}
+
+// Called by every thread of a CTA after its mask words are stored: the last CTA of the grid publishes the step.
+__device__ __forceinline__ void peer_publish(const PeerOut& po)
+{
+    __threadfence_system();                               // this thread's peer stores are ordered before the counter update
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t prev = atomicAdd(po.done, 1u);
+        if (prev == gridDim.x - 1) {
+            *po.done = 0u;                                // ready for the next launch (stream order)
+            __threadfence_system();
+            for (uint32_t p = 0; p < po.world; p++) *reinterpret_cast<volatile uint32_t*>(po.buf[p] + po.flag_off + po.rank) = po.step;
+        }
+    }
+}
+
+// Waits (on the stream) until every rank has published `step`; gives up after ~2 s and records that in *timeout_flag so a
+// dead peer can never hang the GPU (the host reads the flag and reports a device error: the caller falls back).
+__global__ void peer_wait_kernel(const uint32_t* flags, uint32_t world, uint32_t step, uint32_t* timeout_flag)
+{
+    const uint32_t p = threadIdx.x;
+    if (p >= world) return;
+    const long long t0 = clock64();
+    while ((int32_t)(*reinterpret_cast<const volatile uint32_t*>(flags + p) - step) < 0) {
+        if (clock64() - t0 > 4000000000ll) { *timeout_flag = 1u; break; }
+        __nanosleep(200);
+    }
+}
+
+// Fallback for launches whose mask was produced by several kernels (mixed key-table / generic batches): copy the finished local
+// words to every peer, then publish.
+__global__ void peer_scatter_kernel(const uint32_t* __restrict__ local_words, uint32_t n_words, PeerOut po)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_words) peer_store_word(po, i, local_words[i]);
+    peer_publish(po);
+}
+
 // ---- batch-affine key-table kernel (ecdsa_batchaffine.cuh) ----
 #ifndef FAB_BA_THREADS
 #define FAB_BA_THREADS 256            // signatures (= threads) per CTA; the shared inversion is amortised over this many
@@ -251,7 +311,7 @@ __device__ __noinline__ uint32_t ba_fallback_verify(const aff* qtab, const uint8
 __global__ void __launch_bounds__(FAB_BA_THREADS, FAB_BA_MINBLOCKS)
 ecdsa_verify_ba_kernel(const int32_t* __restrict__ key_slot, const uint8_t* __restrict__ e, const uint8_t* __restrict__ r,
                        const uint8_t* __restrict__ s, uint32_t n, const aff* __restrict__ gtab, const aff* __restrict__ qtab,
-                       uint32_t* __restrict__ mask, uint32_t* __restrict__ offcurve, const uint32_t* __restrict__ n_dev, uint32_t n_base)
+                       uint32_t* __restrict__ mask, uint32_t* __restrict__ offcurve, const uint32_t* __restrict__ n_dev, uint32_t n_base, PeerOut po)
 {
     constexpr int T = FAB_BA_THREADS;
     __shared__ uint32_t dig[FAB_BA_NP * T];
@@ -301,6 +361,101 @@ ecdsa_verify_ba_kernel(const int32_t* __restrict__ key_slot, const uint8_t* __re
     if ((threadIdx.x & 31u) == 0 && idx < n) {
         mask[idx >> 5] = vmask;
         if (offcurve) offcurve[idx >> 5] = 0u;
+        if (po.world) peer_store_word(po, idx >> 5, vmask);      // fused epilogue: the ballot word goes to every rank's buffer
+    }
+    if (po.world) peer_publish(po);
+}
+
+// ---- batch-affine, two signatures per thread, no CTA exchange (large batches) ------------------------------------------------
+// The CTA-shared inversion of ecdsa_verify_ba_kernel costs three barrier rounds during which seven of eight warps wait for the
+// inverter warp (ncu: 36 % of all warp time at 256k, profiles/r2_ba_*).  Here a thread carries TWO signatures -- CTA-local
+// indices t and t + T -- and runs Montgomery's trick over its own pair: half an inversion per signature and round, no shared
+// state, no barrier; warps drift freely, so the scheduler always has independent work.  Half as many threads per batch: the
+// launch code uses this kernel only when the batch still fills the machine (see launch_verify).
+#ifndef FAB_BA2_THREADS
+#define FAB_BA2_THREADS 128
+#endif
+#ifndef FAB_BA2_MINBLOCKS
+#define FAB_BA2_MINBLOCKS 4
+#endif
+__device__ __noinline__ void ba2_inverse_pair(bool modn, u256& a, u256& b) { ba_inverse_pair(modn, a, b); }
+// Out-of-line passes: the kernel body unrolls its two signatures (so that their state stays in registers) without holding two
+// copies of the loops.
+__device__ __noinline__ u256 ba2_forward(bool first, const aff* gtab, const aff* qt, const uint32_t* dig, BaScratch* sc, uint32_t m1, uint32_t* exc)
+{
+    uint32_t x = *exc;
+    const u256 c = ba_forward(first, first ? FAB_BA_N1 : FAB_BA_N2, gtab, qt, dig, FAB_BA2_THREADS, sc->pts, m1, sc->pre, x);
+    *exc = x;
+    return c;
+}
+// level 1: returns the infinity flags of its results; level 2: returns the verdict of the signature
+__device__ __noinline__ uint32_t ba2_backward(bool first, const u256& inv, const aff* gtab, const aff* qt, const uint32_t* dig, BaScratch* sc, uint32_t m1,
+                                              const uint8_t* r32)
+{
+    jac acc = jac_infinity();
+    const uint32_t m = ba_backward(first, !first, first ? FAB_BA_N1 : FAB_BA_N2, inv, gtab, qt, dig, FAB_BA2_THREADS, sc->pts, m1, sc->pre, sc->pts, acc);
+    if (first) return m;
+    return final_check(acc, load_be32(r32));
+}
+
+__global__ void __launch_bounds__(FAB_BA2_THREADS, FAB_BA2_MINBLOCKS)
+ecdsa_verify_ba2_kernel(const int32_t* __restrict__ key_slot, const uint8_t* __restrict__ e, const uint8_t* __restrict__ r,
+                        const uint8_t* __restrict__ s, uint32_t n, const aff* __restrict__ gtab, const aff* __restrict__ qtab,
+                        uint32_t* __restrict__ mask, uint32_t* __restrict__ offcurve)
+{
+    constexpr int T = FAB_BA2_THREADS;
+    __shared__ uint32_t dig[2 * FAB_BA_NP * T];
+    const uint32_t base = blockIdx.x * (2 * T) + threadIdx.x;       // signatures base and base + T
+    bool ok[2] = {false, false};
+    const aff* qt[2] = {qtab, qtab};
+    u256 v[2];
+    v[0] = v[1] = u256_const(1, 0, 0, 0, 0, 0, 0, 0);
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const uint32_t idx = base + h * T;
+        if (idx < n) {
+            const int32_t slot = key_slot[idx];
+            if (slot >= 0) {
+                qt[h] = qtab + (size_t)slot * (FAB_Q_WINDOWS * FAB_Q_ENTRIES);
+                const u256 sv = load_be32(s + (size_t)idx * 32);
+                ok[h] = ba_range_ok(load_be32(r + (size_t)idx * 32), sv);
+                if (ok[h]) v[h] = sv;
+            }
+        }
+    }
+    ba2_inverse_pair(true, v[0], v[1]);                              // w = s^-1 R mod n for both
+    BaScratch sc[2];
+    uint32_t exc[2] = {0, 0}, m1[2] = {0, 0};
+    uint32_t res[2] = {V_INVALID, V_INVALID};
+#pragma unroll
+    for (int h = 0; h < 2; h++)
+        if (ok[h]) ba_scalars(load_be32(e + (size_t)(base + h * T) * 32), load_be32(r + (size_t)(base + h * T) * 32), v[h], dig + h * FAB_BA_NP * T + threadIdx.x, T);
+#pragma unroll 1
+    for (int level = 0; level < 2; level++) {
+        const bool first = level == 0;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            v[h] = fe_one();
+            if (ok[h]) v[h] = ba2_forward(first, gtab, qt[h], dig + h * FAB_BA_NP * T + threadIdx.x, &sc[h], m1[h], &exc[h]);
+        }
+        ba2_inverse_pair(false, v[0], v[1]);
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            if (!ok[h]) continue;
+            const size_t o = (size_t)(base + h * T) * 32;
+            const uint32_t m = ba2_backward(first, v[h], gtab, qt[h], dig + h * FAB_BA_NP * T + threadIdx.x, &sc[h], m1[h], r + o);
+            if (first) m1[h] = m;
+            else res[h] = exc[h] ? ba_fallback_verify(qt[h], e + o, r + o, s + o, gtab) : m;
+        }
+    }
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const uint32_t idx = base + h * T;
+        const uint32_t vmask = __ballot_sync(0xffffffffu, res[h] == V_VALID);
+        if ((threadIdx.x & 31u) == 0 && idx < n) {
+            mask[idx >> 5] = vmask;
+            if (offcurve) offcurve[idx >> 5] = 0u;
+        }
     }
 }
 

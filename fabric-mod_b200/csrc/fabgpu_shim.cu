@@ -50,6 +50,12 @@ struct Device {
     int sms = 148;            // multiprocessors (launch shapes)
     aff* qtab = nullptr;      // key_slots tables of FAB_G_WINDOWS * FAB_G_ENTRIES points (per-key fixed-base tables)
     DevSlot slot[FABGPU_SLOTS];
+    // bitmask exchange over peer memory (fabgpu_peer_mask_*): this rank's receive buffer, the peers' mapped ones
+    struct Peer {
+        uint32_t* local = nullptr; uint32_t* mapped[FAB_PEER_MAX] = {nullptr}; bool opened[FAB_PEER_MAX] = {false};
+        uint32_t* done = nullptr; uint32_t* timeout = nullptr; uint32_t* h_timeout = nullptr;
+        int world = 0, rank = 0; size_t words_per_rank = 0; bool ready = false;
+    } peer;
 };
 
 struct HostSlot {
@@ -267,10 +273,16 @@ enum { MODE_GENERIC = 0, MODE_CACHED = 1, MODE_MIXED = 2 };
 // n_dev / n_base (block path): the batch is [0, min(n, n_base + *n_dev)) with *n_dev written by an earlier kernel of the stream.
 int launch_verify(fabgpu_ctx* ctx, const Device& dv, int mode, const int32_t* key_slot, const uint8_t* qx, const uint8_t* qy,
                   const uint8_t* e, const uint8_t* r, const uint8_t* s, size_t n, uint32_t* mask, uint32_t* off, cudaStream_t st,
-                  const uint32_t* n_dev = nullptr, uint32_t n_base = 0)
+                  const uint32_t* n_dev = nullptr, uint32_t n_base = 0, const PeerOut* peer = nullptr)
 {
-    if (n == 0) return FABGPU_OK;
-    if (mode != MODE_GENERIC) {
+    PeerOut po; memset(&po, 0, sizeof po);
+    const bool fused_peer = peer && mode == MODE_CACHED && (ctx->cached_kernel == 1 || ctx->cached_kernel == 3) && n > 0;
+    if (fused_peer) po = *peer;
+    if (peer && !fused_peer) {                            // several kernels write the mask: scatter it afterwards (below)
+        if (n_dev) { ctx->last_error = "peer exchange needs a host-known batch size"; return FABGPU_E_ARG; }
+    }
+    if (n == 0 && !peer) return FABGPU_OK;
+    if (mode != MODE_GENERIC && n > 0) {
         // CTA shape (the kernel allows up to FAB_CACHED_THREADS = 512 threads at 128 registers, i.e. one such CTA per SM).
         // Measured on B200 (profiles/r1_kbench_table_widths.txt): a batch that fits one wave of 512-thread CTAs (64k: 128 CTAs)
         // finishes in 0.315 ms against 0.346 ms as 512 CTAs of 128 threads; beyond one wave 256-thread CTAs quantise best
@@ -283,10 +295,14 @@ int launch_verify(fabgpu_ctx* ctx, const Device& dv, int mode, const int32_t* ke
             if (n_dev) { ctx->last_error = "the lane-split kernel has no device-side batch size"; return FABGPU_E_ARG; }
             if (ctx->cached_kernel == 2) ecdsa_verify_lanes_kernel<2><<<blocks, FAB_LANES_THREADS, 0, st>>>(key_slot, e, r, s, nn, dv.gtab, dv.qtab, mask, off);
             else ecdsa_verify_lanes_kernel<4><<<blocks, FAB_LANES_THREADS, 0, st>>>(key_slot, e, r, s, nn, dv.gtab, dv.qtab, mask, off);
-        } else if (ctx->cached_kernel == 1) {
+        } else if (ctx->cached_kernel == 3 && !n_dev && !fused_peer) {
+            // batch-affine, two signatures per thread, no CTA exchange
+            const unsigned per = 2 * FAB_BA2_THREADS, blocks = (unsigned)((n + per - 1) / per);
+            ecdsa_verify_ba2_kernel<<<blocks, FAB_BA2_THREADS, 0, st>>>(key_slot, e, r, s, (uint32_t)n, dv.gtab, dv.qtab, mask, off);
+        } else if (ctx->cached_kernel == 1 || ctx->cached_kernel == 3) {
             // batch-affine accumulation with CTA-shared inversions (ecdsa_batchaffine.cuh): fixed CTA width
             const unsigned blocks = (unsigned)((n + FAB_BA_THREADS - 1) / FAB_BA_THREADS);
-            ecdsa_verify_ba_kernel<<<blocks, FAB_BA_THREADS, 0, st>>>(key_slot, e, r, s, (uint32_t)n, dv.gtab, dv.qtab, mask, off, n_dev, n_base);
+            ecdsa_verify_ba_kernel<<<blocks, FAB_BA_THREADS, 0, st>>>(key_slot, e, r, s, (uint32_t)n, dv.gtab, dv.qtab, mask, off, n_dev, n_base, po);
         } else {
         unsigned threads = 128;
         const size_t sms = (size_t)dv.sms;
@@ -297,7 +313,7 @@ int launch_verify(fabgpu_ctx* ctx, const Device& dv, int mode, const int32_t* ke
         ctx->launches++;
         CK(ctx, cudaGetLastError());
     }
-    if (mode != MODE_CACHED) {
+    if (mode != MODE_CACHED && n > 0) {
         // same reasoning for the generic kernel (measured: 64k as 147 CTAs of 448 threads 24.1 M/s, as 1024 CTAs of 64 threads 22.6;
         // 256k as CTAs of 256 threads 27.6 M/s, of 448 threads 24.3)
         unsigned gthreads = 64;
@@ -305,6 +321,12 @@ int launch_verify(fabgpu_ctx* ctx, const Device& dv, int mode, const int32_t* ke
         const unsigned blocks = (unsigned)((n + gthreads - 1) / gthreads);
         ecdsa_verify_kernel<<<blocks, gthreads, 0, st>>>(mode == MODE_MIXED ? key_slot : nullptr, qx, qy, e, r, s, (uint32_t)n,
                                                                    dv.gtab, mask, off, n_dev, n_base);
+        ctx->launches++;
+        CK(ctx, cudaGetLastError());
+    }
+    if (peer && !fused_peer) {
+        const uint32_t words = (uint32_t)((n + 31) / 32);
+        peer_scatter_kernel<<<words ? (words + 127) / 128 : 1, 128, 0, st>>>(mask, words, *peer);
         ctx->launches++;
         CK(ctx, cudaGetLastError());
     }
@@ -458,7 +480,7 @@ int init_impl(fabgpu_ctx* ctx, const int* device_ids, int n_dev, size_t max_batc
         const char* mu = getenv("FABGPU_KEY_MIN_USES");
         ctx->key_min_uses = mu ? atoi(mu) : 256;           // a table costs about 300 generic verifications to build
         const char* ck = getenv("FABGPU_CACHED_KERNEL");
-        if (ck) ctx->cached_kernel = (ck[0] == 'j' || ck[0] == '0') ? 0 : (ck[0] == 'l' ? (ck[1] == '4' ? 4 : 2) : 1);   // "jac" / "0": the Jacobian-chain kernel; "l2" / "l4": its lane-split variant
+        if (ck) ctx->cached_kernel = (ck[0] == 'j' || ck[0] == '0') ? 0 : (ck[0] == 'l' ? (ck[1] == '4' ? 4 : 2) : (ck[0] == 'b' && ck[1] == 'a' && ck[2] == '2' ? 3 : 1));   // "jac" / "0": the Jacobian-chain kernel; "l2" / "l4": its lane-split variant
     }
     ctx->dev_cap = round_up32((max_batch + ids.size() - 1) / ids.size());
     ctx->devs.resize(ids.size());
@@ -768,6 +790,106 @@ int fabgpu_verify_p256_device_keyed(fabgpu_ctx* ctx, int dev_index, int all_cach
     return launch_verify(ctx, dv, all_cached ? MODE_CACHED : MODE_MIXED, (const int32_t*)d_key_slot, (const uint8_t*)d_qx,
                          (const uint8_t*)d_qy, (const uint8_t*)d_e, (const uint8_t*)d_r, (const uint8_t*)d_s, n, (uint32_t*)d_mask,
                          (uint32_t*)d_offcurve, (cudaStream_t)cuda_stream);
+}
+
+// ---- bitmask exchange over peer memory -------------------------------------------------------------------------------------
+static const int kPeerGens = 2;
+static size_t peer_buf_words(int world, size_t wpr) { return (size_t)kPeerGens * world * wpr + FAB_PEER_MAX; }
+
+int fabgpu_peer_mask_create(fabgpu_ctx* ctx, int dev_index, int world, int rank, size_t words_per_rank, uint8_t handle_out[FABGPU_IPC_HANDLE_BYTES])
+{
+    if (!ctx || dev_index < 0 || dev_index >= (int)ctx->devs.size() || world < 1 || world > FAB_PEER_MAX || rank < 0 || rank >= world || !words_per_rank || !handle_out)
+        return FABGPU_E_ARG;
+    static_assert(sizeof(cudaIpcMemHandle_t) <= FABGPU_IPC_HANDLE_BYTES, "IPC handle size");
+    Device& dv = ctx->devs[dev_index];
+    auto& pr = dv.peer;
+    if (pr.local) { ctx->last_error = "peer mask already created on this device"; return FABGPU_E_ARG; }
+    CK(ctx, cudaSetDevice(dv.id));
+    const size_t bytes = 4 * peer_buf_words(world, words_per_rank);
+    CK(ctx, cudaMalloc(&pr.local, bytes));
+    CK(ctx, cudaMemset(pr.local, 0, bytes));
+    CK(ctx, cudaMalloc(&pr.done, 8));
+    CK(ctx, cudaMemset(pr.done, 0, 8));
+    pr.timeout = pr.done + 1;
+    CK(ctx, cudaHostAlloc(&pr.h_timeout, 4, cudaHostAllocPortable));
+    *pr.h_timeout = 0;
+    cudaIpcMemHandle_t h;
+    CK(ctx, cudaIpcGetMemHandle(&h, pr.local));
+    memset(handle_out, 0, FABGPU_IPC_HANDLE_BYTES);
+    memcpy(handle_out, &h, sizeof h);
+    pr.world = world; pr.rank = rank; pr.words_per_rank = words_per_rank;
+    for (int p = 0; p < FAB_PEER_MAX; p++) { pr.mapped[p] = nullptr; pr.opened[p] = false; }
+    pr.mapped[rank] = pr.local;
+    pr.ready = world == 1;
+    return FABGPU_OK;
+}
+
+int fabgpu_peer_mask_open(fabgpu_ctx* ctx, int dev_index, const uint8_t* handles)
+{
+    if (!ctx || dev_index < 0 || dev_index >= (int)ctx->devs.size() || !handles) return FABGPU_E_ARG;
+    Device& dv = ctx->devs[dev_index];
+    auto& pr = dv.peer;
+    if (!pr.local) { ctx->last_error = "fabgpu_peer_mask_create first"; return FABGPU_E_ARG; }
+    CK(ctx, cudaSetDevice(dv.id));
+    for (int p = 0; p < pr.world; p++) {
+        if (p == pr.rank || pr.opened[p]) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handles + (size_t)p * FABGPU_IPC_HANDLE_BYTES, sizeof h);
+        void* m = nullptr;
+        CK(ctx, cudaIpcOpenMemHandle(&m, h, cudaIpcMemLazyEnablePeerAccess));
+        pr.mapped[p] = (uint32_t*)m; pr.opened[p] = true;
+    }
+    pr.ready = true;
+    return FABGPU_OK;
+}
+
+int fabgpu_peer_mask_close(fabgpu_ctx* ctx, int dev_index)
+{
+    if (!ctx || dev_index < 0 || dev_index >= (int)ctx->devs.size()) return FABGPU_E_ARG;
+    Device& dv = ctx->devs[dev_index];
+    auto& pr = dv.peer;
+    cudaSetDevice(dv.id);
+    cudaDeviceSynchronize();
+    for (int p = 0; p < FAB_PEER_MAX; p++) if (pr.opened[p]) { cudaIpcCloseMemHandle(pr.mapped[p]); pr.opened[p] = false; pr.mapped[p] = nullptr; }
+    if (pr.local) cudaFree(pr.local);
+    if (pr.done) cudaFree(pr.done);
+    if (pr.h_timeout) cudaFreeHost(pr.h_timeout);
+    pr = Device::Peer();
+    return FABGPU_OK;
+}
+
+int fabgpu_verify_p256_device_keyed_allgather(fabgpu_ctx* ctx, int dev_index, int all_cached, const void* d_key_slot, const void* d_qx,
+                                              const void* d_qy, const void* d_e, const void* d_r, const void* d_s, size_t n, uint32_t step,
+                                              void** d_full_mask, void* cuda_stream)
+{
+    if (!ctx || dev_index < 0 || dev_index >= (int)ctx->devs.size() || !d_full_mask || step == 0) return FABGPU_E_ARG;
+    if (n && (!d_key_slot || !d_e || !d_r || !d_s)) return FABGPU_E_ARG;
+    if (n && !all_cached && (!d_qx || !d_qy)) return FABGPU_E_ARG;
+    Device& dv = ctx->devs[dev_index];
+    auto& pr = dv.peer;
+    if (!pr.ready) { ctx->last_error = "peer masks are not set up (fabgpu_peer_mask_create / _open)"; return FABGPU_E_ARG; }
+    if ((n + 31) / 32 > pr.words_per_rank) { ctx->last_error = "batch exceeds words_per_rank"; return FABGPU_E_ARG; }
+    if (fault_injected()) { ctx->last_error = "fault injected (FABGPU_FAULT_INJECT=1)"; return FABGPU_E_INJECTED; }
+    if (*pr.h_timeout) { ctx->last_error = "a peer did not publish its bitmask in time"; return FABGPU_E_CUDA; }
+    CK(ctx, cudaSetDevice(dv.id));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    PeerOut po; memset(&po, 0, sizeof po);
+    for (int p = 0; p < pr.world; p++) po.buf[p] = pr.mapped[p];
+    po.done = pr.done; po.world = (uint32_t)pr.world; po.rank = (uint32_t)pr.rank; po.words_per_rank = (uint32_t)pr.words_per_rank;
+    po.gen_off = (uint32_t)((step % kPeerGens) * pr.world * pr.words_per_rank);
+    po.flag_off = (uint32_t)((size_t)kPeerGens * pr.world * pr.words_per_rank);
+    po.step = step;
+    // the rank's own words also land in its local segment (buf[rank] is the local buffer): `mask` for the kernels is that segment
+    uint32_t* local_seg = pr.local + po.gen_off + (size_t)pr.rank * pr.words_per_rank;
+    int rc = launch_verify(ctx, dv, all_cached ? MODE_CACHED : MODE_MIXED, (const int32_t*)d_key_slot, (const uint8_t*)d_qx, (const uint8_t*)d_qy,
+                           (const uint8_t*)d_e, (const uint8_t*)d_r, (const uint8_t*)d_s, n, local_seg, nullptr, st, nullptr, 0, &po);
+    if (rc) return rc;
+    peer_wait_kernel<<<1, 32, 0, st>>>(pr.local + po.flag_off, po.world, step, pr.timeout);
+    ctx->launches++;
+    CK(ctx, cudaGetLastError());
+    CK(ctx, cudaMemcpyAsync(pr.h_timeout, pr.timeout, 4, cudaMemcpyDeviceToHost, st));
+    *d_full_mask = pr.local + po.gen_off;
+    return FABGPU_OK;
 }
 
 int fabgpu_gate_signature(const uint8_t* sig, size_t sig_len, uint8_t r_out[32], uint8_t s_out[32])

@@ -118,6 +118,30 @@ int fabgpu_verify_p256_device_keyed(fabgpu_ctx* ctx, int dev_index, int all_cach
                                     const void* d_qy, const void* d_e, const void* d_r, const void* d_s, size_t n,
                                     void* d_mask, void* d_offcurve, void* cuda_stream);
 
+/* ---- validity bitmask across GPUs driven by separate processes (one process per GPU) ----------------
+ * The reference has no counterpart (its verifier is per-signature, bccsp/sw/ecdsa.go:41-57); BASELINE.json's north_star asks for
+ * the batch to be split across the GPUs of a box and the bitmask to be reassembled.  The consumer of the bitmask is the HOST
+ * (the Go provider reads it from pinned memory), so the single-process form (one context, several devices: fabgpu_verify_p256*)
+ * needs no device-to-device collective at all.  For the one-process-per-GPU form the library exchanges the mask words itself,
+ * over peer memory: every rank creates a receive buffer and exports it (CUDA IPC), maps the others', and the verify kernel's
+ * epilogue stores each ballot word into the buffer of every rank (P2P writes over NVLink / NVSwitch), followed by a step flag;
+ * a wait kernel on the same stream returns when all ranks' words of that step have landed.  No NCCL call on the data path
+ * (fabric-mod_b200/sharding.py keeps the NCCL all-gather as the alternative).
+ *   _create: this rank's buffer for `world` ranks x words_per_rank mask words; writes its IPC handle (FABGPU_IPC_HANDLE_BYTES).
+ *   _open:   handles = world x FABGPU_IPC_HANDLE_BYTES bytes, rank-major (the caller exchanges them, e.g. over its process group).
+ *   _allgather: fabgpu_verify_p256_device_keyed for this rank's n signatures (n <= 32 x words_per_rank), then the exchange;
+ *            `step` must be 1, 2, 3, ... in lock step on all ranks; *d_full_mask = device pointer to world x words_per_rank
+ *            words, valid once the stream has run (until step + 2 is launched: two generations).  A peer that never publishes
+ *            makes the NEXT call fail with FABGPU_E_CUDA instead of hanging the GPU. */
+#define FABGPU_IPC_HANDLE_BYTES 64
+int fabgpu_peer_mask_create(fabgpu_ctx* ctx, int dev_index, int world, int rank, size_t words_per_rank,
+                            uint8_t handle_out[FABGPU_IPC_HANDLE_BYTES]);
+int fabgpu_peer_mask_open(fabgpu_ctx* ctx, int dev_index, const uint8_t* handles);
+int fabgpu_peer_mask_close(fabgpu_ctx* ctx, int dev_index);
+int fabgpu_verify_p256_device_keyed_allgather(fabgpu_ctx* ctx, int dev_index, int all_cached, const void* d_key_slot,
+                                              const void* d_qx, const void* d_qy, const void* d_e, const void* d_r,
+                                              const void* d_s, size_t n, uint32_t step, void** d_full_mask, void* cuda_stream);
+
 /* ---- bccsp level: raw DER signatures + digests + keys -> three-valued status (sw.CSP.Verify semantics) -- */
 
 /* keys_xy: K x 64 bytes (X || Y, big-endian).  key_idx[i] in [0,K), or < 0 for a nil key.  digests / sigs are

@@ -67,3 +67,39 @@ def test_world2_allgather_matches_single_process(tmp_path):
         got = np.load(os.path.join(str(tmp_path), "mask_%d.npy" % r))
         assert got.shape == exp.shape and (got == exp).all()
     assert 300 < int(n - np.unpackbits(exp.view(np.uint8)).sum()) < 700
+
+
+def _parity_worker(rank, world, port, n_total, keys, out_dir):
+    """The bench's named-shape parity leg with the oracle standing in for the GPU: shard -> statuses -> mask words -> all-gather."""
+    from tools import parity_workload as pw
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sh = pw.Shard(rank, world, n_total, keys, nthreads=2)
+    st = pw.oracle_status(sh, 2)
+    words = sharding.shard_words(n_total, world)
+    local = np.zeros(words, np.uint32)
+    m = fast.valid_mask(st)
+    local[: m.shape[0]] = m
+    full = sharding.allgather_mask(torch.from_numpy(local.view(np.int32)), n_total, world)
+    st_all = torch.empty(n_total, dtype=torch.uint8)
+    dist.all_gather_into_tensor(st_all, torch.from_numpy(st))
+    if rank == 0:
+        np.save(os.path.join(out_dir, "pmask.npy"), full.numpy().view(np.uint32))
+        np.save(os.path.join(out_dir, "pstatus.npy"), st_all.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_world2_named_shape_parity_plumbing(tmp_path):
+    from tools import parity_workload as pw
+    n_total, keys, world = 4096, 8, 2
+    port = _free_port()
+    mp.spawn(_parity_worker, args=(world, port, n_total, keys, str(tmp_path)), nprocs=world, join=True)
+    exp = np.concatenate([pw.oracle_status(pw.Shard(r, world, n_total, keys, nthreads=2), 2) for r in range(world)])
+    got_mask = np.load(os.path.join(str(tmp_path), "pmask.npy"))
+    got_st = np.load(os.path.join(str(tmp_path), "pstatus.npy"))
+    assert (got_st == exp).all() and (got_mask == fast.valid_mask(exp)).all()
+    last = pw.Shard(world - 1, world, n_total, keys, nthreads=2)
+    assert len(last.tail) > 30 and len(set(int(x) for x in exp)) >= 6          # the adversarial tail brought several error kinds
+    assert 100 < int((exp != 0).sum()) < 400
