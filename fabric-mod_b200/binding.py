@@ -24,6 +24,7 @@ EXPORTS = [
     "fabgpu_verify_p256_keyed_async", "fabgpu_verify_p256_device_keyed", "fabgpu_last_timing", "fabgpu_build_info",
     "fabgpu_msp_configure", "fabgpu_validate_block", "fabgpu_validate_envelopes", "fabgpu_block_buffer", "fabgpu_block_timing", "fabgpu_sha256_segments",
     "fabgpu_bccsp_verify_batch_async", "fabgpu_bccsp_verify_batch_wait", "fabgpu_bccsp_batch_buffers", "fabgpu_bccsp_verify_batch_inplace_async",
+    "fabgpu_msp_identity_groups", "fabgpu_namespace_policies",
     "fabgpu_peer_mask_create", "fabgpu_peer_mask_open", "fabgpu_peer_mask_close", "fabgpu_verify_p256_device_keyed_allgather",
     "fabgpu_validate_block_async", "fabgpu_validate_envelopes_async", "fabgpu_validate_wait", "fabgpu_block_buffer_slot",
 ]
@@ -68,6 +69,47 @@ def lib():
 
 def _p(a):
     return a.ctypes.data_as(ctypes.c_void_p) if a is not None else None
+
+
+def identity_groups(identities):
+    """De-duplication groups for fabgpu_msp_identity_groups: identities = [(serialized SerializedIdentity bytes, mspid, ...)].  Two table
+    entries get the same group id when they are the same certificate of the same MSP in byte-different encodings -- the reference's
+    policy evaluation de-duplicates signers on Mspid + Id with Id = digest of the certificate's DER (common/policies/policy.go:380-386,
+    msp/identities.go:55-76), not on the serialized bytes.  Entries whose PEM does not parse are their own group."""
+    import base64
+    import hashlib
+    import re
+
+    def id_bytes(ser):
+        off, out = 0, b""
+        while off < len(ser):                                   # SerializedIdentity{mspid = 1, id_bytes = 2}
+            key = ser[off]; off += 1
+            if key & 7 != 2:
+                return None
+            ln, shift = 0, 0
+            while True:
+                c = ser[off]; off += 1
+                ln |= (c & 0x7F) << shift
+                shift += 7
+                if not c & 0x80:
+                    break
+            if key >> 3 == 2:
+                out = ser[off:off + ln]
+            off += ln
+        return out
+
+    keys, groups = {}, np.zeros(len(identities), np.int32)
+    for i, it in enumerate(identities):
+        ser, mspid = bytes(it[0]), it[1]
+        k = (mspid, ser)
+        try:
+            m = re.search(rb"-----BEGIN CERTIFICATE-----(.*?)-----END CERTIFICATE-----", id_bytes(ser) or b"", re.S)
+            if m:
+                k = (mspid, hashlib.sha256(base64.b64decode(b"".join(m.group(1).split()))).digest())
+        except Exception:
+            pass
+        groups[i] = keys.setdefault(k, len(keys))
+    return groups
 
 
 def build_info():
@@ -290,8 +332,10 @@ class Context:
         return bool(valid.value), (e if e else None)
 
     # ---- block level ------------------------------------------------------------------------------------
-    def msp_configure(self, identities, policy_nodes, principals, channel):
-        """identities: list of (serialized: bytes, mspid: str, key_xy: 64 bytes, valid: bool)."""
+    def msp_configure(self, identities, policy_nodes, principals, channel, policies=None):
+        """identities: list of (serialized: bytes, mspid: str, key_xy: 64 bytes, valid: bool).  policy_nodes may hold several policy
+        trees; policies = {namespace: root node index} names the tree of each chaincode namespace (None: node 0 for every namespace).
+        The identities' de-duplication groups (Mspid + certificate, identity_groups) are installed as well."""
         def blob(items):
             off = np.zeros(len(items) + 1, np.uint32)
             off[1:] = np.cumsum([len(x) for x in items])
@@ -306,6 +350,13 @@ class Context:
         self._ck(lib().fabgpu_msp_configure(self._h, _p(idb), _p(ido), _p(mb), _p(mo), _p(keys), _p(valid), ctypes.c_int(len(identities)),
                                             _p(nodes), ctypes.c_int(nodes.shape[0]), _p(pbb), _p(pbo), ctypes.c_int(len(principals)),
                                             ctypes.c_char_p(channel.encode())))
+        if identities:
+            groups = np.ascontiguousarray(identity_groups(identities), np.int32)
+            self._ck(lib().fabgpu_msp_identity_groups(self._h, _p(groups), ctypes.c_int(len(identities))))
+        names = sorted(policies) if policies else []
+        nb, no = blob([n.encode() for n in names])
+        roots = np.array([policies[n] for n in names] or [0], np.int32)
+        self._ck(lib().fabgpu_namespace_policies(self._h, _p(nb), _p(no), _p(roots), ctypes.c_int(len(names))))
 
     def block_buffer(self, nbytes, slot=0):
         """Pinned staging buffer (numpy view) for block bytes; one per slot."""

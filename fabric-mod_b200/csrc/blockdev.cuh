@@ -25,10 +25,14 @@ namespace fabgpu { namespace bdev {
 enum : uint8_t {
     TXC_VALID = 0, TXC_BAD_PAYLOAD = 2, TXC_BAD_COMMON_HEADER = 3, TXC_BAD_CREATOR_SIGNATURE = 4, TXC_INVALID_ENDORSER_TRANSACTION = 5,
     TXC_UNSUPPORTED_TX_PAYLOAD = 7, TXC_BAD_PROPOSAL_TXID = 8, TXC_DUPLICATE_TXID = 9, TXC_ENDORSEMENT_POLICY_FAILURE = 10,
-    TXC_TARGET_CHAIN_NOT_FOUND = 14, TXC_NOT_VALIDATED = 254, TXC_INVALID_OTHER_REASON = 255
+    TXC_TARGET_CHAIN_NOT_FOUND = 14, TXC_BAD_HEADER_EXTENSION = 19, TXC_BAD_RESPONSE_PAYLOAD = 21, TXC_BAD_RWSET = 22, TXC_ILLEGAL_WRITESET = 23,
+    TXC_INVALID_CHAINCODE = 25, TXC_NOT_VALIDATED = 254, TXC_INVALID_OTHER_REASON = 255
 };
 
-#define BD_MAX_ENDS 16          // endorsements per transaction handled on the device; more -> that transaction is left to the CPU
+#define BD_MAX_SIGNERS 64       // distinct verified signers one policy evaluation handles (`used` is a 64-bit mask); more -> CPU validator
+#define BD_MAX_NS 4             // namespaces validated per transaction (the invoked chaincode + those it writes to); more -> CPU validator
+#define BD_MAX_NS_SEEN 8        // namespaces of one read/write set checked for duplicates; more -> CPU validator
+#define BD_ENDS_HINT 16         // job-array sizing: expected endorsements per transaction (the capacity is a parameter, see JobArrays::J_cap)
 
 struct Seg { uint32_t off, len; };
 
@@ -39,6 +43,8 @@ struct MspDev {
     const int32_t* key_slot;      // per identity: key-table slot or -1
     const uint8_t* valid;         // per identity: identity.Validate()
     const int32_t* msp_code;      // per identity: code of its MSP id (equal ids <=> equal codes)
+    const int32_t* group;         // per identity: de-duplication id -- Mspid + certificate (policy.go:380-386): two serializations of one
+                                  // certificate share it; null = every table entry is its own group
     const uint8_t* keys_xy;       // per identity: X || Y (64 bytes), for signatures whose key has no table
     const uint64_t* ht_hash;      // open-addressing table, size ht_size (power of two); 0 = empty
     const int32_t* ht_idx;
@@ -258,14 +264,15 @@ struct TxDev {
     uint8_t early;                 // decided by structure alone, else TXC_NOT_VALIDATED
     uint8_t htype;
     uint8_t endorser_parse_ok, channel_ok, endorsements_parse_ok, overflow;
-    uint8_t n_ends;
-    uint8_t pad;
+    uint8_t disp;                  // plugin dispatcher's structural verdict (dispatcher.go:102-179): TXC_VALID or the code it returns
+    uint8_t n_ns;                  // namespaces to validate: wr_ns[0] = the invoked chaincode, then the others it writes to
     int32_t creator_identity;      // -1 unknown
     int32_t creator_has_job;       // creator job index is the transaction index when 1
     Seg txid_ascii;
     Seg phash_claimed;
-    int32_t end_identity[BD_MAX_ENDS];
-    int32_t end_job[BD_MAX_ENDS];  // -1: nothing to verify for that endorsement
+    uint32_t first_end_job;        // endorsement jobs [first_end_job, first_end_job + n_end_jobs), in endorsement order
+    uint32_t n_end_jobs;           // (endorsements without signature bytes get none: they can never verify)
+    Seg wr_ns[BD_MAX_NS];
 };
 
 // Everything plan_tx writes for one transaction besides TxDev: job records live in caller-provided arrays.
@@ -284,13 +291,98 @@ struct JobArrays {
 // more threads than transactions: the walk alone exposed too little parallelism -- ncu: 2 warps/SM, issue active 3 %).
 struct RawJob { Seg ident; Seg sig; uint32_t tx; int32_t k; };   // k = -1: creator signature, else endorsement index; tx = 0xffffffff: unused slot
 
+// Wire scan of one message: known fields must carry their wire type (Go's proto.Unmarshal fails otherwise); on_bytes(field, seg)
+// is called for every length-delimited KNOWN field in order.  bytes_mask / varint_mask: bit f = field f is known with that type.
+template <typename F>
+BD_HD bool scan_msg(const uint8_t* base, Seg msg, uint32_t bytes_mask, uint32_t varint_mask, F on_bytes)
+{
+    Reader r; r.base = base; r.pos = msg.off; r.end = msg.off + msg.len; r.ok = true;
+    uint32_t f, wt; uint64_t v = 0; Seg b; b.off = b.len = 0;
+    while (r.next(f, wt, v, b)) {
+        if (f < 32 && ((bytes_mask >> f) & 1u)) { if (wt != 2) return false; on_bytes(f, b); }
+        else if (f < 32 && ((varint_mask >> f) & 1u)) { if (wt != 0) return false; }
+    }
+    return r.ok;
+}
+#define BD_F(n) (1u << (n))
+
+BD_HD bool seg_equal(const uint8_t* base, Seg a, Seg b)
+{
+    if (a.len != b.len) return false;
+    for (uint32_t i = 0; i < a.len; i++) if (base[a.off + i] != base[b.off + i]) return false;
+    return true;
+}
+
+// The plugin dispatcher's structural checks (plugindispatcher/dispatcher.go:102-179), in its order.  chdr_ext: ChannelHeader.extension;
+// prp / prp_ext: ProposalResponsePayload bytes and its extension (peer.ChaincodeAction).  Fills tx.disp, tx.wr_ns, tx.n_ns.
+BD_HD void dispatch_plan(const uint8_t* base, Seg chdr_ext, bool has_prp, bool has_prp_ext, Seg prp_ext, TxDev& tx)
+{
+    tx.disp = TXC_VALID; tx.n_ns = 0;
+    // hdrExt = ChaincodeHeaderExtension{chaincode_id = 2}, its ChaincodeID{path = 1, name = 2, version = 3} parsed with it
+    Seg h_ccid; h_ccid.off = h_ccid.len = 0; bool has_h_ccid = false;
+    if (!scan_msg(base, chdr_ext, BD_F(2), 0, [&](uint32_t, Seg b) { h_ccid = b; has_h_ccid = true; })) { tx.disp = TXC_BAD_HEADER_EXTENSION; return; }
+    Seg h_name; h_name.off = h_name.len = 0;
+    if (has_h_ccid && !scan_msg(base, h_ccid, BD_F(1) | BD_F(2) | BD_F(3), 0, [&](uint32_t f, Seg b) { if (f == 2) h_name = b; })) { tx.disp = TXC_BAD_HEADER_EXTENSION; return; }
+    // respPayload = GetActionFromEnvelope: ChaincodeAction{results = 1, events = 2, response = 3, chaincode_id = 4}
+    if (!has_prp || !has_prp_ext) { tx.disp = TXC_BAD_RESPONSE_PAYLOAD; return; }
+    Seg results, events, r_ccid; results.off = results.len = events.off = events.len = r_ccid.off = r_ccid.len = 0;
+    bool has_events = false, has_r_ccid = false;
+    if (!scan_msg(base, prp_ext, BD_F(1) | BD_F(2) | BD_F(3) | BD_F(4), 0, [&](uint32_t f, Seg b) {
+            if (f == 1) results = b; else if (f == 2) { events = b; has_events = true; } else if (f == 4) { r_ccid = b; has_r_ccid = true; } })) {
+        tx.disp = TXC_BAD_RESPONSE_PAYLOAD; return;
+    }
+    Seg r_name, r_ver; r_name.off = r_name.len = r_ver.off = r_ver.len = 0;
+    if (has_r_ccid && !scan_msg(base, r_ccid, BD_F(1) | BD_F(2) | BD_F(3), 0, [&](uint32_t f, Seg b) { if (f == 2) r_name = b; else if (f == 3) r_ver = b; })) {
+        tx.disp = TXC_BAD_RESPONSE_PAYLOAD; return;
+    }
+    // txRWSet.FromProtoBytes(results): TxReadWriteSet{data_model = 1, ns_rwset = 2}, every namespace with its KVRWSet and hashed collections
+    Seg seen[BD_MAX_NS_SEEN]; bool wrote[BD_MAX_NS_SEEN]; uint32_t n_seen = 0; bool too_many = false, rw_ok = true;
+    const bool top_ok = scan_msg(base, results, BD_F(2), BD_F(1), [&](uint32_t, Seg nsb) {
+        if (!rw_ok) return;
+        Seg name, kv; name.off = name.len = kv.off = kv.len = 0;
+        bool writes = false;
+        // NsReadWriteSet{namespace = 1, rwset = 2, collection_hashed_rwset = 3}
+        if (!scan_msg(base, nsb, BD_F(1) | BD_F(2) | BD_F(3), 0, [&](uint32_t f, Seg b) {
+                if (f == 1) name = b; else if (f == 2) kv = b;
+                else {                                                  // CollectionHashedReadWriteSet{collection_name = 1, hashed_rwset = 2, pvt_rwset_hash = 3}
+                    Seg hashed; hashed.off = hashed.len = 0;
+                    if (!scan_msg(base, b, BD_F(1) | BD_F(2) | BD_F(3), 0, [&](uint32_t g, Seg c) { if (g == 2) hashed = c; })) { rw_ok = false; return; }
+                    // HashedRWSet{hashed_reads = 1, hashed_writes = 2, metadata_writes = 3}
+                    if (!scan_msg(base, hashed, BD_F(1) | BD_F(2) | BD_F(3), 0, [&](uint32_t g, Seg) { if (g == 2 || g == 3) writes = true; })) rw_ok = false;
+                } })) { rw_ok = false; return; }
+        if (!rw_ok) return;
+        // KVRWSet{reads = 1, range_queries_info = 2, writes = 3, metadata_writes = 4}
+        if (!scan_msg(base, kv, BD_F(1) | BD_F(2) | BD_F(3) | BD_F(4), 0, [&](uint32_t g, Seg) { if (g == 3 || g == 4) writes = true; })) { rw_ok = false; return; }
+        if (n_seen < BD_MAX_NS_SEEN) { seen[n_seen] = name; wrote[n_seen] = writes; n_seen++; } else too_many = true;
+    });
+    if (!top_ok || !rw_ok) { tx.disp = TXC_BAD_RWSET; return; }
+    if (!has_h_ccid || !has_r_ccid) { tx.disp = TXC_INVALID_OTHER_REASON; return; }
+    if (h_name.len == 0 || !seg_equal(base, h_name, r_name) || r_ver.len == 0) { tx.disp = TXC_INVALID_CHAINCODE; return; }
+    if (has_events) {                                                  // ChaincodeEvent{chaincode_id = 1 (string), tx_id = 2, event_name = 3, payload = 4}
+        Seg ev_cc; ev_cc.off = ev_cc.len = 0;
+        if (!scan_msg(base, events, BD_F(1) | BD_F(2) | BD_F(3) | BD_F(4), 0, [&](uint32_t f, Seg b) { if (f == 1) ev_cc = b; }) || !seg_equal(base, ev_cc, h_name)) {
+            tx.disp = TXC_INVALID_OTHER_REASON; return;
+        }
+    }
+    if (too_many) { tx.disp = TXC_NOT_VALIDATED; return; }              // more namespaces than the device tracks: CPU validator
+    tx.wr_ns[0] = h_name; tx.n_ns = 1;
+    for (uint32_t i = 0; i < n_seen; i++) {
+        for (uint32_t j = 0; j < i; j++) if (seg_equal(base, seen[i], seen[j])) { tx.disp = TXC_ILLEGAL_WRITESET; return; }
+    }
+    for (uint32_t i = 0; i < n_seen; i++) {
+        if (!wrote[i] || seg_equal(base, seen[i], h_name)) continue;
+        if (tx.n_ns >= BD_MAX_NS) { tx.disp = TXC_NOT_VALIDATED; return; }
+        tx.wr_ns[tx.n_ns++] = seen[i];
+    }
+}
+
 // alloc_end(n) must return the first index of n fresh endorsement-job slots (atomicAdd on the device, a counter on the host)
 template <typename Alloc>
 BD_HD void walk_tx(const uint8_t* base, Seg env, uint32_t t, const uint8_t* channel, uint32_t channel_len, TxDev& tx, RawJob* raw,
                    JobArrays& ja, Alloc alloc_end)
 {
     tx.early = TXC_NOT_VALIDATED; tx.htype = 0; tx.endorser_parse_ok = 0; tx.channel_ok = 0; tx.endorsements_parse_ok = 1; tx.overflow = 0;
-    tx.n_ends = 0; tx.pad = 0; tx.creator_identity = -1; tx.creator_has_job = 0;
+    tx.disp = TXC_VALID; tx.n_ns = 0; tx.creator_identity = -1; tx.creator_has_job = 0; tx.first_end_job = 0; tx.n_end_jobs = 0;
     tx.txid_ascii.off = tx.txid_ascii.len = 0; tx.phash_claimed.off = tx.phash_claimed.len = 0;
     {
         ShaJobD z; for (int k = 0; k < 3; k++) { z.off[k] = 0; z.len[k] = 0; }
@@ -307,7 +399,7 @@ BD_HD void walk_tx(const uint8_t* base, Seg env, uint32_t t, const uint8_t* chan
     Sel h = make_sel(1, 2);                                           // Header{channel_header=1, signature_header=2}
     if (!parse_sel(base, p.s[0], h)) { tx.early = TXC_BAD_COMMON_HEADER; return; }
     const Seg chdr_b = h.s[0], shdr_b = h.s[1]; const bool has_chdr = h.present[0];
-    Sel ch = make_sel(4, 5, 0, 1, 6);                                 // ChannelHeader{type=1, channel_id=4, tx_id=5, epoch=6}
+    Sel ch = make_sel(4, 5, 7, 1, 6);                                 // ChannelHeader{type=1, channel_id=4, tx_id=5, epoch=6, extension=7}
     if (!parse_sel(base, chdr_b, ch)) { tx.early = TXC_BAD_COMMON_HEADER; return; }
     Sel sh = make_sel(1, 2);                                          // SignatureHeader{creator=1, nonce=2}
     if (!parse_sel(base, shdr_b, sh)) { tx.early = TXC_BAD_COMMON_HEADER; return; }
@@ -338,25 +430,26 @@ BD_HD void walk_tx(const uint8_t* base, Seg env, uint32_t t, const uint8_t* chan
     if (!parse_sel(base, ta.s[0], ah) || ah.s[1].len == 0 || ah.s[0].len == 0) return;
     Sel cap = make_sel(1, 2);                                         // ChaincodeActionPayload{chaincode_proposal_payload=1, action=2}
     if (!parse_sel(base, ta.s[1], cap) || !cap.present[1]) return;
-    Seg prp; prp.off = prp.len = 0; uint32_t n_end = 0;               // ChaincodeEndorsedAction{prp=1, repeated endorsements=2}
+    Seg prp; prp.off = prp.len = 0; uint32_t n_end = 0; bool has_prp = false;   // ChaincodeEndorsedAction{prp=1, repeated endorsements=2}
     {
         Reader r; r.base = base; r.pos = cap.s[1].off; r.end = cap.s[1].off + cap.s[1].len; r.ok = true;
         uint32_t f, wt; uint64_t v; Seg b;
         while (r.next(f, wt, v, b)) {
-            if (f == 1) { if (wt != 2) { r.ok = false; break; } prp = b; }
+            if (f == 1) { if (wt != 2) { r.ok = false; break; } prp = b; has_prp = true; }
             else if (f == 2) { if (wt != 2) { r.ok = false; break; } n_end++; }
         }
         if (!r.ok) return;
     }
-    Sel pr = make_sel(1);                                             // ProposalResponsePayload{proposal_hash=1}
+    Sel pr = make_sel(1, 2);                                          // ProposalResponsePayload{proposal_hash=1, extension=2}
     if (!parse_sel(base, prp, pr)) return;
     if (!has_chdr || !ta.present[0] || !cap.present[0]) return;       // GetProposalHash2 "nil arguments"
     { ShaJobD& b = ja.sha[ja.J_cap + 2 * t + 1];
       b.off[0] = chdr_b.off; b.len[0] = chdr_b.len; b.off[1] = ta.s[0].off; b.len[1] = ta.s[0].len; b.off[2] = cap.s[0].off; b.len[2] = cap.s[0].len; }
     tx.phash_claimed = pr.s[0];
     tx.endorser_parse_ok = 1;
-    if (n_end > BD_MAX_ENDS) { tx.overflow = 1; return; }
-    Seg ends[BD_MAX_ENDS]; Seg sigs[BD_MAX_ENDS]; uint32_t n_jobs = 0, k = 0;
+    dispatch_plan(base, ch.s[2], has_prp, pr.present[1], pr.s[1], tx);
+    // endorsements: one pass to count those that carry a signature, one to emit their jobs (contiguous, in endorsement order)
+    uint32_t n_jobs = 0;
     {
         Reader r; r.base = base; r.pos = cap.s[1].off; r.end = cap.s[1].off + cap.s[1].len; r.ok = true;
         uint32_t f, wt; uint64_t v; Seg b;
@@ -364,31 +457,32 @@ BD_HD void walk_tx(const uint8_t* base, Seg env, uint32_t t, const uint8_t* chan
             if (f != 2) continue;
             Sel en = make_sel(1, 2);                                  // Endorsement{endorser=1, signature=2}
             if (!parse_sel(base, b, en)) { tx.endorsements_parse_ok = 0; break; }
-            ends[k] = en.s[0]; sigs[k] = en.s[1];
-            tx.end_identity[k] = -1;
             // an endorsement without signature bytes can never verify: whatever its identity, it contributes nothing
-            tx.end_job[k] = (en.s[1].len > 0) ? 0 : -1;
-            if (tx.end_job[k] == 0) n_jobs++;
-            k++;
+            if (en.s[1].len > 0) n_jobs++;
         }
     }
-    tx.n_ends = (uint8_t)k;
-    if (n_jobs) {
-        uint32_t j = alloc_end(n_jobs);
-        for (uint32_t i = 0; i < k; i++) {
-            if (tx.end_job[i] < 0) continue;
-            if (j >= ja.J_cap) { tx.overflow = 1; tx.end_job[i] = -1; continue; }
-            raw[j].ident = ends[i]; raw[j].sig = sigs[i]; raw[j].tx = t; raw[j].k = (int32_t)i;
+    if (!tx.endorsements_parse_ok || n_jobs == 0) return;
+    uint32_t j = alloc_end(n_jobs);
+    if (j + n_jobs > ja.J_cap || j + n_jobs < j) { tx.overflow = 1; return; }          // job arrays full: this transaction goes to the CPU validator
+    tx.first_end_job = j; tx.n_end_jobs = n_jobs;
+    {
+        Reader r; r.base = base; r.pos = cap.s[1].off; r.end = cap.s[1].off + cap.s[1].len; r.ok = true;
+        uint32_t f, wt; uint64_t v; Seg b; int32_t k = 0;
+        while (r.next(f, wt, v, b)) {
+            if (f != 2) continue;
+            Sel en = make_sel(1, 2);
+            parse_sel(base, b, en);
+            if (en.s[1].len == 0) continue;
+            raw[j].ident = en.s[0]; raw[j].sig = en.s[1]; raw[j].tx = t; raw[j].k = k++;
             ShaJobD& sj = ja.sha[j];
-            sj.off[0] = prp.off; sj.len[0] = prp.len; sj.off[1] = ends[i].off; sj.len[1] = ends[i].len; sj.off[2] = 0; sj.len[2] = 0;
-            tx.end_job[i] = (int32_t)j;
+            sj.off[0] = prp.off; sj.len[0] = prp.len; sj.off[1] = en.s[0].off; sj.len[1] = en.s[0].len; sj.off[2] = 0; sj.len[2] = 0;
             j++;
         }
     }
 }
 
-// One signature job: identity lookup in the MSP table, DER / low-S gate, operands for the verify kernel, and the identity
-// index written back into the transaction record (distinct fields per job: no two jobs write the same word).
+// One signature job: identity lookup in the MSP table, DER / low-S gate, operands for the verify kernel, and (creator jobs) the
+// identity index written back into the transaction record.
 BD_HD void resolve_job(const uint8_t* base, uint32_t j, const RawJob* raw, const MspDev& msp, JobArrays& ja, TxDev* txs)
 {
     const RawJob rj = raw[j];
@@ -397,7 +491,7 @@ BD_HD void resolve_job(const uint8_t* base, uint32_t j, const RawJob* raw, const
     uint8_t rr[32], ss[32];
     if (rj.tx != 0xffffffffu) {
         identity = msp_find(msp, base + rj.ident.off, rj.ident.len);
-        if (rj.k < 0) txs[rj.tx].creator_identity = identity; else txs[rj.tx].end_identity[rj.k] = identity;
+        if (rj.k < 0) txs[rj.tx].creator_identity = identity;
         if (identity >= 0) ok = gate_signature(base + rj.sig.off, rj.sig.len, rr, ss);
     }
     uint32_t* r4 = reinterpret_cast<uint32_t*>(ja.r + 32 * (size_t)j);
@@ -415,17 +509,21 @@ BD_HD void resolve_job(const uint8_t* base, uint32_t j, const RawJob* raw, const
     }
 }
 
-// ---- policy evaluator: cauthdsl.go:24-92, `used` as a bit mask over at most BD_MAX_ENDS signers --------------------------
-struct PolicyDev { const int32_t* nodes; int32_t n_nodes; const int32_t* principal_code; int32_t n_principals; };
+// ---- policy evaluator: cauthdsl.go:24-92, `used` as a bit mask over at most BD_MAX_SIGNERS signers ------------------------
+// Several policies share one node array (one tree per chaincode namespace); ns_* name the root of each.
+struct PolicyDev {
+    const int32_t* nodes; int32_t n_nodes; const int32_t* principal_code; int32_t n_principals;
+    const uint8_t* ns_blob; const uint32_t* ns_off; const int32_t* ns_root; int32_t n_ns;     // n_ns = 0: one policy (root 0) for every namespace
+};
 
-BD_HD bool eval_policy(const PolicyDev& pol, int idx, const int32_t* signer_code, int n_signers, uint32_t& used, int depth)
+BD_HD bool eval_policy(const PolicyDev& pol, int idx, const int32_t* signer_code, int n_signers, uint64_t& used, int depth)
 {
     if (idx < 0 || idx >= pol.n_nodes || depth > 12) return false;
     const int32_t type = pol.nodes[4 * idx], n = pol.nodes[4 * idx + 1], first = pol.nodes[4 * idx + 2], cnt = pol.nodes[4 * idx + 3];
     if (type == 0) {
         int verified = 0;
         for (int c = first; c < first + cnt; c++) {
-            uint32_t scratch = used;
+            uint64_t scratch = used;
             if (eval_policy(pol, c, signer_code, n_signers, scratch, depth + 1)) { verified++; used = scratch; }
         }
         return verified >= n;
@@ -433,24 +531,42 @@ BD_HD bool eval_policy(const PolicyDev& pol, int idx, const int32_t* signer_code
     if (n < 0 || n >= pol.n_principals) return false;
     const int32_t want = pol.principal_code[n];
     for (int i = 0; i < n_signers; i++) {
-        if (used & (1u << i)) continue;
+        if (used & (1ull << i)) continue;
         if (signer_code[i] < 0 || signer_code[i] != want) continue;
-        used |= 1u << i;
+        used |= 1ull << i;
         return true;
     }
     return false;
 }
 
+// root node of namespace `ns`'s policy, -1 when the table has no chaincode definition for it
+BD_HD int32_t policy_root(const PolicyDev& pol, const uint8_t* base, Seg ns)
+{
+    if (pol.n_ns == 0) return pol.n_nodes > 0 ? 0 : -1;
+    for (int32_t i = 0; i < pol.n_ns; i++) {
+        const uint32_t o = pol.ns_off[i], l = pol.ns_off[i + 1] - o;
+        if (l != ns.len) continue;
+        bool eq = true;
+        for (uint32_t k = 0; k < l && eq; k++) eq = pol.ns_blob[o + k] == base[ns.off + k];
+        if (eq) return pol.ns_root[i];
+    }
+    return -1;
+}
+
 // ---- per-transaction decision ---------------------------------------------------------------------------------------------
-// sig_ok(j): signature job j verified (gate and curve).  digests: 32 bytes per SHA job (same indexing as JobArrays::sha).
+// sig_ok(j): signature job j verified (gate and curve).  job_identity: JobArrays::identity.  digests: 32 bytes per SHA job.
+// An identity the table does not hold, or a namespace without a policy entry, cannot be decided here: TXC_NOT_VALIDATED hands the
+// transaction to the CPU validator (the reference deserialises and validates ANY certificate of the channel's CAs,
+// msgvalidation.go:40-57, and reads chaincode definitions from the ledger, dispatcher.go:224-277).
 template <typename SigOk>
 BD_HD uint8_t decide_tx(const uint8_t* base, const TxDev& tx, uint32_t t, const MspDev& msp, const PolicyDev& pol, SigOk sig_ok,
-                        const uint8_t* digests, uint32_t J_cap, uint64_t* txid_hash_out)
+                        const int32_t* job_identity, const uint8_t* digests, uint32_t J_cap, uint64_t* txid_hash_out)
 {
     const char hex[] = "0123456789abcdef";
     if (tx.early != TXC_NOT_VALIDATED) return tx.early;
-    const bool creator_ok = tx.creator_identity >= 0 && msp.valid[tx.creator_identity] && tx.creator_has_job && sig_ok(t);
-    if (!creator_ok) return TXC_BAD_CREATOR_SIGNATURE;
+    if (!tx.creator_has_job) return TXC_BAD_CREATOR_SIGNATURE;        // "nil arguments"
+    if (tx.creator_identity < 0) return TXC_NOT_VALIDATED;            // not in the device's MSP table
+    if (!msp.valid[tx.creator_identity] || !sig_ok(t)) return TXC_BAD_CREATOR_SIGNATURE;
     if (tx.htype == 1) return TXC_NOT_VALIDATED;                      // config transaction: CPU validator
     if (tx.htype != 3) return TXC_UNSUPPORTED_TX_PAYLOAD;
     {
@@ -464,22 +580,37 @@ BD_HD uint8_t decide_tx(const uint8_t* base, const TxDev& tx, uint32_t t, const 
     if (tx.phash_claimed.len != 32 || !bytes_equal(base + tx.phash_claimed.off, digests + 32 * (size_t)(J_cap + 2 * t + 1), 32))
         return TXC_INVALID_ENDORSER_TRANSACTION;
     if (!tx.channel_ok) return TXC_TARGET_CHAIN_NOT_FOUND;
-    if (tx.overflow) return TXC_NOT_VALIDATED;                        // more endorsements than the device handles: CPU validator
+    if (tx.disp != TXC_VALID) return tx.disp;                         // the plugin dispatcher's own checks
     if (!tx.endorsements_parse_ok) return TXC_INVALID_OTHER_REASON;
-    int32_t seen[BD_MAX_ENDS]; int32_t signer_code[BD_MAX_ENDS]; int n_seen = 0;
-    for (int i = 0; i < tx.n_ends; i++) {
-        const int32_t idn = tx.end_identity[i];
-        if (idn < 0) continue;
-        bool dup = false;
-        for (int s = 0; s < n_seen; s++) if (seen[s] == idn) { dup = true; break; }
-        if (dup) continue;
-        if (tx.end_job[i] < 0 || !sig_ok((uint32_t)tx.end_job[i])) continue;
-        seen[n_seen] = idn;
-        signer_code[n_seen] = msp.valid[idn] ? msp.msp_code[idn] : -1;
-        n_seen++;
+    if (tx.overflow) return TXC_NOT_VALIDATED;                        // job arrays were full: CPU validator
+    int32_t roots[BD_MAX_NS];
+    for (int i = 0; i < tx.n_ns; i++) {
+        roots[i] = policy_root(pol, base, tx.wr_ns[i]);
+        if (roots[i] < 0) return TXC_NOT_VALIDATED;                   // no chaincode definition on the device
     }
-    uint32_t used = 0;
-    if (pol.n_nodes == 0 || !eval_policy(pol, 0, signer_code, n_seen, used, 0)) return TXC_ENDORSEMENT_POLICY_FAILURE;
+    // SignatureSetToValidIdentities (policy.go:365-402): in order; de-duplicated by Mspid + Id against the identities that already
+    // VERIFIED; a failed signature drops that entry only.  One set per transaction, shared by every namespace's evaluation.
+    int32_t signer_code[BD_MAX_SIGNERS]; int n_signers = 0;
+    for (uint32_t i = 0; i < tx.n_end_jobs; i++) {
+        const uint32_t j = tx.first_end_job + i;
+        const int32_t idn = job_identity[j];
+        if (idn < 0) return TXC_NOT_VALIDATED;
+        const int32_t grp = msp.group ? msp.group[idn] : idn;
+        bool dup = false;
+        for (uint32_t i2 = 0; i2 < i && !dup; i2++) {
+            const uint32_t j2 = tx.first_end_job + i2;
+            const int32_t id2 = job_identity[j2];
+            dup = (msp.group ? msp.group[id2] : id2) == grp && sig_ok(j2);
+        }
+        if (dup) continue;
+        if (!sig_ok(j)) continue;
+        if (n_signers >= BD_MAX_SIGNERS) return TXC_NOT_VALIDATED;
+        signer_code[n_signers++] = msp.valid[idn] ? msp.msp_code[idn] : -1;
+    }
+    for (int i = 0; i < tx.n_ns; i++) {
+        uint64_t used = 0;
+        if (!eval_policy(pol, roots[i], signer_code, n_signers, used, 0)) return TXC_ENDORSEMENT_POLICY_FAILURE;
+    }
     uint64_t hsh = 1469598103934665603ull;
     for (uint32_t k = 0; k < tx.txid_ascii.len; k++) hsh = (hsh ^ base[tx.txid_ascii.off + k]) * 1099511628211ull;
     *txid_hash_out = hsh;

@@ -33,13 +33,14 @@ block_resolve_kernel(const uint8_t* __restrict__ block, const RawJob* __restrict
 // Replays the reference's decision order for every transaction on the verification bitmask and the digests.
 __global__ void __launch_bounds__(128)
 block_decide_kernel(const uint8_t* __restrict__ block, const TxDev* __restrict__ txs, uint32_t T, MspDev msp, PolicyDev pol,
-                    const uint32_t* __restrict__ mask, const uint8_t* __restrict__ gate_ok, const uint8_t* __restrict__ digests, uint32_t J_cap,
+                    const uint32_t* __restrict__ mask, const uint8_t* __restrict__ gate_ok, const int32_t* __restrict__ job_identity,
+                    const uint8_t* __restrict__ digests, uint32_t J_cap,
                     uint8_t* __restrict__ flags, uint64_t* __restrict__ txid_hash, Seg* __restrict__ txid_seg)
 {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= T) return;
     uint64_t h = 0;
-    flags[t] = decide_tx(block, txs[t], t, msp, pol, [&](uint32_t j) { return gate_ok[j] && ((mask[j >> 5] >> (j & 31)) & 1u); }, digests, J_cap, &h);
+    flags[t] = decide_tx(block, txs[t], t, msp, pol, [&](uint32_t j) { return gate_ok[j] && ((mask[j >> 5] >> (j & 31)) & 1u); }, job_identity, digests, J_cap, &h);
     txid_hash[t] = h;
     txid_seg[t] = txs[t].txid_ascii;
 }

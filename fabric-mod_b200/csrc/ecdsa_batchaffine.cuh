@@ -74,6 +74,24 @@ FAB_HD void ba_digits(const u256& u1, const u256& u2, uint32_t* dig, int stride)
     }
 }
 
+// Ask the L2 for every table entry of a signature as soon as its digits exist (no register cost).  The forward pass has one
+// multiplication per two gathers: without this, each of its 14 iterations waits out a DRAM round trip (ncu: long_scoreboard 25 % of
+// all warp time); with the lines already on their way only the first wait is a DRAM latency, the rest are L2 hits.
+#ifndef FAB_BA_L2PREFETCH
+#define FAB_BA_L2PREFETCH 1
+#endif
+FAB_HD void ba_prefetch_leaves(const uint32_t* dig, int stride, const aff* gtab, const aff* qtab)
+{
+#if defined(__CUDA_ARCH__) && FAB_BA_L2PREFETCH
+    for (int leaf = 0; leaf < FAB_BA_NP; leaf++) {
+        const uint32_t idx = dig[leaf * stride];
+        if (idx != FAB_BA_INF) asm volatile("prefetch.global.L2 [%0];" :: "l"((leaf < FAB_BA_NGP ? gtab : qtab) + idx));
+    }
+#else
+    (void)dig; (void)stride; (void)gtab; (void)qtab;
+#endif
+}
+
 // Operand `leaf` of a level: first = a table entry named by the digit array, otherwise a level-1 result.  (Runtime flags, not
 // template parameters: the kernel holds ONE copy of each pass and loops over the levels -- the first version, with a copy per
 // level and per modulus, was 212 KB of code.)

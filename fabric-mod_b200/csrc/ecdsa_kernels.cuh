@@ -342,7 +342,7 @@ ecdsa_verify_ba_kernel(const int32_t* __restrict__ key_slot, const uint8_t* __re
     BaScratch sc;
     uint32_t exc = 0, m1 = 0;
     jac acc = jac_infinity();
-    if (ok) ba_scalars(load_be32(e + o), load_be32(r + o), v, mydig, T);
+    if (ok) { ba_scalars(load_be32(e + o), load_be32(r + o), v, mydig, T); ba_prefetch_leaves(mydig, T, gtab, qt); }
 #pragma unroll 1
     for (int level = 0; level < 2; level++) {
         const bool first = level == 0;
@@ -429,7 +429,10 @@ ecdsa_verify_ba2_kernel(const int32_t* __restrict__ key_slot, const uint8_t* __r
     uint32_t res[2] = {V_INVALID, V_INVALID};
 #pragma unroll
     for (int h = 0; h < 2; h++)
-        if (ok[h]) ba_scalars(load_be32(e + (size_t)(base + h * T) * 32), load_be32(r + (size_t)(base + h * T) * 32), v[h], dig + h * FAB_BA_NP * T + threadIdx.x, T);
+        if (ok[h]) {
+            ba_scalars(load_be32(e + (size_t)(base + h * T) * 32), load_be32(r + (size_t)(base + h * T) * 32), v[h], dig + h * FAB_BA_NP * T + threadIdx.x, T);
+            ba_prefetch_leaves(dig + h * FAB_BA_NP * T + threadIdx.x, T, gtab, qt[h]);
+        }
 #pragma unroll 1
     for (int level = 0; level < 2; level++) {
         const bool first = level == 0;

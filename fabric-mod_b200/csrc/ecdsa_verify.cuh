@@ -28,6 +28,9 @@
 #endif
 #define FAB_Q_WINDOWS ((256 + FAB_WQ - 1) / FAB_WQ)
 #define FAB_Q_ENTRIES ((1 << FAB_WQ) - 1)
+#ifndef FAB_JAC_L2PREFETCH
+#define FAB_JAC_L2PREFETCH 0
+#endif
 #ifndef FAB_SAFEGCD
 #define FAB_SAFEGCD 1
 #endif
@@ -177,6 +180,26 @@ FAB_HD uint32_t ecdsa_verify_one_cached(const aff* qtab, const u256& e, const u2
     // One loop over both tables -- 12 windows of u1 in the generator's table, then 16 windows of u2 in the key's table -- so that
     // the kernel holds a single copy of the point addition (expanded in place when FAB_CACHED_INLINE).
     jac acc = jac_infinity();
+#if defined(__CUDA_ARCH__) && FAB_JAC_L2PREFETCH
+    // every table entry this signature will gather, requested from the L2 up front (the tables are HBM-resident: 3.2 GB + 64 MiB per key)
+#pragma unroll 1
+    for (int t = 0; t < 2; t++) {
+        uint32_t kk[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) kk[i] = t ? u2.v[i] : u1.v[i];
+        const aff* tab = t ? qtab : gtab;
+        const uint32_t wbits = t ? FAB_WQ : FAB_WG, entries = (1u << wbits) - 1u;
+        const int windows = t ? FAB_Q_WINDOWS : FAB_G_WINDOWS;
+#pragma unroll 1
+        for (int j = 0; j < windows; j++) {
+            const uint32_t d = kk[0] & entries;
+#pragma unroll
+            for (int i = 0; i < 7; i++) kk[i] = (kk[i] >> wbits) | (kk[i + 1] << (32u - wbits));
+            kk[7] >>= wbits;
+            if (d) asm volatile("prefetch.global.L2 [%0];" :: "l"(tab + (size_t)j * entries + (d - 1)));
+        }
+    }
+#endif
 #pragma unroll 1
     for (int t = 0; t < 2; t++) {
         uint32_t kk[8];

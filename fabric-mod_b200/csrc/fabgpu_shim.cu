@@ -173,6 +173,8 @@ struct fabgpu_ctx {
     struct DevMsp {
         uint8_t *id_blob = nullptr, *valid = nullptr, *keys_xy = nullptr, *channel = nullptr;
         uint32_t* id_off = nullptr; int32_t *key_slot = nullptr, *msp_code = nullptr, *ht_idx = nullptr, *nodes = nullptr, *principal_code = nullptr;
+        int32_t* group = nullptr;                                     // de-duplication groups (fabgpu_msp_identity_groups), null = identity index
+        uint8_t* ns_blob = nullptr; uint32_t* ns_off = nullptr; int32_t* ns_root = nullptr; int32_t n_ns = 0;    // fabgpu_namespace_policies
         uint64_t* ht_hash = nullptr; uint32_t ht_size = 0; int32_t n_ids = 0, n_nodes = 0, n_principals = 0; uint32_t channel_len = 0;
         bool all_slots = true;
     } dm;
@@ -401,7 +403,8 @@ void free_all(fabgpu_ctx* ctx)
             for (void* p : host_ptrs) if (p) cudaFreeHost(p);
         }
         auto& dm = ctx->dm;
-        void* dev2[] = {dm.id_blob, dm.valid, dm.keys_xy, dm.channel, dm.id_off, dm.key_slot, dm.msp_code, dm.ht_idx, dm.nodes, dm.principal_code, dm.ht_hash};
+        void* dev2[] = {dm.id_blob, dm.valid, dm.keys_xy, dm.channel, dm.id_off, dm.key_slot, dm.msp_code, dm.ht_idx, dm.nodes, dm.principal_code, dm.ht_hash,
+                        dm.group, dm.ns_blob, dm.ns_off, dm.ns_root};
         for (void* p : dev2) if (p) cudaFree(p);
         for (auto& db : ctx->dbs) {
             void* dev4[] = {db.d_env_off, db.d_txs, db.d_raw, db.d_sha, db.d_r, db.d_s, db.d_qx, db.d_qy, db.d_gate, db.d_dig, db.d_flags, db.d_ks, db.d_ident, db.d_mask, db.d_off,
@@ -1332,7 +1335,8 @@ static int upload_msp(fabgpu_ctx* ctx, const uint8_t* id_blob, const uint32_t* i
     CK(ctx, cudaSetDevice(ctx->devs[0].id));
     // blocks already enqueued on a slot were launched with the OLD tables (passed by value): let them finish before those go away
     for (auto& ds : ctx->devs[0].slot) CK(ctx, cudaStreamSynchronize(ds.stream));
-    void* old[] = {dm.id_blob, dm.valid, dm.keys_xy, dm.channel, dm.id_off, dm.key_slot, dm.msp_code, dm.ht_idx, dm.nodes, dm.principal_code, dm.ht_hash};
+    void* old[] = {dm.id_blob, dm.valid, dm.keys_xy, dm.channel, dm.id_off, dm.key_slot, dm.msp_code, dm.ht_idx, dm.nodes, dm.principal_code, dm.ht_hash,
+                   dm.group, dm.ns_blob, dm.ns_off, dm.ns_root};
     for (void* p : old) if (p) cudaFree(p);
     dm = fabgpu_ctx::DevMsp();
     // MSP-id codes: equal strings <=> equal codes, shared between identities and policy principals
@@ -1414,6 +1418,51 @@ int fabgpu_msp_configure(fabgpu_ctx* ctx, const uint8_t* id_blob, const uint32_t
     return upload_msp(ctx, id_blob, id_off, keys_xy, valid, n_ids, policy_nodes, n_nodes);
 }
 
+// drains the block slots' streams: kernels already enqueued keep reading the tables they were launched with
+static int drain_block_streams(fabgpu_ctx* ctx)
+{
+    CK(ctx, cudaSetDevice(ctx->devs[0].id));
+    for (auto& ds : ctx->devs[0].slot) CK(ctx, cudaStreamSynchronize(ds.stream));
+    return FABGPU_OK;
+}
+
+int fabgpu_msp_identity_groups(fabgpu_ctx* ctx, const int32_t* group, int n_ids)
+{
+    if (!ctx || n_ids < 0 || (n_ids && !group)) return FABGPU_E_ARG;
+    std::lock_guard<std::mutex> lk0(ctx->slot0_mu);
+    auto& dm = ctx->dm;
+    if (n_ids != dm.n_ids) { ctx->last_error = "group table does not match the identities given to fabgpu_msp_configure"; return FABGPU_E_ARG; }
+    int rc = drain_block_streams(ctx); if (rc) return rc;
+    if (dm.group) { cudaFree(dm.group); dm.group = nullptr; }
+    if (n_ids == 0) return FABGPU_OK;
+    CK(ctx, cudaMalloc(&dm.group, 4 * (size_t)n_ids));
+    CK(ctx, cudaMemcpy(dm.group, group, 4 * (size_t)n_ids, cudaMemcpyHostToDevice));
+    return FABGPU_OK;
+}
+
+int fabgpu_namespace_policies(fabgpu_ctx* ctx, const uint8_t* ns_blob, const uint32_t* ns_off, const int32_t* ns_root, int n_ns)
+{
+    if (!ctx || n_ns < 0 || (n_ns && (!ns_blob || !ns_off || !ns_root))) return FABGPU_E_ARG;
+    std::lock_guard<std::mutex> lk0(ctx->slot0_mu);
+    auto& dm = ctx->dm;
+    for (int i = 0; i < n_ns; i++)
+        if (ns_root[i] < 0 || ns_root[i] >= dm.n_nodes || ns_off[i] > ns_off[i + 1]) { ctx->last_error = "namespace policy root out of range"; return FABGPU_E_ARG; }
+    int rc = drain_block_streams(ctx); if (rc) return rc;
+    void* old[] = {dm.ns_blob, dm.ns_off, dm.ns_root};
+    for (void* p : old) if (p) cudaFree(p);
+    dm.ns_blob = nullptr; dm.ns_off = nullptr; dm.ns_root = nullptr; dm.n_ns = 0;
+    if (n_ns == 0) return FABGPU_OK;
+    const size_t bl = ns_off[n_ns];
+    CK(ctx, cudaMalloc(&dm.ns_blob, bl + 8));
+    if (bl) CK(ctx, cudaMemcpy(dm.ns_blob, ns_blob, bl, cudaMemcpyHostToDevice));
+    CK(ctx, cudaMalloc(&dm.ns_off, 4 * (size_t)(n_ns + 1)));
+    CK(ctx, cudaMemcpy(dm.ns_off, ns_off, 4 * (size_t)(n_ns + 1), cudaMemcpyHostToDevice));
+    CK(ctx, cudaMalloc(&dm.ns_root, 4 * (size_t)n_ns));
+    CK(ctx, cudaMemcpy(dm.ns_root, ns_root, 4 * (size_t)n_ns, cudaMemcpyHostToDevice));
+    dm.n_ns = n_ns;
+    return FABGPU_OK;
+}
+
 int fabgpu_block_buffer_slot(fabgpu_ctx* ctx, int slot, size_t bytes, uint8_t** out)
 {
     if (!ctx || !out || slot < 0 || slot >= FABGPU_SLOTS) return FABGPU_E_ARG;
@@ -1491,9 +1540,9 @@ static int block_submit(fabgpu_ctx* ctx, int slot, const uint8_t* block, size_t 
     const size_t T = n_env;
     db.T = T; db.block = block;
     if (T == 0) return FABGPU_OK;
-    const size_t J_cap = T * (1 + BD_MAX_ENDS);
+    const size_t J_cap = T * (1 + BD_ENDS_HINT);
     if (T > db.tx_cap) {
-        const size_t tc = T + (T >> 2) + 256, jc = tc * (1 + BD_MAX_ENDS);
+        const size_t tc = T + (T >> 2) + 256, jc = tc * (1 + BD_ENDS_HINT);
         int rc = 0;
         db.tx_cap = 0; db.j_cap = 0;                        // reset first: after a partial failure the pointers are gone
         rc |= grow_dev(ctx, db.d_env_off, 8 * (tc + 1)); rc |= grow_dev(ctx, db.d_txs, sizeof(bdev::TxDev) * tc);
@@ -1516,9 +1565,10 @@ static int block_submit(fabgpu_ctx* ctx, int slot, const uint8_t* block, size_t 
     cudaStream_t st = ds.stream;
     CK(ctx, cudaMemcpyAsync(db.d_env_off, db.h_env_off, 8 * T, cudaMemcpyHostToDevice, st));
     CK(ctx, cudaMemsetAsync(db.d_counter, 0, 16, st));
-    bdev::MspDev m; m.id_blob = dm.id_blob; m.id_off = dm.id_off; m.key_slot = dm.key_slot; m.valid = dm.valid; m.msp_code = dm.msp_code;
+    bdev::MspDev m; m.id_blob = dm.id_blob; m.id_off = dm.id_off; m.key_slot = dm.key_slot; m.valid = dm.valid; m.msp_code = dm.msp_code; m.group = dm.group;
     m.keys_xy = dm.keys_xy; m.ht_hash = dm.ht_hash; m.ht_idx = dm.ht_idx; m.ht_size = dm.ht_size; m.n_ids = dm.n_ids;
     bdev::PolicyDev pol; pol.nodes = dm.nodes; pol.n_nodes = dm.n_nodes; pol.principal_code = dm.principal_code; pol.n_principals = dm.n_principals;
+    pol.ns_blob = dm.ns_blob; pol.ns_off = dm.ns_off; pol.ns_root = dm.ns_root; pol.n_ns = dm.n_ns;
     bdev::JobArrays ja; ja.sha = db.d_sha; ja.r = db.d_r; ja.s = db.d_s; ja.key_slot = db.d_ks; ja.identity = db.d_ident; ja.qx = dm.all_slots ? nullptr : db.d_qx;
     ja.qy = dm.all_slots ? nullptr : db.d_qy; ja.gate_ok = db.d_gate; ja.J_cap = (uint32_t)J_cap; ja.T = (uint32_t)T;
     const uint32_t cnt = (uint32_t)T, E_cap = (uint32_t)(J_cap - T);
@@ -1545,7 +1595,7 @@ static int block_submit(fabgpu_ctx* ctx, int slot, const uint8_t* block, size_t 
                            db.d_counter, cnt);
     if (rc) return rc;
     if (db.use_ev) CK(ctx, cudaEventRecord(db.ev[4], st));
-    bdev::block_decide_kernel<<<(cnt + 127) / 128, 128, 0, st>>>(bb.d_block, db.d_txs, cnt, m, pol, db.d_mask, db.d_gate, db.d_dig, (uint32_t)J_cap, db.d_flags,
+    bdev::block_decide_kernel<<<(cnt + 127) / 128, 128, 0, st>>>(bb.d_block, db.d_txs, cnt, m, pol, db.d_mask, db.d_gate, db.d_ident, db.d_dig, (uint32_t)J_cap, db.d_flags,
                                                                db.d_hash, db.d_seg);
     ctx->launches++;
     CK(ctx, cudaGetLastError());
@@ -1601,9 +1651,6 @@ static int block_finish(fabgpu_ctx* ctx, int slot, uint8_t* flags)
     return FABGPU_OK;
 }
 
-static int validate_host(fabgpu_ctx* ctx, const uint8_t* block, size_t block_len, const uint32_t* env_off, size_t n_env, uint8_t* flags,
-                         size_t flags_cap, size_t* n_tx_out);
-
 // serialized: 1 = `block` is a serialized common.Block (env_off unused), 0 = concatenated envelopes with an offset table
 static int validate_submit(fabgpu_ctx* ctx, int slot, const uint8_t* block, size_t block_len, const uint32_t* env_off, size_t n_env)
 {
@@ -1618,17 +1665,8 @@ static int validate_submit(fabgpu_ctx* ctx, int slot, const uint8_t* block, size
     auto& db = ctx->dbs[slot];
     if (db.busy) { ctx->last_error = "slot already holds a block: call fabgpu_validate_wait first"; return FABGPU_E_ARG; }
     if (fault_injected()) { ctx->last_error = "fault injected (FABGPU_FAULT_INJECT=1)"; return FABGPU_E_INJECTED; }
-    const char* hp = getenv("FABGPU_BLOCK_HOST");            // "1": parse / gate / decide on host threads (blockval.cpp) instead of on the device
     int rc;
-    if (hp && hp[0] == '1') {
-        // the host-thread path is synchronous: it completes here and _wait only hands the flags out
-        if (slot != 0 && ctx->dbs[0].busy) { ctx->last_error = "the host-thread path shares slot 0's buffers: wait for slot 0 first"; return FABGPU_E_ARG; }
-        size_t cap = env_off ? n_env : block_len / 2 + 16, n_tx = 0;      // an envelope entry of a Block is at least two bytes
-        db.done_flags.assign(cap ? cap : 1, 0);
-        rc = validate_host(ctx, block, block_len, env_off, n_env, db.done_flags.data(), db.done_flags.size(), &n_tx);
-        if (rc) return rc;
-        db.T = n_tx; db.on_device = false;
-    } else {
+    {
         std::lock_guard<std::mutex> lk0(ctx->slot0_mu);      // key-cache / MSP state: one submitter at a time
         rc = block_submit(ctx, slot, block, block_len, env_off, n_env);
         if (rc) { cudaStreamSynchronize(ctx->devs[0].slot[slot].stream); return rc; }
@@ -1692,152 +1730,6 @@ int fabgpu_validate_envelopes(fabgpu_ctx* ctx, const uint8_t* blob, const uint32
     int rc = fabgpu_validate_envelopes_async(ctx, 0, blob, env_off, n_env);
     if (rc) return rc;
     return fabgpu_validate_wait(ctx, 0, flags, flags_cap, n_tx_out);
-}
-
-// Host-thread form of the pre-pass (FABGPU_BLOCK_HOST=1): blockval.cpp walks / gates / decides, the GPU hashes and verifies.
-static int validate_host(fabgpu_ctx* ctx, const uint8_t* block, size_t block_len, const uint32_t* env_off, size_t n_env, uint8_t* flags,
-                         size_t flags_cap, size_t* n_tx_out)
-{
-    std::lock_guard<std::mutex> lk0(ctx->slot0_mu);
-    auto now = [] { return std::chrono::steady_clock::now(); };
-    auto us = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
-        return std::chrono::duration<double, std::micro>(b - a).count();
-    };
-    auto t0 = now();
-    Device& dv = ctx->devs[0];
-    DevSlot& ds = dv.slot[0];
-    auto& bb = ctx->bbs[0];
-    CK(ctx, cudaSetDevice(dv.id));
-    // 1. the block goes to the device while the host parses it
-    if (block_len > bb.block_cap) {
-        const size_t want = block_len + (block_len >> 2);
-        bb.block_cap = 0;                                   // a failed grow leaves no buffer: do not remember the old capacity
-        int rc = grow_dev(ctx, bb.d_block, want + 64);      // slack: word-wise readers (bytes_equal, the SHA loader) touch the aligned words past the end
-        if (rc) return rc;
-        bb.block_cap = want;
-    }
-    CK(ctx, cudaMemcpyAsync(bb.d_block, block, block_len, cudaMemcpyHostToDevice, ds.stream));
-    // 2. plan: every signature the block needs, every digest the transaction checks need
-    blockval::BlockPlan plan;
-    const int TH = ctx->pool->size();
-    {
-        std::vector<blockval::Seg> envs;
-        if (env_off) {                                    // the caller already holds Block.Data.Data as separate byte strings
-            envs.resize(n_env);
-            for (size_t i = 0; i < n_env; i++) { envs[i].off = env_off[i]; envs[i].len = env_off[i + 1] - env_off[i]; }
-        } else if (!blockval::split_block(block, block_len, envs)) {
-            cudaStreamSynchronize(ds.stream);
-            ctx->last_error = "block does not parse";
-            return FABGPU_E_ARG;
-        }
-        plan.txs.assign(envs.size(), blockval::TxPlan());
-        std::vector<blockval::JobPart> parts(TH);
-        std::vector<size_t> bounds(TH + 1);
-        for (int k = 0; k <= TH; k++) bounds[k] = envs.size() * (size_t)k / TH;
-        ctx->pool->run([&](int tid) {
-            parts[tid].creators.reserve(bounds[tid + 1] - bounds[tid] + 4);
-            parts[tid].endorsements.reserve((bounds[tid + 1] - bounds[tid]) * 4 + 4);
-            blockval::plan_range(block, envs, bounds[tid], bounds[tid + 1], ctx->msp, ctx->channel, plan.txs.data(), parts[tid]);
-        });
-        blockval::merge_plan(plan, parts, bounds);
-    }
-    const size_t T = plan.txs.size(), J = plan.jobs.size(), C = (size_t)plan.n_check, S = J + 2 * C;
-    *n_tx_out = T;
-    if (T > flags_cap) { cudaStreamSynchronize(ds.stream); ctx->last_error = "flags buffer too small"; return FABGPU_E_ARG; }
-    auto t1 = now();
-    if (J > bb.job_cap) {
-        const size_t cap = round_up32(J + (J >> 2) + 1024);
-        int rc = 0;
-        rc |= grow_dev(ctx, bb.d_r, 32 * cap); rc |= grow_dev(ctx, bb.d_s, 32 * cap); rc |= grow_dev(ctx, bb.d_qx, 32 * cap); rc |= grow_dev(ctx, bb.d_qy, 32 * cap);
-        rc |= grow_host(ctx, bb.h_r, 32 * cap); rc |= grow_host(ctx, bb.h_s, 32 * cap); rc |= grow_host(ctx, bb.h_qx, 32 * cap); rc |= grow_host(ctx, bb.h_qy, 32 * cap);
-        rc |= grow_dev(ctx, bb.d_ks, 4 * cap); rc |= grow_host(ctx, bb.h_ks, 4 * cap);
-        rc |= grow_dev(ctx, bb.d_mask, cap / 8 + 4); rc |= grow_dev(ctx, bb.d_off, cap / 8 + 4); rc |= grow_host(ctx, bb.h_mask, cap / 8 + 4);
-        if (rc) return FABGPU_E_CUDA;
-        bb.job_cap = cap;
-    }
-    if (S > bb.sha_cap) {
-        const size_t cap = S + (S >> 2) + 1024;
-        int rc = 0;
-        rc |= grow_dev(ctx, bb.d_sha, sizeof(ShaJob) * cap); rc |= grow_host(ctx, bb.h_sha, sizeof(ShaJob) * cap);
-        rc |= grow_dev(ctx, bb.d_dig, 32 * cap); rc |= grow_host(ctx, bb.h_dig, 32 * cap);
-        if (rc) return FABGPU_E_CUDA;
-        bb.sha_cap = cap;
-    }
-    // 3. host gates on every signature (DER, R > 0, S > 0, low-S, r < 2^256) + digest job descriptors
-    std::vector<uint8_t> gate_ok(J, 0);
-    bool all_slots = true;
-    for (size_t j = 0; j < J && all_slots; j++) all_slots = handle_to_slot(ctx, ctx->identity_slot[plan.jobs[j].identity]) >= 0;
-    static const uint8_t kZero32[32] = {0};
-    ctx->pool->run([&](int tid) {
-        const size_t lo = J * (size_t)tid / TH, hi = J * (size_t)(tid + 1) / TH;
-        for (size_t j = lo; j < hi; j++) {
-            const blockval::SigJob& sj = plan.jobs[j];
-            host::Gate g;
-            host::gate_signature(block + sj.sig.off, sj.sig.len, g, false);
-            const bool ok = g.status == FABGPU_ST_VALID;
-            gate_ok[j] = ok;
-            stage32(bb.h_r + 32 * j, ok ? g.r : kZero32);
-            stage32(bb.h_s + 32 * j, ok ? g.s : kZero32);
-            stage_i32(bb.h_ks + j, handle_to_slot(ctx, ctx->identity_slot[sj.identity]));
-            if (!all_slots) {
-                stage32(bb.h_qx + 32 * j, ctx->msp.keys_xy.data() + 64 * (size_t)sj.identity);
-                stage32(bb.h_qy + 32 * j, ctx->msp.keys_xy.data() + 64 * (size_t)sj.identity + 32);
-            }
-            ShaJob& sh = bb.h_sha[j];
-            sh.off[0] = sj.msg[0].off; sh.len[0] = sj.msg[0].len; sh.off[1] = sj.msg[1].off; sh.len[1] = sj.msg[1].len; sh.off[2] = 0; sh.len[2] = 0;
-        }
-        const size_t tlo = T * (size_t)tid / TH, thi = T * (size_t)(tid + 1) / TH;
-        for (size_t t = tlo; t < thi; t++) {
-            const blockval::TxPlan& tx = plan.txs[t];
-            if (tx.check_job < 0) continue;
-            ShaJob& a = bb.h_sha[J + 2 * (size_t)tx.check_job];
-            ShaJob& b = bb.h_sha[J + 2 * (size_t)tx.check_job + 1];
-            a.off[0] = tx.txid_msg[0].off; a.len[0] = tx.txid_msg[0].len; a.off[1] = tx.txid_msg[1].off; a.len[1] = tx.txid_msg[1].len; a.off[2] = 0; a.len[2] = 0;
-            for (int k = 0; k < 3; k++) { b.off[k] = tx.phash_msg[k].off; b.len[k] = tx.phash_msg[k].len; }
-        }
-        stage_fence();
-    });
-    auto t2 = now();
-    // 4. device: digests of every signed message (and the check digests), then one verification batch
-    const size_t words = (J + 31) / 32;
-    if (S) {
-        CK(ctx, cudaMemcpyAsync(bb.d_sha, bb.h_sha, sizeof(ShaJob) * S, cudaMemcpyHostToDevice, ds.stream));
-        sha256_segments_kernel<<<(unsigned)((S + 127) / 128), 128, 0, ds.stream>>>(bb.d_block, bb.d_sha, (uint32_t)S, bb.d_dig);
-        ctx->launches++;
-        CK(ctx, cudaGetLastError());
-    }
-    if (J) {
-        CK(ctx, cudaMemcpyAsync(bb.d_r, bb.h_r, 32 * J, cudaMemcpyHostToDevice, ds.stream));
-        CK(ctx, cudaMemcpyAsync(bb.d_s, bb.h_s, 32 * J, cudaMemcpyHostToDevice, ds.stream));
-        CK(ctx, cudaMemcpyAsync(bb.d_ks, bb.h_ks, 4 * J, cudaMemcpyHostToDevice, ds.stream));
-        if (!all_slots) {
-            CK(ctx, cudaMemcpyAsync(bb.d_qx, bb.h_qx, 32 * J, cudaMemcpyHostToDevice, ds.stream));
-            CK(ctx, cudaMemcpyAsync(bb.d_qy, bb.h_qy, 32 * J, cudaMemcpyHostToDevice, ds.stream));
-        }
-        int rc = launch_verify(ctx, dv, all_slots ? MODE_CACHED : MODE_MIXED, bb.d_ks, bb.d_qx, bb.d_qy, bb.d_dig, bb.d_r, bb.d_s, J, bb.d_mask,
-                               bb.d_off, ds.stream);
-        if (rc) return rc;
-        CK(ctx, cudaMemcpyAsync(bb.h_mask, bb.d_mask, 4 * words, cudaMemcpyDeviceToHost, ds.stream));
-    }
-    if (C) CK(ctx, cudaMemcpyAsync(bb.h_dig, bb.d_dig + 32 * J, 64 * C, cudaMemcpyDeviceToHost, ds.stream));
-    CK(ctx, cudaStreamSynchronize(ds.stream));
-    auto t3 = now();
-    // 5. replay the reference's per-transaction decisions on the results
-    std::vector<uint8_t> sig_valid(J ? J : 1, 0);
-    for (size_t j = 0; j < J; j++) sig_valid[j] = gate_ok[j] && ((bb.h_mask[j >> 5] >> (j & 31)) & 1u);
-    // digests arrive as [txid_0, phash_0, txid_1, phash_1, ...]; decide_block wants two strided views
-    std::vector<uint8_t> txid_d(32 * (C ? C : 1)), phash_d(32 * (C ? C : 1));
-    for (size_t c = 0; c < C; c++) { memcpy(&txid_d[32 * c], bb.h_dig + 64 * c, 32); memcpy(&phash_d[32 * c], bb.h_dig + 64 * c + 32, 32); }
-    std::vector<uint64_t> txid_hash(T + 1, 0);
-    ctx->pool->run([&](int tid) {
-        blockval::decide_range(block, plan, ctx->msp, ctx->policy, ctx->principals, sig_valid.data(), txid_d.data(), phash_d.data(),
-                               T * (size_t)tid / TH, T * (size_t)(tid + 1) / TH, flags, txid_hash.data());
-    });
-    blockval::mark_duplicates(block, plan, txid_hash.data(), flags);
-    auto t4 = now();
-    ctx->block_timing[0] = us(t0, t1); ctx->block_timing[1] = us(t1, t2); ctx->block_timing[2] = us(t2, t3); ctx->block_timing[3] = us(t3, t4);
-    ctx->block_timing[4] = us(t0, t4);
-    return FABGPU_OK;
 }
 
 int fabgpu_block_timing(const fabgpu_ctx* ctx, double out_us[10])

@@ -200,6 +200,17 @@ int fabgpu_msp_configure(fabgpu_ctx* ctx, const uint8_t* id_blob, const uint32_t
                          const uint32_t* mspid_off, const uint8_t* keys_xy, const uint8_t* valid, int n_ids,
                          const int32_t* policy_nodes, int n_nodes, const uint8_t* principal_blob, const uint32_t* principal_off,
                          int n_principals, const char* channel_id);
+/* Two optional refinements of the table fabgpu_msp_configure installed (call them after it; each drains the block slots first):
+ *   _identity_groups: group[i] = de-duplication id of identity i.  The reference de-duplicates a transaction's signers on
+ *       Mspid + certificate digest (common/policies/policy.go:380-386), so two byte-different serializations of ONE certificate
+ *       must share a group; without this call every table entry is its own group.
+ *   _namespace_policies: the endorsement policy of each chaincode namespace (what the plugin dispatcher looks up per namespace a
+ *       transaction writes to, core/committer/txvalidator/v20/plugindispatcher/dispatcher.go:166-221,265-277): ns_root[i] is the
+ *       root node -- an index into the node array given to fabgpu_msp_configure, which may hold several trees -- of namespace i's
+ *       policy.  n_ns = 0 restores "node 0 is the policy of every namespace".  A transaction that needs a namespace without an
+ *       entry is flagged 254 (NOT_VALIDATED): the CPU validator reads the chaincode definition from the ledger. */
+int fabgpu_msp_identity_groups(fabgpu_ctx* ctx, const int32_t* group, int n_ids);
+int fabgpu_namespace_policies(fabgpu_ctx* ctx, const uint8_t* ns_blob, const uint32_t* ns_off, const int32_t* ns_root, int n_ns);
 /* flags[i] receives the validation code of transaction i; *n_tx_out the number of transactions. */
 int fabgpu_validate_block(fabgpu_ctx* ctx, const uint8_t* block, size_t block_len, uint8_t* flags, size_t flags_cap, size_t* n_tx_out);
 /* Same for a caller that already holds Block.Data.Data as separate byte strings (the Go validator does): `blob` is their

@@ -35,6 +35,7 @@ from . import fast
 VALID, NIL_ENVELOPE, BAD_PAYLOAD, BAD_COMMON_HEADER, BAD_CREATOR_SIGNATURE = 0, 1, 2, 3, 4
 INVALID_ENDORSER_TRANSACTION, INVALID_CONFIG_TRANSACTION, UNSUPPORTED_TX_PAYLOAD, BAD_PROPOSAL_TXID, DUPLICATE_TXID = 5, 6, 7, 8, 9
 ENDORSEMENT_POLICY_FAILURE, UNKNOWN_TX_TYPE, TARGET_CHAIN_NOT_FOUND = 10, 13, 14
+BAD_HEADER_EXTENSION, BAD_CHANNEL_HEADER, BAD_RESPONSE_PAYLOAD, BAD_RWSET, ILLEGAL_WRITESET, INVALID_WRITESET, INVALID_CHAINCODE = 19, 20, 21, 22, 23, 24, 25
 NOT_VALIDATED, INVALID_OTHER_REASON = 254, 255
 
 S_BLOCK = {1: ("header", "bytes"), 2: ("data", "bytes"), 3: ("metadata", "bytes")}
@@ -50,16 +51,50 @@ S_CAP = {1: ("chaincode_proposal_payload", "bytes"), 2: ("action", "bytes")}
 S_CEA = {1: ("proposal_response_payload", "bytes"), 2: ("endorsements", "rep_bytes")}
 S_ENDORSEMENT = {1: ("endorser", "bytes"), 2: ("signature", "bytes")}
 S_PRP = {1: ("proposal_hash", "bytes"), 2: ("extension", "bytes")}
+# the plugin dispatcher's view (core/committer/txvalidator/v20/plugindispatcher/dispatcher.go:102-221)
+S_CHDR_EXT = {1: ("type", "uint"), 4: ("channel_id", "bytes"), 5: ("tx_id", "bytes"), 6: ("epoch", "uint"), 7: ("extension", "bytes")}
+S_CC_HDR_EXT = {2: ("chaincode_id", "bytes")}                                    # peer.ChaincodeHeaderExtension
+S_CCID = {1: ("path", "bytes"), 2: ("name", "bytes"), 3: ("version", "bytes")}   # peer.ChaincodeID
+S_CCACTION = {1: ("results", "bytes"), 2: ("events", "bytes"), 3: ("response", "bytes"), 4: ("chaincode_id", "bytes")}   # peer.ChaincodeAction
+S_CCEVENT = {1: ("chaincode_id", "bytes"), 2: ("tx_id", "bytes"), 3: ("event_name", "bytes"), 4: ("payload", "bytes")}
+S_TXRWSET = {1: ("data_model", "uint"), 2: ("ns_rwset", "rep_bytes")}            # rwset.TxReadWriteSet
+S_NSRWSET = {1: ("namespace", "bytes"), 2: ("rwset", "bytes"), 3: ("collection_hashed_rwset", "rep_bytes")}
+S_KVRWSET = {1: ("reads", "rep_bytes"), 2: ("range_queries_info", "rep_bytes"), 3: ("writes", "rep_bytes"), 4: ("metadata_writes", "rep_bytes")}
+S_COLLHASHED = {1: ("collection_name", "bytes"), 2: ("hashed_rwset", "bytes"), 3: ("pvt_rwset_hash", "bytes")}
+S_HASHEDRWSET = {1: ("hashed_reads", "rep_bytes"), 2: ("hashed_writes", "rep_bytes"), 3: ("metadata_writes", "rep_bytes")}
+
+
+def identity_id(serialized: bytes, mspid: str):
+    """The IdentityIdentifier the reference de-duplicates on (common/policies/policy.go:380-386: Mspid + Id, with
+    Id = hex(SHA-256(certificate DER)), msp/identities.go:55-76): two byte-different serializations of ONE certificate (PEM line
+    wrapping, trailing whitespace) are the same identity.  Falls back to the serialized bytes when no PEM block parses."""
+    import base64
+    import re
+    try:
+        sid = pb.parse(bytes(serialized), {1: ("mspid", "bytes"), 2: ("id_bytes", "bytes")})
+        m = re.search(rb"-----BEGIN CERTIFICATE-----(.*?)-----END CERTIFICATE-----", sid["id_bytes"] or b"", re.S)
+        if m:
+            der = base64.b64decode(b"".join(m.group(1).split()), validate=False)
+            return (mspid, hashlib.sha256(der).hexdigest())
+    except Exception:
+        pass
+    return (mspid, bytes(serialized).hex())
 
 
 class Msp:
-    """identities: list of (serialized: bytes, mspid: str, key_xy: 64 bytes, valid: bool)."""
+    """identities: list of (serialized: bytes, mspid: str, key_xy: 64 bytes, valid: bool).  deserialize -> (dedup id, mspid, xy, valid).
+    `known` (optional): the serialized identities the DEVICE's table holds; an identity outside it makes the device hand the
+    transaction back (NOT_VALIDATED) -- see validate_tx."""
 
-    def __init__(self, identities):
-        self.by_bytes = {bytes(ser): (i, mspid, bytes(xy), bool(valid)) for i, (ser, mspid, xy, valid) in enumerate(identities)}
+    def __init__(self, identities, known=None):
+        self.by_bytes = {bytes(ser): (identity_id(ser, mspid), mspid, bytes(xy), bool(valid)) for (ser, mspid, xy, valid) in identities}
+        self.known = None if known is None else {bytes(k) for k in known}
 
     def deserialize(self, ser):
         return self.by_bytes.get(bytes(ser))
+
+    def on_device(self, ser):
+        return self.known is None or bytes(ser) in self.known
 
 
 def _verify(xy: bytes, msg: bytes, sig: bytes) -> bool:
@@ -99,8 +134,51 @@ def evaluate_policy(nodes, principals, identities_mspid):
     return run(0, [False] * len(identities_mspid))
 
 
-def validate_tx(env_bytes, msp: Msp, channel: str, nodes, principals, verify=_verify_fast):
-    """One transaction -> (code, txid).  Mirrors ValidateTx + ValidateTransaction + the VSCC signature-policy check."""
+def evaluate_policy_at(nodes, principals, identities_mspid, root):
+    """evaluate_policy with the tree rooted at node `root` (several policies share one node array)."""
+    def run(idx, used):
+        t, n, first, cnt = [int(x) for x in nodes[idx]]
+        if t == 0:
+            verified = 0
+            for c in range(first, first + cnt):
+                _used = list(used)
+                if run(c, _used):
+                    verified += 1
+                    used[:] = _used
+            return verified >= n
+        want = principals[n]
+        for i, mspid in enumerate(identities_mspid):
+            if used[i] or mspid != want:
+                continue
+            used[i] = True
+            return True
+        return False
+    return run(int(root), [False] * len(identities_mspid))
+
+
+def written_namespaces(results: bytes):
+    """rwsetutil.TxRwSet.FromProtoBytes + txWritesToNamespace (dispatcher.go:121-124,166-179,278-300): the namespaces of the
+    read/write set in order, each with "writes something"; raises PbError where proto.Unmarshal of a message on that path would.
+    (The KVRead / KVWrite entries themselves are not re-parsed: restated scope = what decides the namespace set.)"""
+    out = []
+    tx = pb.parse(results or b"", S_TXRWSET)
+    for nsb in tx["ns_rwset"]:
+        ns = pb.parse(nsb, S_NSRWSET)
+        kv = pb.parse(ns["rwset"] or b"", S_KVRWSET)
+        writes = len(kv["writes"]) > 0 or len(kv["metadata_writes"]) > 0
+        for cb in ns["collection_hashed_rwset"]:
+            c = pb.parse(cb, S_COLLHASHED)
+            h = pb.parse(c["hashed_rwset"] or b"", S_HASHEDRWSET)
+            writes = writes or len(h["hashed_writes"]) > 0 or len(h["metadata_writes"]) > 0
+        out.append(((ns["namespace"] or b"").decode("utf-8", "replace"), writes))
+    return out
+
+
+def validate_tx(env_bytes, msp: Msp, channel: str, nodes, principals, verify=_verify_fast, policies=None):
+    """One transaction -> (code, txid).  Mirrors ValidateTx + ValidateTransaction + the plugin dispatcher + the VSCC signature-policy
+    check.  policies: {namespace: root node index} -- the endorsement policy of each chaincode (what GetInfoForValidate returns,
+    dispatcher.go:265-277); None = one policy (root 0) for every namespace.  A namespace without an entry, like an identity the
+    device table does not hold (Msp.known), cannot be decided by the device: NOT_VALIDATED at the point where it is needed."""
     # zero-length data unmarshals to an empty Envelope (protoutil.GetEnvelopeFromBlock): no header -> BAD_COMMON_HEADER
     try:
         env = pb.parse(env_bytes, S_ENVELOPE)
@@ -115,7 +193,7 @@ def validate_tx(env_bytes, msp: Msp, channel: str, nodes, principals, verify=_ve
         if payload["header"] is None:
             raise pb.PbError("nil header")
         hdr = pb.parse(payload["header"], S_HEADER)
-        chdr = pb.parse(hdr["channel_header"] or b"", S_CHDR)
+        chdr = pb.parse(hdr["channel_header"] or b"", S_CHDR_EXT)
         shdr = pb.parse(hdr["signature_header"] or b"", S_SHDR)
         if (chdr["type"] or 0) not in (1, 2, 3):
             raise pb.PbError("invalid header type")
@@ -130,6 +208,8 @@ def validate_tx(env_bytes, msp: Msp, channel: str, nodes, principals, verify=_ve
     # checkSignatureFromCreator (msgvalidation.go:26-64)
     if not env["signature"] or not env["payload"]:
         return BAD_CREATOR_SIGNATURE, ""              # "nil arguments"
+    if not msp.on_device(shdr["creator"]):
+        return NOT_VALIDATED, ""                      # the device cannot deserialize / validate a certificate it was not given
     ident = msp.deserialize(shdr["creator"])
     if ident is None or not ident[3]:
         return BAD_CREATOR_SIGNATURE, ""              # MSP error / certificate not valid
@@ -169,20 +249,73 @@ def validate_tx(env_bytes, msp: Msp, channel: str, nodes, principals, verify=_ve
     # ---- ValidateTx ----
     if (chdr["channel_id"] or b"").decode("utf-8", "replace") != channel:
         return TARGET_CHAIN_NOT_FOUND, ""
+    # ---- plugin dispatcher (plugindispatcher/dispatcher.go:102-221) ----
+    try:                                               # nested messages are parsed with their parent (proto.Unmarshal)
+        hext = pb.parse(chdr["extension"] or b"", S_CC_HDR_EXT)
+        h_ccid = pb.parse(hext["chaincode_id"], S_CCID) if hext["chaincode_id"] is not None else None
+    except pb.PbError:
+        return BAD_HEADER_EXTENSION, ""
+    try:                                               # GetActionFromEnvelope -> GetPayloads (protoutil/txutils.go:20-45)
+        if cea["proposal_response_payload"] is None:
+            raise pb.PbError("no payload in ChaincodeActionPayload")
+        if prp["extension"] is None:
+            raise pb.PbError("response payload is missing extension")
+        cca = pb.parse(prp["extension"], S_CCACTION)
+        r_ccid = pb.parse(cca["chaincode_id"], S_CCID) if cca["chaincode_id"] is not None else None
+    except pb.PbError:
+        return BAD_RESPONSE_PAYLOAD, ""
+    try:
+        ns_list = written_namespaces(cca["results"])
+    except pb.PbError:
+        return BAD_RWSET, ""
+    if h_ccid is None or r_ccid is None:
+        return INVALID_OTHER_REASON, ""
+    ccid = (h_ccid["name"] or b"").decode("utf-8", "replace")
+    if ccid == "" or ccid != (r_ccid["name"] or b"").decode("utf-8", "replace") or not (r_ccid["version"] or b""):
+        return INVALID_CHAINCODE, ""
+    if cca["events"] is not None:
+        try:
+            ev = pb.parse(cca["events"], S_CCEVENT)
+        except pb.PbError:
+            return INVALID_OTHER_REASON, ""
+        if (ev["chaincode_id"] or b"").decode("utf-8", "replace") != ccid:
+            return INVALID_OTHER_REASON, ""
+    wr = [ccid]
+    seen_ns = set()
+    for name, writes in ns_list:
+        if name in seen_ns:
+            return ILLEGAL_WRITESET, ""
+        seen_ns.add(name)
+        if writes and name not in wr:
+            wr.append(name)
     # ---- VSCC: endorsement policy over the signature set (validator_keylevel.go:243-259, policy.go:365-402) ----
+    # One signature set per transaction; the reference rebuilds and re-verifies it for every namespace it validates -- the
+    # verdicts cannot differ, so it is evaluated once here and every namespace's policy runs over the same identities.
     try:
         ends = [pb.parse(e, S_ENDORSEMENT) for e in cea["endorsements"]]
     except pb.PbError:
         return INVALID_OTHER_REASON, ""
+    roots = []
+    for name in wr:
+        if policies is None:
+            roots.append(0)
+        elif name in policies:
+            roots.append(policies[name])
+        else:
+            return NOT_VALIDATED, ""                    # no chaincode definition on the device: the CPU validator looks it up in the ledger
     seen, signer_msps = set(), []
     prp_bytes = cea["proposal_response_payload"] or b""
     for e in ends:
         endorser = e["endorser"] or b""
+        if not (e["signature"] or b""):
+            continue                                    # can never verify, whoever signed (and needs no identity)
+        if not msp.on_device(endorser):
+            return NOT_VALIDATED, ""
         idn = msp.deserialize(endorser)
         if idn is None:
             continue                                    # invalid identity: skipped
         if idn[0] in seen:
-            continue                                    # de-duplicated before any signature work
+            continue                                    # de-duplicated (by Mspid + Id) before any signature work
         if not verify(idn[2], prp_bytes + endorser, e["signature"] or b""):
             continue                                    # signature invalid: identity dropped
         seen.add(idn[0])
@@ -190,20 +323,22 @@ def validate_tx(env_bytes, msp: Msp, channel: str, nodes, principals, verify=_ve
             signer_msps.append(idn[1])
         else:
             signer_msps.append(None)
-    if not evaluate_policy(nodes, principals, signer_msps):
-        return ENDORSEMENT_POLICY_FAILURE, ""
+    for root in roots:
+        if not evaluate_policy_at(nodes, principals, signer_msps, root):
+            return ENDORSEMENT_POLICY_FAILURE, ""
     return VALID, txid
 
 
-def validate_block(block_bytes, identities, channel, nodes, principals, verify=_verify_fast):
-    """-> uint8 flags (TRANSACTIONS_FILTER), or raises for config transactions (outside the restated scope)."""
-    msp = Msp(identities)
+def validate_block(block_bytes, identities, channel, nodes, principals, verify=_verify_fast, policies=None, known=None):
+    """-> uint8 flags (TRANSACTIONS_FILTER), or raises for config transactions (outside the restated scope).
+    policies / known: see validate_tx and Msp."""
+    msp = Msp(identities, known)
     blk = pb.parse(block_bytes, S_BLOCK)
     data = pb.parse(blk["data"] or b"", S_BLOCKDATA)["data"]
     flags = np.full(len(data), NOT_VALIDATED, np.uint8)
     txids = [""] * len(data)
     for i, d in enumerate(data):
-        code, txid = validate_tx(d, msp, channel, nodes, principals, verify)
+        code, txid = validate_tx(d, msp, channel, nodes, principals, verify, policies)
         if code is None:
             raise NotImplementedError("config transaction at index %d" % i)
         flags[i] = code

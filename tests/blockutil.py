@@ -28,22 +28,6 @@ def fault_map(n_tx, stride=3, start=2):
     return faults
 
 
-_BV = None
-
-
-def bv_lib():
-    global _BV
-    if _BV is None:
-        d = os.path.join(ROOT, "tests", "host_sim")
-        so, src = os.path.join(d, "libblockval_host.so"), os.path.join(d, "blockval_host.cpp")
-        deps = [src, os.path.join(ROOT, "fabric-mod_b200", "csrc", "blockval.cpp"), os.path.join(ROOT, "fabric-mod_b200", "csrc", "blockval.hpp")]
-        if not os.path.exists(so) or any(os.path.getmtime(so) < os.path.getmtime(f) for f in deps):
-            subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", so, src])
-        _BV = ctypes.CDLL(so)
-        _BV.bv_new.restype = ctypes.c_void_p
-    return _BV
-
-
 def _blob(items):
     off = np.zeros(len(items) + 1, np.uint32)
     off[1:] = np.cumsum([len(x) for x in items])
@@ -52,51 +36,6 @@ def _blob(items):
 
 def _p(a):
     return a.ctypes.data_as(ctypes.c_void_p)
-
-
-def host_logic_flags(block, identities, channel, nodes, principals):
-    """Product host logic (plan_block + decide_block) driven by oracle verdicts and hashlib digests: no GPU involved."""
-    L = bv_lib()
-    idb, ido = _blob([bytes(i[0]) for i in identities])
-    mb, mo = _blob([i[1].encode() for i in identities])
-    keys = np.ascontiguousarray(np.frombuffer(b"".join(bytes(i[2]) for i in identities), np.uint8))
-    valid = np.array([1 if i[3] else 0 for i in identities], np.uint8)
-    nodes = np.ascontiguousarray(nodes, np.int32)
-    pbb, pbo = _blob([p.encode() for p in principals])
-    h = ctypes.c_void_p(L.bv_new(_p(idb), _p(ido), _p(mb), _p(mo), _p(keys), _p(valid), len(identities), _p(nodes), nodes.shape[0], _p(pbb), _p(pbo),
-                                 len(principals), channel.encode()))
-    barr = np.frombuffer(block, np.uint8)
-    nj, nc = ctypes.c_int(0), ctypes.c_int(0)
-    T = L.bv_plan(h, _p(barr), ctypes.c_size_t(len(block)), ctypes.byref(nj), ctypes.byref(nc))
-    assert T >= 0
-    J, C = nj.value, nc.value
-    # signature verdicts from the oracle
-    segs = (ctypes.c_uint32 * 10)()
-    ident = ctypes.c_int(0)
-    key_idx, digs, sigs = [], [], []
-    for j in range(J):
-        L.bv_job(h, j, ctypes.byref(ident), segs)
-        key_idx.append(ident.value)
-        digs.append(hashlib.sha256(block[segs[0]:segs[0] + segs[1]] + block[segs[2]:segs[2] + segs[3]]).digest())
-        sigs.append(block[segs[4]:segs[4] + segs[5]])
-    soff = np.zeros(J + 1, np.uint32); soff[1:] = np.cumsum([len(s) for s in sigs])
-    if J:
-        st = fast.verify_batch(keys.reshape(-1, 64), np.array(key_idx, np.int32), np.frombuffer(b"".join(digs), np.uint8),
-                               (np.arange(J + 1) * 32).astype(np.uint32), np.frombuffer(b"".join(sigs), np.uint8), soff, nthreads=4)
-        sig_valid = (st == o.VALID).astype(np.uint8)
-    else:
-        sig_valid = np.zeros(1, np.uint8)
-    txd = np.zeros((max(C, 1), 32), np.uint8); phd = np.zeros((max(C, 1), 32), np.uint8)
-    for t in range(T):
-        c = L.bv_check(h, t, segs)
-        if c < 0:
-            continue
-        txd[c] = np.frombuffer(hashlib.sha256(block[segs[0]:segs[0] + segs[1]] + block[segs[2]:segs[2] + segs[3]]).digest(), np.uint8)
-        phd[c] = np.frombuffer(hashlib.sha256(block[segs[4]:segs[4] + segs[5]] + block[segs[6]:segs[6] + segs[7]] + block[segs[8]:segs[8] + segs[9]]).digest(), np.uint8)
-    flags = np.full(max(T, 1), 254, np.uint8)
-    L.bv_decide(h, _p(sig_valid), _p(txd), _p(phd), _p(flags))
-    L.bv_free(h)
-    return flags[:T], J
 
 
 _BD = None
@@ -115,9 +54,11 @@ def bd_lib():
     return _BD
 
 
-def device_logic_flags(env_blob, env_off, identities, channel, nodes, principals):
-    """The device-side block logic (blockdev.cuh) executed on the host, driven by oracle verdicts and hashlib digests."""
+def device_logic_flags(env_blob, env_off, identities, channel, nodes, principals, policies=None):
+    """The device-side block logic (blockdev.cuh) executed on the host, driven by oracle verdicts and hashlib digests.
+    policies: {namespace: root node} (None: one policy for every namespace)."""
     from oracle import goasn1
+    from util import pkg
     L = bd_lib()
     idb, ido = _blob([bytes(i[0]) for i in identities])
     mb, mo = _blob([i[1].encode() for i in identities])
@@ -127,6 +68,13 @@ def device_logic_flags(env_blob, env_off, identities, channel, nodes, principals
     pbb, pbo = _blob([p.encode() for p in principals])
     h = ctypes.c_void_p(L.bd_new(_p(idb), _p(ido), _p(mb), _p(mo), _p(valid), len(identities), _p(nodes), nodes.shape[0], _p(pbb), _p(pbo),
                                  len(principals), channel.encode()))
+    groups = np.ascontiguousarray(pkg().binding.identity_groups(identities), np.int32)      # product code: Mspid + certificate groups
+    L.bd_groups(h, _p(groups), len(identities))
+    if policies:
+        names = sorted(policies)
+        nb, no = _blob([n.encode() for n in names])
+        roots = np.array([policies[n] for n in names], np.int32)
+        L.bd_namespaces(h, _p(nb), _p(no), _p(roots), len(names))
     blob = np.frombuffer(env_blob, np.uint8) if len(env_blob) else np.zeros(1, np.uint8)
     env_off = np.ascontiguousarray(env_off, np.uint32)
     T = env_off.shape[0] - 1

@@ -13,11 +13,13 @@ using namespace fabgpu::bdev;
 struct H {
     std::vector<uint8_t> id_blob; std::vector<uint32_t> id_off; std::vector<int32_t> key_slot, msp_code, ht_idx, nodes, principal_code;
     std::vector<uint8_t> valid; std::vector<uint64_t> ht_hash; std::string channel;
+    std::vector<int32_t> group, ns_root; std::vector<uint8_t> ns_blob; std::vector<uint32_t> ns_off;
     std::vector<uint8_t> block; std::vector<uint32_t> env_off;
     std::vector<TxDev> txs; std::vector<RawJob> raw; std::vector<ShaJobD> sha; std::vector<uint8_t> r, s, gate_ok; std::vector<int32_t> jks, jid;
     uint32_t T = 0, J_cap = 0, n_end = 0;
     MspDev msp() const {
         MspDev m; m.id_blob = id_blob.data(); m.id_off = id_off.data(); m.key_slot = key_slot.data(); m.valid = valid.data(); m.msp_code = msp_code.data();
+        m.group = group.empty() ? nullptr : group.data();
         m.keys_xy = nullptr; m.ht_hash = ht_hash.data(); m.ht_idx = ht_idx.data(); m.ht_size = (uint32_t)ht_hash.size(); m.n_ids = (int32_t)valid.size(); return m;
     }
 };
@@ -47,13 +49,21 @@ void* bd_new(const uint8_t* id_blob, const uint32_t* id_off, const uint8_t* mspi
     return h;
 }
 void bd_free(void* p) { delete (H*)p; }
+// de-duplication groups of the identities (Mspid + certificate) and the namespace -> policy root table
+void bd_groups(void* p, const int32_t* group, int n_ids) { H* h = (H*)p; h->group.assign(group, group + n_ids); }
+void bd_namespaces(void* p, const uint8_t* ns_blob, const uint32_t* ns_off, const int32_t* ns_root, int n_ns)
+{
+    H* h = (H*)p;
+    h->ns_blob.assign(ns_blob, ns_blob + ns_off[n_ns]); h->ns_off.assign(ns_off, ns_off + n_ns + 1); h->ns_root.assign(ns_root, ns_root + n_ns);
+    if (h->ns_blob.empty()) h->ns_blob.push_back(0);
+}
 
 // plans every transaction; returns the number of endorsement jobs; J = T + n_end signature jobs, 2T check digests after J_cap
 int bd_plan(void* p, const uint8_t* blob, const uint32_t* env_off, int n_env)
 {
     H* h = (H*)p;
     h->block.assign(blob, blob + env_off[n_env]); h->env_off.assign(env_off, env_off + n_env + 1);
-    h->T = (uint32_t)n_env; h->J_cap = h->T * (1 + BD_MAX_ENDS); h->n_end = 0;
+    h->T = (uint32_t)n_env; h->J_cap = h->T * (1 + BD_ENDS_HINT); h->n_end = 0;
     h->txs.assign(h->T, TxDev()); h->sha.assign(h->J_cap + 2 * h->T, ShaJobD());
     { RawJob dead; dead.ident.off = dead.ident.len = dead.sig.off = dead.sig.len = 0; dead.tx = 0xffffffffu; dead.k = -1; h->raw.assign(h->J_cap, dead); }
     h->r.assign(32 * (size_t)h->J_cap, 0); h->s.assign(32 * (size_t)h->J_cap, 0); h->gate_ok.assign(h->J_cap, 0); h->jks.assign(h->J_cap, -1); h->jid.assign(h->J_cap, -1);
@@ -88,10 +98,11 @@ void bd_decide(void* p, const uint8_t* sig_ok, const uint8_t* check_digests, uin
     std::vector<uint8_t> dig(32 * (size_t)(h->J_cap + 2 * h->T), 0);
     memcpy(&dig[32 * (size_t)h->J_cap], check_digests, 64 * (size_t)h->T);
     PolicyDev pol; pol.nodes = h->nodes.data(); pol.n_nodes = (int32_t)h->nodes.size() / 4; pol.principal_code = h->principal_code.data(); pol.n_principals = (int32_t)h->principal_code.size();
+    pol.ns_blob = h->ns_blob.data(); pol.ns_off = h->ns_off.data(); pol.ns_root = h->ns_root.data(); pol.n_ns = (int32_t)h->ns_root.size();
     const MspDev m = h->msp();
     std::vector<uint64_t> th(h->T, 0);
     for (uint32_t t = 0; t < h->T; t++)
-        flags[t] = decide_tx(h->block.data(), h->txs[t], t, m, pol, [&](uint32_t j) { return sig_ok[j] != 0; }, dig.data(), h->J_cap, &th[t]);
+        flags[t] = decide_tx(h->block.data(), h->txs[t], t, m, pol, [&](uint32_t j) { return sig_ok[j] != 0; }, h->jid.data(), dig.data(), h->J_cap, &th[t]);
     // duplicate pass as the shim does it
     std::multimap<uint64_t, uint32_t> seen;
     for (uint32_t t = 0; t < h->T; t++) {

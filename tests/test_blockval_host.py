@@ -1,73 +1,12 @@
-"""Host logic of the block pre-pass (fabric-mod_b200/csrc/blockval.cpp) against the oracle's restatement of the reference's
-validator (oracle/blockval.py), on the CPU: every fault class of tools/blockgen.py, policy-evaluator semantics, duplicates."""
+"""The device-side block logic (fabric-mod_b200/csrc/blockdev.cuh: walk, dispatcher checks, gates, decisions), compiled for the host,
+against the oracle's restatement of the reference's validator (oracle/blockval.py), on the CPU: every fault class of
+tools/blockgen.py, per-chaincode policies, policy-evaluator semantics, de-duplication, duplicates, structural corner cases."""
 import numpy as np
 
 from oracle import blockval as ob
 from tools import blockgen
 from tools import fabricpb as pb
 import blockutil
-
-
-def test_fault_classes_match_oracle():
-    net = blockgen.Network()
-    faults = blockutil.fault_map(70)
-    assert set(faults.values()) == set(blockgen.FAULTS)
-    blk, info = blockgen.build_block(net, 70, 3, faults, seed=11, nthreads=2)
-    ids = blockutil.identities_of(net)
-    exp = ob.validate_block(blk, ids, net.channel, net.policy_n_of(3), net.principals)
-    got, njobs = blockutil.host_logic_flags(blk, ids, net.channel, net.policy_n_of(3), net.principals)
-    assert got.tolist() == exp.tolist()
-    seen = set(int(x) for x in exp)
-    assert {ob.VALID, ob.BAD_PAYLOAD, ob.BAD_COMMON_HEADER, ob.BAD_CREATOR_SIGNATURE, ob.INVALID_ENDORSER_TRANSACTION, ob.UNSUPPORTED_TX_PAYLOAD,
-            ob.BAD_PROPOSAL_TXID, ob.DUPLICATE_TXID, ob.ENDORSEMENT_POLICY_FAILURE, ob.TARGET_CHAIN_NOT_FOUND} <= seen
-    for t in range(70):
-        if t not in faults:
-            assert exp[t] == ob.VALID, t
-    assert exp[[t for t, f in faults.items() if f == "dup_txid"][0]] == ob.DUPLICATE_TXID
-
-
-def test_policy_thresholds_and_dedup():
-    # common/policies/policy_test.go:255-288 (two identical SignedData => one identity) and cauthdsl N-out-of semantics
-    net = blockgen.Network()
-    ids = blockutil.identities_of(net)
-    blk, _ = blockgen.build_block(net, 12, 3, {3: "dup_endorser", 5: "bad_endorsement_sig", 7: "unknown_endorser"}, seed=3, nthreads=2)
-    for n, expect_fail in ((2, []), (3, [3, 5, 7]), (4, list(range(12)))):
-        exp = ob.validate_block(blk, ids, net.channel, net.policy_n_of(n), net.principals)
-        got, _ = blockutil.host_logic_flags(blk, ids, net.channel, net.policy_n_of(n), net.principals)
-        assert got.tolist() == exp.tolist()
-        assert [t for t in range(12) if exp[t] == ob.ENDORSEMENT_POLICY_FAILURE] == expect_fail
-    # nested policy: AND(Org1, OR(Org2, Org3)) = NOutOf(2, [SignedBy 0, NOutOf(1, [SignedBy 1, SignedBy 2])])
-    nodes = np.array([(0, 2, 1, 2), (1, 0, 0, 0), (0, 1, 3, 2), (1, 1, 0, 0), (1, 2, 0, 0)], np.int32)
-    exp = ob.validate_block(blk, ids, net.channel, nodes, net.principals)
-    got, _ = blockutil.host_logic_flags(blk, ids, net.channel, nodes, net.principals)
-    assert got.tolist() == exp.tolist() and ob.VALID in exp and ob.ENDORSEMENT_POLICY_FAILURE in exp
-
-
-def test_structural_corner_cases():
-    net = blockgen.Network()
-    ids = blockutil.identities_of(net)
-    blk, _ = blockgen.build_block(net, 6, 3, {}, seed=5, nthreads=2)
-    envs = pb.parse(pb.parse(blk, ob.S_BLOCK)["data"], ob.S_BLOCKDATA)["data"]
-    good = envs[0]
-    variants = [
-        good,
-        b"",                                              # empty envelope bytes
-        b"\x0a\x05abc",                                   # truncated length-delimited field
-        pb.f_uint(1, 5),                                  # payload field with varint wire type
-        good + pb.f_bytes(9, b"unknown field is skipped"),
-        pb.f_bytes(1, b""),                               # empty payload
-        envs[1][: len(envs[1]) // 2],                     # cut in the middle
-        pb.f_bytes(2, b"sig-only"),
-    ]
-    blk2 = pb.block(9, variants)
-    exp = ob.validate_block(blk2, ids, net.channel, net.policy_n_of(3), net.principals)
-    got, _ = blockutil.host_logic_flags(blk2, ids, net.channel, net.policy_n_of(3), net.principals)
-    assert got.tolist() == exp.tolist()
-    assert exp[0] == ob.VALID and exp[4] == ob.DUPLICATE_TXID       # same transaction + an unknown field: parses, same tx id
-    assert exp[1] == ob.BAD_COMMON_HEADER and exp[5] == ob.BAD_COMMON_HEADER
-    # empty block
-    blk3 = pb.block(10, [])
-    assert blockutil.host_logic_flags(blk3, ids, net.channel, net.policy_n_of(3), net.principals)[0].tolist() == []
 
 
 # ---- the device-side implementation of the same logic (blockdev.cuh), executed on the host ---------------------------------
@@ -78,18 +17,67 @@ def _envs(blk):
     return b"".join(envs), off
 
 
+def _known(ids):
+    return [i[0] for i in ids]
+
+
 def test_device_logic_fault_classes_match_oracle():
     net = blockgen.Network()
-    faults = blockutil.fault_map(70)
-    blk, info = blockgen.build_block(net, 70, 3, faults, seed=11, nthreads=2)
+    n = 3 * len(blockgen.FAULTS) + 4
+    faults = blockutil.fault_map(n)
+    assert set(faults.values()) == set(blockgen.FAULTS)
+    blk, info = blockgen.build_block(net, n, 3, faults, seed=11, nthreads=2)
     ids = blockutil.identities_of(net)
-    for n in (2, 3, 4):
-        exp = ob.validate_block(blk, ids, net.channel, net.policy_n_of(n), net.principals)
-        got = blockutil.device_logic_flags(info["env_blob"], info["env_off"], ids, net.channel, net.policy_n_of(n), net.principals)
-        assert got.tolist() == exp.tolist(), n
+    for k in (2, 3, 4):
+        exp = ob.validate_block(blk, ids, net.channel, net.policy_n_of(k), net.principals, known=_known(ids))
+        got = blockutil.device_logic_flags(info["env_blob"], info["env_off"], ids, net.channel, net.policy_n_of(k), net.principals)
+        assert got.tolist() == exp.tolist(), k
     nodes = np.array([(0, 2, 1, 2), (1, 0, 0, 0), (0, 1, 3, 2), (1, 1, 0, 0), (1, 2, 0, 0)], np.int32)
-    exp = ob.validate_block(blk, ids, net.channel, nodes, net.principals)
+    exp = ob.validate_block(blk, ids, net.channel, nodes, net.principals, known=_known(ids))
     assert blockutil.device_logic_flags(info["env_blob"], info["env_off"], ids, net.channel, nodes, net.principals).tolist() == exp.tolist()
+    exp3 = ob.validate_block(blk, ids, net.channel, net.policy_n_of(3), net.principals, known=_known(ids))
+    assert exp3[[t for t, f in faults.items() if f == "dup_txid"][0]] == ob.DUPLICATE_TXID
+    for t in range(n):
+        if t not in faults:
+            assert exp3[t] == ob.VALID, t
+
+
+def test_device_logic_per_chaincode_policies():
+    """One policy per namespace (plugindispatcher/dispatcher.go:166-221): writes to a second chaincode bring its policy in, reads do
+    not; namespaces / identities the device table lacks -> NOT_VALIDATED; signers de-duplicate on Mspid + certificate."""
+    net = blockgen.Network()
+    n = 3 * len(blockgen.FAULTS) + 4
+    faults = blockutil.fault_map(n)
+    blk, info = blockgen.build_block(net, n, 3, faults, seed=11, nthreads=2)
+    ids = blockutil.identities_of(net)
+    for k in (2, 3):
+        nodes, pol = net.policies_for(k)
+        exp = ob.validate_block(blk, ids, net.channel, nodes, net.principals, policies=pol, known=_known(ids))
+        got = blockutil.device_logic_flags(info["env_blob"], info["env_off"], ids, net.channel, nodes, net.principals, policies=pol)
+        assert got.tolist() == exp.tolist(), k
+        byf = {f: int(exp[t]) for t, f in faults.items()}
+        assert byf["reads_strict_namespace"] == ob.VALID and byf["writes_unknown_namespace"] == ob.NOT_VALIDATED
+        assert byf["unknown_endorser"] == ob.NOT_VALIDATED and byf["unknown_creator"] == ob.NOT_VALIDATED and byf["many_endorsements"] == ob.VALID
+        assert byf["writes_strict_namespace"] == (ob.ENDORSEMENT_POLICY_FAILURE if k == 3 else ob.VALID)      # 3 endorsements: 4-of-4 fails, 3-of-4 holds
+        assert byf["same_cert_two_encodings"] == (ob.ENDORSEMENT_POLICY_FAILURE if k == 3 else ob.VALID)
+        assert {ob.BAD_HEADER_EXTENSION, ob.BAD_RESPONSE_PAYLOAD, ob.BAD_RWSET, ob.ILLEGAL_WRITESET, ob.INVALID_CHAINCODE} <= set(exp.tolist())
+    # the reference itself (every identity known to the MSP, no device in the picture) gives a verdict where the device abstains:
+    # an unknown creator is a BAD_CREATOR_SIGNATURE there
+    ref = ob.validate_block(blk, ids, net.channel, nodes, net.principals, policies=pol)
+    t = [t for t, f in faults.items() if f == "unknown_creator"][0]
+    assert ref[t] == ob.BAD_CREATOR_SIGNATURE and exp[t] == ob.NOT_VALIDATED
+
+
+def test_policy_thresholds_and_dedup():
+    # common/policies/policy_test.go:255-288 (two identical SignedData => one identity) and cauthdsl N-out-of semantics
+    net = blockgen.Network()
+    ids = blockutil.identities_of(net)
+    blk, info = blockgen.build_block(net, 12, 3, {3: "dup_endorser", 5: "bad_endorsement_sig", 7: "same_cert_two_encodings"}, seed=3, nthreads=2)
+    for k, expect_fail in ((2, []), (3, [3, 5, 7]), (4, list(range(12)))):
+        exp = ob.validate_block(blk, ids, net.channel, net.policy_n_of(k), net.principals, known=_known(ids))
+        got = blockutil.device_logic_flags(info["env_blob"], info["env_off"], ids, net.channel, net.policy_n_of(k), net.principals)
+        assert got.tolist() == exp.tolist()
+        assert [t for t in range(12) if exp[t] == ob.ENDORSEMENT_POLICY_FAILURE] == expect_fail
 
 
 def test_device_logic_structural_corner_cases():
@@ -101,7 +89,9 @@ def test_device_logic_structural_corner_cases():
     variants = [good, b"", b"\x0a\x05abc", pb.f_uint(1, 5), good + pb.f_bytes(9, b"unknown field is skipped"), pb.f_bytes(1, b""),
                 envs[1][: len(envs[1]) // 2], pb.f_bytes(2, b"sig-only"), envs[2], envs[3]]
     blk2 = pb.block(9, variants)
-    exp = ob.validate_block(blk2, ids, net.channel, net.policy_n_of(3), net.principals)
+    exp = ob.validate_block(blk2, ids, net.channel, net.policy_n_of(3), net.principals, known=_known(ids))
+    assert exp[0] == ob.VALID and exp[4] == ob.DUPLICATE_TXID       # same transaction + an unknown field: parses, same tx id
+    assert exp[1] == ob.BAD_COMMON_HEADER and exp[5] == ob.BAD_COMMON_HEADER
     blob, off = _envs(blk2)
     assert blockutil.device_logic_flags(blob, off, ids, net.channel, net.policy_n_of(3), net.principals).tolist() == exp.tolist()
     assert blockutil.device_logic_flags(b"", np.zeros(1, np.uint32), ids, net.channel, net.policy_n_of(3), net.principals).tolist() == []

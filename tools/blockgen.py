@@ -19,7 +19,33 @@ from . import workload
 
 FAULTS = ("bad_creator_sig", "bad_endorsement_sig", "dup_endorser", "unknown_endorser", "unknown_creator", "bad_txid", "dup_txid",
           "bad_proposal_hash", "bad_payload", "wrong_channel", "two_bad_endorsements", "invalid_creator_cert", "high_s_endorsement",
-          "empty_nonce", "config_update_type", "nonzero_epoch", "no_signature")
+          "empty_nonce", "config_update_type", "nonzero_epoch", "no_signature",
+          # the plugin dispatcher's checks and per-chaincode policies (plugindispatcher/dispatcher.go:102-221)
+          "bad_header_extension", "no_prp_extension", "bad_rwset", "cc_name_mismatch", "empty_cc_version", "event_wrong_cc", "dup_namespace",
+          "writes_strict_namespace", "reads_strict_namespace", "writes_unknown_namespace", "same_cert_two_encodings", "many_endorsements")
+
+CHAINCODE = "mycc"                 # the chaincode every synthetic transaction invokes
+STRICT_NAMESPACE = "strictcc"      # a second chaincode whose policy wants one endorsement more than transactions carry
+UNKNOWN_NAMESPACE = "ghostcc"      # a namespace without a chaincode definition in the table given to the device
+
+
+def chaincode_id(name: str, version: str = "") -> bytes:
+    return pb.f_bytes(2, name.encode()) + (pb.f_bytes(3, version.encode()) if version else b"")
+
+
+def kv_rwset(n_reads=1, n_writes=1, tag=b"k") -> bytes:
+    """kvrwset.KVRWSet{reads=1, writes=3}: KVRead{key=1}, KVWrite{key=1, value=3}."""
+    out = b""
+    for i in range(n_reads):
+        out += pb.f_bytes(1, pb.f_bytes(1, tag + b"-r%d" % i))
+    for i in range(n_writes):
+        out += pb.f_bytes(3, pb.f_bytes(1, tag + b"-w%d" % i) + pb.f_bytes(3, b"value-%d" % i))
+    return out
+
+
+def tx_rwset(namespaces) -> bytes:
+    """rwset.TxReadWriteSet{data_model=1 (KV = 0), ns_rwset=2}; namespaces: list of (name, n_reads, n_writes)."""
+    return b"".join(pb.f_bytes(2, pb.f_bytes(1, name.encode()) + pb.f_bytes(2, kv_rwset(nr, nw, name.encode()))) for name, nr, nw in namespaces)
 
 
 class Identity:
@@ -61,8 +87,19 @@ class Network:
                         for i in range(n_clients)]
         self.unknown = Identity("Org1MSP", K - 2, bytes(self.keys_xy[K - 2]), _pem_blob(b"unknown"))
         self.invalid_cert = Identity("Org2MSP", K - 1, bytes(self.keys_xy[K - 1]), _pem_blob(b"revoked"), valid=False)
-        self.msp_table = self.peers + self.clients + [self.invalid_cert]        # `unknown` deliberately absent
+        # every peer certificate once more in a byte-different PEM encoding (CRLF line ends): another serialization of the SAME
+        # identity -- the reference de-duplicates on Mspid + certificate digest, not on the serialized bytes (policy.go:380-386)
+        self.peers_alt = [Identity(p.mspid, p.priv_index, p.xy, p.cert_pem.replace(b"\n", b"\r\n")) for p in self.peers]
+        self.msp_table = self.peers + self.clients + [self.invalid_cert] + self.peers_alt        # `unknown` deliberately absent
         self.principals = ["Org%dMSP" % (i + 1) for i in range(n_orgs)]
+
+    def policies_for(self, n_endorsements):
+        """(nodes, {namespace: root}): CHAINCODE wants n_endorsements of the orgs, STRICT_NAMESPACE one more; UNKNOWN_NAMESPACE has no entry."""
+        a = self.policy_n_of(n_endorsements)
+        b = self.policy_n_of(n_endorsements + 1).copy()
+        b[0, 2] += a.shape[0]                                    # children of the second tree follow its root
+        nodes = np.concatenate([a, b])
+        return nodes, {CHAINCODE: 0, STRICT_NAMESPACE: int(a.shape[0])}
 
     def policy_n_of(self, n):
         """cauthdsl N-out-of over SignedBy(i) for every org: nodes as (type, n, first_child, n_children); type 0 = NOutOf, 1 = SignedBy."""
@@ -97,14 +134,33 @@ def build_block(net: Network, n_tx: int, n_endorsements: int = 3, faults=None, s
             txid = hashlib.sha256(b"x" + nonce + creator).hexdigest()
         channel = net.channel if f != "wrong_channel" else "other-channel"
         htype = pb.HEADER_TYPE_ENDORSER_TRANSACTION if f != "config_update_type" else pb.HEADER_TYPE_CONFIG_UPDATE
-        chdr = pb.channel_header(htype, channel, txid, epoch=(5 if f == "nonzero_epoch" else 0), extension=b"\x12\x06mycc:1")
+        hext = pb.f_bytes(2, chaincode_id(CHAINCODE))                      # peer.ChaincodeHeaderExtension{chaincode_id = 2}
+        if f == "bad_header_extension":
+            hext = b"\x12\x7fshort"                                         # length prefix runs past the end
+        chdr = pb.channel_header(htype, channel, txid, epoch=(5 if f == "nonzero_epoch" else 0), extension=hext)
         shdr = pb.signature_header(creator, b"" if f == "empty_nonce" else nonce)
         cpp = pb.f_bytes(1, b"invoke-args-" + bytes(rng.integers(0, 256, 40, dtype=np.uint8)))     # ChaincodeProposalPayload
         phash = hashlib.sha256(chdr + shdr + cpp).digest()
         if f == "bad_proposal_hash":
             phash = bytes(32)
-        rwset = bytes(rng.integers(0, 256, 180, dtype=np.uint8))
-        prp = pb.proposal_response_payload(phash, pb.f_bytes(1, rwset) + pb.f_bytes(4, b"\x0a\x04mycc"))
+        nss = [(CHAINCODE, 2, 2)]
+        if f == "writes_strict_namespace":
+            nss.append((STRICT_NAMESPACE, 0, 1))                            # cc-to-cc call that WRITES there: that policy applies too
+        if f == "reads_strict_namespace":
+            nss.append((STRICT_NAMESPACE, 2, 0))                            # only reads: the namespace is not validated
+        if f == "writes_unknown_namespace":
+            nss.append((UNKNOWN_NAMESPACE, 0, 1))
+        if f == "dup_namespace":
+            nss.append((CHAINCODE, 1, 0))
+        rwset = tx_rwset(nss)
+        if f == "bad_rwset":
+            rwset = pb.f_bytes(2, b"\x0a\x7fnamespace-length-runs-past-the-end")
+        ccact = pb.f_bytes(1, rwset) + pb.f_bytes(4, chaincode_id("othercc" if f == "cc_name_mismatch" else CHAINCODE, "" if f == "empty_cc_version" else "1.0"))
+        if f == "event_wrong_cc":
+            ccact += pb.f_bytes(2, pb.f_bytes(1, b"othercc") + pb.f_bytes(3, b"evt"))
+        prp = pb.proposal_response_payload(phash, ccact)
+        if f == "no_prp_extension":
+            prp = pb.f_bytes(1, phash)
         # endorsers: the first n_endorsements orgs, rotated per tx
         order = [(t + k) % net.n_orgs for k in range(n_endorsements)]
         ends = [net.peers[o] for o in order]
@@ -112,6 +168,10 @@ def build_block(net: Network, n_tx: int, n_endorsements: int = 3, faults=None, s
             ends[-1] = ends[0]
         if f == "unknown_endorser":
             ends[-1] = net.unknown
+        if f == "same_cert_two_encodings":
+            ends[-1] = net.peers_alt[order[0]]                             # the first endorser again, serialized differently
+        if f == "many_endorsements":                                       # 21 endorsements: every org five times over (both encodings) + one
+            ends = [(net.peers if (k // net.n_orgs) % 2 == 0 else net.peers_alt)[k % net.n_orgs] for k in range(5 * net.n_orgs + 1)]
         for e in ends:
             sign_msgs.append(prp + e.serialized)
             sign_keys.append(e.priv_index)
@@ -162,5 +222,5 @@ def build_block(net: Network, n_tx: int, n_endorsements: int = 3, faults=None, s
         envs.append(env)
     env_off = np.zeros(len(envs) + 1, np.uint32)
     env_off[1:] = np.cumsum([len(e) for e in envs])
-    return pb.block(number, envs), dict(n_tx=n_tx, faults=dict(faults), n_sigs=n_tx * (1 + n_endorsements),
+    return pb.block(number, envs), dict(n_tx=n_tx, faults=dict(faults), n_sigs=n_tx + sum(len(tx["ends"]) for tx in txs),
                                         env_blob=b"".join(envs), env_off=env_off)   # Block.Data.Data as the Go validator holds it
