@@ -387,6 +387,20 @@ def run_gpu(args):
     e2e_reps = pipelined(lambda sl: ctx.bccsp_verify_batch_inplace_async(sl, KK, B))
     e2e_s = sorted(e2e_reps)[len(e2e_reps) // 2]
     e2e_pageable_s = sorted(e2e_reps_pageable)[len(e2e_reps_pageable) // 2]
+    # (c) "first sight" mix: half of the batch signed by the 64 busy identities (tables), half by 4096 identities that sign 8 times each and
+    #     therefore stay on the generic kernel (FABGPU_KEY_MIN_USES = 256): what a block with many one-off client certificates looks like
+    hot, cold = KEYS, 4096
+    rng_m = np.random.default_rng(workload.DEFAULT_SEED + 77 + rank)
+    kidx_m = np.concatenate([rng_m.integers(0, hot, size=B // 2), hot + (np.arange(B - B // 2) % cold)]).astype(np.int32)
+    rng_m.shuffle(kidx_m)
+    wm = workload.Workload(B, hot + cold, seed=workload.DEFAULT_SEED + 9 + 1000 * rank, key_idx=kidx_m)
+    mixed_args = (wm.keys_xy, wm.key_idx, wm.digest, wm.dig_off(), wm.sigs, wm.sig_off)
+    stm = ctx.bccsp_verify_batch(*mixed_args)
+    assert (stm == 0).all()
+    e2e_steps_saved, e2e_steps = e2e_steps, max(4, e2e_steps // 4)
+    e2e_mixed_reps = pipelined(lambda sl: ctx.bccsp_verify_batch_async(sl, *mixed_args))
+    e2e_mixed_steps, e2e_steps = e2e_steps, e2e_steps_saved
+    e2e_mixed_s = sorted(e2e_mixed_reps)[len(e2e_mixed_reps) // 2]
     e2e_h2d = int(w.sig_off[B]) + int(dig_off[B]) + 4 * (B + 1) * 2 + 4 * B + 68 * KEYS
     e2e_d2h = B
 
@@ -523,6 +537,9 @@ def run_gpu(args):
                     "pageable_value": n_total * e2e_steps / (e2e_pageable_ms * 1e-3),
                     "pageable_api": "fabgpu_bccsp_verify_batch_async: the same pipeline fed from ordinary (pageable) host arrays; the library's staging threads copy them into the pinned buffers first",
                     "pageable_repetitions_verifies_per_s": [n_total * e2e_steps / t for t in e2e_reps_pageable],
+                    "mixed_value_rank0": B * e2e_mixed_steps / e2e_mixed_s,
+                    "mixed_what": "same pipeline (pageable arrays), per GPU: half of the %d signatures from the %d identities with key tables, half from %d identities that sign 8 times each "
+                                  "(no table: generic kernel); rank 0's rate" % (B, hot, cold),
                     "steps": e2e_steps, "repetitions_verifies_per_s": [n_total * e2e_steps / t for t in e2e_reps], "reported": "median repetition (max over ranks)",
                     "sync_value": n_total * e2e_steps / (e2e_sync_ms * 1e-3), "sync_api": "fabgpu_bccsp_verify_batch, one blocking call per step",
                     "last_call_phases_us": {"key_lookup": e2e_phases[0], "host_staging_copy": e2e_phases[1], "h2d_gate_verify_status_d2h": e2e_phases[2], "status_copy": e2e_phases[3]},

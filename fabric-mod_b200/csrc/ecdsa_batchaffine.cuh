@@ -78,7 +78,7 @@ FAB_HD void ba_digits(const u256& u1, const u256& u2, uint32_t* dig, int stride)
 // multiplication per two gathers: without this, each of its 14 iterations waits out a DRAM round trip (ncu: long_scoreboard 25 % of
 // all warp time); with the lines already on their way only the first wait is a DRAM latency, the rest are L2 hits.
 #ifndef FAB_BA_L2PREFETCH
-#define FAB_BA_L2PREFETCH 1
+#define FAB_BA_L2PREFETCH 0             // measured on B200: 181 -> 165 M/s at 64k with it on (profiles/r2_kernel_variants.txt): the extra requests compete with the gathers
 #endif
 FAB_HD void ba_prefetch_leaves(const uint32_t* dig, int stride, const aff* gtab, const aff* qtab)
 {

@@ -64,6 +64,68 @@ ecdsa_verify_kernel(const int32_t* __restrict__ key_slot, const uint8_t* __restr
     }
 }
 
+// ---- validity-bitmask exchange over peer memory (one process per GPU; SURVEY.md section 8e) -----------------------------------
+// Every rank owns a receive buffer (cudaMalloc'ed, exported through CUDA IPC, mapped by all peers): `gens` generations of
+// world x words_per_rank mask words, then world step flags.  The verify kernel's epilogue stores each warp's ballot word into
+// the buffer of EVERY rank (plain st.global on peer-mapped addresses: P2P writes over NVLink / NVSwitch); the last CTA to finish
+// publishes the step number into every rank's flag array; peer_wait_kernel (same stream) then spins until the flags of all ranks
+// have reached the step, i.e. until the whole bitmask has landed locally.  No NCCL call on the data path.
+#define FAB_PEER_MAX 8
+struct PeerOut {
+    uint32_t* buf[FAB_PEER_MAX];   // every rank's receive buffer as mapped in THIS process (buf[rank] is the local one)
+    uint32_t* done;                // local counter of finished CTAs (device memory, zero between launches)
+    uint32_t world, rank;
+    uint32_t words_per_rank;       // mask words each rank contributes
+    uint32_t gen_off;              // word offset of this step's generation inside a buffer
+    uint32_t flag_off;             // word offset of the flag array inside a buffer
+    uint32_t step;                 // published when this rank's words are all written
+};
+
+__device__ __forceinline__ void peer_store_word(const PeerOut& po, uint32_t word_index, uint32_t v)
+{
+    const uint32_t at = po.gen_off + po.rank * po.words_per_rank + word_index;
+#pragma unroll
+    for (uint32_t p = 0; p < FAB_PEER_MAX; p++) if (p < po.world) po.buf[p][at] = v;      // static indices: the parameter stays in constant memory
+}
+
+// Called by every thread of a CTA after its mask words are stored: the last CTA of the grid publishes the step.
+__device__ __forceinline__ void peer_publish(const PeerOut& po)
+{
+    __threadfence_system();                               // this thread's peer stores are ordered before the counter update
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t prev = atomicAdd(po.done, 1u);
+        if (prev == gridDim.x - 1) {
+            *po.done = 0u;                                // ready for the next launch (stream order)
+            __threadfence_system();
+#pragma unroll
+            for (uint32_t p = 0; p < FAB_PEER_MAX; p++) if (p < po.world) *reinterpret_cast<volatile uint32_t*>(po.buf[p] + po.flag_off + po.rank) = po.step;
+        }
+    }
+}
+
+// Waits (on the stream) until every rank has published `step`; gives up after ~2 s and records that in *timeout_flag so a
+// dead peer can never hang the GPU (the host reads the flag and reports a device error: the caller falls back).
+__global__ void peer_wait_kernel(const uint32_t* flags, uint32_t world, uint32_t step, uint32_t* timeout_flag)
+{
+    const uint32_t p = threadIdx.x;
+    if (p >= world) return;
+    const long long t0 = clock64();
+    while ((int32_t)(*reinterpret_cast<const volatile uint32_t*>(flags + p) - step) < 0) {
+        if (clock64() - t0 > 4000000000ll) { *timeout_flag = 1u; break; }
+        __nanosleep(200);
+    }
+}
+
+// Fallback for launches whose mask was produced by several kernels (mixed key-table / generic batches): copy the finished local
+// words to every peer, then publish.
+__global__ void peer_scatter_kernel(const uint32_t* __restrict__ local_words, uint32_t n_words, PeerOut po)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_words) peer_store_word(po, i, local_words[i]);
+    peer_publish(po);
+}
+
 #ifndef FAB_CACHED_THREADS
 #define FAB_CACHED_THREADS 512        // largest CTA the kernel may be launched with (launch_verify picks 128 / 256 / 512)
 #endif
@@ -76,7 +138,7 @@ ecdsa_verify_kernel(const int32_t* __restrict__ key_slot, const uint8_t* __restr
 __global__ void __launch_bounds__(FAB_CACHED_THREADS, FAB_CACHED_MINBLOCKS)
 ecdsa_verify_cached_kernel(const int32_t* __restrict__ key_slot, const uint8_t* __restrict__ e, const uint8_t* __restrict__ r,
                            const uint8_t* __restrict__ s, uint32_t n, const aff* __restrict__ gtab, const aff* __restrict__ qtab,
-                           uint32_t* __restrict__ mask, uint32_t* __restrict__ offcurve, const uint32_t* __restrict__ n_dev, uint32_t n_base)
+                           uint32_t* __restrict__ mask, uint32_t* __restrict__ offcurve, const uint32_t* __restrict__ n_dev, uint32_t n_base, PeerOut po)
 {
     if (n_dev) n = min(n, n_base + *n_dev);
     const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -93,7 +155,9 @@ ecdsa_verify_cached_kernel(const int32_t* __restrict__ key_slot, const uint8_t* 
     if ((threadIdx.x & 31u) == 0 && idx < n) {
         mask[idx >> 5] = vmask;
         if (offcurve) offcurve[idx >> 5] = 0u;
+        if (po.world) peer_store_word(po, idx >> 5, vmask);      // fused epilogue: the ballot word goes to every rank's buffer (P2P stores)
     }
+    if (po.world) peer_publish(po);
 }
 
 // ---- lane-split variant of the Jacobian-chain kernel (the "warp-cooperative" shape of BASELINE.json's north_star, measured) ----
@@ -192,66 +256,6 @@ ecdsa_verify_lanes_kernel(const int32_t* __restrict__ key_slot, const uint8_t* _
             else { mask[first >> 5] = packed; if (offcurve) offcurve[first >> 5] = 0; }
         }
     }
-}
-
-// ---- validity-bitmask exchange over peer memory (one process per GPU; SURVEY.md section 8e) -----------------------------------
-// Every rank owns a receive buffer (cudaMalloc'ed, exported through CUDA IPC, mapped by all peers): `gens` generations of
-// world x words_per_rank mask words, then world step flags.  The verify kernel's epilogue stores each warp's ballot word into
-// the buffer of EVERY rank (plain st.global on peer-mapped addresses: P2P writes over NVLink / NVSwitch); the last CTA to finish
-// publishes the step number into every rank's flag array; peer_wait_kernel (same stream) then spins until the flags of all ranks
-// have reached the step, i.e. until the whole bitmask has landed locally.  No NCCL call on the data path.
-#define FAB_PEER_MAX 8
-struct PeerOut {
-    uint32_t* buf[FAB_PEER_MAX];   // every rank's receive buffer as mapped in THIS process (buf[rank] is the local one)
-    uint32_t* done;                // local counter of finished CTAs (device memory, zero between launches)
-    uint32_t world, rank;
-    uint32_t words_per_rank;       // mask words each rank contributes
-    uint32_t gen_off;              // word offset of this step's generation inside a buffer
-    uint32_t flag_off;             // word offset of the flag array inside a buffer
-    uint32_t step;                 // published when this rank's words are all written
-};
-
-__device__ __forceinline__ void peer_store_word(const PeerOut& po, uint32_t word_index, uint32_t v)
-{
-    const uint32_t at = po.gen_off + po.rank * po.words_per_rank + word_index;
-    for (uint32_t p = 0; p < po.world; p++) po.buf[p][at] = v;
-}
-
-// Called by every thread of a CTA after its mask words are stored: the last CTA of the grid publishes the step.
-__device__ __forceinline__ void peer_publish(const PeerOut& po)
-{
-    __threadfence_system();                               // this thread's peer stores are ordered before the counter update
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const uint32_t prev = atomicAdd(po.done, 1u);
-        if (prev == gridDim.x - 1) {
-            *po.done = 0u;                                // ready for the next launch (stream order)
-            __threadfence_system();
-            for (uint32_t p = 0; p < po.world; p++) *reinterpret_cast<volatile uint32_t*>(po.buf[p] + po.flag_off + po.rank) = po.step;
-        }
-    }
-}
-
-// Waits (on the stream) until every rank has published `step`; gives up after ~2 s and records that in *timeout_flag so a
-// dead peer can never hang the GPU (the host reads the flag and reports a device error: the caller falls back).
-__global__ void peer_wait_kernel(const uint32_t* flags, uint32_t world, uint32_t step, uint32_t* timeout_flag)
-{
-    const uint32_t p = threadIdx.x;
-    if (p >= world) return;
-    const long long t0 = clock64();
-    while ((int32_t)(*reinterpret_cast<const volatile uint32_t*>(flags + p) - step) < 0) {
-        if (clock64() - t0 > 4000000000ll) { *timeout_flag = 1u; break; }
-        __nanosleep(200);
-    }
-}
-
-// Fallback for launches whose mask was produced by several kernels (mixed key-table / generic batches): copy the finished local
-// words to every peer, then publish.
-__global__ void peer_scatter_kernel(const uint32_t* __restrict__ local_words, uint32_t n_words, PeerOut po)
-{
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n_words) peer_store_word(po, i, local_words[i]);
-    peer_publish(po);
 }
 
 // ---- batch-affine key-table kernel (ecdsa_batchaffine.cuh) ----

@@ -28,6 +28,9 @@
 #endif
 #define FAB_Q_WINDOWS ((256 + FAB_WQ - 1) / FAB_WQ)
 #define FAB_Q_ENTRIES ((1 << FAB_WQ) - 1)
+#ifndef FAB_JAC_NEXT_PREFETCH
+#define FAB_JAC_NEXT_PREFETCH 1      // measured +0.5 % (64k) .. +1.5 % (1M) on B200, profiles/r2_kernel_variants.txt
+#endif
 #ifndef FAB_JAC_L2PREFETCH
 #define FAB_JAC_L2PREFETCH 0
 #endif
@@ -214,6 +217,15 @@ FAB_HD uint32_t ecdsa_verify_one_cached(const aff* qtab, const u256& e, const u2
 #pragma unroll
             for (int i = 0; i < 7; i++) kk[i] = (kk[i] >> wbits) | (kk[i + 1] << (32u - wbits));
             kk[7] >>= wbits;
+#if defined(__CUDA_ARCH__) && FAB_JAC_NEXT_PREFETCH
+            {   // the entry of the NEXT window (or the first window of the key's table) is requested from the L2 while this addition runs:
+                // the tables are HBM-resident, one DRAM round trip (~1 us) per addition was exposed (profiles/microbench/gather_b200.txt)
+                const aff* nx = nullptr;
+                if (j + 1 < windows) { const uint32_t dn = kk[0] & entries; if (dn) nx = tab + (size_t)(j + 1) * entries + (dn - 1); }
+                else if (t == 0) { const uint32_t dn = u2.v[0] & ((1u << FAB_WQ) - 1u); if (dn) nx = qtab + (dn - 1); }
+                if (nx) asm volatile("prefetch.global.L2 [%0];" :: "l"(nx));
+            }
+#endif
             if (d) acc = jac_add_aff_t<FAB_CACHED_INLINE != 0>(acc, tab[(size_t)j * entries + (d - 1)]);
         }
     }

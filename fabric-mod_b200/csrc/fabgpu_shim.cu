@@ -148,7 +148,10 @@ struct fabgpu_ctx {
     std::vector<uint32_t> slot_gen;          // bumped whenever a slot is recycled: handles carry the generation they were issued under
     unsigned long long tick = 0;
     int key_min_uses = 256;
-    int cached_kernel = 1;     // key-table kernel: 1 = batch-affine (ecdsa_verify_ba_kernel), 0 = Jacobian chain (ecdsa_verify_cached_kernel); FABGPU_CACHED_KERNEL
+    // key-table kernel (FABGPU_CACHED_KERNEL): 0 "jac" = Jacobian chain, one signature per thread (ecdsa_verify_cached_kernel) -- the DEFAULT: fastest at
+    // every batch size measured on B200 (profiles/r2_kernel_variants.txt); 1 "ba" = batch-affine with CTA-shared inversions, 3 "ba2" = batch-affine, two
+    // signatures per thread, 2 / 4 "l2" / "l4" = the Jacobian chain split over 2 / 4 lanes.  The alternatives stay selectable: they are the measurements.
+    int cached_kernel = 0;
     double timing[4] = {0, 0, 0, 0};   // last fabgpu_bccsp_verify_batch: key lookup, host gates, device (H2D+kernel+D2H), scatter [us]
     // block validation (fabgpu_msp_configure / fabgpu_validate_block), device 0 of the context
     blockval::MspTable msp;
@@ -278,7 +281,7 @@ int launch_verify(fabgpu_ctx* ctx, const Device& dv, int mode, const int32_t* ke
                   const uint32_t* n_dev = nullptr, uint32_t n_base = 0, const PeerOut* peer = nullptr)
 {
     PeerOut po; memset(&po, 0, sizeof po);
-    const bool fused_peer = peer && mode == MODE_CACHED && (ctx->cached_kernel == 1 || ctx->cached_kernel == 3) && n > 0;
+    const bool fused_peer = peer && mode == MODE_CACHED && (ctx->cached_kernel == 0 || ctx->cached_kernel == 1 || ctx->cached_kernel == 3) && n > 0 && !n_dev;
     if (fused_peer) po = *peer;
     if (peer && !fused_peer) {                            // several kernels write the mask: scatter it afterwards (below)
         if (n_dev) { ctx->last_error = "peer exchange needs a host-known batch size"; return FABGPU_E_ARG; }
@@ -310,7 +313,7 @@ int launch_verify(fabgpu_ctx* ctx, const Device& dv, int mode, const int32_t* ke
         const size_t sms = (size_t)dv.sms;
         if (!n_dev && n > sms * 384) threads = (n <= sms * FAB_CACHED_THREADS) ? FAB_CACHED_THREADS : 256;
         const unsigned blocks = (unsigned)((n + threads - 1) / threads);
-        ecdsa_verify_cached_kernel<<<blocks, threads, 0, st>>>(key_slot, e, r, s, (uint32_t)n, dv.gtab, dv.qtab, mask, off, n_dev, n_base);
+        ecdsa_verify_cached_kernel<<<blocks, threads, 0, st>>>(key_slot, e, r, s, (uint32_t)n, dv.gtab, dv.qtab, mask, off, n_dev, n_base, po);
         }
         ctx->launches++;
         CK(ctx, cudaGetLastError());

@@ -35,7 +35,7 @@ class Workload:
     """n signatures over K keys.  Arrays: keys_xy uint8[K,64], priv uint8[K,32], key_idx int32[n],
     digest uint8[n,32], r/s uint8[n,32] (big-endian), sigs uint8 blob + sig_off uint32[n+1] (DER)."""
 
-    def __init__(self, n, K, seed=DEFAULT_SEED, msg_len=1024, nthreads=None):
+    def __init__(self, n, K, seed=DEFAULT_SEED, msg_len=1024, nthreads=None, key_idx=None):
         nthreads = nthreads or min(os.cpu_count() or 1, 64)
         L = lib()
         self.n, self.K, self.seed = n, K, seed
@@ -43,7 +43,7 @@ class Workload:
         self.keys_xy = np.zeros((K, 64), np.uint8)
         L.siggen_keys(ctypes.c_uint64(seed), ctypes.c_int(K), _p(self.priv), _p(self.keys_xy))
         rng = np.random.default_rng(seed)
-        self.key_idx = rng.integers(0, K, size=n, dtype=np.int32)
+        self.key_idx = rng.integers(0, K, size=n, dtype=np.int32) if key_idx is None else np.ascontiguousarray(key_idx, dtype=np.int32)
         self.digest = np.zeros((n, 32), np.uint8)
         L.siggen_digests(ctypes.c_uint64(seed), ctypes.c_int(n), ctypes.c_int(msg_len), _p(self.digest))
         self.r = np.zeros((n, 32), np.uint8)
