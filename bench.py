@@ -175,7 +175,7 @@ def run_reference(args):
         "data": "synthetic",
         "config": {"workload": workload_string(w.n), "batch_per_step": w.n,
                    "note": "the CPU arm runs on rank 0 only and verifies one batch per step whatever --gpus says (the GPU arm verifies one batch per GPU per step); both are rates"},
-        "cpu_baseline": {"value": v, "unit": "verifies/s", "cores": cores, "kind": "port",
+        "cpu_baseline": {"value": v, "unit": "verifies/s", "cores": cores, "kind": "port", "value_per_core": v / max(1, cores),
                          "sample": "%d steps x %d signatures through oracle/c (bccsp/sw gates + ecdsa.Verify steps on OpenSSL BN/EC primitives), %d of %d logical CPUs (best of all/half/quarter)" % (args.steps, w.n, cores, os.cpu_count() or 1)},
         "e2e": {"value": v, "unit": "verifies/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     })
@@ -571,7 +571,7 @@ def run_gpu(args):
                              "peak_source": "model: 148 SM x 64 IMAD/clk x %d MHz" % int(sm_max),
                              "generic_kernel": {"achieved": B * ALG_MACS_PER_VERIFY / gen_launch_s / 1e12,
                                                 "frac": B * ALG_MACS_PER_VERIFY / gen_launch_s / mac_peak, "macs_per_verify": ALG_MACS_PER_VERIFY}},
-            "cpu_baseline": {"value": cpu_v, "unit": "verifies/s", "cores": cores, "kind": "port",
+            "cpu_baseline": {"value": cpu_v, "unit": "verifies/s", "cores": cores, "kind": "port", "value_per_core": cpu_v / max(1, cores),
                              "sample": "%d signatures in %.1f s through oracle/c (bccsp/sw gates + ecdsa.Verify steps on OpenSSL BN/EC primitives), %d of %d logical CPUs (best of all/half/quarter)" % (cpu_done, cpu_el, cores, os.cpu_count() or 1)},
             "clocks": clocks,
             "block_replay": block_replay,

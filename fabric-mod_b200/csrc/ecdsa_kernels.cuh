@@ -64,6 +64,44 @@ ecdsa_verify_kernel(const int32_t* __restrict__ key_slot, const uint8_t* __restr
     }
 }
 
+// ---- mixed batches: signatures without a key table, compacted ------------------------------------------------------------------
+// In a batch where only SOME keys own a table the generic kernel used to run over all n threads and return at once for the tabled ones;
+// with tabled and untabled signatures interleaved every warp still walked the whole generic path (255 doublings) for its untabled lanes:
+// a half-and-half batch cost as much as an all-generic one (bench e2e.mixed: 21 M/s).  Now the untabled indices are compacted first
+// (warp-aggregated append) and the generic arithmetic runs over whole warps of them; results are OR-ed into the mask words the key-table
+// kernel wrote (bit 0 for untabled signatures).
+__global__ void compact_untabled_kernel(const int32_t* __restrict__ key_slot, uint32_t n, uint32_t* __restrict__ idx, uint32_t* __restrict__ count,
+                                        const uint32_t* __restrict__ n_dev, uint32_t n_base)
+{
+    if (n_dev) n = min(n, n_base + *n_dev);
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool g = i < n && key_slot[i] < 0;
+    const uint32_t m = __ballot_sync(0xffffffffu, g);
+    if (m == 0) return;
+    const uint32_t lane = threadIdx.x & 31u;
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(count, (uint32_t)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (g) idx[base + __popc(m & ((1u << lane) - 1u))] = i;
+}
+
+#ifndef FAB_INDEXED_THREADS
+#define FAB_INDEXED_THREADS 128
+#endif
+__global__ void __launch_bounds__(FAB_INDEXED_THREADS, 3)
+ecdsa_verify_indexed_kernel(const uint32_t* __restrict__ idx, const uint32_t* __restrict__ count, const uint8_t* __restrict__ qx, const uint8_t* __restrict__ qy,
+                            const uint8_t* __restrict__ e, const uint8_t* __restrict__ r, const uint8_t* __restrict__ s, const aff* __restrict__ gtab,
+                            uint32_t* __restrict__ mask, uint32_t* __restrict__ offcurve)
+{
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= *count) return;
+    const uint32_t i = idx[t];
+    const size_t o = (size_t)i * 32;
+    const uint32_t res = ecdsa_verify_one(load_be32(qx + o), load_be32(qy + o), load_be32(e + o), load_be32(r + o), load_be32(s + o), gtab);
+    if (res == V_VALID) atomicOr(mask + (i >> 5), 1u << (i & 31u));
+    else if (res == V_OFFCURVE && offcurve) atomicOr(offcurve + (i >> 5), 1u << (i & 31u));
+}
+
 // ---- validity-bitmask exchange over peer memory (one process per GPU) -----------------------------------
 // Every rank owns a receive buffer (cudaMalloc'ed, exported through CUDA IPC, mapped by all peers): `gens` generations of
 // world x words_per_rank mask words, then world step flags.  The verify kernel's epilogue stores each warp's ballot word into
@@ -88,12 +126,15 @@ __device__ __forceinline__ void peer_store_word(const PeerOut& po, uint32_t word
     for (uint32_t p = 0; p < FAB_PEER_MAX; p++) if (p < po.world) po.buf[p][at] = v;      // static indices: the parameter stays in constant memory
 }
 
-// Called by every thread of a CTA after its mask words are stored: the last CTA of the grid publishes the step.
+// Called by every thread of a CTA after its mask words are stored: the last CTA of the grid publishes the step.  ONE system-scope
+// fence per CTA, by thread 0 after the barrier (fences are cumulative: the barrier orders the warp leaders' peer stores before it).  The
+// first version fenced in every thread -- 64k system fences per launch, each waiting for its peer writes to be acknowledged -- and was
+// 35 us slower than the NCCL all-gather at 8 ranks (profiles/r2_scale.txt).
 __device__ __forceinline__ void peer_publish(const PeerOut& po)
 {
-    __threadfence_system();                               // this thread's peer stores are ordered before the counter update
     __syncthreads();
     if (threadIdx.x == 0) {
+        __threadfence_system();
         const uint32_t prev = atomicAdd(po.done, 1u);
         if (prev == gridDim.x - 1) {
             *po.done = 0u;                                // ready for the next launch (stream order)
@@ -113,7 +154,7 @@ __global__ void peer_wait_kernel(const uint32_t* flags, uint32_t world, uint32_t
     const long long t0 = clock64();
     while ((int32_t)(*reinterpret_cast<const volatile uint32_t*>(flags + p) - step) < 0) {
         if (clock64() - t0 > 4000000000ll) { *timeout_flag = 1u; break; }
-        __nanosleep(200);
+        __nanosleep(40);
     }
 }
 

@@ -42,6 +42,7 @@ struct DevSlot {
     uint32_t* d_mask = nullptr;
     uint32_t* d_off = nullptr;
     int32_t* d_key_slot = nullptr;
+    uint32_t* d_idx = nullptr;      // dev_cap + 1 words: compaction scratch of mixed batches
 };
 
 struct Device {
@@ -187,7 +188,7 @@ struct fabgpu_ctx {
         int32_t *h_kidx = nullptr, *h_slot_of = nullptr;
         uint8_t *d_sigs = nullptr, *d_digs = nullptr, *d_keys = nullptr, *d_status = nullptr, *d_pre = nullptr, *d_r = nullptr, *d_s = nullptr, *d_e = nullptr,
         *d_qx = nullptr, *d_qy = nullptr; uint32_t *d_sig_off = nullptr, *d_dig_off = nullptr, *d_mask = nullptr, *d_off = nullptr;
-        int32_t *d_kidx = nullptr, *d_slot_of = nullptr, *d_ks = nullptr;
+        int32_t *d_kidx = nullptr, *d_slot_of = nullptr, *d_ks = nullptr; uint32_t* d_idx = nullptr;
         // fabgpu_bccsp_verify_batch_async .. _wait: what is in flight on this slot
         bool busy = false; bool on_device = false; size_t n = 0;
         std::vector<uint8_t> done_status;       // statuses of a batch that could not take the device-gate path (finished at submit time)
@@ -198,7 +199,7 @@ struct fabgpu_ctx {
         size_t tx_cap = 0, j_cap = 0;
         uint32_t* d_env_off = nullptr; bdev::TxDev* d_txs = nullptr; bdev::RawJob* d_raw = nullptr; bdev::ShaJobD* d_sha = nullptr; uint8_t *d_r = nullptr, *d_s = nullptr, *d_qx = nullptr,
         *d_qy = nullptr, *d_gate = nullptr, *d_dig = nullptr, *d_flags = nullptr; int32_t *d_ks = nullptr, *d_ident = nullptr; uint32_t *d_mask = nullptr,
-        *d_off = nullptr, *d_counter = nullptr; uint64_t* d_hash = nullptr; bdev::Seg* d_seg = nullptr;
+        *d_off = nullptr, *d_counter = nullptr, *d_idx = nullptr; uint64_t* d_hash = nullptr; bdev::Seg* d_seg = nullptr;
         uint8_t* h_flags = nullptr; uint64_t* h_hash = nullptr; bdev::Seg* h_seg = nullptr; uint32_t* h_counter = nullptr; uint32_t* h_env_off = nullptr;
         // the block in flight on this slot (fabgpu_validate_*_async .. fabgpu_validate_wait)
         bool busy = false, on_device = false, use_ev = false; size_t T = 0; const uint8_t* block = nullptr;
@@ -278,7 +279,7 @@ enum { MODE_GENERIC = 0, MODE_CACHED = 1, MODE_MIXED = 2 };
 // n_dev / n_base (block path): the batch is [0, min(n, n_base + *n_dev)) with *n_dev written by an earlier kernel of the stream.
 int launch_verify(fabgpu_ctx* ctx, const Device& dv, int mode, const int32_t* key_slot, const uint8_t* qx, const uint8_t* qy,
                   const uint8_t* e, const uint8_t* r, const uint8_t* s, size_t n, uint32_t* mask, uint32_t* off, cudaStream_t st,
-                  const uint32_t* n_dev = nullptr, uint32_t n_base = 0, const PeerOut* peer = nullptr)
+                  const uint32_t* n_dev = nullptr, uint32_t n_base = 0, const PeerOut* peer = nullptr, uint32_t* scratch_idx = nullptr)
 {
     PeerOut po; memset(&po, 0, sizeof po);
     const bool fused_peer = peer && mode == MODE_CACHED && (ctx->cached_kernel == 0 || ctx->cached_kernel == 1 || ctx->cached_kernel == 3) && n > 0 && !n_dev;
@@ -318,14 +319,29 @@ int launch_verify(fabgpu_ctx* ctx, const Device& dv, int mode, const int32_t* ke
         ctx->launches++;
         CK(ctx, cudaGetLastError());
     }
-    if (mode != MODE_CACHED && n > 0) {
+    if (mode == MODE_MIXED && n > 0 && scratch_idx) {
+        // untabled signatures: compact their indices, then whole warps of generic arithmetic (see compact_untabled_kernel).
+        // scratch_idx: n + 1 words owned by the caller's slot (indices, then the counter).
+        CK(ctx, cudaMemsetAsync(scratch_idx + n, 0, 4, st));
+        compact_untabled_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(key_slot, (uint32_t)n, scratch_idx, scratch_idx + n, n_dev, n_base);
+        ecdsa_verify_indexed_kernel<<<(unsigned)((n + FAB_INDEXED_THREADS - 1) / FAB_INDEXED_THREADS), FAB_INDEXED_THREADS, 0, st>>>(
+            scratch_idx, scratch_idx + n, qx, qy, e, r, s, dv.gtab, mask, off);
+        ctx->launches += 2;
+        CK(ctx, cudaGetLastError());
+    } else if (mode == MODE_MIXED && n > 0) {
+        // no scratch (launches on a caller's stream): the generic kernel filters on key_slot itself
+        const unsigned gthreads = 128, blocks = (unsigned)((n + gthreads - 1) / gthreads);
+        ecdsa_verify_kernel<<<blocks, gthreads, 0, st>>>(key_slot, qx, qy, e, r, s, (uint32_t)n, dv.gtab, mask, off, n_dev, n_base);
+        ctx->launches++;
+        CK(ctx, cudaGetLastError());
+    }
+    if (mode == MODE_GENERIC && n > 0) {
         // same reasoning for the generic kernel (measured: 64k as 147 CTAs of 448 threads 24.1 M/s, as 1024 CTAs of 64 threads 22.6;
         // 256k as CTAs of 256 threads 27.6 M/s, of 448 threads 24.3)
         unsigned gthreads = 64;
         if (!n_dev && n > (size_t)dv.sms * 192) gthreads = (n <= (size_t)dv.sms * FAB_VERIFY_THREADS) ? FAB_VERIFY_THREADS : 256;
         const unsigned blocks = (unsigned)((n + gthreads - 1) / gthreads);
-        ecdsa_verify_kernel<<<blocks, gthreads, 0, st>>>(mode == MODE_MIXED ? key_slot : nullptr, qx, qy, e, r, s, (uint32_t)n,
-                                                                   dv.gtab, mask, off, n_dev, n_base);
+        ecdsa_verify_kernel<<<blocks, gthreads, 0, st>>>(nullptr, qx, qy, e, r, s, (uint32_t)n, dv.gtab, mask, off, n_dev, n_base);
         ctx->launches++;
         CK(ctx, cudaGetLastError());
     }
@@ -338,6 +354,9 @@ int launch_verify(fabgpu_ctx* ctx, const Device& dv, int mode, const int32_t* ke
     return FABGPU_OK;
 }
 
+// (The generation field is 19 bits: a handle kept across 524 288 recyclings of ITS slot would match again.  At one recycling per registration
+// call that is days of continuous eviction of one slot while a caller sits on a stale handle; the Go provider re-reads the handle from the key
+// object on every batch, so it never holds one that long.)
 // A key handle is (generation << 12) | slot.  A handle issued before its slot was recycled no longer matches the slot's
 // generation and silently degrades to "no table" (-1): the generic kernel then verifies against the Qx/Qy the caller
 // supplied, so a stale handle can cost speed but never correctness.
@@ -377,7 +396,7 @@ int enqueue_slot(fabgpu_ctx* ctx, int slot, size_t n, bool keyed)
         if (mode != MODE_GENERIC)
             CK(ctx, cudaMemcpyAsync(ds.d_key_slot, hs.h_key_slot + begin, 4 * cnt, cudaMemcpyHostToDevice, ds.stream));
         int rc = launch_verify(ctx, dv, mode, ds.d_key_slot, ds.d_in[0], ds.d_in[1], ds.d_in[2], ds.d_in[3], ds.d_in[4], cnt, ds.d_mask,
-                               ds.d_off, ds.stream);
+                               ds.d_off, ds.stream, nullptr, 0, nullptr, ds.d_idx);
         if (rc) return rc;
         const size_t words = (cnt + 31) / 32;
         CK(ctx, cudaMemcpyAsync(hs.h_mask + begin / 32, ds.d_mask, 4 * words, cudaMemcpyDeviceToHost, ds.stream));
@@ -411,7 +430,7 @@ void free_all(fabgpu_ctx* ctx)
         for (void* p : dev2) if (p) cudaFree(p);
         for (auto& db : ctx->dbs) {
             void* dev4[] = {db.d_env_off, db.d_txs, db.d_raw, db.d_sha, db.d_r, db.d_s, db.d_qx, db.d_qy, db.d_gate, db.d_dig, db.d_flags, db.d_ks, db.d_ident, db.d_mask, db.d_off,
-                            db.d_counter, db.d_hash, db.d_seg};
+                            db.d_counter, db.d_hash, db.d_seg, db.d_idx};
             for (void* p : dev4) if (p) cudaFree(p);
             void* host2[] = {db.h_flags, db.h_hash, db.h_seg, db.h_counter, db.h_env_off};
             for (void* p : host2) if (p) cudaFreeHost(p);
@@ -419,7 +438,7 @@ void free_all(fabgpu_ctx* ctx)
         }
         for (auto& gb : ctx->gb) {
         void* dev3[] = {gb.d_sigs, gb.d_digs, gb.d_keys, gb.d_status, gb.d_pre, gb.d_r, gb.d_s, gb.d_e, gb.d_qx, gb.d_qy, gb.d_sig_off, gb.d_dig_off, gb.d_mask, gb.d_off,
-                        gb.d_kidx, gb.d_slot_of, gb.d_ks};
+                        gb.d_kidx, gb.d_slot_of, gb.d_ks, gb.d_idx};
         for (void* p : dev3) if (p) cudaFree(p);
         void* host3[] = {gb.h_sigs, gb.h_digs, gb.h_keys, gb.h_status, gb.h_sig_off, gb.h_dig_off, gb.h_kidx, gb.h_slot_of};
         for (void* p : host3) if (p) cudaFreeHost(p);
@@ -431,6 +450,7 @@ void free_all(fabgpu_ctx* ctx)
         if (dv.qtab) cudaFree(dv.qtab);
         for (auto& ds : dv.slot) {
             if (ds.d_key_slot) cudaFree(ds.d_key_slot);
+            if (ds.d_idx) cudaFree(ds.d_idx);
             for (auto& p : ds.d_in) if (p) cudaFree(p);
             if (ds.d_mask) cudaFree(ds.d_mask);
             if (ds.d_off) cudaFree(ds.d_off);
@@ -512,6 +532,7 @@ int init_impl(fabgpu_ctx* ctx, const int* device_ids, int n_dev, size_t max_batc
             CK(ctx, cudaMalloc(&ds.d_mask, 4 * words));
             CK(ctx, cudaMalloc(&ds.d_off, 4 * words));
             CK(ctx, cudaMalloc(&ds.d_key_slot, 4 * ctx->dev_cap));
+            CK(ctx, cudaMalloc(&ds.d_idx, 4 * (ctx->dev_cap + 1)));
         }
 #if FAB_G_TWO_LEVEL
         {
@@ -924,7 +945,7 @@ static int gate_bufs_reserve(fabgpu_ctx* ctx, int slot, size_t n, size_t sig_byt
         rc |= grow_dev(ctx, gb.d_sig_off, 4 * (c + 1)); rc |= grow_dev(ctx, gb.d_dig_off, 4 * (c + 1)); rc |= grow_dev(ctx, gb.d_kidx, 4 * c);
         rc |= grow_dev(ctx, gb.d_status, c); rc |= grow_dev(ctx, gb.d_pre, c); rc |= grow_dev(ctx, gb.d_r, 32 * c); rc |= grow_dev(ctx, gb.d_s, 32 * c);
         rc |= grow_dev(ctx, gb.d_e, 32 * c); rc |= grow_dev(ctx, gb.d_qx, 32 * c); rc |= grow_dev(ctx, gb.d_qy, 32 * c); rc |= grow_dev(ctx, gb.d_ks, 4 * c);
-        rc |= grow_dev(ctx, gb.d_mask, c / 8 + 8); rc |= grow_dev(ctx, gb.d_off, c / 8 + 8);
+        rc |= grow_dev(ctx, gb.d_mask, c / 8 + 8); rc |= grow_dev(ctx, gb.d_off, c / 8 + 8); rc |= grow_dev(ctx, gb.d_idx, 4 * (c + 1));
         if (rc) return FABGPU_E_CUDA;
         gb.n_cap = c;
     }
@@ -994,7 +1015,8 @@ static int bccsp_device_submit(fabgpu_ctx* ctx, int slot, const uint8_t* keys_xy
                                                                         all_slots ? nullptr : gb.d_qy, gb.d_pre, sig_base, dig_base);
     ctx->launches++;
     CK(ctx, cudaGetLastError());
-    rc = launch_verify(ctx, dv, all_slots ? MODE_CACHED : MODE_MIXED, gb.d_ks, gb.d_qx, gb.d_qy, gb.d_e, gb.d_r, gb.d_s, n, gb.d_mask, gb.d_off, st);
+    rc = launch_verify(ctx, dv, all_slots ? MODE_CACHED : MODE_MIXED, gb.d_ks, gb.d_qx, gb.d_qy, gb.d_e, gb.d_r, gb.d_s, n, gb.d_mask, gb.d_off, st, nullptr, 0, nullptr,
+                       gb.d_idx);
     if (rc) return rc;
     bdev::bccsp_status_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(gb.d_pre, gb.d_mask, gb.d_off, (uint32_t)n, gb.d_status);
     ctx->launches++;
@@ -1553,7 +1575,7 @@ static int block_submit(fabgpu_ctx* ctx, int slot, const uint8_t* block, size_t 
         rc |= grow_dev(ctx, db.d_sha, sizeof(bdev::ShaJobD) * (jc + 2 * tc)); rc |= grow_dev(ctx, db.d_dig, 32 * (jc + 2 * tc) + 64);
         rc |= grow_dev(ctx, db.d_r, 32 * jc); rc |= grow_dev(ctx, db.d_s, 32 * jc); rc |= grow_dev(ctx, db.d_qx, 32 * jc); rc |= grow_dev(ctx, db.d_qy, 32 * jc);
         rc |= grow_dev(ctx, db.d_gate, jc); rc |= grow_dev(ctx, db.d_ks, 4 * jc); rc |= grow_dev(ctx, db.d_ident, 4 * jc);
-        rc |= grow_dev(ctx, db.d_mask, jc / 8 + 8); rc |= grow_dev(ctx, db.d_off, jc / 8 + 8); rc |= grow_dev(ctx, db.d_counter, 16);
+        rc |= grow_dev(ctx, db.d_mask, jc / 8 + 8); rc |= grow_dev(ctx, db.d_off, jc / 8 + 8); rc |= grow_dev(ctx, db.d_counter, 16); rc |= grow_dev(ctx, db.d_idx, 4 * (jc + 1));
         rc |= grow_dev(ctx, db.d_flags, tc); rc |= grow_dev(ctx, db.d_hash, 8 * tc); rc |= grow_dev(ctx, db.d_seg, 8 * tc);
         rc |= grow_host(ctx, db.h_flags, tc); rc |= grow_host(ctx, db.h_hash, 8 * tc); rc |= grow_host(ctx, db.h_seg, 8 * tc);
         rc |= grow_host(ctx, db.h_counter, 16); rc |= grow_host(ctx, db.h_env_off, 8 * (tc + 1));
@@ -1595,7 +1617,7 @@ static int block_submit(fabgpu_ctx* ctx, int slot, const uint8_t* block, size_t 
     CK(ctx, cudaGetLastError());
     if (db.use_ev) CK(ctx, cudaEventRecord(db.ev[3], st));
     int rc = launch_verify(ctx, dv, dm.all_slots ? MODE_CACHED : MODE_MIXED, db.d_ks, db.d_qx, db.d_qy, db.d_dig, db.d_r, db.d_s, J_cap, db.d_mask, db.d_off, st,
-                           db.d_counter, cnt);
+                           db.d_counter, cnt, nullptr, db.d_idx);
     if (rc) return rc;
     if (db.use_ev) CK(ctx, cudaEventRecord(db.ev[4], st));
     bdev::block_decide_kernel<<<(cnt + 127) / 128, 128, 0, st>>>(bb.d_block, db.d_txs, cnt, m, pol, db.d_mask, db.d_gate, db.d_ident, db.d_dig, (uint32_t)J_cap, db.d_flags,
