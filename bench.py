@@ -235,8 +235,11 @@ def run_gpu(args):
     # N > 1: the bitmask is reassembled by the library's own exchange over peer memory (P2P stores from the verify kernel's epilogue,
     # fabgpu_verify_p256_device_keyed_allgather); the NCCL all-gather stays available (--collective nccl) and is timed beside it.
     peer = None
+    peer_note = None
     if world > 1 and args.collective == "p2p":
         peer = sharding.PeerMaskExchange(ctx, n_total, world, rank, dev)
+        if not peer.ok:                                            # no peer access on this box: every rank falls back to the NCCL all-gather
+            peer_note, peer = "peer-memory exchange unavailable (%s): NCCL all-gather used" % (peer.error or "another rank failed"), None
 
     def step(k, generic=False, nccl=False):
         t = bufs[k % ROT]
@@ -529,7 +532,7 @@ def run_gpu(args):
                        "batch_per_gpu": B, "global_batch": n_total,
                        "parallelism": ("batch split x%d + bitmask exchanged over peer memory (P2P stores from the verify kernel's epilogue, fabgpu_peer_mask_*)" % world) if peer is not None
                                       else ("batch split x%d + NCCL all-gather of the bitmask" % world),
-                       "value_with_nccl_allgather": (n_total * args.steps / (nccl_ms * 1e-3)) if nccl_ms else None,
+                       "value_with_nccl_allgather": (n_total * args.steps / (nccl_ms * 1e-3)) if nccl_ms else None, "collective_note": peer_note,
                        "timing": "per-step CUDA events on the launch stream, summed; L2 flushed (256 MiB fill) between steps; %d rotating input buffers" % ROT,
                        "wall_ms_incl_flush": wall_ms, "rank0_numa_pinning": numa},
             "e2e": {"value": n_total * e2e_steps / (e2e_ms * 1e-3), "unit": "verifies/s", "h2d_bytes_per_step": e2e_h2d * world, "d2h_bytes_per_step": e2e_d2h * world,

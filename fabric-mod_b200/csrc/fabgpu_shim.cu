@@ -446,6 +446,14 @@ void free_all(fabgpu_ctx* ctx)
     }
     for (auto& dv : ctx->devs) {
         cudaSetDevice(dv.id);
+        {   // peer-memory bitmask exchange (fabgpu_peer_mask_*)
+            auto& pr = dv.peer;
+            for (int p = 0; p < FAB_PEER_MAX; p++) if (pr.opened[p]) cudaIpcCloseMemHandle(pr.mapped[p]);
+            if (pr.local) cudaFree(pr.local);
+            if (pr.done) cudaFree(pr.done);
+            if (pr.h_timeout) cudaFreeHost(pr.h_timeout);
+            pr = Device::Peer();
+        }
         if (dv.gtab) cudaFree(dv.gtab);
         if (dv.qtab) cudaFree(dv.qtab);
         for (auto& ds : dv.slot) {

@@ -46,19 +46,44 @@ class PeerMaskExchange:
     """Set-up and per-step driver of fabgpu_verify_p256_device_keyed_allgather for this rank's context `ctx`."""
 
     def __init__(self, ctx, n_total: int, world: int, rank: int, device, group=None):
+        """Collective over `group`.  self.ok is False on EVERY rank when any rank could not create or map a buffer (no peer access
+        between some pair of GPUs, IPC disabled ...): the caller then keeps the NCCL all-gather."""
         self.ctx, self.world, self.rank, self.device = ctx, world, rank, device
         self.n_total = n_total
         self.words = shard_words(n_total, world)
-        mine = torch.from_numpy(ctx.peer_mask_create(world, rank, self.words)).to(device)
+        self.step = 0
+        self.error = None
+
+        def agree(flag: bool) -> bool:
+            t = torch.tensor([1 if flag else 0], dtype=torch.int32, device=device)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+            return bool(int(t.item()))
+
+        mine = torch.zeros(64, dtype=torch.uint8, device=device)
+        try:
+            mine = torch.from_numpy(ctx.peer_mask_create(world, rank, self.words)).to(device)
+            created = True
+        except Exception as e:                                   # noqa: BLE001 -- any failure means "use NCCL"
+            created, self.error = False, str(e)
+        self.ok = agree(created)
+        if not self.ok:
+            if created:
+                ctx.peer_mask_close()
+            return
         handles = torch.empty(64 * world, dtype=torch.uint8, device=device)
         if world == 1:
             handles.copy_(mine)
         else:
             dist.all_gather_into_tensor(handles, mine, group=group)
-        ctx.peer_mask_open(handles.cpu().numpy())
-        if world > 1:
-            dist.barrier(group=group)                  # every rank has mapped every buffer before the first store
-        self.step = 0
+        try:
+            ctx.peer_mask_open(handles.cpu().numpy())
+            opened = True
+        except Exception as e:                                   # noqa: BLE001
+            opened, self.error = False, str(e)
+        self.ok = agree(opened)                                  # also the barrier: every rank has mapped every buffer before the first store
+        if not self.ok:
+            ctx.peer_mask_close()
 
     def verify(self, all_cached, d_key_slot, d_qx, d_qy, d_e, d_r, d_s, n, stream=0) -> torch.Tensor:
         """Enqueues verify + exchange on `stream`; returns the assembled mask (int32[ceil(n_total/32)], device memory owned by the

@@ -112,8 +112,11 @@ int fabgpu_host_key_slots(fabgpu_ctx* ctx, int slot, int32_t** key_slot);
 int fabgpu_verify_p256_keyed(fabgpu_ctx* ctx, int slot, size_t n);
 int fabgpu_verify_p256_keyed_async(fabgpu_ctx* ctx, int slot, size_t n);
 /* Device-resident form: d_key_slot holds raw slot indices (handle & 0xfff) that the caller obtained from
- * fabgpu_keys_register and knows to be live (no registration since).  all_cached != 0 promises every d_key_slot[i] >= 0
- * (d_qx/d_qy may then be NULL). */
+ * fabgpu_keys_register and knows to be live: RAW slots are not re-validated, so the caller must not let a registration that could
+ * recycle them (fabgpu_keys_register of new keys, fabgpu_msp_configure, a fabgpu_bccsp_verify_batch* call that tables new keys) run
+ * between obtaining the slots and the completion of this launch.  The handle-taking entry points (fabgpu_verify_p256_keyed*,
+ * fabgpu_bccsp_verify_batch*, fabgpu_validate_*) hold the library's slot-table lock from resolution to enqueue and need no such care.
+ * all_cached != 0 promises every d_key_slot[i] >= 0 (d_qx/d_qy may then be NULL). */
 int fabgpu_verify_p256_device_keyed(fabgpu_ctx* ctx, int dev_index, int all_cached, const void* d_key_slot, const void* d_qx,
                                     const void* d_qy, const void* d_e, const void* d_r, const void* d_s, size_t n,
                                     void* d_mask, void* d_offcurve, void* cuda_stream);

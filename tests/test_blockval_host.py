@@ -130,3 +130,27 @@ def test_device_der_gate_matches_host_gate_fuzz():
                 assert (r, s) == (r2, s2)
             n += 1
     assert n > 5000
+
+
+def test_identity_groups_follow_the_certificate_not_the_bytes():
+    """binding.identity_groups (what fabgpu_msp_identity_groups is fed): Mspid + certificate digest, as the reference's IdentityIdentifier
+    (common/policies/policy.go:380-386, msp/identities.go:55-76) -- and the same partition as the oracle's identity_id."""
+    from util import pkg
+    net = blockgen.Network()
+    ids = blockutil.identities_of(net)
+    g = pkg().binding.identity_groups(ids)
+    n_peers = len(net.peers)
+    first_alt = len(ids) - n_peers
+    for k in range(n_peers):
+        assert g[k] == g[first_alt + k]                         # CRLF re-encoding of peer k's certificate: same identity
+    assert len(set(g.tolist())) == len(ids) - n_peers
+    oracle_ids = [ob.identity_id(i[0], i[1]) for i in ids]
+    for a in range(len(ids)):
+        for b in range(len(ids)):
+            assert (g[a] == g[b]) == (oracle_ids[a] == oracle_ids[b])
+    # the same certificate under ANOTHER MSP id is another identity; unparsable id_bytes fall back to the bytes themselves
+    other = [(pb.serialized_identity("OtherMSP", net.peers[0].cert_pem), "OtherMSP", net.peers[0].xy, True),
+             (pb.serialized_identity("Org1MSP", b"not a pem"), "Org1MSP", net.peers[0].xy, True),
+             (pb.serialized_identity("Org1MSP", b"not a pem"), "Org1MSP", net.peers[0].xy, True)]
+    g2 = pkg().binding.identity_groups(ids + other)
+    assert g2[len(ids)] not in g2[: len(ids)].tolist() and g2[len(ids) + 1] == g2[len(ids) + 2] != g2[len(ids)]

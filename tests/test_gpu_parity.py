@@ -466,6 +466,37 @@ def test_bccsp_batch_async_two_slots_in_flight():
     c.close()
 
 
+@pytest.mark.parametrize("variant", ["jac", "ba", "ba2", "l2", "l4"])
+def test_key_table_kernel_variants_are_bit_exact(variant):
+    """Every key-table kernel shape that was built and measured (FABGPU_CACHED_KERNEL) gives the oracle's bits:
+    5 % tampered batch of ragged size through the keyed leaf, and the adversarial vectors through the bccsp-level call with every key
+    tabled (u1 = 0, u1 G = +-u2 Q, x(R) >= n, zero digits ...)."""
+    os.environ["FABGPU_CACHED_KERNEL"] = variant
+    os.environ["FABGPU_KEY_MIN_USES"] = "1"
+    try:
+        c = pkg().binding.Context(max_batch=1 << 15)
+    finally:
+        del os.environ["FABGPU_CACHED_KERNEL"]
+        del os.environ["FABGPU_KEY_MIN_USES"]
+    w = workload.Workload(20000 + 7, 16, seed=workload.DEFAULT_SEED + 21)
+    w.tamper_r(0.05)
+    exp = fast.valid_mask(fast.verify_batch(w.keys_xy, w.key_idx, w.digest, w.dig_off(), w.sigs, w.sig_off, nthreads=os.cpu_count()))
+    handles = c.keys_register(w.keys_xy)
+    assert (handles >= 0).all()
+    hb = _fill(c, 0, w, handles[w.key_idx])
+    c.verify_p256_keyed(0, w.n)
+    assert (hb["mask"][: exp.shape[0]] == exp).all()
+    cases = [cs for cs in vectors.build() if len(cs["sig"]) and cs["qx"] < p256.P and cs["qy"] < p256.P]
+    keys = np.stack([np.concatenate([be32(cs["qx"]), be32(cs["qy"])]) for cs in cases])
+    digs, sigs = [cs["digest"] for cs in cases], [cs["sig"] for cs in cases]
+    doff = np.zeros(len(cases) + 1, np.uint32); doff[1:] = np.cumsum([len(d) for d in digs])
+    soff = np.zeros(len(cases) + 1, np.uint32); soff[1:] = np.cumsum([len(x) for x in sigs])
+    st = c.bccsp_verify_batch(keys, np.arange(len(cases), dtype=np.int32), np.frombuffer(b"".join(digs), np.uint8), doff, np.frombuffer(b"".join(sigs), np.uint8), soff)
+    for cs, got in zip(cases, st):
+        assert int(got) == vectors.expected_status(cs), (variant, cs["name"])
+    c.close()
+
+
 def test_bccsp_batch_inplace_pinned_buffers_match_the_copying_form():
     """fabgpu_bccsp_batch_buffers + fabgpu_bccsp_verify_batch_inplace_async: the batch is written straight into the slot's pinned
     buffers; statuses must equal the staging form's and the oracle's, slot after slot, including a ragged adversarial tail."""
