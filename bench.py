@@ -335,6 +335,36 @@ def run_gpu(args):
     gen_ms = sum(a.elapsed_time(b) for a, b in gev)
     assert bool((full == -1).all())
 
+    # small-table tier (keys that recur without being busy: 86 KiB per key, 43 mixed additions for u2*Q), same tuples, same hygiene
+    small_ms = 0.0
+    small_keys = 4096
+    ssteps = max(3, min(args.steps, 10))
+    if ctx.small_slot_capacity() >= small_keys:
+        ws = workload.Workload(B, small_keys, seed=workload.DEFAULT_SEED + 11 + 1000 * rank, nthreads=os.cpu_count())
+        t0 = time.perf_counter()
+        codes = ctx.small_raw_codes(ctx.keys_register_small(ws.keys_xy))
+        assert (codes <= -2).all()
+        sbuf = [torch.from_numpy(a).to(dev) for a in (ws.digest, ws.r, ws.s)]
+        sks = torch.from_numpy(np.ascontiguousarray(codes[ws.key_idx])).to(dev)
+        def sstep():
+            ctx.verify_p256_device_keyed(2, sks.data_ptr(), 0, 0, sbuf[0].data_ptr(), sbuf[1].data_ptr(), sbuf[2].data_ptr(), B,
+                                         local_mask.data_ptr(), 0, stream.cuda_stream)
+        sstep()
+        torch.cuda.synchronize(dev)
+        small_register_ms = (time.perf_counter() - t0) * 1e3       # build of 4 096 tables + first batch
+        sstep()
+        sev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(ssteps)]
+        torch.cuda.synchronize(dev)
+        for k in range(ssteps):
+            flush.fill_(k & 0xFF)
+            sev[k][0].record(stream)
+            sstep()
+            sev[k][1].record(stream)
+        torch.cuda.synchronize(dev)
+        small_ms = sum(a.elapsed_time(b) for a, b in sev)
+        assert bool((local_mask == -1).all())
+        del ws, sbuf, sks
+
     # ---- end-to-end leg: raw DER + digests + keys in host memory through the bccsp-level C-ABI call ----------
     # Headline form: the two halves of the call (fabgpu_bccsp_verify_batch_async / _wait) round-robin over the slots, one batch per slot
     # in flight -- every step still stages its host buffers, copies them H2D, runs gate + verify + status kernels and reads the
@@ -390,8 +420,9 @@ def run_gpu(args):
     e2e_reps = pipelined(lambda sl: ctx.bccsp_verify_batch_inplace_async(sl, KK, B))
     e2e_s = sorted(e2e_reps)[len(e2e_reps) // 2]
     e2e_pageable_s = sorted(e2e_reps_pageable)[len(e2e_reps_pageable) // 2]
-    # (c) "first sight" mix: half of the batch signed by the 64 busy identities (tables), half by 4096 identities that sign 8 times each and
-    #     therefore stay on the generic kernel (FABGPU_KEY_MIN_USES = 256): what a block with many one-off client certificates looks like
+    # (c) mix: half of the batch signed by the 64 busy identities (window tables), half by 4096 identities that sign 8 times each: too few
+    #     for a window table (FABGPU_KEY_MIN_USES = 256), enough for a small one (FABGPU_SMALL_MIN_USES = 4) -- what a block with many client
+    #     certificates looks like
     hot, cold = KEYS, 4096
     rng_m = np.random.default_rng(workload.DEFAULT_SEED + 77 + rank)
     kidx_m = np.concatenate([rng_m.integers(0, hot, size=B // 2), hot + (np.arange(B - B // 2) % cold)]).astype(np.int32)
@@ -541,8 +572,8 @@ def run_gpu(args):
                     "pageable_api": "fabgpu_bccsp_verify_batch_async: the same pipeline fed from ordinary (pageable) host arrays; the library's staging threads copy them into the pinned buffers first",
                     "pageable_repetitions_verifies_per_s": [n_total * e2e_steps / t for t in e2e_reps_pageable],
                     "mixed_value_rank0": B * e2e_mixed_steps / e2e_mixed_s,
-                    "mixed_what": "same pipeline (pageable arrays), per GPU: half of the %d signatures from the %d identities with key tables, half from %d identities that sign 8 times each "
-                                  "(no table: generic kernel); rank 0's rate" % (B, hot, cold),
+                    "mixed_what": "same pipeline (pageable arrays), per GPU: half of the %d signatures from the %d identities with window tables, half from %d identities that sign 8 times each "
+                                  "(they earn SMALL tables at first sight: FABGPU_SMALL_MIN_USES = 4; before the small tier they stayed on the generic kernel); rank 0's rate" % (B, hot, cold),
                     "steps": e2e_steps, "repetitions_verifies_per_s": [n_total * e2e_steps / t for t in e2e_reps], "reported": "median repetition (max over ranks)",
                     "sync_value": n_total * e2e_steps / (e2e_sync_ms * 1e-3), "sync_api": "fabgpu_bccsp_verify_batch, one blocking call per step",
                     "last_call_phases_us": {"key_lookup": e2e_phases[0], "host_staging_copy": e2e_phases[1], "h2d_gate_verify_status_d2h": e2e_phases[2], "status_copy": e2e_phases[3]},
@@ -552,6 +583,11 @@ def run_gpu(args):
                                  "what": "same kernel, device-resident inputs, %d batches in flight on %d streams, no L2 flush: the regime of the pipelined e2e call "
                                          "(a single 64k launch fills 512 of 592 resident CTA slots)" % (pkg.binding.SLOTS, pkg.binding.SLOTS)},
             "value_generic": value_generic,
+            "value_small": (B * ssteps / (small_ms * 1e-3)) if small_ms else None,
+            "small": {"what": "ecdsa_verify_small_kernel, rank 0: %d signatures from %d keys that own a SMALL table (43 windows of signed 6-bit digits, 86 KiB per key): "
+                              "12 + 43 mixed additions per signature, no doublings; device-resident, L2 flushed between steps" % (B, small_keys),
+                      "ms_per_step": (small_ms / ssteps) if small_ms else None, "steps": ssteps,
+                      "register_and_first_batch_ms": small_register_ms if small_ms else None, "tables": ctx.key_table_stats()},
             "generic": {"what": "ecdsa_verify_kernel: no per-key table (first sight of a key); 255 doublings + 52 additions per signature",
                         "ms_per_step": gen_ms / gsteps, "steps": gsteps},
             "key_tables": {"keys": KEYS, "register_ms_once": key_register_ms,

@@ -27,6 +27,7 @@ EXPORTS = [
     "fabgpu_msp_identity_groups", "fabgpu_namespace_policies",
     "fabgpu_peer_mask_create", "fabgpu_peer_mask_open", "fabgpu_peer_mask_close", "fabgpu_verify_p256_device_keyed_allgather",
     "fabgpu_validate_block_async", "fabgpu_validate_envelopes_async", "fabgpu_validate_wait", "fabgpu_block_buffer_slot",
+    "fabgpu_keys_register_small", "fabgpu_small_slot_capacity", "fabgpu_key_table_stats",
 ]
 
 
@@ -219,6 +220,28 @@ class Context:
     def key_slot_capacity(self):
         return int(lib().fabgpu_key_slot_capacity(self._h))
 
+    def keys_register_small(self, keys_xy):
+        """uint8[K,64] -> int32[K] small-table handles (<= -2; -1 = no slot could be had)."""
+        keys_xy = np.ascontiguousarray(keys_xy, dtype=np.uint8).reshape(-1, 64)
+        handles = np.full(keys_xy.shape[0], -1, np.int32)
+        self._ck(lib().fabgpu_keys_register_small(self._h, _p(keys_xy), ctypes.c_int(keys_xy.shape[0]), _p(handles)))
+        return handles
+
+    @staticmethod
+    def small_raw_codes(handles):
+        """small handles -> the raw device codes fabgpu_verify_p256_device_keyed takes (-2 - slot)."""
+        h = np.asarray(handles, np.int64)
+        return np.where(h <= -2, -2 - ((-2 - h) & 0xFFFFF), -1).astype(np.int32)
+
+    def key_table_stats(self):
+        """{'big': window tables alive, 'small': small tables alive, 'small_built': ..., 'small_recycled': ...}"""
+        out = (ctypes.c_ulonglong * 4)()
+        self._ck(lib().fabgpu_key_table_stats(self._h, out))
+        return {"big": int(out[0]), "small": int(out[1]), "small_built": int(out[2]), "small_recycled": int(out[3])}
+
+    def small_slot_capacity(self):
+        return int(lib().fabgpu_small_slot_capacity(self._h))
+
     def host_key_slots(self, slot=0):
         p = ctypes.POINTER(ctypes.c_int32)()
         self._ck(lib().fabgpu_host_key_slots(self._h, ctypes.c_int(slot), ctypes.byref(p)))
@@ -231,7 +254,7 @@ class Context:
         self._ck(lib().fabgpu_verify_p256_keyed_async(self._h, ctypes.c_int(slot), ctypes.c_size_t(n)))
 
     def verify_p256_device_keyed(self, all_cached, d_key_slot, d_qx, d_qy, d_e, d_r, d_s, n, d_mask, d_off=0, stream=0, dev_index=0):
-        self._ck(lib().fabgpu_verify_p256_device_keyed(self._h, ctypes.c_int(dev_index), ctypes.c_int(1 if all_cached else 0),
+        self._ck(lib().fabgpu_verify_p256_device_keyed(self._h, ctypes.c_int(dev_index), ctypes.c_int(int(all_cached)),
                                                        ctypes.c_void_p(d_key_slot), ctypes.c_void_p(d_qx), ctypes.c_void_p(d_qy),
                                                        ctypes.c_void_p(d_e), ctypes.c_void_p(d_r), ctypes.c_void_p(d_s), ctypes.c_size_t(n),
                                                        ctypes.c_void_p(d_mask), ctypes.c_void_p(d_off), ctypes.c_void_p(stream)))

@@ -40,7 +40,7 @@ struct Seg { uint32_t off, len; };
 struct MspDev {
     const uint8_t* id_blob;       // serialized identities back to back
     const uint32_t* id_off;       // n_ids + 1
-    const int32_t* key_slot;      // per identity: key-table slot or -1
+    const int32_t* key_slot;      // per identity: big-table slot (>= 0), small-table code (<= -2) or -1
     const uint8_t* valid;         // per identity: identity.Validate()
     const int32_t* msp_code;      // per identity: code of its MSP id (equal ids <=> equal codes)
     const int32_t* group;         // per identity: de-duplication id -- Mspid + certificate (policy.go:380-386): two serializations of one
@@ -504,7 +504,7 @@ BD_HD void resolve_job(const uint8_t* base, uint32_t j, const RawJob* raw, const
     ja.identity[j] = identity;
     const int32_t slot = (identity >= 0 && ok) ? msp.key_slot[identity] : -1;
     ja.key_slot[j] = slot;
-    if (identity >= 0 && ok && slot < 0 && ja.qx) {
+    if (identity >= 0 && ok && slot == -1 && ja.qx) {
         for (int i = 0; i < 32; i++) { ja.qx[32 * (size_t)j + i] = msp.keys_xy[64 * (size_t)identity + i]; ja.qy[32 * (size_t)j + i] = msp.keys_xy[64 * (size_t)identity + 32 + i]; }
     }
 }

@@ -90,7 +90,7 @@ bccsp_gate_kernel(const uint8_t* __restrict__ sigs, const uint32_t* __restrict__
     }
     const int32_t slot = slot_of[ki];
     key_slot[i] = slot;
-    if (slot < 0 && qx) {
+    if (slot == -1 && qx) {                                       // only the generic arithmetic reads the key itself
         for (int k = 0; k < 32; k++) { qx[32 * (size_t)i + k] = keys_xy[64 * (size_t)ki + k]; qy[32 * (size_t)i + k] = keys_xy[64 * (size_t)ki + 32 + k]; }
     }
     pre[i] = 0;

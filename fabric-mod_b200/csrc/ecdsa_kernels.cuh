@@ -64,25 +64,30 @@ ecdsa_verify_kernel(const int32_t* __restrict__ key_slot, const uint8_t* __restr
     }
 }
 
-// ---- mixed batches: signatures without a key table, compacted ------------------------------------------------------------------
-// In a batch where only SOME keys own a table the generic kernel used to run over all n threads and return at once for the tabled ones;
-// with tabled and untabled signatures interleaved every warp still walked the whole generic path (255 doublings) for its untabled lanes:
-// a half-and-half batch cost as much as an all-generic one (bench e2e.mixed: 21 M/s).  Now the untabled indices are compacted first
-// (warp-aggregated append) and the generic arithmetic runs over whole warps of them; results are OR-ed into the mask words the key-table
-// kernel wrote (bit 0 for untabled signatures).
-__global__ void compact_untabled_kernel(const int32_t* __restrict__ key_slot, uint32_t n, uint32_t* __restrict__ idx, uint32_t* __restrict__ count,
-                                        const uint32_t* __restrict__ n_dev, uint32_t n_base)
+// ---- mixed batches: signatures without a big key table, compacted by class ------------------------------------------------------
+// key_slot codes (device side, after the host resolved the handles): >= 0 slot of a big window table (ecdsa_verify_cached_kernel);
+// -1 no table (generic arithmetic: 255 doublings); <= -2 small table number -2 - code (ecdsa_verify_small_kernel).
+// In a batch where only SOME keys own a big table the generic kernel used to run over all n threads and return at once for the tabled
+// ones; with the kinds interleaved every warp still walked the whole generic path for its untabled lanes: a half-and-half batch cost as
+// much as an all-generic one (bench e2e.mixed: 21 M/s).  Now the indices are compacted first (warp-aggregated append): the untabled
+// ones from the front of idx[0, n), the small-table ones from its back; counters at idx[n] and idx[n + 1].  Each class then runs over
+// whole warps; results are OR-ed into the mask words the big-table kernel wrote (bit 0 for everything that is not its own).
+__global__ void compact_classes_kernel(const int32_t* __restrict__ key_slot, uint32_t n, uint32_t* __restrict__ idx, uint32_t* __restrict__ counts,
+                                       const uint32_t* __restrict__ n_dev, uint32_t n_base)
 {
+    const uint32_t cap = n;                                    // the small-table indices grow down from idx[cap - 1]
     if (n_dev) n = min(n, n_base + *n_dev);
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool g = i < n && key_slot[i] < 0;
-    const uint32_t m = __ballot_sync(0xffffffffu, g);
-    if (m == 0) return;
-    const uint32_t lane = threadIdx.x & 31u;
-    uint32_t base = 0;
-    if (lane == 0) base = atomicAdd(count, (uint32_t)__popc(m));
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (g) idx[base + __popc(m & ((1u << lane) - 1u))] = i;
+    const int32_t ks = i < n ? key_slot[i] : 0;
+    const bool g = ks == -1, sm = ks <= -2;
+    const uint32_t mg = __ballot_sync(0xffffffffu, g), ms = __ballot_sync(0xffffffffu, sm);
+    if ((mg | ms) == 0) return;
+    const uint32_t lane = threadIdx.x & 31u, below = (1u << lane) - 1u;
+    uint32_t bg = 0, bs = 0;
+    if (lane == 0) { if (mg) bg = atomicAdd(counts, (uint32_t)__popc(mg)); if (ms) bs = atomicAdd(counts + 1, (uint32_t)__popc(ms)); }
+    bg = __shfl_sync(0xffffffffu, bg, 0); bs = __shfl_sync(0xffffffffu, bs, 0);
+    if (g) idx[bg + __popc(mg & below)] = i;
+    if (sm) idx[cap - 1u - (bs + __popc(ms & below))] = i;
 }
 
 #ifndef FAB_INDEXED_THREADS
@@ -100,6 +105,63 @@ ecdsa_verify_indexed_kernel(const uint32_t* __restrict__ idx, const uint32_t* __
     const uint32_t res = ecdsa_verify_one(load_be32(qx + o), load_be32(qy + o), load_be32(e + o), load_be32(r + o), load_be32(s + o), gtab);
     if (res == V_VALID) atomicOr(mask + (i >> 5), 1u << (i & 31u));
     else if (res == V_OFFCURVE && offcurve) atomicOr(offcurve + (i >> 5), 1u << (i & 31u));
+}
+
+// ---- small key tables (ecdsa_verify.cuh: FAB_WS, ecdsa_verify_one_small) ---------------------------------------------------------
+#ifndef FAB_SMALL_THREADS
+#define FAB_SMALL_THREADS 256
+#endif
+#ifndef FAB_SMALL_MINBLOCKS
+#define FAB_SMALL_MINBLOCKS 2
+#endif
+// idx != NULL: thread t takes signature idx[cap - 1 - t] for t < *count (the small-table list of compact_classes_kernel) and ORs its
+// verdict into the mask; idx == NULL: every signature of [0, n) has a small table (key_slot[i] <= -2), one ballot word per warp.
+__global__ void __launch_bounds__(FAB_SMALL_THREADS, FAB_SMALL_MINBLOCKS)
+ecdsa_verify_small_kernel(const uint32_t* __restrict__ idx, const uint32_t* __restrict__ count, uint32_t cap, const int32_t* __restrict__ key_slot,
+                          const uint8_t* __restrict__ e, const uint8_t* __restrict__ r, const uint8_t* __restrict__ s, uint32_t n,
+                          const aff* __restrict__ gtab, const aff* __restrict__ stab, uint32_t* __restrict__ mask, uint32_t* __restrict__ offcurve)
+{
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool act = idx ? (t < *count) : (t < n);
+    const uint32_t i = (idx && act) ? idx[cap - 1u - t] : t;
+    uint32_t res = V_INVALID;
+    if (act) {                                                     // one call site: a single expanded copy of the verification
+        const size_t o = (size_t)i * 32;
+        res = ecdsa_verify_one_small(stab + (size_t)(-2 - key_slot[i]) * FAB_S_POINTS, load_be32(e + o), load_be32(r + o), load_be32(s + o), gtab);
+    }
+    if (idx) {
+        if (res == V_VALID) atomicOr(mask + (i >> 5), 1u << (i & 31u));
+        else if (res == V_OFFCURVE && offcurve) atomicOr(offcurve + (i >> 5), 1u << (i & 31u));
+        return;
+    }
+    const uint32_t vmask = __ballot_sync(0xffffffffu, res == V_VALID), omask = __ballot_sync(0xffffffffu, res == V_OFFCURVE);
+    if ((threadIdx.x & 31u) == 0 && t < n) { mask[t >> 5] = vmask; if (offcurve) offcurve[t >> 5] = omask; }
+}
+
+// Build, stage 1: thread f derives the window bases of key keys_xy[f] (small_bases) into bases[f][.]; a key that is not a curve
+// point gets an all-zero bases[f][0] AND an all-zero first table entry (what ecdsa_verify_one_small reports as off-curve).
+__global__ void small_bases_kernel(const uint8_t* __restrict__ keys_xy, const int32_t* __restrict__ slots, int nkeys, aff* __restrict__ bases,
+                                   aff* __restrict__ stab)
+{
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= nkeys) return;
+    aff* b = bases + (size_t)f * FAB_S_WINDOWS;
+    if (!small_bases(load_be32(keys_xy + 64 * (size_t)f), load_be32(keys_xy + 64 * (size_t)f + 32), b)) {
+        aff z; z.x = u256_zero(); z.y = u256_zero();
+        b[0] = z;
+        stab[(size_t)slots[f] * FAB_S_POINTS] = z;
+    }
+}
+// Stage 2: thread (f, j) fills window j of the key's table (small_window).
+__global__ void __launch_bounds__(128)
+small_windows_kernel(const aff* __restrict__ bases, const int32_t* __restrict__ slots, int nkeys, aff* __restrict__ stab)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nkeys * FAB_S_WINDOWS) return;
+    const int f = t / FAB_S_WINDOWS, j = t % FAB_S_WINDOWS;
+    const aff first = bases[(size_t)f * FAB_S_WINDOWS];
+    if (u256_is_zero(first.x) && u256_is_zero(first.y)) return;
+    small_window(bases[t], stab + (size_t)slots[f] * FAB_S_POINTS + (size_t)j * FAB_S_HALF);
 }
 
 // ---- validity-bitmask exchange over peer memory (one process per GPU) -----------------------------------

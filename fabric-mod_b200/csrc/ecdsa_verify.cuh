@@ -232,6 +232,149 @@ FAB_HD uint32_t ecdsa_verify_one_cached(const aff* qtab, const u256& e, const u2
     return final_check(acc, r);
 }
 
+// ---- small key tables: the tier between "never seen" and a 64 MiB window table --------------------------------------------------
+// A key that recurs but not often enough to earn the big table (client / creator certificates: thousands of identities, a few
+// signatures per block each) gets FAB_S_WINDOWS windows of SIGNED FAB_WS-bit digits: entry (j, d) = d * 2^(FAB_WS j) * Q for
+// d = 1 .. 2^(FAB_WS-1); a negative digit is the same entry with Y negated.  FAB_WS = 6: 43 windows x 32 points = 86 KiB per key
+// (744 keys per 64 MiB), u2*Q = at most 43 mixed additions and no doublings, against 255 doublings + 52 additions of the generic
+// kernel; the table costs about nine generic verifications to build (small_bases + 43 x build_multiples_fast).
+// Windows cover 258 >= 257 bits, so the carry of the signed recoding is always absorbed by the last window.
+#ifndef FAB_WS
+#define FAB_WS 6
+#endif
+#define FAB_S_WINDOWS ((257 + FAB_WS - 1) / FAB_WS)
+#define FAB_S_HALF (1 << (FAB_WS - 1))
+#define FAB_S_POINTS (FAB_S_WINDOWS * FAB_S_HALF)
+
+// r += k * Q through Q's small table: signed FAB_WS-bit digits, least significant window first, the carry of a negative digit
+// moves into the next window (k < 2^256 and the windows cover 258 bits: the last one absorbs it).
+FAB_HD jac add_small_table(jac acc, const u256& k, const aff* stab)
+{
+    uint32_t kk[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) kk[i] = k.v[i];
+    uint32_t carry = 0;
+#pragma unroll 1
+    for (int j = 0; j < FAB_S_WINDOWS; j++) {
+        uint32_t d = (kk[0] & ((1u << FAB_WS) - 1u)) + carry;
+#pragma unroll
+        for (int i = 0; i < 7; i++) kk[i] = (kk[i] >> FAB_WS) | (kk[i + 1] << (32 - FAB_WS));
+        kk[7] >>= FAB_WS;
+        const bool neg = d > (uint32_t)FAB_S_HALF;
+        if (neg) d = (1u << FAB_WS) - d;
+        carry = neg ? 1u : 0u;
+        if (d) {
+            aff pt = stab[(size_t)j * FAB_S_HALF + (d - 1)];
+            if (neg) pt.y = fe_neg(pt.y);
+            acc = jac_add_aff(acc, pt);
+        }
+    }
+    return acc;
+}
+
+// Same verification with a small table.  An all-zero first entry marks a key that is not a curve point (small_bases_kernel wrote it).
+// One loop over both tables, like ecdsa_verify_one_cached (a single expanded copy of the point addition): 12 unsigned windows of u1 in
+// the generator's table, then FAB_S_WINDOWS signed windows of u2 in the key's.
+FAB_HD uint32_t ecdsa_verify_one_small(const aff* stab, const u256& e, const u256& r, const u256& s, const aff* gtab)
+{
+    const u256 n = sc_n();
+    if (u256_is_zero(r) || u256_is_zero(s) || !u256_lt(r, n) || !u256_lt(s, n)) return V_INVALID;
+    {
+        const aff first = stab[0];
+        if (u256_is_zero(first.x) && u256_is_zero(first.y)) return V_OFFCURVE;
+    }
+#if FAB_SAFEGCD
+    const u256 w = sc_inv_to_mont_safegcd(s);
+#else
+    const u256 w = sc_inv_to_mont(s);
+#endif
+    const u256 u1 = sc_mul(sc_reduce_once(e), w);
+    const u256 u2 = sc_mul(r, w);
+    jac acc = jac_infinity();
+#pragma unroll 1
+    for (int t = 0; t < 2; t++) {
+        uint32_t kk[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) kk[i] = t ? u2.v[i] : u1.v[i];
+        const aff* tab = t ? stab : gtab;
+        const uint32_t wbits = t ? FAB_WS : FAB_WG, dmask = (1u << wbits) - 1u;
+        const uint32_t stride = t ? (uint32_t)FAB_S_HALF : (uint32_t)FAB_G_ENTRIES;
+        const uint32_t half = t ? (uint32_t)FAB_S_HALF : 0xffffffffu;          // the generator's digits are unsigned: never "negative"
+        const int windows = t ? FAB_S_WINDOWS : FAB_G_WINDOWS;
+        uint32_t carry = 0;
+#pragma unroll 1
+        for (int j = 0; j < windows; j++) {
+            uint32_t d = (kk[0] & dmask) + carry;
+#pragma unroll
+            for (int i = 0; i < 7; i++) kk[i] = (kk[i] >> wbits) | (kk[i + 1] << (32u - wbits));
+            kk[7] >>= wbits;
+            const bool neg = d > half;
+            if (neg) d = (1u << wbits) - d;
+            carry = neg ? 1u : 0u;
+            if (d) {
+                aff pt = tab[(size_t)j * stride + (d - 1)];
+                if (neg) pt.y = fe_neg(pt.y);
+                acc = jac_add_aff_t<FAB_CACHED_INLINE != 0>(acc, pt);
+            }
+        }
+    }
+    return final_check(acc, r);
+}
+
+// Stage 1 of a small table, ONE thread per key: bases[j] = 2^(FAB_WS j) * Q (affine) for every window -- one chain of
+// FAB_WS * (FAB_S_WINDOWS - 1) doublings, the Z's removed by one shared inversion.  Returns false (and writes nothing) when
+// (x, y) is not a curve point.
+FAB_HD bool small_bases(const u256& x, const u256& y, aff* bases)
+{
+    const u256 p = fe_p();
+    if (!u256_lt(x, p) || !u256_lt(y, p)) return false;
+    aff q; q.x = fe_to_mont(x); q.y = fe_to_mont(y);
+    if (!aff_on_curve(q)) return false;
+    u256 zs[FAB_S_WINDOWS], ps[FAB_S_WINDOWS];
+    jac t = jac_from_aff(q);
+    u256 run = fe_one();
+    for (int j = 0; j < FAB_S_WINDOWS; j++) {
+        if (j) for (int b = 0; b < FAB_WS; b++) t = jac_double(t);
+        bases[j].x = t.X; bases[j].y = t.Y;
+        zs[j] = t.Z;
+        run = fe_mul(run, t.Z);
+        ps[j] = run;
+    }
+    u256 inv = fe_inv_safegcd(run);                 // a point of odd prime order never doubles to infinity: run != 0
+    for (int j = FAB_S_WINDOWS - 1; j >= 0; j--) {
+        const u256 zi = (j > 0) ? fe_mul(inv, ps[j - 1]) : inv;
+        if (j > 0) inv = fe_mul(inv, zs[j]);
+        const u256 zi2 = fe_sqr(zi);
+        bases[j].x = fe_mul(bases[j].x, zi2);
+        bases[j].y = fe_mul(bases[j].y, fe_mul(zi2, zi));
+    }
+    return true;
+}
+
+// Stage 2, one thread per (key, window): out[d-1] = d * base for d = 1 .. FAB_S_HALF (chain of mixed additions, one shared
+// division-step inversion; the scratch lives in the thread's frame).
+FAB_HD void small_window(const aff& base, aff* out)
+{
+    u256 zs[FAB_S_HALF], ps[FAB_S_HALF];
+    jac t = jac_from_aff(base);
+    u256 run = fe_one();
+    for (int d = 1; d <= FAB_S_HALF; d++) {
+        if (d > 1) t = jac_add_aff(t, base);         // d = 2 takes the doubling branch of the complete addition
+        out[d - 1].x = t.X; out[d - 1].y = t.Y;
+        zs[d - 1] = t.Z;
+        run = fe_mul(run, t.Z);
+        ps[d - 1] = run;
+    }
+    u256 inv = fe_inv_safegcd(run);
+    for (int d = FAB_S_HALF; d >= 1; d--) {
+        const u256 zi = (d > 1) ? fe_mul(inv, ps[d - 2]) : inv;
+        if (d > 1) inv = fe_mul(inv, zs[d - 1]);
+        const u256 zi2 = fe_sqr(zi);
+        out[d - 1].x = fe_mul(out[d - 1].x, zi2);
+        out[d - 1].y = fe_mul(out[d - 1].y, fe_mul(zi2, zi));
+    }
+}
+
 // Fixed-base table entry (window j, digit d in 1..FAB_G_ENTRIES) = d * 2^(FAB_WG*j) * G, affine Montgomery.
 FAB_HD aff table_entry(const aff& g, int wbits, int j, uint32_t d)
 {

@@ -42,7 +42,7 @@ struct DevSlot {
     uint32_t* d_mask = nullptr;
     uint32_t* d_off = nullptr;
     int32_t* d_key_slot = nullptr;
-    uint32_t* d_idx = nullptr;      // dev_cap + 1 words: compaction scratch of mixed batches
+    uint32_t* d_idx = nullptr;      // dev_cap + 2 words: compaction scratch of mixed batches
 };
 
 struct Device {
@@ -50,6 +50,12 @@ struct Device {
     aff* gtab = nullptr;
     int sms = 148;            // multiprocessors (launch shapes)
     aff* qtab = nullptr;      // key_slots tables of FAB_G_WINDOWS * FAB_G_ENTRIES points (per-key fixed-base tables)
+    // small key tables (FAB_S_POINTS points each): the pool, the build scratch (grown on demand) and the build stream.  Every
+    // enqueue that may read a small table first makes its stream wait for s_ev (the last build): builds are ordered among
+    // themselves by s_stream, so one event covers all earlier ones.
+    aff* stab = nullptr;
+    aff* s_bases = nullptr; uint8_t* s_keys = nullptr; int32_t* s_slots = nullptr; size_t s_cap = 0;
+    cudaStream_t s_stream = nullptr; cudaEvent_t s_ev = nullptr; bool s_ev_set = false;
     DevSlot slot[FABGPU_SLOTS];
     // bitmask exchange over peer memory (fabgpu_peer_mask_*): this rank's receive buffer, the peers' mapped ones
     struct Peer {
@@ -149,6 +155,19 @@ struct fabgpu_ctx {
     std::vector<uint32_t> slot_gen;          // bumped whenever a slot is recycled: handles carry the generation they were issued under
     unsigned long long tick = 0;
     int key_min_uses = 256;
+    // small-table cache (fabgpu_keys_register_small): same protocol as the big tables (tab_mu / mu), least-recently-used eviction
+    // in bulk.  A small handle is -2 - ((generation & 0x3ff) << 20 | slot); on the device the code is -2 - slot.
+    int small_slots = 0;
+    int small_min_uses = 4;                   // cumulative signatures of a key (over all calls) before it earns a small table; < 0: tier off
+    struct Key64 { uint8_t b[64]; bool operator==(const Key64& o) const { return memcmp(b, o.b, 64) == 0; } };
+    struct Key64Hash { size_t operator()(const Key64& k) const { uint64_t h; memcpy(&h, k.b + 8, 8); return (size_t)(h * 0x9E3779B97F4A7C15ull); } };
+    std::unordered_map<Key64, int, Key64Hash> small_map;
+    std::vector<Key64> small_key; std::vector<char> small_used;
+    std::vector<unsigned long long> small_tick;
+    std::vector<uint32_t> small_gen;
+    std::vector<int> small_free;
+    unsigned long long small_built = 0, small_recycled = 0;     // fabgpu_key_table_stats
+    std::unordered_map<Key64, uint32_t, Key64Hash> seen_uses;   // keys without any table: signatures seen so far (bounded, see resolve_key_tables)
     // key-table kernel (FABGPU_CACHED_KERNEL): 0 "jac" = Jacobian chain, one signature per thread (ecdsa_verify_cached_kernel) -- the DEFAULT: fastest at
     // every batch size measured on B200 (profiles/r2_kernel_variants.txt); 1 "ba" = batch-affine with CTA-shared inversions, 3 "ba2" = batch-affine, two
     // signatures per thread, 2 / 4 "l2" / "l4" = the Jacobian chain split over 2 / 4 lanes.  The alternatives stay selectable: they are the measurements.
@@ -180,7 +199,7 @@ struct fabgpu_ctx {
         int32_t* group = nullptr;                                     // de-duplication groups (fabgpu_msp_identity_groups), null = identity index
         uint8_t* ns_blob = nullptr; uint32_t* ns_off = nullptr; int32_t* ns_root = nullptr; int32_t n_ns = 0;    // fabgpu_namespace_policies
         uint64_t* ht_hash = nullptr; uint32_t ht_size = 0; int32_t n_ids = 0, n_nodes = 0, n_principals = 0; uint32_t channel_len = 0;
-        bool all_slots = true;
+        bool all_slots = true; int classes = 0;                    // which non-big classes the identities' keys fall in (CLASS_*)
     } dm;
     struct GateBufs {                          // fabgpu_bccsp_verify_batch with device-side gates
         size_t n_cap = 0, sig_cap = 0, dig_cap = 0, k_cap = 0;
@@ -274,12 +293,17 @@ inline void stage_fence()
 
 // mode: 0 = no signature has a key table (generic kernel only), 1 = all have one (cached kernel only),
 //       2 = mixed (cached kernel, then the generic kernel fills in the rest)
-enum { MODE_GENERIC = 0, MODE_CACHED = 1, MODE_MIXED = 2 };
+//       3 = all have a SMALL table (key_slot codes <= -2 throughout)
+// In mode 2 key_slot codes decide per signature: >= 0 big table, -1 none, <= -2 small table (see compact_classes_kernel).
+enum { MODE_GENERIC = 0, MODE_CACHED = 1, MODE_MIXED = 2, MODE_SMALL = 3 };
 
+// classes (mode 2 with scratch): which of the non-big classes the batch may contain -- a class the caller knows to be absent is not launched.
+enum { CLASS_SMALL = 1, CLASS_GENERIC = 2 };
 // n_dev / n_base (block path): the batch is [0, min(n, n_base + *n_dev)) with *n_dev written by an earlier kernel of the stream.
 int launch_verify(fabgpu_ctx* ctx, const Device& dv, int mode, const int32_t* key_slot, const uint8_t* qx, const uint8_t* qy,
                   const uint8_t* e, const uint8_t* r, const uint8_t* s, size_t n, uint32_t* mask, uint32_t* off, cudaStream_t st,
-                  const uint32_t* n_dev = nullptr, uint32_t n_base = 0, const PeerOut* peer = nullptr, uint32_t* scratch_idx = nullptr)
+                  const uint32_t* n_dev = nullptr, uint32_t n_base = 0, const PeerOut* peer = nullptr, uint32_t* scratch_idx = nullptr,
+                  int classes = CLASS_SMALL | CLASS_GENERIC)
 {
     PeerOut po; memset(&po, 0, sizeof po);
     const bool fused_peer = peer && mode == MODE_CACHED && (ctx->cached_kernel == 0 || ctx->cached_kernel == 1 || ctx->cached_kernel == 3) && n > 0 && !n_dev;
@@ -288,7 +312,14 @@ int launch_verify(fabgpu_ctx* ctx, const Device& dv, int mode, const int32_t* ke
         if (n_dev) { ctx->last_error = "peer exchange needs a host-known batch size"; return FABGPU_E_ARG; }
     }
     if (n == 0 && !peer) return FABGPU_OK;
-    if (mode != MODE_GENERIC && n > 0) {
+    if ((mode == MODE_MIXED || mode == MODE_SMALL) && dv.s_ev_set) CK(ctx, cudaStreamWaitEvent(st, dv.s_ev, 0));   // small tables still being built
+    if (mode == MODE_SMALL && n > 0) {
+        ecdsa_verify_small_kernel<<<(unsigned)((n + FAB_SMALL_THREADS - 1) / FAB_SMALL_THREADS), FAB_SMALL_THREADS, 0, st>>>(
+            nullptr, nullptr, 0u, key_slot, e, r, s, (uint32_t)n, dv.gtab, dv.stab, mask, off);
+        ctx->launches++;
+        CK(ctx, cudaGetLastError());
+    }
+    if (mode != MODE_GENERIC && mode != MODE_SMALL && n > 0) {
         // CTA shape (the kernel allows up to FAB_CACHED_THREADS = 512 threads at 128 registers, i.e. one such CTA per SM).
         // Measured on B200 (profiles/r1_kbench_table_widths.txt): a batch that fits one wave of 512-thread CTAs (64k: 128 CTAs)
         // finishes in 0.315 ms against 0.346 ms as 512 CTAs of 128 threads; beyond one wave 256-thread CTAs quantise best
@@ -320,13 +351,17 @@ int launch_verify(fabgpu_ctx* ctx, const Device& dv, int mode, const int32_t* ke
         CK(ctx, cudaGetLastError());
     }
     if (mode == MODE_MIXED && n > 0 && scratch_idx) {
-        // untabled signatures: compact their indices, then whole warps of generic arithmetic (see compact_untabled_kernel).
-        // scratch_idx: n + 1 words owned by the caller's slot (indices, then the counter).
-        CK(ctx, cudaMemsetAsync(scratch_idx + n, 0, 4, st));
-        compact_untabled_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(key_slot, (uint32_t)n, scratch_idx, scratch_idx + n, n_dev, n_base);
-        ecdsa_verify_indexed_kernel<<<(unsigned)((n + FAB_INDEXED_THREADS - 1) / FAB_INDEXED_THREADS), FAB_INDEXED_THREADS, 0, st>>>(
-            scratch_idx, scratch_idx + n, qx, qy, e, r, s, dv.gtab, mask, off);
-        ctx->launches += 2;
+        // signatures without a big table: compact their indices by class, then whole warps of small-table / generic arithmetic
+        // (see compact_classes_kernel).  scratch_idx: n + 2 words owned by the caller's slot (indices, then the two counters).
+        CK(ctx, cudaMemsetAsync(scratch_idx + n, 0, 8, st));
+        compact_classes_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(key_slot, (uint32_t)n, scratch_idx, scratch_idx + n, n_dev, n_base);
+        if (classes & CLASS_SMALL)
+            ecdsa_verify_small_kernel<<<(unsigned)((n + FAB_SMALL_THREADS - 1) / FAB_SMALL_THREADS), FAB_SMALL_THREADS, 0, st>>>(
+                scratch_idx, scratch_idx + n + 1, (uint32_t)n, key_slot, e, r, s, (uint32_t)n, dv.gtab, dv.stab, mask, off);
+        if (classes & CLASS_GENERIC)
+            ecdsa_verify_indexed_kernel<<<(unsigned)((n + FAB_INDEXED_THREADS - 1) / FAB_INDEXED_THREADS), FAB_INDEXED_THREADS, 0, st>>>(
+                scratch_idx, scratch_idx + n, qx, qy, e, r, s, dv.gtab, mask, off);
+        ctx->launches += 1 + ((classes & CLASS_SMALL) ? 1 : 0) + ((classes & CLASS_GENERIC) ? 1 : 0);
         CK(ctx, cudaGetLastError());
     } else if (mode == MODE_MIXED && n > 0) {
         // no scratch (launches on a caller's stream): the generic kernel filters on key_slot itself
@@ -361,19 +396,30 @@ int launch_verify(fabgpu_ctx* ctx, const Device& dv, int mode, const int32_t* ke
 // generation and silently degrades to "no table" (-1): the generic kernel then verifies against the Qx/Qy the caller
 // supplied, so a stale handle can cost speed but never correctness.
 inline int32_t make_handle(const fabgpu_ctx* ctx, int sl) { return (int32_t)(((ctx->slot_gen[sl] & 0x7ffffu) << 12) | (uint32_t)sl); }
+inline int32_t make_small_handle(const fabgpu_ctx* ctx, int sl) { return -2 - (int32_t)(((ctx->small_gen[sl] & 0x3ffu) << 20) | (uint32_t)sl); }
+// handle -> device code: >= 0 big-table slot, -2 - slot for a live small table, -1 otherwise (no table, stale handle)
 inline int32_t handle_to_slot(const fabgpu_ctx* ctx, int32_t h)
 {
+    if (h <= -2) {
+        const uint32_t v = (uint32_t)(-2 - h);
+        const int sl = (int)(v & 0xfffffu);
+        if (sl >= ctx->small_slots || (v >> 20) != (ctx->small_gen[sl] & 0x3ffu) || !ctx->small_used[sl]) return -1;
+        return -2 - sl;
+    }
     if (h < 0) return -1;
     const int sl = h & 0xfff;
     if (sl >= ctx->key_slots || ((uint32_t)h >> 12) != (ctx->slot_gen[sl] & 0x7ffffu) || ctx->slot_key[sl].empty()) return -1;
     return sl;
 }
 
-int slots_mode(const int32_t* ks, size_t n)
+int slots_mode(const int32_t* ks, size_t n, int* classes)
 {
-    bool any_c = false, any_g = false;
-    for (size_t i = 0; i < n; i++) { if (ks[i] >= 0) any_c = true; else any_g = true; }
-    return any_c ? (any_g ? MODE_MIXED : MODE_CACHED) : MODE_GENERIC;
+    bool any_c = false, any_g = false, any_s = false;
+    for (size_t i = 0; i < n; i++) { if (ks[i] >= 0) any_c = true; else if (ks[i] == -1) any_g = true; else any_s = true; }
+    *classes = (any_s ? CLASS_SMALL : 0) | (any_g ? CLASS_GENERIC : 0);
+    if (!any_c && !any_g && any_s) return MODE_SMALL;
+    if (!any_c && !any_s) return MODE_GENERIC;
+    return (any_g || any_s) ? MODE_MIXED : MODE_CACHED;
 }
 
 int enqueue_slot(fabgpu_ctx* ctx, int slot, size_t n, bool keyed)
@@ -390,13 +436,14 @@ int enqueue_slot(fabgpu_ctx* ctx, int slot, size_t n, bool keyed)
         HostSlot& hs = ctx->hslot[slot];
         CK(ctx, cudaSetDevice(dv.id));
         if (keyed) for (size_t i = begin; i < end; i++) hs.h_key_slot[i] = handle_to_slot(ctx, hs.h_key_slot[i]);   // handles -> live slots
-        const int mode = keyed ? slots_mode(hs.h_key_slot + begin, cnt) : MODE_GENERIC;
-        for (int a = (mode == MODE_CACHED ? 2 : 0); a < 5; a++)            // an all-cached range needs no Qx/Qy on the device
+        int classes = CLASS_GENERIC;
+        const int mode = keyed ? slots_mode(hs.h_key_slot + begin, cnt, &classes) : MODE_GENERIC;
+        for (int a = ((mode == MODE_CACHED || mode == MODE_SMALL) ? 2 : 0); a < 5; a++)     // a range where every key has a table needs no Qx/Qy on the device
             CK(ctx, cudaMemcpyAsync(ds.d_in[a], hs.h_in[a] + 32 * begin, 32 * cnt, cudaMemcpyHostToDevice, ds.stream));
         if (mode != MODE_GENERIC)
             CK(ctx, cudaMemcpyAsync(ds.d_key_slot, hs.h_key_slot + begin, 4 * cnt, cudaMemcpyHostToDevice, ds.stream));
         int rc = launch_verify(ctx, dv, mode, ds.d_key_slot, ds.d_in[0], ds.d_in[1], ds.d_in[2], ds.d_in[3], ds.d_in[4], cnt, ds.d_mask,
-                               ds.d_off, ds.stream, nullptr, 0, nullptr, ds.d_idx);
+                               ds.d_off, ds.stream, nullptr, 0, nullptr, ds.d_idx, classes);
         if (rc) return rc;
         const size_t words = (cnt + 31) / 32;
         CK(ctx, cudaMemcpyAsync(hs.h_mask + begin / 32, ds.d_mask, 4 * words, cudaMemcpyDeviceToHost, ds.stream));
@@ -456,6 +503,10 @@ void free_all(fabgpu_ctx* ctx)
         }
         if (dv.gtab) cudaFree(dv.gtab);
         if (dv.qtab) cudaFree(dv.qtab);
+        void* sm[] = {dv.stab, dv.s_bases, dv.s_keys, dv.s_slots};
+        for (void* q : sm) if (q) cudaFree(q);
+        if (dv.s_ev) cudaEventDestroy(dv.s_ev);
+        if (dv.s_stream) cudaStreamDestroy(dv.s_stream);
         for (auto& ds : dv.slot) {
             if (ds.d_key_slot) cudaFree(ds.d_key_slot);
             if (ds.d_idx) cudaFree(ds.d_idx);
@@ -511,6 +562,26 @@ int init_impl(fabgpu_ctx* ctx, const int* device_ids, int n_dev, size_t max_batc
         ctx->slot_key.assign(ctx->key_slots, std::string());
         ctx->slot_tick.assign(ctx->key_slots, 0ull);
         ctx->slot_gen.assign(ctx->key_slots, 0u);
+        // Small tables (FAB_S_POINTS * 64 bytes = 86 KiB each): default 16 384 of them (1.4 GB); FABGPU_SMALL_SLOTS = 0 turns the tier off.
+        const char* ss = getenv("FABGPU_SMALL_SLOTS");
+        ctx->small_slots = ss ? std::max(0, atoi(ss)) : 16384;
+        if (ctx->small_slots > (1 << 20)) ctx->small_slots = 1 << 20;       // a handle keeps 20 bits for the slot
+        for (int id : ids) {
+            size_t free_b = 0, total_b = 0;
+            CK(ctx, cudaSetDevice(id));
+            CK(ctx, cudaMemGetInfo(&free_b, &total_b));
+            const size_t per_small = (size_t)FAB_S_POINTS * sizeof(aff);
+            ctx->small_slots = (int)std::min<size_t>((size_t)ctx->small_slots, free_b / 8 / per_small);
+        }
+        ctx->small_key.assign(ctx->small_slots, fabgpu_ctx::Key64());
+        ctx->small_used.assign(ctx->small_slots, 0);
+        ctx->small_tick.assign(ctx->small_slots, 0ull);
+        ctx->small_gen.assign(ctx->small_slots, 0u);
+        ctx->small_free.clear();
+        for (int sl = ctx->small_slots - 1; sl >= 0; sl--) ctx->small_free.push_back(sl);
+        const char* smu = getenv("FABGPU_SMALL_MIN_USES");
+        ctx->small_min_uses = smu ? atoi(smu) : 4;
+        if (ctx->small_slots == 0) ctx->small_min_uses = -1;
         const char* mu = getenv("FABGPU_KEY_MIN_USES");
         ctx->key_min_uses = mu ? atoi(mu) : 256;           // a table costs about 300 generic verifications to build
         const char* ck = getenv("FABGPU_CACHED_KERNEL");
@@ -534,13 +605,16 @@ int init_impl(fabgpu_ctx* ctx, const int* device_ids, int n_dev, size_t max_batc
         }
         CK(ctx, cudaMalloc(&dv.gtab, tab_entries * sizeof(aff)));
         CK(ctx, cudaMalloc(&dv.qtab, (size_t)ctx->key_slots * FAB_Q_WINDOWS * FAB_Q_ENTRIES * sizeof(aff)));
+        if (ctx->small_slots > 0) CK(ctx, cudaMalloc(&dv.stab, (size_t)ctx->small_slots * FAB_S_POINTS * sizeof(aff)));
+        CK(ctx, cudaStreamCreateWithFlags(&dv.s_stream, cudaStreamNonBlocking));
+        CK(ctx, cudaEventCreateWithFlags(&dv.s_ev, cudaEventDisableTiming));
         for (auto& ds : dv.slot) {
             CK(ctx, cudaStreamCreateWithFlags(&ds.stream, cudaStreamNonBlocking));
             for (auto& p : ds.d_in) CK(ctx, cudaMalloc(&p, 32 * ctx->dev_cap));
             CK(ctx, cudaMalloc(&ds.d_mask, 4 * words));
             CK(ctx, cudaMalloc(&ds.d_off, 4 * words));
             CK(ctx, cudaMalloc(&ds.d_key_slot, 4 * ctx->dev_cap));
-            CK(ctx, cudaMalloc(&ds.d_idx, 4 * (ctx->dev_cap + 1)));
+            CK(ctx, cudaMalloc(&ds.d_idx, 4 * (ctx->dev_cap + 2)));
         }
 #if FAB_G_TWO_LEVEL
         {
@@ -758,6 +832,121 @@ int fabgpu_keys_register(fabgpu_ctx* ctx, const uint8_t* keys_xy, int K, int32_t
     return FABGPU_OK;
 }
 
+// Small tables for the keys that have none yet; handles_out[k] = small handle, or -1 when no slot could be had.  The builds are
+// enqueued on every device's build stream and NOT waited for: consumers order themselves behind Device::s_ev (launch_verify).
+// Caller holds neither tab_mu nor mu.
+static int small_register(fabgpu_ctx* ctx, const uint8_t* keys_xy, int K, int32_t* handles_out)
+{
+    if (ctx->small_slots <= 0) { for (int k = 0; k < K; k++) handles_out[k] = -1; return FABGPU_OK; }
+    {   // fast path under the shared lock: every key already owns a small table
+        std::shared_lock<std::shared_mutex> rl(ctx->tab_mu);
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        bool all = true;
+        fabgpu_ctx::Key64 kk;
+        for (int k = 0; k < K && all; k++) { memcpy(kk.b, keys_xy + 64 * (size_t)k, 64); all = ctx->small_map.count(kk) != 0; }
+        if (all) {
+            ctx->tick++;
+            for (int k = 0; k < K; k++) {
+                memcpy(kk.b, keys_xy + 64 * (size_t)k, 64);
+                const int sl = ctx->small_map[kk];
+                handles_out[k] = make_small_handle(ctx, sl); ctx->small_tick[sl] = ctx->tick;
+            }
+            return FABGPU_OK;
+        }
+    }
+    std::unique_lock<std::shared_mutex> wl(ctx->tab_mu);
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ctx->tick++;
+    std::vector<int> fresh; std::vector<int32_t> fresh_slot;
+    fabgpu_ctx::Key64 kk;
+    int need = 0;
+    for (int k = 0; k < K; k++) { memcpy(kk.b, keys_xy + 64 * (size_t)k, 64); if (!ctx->small_map.count(kk)) need++; }
+    if (need > (int)ctx->small_free.size()) {
+        // Out of free slots: recycle the least recently used ones in bulk (an eighth of the pool at least), after draining every device --
+        // a batch in flight may still read them.  Rare by construction: the pool holds thousands of keys.
+        for (auto& dv : ctx->devs) { CK(ctx, cudaSetDevice(dv.id)); CK(ctx, cudaDeviceSynchronize()); }
+        std::vector<int> order;
+        for (int sl = 0; sl < ctx->small_slots; sl++) if (ctx->small_used[sl]) order.push_back(sl);
+        // keys of THIS call keep their tables
+        for (int k = 0; k < K; k++) { memcpy(kk.b, keys_xy + 64 * (size_t)k, 64); auto it = ctx->small_map.find(kk); if (it != ctx->small_map.end()) ctx->small_tick[it->second] = ctx->tick; }
+        std::sort(order.begin(), order.end(), [&](int a, int b) { return ctx->small_tick[a] < ctx->small_tick[b]; });
+        const size_t want = std::max<size_t>((size_t)need - ctx->small_free.size(), (size_t)ctx->small_slots / 8);
+        for (size_t i = 0; i < order.size() && i < want; i++) {
+            const int sl = order[i];
+            if (ctx->small_tick[sl] == ctx->tick) break;
+            ctx->small_map.erase(ctx->small_key[sl]); ctx->small_used[sl] = 0; ctx->small_gen[sl]++;
+            ctx->small_free.push_back(sl); ctx->small_recycled++;
+        }
+    }
+    for (int k = 0; k < K; k++) {
+        memcpy(kk.b, keys_xy + 64 * (size_t)k, 64);
+        auto it = ctx->small_map.find(kk);
+        if (it != ctx->small_map.end()) { handles_out[k] = make_small_handle(ctx, it->second); ctx->small_tick[it->second] = ctx->tick; continue; }
+        handles_out[k] = -1;
+        if (ctx->small_free.empty()) continue;                      // more distinct keys in one call than the pool holds: stays generic
+        const int sl = ctx->small_free.back(); ctx->small_free.pop_back();
+        // mapped at once (a duplicate later in this call finds it); un-mapped again below if the enqueue fails
+        ctx->small_map[kk] = sl; ctx->small_key[sl] = kk; ctx->small_used[sl] = 1; ctx->small_tick[sl] = ctx->tick;
+        fresh.push_back(k); fresh_slot.push_back(sl);
+        handles_out[k] = make_small_handle(ctx, sl);
+    }
+    if (fresh.empty()) return FABGPU_OK;
+    const int F = (int)fresh.size();
+    ctx->small_built += (unsigned long long)F;
+    std::vector<uint8_t> fk(64 * (size_t)F);
+    for (int i = 0; i < F; i++) memcpy(fk.data() + 64 * (size_t)i, keys_xy + 64 * (size_t)fresh[i], 64);
+    auto build_on = [&](Device& dv) -> int {
+        CK(ctx, cudaSetDevice(dv.id));
+        if ((size_t)F > dv.s_cap) {
+            CK(ctx, cudaStreamSynchronize(dv.s_stream));            // an earlier build may still use the scratch
+            const size_t c = (size_t)F + (size_t)F / 2 + 256;
+            void* old[] = {dv.s_bases, dv.s_keys, dv.s_slots};
+            for (void* q : old) if (q) cudaFree(q);
+            dv.s_bases = nullptr; dv.s_keys = nullptr; dv.s_slots = nullptr; dv.s_cap = 0;
+            CK(ctx, cudaMalloc(&dv.s_bases, c * FAB_S_WINDOWS * sizeof(aff)));
+            CK(ctx, cudaMalloc(&dv.s_keys, 64 * c));
+            CK(ctx, cudaMalloc(&dv.s_slots, 4 * c));
+            dv.s_cap = c;
+        }
+        CK(ctx, cudaMemcpyAsync(dv.s_keys, fk.data(), fk.size(), cudaMemcpyHostToDevice, dv.s_stream));
+        CK(ctx, cudaMemcpyAsync(dv.s_slots, fresh_slot.data(), 4 * (size_t)F, cudaMemcpyHostToDevice, dv.s_stream));
+        CK(ctx, cudaStreamSynchronize(dv.s_stream));                // the sources are local vectors
+        small_bases_kernel<<<(unsigned)((F + 31) / 32), 32, 0, dv.s_stream>>>(dv.s_keys, dv.s_slots, F, dv.s_bases, dv.stab);
+        small_windows_kernel<<<(unsigned)(((size_t)F * FAB_S_WINDOWS + 127) / 128), 128, 0, dv.s_stream>>>(dv.s_bases, dv.s_slots, F, dv.stab);
+        ctx->launches += 2;
+        CK(ctx, cudaGetLastError());
+        CK(ctx, cudaEventRecord(dv.s_ev, dv.s_stream));
+        dv.s_ev_set = true;
+        return FABGPU_OK;
+    };
+    for (auto& dv : ctx->devs) {
+        const int rc = build_on(dv);
+        if (rc) {                                                   // nothing usable was built: give the slots back, the keys stay generic
+            for (int i = 0; i < F; i++) {
+                const int sl = fresh_slot[i];
+                ctx->small_map.erase(ctx->small_key[sl]); ctx->small_used[sl] = 0; ctx->small_gen[sl]++; ctx->small_free.push_back(sl);
+                handles_out[fresh[i]] = -1;
+            }
+            return rc;
+        }
+    }
+    return FABGPU_OK;
+}
+
+int fabgpu_keys_register_small(fabgpu_ctx* ctx, const uint8_t* keys_xy, int K, int32_t* handles_out)
+{
+    if (!ctx || K < 0 || (K && (!keys_xy || !handles_out))) return FABGPU_E_ARG;
+    return small_register(ctx, keys_xy, K, handles_out);
+}
+int fabgpu_small_slot_capacity(const fabgpu_ctx* ctx) { return ctx ? ctx->small_slots : 0; }
+int fabgpu_key_table_stats(fabgpu_ctx* ctx, unsigned long long out[4])
+{
+    if (!ctx || !out) return FABGPU_E_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    out[0] = ctx->key_map.size(); out[1] = ctx->small_map.size(); out[2] = ctx->small_built; out[3] = ctx->small_recycled;
+    return FABGPU_OK;
+}
+
 int fabgpu_wait(fabgpu_ctx* ctx, int slot)
 {
     if (!ctx || slot < 0 || slot >= FABGPU_SLOTS) return FABGPU_E_ARG;
@@ -822,7 +1011,7 @@ int fabgpu_verify_p256_device_keyed(fabgpu_ctx* ctx, int dev_index, int all_cach
     if (fault_injected()) { ctx->last_error = "fault injected (FABGPU_FAULT_INJECT=1)"; return FABGPU_E_INJECTED; }
     Device& dv = ctx->devs[dev_index];
     CK(ctx, cudaSetDevice(dv.id));
-    return launch_verify(ctx, dv, all_cached ? MODE_CACHED : MODE_MIXED, (const int32_t*)d_key_slot, (const uint8_t*)d_qx,
+    return launch_verify(ctx, dv, all_cached == 2 ? MODE_SMALL : (all_cached ? MODE_CACHED : MODE_MIXED), (const int32_t*)d_key_slot, (const uint8_t*)d_qx,
                          (const uint8_t*)d_qy, (const uint8_t*)d_e, (const uint8_t*)d_r, (const uint8_t*)d_s, n, (uint32_t*)d_mask,
                          (uint32_t*)d_offcurve, (cudaStream_t)cuda_stream);
 }
@@ -953,7 +1142,7 @@ static int gate_bufs_reserve(fabgpu_ctx* ctx, int slot, size_t n, size_t sig_byt
         rc |= grow_dev(ctx, gb.d_sig_off, 4 * (c + 1)); rc |= grow_dev(ctx, gb.d_dig_off, 4 * (c + 1)); rc |= grow_dev(ctx, gb.d_kidx, 4 * c);
         rc |= grow_dev(ctx, gb.d_status, c); rc |= grow_dev(ctx, gb.d_pre, c); rc |= grow_dev(ctx, gb.d_r, 32 * c); rc |= grow_dev(ctx, gb.d_s, 32 * c);
         rc |= grow_dev(ctx, gb.d_e, 32 * c); rc |= grow_dev(ctx, gb.d_qx, 32 * c); rc |= grow_dev(ctx, gb.d_qy, 32 * c); rc |= grow_dev(ctx, gb.d_ks, 4 * c);
-        rc |= grow_dev(ctx, gb.d_mask, c / 8 + 8); rc |= grow_dev(ctx, gb.d_off, c / 8 + 8); rc |= grow_dev(ctx, gb.d_idx, 4 * (c + 1));
+        rc |= grow_dev(ctx, gb.d_mask, c / 8 + 8); rc |= grow_dev(ctx, gb.d_off, c / 8 + 8); rc |= grow_dev(ctx, gb.d_idx, 4 * (c + 2));
         if (rc) return FABGPU_E_CUDA;
         gb.n_cap = c;
     }
@@ -991,10 +1180,15 @@ static int bccsp_device_submit(fabgpu_ctx* ctx, int slot, const uint8_t* keys_xy
     // stage: every host thread copies its slice of each array
     const int T = ctx->pool->size();
     bool all_slots = K > 0;
+    int classes = K > 0 ? 0 : CLASS_GENERIC;                  // which non-big classes the batch holds (signatures with a bad key index are decided by the gates)
     std::shared_lock<std::shared_mutex> rl(ctx->tab_mu);      // held until the verify kernel is enqueued: the slots cannot be recycled in between
     {
         std::lock_guard<std::mutex> lk(ctx->mu);
-        for (int k = 0; k < K; k++) { gb.h_slot_of[k] = handle_to_slot(ctx, slot_of[k]); if (gb.h_slot_of[k] < 0) all_slots = false; }
+        for (int k = 0; k < K; k++) {
+            gb.h_slot_of[k] = handle_to_slot(ctx, slot_of[k]);
+            if (gb.h_slot_of[k] < 0) all_slots = false;
+            if (gb.h_slot_of[k] == -1) classes |= CLASS_GENERIC; else if (gb.h_slot_of[k] <= -2) classes |= CLASS_SMALL;
+        }
     }
     if (K > 0 && !inplace) memcpy(gb.h_keys, keys_xy, 64 * (size_t)K);
     if (!inplace) ctx->pool->run([&](int tid) {
@@ -1019,12 +1213,12 @@ static int bccsp_device_submit(fabgpu_ctx* ctx, int slot, const uint8_t* keys_xy
         CK(ctx, cudaMemcpyAsync(gb.d_slot_of, gb.h_slot_of, 4 * (size_t)K, cudaMemcpyHostToDevice, st));
     }
     bdev::bccsp_gate_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(gb.d_sigs, gb.d_sig_off, gb.d_digs, gb.d_dig_off, gb.d_kidx, gb.d_slot_of, gb.d_keys, K,
-                                                                        (uint32_t)n, gb.d_r, gb.d_s, gb.d_e, gb.d_ks, all_slots ? nullptr : gb.d_qx,
-                                                                        all_slots ? nullptr : gb.d_qy, gb.d_pre, sig_base, dig_base);
+                                                                        (uint32_t)n, gb.d_r, gb.d_s, gb.d_e, gb.d_ks, (classes & CLASS_GENERIC) ? gb.d_qx : nullptr,
+                                                                        (classes & CLASS_GENERIC) ? gb.d_qy : nullptr, gb.d_pre, sig_base, dig_base);
     ctx->launches++;
     CK(ctx, cudaGetLastError());
     rc = launch_verify(ctx, dv, all_slots ? MODE_CACHED : MODE_MIXED, gb.d_ks, gb.d_qx, gb.d_qy, gb.d_e, gb.d_r, gb.d_s, n, gb.d_mask, gb.d_off, st, nullptr, 0, nullptr,
-                       gb.d_idx);
+                       gb.d_idx, classes ? classes : CLASS_GENERIC);
     if (rc) return rc;
     bdev::bccsp_status_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(gb.d_pre, gb.d_mask, gb.d_off, (uint32_t)n, gb.d_status);
     ctx->launches++;
@@ -1051,23 +1245,66 @@ static int bccsp_device_finish(fabgpu_ctx* ctx, int slot, uint8_t* status)
     return FABGPU_OK;
 }
 
-// Keys that recur (>= key_min_uses signatures in this call) or already own a table use the fixed-base kernel; this is what
-// KeyImport does once per identity in the Go provider.  slot_of[k]: handle of key k's table or -1.
+// Which table serves each key of a call.  slot_of[k]: handle of key k's big table (>= 0), of its small table (<= -2), or -1.
+//   * a key that already owns a table keeps using it, however few signatures it has in this call;
+//   * >= key_min_uses signatures in this call earn the big table (what KeyImport does once per identity in the Go provider);
+//   * otherwise the key's signatures are counted across calls, and small_min_uses of them earn a small table.
 static int resolve_key_tables(fabgpu_ctx* ctx, const uint8_t* keys_xy, int K, const int32_t* key_idx, size_t n, std::vector<int32_t>& slot_of)
 {
     slot_of.assign(K > 0 ? K : 0, -1);
     if (!(K > 0 && keys_xy && ctx->key_min_uses >= 0)) return FABGPU_OK;
     std::vector<uint32_t> uses(K, 0);
     for (size_t i = 0; i < n; i++) if (key_idx[i] >= 0 && key_idx[i] < K) uses[key_idx[i]]++;
-    std::vector<int> want;
-    for (int k = 0; k < K; k++) if (uses[k] >= (uint32_t)ctx->key_min_uses && uses[k] > 0) want.push_back(k);
-    if (want.empty() || (int)want.size() > ctx->key_slots) return FABGPU_OK;
-    std::vector<uint8_t> wk(64 * want.size());
-    std::vector<int32_t> ws(want.size(), -1);
-    for (size_t i = 0; i < want.size(); i++) memcpy(wk.data() + 64 * i, keys_xy + 64 * (size_t)want[i], 64);
-    int rc = fabgpu_keys_register(ctx, wk.data(), (int)want.size(), ws.data());
-    if (rc) return rc;
-    for (size_t i = 0; i < want.size(); i++) slot_of[want[i]] = ws[i];
+    std::vector<int> want_big, want_small;
+    {
+        std::shared_lock<std::shared_mutex> rl(ctx->tab_mu);
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        fabgpu_ctx::Key64 kk;
+        bool touched = false;
+        for (int k = 0; k < K; k++) {
+            if (!uses[k]) continue;
+            if (!ctx->key_map.empty() || uses[k] >= (uint32_t)ctx->key_min_uses) {
+                auto it = ctx->key_map.find(std::string((const char*)keys_xy + 64 * (size_t)k, 64));
+                if (it != ctx->key_map.end()) {
+                    if (!touched) { ctx->tick++; touched = true; }
+                    slot_of[k] = make_handle(ctx, it->second); ctx->slot_tick[it->second] = ctx->tick; continue;
+                }
+            }
+            if (uses[k] >= (uint32_t)ctx->key_min_uses) { want_big.push_back(k); continue; }
+            if (ctx->small_min_uses < 0) continue;
+            memcpy(kk.b, keys_xy + 64 * (size_t)k, 64);
+            auto sm = ctx->small_map.find(kk);
+            if (sm != ctx->small_map.end()) {
+                if (!touched) { ctx->tick++; touched = true; }
+                slot_of[k] = make_small_handle(ctx, sm->second); ctx->small_tick[sm->second] = ctx->tick; continue;
+            }
+            uint32_t total = uses[k];
+            if (total < (uint32_t)ctx->small_min_uses) {
+                if (ctx->seen_uses.size() > (1u << 20)) ctx->seen_uses.clear();     // bounded memory: forgetting only delays a table
+                uint32_t& c = ctx->seen_uses[kk];
+                c += uses[k]; total = c;
+            }
+            if (total >= (uint32_t)ctx->small_min_uses) { want_small.push_back(k); ctx->seen_uses.erase(kk); }
+        }
+    }
+    if (!want_big.empty() && (int)want_big.size() <= ctx->key_slots) {
+        std::vector<uint8_t> wk(64 * want_big.size());
+        std::vector<int32_t> ws(want_big.size(), -1);
+        for (size_t i = 0; i < want_big.size(); i++) memcpy(wk.data() + 64 * i, keys_xy + 64 * (size_t)want_big[i], 64);
+        int rc = fabgpu_keys_register(ctx, wk.data(), (int)want_big.size(), ws.data());
+        if (rc) return rc;
+        for (size_t i = 0; i < want_big.size(); i++) slot_of[want_big[i]] = ws[i];
+    } else if (ctx->small_min_uses >= 0) {
+        for (int k : want_big) want_small.push_back(k);              // more busy keys than big slots: the small tier takes them
+    }
+    if (!want_small.empty()) {
+        std::vector<uint8_t> wk(64 * want_small.size());
+        std::vector<int32_t> ws(want_small.size(), -1);
+        for (size_t i = 0; i < want_small.size(); i++) memcpy(wk.data() + 64 * i, keys_xy + 64 * (size_t)want_small[i], 64);
+        int rc = small_register(ctx, wk.data(), (int)want_small.size(), ws.data());
+        if (rc) return rc;
+        for (size_t i = 0; i < want_small.size(); i++) slot_of[want_small[i]] = ws[i];
+    }
     return FABGPU_OK;
 }
 
@@ -1388,7 +1625,14 @@ static int upload_msp(fabgpu_ctx* ctx, const uint8_t* id_blob, const uint32_t* i
     }
     dm.all_slots = true;
     std::vector<int32_t> raw_slot(n_ids > 0 ? n_ids : 1, -1);
-    for (int i = 0; i < n_ids; i++) { raw_slot[i] = handle_to_slot(ctx, ctx->identity_slot[i]); if (raw_slot[i] < 0) dm.all_slots = false; }
+    dm.classes = 0;
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        for (int i = 0; i < n_ids; i++) {
+            raw_slot[i] = handle_to_slot(ctx, ctx->identity_slot[i]);
+            if (raw_slot[i] < 0) { dm.all_slots = false; dm.classes |= raw_slot[i] == -1 ? CLASS_GENERIC : CLASS_SMALL; }
+        }
+    }
     auto up = [&](auto*& dst, const void* src, size_t bytes) -> int {
         CK(ctx, cudaMalloc(&dst, bytes + 8));                 // slack: word-wise readers may touch the aligned word past the end
         if (bytes) CK(ctx, cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice));
@@ -1444,8 +1688,12 @@ int fabgpu_msp_configure(fabgpu_ctx* ctx, const uint8_t* id_blob, const uint32_t
         ctx->identity_slot.assign(n_ids, -1);
     }
     // identities are long-lived: give every key a table now (what KeyImport does when the MSP deserialises an identity)
+    // An MSP with more identities than big-table slots (client certificates) puts them in the small tier instead.
     if (n_ids > 0 && n_ids <= ctx->key_slots) {
         int rc = fabgpu_keys_register(ctx, keys_xy, n_ids, ctx->identity_slot.data());
+        if (rc) return rc;
+    } else if (n_ids > 0 && n_ids <= ctx->small_slots && ctx->small_min_uses >= 0) {
+        int rc = small_register(ctx, keys_xy, n_ids, ctx->identity_slot.data());
         if (rc) return rc;
     }
     return upload_msp(ctx, id_blob, id_off, keys_xy, valid, n_ids, policy_nodes, n_nodes);
@@ -1532,22 +1780,28 @@ static int block_submit(fabgpu_ctx* ctx, int slot, const uint8_t* block, size_t 
         auto any_stale = [&] {
             std::lock_guard<std::mutex> lk(ctx->mu);
             for (size_t i = 0; i < ctx->identity_slot.size(); i++)
-                if (ctx->identity_slot[i] >= 0 && handle_to_slot(ctx, ctx->identity_slot[i]) < 0) return true;
+                if (ctx->identity_slot[i] != -1 && handle_to_slot(ctx, ctx->identity_slot[i]) == -1) return true;
             return false;
         };
         if (any_stale()) {
             rl.unlock();
             const int n_ids = (int)ctx->identity_slot.size();
-            int rc = fabgpu_keys_register(ctx, ctx->msp.keys_xy.data(), n_ids, ctx->identity_slot.data());     // exclusive; drains every stream first
+            const bool big = n_ids <= ctx->key_slots;
+            int rc = big ? fabgpu_keys_register(ctx, ctx->msp.keys_xy.data(), n_ids, ctx->identity_slot.data())     // exclusive; drains every stream first
+                         : small_register(ctx, ctx->msp.keys_xy.data(), n_ids, ctx->identity_slot.data());
             if (rc) return rc;
             rl.lock();
             std::vector<int32_t> raw(n_ids, -1);
-            dm.all_slots = true;
+            dm.all_slots = true; dm.classes = 0;
             {
                 std::lock_guard<std::mutex> lk(ctx->mu);      // a handle recycled again in the gap resolves to -1: that identity goes through the generic kernel
-                for (int i = 0; i < n_ids; i++) { raw[i] = handle_to_slot(ctx, ctx->identity_slot[i]); if (raw[i] < 0) dm.all_slots = false; }
+                for (int i = 0; i < n_ids; i++) {
+                    raw[i] = handle_to_slot(ctx, ctx->identity_slot[i]);
+                    if (raw[i] < 0) { dm.all_slots = false; dm.classes |= raw[i] == -1 ? CLASS_GENERIC : CLASS_SMALL; }
+                }
             }
-            // submitters are serialised by slot0_mu and the registration drained the device: no kernel is reading dm.key_slot now
+            // submitters are serialised by slot0_mu; blocks in flight on the other slots still read dm.key_slot: let them finish first
+            for (auto& dsx : dv.slot) CK(ctx, cudaStreamSynchronize(dsx.stream));
             CK(ctx, cudaMemcpy(dm.key_slot, raw.data(), 4 * (size_t)n_ids, cudaMemcpyHostToDevice));
         }
     }
@@ -1583,7 +1837,7 @@ static int block_submit(fabgpu_ctx* ctx, int slot, const uint8_t* block, size_t 
         rc |= grow_dev(ctx, db.d_sha, sizeof(bdev::ShaJobD) * (jc + 2 * tc)); rc |= grow_dev(ctx, db.d_dig, 32 * (jc + 2 * tc) + 64);
         rc |= grow_dev(ctx, db.d_r, 32 * jc); rc |= grow_dev(ctx, db.d_s, 32 * jc); rc |= grow_dev(ctx, db.d_qx, 32 * jc); rc |= grow_dev(ctx, db.d_qy, 32 * jc);
         rc |= grow_dev(ctx, db.d_gate, jc); rc |= grow_dev(ctx, db.d_ks, 4 * jc); rc |= grow_dev(ctx, db.d_ident, 4 * jc);
-        rc |= grow_dev(ctx, db.d_mask, jc / 8 + 8); rc |= grow_dev(ctx, db.d_off, jc / 8 + 8); rc |= grow_dev(ctx, db.d_counter, 16); rc |= grow_dev(ctx, db.d_idx, 4 * (jc + 1));
+        rc |= grow_dev(ctx, db.d_mask, jc / 8 + 8); rc |= grow_dev(ctx, db.d_off, jc / 8 + 8); rc |= grow_dev(ctx, db.d_counter, 16); rc |= grow_dev(ctx, db.d_idx, 4 * (jc + 2));
         rc |= grow_dev(ctx, db.d_flags, tc); rc |= grow_dev(ctx, db.d_hash, 8 * tc); rc |= grow_dev(ctx, db.d_seg, 8 * tc);
         rc |= grow_host(ctx, db.h_flags, tc); rc |= grow_host(ctx, db.h_hash, 8 * tc); rc |= grow_host(ctx, db.h_seg, 8 * tc);
         rc |= grow_host(ctx, db.h_counter, 16); rc |= grow_host(ctx, db.h_env_off, 8 * (tc + 1));
@@ -1602,8 +1856,9 @@ static int block_submit(fabgpu_ctx* ctx, int slot, const uint8_t* block, size_t 
     m.keys_xy = dm.keys_xy; m.ht_hash = dm.ht_hash; m.ht_idx = dm.ht_idx; m.ht_size = dm.ht_size; m.n_ids = dm.n_ids;
     bdev::PolicyDev pol; pol.nodes = dm.nodes; pol.n_nodes = dm.n_nodes; pol.principal_code = dm.principal_code; pol.n_principals = dm.n_principals;
     pol.ns_blob = dm.ns_blob; pol.ns_off = dm.ns_off; pol.ns_root = dm.ns_root; pol.n_ns = dm.n_ns;
-    bdev::JobArrays ja; ja.sha = db.d_sha; ja.r = db.d_r; ja.s = db.d_s; ja.key_slot = db.d_ks; ja.identity = db.d_ident; ja.qx = dm.all_slots ? nullptr : db.d_qx;
-    ja.qy = dm.all_slots ? nullptr : db.d_qy; ja.gate_ok = db.d_gate; ja.J_cap = (uint32_t)J_cap; ja.T = (uint32_t)T;
+    const bool need_q = (dm.classes & CLASS_GENERIC) != 0;   // only the generic arithmetic reads the key itself
+    bdev::JobArrays ja; ja.sha = db.d_sha; ja.r = db.d_r; ja.s = db.d_s; ja.key_slot = db.d_ks; ja.identity = db.d_ident; ja.qx = need_q ? db.d_qx : nullptr;
+    ja.qy = need_q ? db.d_qy : nullptr; ja.gate_ok = db.d_gate; ja.J_cap = (uint32_t)J_cap; ja.T = (uint32_t)T;
     const uint32_t cnt = (uint32_t)T, E_cap = (uint32_t)(J_cap - T);
     // One copy, then the walk.  (Copying in chunks with a walk per chunk was measured slower on B200 -- 1 chunk 1.93 ms, 4 chunks
     // 2.27 ms, 8 chunks 3.52 ms per 10k-tx block: hashing a 4.6 KB payload is ~250 us of dependent rounds per thread however few
@@ -1625,7 +1880,7 @@ static int block_submit(fabgpu_ctx* ctx, int slot, const uint8_t* block, size_t 
     CK(ctx, cudaGetLastError());
     if (db.use_ev) CK(ctx, cudaEventRecord(db.ev[3], st));
     int rc = launch_verify(ctx, dv, dm.all_slots ? MODE_CACHED : MODE_MIXED, db.d_ks, db.d_qx, db.d_qy, db.d_dig, db.d_r, db.d_s, J_cap, db.d_mask, db.d_off, st,
-                           db.d_counter, cnt, nullptr, db.d_idx);
+                           db.d_counter, cnt, nullptr, db.d_idx, dm.classes ? dm.classes : CLASS_GENERIC);
     if (rc) return rc;
     if (db.use_ev) CK(ctx, cudaEventRecord(db.ev[4], st));
     bdev::block_decide_kernel<<<(cnt + 127) / 128, 128, 0, st>>>(bb.d_block, db.d_txs, cnt, m, pol, db.d_mask, db.d_gate, db.d_ident, db.d_dig, (uint32_t)J_cap, db.d_flags,

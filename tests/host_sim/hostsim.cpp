@@ -177,6 +177,30 @@ void hostsim_verify_batch_ba(const uint8_t* qx, const uint8_t* qy, const uint8_t
     }
 }
 
+// Same batch through the small-table tier: per distinct key small_bases + small_window (exactly what small_bases_kernel and
+// small_windows_kernel do), then ecdsa_verify_one_small.  A key that is not a curve point gets the all-zero first entry.
+void hostsim_verify_batch_small(const uint8_t* qx, const uint8_t* qy, const uint8_t* e, const uint8_t* r, const uint8_t* s, int n, uint8_t* out)
+{
+    hostsim_build_gtable();
+    std::vector<std::pair<std::vector<uint8_t>, std::vector<aff>>> cache;
+    for (int i = 0; i < n; i++) {
+        size_t o = 32 * (size_t)i;
+        std::vector<uint8_t> key(qx + o, qx + o + 32);
+        key.insert(key.end(), qy + o, qy + o + 32);
+        const std::vector<aff>* tab = nullptr;
+        for (auto& c : cache) if (c.first == key) tab = &c.second;
+        if (!tab) {
+            std::vector<aff> t((size_t)FAB_S_POINTS), bases(FAB_S_WINDOWS);
+            memset(t.data(), 0, t.size() * sizeof(aff));
+            if (small_bases(u256_from_be(qx + o), u256_from_be(qy + o), bases.data()))
+                for (int j = 0; j < FAB_S_WINDOWS; j++) small_window(bases[j], t.data() + (size_t)j * FAB_S_HALF);
+            cache.emplace_back(key, std::move(t));
+            tab = &cache.back().second;
+        }
+        out[i] = (uint8_t)ecdsa_verify_one_small(tab->data(), u256_from_be(e + o), u256_from_be(r + o), u256_from_be(s + o), g_tab.data());
+    }
+}
+
 // field / scalar unit hooks: op 0 fe_mul, 1 fe_add, 2 fe_sub, 3 sc_mul, 4 fe_inv, 5 sc_inv_to_mont (b ignored for 4,5)
 void hostsim_fieldop(int op, const uint8_t* a, const uint8_t* b, int n, uint8_t* out)
 {
@@ -206,6 +230,19 @@ void hostsim_scalar_mul(const uint8_t* k, const uint8_t* px, const uint8_t* py, 
     build_q_table(tab, q);
     jac r = scalar_mul_var(u256_from_be(k), tab);
     if (jac_is_infinity(r)) { memset(ox, 0, 32); memset(oy, 0, 32); return; }
+    aff a = jac_to_aff(r);
+    u256_to_be(fe_from_mont(a.x), ox); u256_to_be(fe_from_mont(a.y), oy);
+}
+
+// k*P through P's small table (signed-window recoding check): affine plain coordinates, all-zero for infinity
+void hostsim_small_mul(const uint8_t* k, const uint8_t* px, const uint8_t* py, uint8_t* ox, uint8_t* oy)
+{
+    std::vector<aff> t((size_t)FAB_S_POINTS), bases(FAB_S_WINDOWS);
+    memset(ox, 0, 32); memset(oy, 0, 32);
+    if (!small_bases(u256_from_be(px), u256_from_be(py), bases.data())) return;
+    for (int j = 0; j < FAB_S_WINDOWS; j++) small_window(bases[j], t.data() + (size_t)j * FAB_S_HALF);
+    jac r = add_small_table(jac_infinity(), u256_from_be(k), t.data());
+    if (jac_is_infinity(r)) return;
     aff a = jac_to_aff(r);
     u256_to_be(fe_from_mont(a.x), ox); u256_to_be(fe_from_mont(a.y), oy);
 }

@@ -13,7 +13,7 @@ import vectors
 V_INVALID, V_VALID, V_OFFCURVE = 0, 1, 2
 
 
-@pytest.mark.parametrize("cached", [False, True, "ba"])
+@pytest.mark.parametrize("cached", [False, True, "ba", "small"])
 def test_constructed_edge_cases(cached):
     b = pkg().binding
     for c in vectors.build():
@@ -27,7 +27,7 @@ def test_constructed_edge_cases(cached):
             assert st == exp, c["name"]
             continue
         out = hostsim_verify(be32(c["qx"] % (1 << 256)), be32(c["qy"] % (1 << 256)), hash_to_e32(c["digest"]),
-                             np.frombuffer(r, np.uint8), np.frombuffer(s, np.uint8), cached=cached is True, ba=cached == "ba")[0]
+                             np.frombuffer(r, np.uint8), np.frombuffer(s, np.uint8), cached=cached is True, ba=cached == "ba", small=cached == "small")[0]
         got = {V_VALID: o.VALID, V_INVALID: o.INVALID, V_OFFCURVE: o.ERR_OFF_CURVE}[int(out)]
         assert got == exp, c["name"]
 
@@ -54,6 +54,9 @@ def test_tampered_matches_oracle_bit_for_bit():
     # and so does the batch-affine accumulation with its shared inversions (groups of 64 with a ragged tail: 768 + 37)
     out_b = hostsim_verify(w.qx(), w.qy(), w.digest, w.r, w.s, ba=True)
     assert (out_b == out).all()
+    # the small-table tier (signed 6-bit windows, no doublings)
+    out_s = hostsim_verify(w.qx(), w.qy(), w.digest, w.r, w.s, small=True)
+    assert (out_s == out).all()
     k = 37
     out_b2 = hostsim_verify(w.qx()[:k], w.qy()[:k], w.digest[:k], w.r[:k], w.s[:k], ba=True)
     assert (out_b2 == out[:k]).all()
@@ -77,3 +80,25 @@ def test_field_inversion_by_division_steps():
     R = 1 << 256
     for x, o_ in zip(xs, outs[1]):          # Montgomery in / out: x = a R  ->  a^-1 R = R^2 / x
         assert from_be(o_) == (R * R * pow(x, -1, p)) % p
+
+
+def test_small_table_signed_recoding_on_crafted_scalars():
+    """k * Q through the small table (signed 6-bit windows) for scalars that stress the recoding: runs of ones (carry through every
+    window), digits exactly at the sign boundary (32 / 33), the largest values below 2^256 (the last window absorbs the carry)."""
+    import ctypes
+    import random
+    from oracle import p256
+    from util import hostsim
+    hs = hostsim()
+    Q = p256.scalar_mult(0x1234567, (p256.GX, p256.GY))
+    rng = random.Random(99)
+    ks = [1, 2, 31, 32, 33, 63, 64, 65, (1 << 256) - 1, (1 << 256) - 2, p256.N - 1, p256.N, p256.N + 1, (1 << 255), (1 << 255) - 1,
+          int("100000" * 43, 2) & ((1 << 256) - 1), int("100001" * 43, 2) & ((1 << 256) - 1), int("011111" * 43, 2) & ((1 << 256) - 1),
+          int("111111" * 42, 2), 0]
+    ks += [rng.getrandbits(256) for _ in range(12)]
+    for k in ks:
+        ox = (ctypes.c_uint8 * 32)(); oy = (ctypes.c_uint8 * 32)()
+        hs.hostsim_small_mul(k.to_bytes(32, "big"), Q[0].to_bytes(32, "big"), Q[1].to_bytes(32, "big"), ox, oy)
+        exp = p256.scalar_mult(k % p256.N, Q)
+        got = (int.from_bytes(bytes(ox), "big"), int.from_bytes(bytes(oy), "big"))
+        assert got == ((0, 0) if exp is p256.INF else exp), hex(k)

@@ -52,11 +52,11 @@ def hostsim():
     return _HS
 
 
-def hostsim_verify(qx, qy, e, r, s, cached=False, ba=False):
+def hostsim_verify(qx, qy, e, r, s, cached=False, ba=False, small=False):
     arrs = [np.ascontiguousarray(a, dtype=np.uint8).reshape(-1, 32) for a in (qx, qy, e, r, s)]
     n = arrs[0].shape[0]
     out = np.zeros(n, np.uint8)
-    fn = hostsim().hostsim_verify_batch_ba if ba else (hostsim().hostsim_verify_batch_cached if cached else hostsim().hostsim_verify_batch)
+    fn = hostsim().hostsim_verify_batch_small if small else hostsim().hostsim_verify_batch_ba if ba else (hostsim().hostsim_verify_batch_cached if cached else hostsim().hostsim_verify_batch)
     fn(*[a.ctypes.data_as(ctypes.c_void_p) for a in arrs], ctypes.c_int(n), out.ctypes.data_as(ctypes.c_void_p))
     return out
 
