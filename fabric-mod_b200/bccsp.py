@@ -173,6 +173,11 @@ class GPUCSP:
         self.flush_seconds = flush_seconds
         self.fallbacks = 0
         self.batches = 0
+        # per-key use counts and table handles, as the Go provider keeps them on its key objects (gpu.go: smallTableAfterUses / tableAfterUses)
+        self._key_state = {}
+        self._key_mu = threading.Lock()
+        self.small_table_after_uses = 4
+        self.table_after_uses = 512
         self._reqs = None
         self._agg = None
 
@@ -217,7 +222,26 @@ class GPUCSP:
             self._agg = threading.Thread(target=self._aggregate, daemon=True)
             self._agg.start()
 
-    def VerifyQueued(self, k, signature, digest, opts=None, handle=-1):
+    def _handle_of(self, k):
+        """The table handle VerifyQueued passes for key k: none at first, a small table from the 4th verification on, the window table
+        from the 512th (gpu.go: registerSmallTable / registerTable)."""
+        with self._key_mu:
+            st = self._key_state.setdefault(k.xy, [0, -1])
+            st[0] += 1
+            uses = st[0]
+        if uses == self.small_table_after_uses:
+            h = int(self.ctx.keys_register_small(np.frombuffer(k.xy, np.uint8))[0])
+            with self._key_mu:
+                if h <= -2 and st[1] == -1:
+                    st[1] = h
+        elif uses == self.table_after_uses:
+            h = int(self.ctx.keys_register(np.frombuffer(k.xy, np.uint8))[0])
+            with self._key_mu:
+                if h >= 0:
+                    st[1] = h
+        return st[1]
+
+    def VerifyQueued(self, k, signature, digest, opts=None, handle=None):
         if k is None:
             return False, "Invalid Key. It must not be nil."
         if isinstance(k, ECDSAP256PrivateKey):
@@ -232,6 +256,8 @@ class GPUCSP:
         if st != binding.ST_VALID:
             return self.ctx.bccsp_verify(k.xy, signature, digest)          # rare: let the one-signature entry point word the error
         self._start_aggregator()
+        if handle is None:
+            handle = self._handle_of(k)
         d = bytes(digest[:32])
         req = {"k": k, "sig": signature, "dig": digest, "e": b"\x00" * (32 - len(d)) + d, "r": r, "s": s, "h": handle,
                "ev": threading.Event(), "res": None}

@@ -109,10 +109,10 @@ ecdsa_verify_indexed_kernel(const uint32_t* __restrict__ idx, const uint32_t* __
 
 // ---- small key tables (ecdsa_verify.cuh: FAB_WS, ecdsa_verify_one_small) ---------------------------------------------------------
 #ifndef FAB_SMALL_THREADS
-#define FAB_SMALL_THREADS 256
+#define FAB_SMALL_THREADS 512         // largest CTA the kernel may be launched with (launch_small picks the shape by batch size, like launch_verify)
 #endif
 #ifndef FAB_SMALL_MINBLOCKS
-#define FAB_SMALL_MINBLOCKS 2
+#define FAB_SMALL_MINBLOCKS 1
 #endif
 // idx != NULL: thread t takes signature idx[cap - 1 - t] for t < *count (the small-table list of compact_classes_kernel) and ORs its
 // verdict into the mask; idx == NULL: every signature of [0, n) has a small table (key_slot[i] <= -2), one ballot word per warp.

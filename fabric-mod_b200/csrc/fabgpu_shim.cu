@@ -158,6 +158,7 @@ struct fabgpu_ctx {
     // small-table cache (fabgpu_keys_register_small): same protocol as the big tables (tab_mu / mu), least-recently-used eviction
     // in bulk.  A small handle is -2 - ((generation & 0x3ff) << 20 | slot); on the device the code is -2 - slot.
     int small_slots = 0;
+    int small_threads_env = 0;                // FABGPU_SMALL_THREADS: CTA width of ecdsa_verify_small_kernel (0 = by batch size)
     int small_min_uses = 4;                   // cumulative signatures of a key (over all calls) before it earns a small table; < 0: tier off
     struct Key64 { uint8_t b[64]; bool operator==(const Key64& o) const { return memcmp(b, o.b, 64) == 0; } };
     struct Key64Hash { size_t operator()(const Key64& k) const { uint64_t h; memcpy(&h, k.b + 8, 8); return (size_t)(h * 0x9E3779B97F4A7C15ull); } };
@@ -297,6 +298,17 @@ inline void stage_fence()
 // In mode 2 key_slot codes decide per signature: >= 0 big table, -1 none, <= -2 small table (see compact_classes_kernel).
 enum { MODE_GENERIC = 0, MODE_CACHED = 1, MODE_MIXED = 2, MODE_SMALL = 3 };
 
+// CTA width of the small-table kernel: as for the key-table kernel, a batch that fits one wave of 512-thread CTAs runs best as such; when
+// the count is only an upper bound (compacted list) small CTAs spread the unknown number of live warps over all SMs.  FABGPU_SMALL_THREADS
+// overrides (measurements).
+unsigned small_threads(const fabgpu_ctx* ctx, const Device& dv, size_t n, bool bound_only)
+{
+    if (ctx->small_threads_env) return (unsigned)ctx->small_threads_env;
+    if (bound_only) return 128;
+    const size_t sms = (size_t)dv.sms;
+    if (n > sms * 384) return (n <= sms * FAB_SMALL_THREADS) ? FAB_SMALL_THREADS : 256;
+    return 128;
+}
 // classes (mode 2 with scratch): which of the non-big classes the batch may contain -- a class the caller knows to be absent is not launched.
 enum { CLASS_SMALL = 1, CLASS_GENERIC = 2 };
 // n_dev / n_base (block path): the batch is [0, min(n, n_base + *n_dev)) with *n_dev written by an earlier kernel of the stream.
@@ -314,7 +326,8 @@ int launch_verify(fabgpu_ctx* ctx, const Device& dv, int mode, const int32_t* ke
     if (n == 0 && !peer) return FABGPU_OK;
     if ((mode == MODE_MIXED || mode == MODE_SMALL) && dv.s_ev_set) CK(ctx, cudaStreamWaitEvent(st, dv.s_ev, 0));   // small tables still being built
     if (mode == MODE_SMALL && n > 0) {
-        ecdsa_verify_small_kernel<<<(unsigned)((n + FAB_SMALL_THREADS - 1) / FAB_SMALL_THREADS), FAB_SMALL_THREADS, 0, st>>>(
+        const unsigned sthreads = small_threads(ctx, dv, n, false);
+        ecdsa_verify_small_kernel<<<(unsigned)((n + sthreads - 1) / sthreads), sthreads, 0, st>>>(
             nullptr, nullptr, 0u, key_slot, e, r, s, (uint32_t)n, dv.gtab, dv.stab, mask, off);
         ctx->launches++;
         CK(ctx, cudaGetLastError());
@@ -355,9 +368,11 @@ int launch_verify(fabgpu_ctx* ctx, const Device& dv, int mode, const int32_t* ke
         // (see compact_classes_kernel).  scratch_idx: n + 2 words owned by the caller's slot (indices, then the two counters).
         CK(ctx, cudaMemsetAsync(scratch_idx + n, 0, 8, st));
         compact_classes_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(key_slot, (uint32_t)n, scratch_idx, scratch_idx + n, n_dev, n_base);
-        if (classes & CLASS_SMALL)
-            ecdsa_verify_small_kernel<<<(unsigned)((n + FAB_SMALL_THREADS - 1) / FAB_SMALL_THREADS), FAB_SMALL_THREADS, 0, st>>>(
+        if (classes & CLASS_SMALL) {
+            const unsigned sthreads = small_threads(ctx, dv, n, true);
+            ecdsa_verify_small_kernel<<<(unsigned)((n + sthreads - 1) / sthreads), sthreads, 0, st>>>(
                 scratch_idx, scratch_idx + n + 1, (uint32_t)n, key_slot, e, r, s, (uint32_t)n, dv.gtab, dv.stab, mask, off);
+        }
         if (classes & CLASS_GENERIC)
             ecdsa_verify_indexed_kernel<<<(unsigned)((n + FAB_INDEXED_THREADS - 1) / FAB_INDEXED_THREADS), FAB_INDEXED_THREADS, 0, st>>>(
                 scratch_idx, scratch_idx + n, qx, qy, e, r, s, dv.gtab, mask, off);
@@ -579,6 +594,8 @@ int init_impl(fabgpu_ctx* ctx, const int* device_ids, int n_dev, size_t max_batc
         ctx->small_gen.assign(ctx->small_slots, 0u);
         ctx->small_free.clear();
         for (int sl = ctx->small_slots - 1; sl >= 0; sl--) ctx->small_free.push_back(sl);
+        const char* sth = getenv("FABGPU_SMALL_THREADS");
+        if (sth) { const int v = atoi(sth); if (v == 64 || v == 128 || v == 256 || v == 512) ctx->small_threads_env = v; }
         const char* smu = getenv("FABGPU_SMALL_MIN_USES");
         ctx->small_min_uses = smu ? atoi(smu) : 4;
         if (ctx->small_slots == 0) ctx->small_min_uses = -1;
@@ -605,7 +622,16 @@ int init_impl(fabgpu_ctx* ctx, const int* device_ids, int n_dev, size_t max_batc
         }
         CK(ctx, cudaMalloc(&dv.gtab, tab_entries * sizeof(aff)));
         CK(ctx, cudaMalloc(&dv.qtab, (size_t)ctx->key_slots * FAB_Q_WINDOWS * FAB_Q_ENTRIES * sizeof(aff)));
-        if (ctx->small_slots > 0) CK(ctx, cudaMalloc(&dv.stab, (size_t)ctx->small_slots * FAB_S_POINTS * sizeof(aff)));
+        if (ctx->small_slots > 0) {
+            CK(ctx, cudaMalloc(&dv.stab, (size_t)ctx->small_slots * FAB_S_POINTS * sizeof(aff)));
+            // build scratch for up to 16 384 keys per registration, allocated once: growing it later costs a cudaFree + cudaMalloc pair in the
+            // middle of traffic (measured 86 ms on B200 with work in flight; profiles/r2_small_tables_shapes.txt)
+            const size_t c = (size_t)std::min(ctx->small_slots, 16384);
+            CK(ctx, cudaMalloc(&dv.s_bases, c * FAB_S_WINDOWS * sizeof(aff)));
+            CK(ctx, cudaMalloc(&dv.s_keys, 64 * c));
+            CK(ctx, cudaMalloc(&dv.s_slots, 4 * c));
+            dv.s_cap = c;
+        }
         CK(ctx, cudaStreamCreateWithFlags(&dv.s_stream, cudaStreamNonBlocking));
         CK(ctx, cudaEventCreateWithFlags(&dv.s_ev, cudaEventDisableTiming));
         for (auto& ds : dv.slot) {
@@ -854,8 +880,13 @@ static int small_register(fabgpu_ctx* ctx, const uint8_t* keys_xy, int K, int32_
             return FABGPU_OK;
         }
     }
+    const bool trace = getenv("FABGPU_TRACE") != nullptr;
+    auto tnow = [] { return std::chrono::steady_clock::now(); };
+    auto tus = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::micro>(b - a).count(); };
+    auto tr0 = tnow();
     std::unique_lock<std::shared_mutex> wl(ctx->tab_mu);
     std::lock_guard<std::mutex> lk(ctx->mu);
+    auto tr1 = tnow();
     ctx->tick++;
     std::vector<int> fresh; std::vector<int32_t> fresh_slot;
     fabgpu_ctx::Key64 kk;
@@ -895,8 +926,10 @@ static int small_register(fabgpu_ctx* ctx, const uint8_t* keys_xy, int K, int32_
     ctx->small_built += (unsigned long long)F;
     std::vector<uint8_t> fk(64 * (size_t)F);
     for (int i = 0; i < F; i++) memcpy(fk.data() + 64 * (size_t)i, keys_xy + 64 * (size_t)fresh[i], 64);
+    auto tr2 = tnow();
     auto build_on = [&](Device& dv) -> int {
         CK(ctx, cudaSetDevice(dv.id));
+        auto b0 = tnow();
         if ((size_t)F > dv.s_cap) {
             CK(ctx, cudaStreamSynchronize(dv.s_stream));            // an earlier build may still use the scratch
             const size_t c = (size_t)F + (size_t)F / 2 + 256;
@@ -908,15 +941,19 @@ static int small_register(fabgpu_ctx* ctx, const uint8_t* keys_xy, int K, int32_
             CK(ctx, cudaMalloc(&dv.s_slots, 4 * c));
             dv.s_cap = c;
         }
+        auto b1 = tnow();
         CK(ctx, cudaMemcpyAsync(dv.s_keys, fk.data(), fk.size(), cudaMemcpyHostToDevice, dv.s_stream));
         CK(ctx, cudaMemcpyAsync(dv.s_slots, fresh_slot.data(), 4 * (size_t)F, cudaMemcpyHostToDevice, dv.s_stream));
         CK(ctx, cudaStreamSynchronize(dv.s_stream));                // the sources are local vectors
+        auto b2 = tnow();
         small_bases_kernel<<<(unsigned)((F + 31) / 32), 32, 0, dv.s_stream>>>(dv.s_keys, dv.s_slots, F, dv.s_bases, dv.stab);
         small_windows_kernel<<<(unsigned)(((size_t)F * FAB_S_WINDOWS + 127) / 128), 128, 0, dv.s_stream>>>(dv.s_bases, dv.s_slots, F, dv.stab);
         ctx->launches += 2;
         CK(ctx, cudaGetLastError());
         CK(ctx, cudaEventRecord(dv.s_ev, dv.s_stream));
         dv.s_ev_set = true;
+        if (trace) fprintf(stderr, "[fabgpu] small_register F=%d: lock %.0f us, bookkeeping %.0f us, scratch %.0f us, copies %.0f us, launches %.0f us\n", F, tus(tr0, tr1),
+                           tus(tr1, tr2), tus(b0, b1), tus(b1, b2), tus(b2, tnow()));
         return FABGPU_OK;
     };
     for (auto& dv : ctx->devs) {
@@ -1105,7 +1142,7 @@ int fabgpu_verify_p256_device_keyed_allgather(fabgpu_ctx* ctx, int dev_index, in
     po.step = step;
     // the rank's own words also land in its local segment (buf[rank] is the local buffer): `mask` for the kernels is that segment
     uint32_t* local_seg = pr.local + po.gen_off + (size_t)pr.rank * pr.words_per_rank;
-    int rc = launch_verify(ctx, dv, all_cached ? MODE_CACHED : MODE_MIXED, (const int32_t*)d_key_slot, (const uint8_t*)d_qx, (const uint8_t*)d_qy,
+    int rc = launch_verify(ctx, dv, all_cached == 2 ? MODE_SMALL : (all_cached ? MODE_CACHED : MODE_MIXED), (const int32_t*)d_key_slot, (const uint8_t*)d_qx, (const uint8_t*)d_qy,
                            (const uint8_t*)d_e, (const uint8_t*)d_r, (const uint8_t*)d_s, n, local_seg, nullptr, st, nullptr, 0, &po);
     if (rc) return rc;
     peer_wait_kernel<<<1, 32, 0, st>>>(pr.local + po.flag_off, po.world, step, pr.timeout);

@@ -31,7 +31,7 @@ type device struct {
 type slot struct {
 	qx, qy, e, r, s []byte
 	mask, offcurve  []uint32
-	keySlot         []int32 // per signature: table slot of its key (fabgpu_keys_register) or -1
+	keySlot         []int32 // per signature: handle of its key's table (fabgpu_keys_register / fabgpu_keys_register_small) or -1
 }
 
 func openDevice(deviceIDs []int, maxBatch int) (*device, error) {
@@ -105,6 +105,15 @@ func (d *device) wait(i int) error {
 func (d *device) registerKey(xy *[64]byte) int32 {
 	var s C.int32_t = -1
 	if rc := C.fabgpu_keys_register(d.ctx, (*C.uint8_t)(unsafe.Pointer(&xy[0])), 1, &s); rc != C.FABGPU_OK {
+		return -1
+	}
+	return int32(s)
+}
+
+// registerSmallKey builds (or finds) the small table of one public key (handle <= -2); -1 means "no table".
+func (d *device) registerSmallKey(xy *[64]byte) int32 {
+	var s C.int32_t = -1
+	if rc := C.fabgpu_keys_register_small(d.ctx, (*C.uint8_t)(unsafe.Pointer(&xy[0])), 1, &s); rc != C.FABGPU_OK {
 		return -1
 	}
 	return int32(s)

@@ -39,13 +39,15 @@ type ecdsaP256Key struct {
 	bccsp.Key                  // the sw key: SKI, Bytes, ... are unchanged
 	pub       *ecdsa.PublicKey // parsed once at import
 	x, y      [32]byte
-	slot      int32  // handle of the key's fixed-base table on the device(s), -1 if none (fabgpu_keys_register); atomic
+	slot      int32  // handle of the key's table on the device(s): >= 0 window table (fabgpu_keys_register), <= -2 small table (fabgpu_keys_register_small), -1 none; atomic
 	uses      uint32 // verifications requested with this key; atomic
 }
 
 // A key gets its 64 MiB window table once it has been used this often: identities the MSP imports but that sign rarely
-// (or once) stay on the generic kernel instead of evicting the tables of the busy ones.
+// (or once) do not evict the tables of the busy ones.  Before that, from its smallTableAfterUses-th verification on, it owns a
+// SMALL table (86 KiB, no doublings: about five times the generic kernel's rate) -- the tier client / creator certificates live in.
 const tableAfterUses = 512
+const smallTableAfterUses = 4
 
 // fill32 writes v as 32 big-endian bytes (big.Int.FillBytes needs Go 1.15; the reference builds with 1.14).
 func fill32(dst *[32]byte, v *big.Int) {
@@ -178,7 +180,19 @@ func (csp *impl) registerTable(gk *ecdsaP256Key) {
 	var xy [64]byte
 	copy(xy[:32], gk.x[:])
 	copy(xy[32:], gk.y[:])
-	atomic.StoreInt32(&gk.slot, csp.dev.registerKey(&xy))
+	if h := csp.dev.registerKey(&xy); h >= 0 {
+		atomic.StoreInt32(&gk.slot, h) // a failed registration keeps whatever table the key already has
+	}
+}
+
+// registerSmallTable gives the key a small table (enqueued on the device's build stream; batches order themselves behind it).
+func (csp *impl) registerSmallTable(gk *ecdsaP256Key) {
+	var xy [64]byte
+	copy(xy[:32], gk.x[:])
+	copy(xy[32:], gk.y[:])
+	if h := csp.dev.registerSmallKey(&xy); h <= -2 {
+		atomic.CompareAndSwapInt32(&gk.slot, -1, h) // never replaces a window table
+	}
 }
 
 // Verify has exactly sw.CSP.Verify's contract (bccsp/sw/impl.go:247-270).
@@ -214,8 +228,11 @@ func (csp *impl) Verify(k bccsp.Key, signature, digest []byte, opts bccsp.Signer
 		atomic.AddUint64(&csp.CacheHits, 1)
 		return valid, nil
 	}
-	if atomic.AddUint32(&gk.uses, 1) == tableAfterUses {
-		go csp.registerTable(gk) // identities are verified many times (msp/cache keeps them): worth a table from here on
+	switch atomic.AddUint32(&gk.uses, 1) {
+	case smallTableAfterUses:
+		go csp.registerSmallTable(gk) // seen again: the cheap table
+	case tableAfterUses:
+		go csp.registerTable(gk) // identities are verified many times (msp/cache keeps them): worth the window table from here on
 	}
 	req := &request{key: gk, done: make(chan result, 1)}
 	fill32(&req.r, r)
