@@ -335,7 +335,7 @@ def run_gpu(args):
     gen_ms = sum(a.elapsed_time(b) for a, b in gev)
     assert bool((full == -1).all())
 
-    # small-table tier (keys that recur without being busy: 86 KiB per key, 43 mixed additions for u2*Q), same tuples, same hygiene
+    # small-table tier (keys that recur without being busy: 264 KiB per key, 33 mixed additions for u2*Q), same tuples, same hygiene
     small_ms = 0.0
     small_keys = 4096
     ssteps = max(3, min(args.steps, 10))
@@ -548,6 +548,7 @@ def run_gpu(args):
         ach_gbs = B * ALG_BYTES_PER_VERIFY / per_launch_s / 1e9
         mac_peak = 148 * 4 * 16 * sm_max * 1e6                  # 148 SMs x 4 SMSP x 16 lanes/clk (IMAD, rt 2)
         wg, wq = pkg.binding.build_info()
+        s_wb, s_nw, s_bytes = pkg.binding.Context.small_table_info()
         macs_cached = alg_macs_cached(wg, wq)
         n_gather = (256 + wg - 1) // wg + (256 + wq - 1) // wq
         ach_macs = B * macs_cached / per_launch_s
@@ -584,8 +585,9 @@ def run_gpu(args):
                                          "(a single 64k launch fills 512 of 592 resident CTA slots)" % (pkg.binding.SLOTS, pkg.binding.SLOTS)},
             "value_generic": value_generic,
             "value_small": (B * ssteps / (small_ms * 1e-3)) if small_ms else None,
-            "small": {"what": "ecdsa_verify_small_kernel, rank 0: %d signatures from %d keys that own a SMALL table (43 windows of signed 6-bit digits, 86 KiB per key): "
-                              "12 + 43 mixed additions per signature, no doublings; device-resident, L2 flushed between steps" % (B, small_keys),
+            "small": {"what": "ecdsa_verify_small_kernel, rank 0: %d signatures from %d keys that own a SMALL table (%d windows of signed %d-bit digits, %d KiB per key): "
+                              "%d + %d mixed additions per signature, no doublings; device-resident, L2 flushed between steps" % (
+                                  B, small_keys, s_nw, s_wb, s_bytes // 1024, (256 + wg - 1) // wg, s_nw),
                       "ms_per_step": (small_ms / ssteps) if small_ms else None, "steps": ssteps,
                       "register_and_first_batch_ms": small_register_ms if small_ms else None, "tables": ctx.key_table_stats()},
             "generic": {"what": "ecdsa_verify_kernel: no per-key table (first sight of a key); 255 doublings + 52 additions per signature",

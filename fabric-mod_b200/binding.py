@@ -27,7 +27,7 @@ EXPORTS = [
     "fabgpu_msp_identity_groups", "fabgpu_namespace_policies",
     "fabgpu_peer_mask_create", "fabgpu_peer_mask_open", "fabgpu_peer_mask_close", "fabgpu_verify_p256_device_keyed_allgather",
     "fabgpu_validate_block_async", "fabgpu_validate_envelopes_async", "fabgpu_validate_wait", "fabgpu_block_buffer_slot",
-    "fabgpu_keys_register_small", "fabgpu_small_slot_capacity", "fabgpu_key_table_stats",
+    "fabgpu_keys_register_small", "fabgpu_small_slot_capacity", "fabgpu_key_table_stats", "fabgpu_small_table_info",
 ]
 
 
@@ -238,6 +238,13 @@ class Context:
         out = (ctypes.c_ulonglong * 4)()
         self._ck(lib().fabgpu_key_table_stats(self._h, out))
         return {"big": int(out[0]), "small": int(out[1]), "small_built": int(out[2]), "small_recycled": int(out[3])}
+
+    @staticmethod
+    def small_table_info():
+        """(signed window bits, windows, bytes per table) of the small key tables."""
+        wb, nw, nb = ctypes.c_int(0), ctypes.c_int(0), ctypes.c_size_t(0)
+        lib().fabgpu_small_table_info(ctypes.byref(wb), ctypes.byref(nw), ctypes.byref(nb))
+        return wb.value, nw.value, nb.value
 
     def small_slot_capacity(self):
         return int(lib().fabgpu_small_slot_capacity(self._h))

@@ -235,16 +235,21 @@ FAB_HD uint32_t ecdsa_verify_one_cached(const aff* qtab, const u256& e, const u2
 // ---- small key tables: the tier between "never seen" and a 64 MiB window table --------------------------------------------------
 // A key that recurs but not often enough to earn the big table (client / creator certificates: thousands of identities, a few
 // signatures per block each) gets FAB_S_WINDOWS windows of SIGNED FAB_WS-bit digits: entry (j, d) = d * 2^(FAB_WS j) * Q for
-// d = 1 .. 2^(FAB_WS-1); a negative digit is the same entry with Y negated.  FAB_WS = 6: 43 windows x 32 points = 86 KiB per key
-// (744 keys per 64 MiB), u2*Q = at most 43 mixed additions and no doublings, against 255 doublings + 52 additions of the generic
-// kernel; the table costs about nine generic verifications to build (small_bases + 43 x build_multiples_fast).
-// Windows cover 258 >= 257 bits, so the carry of the signed recoding is always absorbed by the last window.
+// d = 1 .. 2^(FAB_WS-1); a negative digit is the same entry with Y negated.  u2*Q = at most FAB_S_WINDOWS mixed additions and no
+// doublings, against 255 doublings + 52 additions of the generic kernel.  Windows cover >= 257 bits, so the carry of the signed
+// recoding is always absorbed by the last window.  Width measured on B200 (profiles/r2_small_ws_sweep.txt, 64k / 256k batches):
+//   FAB_WS   windows   table      build      rate
+//     5        52       52 KiB   0.64 us   101 / 116 M/s
+//     6        43       86 KiB   0.74 us   115 / 132 M/s
+//     7        37      148 KiB   0.92 us   127 / 146 M/s
+//     8        33      264 KiB   1.51 us   135 / 157 M/s     <- default: 16 384 tables are 4.4 GB of the 180 GB
 #ifndef FAB_WS
-#define FAB_WS 6
+#define FAB_WS 8
 #endif
 #define FAB_S_WINDOWS ((257 + FAB_WS - 1) / FAB_WS)
 #define FAB_S_HALF (1 << (FAB_WS - 1))
 #define FAB_S_POINTS (FAB_S_WINDOWS * FAB_S_HALF)
+#define FAB_S_SEG 32                  /* entries normalised per shared inversion when a window is built (bounds the builder's frame) */
 
 // r += k * Q through Q's small table: signed FAB_WS-bit digits, least significant window first, the carry of a negative digit
 // moves into the next window (k < 2^256 and the windows cover 258 bits: the last one absorbs it).
@@ -322,7 +327,7 @@ FAB_HD uint32_t ecdsa_verify_one_small(const aff* stab, const u256& e, const u25
 }
 
 // Stage 1 of a small table, ONE thread per key: bases[j] = 2^(FAB_WS j) * Q (affine) for every window -- one chain of
-// FAB_WS * (FAB_S_WINDOWS - 1) doublings, the Z's removed by one shared inversion.  Returns false (and writes nothing) when
+// FAB_WS * (FAB_S_WINDOWS - 1) = 256 doublings, the Z's removed by one shared inversion.  Returns false (and writes nothing) when
 // (x, y) is not a curve point.
 FAB_HD bool small_bases(const u256& x, const u256& y, aff* bases)
 {
@@ -351,27 +356,30 @@ FAB_HD bool small_bases(const u256& x, const u256& y, aff* bases)
     return true;
 }
 
-// Stage 2, one thread per (key, window): out[d-1] = d * base for d = 1 .. FAB_S_HALF (chain of mixed additions, one shared
-// division-step inversion; the scratch lives in the thread's frame).
+// Stage 2, one thread per (key, window): out[d-1] = d * base for d = 1 .. FAB_S_HALF -- one chain of mixed additions, brought to
+// affine FAB_S_SEG entries at a time (one shared division-step inversion per segment; the scratch lives in the thread's frame).
 FAB_HD void small_window(const aff& base, aff* out)
 {
-    u256 zs[FAB_S_HALF], ps[FAB_S_HALF];
+    u256 zs[FAB_S_SEG], ps[FAB_S_SEG];
     jac t = jac_from_aff(base);
-    u256 run = fe_one();
-    for (int d = 1; d <= FAB_S_HALF; d++) {
-        if (d > 1) t = jac_add_aff(t, base);         // d = 2 takes the doubling branch of the complete addition
-        out[d - 1].x = t.X; out[d - 1].y = t.Y;
-        zs[d - 1] = t.Z;
-        run = fe_mul(run, t.Z);
-        ps[d - 1] = run;
-    }
-    u256 inv = fe_inv_safegcd(run);
-    for (int d = FAB_S_HALF; d >= 1; d--) {
-        const u256 zi = (d > 1) ? fe_mul(inv, ps[d - 2]) : inv;
-        if (d > 1) inv = fe_mul(inv, zs[d - 1]);
-        const u256 zi2 = fe_sqr(zi);
-        out[d - 1].x = fe_mul(out[d - 1].x, zi2);
-        out[d - 1].y = fe_mul(out[d - 1].y, fe_mul(zi2, zi));
+    for (int d0 = 1; d0 <= FAB_S_HALF; d0 += FAB_S_SEG) {
+        const int cnt = (FAB_S_HALF - d0 + 1 < FAB_S_SEG) ? (FAB_S_HALF - d0 + 1) : FAB_S_SEG;
+        u256 run = fe_one();
+        for (int k = 0; k < cnt; k++) {
+            if (d0 + k > 1) t = jac_add_aff(t, base);    // d = 2 takes the doubling branch of the complete addition
+            out[d0 + k - 1].x = t.X; out[d0 + k - 1].y = t.Y;
+            zs[k] = t.Z;
+            run = fe_mul(run, t.Z);
+            ps[k] = run;
+        }
+        u256 inv = fe_inv_safegcd(run);
+        for (int k = cnt - 1; k >= 0; k--) {
+            const u256 zi = (k > 0) ? fe_mul(inv, ps[k - 1]) : inv;
+            if (k > 0) inv = fe_mul(inv, zs[k]);
+            const u256 zi2 = fe_sqr(zi);
+            out[d0 + k - 1].x = fe_mul(out[d0 + k - 1].x, zi2);
+            out[d0 + k - 1].y = fe_mul(out[d0 + k - 1].y, fe_mul(zi2, zi));
+        }
     }
 }
 

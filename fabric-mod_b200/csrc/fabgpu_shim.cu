@@ -577,7 +577,7 @@ int init_impl(fabgpu_ctx* ctx, const int* device_ids, int n_dev, size_t max_batc
         ctx->slot_key.assign(ctx->key_slots, std::string());
         ctx->slot_tick.assign(ctx->key_slots, 0ull);
         ctx->slot_gen.assign(ctx->key_slots, 0u);
-        // Small tables (FAB_S_POINTS * 64 bytes = 86 KiB each): default 16 384 of them (1.4 GB); FABGPU_SMALL_SLOTS = 0 turns the tier off.
+        // Small tables (FAB_S_POINTS * 64 bytes = 264 KiB each): default 16 384 of them (4.4 GB); FABGPU_SMALL_SLOTS = 0 turns the tier off.
         const char* ss = getenv("FABGPU_SMALL_SLOTS");
         ctx->small_slots = ss ? std::max(0, atoi(ss)) : 16384;
         if (ctx->small_slots > (1 << 20)) ctx->small_slots = 1 << 20;       // a handle keeps 20 bits for the slot
@@ -976,6 +976,12 @@ int fabgpu_keys_register_small(fabgpu_ctx* ctx, const uint8_t* keys_xy, int K, i
     return small_register(ctx, keys_xy, K, handles_out);
 }
 int fabgpu_small_slot_capacity(const fabgpu_ctx* ctx) { return ctx ? ctx->small_slots : 0; }
+void fabgpu_small_table_info(int* window_bits, int* windows, size_t* table_bytes)
+{
+    if (window_bits) *window_bits = FAB_WS;
+    if (windows) *windows = FAB_S_WINDOWS;
+    if (table_bytes) *table_bytes = (size_t)FAB_S_POINTS * sizeof(aff);
+}
 int fabgpu_key_table_stats(fabgpu_ctx* ctx, unsigned long long out[4])
 {
     if (!ctx || !out) return FABGPU_E_ARG;

@@ -45,7 +45,7 @@ type ecdsaP256Key struct {
 
 // A key gets its 64 MiB window table once it has been used this often: identities the MSP imports but that sign rarely
 // (or once) do not evict the tables of the busy ones.  Before that, from its smallTableAfterUses-th verification on, it owns a
-// SMALL table (86 KiB, no doublings: about five times the generic kernel's rate) -- the tier client / creator certificates live in.
+// SMALL table (264 KiB, no doublings: more than five times the generic kernel's rate) -- the tier client / creator certificates live in.
 const tableAfterUses = 512
 const smallTableAfterUses = 4
 

@@ -105,18 +105,20 @@ int fabgpu_verify_p256_device(fabgpu_ctx* ctx, int dev_index, const void* d_qx, 
  * so a stale handle costs speed, never correctness.  Capacity: env FABGPU_KEY_SLOTS (default 256, at most 4096). */
 int fabgpu_keys_register(fabgpu_ctx* ctx, const uint8_t* keys_xy, int K, int32_t* slots_out);
 int fabgpu_key_slot_capacity(const fabgpu_ctx* ctx);
-/* The tier between "never seen" and a window table: a SMALL table (43 windows of signed 6-bit digits, 86 KiB, about nine generic
- * verifications to build) makes u2*Q 43 mixed additions and no doublings.  Meant for keys that recur without being busy -- client /
+/* The tier between "never seen" and a window table: a SMALL table (33 windows of signed 8-bit digits, 264 KiB, built in
+ * about 1.5 us of GPU time) makes u2*Q 33 mixed additions and no doublings.  Meant for keys that recur without being busy -- client /
  * creator certificates, thousands of identities with a few signatures per block each (the reference caches exactly those identities:
  * msp/cache/cache.go:38-129).  handles_out[k] <= -2 is the key's small HANDLE (-2 - ((generation << 20) | slot)), -1 = no slot could
  * be had; every entry point that takes key handles accepts both kinds.  A key that is not a curve point still gets a handle: its
  * signatures are reported off-curve, exactly as by the generic kernel.  The build is enqueued, not waited for; consumers are ordered
  * behind it on the device.  fabgpu_bccsp_verify_batch* give a key a small table by themselves once FABGPU_SMALL_MIN_USES (default 4)
  * of its signatures have been seen without a window table; fabgpu_msp_configure uses small tables when the MSP holds more identities
- * than window-table slots.  Capacity: env FABGPU_SMALL_SLOTS (default 16 384 = 1.4 GB per device; 0 turns the tier off); least recently
+ * than window-table slots.  Capacity: env FABGPU_SMALL_SLOTS (default 16 384 = 4.4 GB per device; 0 turns the tier off); least recently
  * used tables are recycled in bulk (stale handles are detected like the big ones). */
 int fabgpu_keys_register_small(fabgpu_ctx* ctx, const uint8_t* keys_xy, int K, int32_t* handles_out);
 int fabgpu_small_slot_capacity(const fabgpu_ctx* ctx);
+/* Build constants of the small tables: signed window width in bits, number of windows, bytes per table. */
+void fabgpu_small_table_info(int* window_bits, int* windows, size_t* table_bytes);
 /* out[0] = window tables alive, out[1] = small tables alive, out[2] = small tables built so far, out[3] = small tables recycled. */
 int fabgpu_key_table_stats(fabgpu_ctx* ctx, unsigned long long out[4]);
 /* Pinned int32[max_batch] of one slot: key_slot[i] = handle of signature i's key (from fabgpu_keys_register), or -1.

@@ -1,4 +1,4 @@
-"""GPU: the small-table tier (signed 6-bit windows, fabgpu_keys_register_small; ecdsa_verify_small_kernel) against the oracle, through
+"""GPU: the small-table tier (signed 8-bit windows, fabgpu_keys_register_small; ecdsa_verify_small_kernel) against the oracle, through
 every entry point that takes key handles.  Same bar as the other tiers: bit-exact."""
 import os
 
@@ -170,4 +170,27 @@ def test_block_prepass_with_more_identities_than_window_tables():
     other = workload.Workload(128, 64, seed=173)
     assert (c.keys_register_small(other.keys_xy) <= -2).all()      # recycles the identities' tables
     assert c.validate_block(blk).tolist() == exp.tolist()
+    c.close()
+
+
+def test_config5_shape_through_small_tables_full_size():
+    """BASELINE.json configs[4]'s size (262 144 signatures, 5 % tampered r) with every key in the small tier (8 192 keys, 32 signatures
+    each): statuses equal the C oracle's bit for bit, plus the size-independent properties -- no tampered signature accepted, every
+    untouched one accepted."""
+    n = 1 << 18
+    w = workload.Workload(n, 8192, seed=workload.DEFAULT_SEED + 21, nthreads=os.cpu_count())
+    picked = w.tamper_r(0.05)
+    exp = fast.verify_batch(w.keys_xy, w.key_idx, w.digest, w.dig_off(), w.sigs, w.sig_off, nthreads=os.cpu_count())
+    assert int((exp != o.VALID).sum()) == len(picked) and 12000 < len(picked) < 14500
+    c = pkg().binding.Context(max_batch=n)
+    st = c.bccsp_verify_batch(w.keys_xy, w.key_idx, w.digest, w.dig_off(), w.sigs, w.sig_off)     # 32 signatures per key: small tables at first sight
+    assert (st == exp).all()
+    stats = c.key_table_stats()
+    assert stats["small"] == 8192 and stats["big"] == 0
+    hs = c.keys_register_small(w.keys_xy)
+    hb = _fill(c, 0, w, hs[w.key_idx])
+    c.verify_p256_keyed(0, n)
+    bits = mask_bits(hb["mask"], n)
+    assert (hb["mask"][: n // 32] == fast.valid_mask(exp)).all()
+    assert int(bits.sum()) == n - len(picked) and bits[picked].sum() == 0
     c.close()

@@ -54,7 +54,7 @@ def test_tampered_matches_oracle_bit_for_bit():
     # and so does the batch-affine accumulation with its shared inversions (groups of 64 with a ragged tail: 768 + 37)
     out_b = hostsim_verify(w.qx(), w.qy(), w.digest, w.r, w.s, ba=True)
     assert (out_b == out).all()
-    # the small-table tier (signed 6-bit windows, no doublings)
+    # the small-table tier (signed windows, no doublings)
     out_s = hostsim_verify(w.qx(), w.qy(), w.digest, w.r, w.s, small=True)
     assert (out_s == out).all()
     k = 37
@@ -83,7 +83,7 @@ def test_field_inversion_by_division_steps():
 
 
 def test_small_table_signed_recoding_on_crafted_scalars():
-    """k * Q through the small table (signed 6-bit windows) for scalars that stress the recoding: runs of ones (carry through every
+    """k * Q through the small table (signed FAB_WS-bit windows; the host build uses the product's width) for scalars that stress the recoding: runs of ones (carry through every
     window), digits exactly at the sign boundary (32 / 33), the largest values below 2^256 (the last window absorbs the carry)."""
     import ctypes
     import random
@@ -94,7 +94,8 @@ def test_small_table_signed_recoding_on_crafted_scalars():
     rng = random.Random(99)
     ks = [1, 2, 31, 32, 33, 63, 64, 65, (1 << 256) - 1, (1 << 256) - 2, p256.N - 1, p256.N, p256.N + 1, (1 << 255), (1 << 255) - 1,
           int("100000" * 43, 2) & ((1 << 256) - 1), int("100001" * 43, 2) & ((1 << 256) - 1), int("011111" * 43, 2) & ((1 << 256) - 1),
-          int("111111" * 42, 2), 0]
+          int("111111" * 42, 2), 0,
+          int("10000000" * 32, 2), int("10000001" * 32, 2), int("01111111" * 32, 2), int("11111111" * 31 + "11111110", 2), int("10000000" * 31 + "01111111", 2)]
     ks += [rng.getrandbits(256) for _ in range(12)]
     for k in ks:
         ox = (ctypes.c_uint8 * 32)(); oy = (ctypes.c_uint8 * 32)()
