@@ -176,7 +176,7 @@ class GPUCSP:
         # per-key use counts and table handles, as the Go provider keeps them on its key objects (gpu.go: smallTableAfterUses / tableAfterUses)
         self._key_state = {}
         self._key_mu = threading.Lock()
-        self.small_table_after_uses = 4
+        self.small_table_after_uses = 32
         self.table_after_uses = 512
         self._reqs = None
         self._agg = None
@@ -223,7 +223,7 @@ class GPUCSP:
             self._agg.start()
 
     def _handle_of(self, k):
-        """The table handle VerifyQueued passes for key k: none at first, a small table from the 4th verification on, the window table
+        """The table handle VerifyQueued passes for key k: none at first, a small table from the 32nd verification on, the window table
         from the 512th (gpu.go: registerSmallTable / registerTable)."""
         with self._key_mu:
             st = self._key_state.setdefault(k.xy, [0, -1])

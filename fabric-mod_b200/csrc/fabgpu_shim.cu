@@ -159,7 +159,11 @@ struct fabgpu_ctx {
     // in bulk.  A small handle is -2 - ((generation & 0x3ff) << 20 | slot); on the device the code is -2 - slot.
     int small_slots = 0;
     int small_threads_env = 0;                // FABGPU_SMALL_THREADS: CTA width of ecdsa_verify_small_kernel (0 = by batch size)
-    int small_min_uses = 4;                   // cumulative signatures of a key (over all calls) before it earns a small table; < 0: tier off
+    // Cumulative signatures of a key (over all calls) before it earns a small table; < 0: tier off.  A table costs about as much GPU time as 37 generic
+    // verifications (1.5 us against 41 ns) and saves 34 ns per later signature: 32 is the rent-or-buy point -- by then the key has cost as much on the
+    // generic kernel as its table does, so building is at most twice the optimum whatever the key does next, and a block full of one-off keys is
+    // not slowed down by thousands of useless builds.
+    int small_min_uses = 32;
     struct Key64 { uint8_t b[64]; bool operator==(const Key64& o) const { return memcmp(b, o.b, 64) == 0; } };
     struct Key64Hash { size_t operator()(const Key64& k) const { uint64_t h; memcpy(&h, k.b + 8, 8); return (size_t)(h * 0x9E3779B97F4A7C15ull); } };
     std::unordered_map<Key64, int, Key64Hash> small_map;
@@ -597,7 +601,7 @@ int init_impl(fabgpu_ctx* ctx, const int* device_ids, int n_dev, size_t max_batc
         const char* sth = getenv("FABGPU_SMALL_THREADS");
         if (sth) { const int v = atoi(sth); if (v == 64 || v == 128 || v == 256 || v == 512) ctx->small_threads_env = v; }
         const char* smu = getenv("FABGPU_SMALL_MIN_USES");
-        ctx->small_min_uses = smu ? atoi(smu) : 4;
+        ctx->small_min_uses = smu ? atoi(smu) : 32;
         if (ctx->small_slots == 0) ctx->small_min_uses = -1;
         const char* mu = getenv("FABGPU_KEY_MIN_USES");
         ctx->key_min_uses = mu ? atoi(mu) : 256;           // a table costs about 300 generic verifications to build

@@ -47,7 +47,7 @@ type ecdsaP256Key struct {
 // (or once) do not evict the tables of the busy ones.  Before that, from its smallTableAfterUses-th verification on, it owns a
 // SMALL table (264 KiB, no doublings: more than five times the generic kernel's rate) -- the tier client / creator certificates live in.
 const tableAfterUses = 512
-const smallTableAfterUses = 4
+const smallTableAfterUses = 32 // a small table costs about as much GPU time as 37 generic verifications: rent until then, buy from here on
 
 // fill32 writes v as 32 big-endian bytes (big.Int.FillBytes needs Go 1.15; the reference builds with 1.14).
 func fill32(dst *[32]byte, v *big.Int) {

@@ -111,8 +111,8 @@ int fabgpu_key_slot_capacity(const fabgpu_ctx* ctx);
  * msp/cache/cache.go:38-129).  handles_out[k] <= -2 is the key's small HANDLE (-2 - ((generation << 20) | slot)), -1 = no slot could
  * be had; every entry point that takes key handles accepts both kinds.  A key that is not a curve point still gets a handle: its
  * signatures are reported off-curve, exactly as by the generic kernel.  The build is enqueued, not waited for; consumers are ordered
- * behind it on the device.  fabgpu_bccsp_verify_batch* give a key a small table by themselves once FABGPU_SMALL_MIN_USES (default 4)
- * of its signatures have been seen without a window table; fabgpu_msp_configure uses small tables when the MSP holds more identities
+ * behind it on the device.  fabgpu_bccsp_verify_batch* give a key a small table by themselves once FABGPU_SMALL_MIN_USES (default 32: the
+ * point where the key has cost as much on the generic kernel as its table does) of its signatures have been seen without a window table; fabgpu_msp_configure uses small tables when the MSP holds more identities
  * than window-table slots.  Capacity: env FABGPU_SMALL_SLOTS (default 16 384 = 4.4 GB per device; 0 turns the tier off); least recently
  * used tables are recycled in bulk (stale handles are detected like the big ones). */
 int fabgpu_keys_register_small(fabgpu_ctx* ctx, const uint8_t* keys_xy, int K, int32_t* handles_out);

@@ -134,7 +134,7 @@ def test_aggregator_protocol_many_threads(csp):
         assert g[0] == e[0] and (g[1] is None) == e[1], (i, g, e)
     nb = csp.batches - batches0
     assert 1 <= nb < len(reqs) / 4, "requests were not aggregated into batches (%d batches)" % nb
-    # every key was verified hundreds of times: from its 4th verification on it owns a small table (gpu.go: smallTableAfterUses)
+    # every key was verified hundreds of times: from its 32nd verification on it owns a small table (gpu.go: smallTableAfterUses)
     assert csp.ctx.key_table_stats()["small"] >= 5
     # same traffic with key-table handles: registered keys take the key-table kernel, the rest the generic one
     w_keys = np.stack([np.frombuffer(k.xy, np.uint8) for k, _, _ in reqs[:3000:500]])

@@ -104,7 +104,11 @@ def test_edge_vectors_and_off_curve_keys_through_small_tables():
 
 
 def test_a_key_earns_its_small_table_after_min_uses_signatures():
-    c = pkg().binding.Context(max_batch=4096)                      # defaults: 4 signatures seen, 256 in one call for a window table
+    os.environ["FABGPU_SMALL_MIN_USES"] = "4"
+    try:
+        c = pkg().binding.Context(max_batch=4096)                  # 4 signatures seen earn a small table (default 32), 256 in one call a window table
+    finally:
+        del os.environ["FABGPU_SMALL_MIN_USES"]
     w = workload.Workload(600, 300, seed=157)                      # two signatures per key and call
     w.tamper_r(0.1)
     exp = fast.verify_batch(w.keys_xy, w.key_idx, w.digest, w.dig_off(), w.sigs, w.sig_off, nthreads=8)
@@ -182,8 +186,12 @@ def test_config5_shape_through_small_tables_full_size():
     picked = w.tamper_r(0.05)
     exp = fast.verify_batch(w.keys_xy, w.key_idx, w.digest, w.dig_off(), w.sigs, w.sig_off, nthreads=os.cpu_count())
     assert int((exp != o.VALID).sum()) == len(picked) and 12000 < len(picked) < 14500
-    c = pkg().binding.Context(max_batch=n)
-    st = c.bccsp_verify_batch(w.keys_xy, w.key_idx, w.digest, w.dig_off(), w.sigs, w.sig_off)     # 32 signatures per key: small tables at first sight
+    os.environ["FABGPU_SMALL_MIN_USES"] = "1"
+    try:
+        c = pkg().binding.Context(max_batch=n)
+    finally:
+        del os.environ["FABGPU_SMALL_MIN_USES"]
+    st = c.bccsp_verify_batch(w.keys_xy, w.key_idx, w.digest, w.dig_off(), w.sigs, w.sig_off)     # every key earns its small table at first sight
     assert (st == exp).all()
     stats = c.key_table_stats()
     assert stats["small"] == 8192 and stats["big"] == 0
