@@ -52,8 +52,8 @@ def workload_string(B):
     """config.workload, identical for both arms (the driver compares the two strings)."""
     return "configs[1]: %d-signature batch per step and GPU, %d keys, SHA-256 digests of 1 KiB messages, low-S DER signatures" % (B, KEYS)
 
-NCU_DRAM_BYTES_PER_LAUNCH_64K = 231995648 + 6491392   # ecdsa_verify_cached_kernel, profiles/r1_final_cached_ncu_summary.txt (dram read + write)
-NCU_FMAHEAVY_BUSY = 0.6222              # sm__pipe_fmaheavy_cycles_active, % of elapsed, same capture: the binding unit of that kernel
+NCU_DRAM_BYTES_PER_LAUNCH_64K = 228455168 + 6074880   # ecdsa_verify_cached_kernel, profiles/r2_final_cached_ncu_summary.txt (dram read + write)
+NCU_FMAHEAVY_BUSY = 0.6286              # sm__pipe_fmaheavy_cycles_active, % of elapsed, same capture: the binding unit of that kernel
 
 
 def _peaks():
@@ -597,7 +597,7 @@ def run_gpu(args):
                            "what": "fabgpu_keys_register builds a %d-bit window table (%.1f MiB) per public key -- what KeyImport does once per identity" % (wq, ((256 + wq - 1) // wq) * ((1 << wq) - 1) * 64 / 2**20)},
             "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
                          "traffic": (NCU_DRAM_BYTES_PER_LAUNCH_64K if B == 65536 else None),
-                         "traffic_note": "dram read+write of one launch at batch 65536 from profiles/r1_final_cached_ncu_summary.txt; it exceeds the "
+                         "traffic_note": "dram read+write of one launch at batch 65536 from profiles/r2_final_cached_ncu_summary.txt; it exceeds the "
                                          "algorithmic 10.5 MB because the kernel gathers %d table points (64 B each) per signature from HBM-resident "
                                          "window tables (%.1f GB for G, %.0f MiB per key) by design -- that is what replaces 255 doublings" % (
                                              n_gather, ((256 + wg - 1) // wg) * ((1 << wg) - 1) * 64 / 1e9, ((256 + wq - 1) // wq) * ((1 << wq) - 1) * 64 / 2**20),
@@ -608,7 +608,7 @@ def run_gpu(args):
                              "macs_per_verify": macs_cached,
                              "binding_unit": {"name": "fmaheavy pipe (IMAD / IMAD.WIDE)", "busy_frac_of_elapsed_ncu": NCU_FMAHEAVY_BUSY,
                                               "note": "the multiplier's carry-chained wide MAC issues at 31 /clk/SM, half the plain IMAD.WIDE rate "
-                                                      "(profiles/microbench/int_pipe_b200.txt); averaged over all 148 SMs the pipe is 62 % busy over the launch "
+                                                      "(profiles/microbench/int_pipe_b200.txt); averaged over all 148 SMs the pipe is 63 % busy over the launch "
                                                       "(72 % on the 128 SMs the 128 CTAs of 512 threads occupy), ALU pipe 45 % (52 %)"},
                              "peak_source": "model: 148 SM x 64 IMAD/clk x %d MHz" % int(sm_max),
                              "generic_kernel": {"achieved": B * ALG_MACS_PER_VERIFY / gen_launch_s / 1e12,

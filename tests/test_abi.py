@@ -45,3 +45,15 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h", ".go")):
                 src = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "oracle" not in src.lower() and "tools.workload" not in src, (dirpath, f)
+
+
+def test_small_table_constants_and_handle_codes():
+    """No compute: the build constants of the small key tables are self-consistent (windows cover the 257 bits a signed recoding of a
+    256-bit scalar needs) and the binding turns small handles (-2 - (generation << 20 | slot)) into the raw device codes (-2 - slot)."""
+    import numpy as np
+    b = pkg().binding
+    wb, nw, nbytes = b.Context.small_table_info()
+    assert 4 <= wb <= 12 and nw * wb >= 257 and (nw - 1) * wb < 257
+    assert nbytes == nw * (1 << (wb - 1)) * 64
+    handles = np.array([-2, -3, -2 - ((5 << 20) | 7), -2 - ((1023 << 20) | 0xFFFFF), -1, 17], np.int32)
+    assert b.Context.small_raw_codes(handles).tolist() == [-2, -3, -9, -2 - 0xFFFFF, -1, -1]
