@@ -172,7 +172,9 @@ struct fabgpu_ctx {
     std::vector<uint32_t> small_gen;
     std::vector<int> small_free;
     unsigned long long small_built = 0, small_recycled = 0;     // fabgpu_key_table_stats
-    std::unordered_map<Key64, uint32_t, Key64Hash> seen_uses;   // keys without any table: signatures seen so far (bounded, see resolve_key_tables)
+    // Keys without any table: signatures seen so far.  Buckets of four (tag, count) entries indexed by a hash of the key bytes -- no allocation
+    // on the batch path; a full bucket gives up its least used entry, which only delays that key's table (resolve_key_tables).
+    std::vector<uint64_t> seen_tag; std::vector<uint32_t> seen_cnt;
     // key-table kernel (FABGPU_CACHED_KERNEL): 0 "jac" = Jacobian chain, one signature per thread (ecdsa_verify_cached_kernel) -- the DEFAULT: fastest at
     // every batch size measured on B200 (profiles/r2_kernel_variants.txt); 1 "ba" = batch-affine with CTA-shared inversions, 3 "ba2" = batch-affine, two
     // signatures per thread, 2 / 4 "l2" / "l4" = the Jacobian chain split over 2 / 4 lanes.  The alternatives stay selectable: they are the measurements.
@@ -598,6 +600,7 @@ int init_impl(fabgpu_ctx* ctx, const int* device_ids, int n_dev, size_t max_batc
         ctx->small_gen.assign(ctx->small_slots, 0u);
         ctx->small_free.clear();
         for (int sl = ctx->small_slots - 1; sl >= 0; sl--) ctx->small_free.push_back(sl);
+        ctx->seen_tag.assign((size_t)1 << 18, 0ull); ctx->seen_cnt.assign((size_t)1 << 18, 0u);
         const char* sth = getenv("FABGPU_SMALL_THREADS");
         if (sth) { const int v = atoi(sth); if (v == 64 || v == 128 || v == 256 || v == 512) ctx->small_threads_env = v; }
         const char* smu = getenv("FABGPU_SMALL_MIN_USES");
@@ -1308,10 +1311,12 @@ static int resolve_key_tables(fabgpu_ctx* ctx, const uint8_t* keys_xy, int K, co
         std::lock_guard<std::mutex> lk(ctx->mu);
         fabgpu_ctx::Key64 kk;
         bool touched = false;
+        static thread_local std::string kbuf(64, '\0');          // lookup key without a heap allocation per key
         for (int k = 0; k < K; k++) {
             if (!uses[k]) continue;
             if (!ctx->key_map.empty() || uses[k] >= (uint32_t)ctx->key_min_uses) {
-                auto it = ctx->key_map.find(std::string((const char*)keys_xy + 64 * (size_t)k, 64));
+                memcpy(&kbuf[0], keys_xy + 64 * (size_t)k, 64);
+                auto it = ctx->key_map.find(kbuf);
                 if (it != ctx->key_map.end()) {
                     if (!touched) { ctx->tick++; touched = true; }
                     slot_of[k] = make_handle(ctx, it->second); ctx->slot_tick[it->second] = ctx->tick; continue;
@@ -1327,11 +1332,23 @@ static int resolve_key_tables(fabgpu_ctx* ctx, const uint8_t* keys_xy, int K, co
             }
             uint32_t total = uses[k];
             if (total < (uint32_t)ctx->small_min_uses) {
-                if (ctx->seen_uses.size() > (1u << 20)) ctx->seen_uses.clear();     // bounded memory: forgetting only delays a table
-                uint32_t& c = ctx->seen_uses[kk];
-                c += uses[k]; total = c;
+                uint64_t h0, h1;
+                memcpy(&h0, kk.b + 8, 8); memcpy(&h1, kk.b + 40, 8);
+                const uint64_t tag = ((h0 * 0x9E3779B97F4A7C15ull) ^ (h1 * 0xC2B2AE3D27D4EB4Full)) | 1ull;
+                const size_t b0 = (size_t)(tag >> 20) & (ctx->seen_tag.size() - 1) & ~(size_t)3;   // bucket of four entries
+                size_t at = b0, weakest = b0;
+                bool found = false;
+                for (size_t q = b0; q < b0 + 4 && !found; q++) {
+                    if (ctx->seen_tag[q] == tag) { at = q; found = true; }
+                    else if (ctx->seen_tag[q] == 0) { if (ctx->seen_tag[weakest] != 0) weakest = q; }
+                    else if (ctx->seen_tag[weakest] != 0 && ctx->seen_cnt[q] < ctx->seen_cnt[weakest]) weakest = q;
+                }
+                if (!found) { at = weakest; ctx->seen_tag[at] = tag; ctx->seen_cnt[at] = 0; }      // an empty entry, else the least used one
+                ctx->seen_cnt[at] += uses[k];
+                total = ctx->seen_cnt[at];
+                if (total >= (uint32_t)ctx->small_min_uses) { ctx->seen_tag[at] = 0; ctx->seen_cnt[at] = 0; }
             }
-            if (total >= (uint32_t)ctx->small_min_uses) { want_small.push_back(k); ctx->seen_uses.erase(kk); }
+            if (total >= (uint32_t)ctx->small_min_uses) want_small.push_back(k);
         }
     }
     if (!want_big.empty() && (int)want_big.size() <= ctx->key_slots) {
