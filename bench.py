@@ -211,8 +211,11 @@ def run_gpu(args):
     os.environ.setdefault("FABGPU_GATE_THREADS", str(max(4, min(32, (os.cpu_count() or 8) // (2 * world)))))
     ctx = pkg.binding.Context(max_batch=B, device_ids=[local])
 
-    # ---- device-resident leg: ROT distinct input buffers, L2 flushed between steps ---------------------------
-    ROT = 3
+    # ---- device-resident leg: ROT distinct input buffers (ROT x 10.5 MB = 168 MB > the 126 MB L2), steps back to back ----------------
+    # The kernel's other input -- the window tables, 3.2 GB + 64 x 64 MiB, gathered at random -- is far larger than the L2 by itself.  The
+    # same loop with a 256 MiB fill between steps (round 1's method) is timed beside it (config.value_l2_fill_between_steps): the fill
+    # leaves the L2 full of DIRTY lines whose write-back competes with the next launch's table gathers, which no real batch stream does.
+    ROT = 16
     host = [w.qx(), w.qy(), w.digest, w.r, w.s]
     bufs = []
     for k in range(ROT):
@@ -271,7 +274,6 @@ def run_gpu(args):
     sync_all()
     wall0 = time.perf_counter()
     for k in range(args.steps):
-        flush.fill_(k & 0xFF)                                 # L2 flush (256 MiB > 126 MB L2), outside the event pair
         ev[k][0].record(stream)
         full = step(k)
         ev[k][1].record(stream)
@@ -279,6 +281,17 @@ def run_gpu(args):
     wall = time.perf_counter() - wall0
     launches = ctx.launch_count() - launches0
     dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    assert bool((full == -1).all())
+    # the same loop with the L2 overwritten between steps (256 MiB fill, outside the event pairs)
+    fev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    sync_all()
+    for k in range(args.steps):
+        flush.fill_(k & 0xFF)
+        fev[k][0].record(stream)
+        full = step(k)
+        fev[k][1].record(stream)
+    sync_all()
+    fill_ms = sum(a.elapsed_time(b) for a, b in fev)
     assert bool((full == -1).all())
     # The same kernel with several batches in flight (one stream per batch, inputs resident, no flush): a 64k batch is 512 CTAs
     # on 592 resident CTA slots, so a launch on its own leaves part of the machine idle in its tail; concurrent streams fill it.
@@ -537,10 +550,10 @@ def run_gpu(args):
 
 
     # ---- max over ranks ---------------------------------------------------------------------------------------
-    times = torch.tensor([dev_ms, e2e_s * 1e3, wall * 1e3, gen_ms, key_register_ms, e2e_sync_s * 1e3, conc_ms, e2e_pageable_s * 1e3, nccl_ms], dtype=torch.float64, device=dev)
+    times = torch.tensor([dev_ms, e2e_s * 1e3, wall * 1e3, gen_ms, key_register_ms, e2e_sync_s * 1e3, conc_ms, e2e_pageable_s * 1e3, nccl_ms, fill_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms, wall_ms, gen_ms, key_register_ms, e2e_sync_ms, conc_ms, e2e_pageable_ms, nccl_ms = [float(x) for x in times.tolist()]
+    dev_ms, e2e_ms, wall_ms, gen_ms, key_register_ms, e2e_sync_ms, conc_ms, e2e_pageable_ms, nccl_ms, fill_ms = [float(x) for x in times.tolist()]
 
     if rank == 0:
         hbm_peak, peak_src, sm_max = _peaks()
@@ -566,8 +579,13 @@ def run_gpu(args):
                        "parallelism": ("batch split x%d + bitmask exchanged over peer memory (P2P stores from the verify kernel's epilogue, fabgpu_peer_mask_*)" % world) if peer is not None
                                       else ("batch split x%d + NCCL all-gather of the bitmask" % world),
                        "value_with_nccl_allgather": (n_total * args.steps / (nccl_ms * 1e-3)) if nccl_ms else None, "collective_note": peer_note,
-                       "timing": "per-step CUDA events on the launch stream, summed; L2 flushed (256 MiB fill) between steps; %d rotating input buffers" % ROT,
-                       "wall_ms_incl_flush": wall_ms, "rank0_numa_pinning": numa},
+                       "timing": "per-step CUDA events on the launch stream, summed; steps back to back over %d rotating input buffers (%.0f MB > the 126 MB L2); "
+                                 "the window tables the kernel gathers from (%.1f GB) are far larger than the L2 by themselves" % (
+                                     ROT, ROT * B * 160 / 1e6, (((256 + wg - 1) // wg) * ((1 << wg) - 1) * 64 + KEYS * ((256 + wq - 1) // wq) * ((1 << wq) - 1) * 64) / 1e9),
+                       "value_l2_fill_between_steps": n_total * args.steps / (fill_ms * 1e-3),
+                       "value_l2_fill_note": "the same loop with a 256 MiB fill between steps (round 1's method): the fill leaves the L2 full of dirty lines whose write-back "
+                                             "competes with the next launch's table gathers",
+                       "wall_ms": wall_ms, "rank0_numa_pinning": numa},
             "e2e": {"value": n_total * e2e_steps / (e2e_ms * 1e-3), "unit": "verifies/s", "h2d_bytes_per_step": e2e_h2d * world, "d2h_bytes_per_step": e2e_d2h * world,
                     "api": "fabgpu_bccsp_verify_batch_inplace_async + _wait over the context's %d slots, that many batches in flight (raw DER signatures + digests + keys in the library's PINNED host buffers -> status bytes in host memory)" % pkg.binding.SLOTS,
                     "pageable_value": n_total * e2e_steps / (e2e_pageable_ms * 1e-3),
