@@ -235,17 +235,21 @@ def run_gpu(args):
     assert (slots >= 0).all()
     kslots = [torch.from_numpy(np.ascontiguousarray(slots[w.key_idx][np.roll(np.arange(B), 997 * k)])).to(dev) for k in range(ROT)]
 
-    # N > 1: the bitmask is reassembled by the library's own exchange over peer memory (P2P stores from the verify kernel's epilogue,
-    # fabgpu_verify_p256_device_keyed_allgather); the NCCL all-gather stays available (--collective nccl) and is timed beside it.
+    # N > 1: two ways to reassemble the bitmask, both timed with the same loop: the NCCL all-gather north_star names (the default `value`:
+    # measured faster at every N on this pool's boxes, profiles/r2_scale.txt) and the library's own exchange over peer memory (P2P stores
+    # from the verify kernel's epilogue, fabgpu_verify_p256_device_keyed_allgather; --collective p2p makes it the `value`).
     peer = None
     peer_note = None
-    if world > 1 and args.collective == "p2p":
+    main_nccl = args.collective == "nccl"
+    if world > 1:
         peer = sharding.PeerMaskExchange(ctx, n_total, world, rank, dev)
         if not peer.ok:                                            # no peer access on this box: every rank falls back to the NCCL all-gather
             peer_note, peer = "peer-memory exchange unavailable (%s): NCCL all-gather used" % (peer.error or "another rank failed"), None
 
-    def step(k, generic=False, nccl=False):
+    def step(k, generic=False, nccl=None):
         t = bufs[k % ROT]
+        if nccl is None:
+            nccl = main_nccl
         if peer is not None and not generic and not nccl:
             return peer.verify(True, kslots[k % ROT].data_ptr(), 0, 0, t[2].data_ptr(), t[3].data_ptr(), t[4].data_ptr(), B, stream.cuda_stream)
         if generic:
@@ -318,17 +322,16 @@ def run_gpu(args):
     sync_all()
     conc_ms = max(c0.elapsed_time(e) for e in cends)
     assert all(bool((m == -1).all()) for m in cmasks)
-    # the same timed loop with the NCCL all-gather instead of the peer-memory exchange (comparison; N > 1 only)
+    # the same timed loop with the OTHER way of reassembling the bitmask (comparison; N > 1 only)
     nccl_ms = 0.0
     if peer is not None:
         for k in range(args.warmup):
-            full = step(k, nccl=True)
+            full = step(k, nccl=not main_nccl)
         nev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
         sync_all()
         for k in range(args.steps):
-            flush.fill_(k & 0xFF)
             nev[k][0].record(stream)
-            full = step(k, nccl=True)
+            full = step(k, nccl=not main_nccl)
             nev[k][1].record(stream)
         sync_all()
         nccl_ms = sum(a.elapsed_time(b_) for a, b_ in nev)
@@ -576,9 +579,12 @@ def run_gpu(args):
             "dtype": "u32 limbs (256-bit modular integer)", "data": "synthetic",
             "config": {"workload": workload_string(B),
                        "batch_per_gpu": B, "global_batch": n_total,
-                       "parallelism": ("batch split x%d + bitmask exchanged over peer memory (P2P stores from the verify kernel's epilogue, fabgpu_peer_mask_*)" % world) if peer is not None
-                                      else ("batch split x%d + NCCL all-gather of the bitmask" % world),
-                       "value_with_nccl_allgather": (n_total * args.steps / (nccl_ms * 1e-3)) if nccl_ms else None, "collective_note": peer_note,
+                       "parallelism": ("batch split x%d + bitmask exchanged over peer memory (P2P stores from the verify kernel's epilogue, fabgpu_peer_mask_*)" % world)
+                                      if (peer is not None and not main_nccl) else ("batch split x%d + NCCL all-gather of the bitmask" % world),
+                       "collective": "p2p" if (peer is not None and not main_nccl) else "nccl",
+                       "value_with_nccl_allgather": (n_total * args.steps / (nccl_ms * 1e-3)) if (nccl_ms and not main_nccl) else None,
+                       "value_with_peer_memory_exchange": (n_total * args.steps / (nccl_ms * 1e-3)) if (nccl_ms and main_nccl) else None,
+                       "collective_note": peer_note,
                        "timing": "per-step CUDA events on the launch stream, summed; steps back to back over %d rotating input buffers (%.0f MB > the 126 MB L2); "
                                  "the window tables the kernel gathers from (%.1f GB) are far larger than the L2 by themselves" % (
                                      ROT, ROT * B * 160 / 1e6, (((256 + wg - 1) // wg) * ((1 << wg) - 1) * 64 + KEYS * ((256 + wq - 1) // wq) * ((1 << wq) - 1) * 64) / 1e9),
@@ -658,7 +664,7 @@ def main():
     ap.add_argument("--block-txs", type=int, default=10000, help="transactions in the block-replay leg (configs[2])")
     ap.add_argument("--no-block", action="store_true", help="skip the block-replay leg")
     ap.add_argument("--no-parity", action="store_true", help="skip the (untimed) named-shape parity leg")
-    ap.add_argument("--collective", default="p2p", choices=["p2p", "nccl"], help="N > 1: how the bitmask is reassembled in the timed loop")
+    ap.add_argument("--collective", default="nccl", choices=["p2p", "nccl"], help="N > 1: how the bitmask is reassembled in the timed loop (the other way is timed beside it)")
     args = ap.parse_args()
     # The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version line on the first
     # collective), so everything but the result goes to stderr: fd 1 is pointed at fd 2 for the duration of the run and the
