@@ -1722,6 +1722,24 @@ static int upload_msp(fabgpu_ctx* ctx, const uint8_t* id_blob, const uint32_t* i
 }
 
 
+// An MSP with more identities than window-table slots: every identity gets a small table; the ones whose key ALREADY owns a window table --
+// the integrator registered the few busy ones (the endorsing peers) with fabgpu_keys_register beforehand -- keep using that.
+static int msp_small_tier(fabgpu_ctx* ctx, const uint8_t* keys_xy, int n_ids)
+{
+    int rc = small_register(ctx, keys_xy, n_ids, ctx->identity_slot.data());
+    if (rc) return rc;
+    std::shared_lock<std::shared_mutex> rl(ctx->tab_mu);
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (ctx->key_map.empty()) return FABGPU_OK;
+    std::string kbuf(64, '\0');
+    for (int i = 0; i < n_ids; i++) {
+        memcpy(&kbuf[0], keys_xy + 64 * (size_t)i, 64);
+        auto it = ctx->key_map.find(kbuf);
+        if (it != ctx->key_map.end()) ctx->identity_slot[i] = make_handle(ctx, it->second);
+    }
+    return FABGPU_OK;
+}
+
 int fabgpu_msp_configure(fabgpu_ctx* ctx, const uint8_t* id_blob, const uint32_t* id_off, const uint8_t* mspid_blob,
                          const uint32_t* mspid_off, const uint8_t* keys_xy, const uint8_t* valid, int n_ids,
                          const int32_t* policy_nodes, int n_nodes, const uint8_t* principal_blob, const uint32_t* principal_off,
@@ -1757,7 +1775,7 @@ int fabgpu_msp_configure(fabgpu_ctx* ctx, const uint8_t* id_blob, const uint32_t
         int rc = fabgpu_keys_register(ctx, keys_xy, n_ids, ctx->identity_slot.data());
         if (rc) return rc;
     } else if (n_ids > 0 && n_ids <= ctx->small_slots && ctx->small_min_uses >= 0) {
-        int rc = small_register(ctx, keys_xy, n_ids, ctx->identity_slot.data());
+        int rc = msp_small_tier(ctx, keys_xy, n_ids);
         if (rc) return rc;
     }
     return upload_msp(ctx, id_blob, id_off, keys_xy, valid, n_ids, policy_nodes, n_nodes);
@@ -1852,7 +1870,7 @@ static int block_submit(fabgpu_ctx* ctx, int slot, const uint8_t* block, size_t 
             const int n_ids = (int)ctx->identity_slot.size();
             const bool big = n_ids <= ctx->key_slots;
             int rc = big ? fabgpu_keys_register(ctx, ctx->msp.keys_xy.data(), n_ids, ctx->identity_slot.data())     // exclusive; drains every stream first
-                         : small_register(ctx, ctx->msp.keys_xy.data(), n_ids, ctx->identity_slot.data());
+                         : msp_small_tier(ctx, ctx->msp.keys_xy.data(), n_ids);
             if (rc) return rc;
             rl.lock();
             std::vector<int32_t> raw(n_ids, -1);

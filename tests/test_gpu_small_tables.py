@@ -174,6 +174,16 @@ def test_block_prepass_with_more_identities_than_window_tables():
     other = workload.Workload(128, 64, seed=173)
     assert (c.keys_register_small(other.keys_xy) <= -2).all()      # recycles the identities' tables
     assert c.validate_block(blk).tolist() == exp.tolist()
+    # the busy identities (the four endorsing peers) registered for window tables BEFORE the MSP is configured keep them; the rest go small
+    peer_keys = np.stack([np.frombuffer(p.xy, np.uint8) for p in net.peers])
+    assert (c.keys_register(peer_keys) >= 0).all()
+    c.msp_configure(ids, net.policy_n_of(3), net.principals, net.channel)
+    st = c.key_table_stats()
+    assert st["big"] == 4
+    assert c.validate_block(blk).tolist() == exp.tolist()
+    assert c.validate_envelopes(binfo["env_blob"], binfo["env_off"]).tolist() == exp.tolist()
+    assert (c.keys_register(other.keys_xy[:4]) >= 0).all()         # evicts the peers' window tables: their identities fall back to small ones
+    assert c.validate_block(blk).tolist() == exp.tolist()
     c.close()
 
 
