@@ -1774,8 +1774,8 @@ int fabgpu_msp_configure(fabgpu_ctx* ctx, const uint8_t* id_blob, const uint32_t
     if (n_ids > 0 && n_ids <= ctx->key_slots) {
         int rc = fabgpu_keys_register(ctx, keys_xy, n_ids, ctx->identity_slot.data());
         if (rc) return rc;
-    } else if (n_ids > 0 && n_ids <= ctx->small_slots && ctx->small_min_uses >= 0) {
-        int rc = msp_small_tier(ctx, keys_xy, n_ids);
+    } else if (n_ids > 0) {
+        int rc = msp_small_tier(ctx, keys_xy, n_ids);             // also with the small tier off or too small: pre-registered window tables are still picked up
         if (rc) return rc;
     }
     return upload_msp(ctx, id_blob, id_off, keys_xy, valid, n_ids, policy_nodes, n_nodes);
