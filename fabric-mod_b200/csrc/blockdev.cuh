@@ -52,11 +52,20 @@ struct MspDev {
     int32_t n_ids;
 };
 
+// Hash of a serialized identity from 16 + 32 + 32 + 24 sampled bytes.  A SerializedIdentity is the MSP id followed by a PEM certificate: every
+// identity of an MSP starts with the same bytes and ends with the same "-----END CERTIFICATE-----" footer, so head and tail alone (round 1) put all
+// of an MSP's identities into ONE probe chain -- harmless with a dozen identities, 1.7 ms per block with 2 000 client certificates
+// (profiles/r2_bench_n1_many_clients.json).  The two inner windows fall into the base64 body: the middle (subject / public key) and the end of
+// the signature just before the footer.
 BD_HD uint64_t sample_hash(const uint8_t* p, uint32_t n)
 {
     uint64_t h = 1469598103934665603ull ^ n;
     const uint32_t head = n < 16 ? n : 16, tail = n < 24 ? n : 24;
     for (uint32_t i = 0; i < head; i++) h = (h ^ p[i]) * 1099511628211ull;
+    if (n >= 160) {
+        for (uint32_t i = n / 2 - 16; i < n / 2 + 16; i++) h = (h ^ p[i]) * 1099511628211ull;
+        for (uint32_t i = n - 72; i < n - 40; i++) h = (h ^ p[i]) * 1099511628211ull;
+    }
     for (uint32_t i = n - tail; i < n; i++) h = (h ^ p[i]) * 1099511628211ull;
     return h ? h : 1;
 }
