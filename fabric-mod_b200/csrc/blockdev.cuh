@@ -54,9 +54,9 @@ struct MspDev {
 
 // Hash of a serialized identity from 16 + 32 + 32 + 24 sampled bytes.  A SerializedIdentity is the MSP id followed by a PEM certificate: every
 // identity of an MSP starts with the same bytes and ends with the same "-----END CERTIFICATE-----" footer, so head and tail alone (round 1) put all
-// of an MSP's identities into ONE probe chain -- harmless with a dozen identities, 1.7 ms per block with 2 000 client certificates
-// (profiles/r2_bench_n1_many_clients.json).  The two inner windows fall into the base64 body: the middle (subject / public key) and the end of
-// the signature just before the footer.
+// of an MSP's identities into ONE probe chain -- harmless with a dozen identities, 1.7 ms per block with 2 000 client certificates (the creator
+// pass of block_resolve_kernel: 1 696 us against 46 us, profiles/r2_block_many_clients_launches.csv).  The two inner windows fall into the base64
+// body: the middle (subject / public key) and the end of the signature just before the footer.
 BD_HD uint64_t sample_hash(const uint8_t* p, uint32_t n)
 {
     uint64_t h = 1469598103934665603ull ^ n;

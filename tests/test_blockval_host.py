@@ -154,3 +154,33 @@ def test_identity_groups_follow_the_certificate_not_the_bytes():
              (pb.serialized_identity("Org1MSP", b"not a pem"), "Org1MSP", net.peers[0].xy, True)]
     g2 = pkg().binding.identity_groups(ids + other)
     assert g2[len(ids)] not in g2[: len(ids)].tolist() and g2[len(ids) + 1] == g2[len(ids) + 2] != g2[len(ids)]
+
+
+def test_device_logic_with_hundreds_of_client_identities():
+    """An MSP of 300 client certificates (plus peers): the identity lookup (sample_hash + msp_find of blockdev.cuh) must keep finding every
+    identity when the table is large and the certificates share header, MSP id and PEM footer -- flags equal the oracle's on a block with
+    every fault class, and the lookup's hash puts (almost) every identity into its own bucket."""
+    net = blockgen.Network(n_orgs=4, n_clients=300, seed=0xC11E)
+    n = 3 * len(blockgen.FAULTS) + 40
+    faults = blockutil.fault_map(n)
+    blk, info = blockgen.build_block(net, n, 3, faults, seed=29, nthreads=2)
+    ids = blockutil.identities_of(net)
+    assert len(ids) > 300
+    exp = ob.validate_block(blk, ids, net.channel, net.policy_n_of(3), net.principals, known=_known(ids))
+    got = blockutil.device_logic_flags(info["env_blob"], info["env_off"], ids, net.channel, net.policy_n_of(3), net.principals)
+    assert got.tolist() == exp.tolist()
+    assert int((exp == ob.VALID).sum()) > 40
+    # the same hash, restated: FNV-style over 16 head + 32 middle + 32 pre-footer + 24 tail bytes
+    M = (1 << 64) - 1
+
+    def h(p):
+        x = 1469598103934665603 ^ len(p)
+        idx = list(range(min(16, len(p))))
+        if len(p) >= 160:
+            idx += list(range(len(p) // 2 - 16, len(p) // 2 + 16)) + list(range(len(p) - 72, len(p) - 40))
+        idx += list(range(len(p) - min(24, len(p)), len(p)))
+        for i in idx:
+            x = ((x ^ p[i]) * 1099511628211) & M
+        return x or 1
+    hashes = {h(i[0]) for i in ids}
+    assert len(hashes) == len(ids)                      # head + tail alone gave one value per MSP id
