@@ -103,3 +103,38 @@ def test_small_table_signed_recoding_on_crafted_scalars():
         exp = p256.scalar_mult(k % p256.N, Q)
         got = (int.from_bytes(bytes(ox), "big"), int.from_bytes(bytes(oy), "big"))
         assert got == ((0, 0) if exp is p256.INF else exp), hex(k)
+
+
+@pytest.mark.parametrize("ws", [5, 6, 7])
+def test_small_tables_at_other_window_widths(ws):
+    """The small-table code is width-generic (FAB_WS; the product builds 8): the host build at 5, 6 and 7 bits multiplies crafted scalars
+    correctly (signed recoding with the carry absorbed by the last window) and verifies a tampered batch like the generic path."""
+    import ctypes
+    import os
+    import subprocess
+    from oracle import p256
+    from util import ROOT
+    d = os.path.join(ROOT, "tests", "host_sim")
+    so = os.path.join(d, "libhostsim_ws%d.so" % ws)
+    src = os.path.join(d, "hostsim.cpp")
+    hdr = os.path.join(ROOT, "fabric-mod_b200", "csrc", "ecdsa_verify.cuh")
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-DFAB_WG=8", "-DFAB_WQ=8", "-DFAB_Q_TWO_LEVEL=1", "-DFAB_WS=%d" % ws, "-shared", "-fPIC", "-o", so, src])
+    hs = ctypes.CDLL(so)
+    Q = p256.scalar_mult(0x7654321, (p256.GX, p256.GY))
+    half, full = 1 << (ws - 1), 1 << ws
+    nw = (257 + ws - 1) // ws
+    pat = lambda digit: sum(digit << (ws * j) for j in range(nw)) & ((1 << 256) - 1)      # the same digit in every window
+    ks = [1, half, half + 1, full - 1, full, pat(half), pat(half + 1), pat(half - 1), pat(full - 1), (1 << 256) - 1, p256.N - 1, p256.N + 1, 1 << 255]
+    for k in ks:
+        ox = (ctypes.c_uint8 * 32)(); oy = (ctypes.c_uint8 * 32)()
+        hs.hostsim_small_mul(k.to_bytes(32, "big"), Q[0].to_bytes(32, "big"), Q[1].to_bytes(32, "big"), ox, oy)
+        exp = p256.scalar_mult(k % p256.N, Q)
+        assert (int.from_bytes(bytes(ox), "big"), int.from_bytes(bytes(oy), "big")) == ((0, 0) if exp is p256.INF else exp), (ws, hex(k))
+    w = workload.Workload(256, 4, seed=70 + ws, nthreads=2)
+    w.tamper_r(frac=0.25)
+    exp = fast.verify_batch(w.keys_xy, w.key_idx, w.digest, w.dig_off(), w.sigs, w.sig_off, nthreads=2)
+    arrs = [np.ascontiguousarray(a, dtype=np.uint8).reshape(-1, 32) for a in (w.qx(), w.qy(), w.digest, w.r, w.s)]
+    out = np.zeros(w.n, np.uint8)
+    hs.hostsim_verify_batch_small(*[a.ctypes.data_as(ctypes.c_void_p) for a in arrs], ctypes.c_int(w.n), out.ctypes.data_as(ctypes.c_void_p))
+    assert ((out == V_VALID) == (exp == o.VALID)).all() and 30 < int((exp != o.VALID).sum()) < 100
